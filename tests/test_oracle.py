@@ -1,0 +1,213 @@
+"""CPU tests (-m "not gpu"): pin the oracles.
+
+ * oracle/_ref/liboracle_ref.so  = the reference's own headers compiled through oracle/ref_shim.cpp
+ * oracle/liboracle_port.so      = oracle/igab_oracle.c, the plain-C restatement
+are both replayed against every literal the reference's unit tests hold for this path
+(tests/golden/reference_literals.json, see make_reference_literals.py) and against each other on seeded patches.
+Tolerance for literals: the reference's own, Dune::FloatCmp::eq default = 8 eps relative, widened to 64 eps because the
+literals are printed with 16 digits and the reference's last bits are compiler-dependent.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import portbind as PT
+import refbind as RF
+import patches_for_tests as PFT
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_literals.json")))
+EPS = 64 * np.finfo(float).eps
+
+needs_ref = pytest.mark.skipif(not RF.available(), reason="oracle/_ref not built")
+IMPLS = [pytest.param("port", id="port"), pytest.param("ref", id="ref", marks=needs_ref)]
+
+
+def mod(name):
+    return PT if name == "port" else RF
+
+
+def make(name, degree, knots, cp, dw):
+    return PT.PortPatch(degree, knots, cp, dw) if name == "port" else RF.RefPatch.create(degree, knots, cp, dw)
+
+
+def close(a, b, tol=EPS):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.all(np.abs(a - b) <= tol * np.maximum(1.0, np.maximum(np.abs(a), np.abs(b)).max()))
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_bspline1d_literals(impl):
+    M = mod(impl)
+    for c in G["bspline1d_values"]:
+        assert close(M.bspline_basis(c["u"], c["knots"], c["p"]), c["N"]), c["cite"]
+    c = G["bspline1d_ders"]
+    assert close(M.bspline_basis(c["u"], c["knots"], c["p"]), c["N"])
+    assert close(M.bspline_ders(c["u"], c["knots"], c["p"], 3), c["dN"])
+    c = G["bspline1d_N0_sweep"]
+    got = [M.bspline_basis(u, c["knots"], c["p"])[0] for u in c["u"]]
+    assert close(got, c["N0"])
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_find_span_semantics(impl):
+    # bsplinealgorithms.hh:24-32: clamps at both ends, upper_bound semantics with repeated interior knots
+    M = mod(impl)
+    U = [0, 0, 0, 0.5, 0.5, 2, 2, 3, 3, 3]
+    assert M.find_span(2, -1.0, U) == 2
+    assert M.find_span(2, 0.0, U) == 2
+    assert M.find_span(2, 0.3, U) == 2
+    assert M.find_span(2, 0.5, U) == 4
+    assert M.find_span(2, 1.0, U) == 4
+    assert M.find_span(2, 2.0, U) == 6
+    assert M.find_span(2, 3.0, U) == len(U) - 2 - 2
+    assert M.find_span(2, 9.0, U) == len(U) - 2 - 2
+    # element path: value = unique knot e, offset = e
+    uq = [0, 0.5, 2, 3]
+    assert [M.find_span(2, uq[e], U, e) for e in range(3)] == [2, 4, 6]
+
+
+def nurbs2d_patch(impl):
+    n = G["nurbs2d"]
+    w = np.ones((3, 7))  # [j][i], proper 7x3 net; only the 3x3 block of the first span is read
+    for i in range(3):
+        for j in range(3):
+            w[j, i] = n["weights_3x3_block"][i][j]
+    cp = np.zeros((21, 3))
+    cp[:, 2] = w.reshape(-1)
+    return make(impl, n["degree"], n["knots"], cp, 2)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_nurbs2d_literals(impl):
+    P = nurbs2d_patch(impl)
+    n = G["nurbs2d"]
+    for v in n["values"]:
+        R = P.nurbs_basis(v["u"])
+        assert close(R, v["R"])
+        assert abs(R.sum() - 1.0) < EPS  # partition of unity, gridtests.cpp:787,804
+    d = P.nurbs_ders([0.0, 0.1], 5)
+    for key, val in n["derivatives_at_0_0.1"].items():
+        a, b = map(int, key.split(","))
+        assert close(d[a + 6 * b], val), key
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_geometry_literals(impl):
+    c = G["geometry_curve"]
+    P = make(impl, c["degree"], c["knots"], c["cp"], c["dimworld"])
+    for u, x in c["global"]:
+        assert close(P.geo_global(u), x)
+    for u, J in c["jacobianTransposed"]:
+        assert close(P.geo_jt(u), J)
+    s = G["geometry_surface"]
+    cp = np.array([[s["cp_table_ij"][i][j] for i in range(3)] for j in range(3)], float).reshape(9, 4)
+    P = make(impl, s["degree"], s["knots"], cp, s["dimworld"])
+    for u, x in s["global"]:
+        assert close(P.geo_global(u), x)
+    for u, J in s["jacobianTransposed"]:
+        assert close(P.geo_jt(u), J)
+    for k, corner in enumerate(s["corners"]):
+        assert close(P.geo_global([(k >> 0) & 1, (k >> 1) & 1]), corner)
+
+
+@needs_ref
+def test_degree_elevate_literal():
+    c = G["degree_elevate_curve"]
+    P = RF.RefPatch.create(c["degree"], c["knots"], c["cp"], c["dimworld"]).degree_elevate(0, c["elevate_by"])
+    assert P.degree == [4]
+    assert np.allclose(P.cp[:, :3], c["expected_cp"], rtol=0, atol=1e-10 * 6)
+    assert np.allclose(P.cp[:, 3], c["expected_w"], rtol=0, atol=1e-10 * 12)
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["plate_hole_p2", "cylinder_p3", "torus_p2", "square_p3", "mixed_deg_3d"])
+def test_port_equals_reference_on_seeded_patches(name):
+    """The restatement against the reference itself, pointwise, all outputs, order 2."""
+    spec = PFT.small_patch(name)
+    Pp = PT.PortPatch(spec["degree"], spec["knots"], spec["cp"], spec["dimworld"])
+    Pr = RF.RefPatch.create(spec["degree"], spec["knots"], spec["cp"], spec["dimworld"])
+    assert Pp.nelem == Pr.nelem
+    assert np.array_equal(Pp.spans(), Pr.spans())  # integers: bit-exact
+    xi1d = [PT.gauss01(p + 1)[0] for p in spec["degree"]]
+    a = Pp.eval_tensor(xi1d, order=2)
+    b = Pr.eval_tensor(xi1d, order=2)
+    for k in ("N", "dN", "d2N", "x", "Jt", "H", "detJ"):
+        scale = max(1.0, np.abs(b[k]).max())
+        assert np.abs(a[k] - b[k]).max() <= 1e-13 * scale, k
+    # corners and corner +- 1e-8, as checkJacobianAndPartialConsistency does (gridtests.cpp:514-576)
+    rng = np.random.default_rng(42)
+    elem = rng.integers(0, Pp.nelem, 64).astype(np.int32)
+    xi = rng.random((64, Pp.dim))
+    xi[:8] = 0.0
+    xi[8:16] = 1.0
+    xi[16:24] = 1e-8
+    xi[24:32] = 1 - 1e-8
+    a = Pp.eval_points(elem, xi, order=2)
+    b = Pr.eval_points(elem, xi, order=2)
+    for k in ("N", "dN", "d2N", "x", "Jt", "H", "detJ"):
+        scale = max(1.0, np.abs(b[k]).max())
+        assert np.abs(a[k] - b[k]).max() <= 1e-13 * scale, k
+    # evaluateJacobian column d == partial(e_d)  (gridtests.cpp:514-576, 1e-14)
+    for d in range(Pp.dim):
+        al = [0] * Pp.dim
+        al[d] = 1
+        for Q, o in ((Pp, a), (Pr, b)):
+            part = Q.partial(elem, xi, al)
+            assert np.abs(part - o["dN"][:, :, d]).max() <= 1e-14 * max(1.0, np.abs(part).max())
+
+
+@needs_ref
+def test_torus_invariants_reference():
+    """gridtests.cpp:338-363: torus area 4 pi^2 r R (1e-4) and Gauss-Bonnet (1e-5) through the oracle."""
+    t = G["torus"]
+    spec = PFT.small_patch("torus_p2", level=2)
+    Pp = PT.PortPatch(spec["degree"], spec["knots"], spec["cp"], 3)
+    x, w = PT.gauss01(3)  # order 2*max(p)=4 -> 3 points (nurbsgridentity.hh:123-133)
+    area = Pp.volume([x, x], [w, w])
+    assert abs(area - 4 * np.pi ** 2 * t["r"] * t["R"]) < t["area_tol"]
+    o = Pp.eval_tensor([x, x], order=2)
+    J, H, det = o["Jt"], o["H"], o["detJ"]
+    nrm = np.cross(J[:, 0], J[:, 1])
+    nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    b00, b11, b01 = (H[:, 0] * nrm).sum(1), (H[:, 1] * nrm).sum(1), (H[:, 2] * nrm).sum(1)
+    g00, g11, g01 = (J[:, 0] ** 2).sum(1), (J[:, 1] ** 2).sum(1), (J[:, 0] * J[:, 1]).sum(1)
+    K = (b00 * b11 - b01 ** 2) / (g00 * g11 - g01 ** 2)
+    ww = np.tile(np.outer(w, w).reshape(-1), Pp.nelem)
+    assert abs((K * det * ww).sum()) < t["gauss_bonnet_tol"]
+    r, R = t["r"], t["R"]
+    assert K.min() >= -1 / (r * (R - r)) - 1e-8 and K.max() <= 1 / (r * (R + r)) + 1e-8
+
+
+def test_dofmap_port():
+    """nurbsbasis.hh:552-587: simple interior knots -> g_d = e_d + l_d; repeated knots shift; trim compaction."""
+    kn = [np.array([0, 0, 0, .25, .5, .75, 1, 1, 1.]), np.array([0, 0, 0, .5, .5, 1, 1, 1.])]
+    ncp = [6, 5]
+    cp = np.ones((30, 3))
+    P = PT.PortPatch([2, 2], kn, cp, 2)
+    dof, n = P.dofmap()
+    assert n == 30 and P.nelem == 8
+    assert list(dof[0]) == [0, 1, 2, 6, 7, 8, 12, 13, 14]
+    # element (1,1): span0 = 3, span1 = 4 (double knot) -> start (1,2)
+    assert list(dof[1 + 4 * 1]) == [13, 14, 15, 19, 20, 21, 25, 26, 27]
+    flags = np.zeros(8, np.uint8)
+    flags[[0, 1]] = 1  # two empty elements
+    dof2, n2 = P.dofmap(flags)
+    used = sorted(set(dof[2:].reshape(-1)))
+    assert n2 == len(used)
+    remap = {g: k for k, g in enumerate(used)}
+    assert all(dof2[e, i] == remap[dof[e, i]] for e in range(2, 8) for i in range(9))
+
+
+def test_assembly_port_properties():
+    """K_e symmetric, rows sum to zero (constants in the kernel of the Laplacian), sum of mass = volume."""
+    spec = PFT.small_patch("plate_hole_p2")
+    P = PT.PortPatch(spec["degree"], spec["knots"], spec["cp"], 2)
+    x, w = PT.gauss01(3)
+    Ke, fe = P.assemble(0, [x, x], [w, w])
+    assert np.abs(Ke - Ke.transpose(0, 2, 1)).max() < 1e-13
+    assert np.abs(Ke.sum(2)).max() < 1e-12
+    Me, _ = P.assemble(1, [x, x], [w, w])
+    assert abs(Me.sum() - P.volume([x, x], [w, w])) < 1e-12
+    assert abs(fe.sum() - P.volume([x, x], [w, w])) < 1e-12
