@@ -1,0 +1,278 @@
+"""ctypes binding of dune-iga_b200/libigab200.so (the C-ABI of include/igab200.h) and a thin host-side mirror of the
+reference's batched objects.  This is what a dune.iga Python caller would use in place of the per-point pybind11
+calls of dune/python/test/poisson.py:47-68 -- numpy in / numpy out, or device pointers in place.
+
+There is NO fallback: if the shared library is missing or no CUDA device is present, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libigab200.so")
+_lib = None
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+HOST, DEVICE = 0, 1
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TENSOR = 0, 1, 2
+ASM_POISSON, ASM_MASS, ASM_ELASTICITY = 0, 1, 2
+FIELDS = ("N", "dN", "d2N", "x", "Jt", "H", "detJ", "JinvT")
+EXPORTS = ("igab_last_error_string", "igab_version", "igab_launch_count", "igab_host_alloc", "igab_host_free",
+           "igab_patch_create", "igab_patch_destroy", "igab_patch_sizes", "igab_patch_set_kernel",
+           "igab_patch_update_control_points", "igab_patch_spans", "igab_patch_dofmap", "igab_eval_tensor",
+           "igab_eval_points", "igab_partial", "igab_assemble", "igab_reduce_volume")
+
+
+class EvalOut(C.Structure):
+    _fields_ = [(f, C.c_void_p) for f in FIELDS]
+
+
+class IgabError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("igab status %d: %s" % (status, msg))
+        self.status = status
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise ImportError("%s not built (run __graft_entry__.build()); there is no CPU fallback" % SO_PATH)
+        L = C.CDLL(SO_PATH)
+        L.igab_last_error_string.restype = C.c_char_p
+        L.igab_version.restype = C.c_char_p
+        L.igab_launch_count.restype = C.c_int64
+        L.igab_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
+        L.igab_host_free.argtypes = [C.c_void_p]
+        L.igab_patch_create.argtypes = [C.c_int, C.c_int, ip, ip, C.POINTER(dp), dp, C.POINTER(C.c_ubyte),
+                                        C.POINTER(C.c_void_p)]
+        L.igab_patch_destroy.argtypes = [C.c_void_p]
+        L.igab_patch_destroy.restype = None
+        L.igab_patch_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_int64)]
+        L.igab_patch_set_kernel.argtypes = [C.c_void_p, C.c_int]
+        L.igab_patch_update_control_points.argtypes = [C.c_void_p, dp]
+        L.igab_patch_spans.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.igab_patch_dofmap.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.c_void_p]
+        L.igab_eval_tensor.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, ip, C.POINTER(dp),
+                                       C.POINTER(EvalOut), C.c_int, C.c_void_p]
+        L.igab_eval_points.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(EvalOut),
+                                       C.c_int, C.c_void_p]
+        L.igab_partial.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, ip, C.c_void_p, C.c_int, C.c_void_p]
+        L.igab_assemble.argtypes = [C.c_void_p, C.c_int, dp, C.c_double, C.c_int64, C.c_int64, ip, C.POINTER(dp),
+                                    C.POINTER(dp), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.igab_reduce_volume.argtypes = [C.c_void_p, C.c_int64, C.c_int64, ip, C.POINTER(dp), C.POINTER(dp),
+                                         C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _check(st):
+    if st != 0:
+        raise IgabError(st, lib().igab_last_error_string().decode())
+
+
+def launch_count():
+    return lib().igab_launch_count()
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _ptr(a):
+    """(address, memspace) of a numpy array (HOST) or of anything with data_ptr() living on a CUDA device (DEVICE)."""
+    if a is None:
+        return None, None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data, HOST
+    if hasattr(a, "data_ptr"):
+        assert a.is_contiguous()
+        return a.data_ptr(), (DEVICE if a.is_cuda else HOST)
+    raise TypeError("expected numpy array or CUDA tensor")
+
+
+def _rule_arrays(rule1d):
+    arrs = [_f64(x) for x in rule1d]
+    ptrs = (dp * len(arrs))(*[a.ctypes.data_as(dp) for a in arrs])
+    return arrs, ptrs
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array over page-locked memory from igab_host_alloc (freed when the array is collected)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    _check(lib().igab_host_alloc(C.byref(p), max(n, 1)))
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[arr.ctypes.data] = p.value
+    return arr
+
+
+_PINNED = {}
+
+
+def pinned_free(arr):
+    p = _PINNED.pop(arr.ctypes.data, None)
+    if p is not None:
+        _check(lib().igab_host_free(C.c_void_p(p)))
+
+
+class Patch:
+    """Device-resident patch handle.  Mirrors what NURBSPatch + NURBSGeometry + NurbsPreBasis hold for the hot path
+    (dune/iga/nurbspatch.hh:53-69, nurbsgeometry.hh:58-85, nurbsbasis.hh:503-518)."""
+
+    def __init__(self, degree, knotSpans, cp, dimworld, trimflags=None):
+        self.dim = len(degree)
+        self.dimworld = int(dimworld)
+        self.degree = [int(p) for p in degree]
+        kn = [_f64(k) for k in knotSpans]
+        cp = _f64(cp).reshape(-1, self.dimworld + 1)
+        ncp = [len(kn[d]) - self.degree[d] - 1 for d in range(self.dim)]
+        if cp.shape[0] != int(np.prod(ncp)):
+            raise ValueError("control net has %d points, knots/degree imply %s" % (cp.shape[0], ncp))
+        kptr = (dp * self.dim)(*[k.ctypes.data_as(dp) for k in kn])
+        tf = None
+        if trimflags is not None:
+            tf = np.ascontiguousarray(trimflags, dtype=np.uint8)
+        h = C.c_void_p()
+        _check(lib().igab_patch_create(self.dim, self.dimworld, _i32(self.degree).ctypes.data_as(ip),
+                                       _i32([len(k) for k in kn]).ctypes.data_as(ip), kptr, cp.ctypes.data_as(dp),
+                                       tf.ctypes.data_as(C.POINTER(C.c_ubyte)) if tf is not None else None,
+                                       C.byref(h)))
+        self.h = h
+        ne, nb, nd = C.c_int64(), C.c_int32(), C.c_int64()
+        ned = (C.c_int32 * 3)()
+        _check(lib().igab_patch_sizes(self.h, C.byref(ne), ned, C.byref(nb), C.byref(nd)))
+        self.nelem, self.nb, self.ndof_untrimmed = ne.value, nb.value, nd.value
+        self.nel_dir = [ned[d] for d in range(self.dim)]
+        self.nh = self.dim * (self.dim + 1) // 2
+
+    @classmethod
+    def fromPatchData(cls, pd, trimflags=None):
+        return cls(pd.degree, pd.knotSpans, pd.cp, pd.dimworld, trimflags)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().igab_patch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def setKernel(self, mode):
+        _check(lib().igab_patch_set_kernel(self.h, mode))
+
+    def updateControlPoints(self, cp):
+        cp = _f64(cp)
+        _check(lib().igab_patch_update_control_points(self.h, cp.ctypes.data_as(dp)))
+
+    # ---- integers
+    def spans(self):
+        out = np.empty((self.nelem, self.dim), dtype=np.int32)
+        _check(lib().igab_patch_spans(self.h, out.ctypes.data, HOST, None))
+        return out
+
+    def dofmap(self):
+        out = np.empty((self.nelem, self.nb), dtype=np.int32)
+        n = C.c_int64()
+        _check(lib().igab_patch_dofmap(self.h, out.ctypes.data, C.byref(n), HOST, None))
+        return out, n.value
+
+    # ---- evaluation
+    def shapes(self, npts):
+        return dict(N=(npts, self.nb), dN=(npts, self.nb, self.dim), d2N=(npts, self.nb, self.nh),
+                    x=(npts, self.dimworld), Jt=(npts, self.dim, self.dimworld), H=(npts, self.nh, self.dimworld),
+                    detJ=(npts,), JinvT=(npts, self.dimworld, self.dim))
+
+    def _outset(self, npts, order, want, out):
+        sh = self.shapes(npts)
+        res, eo, space = {}, EvalOut(), None
+        for f in FIELDS:
+            need = f in want and not (f in ("d2N", "H") and order < 2) and not (
+                f in ("dN", "Jt", "detJ", "JinvT") and order < 1)
+            if not need:
+                continue
+            arr = out[f] if (out is not None and f in out) else np.empty(sh[f])
+            addr, sp = _ptr(arr)
+            if space is not None and sp != space:
+                raise ValueError("all outputs must live in the same memory space")
+            space = sp
+            setattr(eo, f, addr)
+            res[f] = arr
+        return res, eo, (HOST if space is None else space)
+
+    def evalTensor(self, xi1d, order=1, elem_begin=0, elem_end=None, want=FIELDS, out=None, stream=None):
+        """All points of all elements [elem_begin, elem_end) at the tensor rule xi1d (list of 1-D arrays in [0,1])."""
+        if elem_end is None:
+            elem_end = self.nelem
+        arrs, ptrs = _rule_arrays(xi1d)
+        nq1 = _i32([len(a) for a in arrs])
+        npts = (elem_end - elem_begin) * int(np.prod(nq1))
+        res, eo, space = self._outset(npts, order, want, out)
+        _check(lib().igab_eval_tensor(self.h, elem_begin, elem_end, order, nq1.ctypes.data_as(ip), ptrs,
+                                      C.byref(eo), space, stream))
+        return res
+
+    def evalPoints(self, elem, xi, order=1, want=FIELDS, out=None, stream=None):
+        ea, es = _ptr(elem if not isinstance(elem, (list, tuple)) else _i32(elem))
+        if isinstance(elem, (list, tuple, np.ndarray)):
+            elem = _i32(elem)
+            xi = _f64(xi).reshape(len(elem), self.dim)
+            ea, es = _ptr(elem)
+        xa, xs = _ptr(xi)
+        npts = len(elem) if es == HOST else elem.numel()
+        res, eo, space = self._outset(npts, order, want, out)
+        if npts and space != es:
+            raise ValueError("inputs and outputs must live in the same memory space")
+        _check(lib().igab_eval_points(self.h, npts, ea, xa, order, C.byref(eo), es, stream))
+        return res
+
+    def partial(self, elem, xi, alpha):
+        elem = _i32(elem)
+        xi = _f64(xi).reshape(len(elem), self.dim)
+        out = np.empty((len(elem), self.nb))
+        _check(lib().igab_partial(self.h, len(elem), elem.ctypes.data, xi.ctypes.data,
+                                  _i32(alpha).ctypes.data_as(ip), out.ctypes.data, HOST, None))
+        return out
+
+    # ---- element matrices / reductions
+    def assemble(self, kind, xi1d, w1d, D=None, fconst=1.0, elem_begin=0, elem_end=None, want_fe=True, Ke=None,
+                 fe=None, stream=None):
+        if elem_end is None:
+            elem_end = self.nelem
+        n = self.nb * (self.dim if kind == ASM_ELASTICITY else 1)
+        ne = elem_end - elem_begin
+        if Ke is None:
+            Ke = np.empty((ne, n, n))
+            fe = np.empty((ne, n)) if want_fe else None
+        ka, ks = _ptr(Ke)
+        fa, _ = _ptr(fe)
+        xa, xp = _rule_arrays(xi1d)
+        wa, wp = _rule_arrays(w1d)
+        nq1 = _i32([len(a) for a in xa])
+        Dm = _f64(D) if D is not None else None
+        _check(lib().igab_assemble(self.h, kind, Dm.ctypes.data_as(dp) if Dm is not None else None, fconst,
+                                   elem_begin, elem_end, nq1.ctypes.data_as(ip), xp, wp, ka, fa, ks, stream))
+        return Ke, fe
+
+    def volume(self, xi1d, w1d, elem_begin=0, elem_end=None, nccl_comm=None, stream=None):
+        if elem_end is None:
+            elem_end = self.nelem
+        xa, xp = _rule_arrays(xi1d)
+        wa, wp = _rule_arrays(w1d)
+        nq1 = _i32([len(a) for a in xa])
+        r = C.c_double()
+        _check(lib().igab_reduce_volume(self.h, elem_begin, elem_end, nq1.ctypes.data_as(ip), xp, wp, C.byref(r),
+                                        nccl_comm, stream))
+        return r.value

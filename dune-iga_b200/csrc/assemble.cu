@@ -1,0 +1,373 @@
+// assemble.cu -- element matrices K_e = sum_q w detJ B^T D B (K5) and patch reductions (K6).
+// Functional spec: the Python loop dune/python/test/poisson.py:37-81 (localAssembler), generalised to a B-operator
+// with `nrow` rows per quadrature point:
+//     Poisson     B = J^-T grad_xi R_i              (dimworld rows)   poisson.py:58,64-77
+//     mass        B = R_i                            (1 row)
+//     elasticity  B = Voigt strain operator          (3 | 6 rows), D from the caller, DOFs interleaved i*dim+c
+// Written as a batched FP64 contraction  K_e = A1_e^T A2_e  with A1 = B-stack [(q,row)][n], A2 = w detJ D B-stack.
+// Round-1 structure: (1) evaluation kernel (tensor sum-factorised or general) -> N, dN, detJ, JinvT in stream-ordered
+// scratch, (2) B-stack kernel, (3) contraction kernel: FP64 tensor-core DMMA (mma.sync.m8n8k4.f64) for n >= 32,
+// shared-memory FMA tiles below that.
+#include "igab_internal.cuh"
+
+namespace igab {
+
+namespace {
+
+// ---- (2) B-stacks ---------------------------------------------------------------------------------------------------
+// one thread per (point, basis function)
+template <int DIM, int DW>
+__global__ void bstack_kernel(int kind, long long npts, int nb, long long nq, int nq0, int nq1_, int nq2,
+                              const double* __restrict__ w0, const double* __restrict__ w1, const double* __restrict__ w2,
+                              const double* __restrict__ N, const double* __restrict__ dN,
+                              const double* __restrict__ detJ, const double* __restrict__ JinvT,
+                              const double* __restrict__ Dm, double* __restrict__ A1, double* __restrict__ A2, int nrow,
+                              int n) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npts * nb) return;
+  const long long pt = t / nb;
+  const int i = (int)(t % nb);
+  long long q = pt % nq;
+  const long long e = pt / nq;
+  double w = w0[q % nq0];
+  q /= nq0;
+  if (DIM > 1) { w *= w1[q % nq1_]; q /= nq1_; }
+  if (DIM > 2) { w *= w2[q % nq2]; }
+  const double s = w * detJ[pt];
+  // rows of this point inside the element's stack: [(q,row)][n]
+  const long long rowBase = (e * nq + (pt % nq)) * nrow;
+  if (kind == IGAB_ASM_MASS) {
+    const double v = N[pt * nb + i];
+    A1[rowBase * n + i] = v;
+    A2[rowBase * n + i] = s * v;
+    return;
+  }
+  double g[DW];
+#pragma unroll
+  for (int c = 0; c < DW; ++c) {
+    double acc = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) acc += JinvT[pt * DIM * DW + c * DIM + d] * dN[(pt * nb + i) * DIM + d];
+    g[c] = acc;
+  }
+  if (kind == IGAB_ASM_POISSON) {
+#pragma unroll
+    for (int c = 0; c < DW; ++c) {
+      A1[(rowBase + c) * n + i] = g[c];
+      A2[(rowBase + c) * n + i] = s * g[c];
+    }
+    return;
+  }
+  // elasticity: B columns i*DIM + c
+  constexpr int NS = (DIM == 2) ? 3 : 6;
+  double Bc[NS][DIM];
+#pragma unroll
+  for (int r = 0; r < NS; ++r)
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) Bc[r][c] = 0.0;
+  if constexpr (DIM == 2) {
+    Bc[0][0] = g[0]; Bc[1][1] = g[1]; Bc[2][0] = g[1]; Bc[2][1] = g[0];
+  } else if constexpr (DIM == 3) {
+    Bc[0][0] = g[0]; Bc[1][1] = g[1]; Bc[2][2] = g[2];
+    Bc[3][1] = g[2]; Bc[3][2] = g[1];
+    Bc[4][0] = g[2]; Bc[4][2] = g[0];
+    Bc[5][0] = g[1]; Bc[5][1] = g[0];
+  }
+#pragma unroll
+  for (int r = 0; r < NS; ++r)
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) {
+      A1[(rowBase + r) * n + i * DIM + c] = Bc[r][c];
+      double acc = 0.0;
+#pragma unroll
+      for (int t2 = 0; t2 < NS; ++t2) acc += Dm[r * NS + t2] * Bc[t2][c];
+      A2[(rowBase + r) * n + i * DIM + c] = s * acc;
+    }
+}
+
+// f_e[i] = sum_q w detJ N_i fconst  (poisson.py:79); one thread per (element, dof)
+template <int DIM>
+__global__ void load_kernel(long long nel, int nb, int ncomp, long long nq, int nq0, int nq1_, int nq2,
+                            const double* __restrict__ w0, const double* __restrict__ w1, const double* __restrict__ w2,
+                            const double* __restrict__ N, const double* __restrict__ detJ, double fconst,
+                            double* __restrict__ fe) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nel * nb) return;
+  const long long e = t / nb;
+  const int i = (int)(t % nb);
+  double acc = 0.0;
+  for (long long q = 0; q < nq; ++q) {
+    long long h = q;
+    double w = w0[h % nq0];
+    h /= nq0;
+    if (DIM > 1) { w *= w1[h % nq1_]; h /= nq1_; }
+    if (DIM > 2) { w *= w2[h % nq2]; }
+    const long long pt = e * nq + q;
+    acc += w * detJ[pt] * N[pt * nb + i] * fconst;
+  }
+  for (int c = 0; c < ncomp; ++c) fe[(e * nb + i) * ncomp + c] = acc;
+}
+
+// ---- (3a) contraction, FMA path: K_e = A1^T A2, 16x16 thread tile, 2x2 outputs per thread ---------------------------
+__global__ void __launch_bounds__(256) contract_fma_kernel(int n, int kdim, const double* __restrict__ A1,
+                                                           const double* __restrict__ A2, double* __restrict__ Ke) {
+  constexpr int T = 32, KT = 16;
+  __shared__ double sa[KT][T + 1], sb[KT][T + 1];
+  const long long e = blockIdx.z;
+  const double* a1 = A1 + e * (long long)kdim * n;
+  const double* a2 = A2 + e * (long long)kdim * n;
+  const int i0 = blockIdx.y * T, j0 = blockIdx.x * T;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[2][2] = {{0, 0}, {0, 0}};
+  for (int k0 = 0; k0 < kdim; k0 += KT) {
+    for (int idx = threadIdx.x; idx < KT * T; idx += 256) {
+      const int kk = idx / T, c = idx % T;
+      const int k = k0 + kk;
+      sa[kk][c] = (k < kdim && i0 + c < n) ? a1[(long long)k * n + i0 + c] : 0.0;
+      sb[kk][c] = (k < kdim && j0 + c < n) ? a2[(long long)k * n + j0 + c] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) {
+      const double x0 = sa[kk][ty], x1 = sa[kk][ty + 16], y0 = sb[kk][tx], y1 = sb[kk][tx + 16];
+      acc[0][0] += x0 * y0; acc[0][1] += x0 * y1; acc[1][0] += x1 * y0; acc[1][1] += x1 * y1;
+    }
+    __syncthreads();
+  }
+  double* K = Ke + e * (long long)n * n;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
+      if (i < n && j < n) K[(long long)i * n + j] = acc[a][b];
+    }
+}
+
+// ---- (3b) contraction, FP64 tensor cores: mma.sync.aligned.m8n8k4.row.col.f64 ---------------------------------------
+// Block = 4 warps computes a 64x64 tile of K_e; each warp a 32x32 sub-tile = 4x4 DMMA tiles (2 doubles per lane each).
+// C[i][j] = sum_k A1[k][i] A2[k][j]:  A-operand (row-major M x K) element (i,k) = A1[k][i]; B-operand (K x N) = A2[k][j].
+// Fragment layout of m8n8k4.f64: lane = 4*g + t (g = 0..7, t = 0..3): a = A[g][t], b = B[t][g], c0 = C[g][2t], c1 = C[g][2t+1].
+__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(128) contract_dmma_kernel(int n, int kdim, const double* __restrict__ A1,
+                                                            const double* __restrict__ A2, double* __restrict__ Ke) {
+  constexpr int T = 64, KT = 16, LD = T + 4;  // row stride 68 doubles: the 4 k-rows of a fragment land in 4 distinct bank groups
+  __shared__ double sa[KT][LD], sb[KT][LD];
+  const long long e = blockIdx.z;
+  const double* a1 = A1 + e * (long long)kdim * n;
+  const double* a2 = A2 + e * (long long)kdim * n;
+  const int i0 = blockIdx.y * T, j0 = blockIdx.x * T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wi = (warp >> 1) * 32, wj = (warp & 1) * 32;
+  double c[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) c[a][b][0] = c[a][b][1] = 0.0;
+  for (int k0 = 0; k0 < kdim; k0 += KT) {
+    for (int idx = threadIdx.x; idx < KT * T; idx += 128) {
+      const int kk = idx / T, col = idx % T;
+      const int k = k0 + kk;
+      sa[kk][col] = (k < kdim && i0 + col < n) ? a1[(long long)k * n + i0 + col] : 0.0;
+      sb[kk][col] = (k < kdim && j0 + col < n) ? a2[(long long)k * n + j0 + col] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < KT; ks += 4) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) af[a] = sa[ks + t][wi + 8 * a + g];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bf[b] = sb[ks + t][wj + 8 * b + g];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dmma8x8x4(c[a][b][0], c[a][b][1], af[a], bf[b]);
+    }
+    __syncthreads();
+  }
+  double* K = Ke + e * (long long)n * n;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = i0 + wi + 8 * a + g, j = j0 + wj + 8 * b + 2 * t;
+      if (i < n) {
+        if (j < n) K[(long long)i * n + j] = c[a][b][0];
+        if (j + 1 < n) K[(long long)i * n + j + 1] = c[a][b][1];
+      }
+    }
+}
+
+// ---- K6: deterministic volume reduction -----------------------------------------------------------------------------
+// partial[b] = sum over a fixed contiguous slice of points of detJ*w (sequential per thread, fixed tree per block);
+// result = fixed-order sum of the partials.  Same launch geometry => bitwise reproducible.
+template <int DIM>
+__global__ void __launch_bounds__(256) volume_partial_kernel(long long npts, long long nq, int nq0, int nq1_, int nq2,
+                                                             const double* __restrict__ w0, const double* __restrict__ w1,
+                                                             const double* __restrict__ w2,
+                                                             const double* __restrict__ detJ, double* __restrict__ partial) {
+  __shared__ double sh[256];
+  const long long per = (npts + gridDim.x - 1) / gridDim.x;
+  const long long b0 = (long long)blockIdx.x * per, b1 = min(npts, b0 + per);
+  double acc = 0.0;
+  for (long long pt = b0 + threadIdx.x; pt < b1; pt += 256) {
+    long long q = pt % nq;
+    double w = w0[q % nq0];
+    q /= nq0;
+    if (DIM > 1) { w *= w1[q % nq1_]; q /= nq1_; }
+    if (DIM > 2) { w *= w2[q % nq2]; }
+    acc += detJ[pt] * w;
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(1024) volume_final_kernel(int n, const double* __restrict__ partial, double* __restrict__ result) {
+  __shared__ double sh[1024];
+  sh[threadIdx.x] = threadIdx.x < n ? partial[threadIdx.x] : 0.0;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *result = sh[0];
+}
+
+igab_status eval_for(const PatchDev& P, long long eb, long long nel, const int* nq1, const double* const* xi1d_dev,
+                     const EvalOutDev& out, cudaStream_t stream) {
+  PointSource src{};
+  src.tensor = 1;
+  src.elem_begin = eb;
+  src.nq = 1;
+  for (int d = 0; d < P.dim; ++d) {
+    src.nq1[d] = nq1[d];
+    src.nq *= nq1[d];
+    src.xi1d[d] = xi1d_dev[d];
+  }
+  if (eval_tensor_sf_supported(P, nq1, 1, out)) return launch_eval_tensor_sf(P, src, nel, 1, out, stream);
+  return launch_eval_generic(P, src, nel * src.nq, 1, out, stream);
+}
+
+template <int DIM, int DW>
+igab_status assemble_dd(const PatchDev& P, int kind, const double* D_dev, double fconst, long long eb, long long nel,
+                        const int* nq1, const double* const* xi, const double* const* w, double* Ke, double* fe,
+                        cudaStream_t stream) {
+  long long nq = 1;
+  for (int d = 0; d < DIM; ++d) nq *= nq1[d];
+  const int nb = P.nb;
+  const int ncomp = kind == IGAB_ASM_ELASTICITY ? DIM : 1;
+  const int n = nb * ncomp;
+  const int nrow = kind == IGAB_ASM_MASS ? 1 : (kind == IGAB_ASM_POISSON ? DW : (DIM == 2 ? 3 : 6));
+  const int kdim = (int)nq * nrow;
+  // element chunks bounded by scratch (A1 + A2 dominate)
+  const long long perEl = 8LL * (2LL * kdim * n + nq * (nb + nb * DIM + 1 + DIM * DW));
+  const long long chunk = std::max(1LL, std::min(nel, (2LL << 30) / perEl));
+  const int q0 = nq1[0], q1 = DIM > 1 ? nq1[1] : 1, q2 = DIM > 2 ? nq1[2] : 1;
+  for (long long c0 = 0; c0 < nel; c0 += chunk) {
+    const long long m = std::min(chunk, nel - c0);
+    const long long npts = m * nq;
+    double *dNv = nullptr, *ddN = nullptr, *ddet = nullptr, *dJi = nullptr, *A1 = nullptr, *A2 = nullptr;
+    IGAB_CUDA_TRY(cudaMallocAsync(&dNv, 8 * npts * nb, stream));
+    IGAB_CUDA_TRY(cudaMallocAsync(&ddN, 8 * npts * nb * DIM, stream));
+    IGAB_CUDA_TRY(cudaMallocAsync(&ddet, 8 * npts, stream));
+    IGAB_CUDA_TRY(cudaMallocAsync(&dJi, 8 * npts * DIM * DW, stream));
+    IGAB_CUDA_TRY(cudaMallocAsync(&A1, 8LL * m * kdim * n, stream));
+    IGAB_CUDA_TRY(cudaMallocAsync(&A2, 8LL * m * kdim * n, stream));
+    EvalOutDev o{};
+    o.N = dNv; o.dN = ddN; o.detJ = ddet; o.JinvT = dJi;
+    igab_status st = eval_for(P, eb + c0, m, nq1, xi, o, stream);
+    if (st) return st;
+    if (kind == IGAB_ASM_ELASTICITY) {
+      // zero the structural zeros of B once (bstack writes every entry of its rows, so nothing to clear)
+    }
+    {
+      const long long tot = npts * nb;
+      bstack_kernel<DIM, DW><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(
+          kind, npts, nb, nq, q0, q1, q2, w[0], w[DIM > 1 ? 1 : 0], w[DIM > 2 ? 2 : 0], dNv, ddN, ddet, dJi, D_dev, A1, A2,
+          nrow, n);
+      count_launch();
+    }
+    double* K = Ke + (long long)c0 * n * n;
+    if (n >= 32) {
+      dim3 grid((n + 63) / 64, (n + 63) / 64, (unsigned)m);
+      contract_dmma_kernel<<<grid, 128, 0, stream>>>(n, kdim, A1, A2, K);
+    } else {
+      dim3 grid((n + 31) / 32, (n + 31) / 32, (unsigned)m);
+      contract_fma_kernel<<<grid, 256, 0, stream>>>(n, kdim, A1, A2, K);
+    }
+    count_launch();
+    if (fe) {
+      const long long tot = m * nb;
+      load_kernel<DIM><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(m, nb, ncomp, nq, q0, q1, q2, w[0],
+                                                                           w[DIM > 1 ? 1 : 0], w[DIM > 2 ? 2 : 0], dNv,
+                                                                           ddet, fconst, fe + (long long)c0 * n);
+      count_launch();
+    }
+    IGAB_CUDA_TRY(cudaGetLastError());
+    cudaFreeAsync(dNv, stream); cudaFreeAsync(ddN, stream); cudaFreeAsync(ddet, stream);
+    cudaFreeAsync(dJi, stream); cudaFreeAsync(A1, stream); cudaFreeAsync(A2, stream);
+  }
+  return IGAB_OK;
+}
+
+}  // namespace
+
+igab_status launch_assemble(const PatchDev& P, int kind, const double* D_dev, double fconst, long long elem_begin,
+                            long long nelem, const int* nq1, const double* const* xi1d_dev,
+                            const double* const* w1d_dev, double* Ke, double* fe, cudaStream_t stream) {
+  switch (P.dim * 10 + P.dw) {
+    case 11: return assemble_dd<1, 1>(P, kind, D_dev, fconst, elem_begin, nelem, nq1, xi1d_dev, w1d_dev, Ke, fe, stream);
+    case 22: return assemble_dd<2, 2>(P, kind, D_dev, fconst, elem_begin, nelem, nq1, xi1d_dev, w1d_dev, Ke, fe, stream);
+    case 23: return assemble_dd<2, 3>(P, kind, D_dev, fconst, elem_begin, nelem, nq1, xi1d_dev, w1d_dev, Ke, fe, stream);
+    case 33: return assemble_dd<3, 3>(P, kind, D_dev, fconst, elem_begin, nelem, nq1, xi1d_dev, w1d_dev, Ke, fe, stream);
+  }
+  set_error("assemble: unsupported (dim, dimworld)");
+  return IGAB_UNSUPPORTED;
+}
+
+igab_status launch_volume(const PatchDev& P, long long elem_begin, long long nelem, const int* nq1,
+                          const double* const* xi1d_dev, const double* const* w1d_dev, double* partial_dev,
+                          int npartial, double* result_dev, cudaStream_t stream) {
+  long long nq = 1;
+  for (int d = 0; d < P.dim; ++d) nq *= nq1[d];
+  const long long npts = nelem * nq;
+  if (npts == 0) {
+    IGAB_CUDA_TRY(cudaMemsetAsync(result_dev, 0, sizeof(double), stream));
+    return IGAB_OK;
+  }
+  double* ddet = nullptr;
+  IGAB_CUDA_TRY(cudaMallocAsync(&ddet, 8 * npts, stream));
+  EvalOutDev o{};
+  o.detJ = ddet;
+  igab_status st = eval_for(P, elem_begin, nelem, nq1, xi1d_dev, o, stream);
+  if (st) return st;
+  const int q0 = nq1[0], q1 = P.dim > 1 ? nq1[1] : 1, q2 = P.dim > 2 ? nq1[2] : 1;
+  const int nblk = (int)std::min<long long>(npartial, (npts + 255) / 256);
+  const double* w0 = w1d_dev[0];
+  const double* w1 = w1d_dev[P.dim > 1 ? 1 : 0];
+  const double* w2 = w1d_dev[P.dim > 2 ? 2 : 0];
+  if (P.dim == 1)
+    volume_partial_kernel<1><<<nblk, 256, 0, stream>>>(npts, nq, q0, q1, q2, w0, w1, w2, ddet, partial_dev);
+  else if (P.dim == 2)
+    volume_partial_kernel<2><<<nblk, 256, 0, stream>>>(npts, nq, q0, q1, q2, w0, w1, w2, ddet, partial_dev);
+  else
+    volume_partial_kernel<3><<<nblk, 256, 0, stream>>>(npts, nq, q0, q1, q2, w0, w1, w2, ddet, partial_dev);
+  volume_final_kernel<<<1, 1024, 0, stream>>>(nblk, partial_dev, result_dev);
+  count_launch(2);
+  IGAB_CUDA_TRY(cudaGetLastError());
+  cudaFreeAsync(ddet, stream);
+  return IGAB_OK;
+}
+
+}  // namespace igab

@@ -1,0 +1,753 @@
+// igab_api.cu -- the C-ABI of include/igab200.h: handle management, integer kernels (spans, DOF map), dispatch of the
+// evaluation / assembly / reduction kernels, and host<->device staging for IGAB_HOST buffers.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <string>
+
+#include "igab_internal.cuh"
+
+namespace igab {
+
+static thread_local std::string g_last_error;
+static std::atomic<long long> g_launches{0};
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+igab_status cuda_fail(cudaError_t e, const char* what) {
+  g_last_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  return e == cudaErrorMemoryAllocation ? IGAB_OUT_OF_MEMORY : IGAB_CUDA_ERROR;
+}
+
+// ---- integer kernels ------------------------------------------------------------------------------------------------
+// K7a: spans of all elements [nelem][dim]  (nurbspatch.hh:248-253; element index first-direction-fastest)
+__global__ void spans_kernel(PatchDev P, int32_t* __restrict__ span) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P.nelem) return;
+  long long h = e;
+  for (int d = 0; d < P.dim; ++d) {
+    span[e * P.dim + d] = P.spanTab[d][h % P.nel[d]];
+    h /= P.nel[d];
+  }
+}
+
+// K7b: element-to-global DOF map (nurbsbasis.hh:552-587): one thread per (element, local basis function);
+// g_d = max(s_d - p_d, 0) + l_d ; flat = g_0 + n_0 (g_1 + n_1 g_2), n_d = |U_d| - p_d - 1.
+__global__ void dofmap_kernel(PatchDev P, int32_t* __restrict__ dof) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P.nelem * P.nb) return;
+  const long long e = t / P.nb;
+  int i = (int)(t % P.nb);
+  long long h = e, flat = 0, stride = 1;
+  for (int d = 0; d < P.dim; ++d) {
+    const int s = P.spanTab[d][h % P.nel[d]];
+    h /= P.nel[d];
+    const int l = i % (P.degree[d] + 1);
+    i /= (P.degree[d] + 1);
+    const int g = max(s - P.degree[d], 0) + l;
+    flat += g * stride;
+    stride *= (P.nknots[d] - P.degree[d] - 1);
+  }
+  dof[t] = (int32_t)flat;
+}
+
+// trim compaction (nurbsbasis.hh:599-615): mark DOFs touched by non-empty elements, exclusive scan, remap.
+__global__ void dof_mark_kernel(PatchDev P, const uint8_t* __restrict__ trim, const int32_t* __restrict__ dof,
+                                int32_t* __restrict__ used) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P.nelem * P.nb) return;
+  if (trim[t / P.nb] != IGAB_TRIM_EMPTY) used[dof[t]] = 1;
+}
+// single-block ordered scan (the DOF count of one patch is small next to the evaluation; kept simple and exact)
+__global__ void dof_scan_kernel(const int32_t* __restrict__ used, int32_t* __restrict__ map, long long n,
+                                long long* __restrict__ total) {
+  __shared__ long long carry;
+  __shared__ int wsum[32];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long base = 0; base < n; base += blockDim.x) {
+    const long long i = base + threadIdx.x;
+    const int v = (i < n) ? used[i] : 0;
+    int s = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += t;
+    }
+    if (lane == 31) wsum[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+      int w = (lane < (int)(blockDim.x >> 5)) ? wsum[lane] : 0;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      wsum[lane] = w;
+    }
+    __syncthreads();
+    const long long excl = carry + (warp ? wsum[warp - 1] : 0) + s - v;
+    if (i < n) map[i] = v ? (int32_t)excl : -1;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += wsum[(blockDim.x >> 5) - 1];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+__global__ void dof_remap_kernel(long long n, const int32_t* __restrict__ map, int32_t* __restrict__ dof) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) dof[t] = map[dof[t]];
+}
+
+igab_status launch_spans(const PatchDev& P, int32_t* span, cudaStream_t stream) {
+  const int th = 256;
+  spans_kernel<<<(unsigned)((P.nelem + th - 1) / th), th, 0, stream>>>(P, span);
+  count_launch();
+  IGAB_CUDA_TRY(cudaGetLastError());
+  return IGAB_OK;
+}
+igab_status launch_dofmap(const PatchDev& P, int32_t* dof, cudaStream_t stream) {
+  const int th = 256;
+  const long long n = P.nelem * P.nb;
+  dofmap_kernel<<<(unsigned)((n + th - 1) / th), th, 0, stream>>>(P, dof);
+  count_launch();
+  IGAB_CUDA_TRY(cudaGetLastError());
+  return IGAB_OK;
+}
+igab_status launch_dof_compact(const PatchDev& P, const uint8_t* trim_dev, int32_t* dof, int32_t* used, int32_t* map,
+                               long long ndof, long long* total_dev, cudaStream_t stream) {
+  const int th = 256;
+  const long long n = P.nelem * P.nb;
+  IGAB_CUDA_TRY(cudaMemsetAsync(used, 0, sizeof(int32_t) * ndof, stream));
+  dof_mark_kernel<<<(unsigned)((n + th - 1) / th), th, 0, stream>>>(P, trim_dev, dof, used);
+  dof_scan_kernel<<<1, 1024, 0, stream>>>(used, map, ndof, total_dev);
+  dof_remap_kernel<<<(unsigned)((n + th - 1) / th), th, 0, stream>>>(n, map, dof);
+  count_launch(3);
+  IGAB_CUDA_TRY(cudaGetLastError());
+  return IGAB_OK;
+}
+
+// ---- host helpers ---------------------------------------------------------------------------------------------------
+static bool feq8(double a, double b) {
+  const double eps = 8.0 * 2.220446049250313e-16;
+  return std::fabs(a - b) <= eps * std::max(std::fabs(a), std::fabs(b));
+}
+// findSpanCorrected (bsplinealgorithms.hh:24-32): integer work done once per direction on the host at handle creation
+static int find_span_corrected(int p, double u, const std::vector<double>& U, int offset) {
+  if (u <= U.front()) return p;
+  if (u >= U.back()) return (int)U.size() - p - 2;
+  auto it = std::upper_bound(U.begin() + p - 1 + offset, U.end(), u);
+  return (int)(it - U.begin()) - 1;
+}
+
+constexpr int kMaxRule = 64;  // points per direction of a tensor rule
+
+struct RuleDev {
+  const double* xi[kMaxDim];
+  const double* w[kMaxDim];
+};
+// copies the rule to the handle's device scratch on `stream`
+static igab_status stage_rule(igab_patch* p, const int* nq1, const double* const* xi1d, const double* const* w1d,
+                              RuleDev* r, cudaStream_t stream) {
+  double host[2 * kMaxDim * kMaxRule];
+  std::memset(host, 0, sizeof(host));
+  for (int d = 0; d < p->dev.dim; ++d) {
+    if (nq1[d] < 1 || nq1[d] > kMaxRule) {
+      set_error("quadrature rule: 1..64 points per direction supported");
+      return IGAB_INVALID_ARGUMENT;
+    }
+    if (!xi1d || !xi1d[d]) {
+      set_error("quadrature rule: null abscissae");
+      return IGAB_INVALID_ARGUMENT;
+    }
+    std::memcpy(host + d * kMaxRule, xi1d[d], sizeof(double) * nq1[d]);
+    if (w1d && w1d[d]) std::memcpy(host + (kMaxDim + d) * kMaxRule, w1d[d], sizeof(double) * nq1[d]);
+  }
+  // pageable source: the copy is staged by the runtime before the call returns, so `host` may go out of scope
+  IGAB_CUDA_TRY(cudaMemcpyAsync(p->d_rule, host, sizeof(host), cudaMemcpyHostToDevice, stream));
+  for (int d = 0; d < kMaxDim; ++d) {
+    r->xi[d] = p->d_rule + d * kMaxRule;
+    r->w[d] = p->d_rule + (kMaxDim + d) * kMaxRule;
+  }
+  return IGAB_OK;
+}
+
+static void out_sizes(const PatchDev& P, long long npts, long long sz[8]) {
+  const int nh = P.dim * (P.dim + 1) / 2;
+  sz[0] = npts * P.nb;
+  sz[1] = npts * P.nb * P.dim;
+  sz[2] = npts * P.nb * nh;
+  sz[3] = npts * P.dw;
+  sz[4] = npts * P.dim * P.dw;
+  sz[5] = npts * nh * P.dw;
+  sz[6] = npts;
+  sz[7] = npts * P.dim * P.dw;
+}
+static double** out_field(igab_eval_out* o, int k) {
+  double** f[8] = {&o->N, &o->dN, &o->d2N, &o->x, &o->Jt, &o->H, &o->detJ, &o->JinvT};
+  return f[k];
+}
+static igab_status check_out(const igab_eval_out* out, int order, igab_eval_out* eff) {
+  if (!out) {
+    set_error("eval: null output set");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  if (order < 0 || order > 2) {
+    set_error("eval: deriv_order must be 0, 1 or 2");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  *eff = *out;
+  if (order < 2) eff->d2N = eff->H = nullptr;
+  if (order < 1) eff->dN = eff->Jt = eff->detJ = eff->JinvT = nullptr;
+  return IGAB_OK;
+}
+static EvalOutDev to_dev(const igab_eval_out& o) { return EvalOutDev{o.N, o.dN, o.d2N, o.x, o.Jt, o.H, o.detJ, o.JinvT}; }
+
+static igab_status run_eval_tensor_device(igab_patch* p, long long eb, long long ee, int order, const int* nq1,
+                                          const RuleDev& rule, const igab_eval_out& out, cudaStream_t stream) {
+  PointSource src{};
+  src.tensor = 1;
+  src.elem_begin = eb;
+  src.nq = 1;
+  for (int d = 0; d < p->dev.dim; ++d) {
+    src.nq1[d] = nq1[d];
+    src.nq *= nq1[d];
+    src.xi1d[d] = rule.xi[d];
+  }
+  const EvalOutDev od = to_dev(out);
+  const long long nel = ee - eb;
+  if (nel == 0) return IGAB_OK;
+  bool sf = p->kernel_mode != IGAB_KERNEL_GENERIC && eval_tensor_sf_supported(p->dev, nq1, order, od);
+  if (p->kernel_mode == IGAB_KERNEL_TENSOR && !sf) {
+    set_error("eval_tensor: no sum-factorised kernel compiled for this (dim, dimworld, degree, rule, outputs)");
+    return IGAB_UNSUPPORTED;
+  }
+  if (sf) return launch_eval_tensor_sf(p->dev, src, nel, order, od, stream);
+  // general kernel: bounded launches
+  const long long maxPts = 1LL << 30;
+  const long long elPer = std::max(1LL, maxPts / src.nq);
+  for (long long b = 0; b < nel; b += elPer) {
+    const long long n = std::min(elPer, nel - b);
+    PointSource s2 = src;
+    s2.elem_begin = eb + b;
+    igab_eval_out o2 = out;
+    long long sz[8];
+    out_sizes(p->dev, b * src.nq, sz);
+    for (int k = 0; k < 8; ++k)
+      if (*out_field(&o2, k)) *out_field(&o2, k) += sz[k];
+    igab_status st = launch_eval_generic(p->dev, s2, n * src.nq, order, to_dev(o2), stream);
+    if (st) return st;
+  }
+  return IGAB_OK;
+}
+
+}  // namespace igab
+
+using namespace igab;
+
+// =====================================================================================================================
+extern "C" {
+
+const char* igab_last_error_string(void) { return g_last_error.c_str(); }
+const char* igab_version(void) { return "igab200 0.1 (sm_100a)"; }
+int64_t igab_launch_count(void) { return g_launches.load(); }
+
+igab_status igab_host_alloc(void** ptr, uint64_t bytes) {
+  if (!ptr) return IGAB_INVALID_ARGUMENT;
+  IGAB_CUDA_TRY(cudaMallocHost(ptr, bytes));
+  return IGAB_OK;
+}
+igab_status igab_host_free(void* ptr) {
+  IGAB_CUDA_TRY(cudaFreeHost(ptr));
+  return IGAB_OK;
+}
+
+igab_status igab_patch_create(int dim, int dimworld, const int* degree, const int* nknots, const double* const* knots,
+                              const double* cp, const uint8_t* trimflags, igab_patch** out) {
+  if (!out) return IGAB_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (dim < 1 || dim > kMaxDim || dimworld < dim || dimworld > 3 || !degree || !nknots || !knots || !cp) {
+    set_error("patch_create: need 1 <= dim <= dimworld <= 3 and non-null degree/nknots/knots/cp");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  if (!((dim == 1) || (dim == 2 && dimworld >= 2) || (dim == 3 && dimworld == 3))) {
+    set_error("patch_create: unsupported (dim, dimworld)");
+    return IGAB_UNSUPPORTED;
+  }
+  igab_patch* p = new (std::nothrow) igab_patch();
+  if (!p) return IGAB_OUT_OF_MEMORY;
+  PatchDev& D = p->dev;
+  D.dim = dim;
+  D.dw = dimworld;
+  D.nb = 1;
+  D.nelem = 1;
+  p->ncp_total = 1;
+  for (int d = 0; d < dim; ++d) {
+    const int pd = degree[d], n = nknots[d];
+    if (pd < 1 || pd > kMaxDegree || n < 2 * (pd + 1) || !knots[d]) {
+      set_error("patch_create: degree must be 1..8 and the knot vector must hold at least 2(p+1) knots");
+      delete p;
+      return IGAB_INVALID_ARGUMENT;
+    }
+    std::vector<double>& U = p->hknots[d];
+    U.assign(knots[d], knots[d] + n);
+    bool ok = std::is_sorted(U.begin(), U.end());
+    for (int i = 0; i <= pd && ok; ++i) ok = (U[i] == U[0]) && (U[n - 1 - i] == U[n - 1]);
+    if (!ok || !(U[0] < U[n - 1])) {
+      // the reference asserts open knot vectors (bsplinealgorithms.hh:98-99, nurbsgrid.hh:112-122)
+      set_error("patch_create: knot vector must be sorted and open (degree+1 equal end knots)");
+      delete p;
+      return IGAB_INVALID_ARGUMENT;
+    }
+    // unique knots with FloatCmp::eq (nurbspatch.hh:58-63) and the per-direction element->span table
+    std::vector<double> uq;
+    for (double v : U)
+      if (uq.empty() || !feq8(uq.back(), v)) uq.push_back(v);
+    const int nel = (int)uq.size() - 1;
+    p->hspan[d].resize(nel);
+    for (int e = 0; e < nel; ++e) p->hspan[d][e] = find_span_corrected(pd, uq[e], U, e);
+    D.degree[d] = pd;
+    D.nknots[d] = n;
+    D.ncp[d] = n - pd - 1;
+    D.nel[d] = nel;
+    D.nb *= pd + 1;
+    D.nelem *= nel;
+    p->ncp_total *= D.ncp[d];
+  }
+  p->ndof_untrimmed = p->ncp_total;
+  if (trimflags) p->htrim.assign(trimflags, trimflags + D.nelem);
+
+  cudaError_t e = cudaGetDevice(&p->device);
+  if (e != cudaSuccess) {
+    igab_status st = cuda_fail(e, "cudaGetDevice (no CUDA device: this library has no CPU fallback)");
+    delete p;
+    return st;
+  }
+  auto fail = [&](cudaError_t err, const char* what) {
+    igab_status st = cuda_fail(err, what);
+    igab_patch_destroy(p);
+    return st;
+  };
+  for (int d = 0; d < dim; ++d) {
+    if ((e = cudaMalloc(&p->d_knots[d], sizeof(double) * D.nknots[d])) != cudaSuccess) return fail(e, "cudaMalloc knots");
+    if ((e = cudaMalloc(&p->d_span[d], sizeof(int) * D.nel[d])) != cudaSuccess) return fail(e, "cudaMalloc spans");
+    if ((e = cudaMemcpy(p->d_knots[d], p->hknots[d].data(), sizeof(double) * D.nknots[d], cudaMemcpyHostToDevice)) != cudaSuccess)
+      return fail(e, "copy knots");
+    if ((e = cudaMemcpy(p->d_span[d], p->hspan[d].data(), sizeof(int) * D.nel[d], cudaMemcpyHostToDevice)) != cudaSuccess)
+      return fail(e, "copy spans");
+    D.knots[d] = p->d_knots[d];
+    D.spanTab[d] = p->d_span[d];
+  }
+  const size_t cpBytes = sizeof(double) * p->ncp_total * (dimworld + 1);
+  if ((e = cudaMalloc(&p->d_cp, cpBytes)) != cudaSuccess) return fail(e, "cudaMalloc control net");
+  if ((e = cudaMemcpy(p->d_cp, cp, cpBytes, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e, "copy control net");
+  D.cp = p->d_cp;
+  if (trimflags) {
+    if ((e = cudaMalloc(&p->d_trim, D.nelem)) != cudaSuccess) return fail(e, "cudaMalloc trim flags");
+    if ((e = cudaMemcpy(p->d_trim, trimflags, D.nelem, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e, "copy trim");
+  }
+  if ((e = cudaMalloc(&p->d_rule, sizeof(double) * 2 * kMaxDim * kMaxRule)) != cudaSuccess) return fail(e, "cudaMalloc rule");
+  *out = p;
+  return IGAB_OK;
+}
+
+void igab_patch_destroy(igab_patch* p) {
+  if (!p) return;
+  for (int d = 0; d < kMaxDim; ++d) {
+    if (p->d_knots[d]) cudaFree(p->d_knots[d]);
+    if (p->d_span[d]) cudaFree(p->d_span[d]);
+  }
+  if (p->d_cp) cudaFree(p->d_cp);
+  if (p->d_trim) cudaFree(p->d_trim);
+  if (p->d_rule) cudaFree(p->d_rule);
+  if (p->d_red) cudaFree(p->d_red);
+  delete p;
+}
+
+igab_status igab_patch_sizes(const igab_patch* p, int64_t* n_elem, int32_t* n_elem_dir, int32_t* nb,
+                             int64_t* ndof_untrimmed) {
+  if (!p) return IGAB_INVALID_ARGUMENT;
+  if (n_elem) *n_elem = p->dev.nelem;
+  if (n_elem_dir)
+    for (int d = 0; d < p->dev.dim; ++d) n_elem_dir[d] = p->dev.nel[d];
+  if (nb) *nb = p->dev.nb;
+  if (ndof_untrimmed) *ndof_untrimmed = p->ndof_untrimmed;
+  return IGAB_OK;
+}
+
+igab_status igab_patch_set_kernel(igab_patch* p, int kernel) {
+  if (!p || kernel < 0 || kernel > 2) return IGAB_INVALID_ARGUMENT;
+  p->kernel_mode = kernel;
+  return IGAB_OK;
+}
+
+igab_status igab_patch_update_control_points(igab_patch* p, const double* cp) {
+  if (!p || !cp) return IGAB_INVALID_ARGUMENT;
+  IGAB_CUDA_TRY(cudaMemcpy(p->d_cp, cp, sizeof(double) * p->ncp_total * (p->dev.dw + 1), cudaMemcpyHostToDevice));
+  return IGAB_OK;
+}
+
+igab_status igab_patch_spans(igab_patch* p, int32_t* span, igab_memspace space, void* stream_) {
+  if (!p || !span) return IGAB_INVALID_ARGUMENT;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (space == IGAB_DEVICE) return launch_spans(p->dev, span, stream);
+  int32_t* d = nullptr;
+  const size_t bytes = sizeof(int32_t) * p->dev.nelem * p->dev.dim;
+  IGAB_CUDA_TRY(cudaMalloc(&d, bytes));
+  igab_status st = launch_spans(p->dev, d, stream);
+  if (!st) {
+    cudaError_t e = cudaMemcpyAsync(span, d, bytes, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) st = cuda_fail(e, "spans D2H");
+  }
+  cudaFree(d);
+  return st;
+}
+
+igab_status igab_patch_dofmap(igab_patch* p, int32_t* dof, int64_t* ndof, igab_memspace space, void* stream_) {
+  if (!p || !dof) return IGAB_INVALID_ARGUMENT;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const long long n = p->dev.nelem * p->dev.nb;
+  if (n > 0x7fffffffLL * 256LL) {
+    set_error("dofmap: too many entries");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  int32_t* d = dof;
+  if (space == IGAB_HOST) IGAB_CUDA_TRY(cudaMalloc(&d, sizeof(int32_t) * n));
+  igab_status st = launch_dofmap(p->dev, d, stream);
+  long long total = p->ndof_untrimmed;
+  int32_t *used = nullptr, *map = nullptr;
+  long long* total_dev = nullptr;
+  if (!st && p->d_trim) {
+    cudaError_t e = cudaMalloc(&used, sizeof(int32_t) * p->ndof_untrimmed);
+    if (e == cudaSuccess) e = cudaMalloc(&map, sizeof(int32_t) * p->ndof_untrimmed);
+    if (e == cudaSuccess) e = cudaMalloc(&total_dev, sizeof(long long));
+    if (e != cudaSuccess) st = cuda_fail(e, "dofmap scratch");
+    if (!st) st = launch_dof_compact(p->dev, p->d_trim, d, used, map, p->ndof_untrimmed, total_dev, stream);
+    if (!st) {
+      e = cudaMemcpyAsync(&total, total_dev, sizeof(long long), cudaMemcpyDeviceToHost, stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+      if (e != cudaSuccess) st = cuda_fail(e, "dofmap total D2H");
+    }
+  }
+  if (!st && space == IGAB_HOST) {
+    cudaError_t e = cudaMemcpyAsync(dof, d, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) st = cuda_fail(e, "dofmap D2H");
+  }
+  if (used) cudaFree(used);
+  if (map) cudaFree(map);
+  if (total_dev) cudaFree(total_dev);
+  if (space == IGAB_HOST && d) cudaFree(d);
+  if (!st && ndof) *ndof = total;
+  return st;
+}
+
+// ---- evaluation -----------------------------------------------------------------------------------------------------
+igab_status igab_eval_tensor(igab_patch* p, int64_t elem_begin, int64_t elem_end, int deriv_order, const int* nq1,
+                             const double* const* xi1d, const igab_eval_out* out, igab_memspace out_space,
+                             void* stream_) {
+  if (!p || !nq1 || !xi1d) {
+    set_error("eval_tensor: null argument");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  if (elem_begin < 0 || elem_end < elem_begin || elem_end > p->dev.nelem) {
+    set_error("eval_tensor: element range outside [0, n_elem]");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  igab_eval_out eff;
+  igab_status st = check_out(out, deriv_order, &eff);
+  if (st) return st;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RuleDev rule;
+  if ((st = stage_rule(p, nq1, xi1d, nullptr, &rule, stream))) return st;
+  if (out_space == IGAB_DEVICE) return run_eval_tensor_device(p, elem_begin, elem_end, deriv_order, nq1, rule, eff, stream);
+
+  // HOST outputs: element chunks through two sets of device buffers; the D2H copy of chunk k overlaps the kernel of
+  // chunk k+1 (copy stream + events).  Full PCIe rate needs pinned destination memory (igab_host_alloc).
+  long long nq = 1;
+  for (int d = 0; d < p->dev.dim; ++d) nq *= nq1[d];
+  long long per_pt[8], bytes_pt = 0;
+  out_sizes(p->dev, 1, per_pt);
+  for (int k = 0; k < 8; ++k)
+    if (*out_field(&eff, k)) bytes_pt += per_pt[k] * 8;
+  const long long nel = elem_end - elem_begin;
+  if (nel == 0 || bytes_pt == 0) return IGAB_OK;
+  const long long chunkBytes = 512LL << 20;  // per buffer set
+  const long long elChunk = std::max(1LL, std::min(nel, chunkBytes / (bytes_pt * nq)));
+  double* dbuf[2][8] = {};
+  cudaStream_t cstream = nullptr;
+  cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+  cudaError_t e = cudaStreamCreateWithFlags(&cstream, cudaStreamNonBlocking);
+  for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+    e = cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming);
+    for (int k = 0; k < 8 && e == cudaSuccess; ++k)
+      if (*out_field(&eff, k)) e = cudaMalloc(&dbuf[b][k], per_pt[k] * 8 * nq * elChunk);
+  }
+  if (e != cudaSuccess) st = cuda_fail(e, "eval_tensor host staging allocation");
+  int b = 0;
+  for (long long c0 = 0; c0 < nel && !st; c0 += elChunk, b ^= 1) {
+    const long long n = std::min(elChunk, nel - c0);
+    igab_eval_out dv{};
+    for (int k = 0; k < 8; ++k) *out_field(&dv, k) = dbuf[b][k];
+    if ((e = cudaStreamWaitEvent(stream, copied[b], 0)) != cudaSuccess) { st = cuda_fail(e, "wait copied"); break; }
+    st = run_eval_tensor_device(p, elem_begin + c0, elem_begin + c0 + n, deriv_order, nq1, rule, dv, stream);
+    if (st) break;
+    if ((e = cudaEventRecord(done[b], stream)) != cudaSuccess) { st = cuda_fail(e, "record done"); break; }
+    if ((e = cudaStreamWaitEvent(cstream, done[b], 0)) != cudaSuccess) { st = cuda_fail(e, "wait done"); break; }
+    for (int k = 0; k < 8; ++k) {
+      double* h = *out_field(&eff, k);
+      if (!h) continue;
+      e = cudaMemcpyAsync(h + per_pt[k] * nq * c0, dbuf[b][k], per_pt[k] * 8 * nq * n, cudaMemcpyDeviceToHost, cstream);
+      if (e != cudaSuccess) { st = cuda_fail(e, "eval_tensor D2H"); break; }
+    }
+    if (st) break;
+    if ((e = cudaEventRecord(copied[b], cstream)) != cudaSuccess) { st = cuda_fail(e, "record copied"); break; }
+  }
+  if (cstream) {
+    e = cudaStreamSynchronize(cstream);
+    if (e != cudaSuccess && !st) st = cuda_fail(e, "sync copy stream");
+  }
+  e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess && !st) st = cuda_fail(e, "sync stream");
+  for (int bb = 0; bb < 2; ++bb) {
+    for (int k = 0; k < 8; ++k)
+      if (dbuf[bb][k]) cudaFree(dbuf[bb][k]);
+    if (done[bb]) cudaEventDestroy(done[bb]);
+    if (copied[bb]) cudaEventDestroy(copied[bb]);
+  }
+  if (cstream) cudaStreamDestroy(cstream);
+  return st;
+}
+
+igab_status igab_eval_points(igab_patch* p, int64_t npts, const int32_t* elem, const double* xi, int deriv_order,
+                             const igab_eval_out* out, igab_memspace space, void* stream_) {
+  if (!p || npts < 0 || (npts > 0 && (!elem || !xi))) {
+    set_error("eval_points: null argument");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  igab_eval_out eff;
+  igab_status st = check_out(out, deriv_order, &eff);
+  if (st) return st;
+  if (npts == 0) return IGAB_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PointSource src{};
+  src.tensor = 0;
+  if (space == IGAB_DEVICE) {
+    src.elem = elem;
+    src.xi = xi;
+    return launch_eval_generic(p->dev, src, npts, deriv_order, to_dev(eff), stream);
+  }
+  for (long long k = 0; k < npts; ++k)
+    if (elem[k] < 0 || elem[k] >= p->dev.nelem) {
+      set_error("eval_points: element index out of range");
+      return IGAB_INVALID_ARGUMENT;
+    }
+  int* d_elem = nullptr;
+  double* d_xi = nullptr;
+  double* dbuf[8] = {};
+  long long sz[8];
+  out_sizes(p->dev, npts, sz);
+  cudaError_t e = cudaMalloc(&d_elem, sizeof(int) * npts);
+  if (e == cudaSuccess) e = cudaMalloc(&d_xi, sizeof(double) * npts * p->dev.dim);
+  for (int k = 0; k < 8 && e == cudaSuccess; ++k)
+    if (*out_field(&eff, k)) e = cudaMalloc(&dbuf[k], sz[k] * 8);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_elem, elem, sizeof(int) * npts, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_xi, xi, sizeof(double) * npts * p->dev.dim, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) st = cuda_fail(e, "eval_points staging");
+  if (!st) {
+    src.elem = d_elem;
+    src.xi = d_xi;
+    igab_eval_out dv{};
+    for (int k = 0; k < 8; ++k) *out_field(&dv, k) = dbuf[k];
+    st = launch_eval_generic(p->dev, src, npts, deriv_order, to_dev(dv), stream);
+  }
+  for (int k = 0; k < 8 && !st; ++k)
+    if (dbuf[k]) {
+      e = cudaMemcpyAsync(*out_field(&eff, k), dbuf[k], sz[k] * 8, cudaMemcpyDeviceToHost, stream);
+      if (e != cudaSuccess) st = cuda_fail(e, "eval_points D2H");
+    }
+  e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess && !st) st = cuda_fail(e, "eval_points sync");
+  if (d_elem) cudaFree(d_elem);
+  if (d_xi) cudaFree(d_xi);
+  for (int k = 0; k < 8; ++k)
+    if (dbuf[k]) cudaFree(dbuf[k]);
+  return st;
+}
+
+igab_status igab_partial(igab_patch* p, int64_t npts, const int32_t* elem, const double* xi, const int* alpha,
+                         double* out, igab_memspace space, void* stream_) {
+  if (!p || !alpha || npts < 0 || (npts > 0 && (!elem || !xi || !out))) {
+    set_error("partial: null argument");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  for (int d = 0; d < p->dev.dim; ++d)
+    if (alpha[d] < 0 || alpha[d] > 15) {
+      set_error("partial: derivative order per direction must be 0..15");
+      return IGAB_INVALID_ARGUMENT;
+    }
+  if (npts == 0) return IGAB_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (space == IGAB_DEVICE) return launch_partial(p->dev, npts, elem, xi, alpha, out, stream);
+  for (long long k = 0; k < npts; ++k)
+    if (elem[k] < 0 || elem[k] >= p->dev.nelem) {
+      set_error("partial: element index out of range");
+      return IGAB_INVALID_ARGUMENT;
+    }
+  int* d_elem = nullptr;
+  double *d_xi = nullptr, *d_out = nullptr;
+  igab_status st = IGAB_OK;
+  cudaError_t e = cudaMalloc(&d_elem, sizeof(int) * npts);
+  if (e == cudaSuccess) e = cudaMalloc(&d_xi, sizeof(double) * npts * p->dev.dim);
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(double) * npts * p->dev.nb);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_elem, elem, sizeof(int) * npts, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_xi, xi, sizeof(double) * npts * p->dev.dim, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) st = cuda_fail(e, "partial staging");
+  if (!st) st = launch_partial(p->dev, npts, d_elem, d_xi, alpha, d_out, stream);
+  if (!st) {
+    e = cudaMemcpyAsync(out, d_out, sizeof(double) * npts * p->dev.nb, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) st = cuda_fail(e, "partial D2H");
+  }
+  if (d_elem) cudaFree(d_elem);
+  if (d_xi) cudaFree(d_xi);
+  if (d_out) cudaFree(d_out);
+  return st;
+}
+
+// ---- element matrices -----------------------------------------------------------------------------------------------
+igab_status igab_assemble(igab_patch* p, int kind, const double* D, double fconst, int64_t elem_begin,
+                          int64_t elem_end, const int* nq1, const double* const* xi1d, const double* const* w1d,
+                          double* Ke, double* fe, igab_memspace out_space, void* stream_) {
+  if (!p || !nq1 || !xi1d || !w1d || !Ke) {
+    set_error("assemble: null argument");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  if (kind < 0 || kind > 2) {
+    set_error("assemble: unknown kind");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  if (elem_begin < 0 || elem_end < elem_begin || elem_end > p->dev.nelem) {
+    set_error("assemble: element range outside [0, n_elem]");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  if (kind == IGAB_ASM_ELASTICITY && (p->dev.dim != p->dev.dw || p->dev.dim < 2 || !D)) {
+    set_error("assemble: elasticity needs dim == dimworld in {2,3} and a D matrix");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  if (kind == IGAB_ASM_POISSON && p->dev.dim != p->dev.dw && p->dev.dim == 3) {
+    set_error("assemble: unsupported dims");
+    return IGAB_UNSUPPORTED;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RuleDev rule;
+  igab_status st = stage_rule(p, nq1, xi1d, w1d, &rule, stream);
+  if (st) return st;
+  const long long nel = elem_end - elem_begin;
+  if (nel == 0) return IGAB_OK;
+  const int n = p->dev.nb * (kind == IGAB_ASM_ELASTICITY ? p->dev.dim : 1);
+  const int ns = p->dev.dim == 2 ? 3 : 6;
+  double* d_D = nullptr;
+  cudaError_t e;
+  if (kind == IGAB_ASM_ELASTICITY) {
+    if ((e = cudaMalloc(&d_D, sizeof(double) * ns * ns)) != cudaSuccess) return cuda_fail(e, "assemble D");
+    if ((e = cudaMemcpyAsync(d_D, D, sizeof(double) * ns * ns, cudaMemcpyHostToDevice, stream)) != cudaSuccess) {
+      cudaFree(d_D);
+      return cuda_fail(e, "assemble D copy");
+    }
+  }
+  if (out_space == IGAB_DEVICE) {
+    st = launch_assemble(p->dev, kind, d_D, fconst, elem_begin, nel, nq1, rule.xi, rule.w, Ke, fe, stream);
+    if (d_D) {
+      cudaStreamSynchronize(stream);
+      cudaFree(d_D);
+    }
+    return st;
+  }
+  // HOST outputs: chunked through one device buffer
+  const long long keBytes = 8LL * n * n, chunkBytes = 512LL << 20;
+  const long long elChunk = std::max(1LL, std::min(nel, chunkBytes / keBytes));
+  double *dK = nullptr, *dF = nullptr;
+  e = cudaMalloc(&dK, keBytes * elChunk);
+  if (e == cudaSuccess && fe) e = cudaMalloc(&dF, 8LL * n * elChunk);
+  if (e != cudaSuccess) st = cuda_fail(e, "assemble staging");
+  for (long long c0 = 0; c0 < nel && !st; c0 += elChunk) {
+    const long long m = std::min(elChunk, nel - c0);
+    st = launch_assemble(p->dev, kind, d_D, fconst, elem_begin + c0, m, nq1, rule.xi, rule.w, dK, dF, stream);
+    if (st) break;
+    e = cudaMemcpyAsync(Ke + (long long)n * n * c0, dK, keBytes * m, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && fe) e = cudaMemcpyAsync(fe + (long long)n * c0, dF, 8LL * n * m, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) st = cuda_fail(e, "assemble D2H");
+  }
+  cudaStreamSynchronize(stream);
+  if (dK) cudaFree(dK);
+  if (dF) cudaFree(dF);
+  if (d_D) cudaFree(d_D);
+  return st;
+}
+
+// ---- reductions -----------------------------------------------------------------------------------------------------
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+static nccl_allreduce_fn resolve_nccl_allreduce() {
+  // NCCL is resolved at run time from the process (torch ships libnccl.so.2) so that the library has no link-time
+  // dependency on it; used only when the caller passes a communicator.
+  static nccl_allreduce_fn fn = nullptr;
+  static bool tried = false;
+  if (tried) return fn;
+  tried = true;
+  void* sym = dlsym(RTLD_DEFAULT, "ncclAllReduce");
+  if (!sym) {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (h) sym = dlsym(h, "ncclAllReduce");
+  }
+  fn = (nccl_allreduce_fn)sym;
+  return fn;
+}
+
+igab_status igab_reduce_volume(igab_patch* p, int64_t elem_begin, int64_t elem_end, const int* nq1,
+                               const double* const* xi1d, const double* const* w1d, double* result, void* nccl_comm,
+                               void* stream_) {
+  if (!p || !nq1 || !xi1d || !w1d || !result) {
+    set_error("reduce_volume: null argument");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  if (elem_begin < 0 || elem_end < elem_begin || elem_end > p->dev.nelem) {
+    set_error("reduce_volume: element range outside [0, n_elem]");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RuleDev rule;
+  igab_status st = stage_rule(p, nq1, xi1d, w1d, &rule, stream);
+  if (st) return st;
+  const int npartial = 1024;
+  if (!p->d_red) {
+    IGAB_CUDA_TRY(cudaMalloc(&p->d_red, sizeof(double) * (npartial + 2)));
+    p->red_cap = npartial;
+  }
+  double* res_dev = p->d_red + npartial;
+  st = launch_volume(p->dev, elem_begin, elem_end - elem_begin, nq1, rule.xi, rule.w, p->d_red, npartial, res_dev, stream);
+  if (st) return st;
+  if (nccl_comm) {
+    nccl_allreduce_fn ar = resolve_nccl_allreduce();
+    if (!ar) {
+      set_error("reduce_volume: NCCL communicator given but libnccl.so.2 could not be resolved");
+      return IGAB_NCCL_ERROR;
+    }
+    // ncclDouble = 8, ncclSum = 0 (nccl.h); in place on the one-element device scalar
+    const int rc = ar(res_dev, res_dev, 1, 8, 0, nccl_comm, stream);
+    if (rc != 0) {
+      set_error("reduce_volume: ncclAllReduce failed with code " + std::to_string(rc));
+      return IGAB_NCCL_ERROR;
+    }
+  }
+  IGAB_CUDA_TRY(cudaMemcpyAsync(result, res_dev, sizeof(double), cudaMemcpyDeviceToHost, stream));
+  IGAB_CUDA_TRY(cudaStreamSynchronize(stream));
+  return IGAB_OK;
+}
+
+}  // extern "C"

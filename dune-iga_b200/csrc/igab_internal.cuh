@@ -1,0 +1,97 @@
+// Internal declarations shared by the translation units of libigab200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/igab200.h"
+
+namespace igab {
+
+constexpr int kMaxDim = 3;
+constexpr int kMaxDegree = 8;           // per direction
+constexpr int kMaxOrder1D = kMaxDegree + 1;
+
+// Everything a kernel needs to know about a patch; passed by value (lives in constant param space).
+struct PatchDev {
+  int dim, dw;
+  int degree[kMaxDim];
+  int nknots[kMaxDim];
+  int ncp[kMaxDim];
+  int nel[kMaxDim];               // elements (non-empty spans) per direction
+  const double* knots[kMaxDim];   // device
+  const int* spanTab[kMaxDim];    // device: span index of element e_d, bit-exact with findSpanCorrected(p,uq[e],U,e)
+  const double* cp;               // device [prod ncp][dw+1]  (x.., w)
+  int nb;                         // prod (degree+1)
+  long long nelem;
+};
+
+// Where the points of a batch come from.
+struct PointSource {
+  int tensor;                     // 1: tensor rule over elements [elem_begin, ...), 0: explicit list
+  long long elem_begin;
+  int nq1[kMaxDim];
+  long long nq;                   // prod nq1
+  const double* xi1d[kMaxDim];    // device
+  const int* elem;                // device [npts]     (list mode)
+  const double* xi;               // device [npts][dim] (list mode)
+};
+
+struct EvalOutDev {
+  double *N, *dN, *d2N, *x, *Jt, *H, *detJ, *JinvT;
+};
+
+void set_error(const std::string& msg);
+igab_status cuda_fail(cudaError_t e, const char* what);
+void count_launch(int n = 1);
+
+#define IGAB_CUDA_TRY(expr)                                           \
+  do {                                                                \
+    cudaError_t _e = (expr);                                          \
+    if (_e != cudaSuccess) return ::igab::cuda_fail(_e, #expr);       \
+  } while (0)
+
+// ---- kernels' host launchers (each returns after enqueueing on `stream`)
+igab_status launch_eval_generic(const PatchDev& P, const PointSource& src, long long npts, int order,
+                                const EvalOutDev& out, cudaStream_t stream);
+// returns IGAB_UNSUPPORTED when no sum-factorised instantiation matches
+igab_status launch_eval_tensor_sf(const PatchDev& P, const PointSource& src, long long nelem, int order,
+                                  const EvalOutDev& out, cudaStream_t stream);
+bool eval_tensor_sf_supported(const PatchDev& P, const int* nq1, int order, const EvalOutDev& out);
+igab_status launch_partial(const PatchDev& P, long long npts, const int* elem, const double* xi, const int* alpha,
+                           double* out, cudaStream_t stream);
+igab_status launch_spans(const PatchDev& P, int32_t* span, cudaStream_t stream);
+igab_status launch_dofmap(const PatchDev& P, int32_t* dof, cudaStream_t stream);
+igab_status launch_dof_compact(const PatchDev& P, const uint8_t* trim_dev, int32_t* dof, int32_t* scratch_used,
+                               int32_t* scratch_map, long long ndof, long long* ndof_out_host, cudaStream_t stream);
+igab_status launch_assemble(const PatchDev& P, int kind, const double* D_dev, double fconst, long long elem_begin,
+                            long long nelem, const int* nq1, const double* const* xi1d_dev,
+                            const double* const* w1d_dev, double* Ke, double* fe, cudaStream_t stream);
+igab_status launch_volume(const PatchDev& P, long long elem_begin, long long nelem, const int* nq1,
+                          const double* const* xi1d_dev, const double* const* w1d_dev, double* partial_dev,
+                          int npartial, double* result_dev, cudaStream_t stream);
+
+}  // namespace igab
+
+// The host-side object behind the opaque handle.
+struct igab_patch {
+  igab::PatchDev dev{};
+  int device = 0;
+  int kernel_mode = IGAB_KERNEL_AUTO;
+  std::vector<double> hknots[igab::kMaxDim];
+  std::vector<int> hspan[igab::kMaxDim];
+  std::vector<uint8_t> htrim;
+  double* d_knots[igab::kMaxDim] = {nullptr, nullptr, nullptr};
+  int* d_span[igab::kMaxDim] = {nullptr, nullptr, nullptr};
+  double* d_cp = nullptr;
+  uint8_t* d_trim = nullptr;
+  long long ncp_total = 0;
+  long long ndof_untrimmed = 0;
+  // small device scratch for quadrature rules (xi, w per direction), reused across calls
+  double* d_rule = nullptr;  // [2][kMaxDim][kMaxRule]
+  // reduction scratch
+  double* d_red = nullptr;
+  int red_cap = 0;
+};

@@ -1,0 +1,161 @@
+/* igab200.h -- C-ABI of the B200-native NURBS evaluation / assembly path behind dune-iga's local-finite-element and
+ * geometry API.  Plain pointers and sizes only; no C++ / torch types.  Every entry point returns an igab_status
+ * (0 == ok), never throws and never aborts; igab_last_error_string() explains the last failure of the calling thread.
+ *
+ * The reference (rath3t/dune-iga v0.1.7, header-only C++) has NO plugin / FFI layer for this path: the boundary a
+ * replacement sits behind is the set of C++ methods its clients call once per quadrature point.  Each entry point
+ * below names the reference interface it replaces (file:line relative to the reference root) and batches it over
+ * all points of all elements of a patch.  INTEGRATION.md shows the reference-side binding (a header-only adaptor
+ * keeping the reference's method names, and the pybind11 / ctypes stub for dune.iga).
+ *
+ * Layout contract (identical to the reference's MultiDimensionNet, dune/iga/utils/mdnet.hh:329-345):
+ *   - every multi-index is flattened FIRST DIRECTION FASTEST: elements, local basis functions, quadrature points,
+ *     control points;
+ *   - control point k is the row (x_0 .. x_{dimworld-1}, w) -- ControlPoint{p,w}, dune/iga/controlpoint.hh:15-38;
+ *   - points are numbered pt = (e - elem_begin) * nq + q for tensor rules, or as given for point lists;
+ *   - outputs per point, all FP64, contiguous per point:
+ *       N    [pt][nb]              R_i(xi)                       NurbsLocalBasis::evaluateFunction   nurbsbasis.hh:77-82
+ *       dN   [pt][nb][dim]         dR_i/dxi_d  (reference elem.) NurbsLocalBasis::evaluateJacobian   nurbsbasis.hh:87-96
+ *       d2N  [pt][nb][nh]          partial(alpha), |alpha| = 2   NurbsLocalBasis::partial            nurbsbasis.hh:99-108
+ *       x    [pt][dimworld]        NURBSGeometry::global                                             nurbsgeometry.hh:133-138
+ *       Jt   [pt][dim][dimworld]   NURBSGeometry::jacobianTransposed                                 nurbsgeometry.hh:182-196
+ *       H    [pt][nh][dimworld]    NURBSGeometry::secondDerivativeOfPosition                         nurbsgeometry.hh:257-292
+ *       detJ [pt]                  NURBSGeometry::integrationElement                                 nurbsgeometry.hh:200-203
+ *       JinvT[pt][dimworld][dim]   NURBSGeometry::jacobianInverseTransposed                          nurbsgeometry.hh:205-210
+ *     nb = prod(degree_d + 1); nh = dim (dim+1)/2 with the reference's row order: pure second derivatives first,
+ *     then mixed (0,1),(0,2),(1,2)  (nurbsgeometry.hh:262-289).
+ *   - integers (spans, DOF maps) are int32 and bit-exact with the reference.
+ *
+ * Memory spaces: patch data is always given in HOST memory and copied to the current CUDA device by
+ * igab_patch_create.  Bulk inputs/outputs carry an igab_memspace: IGAB_DEVICE pointers are used in place on the
+ * given stream (asynchronous); IGAB_HOST pointers are staged through device buffers owned by the handle, and the call
+ * returns after the results have landed (synchronous).  There is no CPU fallback: without a CUDA device every
+ * compute entry point returns IGAB_CUDA_ERROR.
+ *
+ * Threading: one host thread per patch handle at a time (the reference is threadSafe=false,
+ * dune/iga/gridcapabilities.hh:53-63); different handles may be used concurrently.
+ */
+#ifndef IGAB200_H
+#define IGAB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct igab_patch igab_patch;
+typedef int igab_status;
+
+enum {
+  IGAB_OK = 0,
+  IGAB_INVALID_ARGUMENT = 1,
+  IGAB_OUT_OF_MEMORY = 2,
+  IGAB_CUDA_ERROR = 3,
+  IGAB_NCCL_ERROR = 4,
+  IGAB_UNSUPPORTED = 5
+};
+
+typedef enum { IGAB_HOST = 0, IGAB_DEVICE = 1 } igab_memspace;
+
+/* igab_eval_* kernel choice (igab_patch_set_kernel): AUTO picks the sum-factorised tensor kernel when one is
+ * compiled for the patch's (dim, dimworld, degree, rule) and the general per-point kernel otherwise. */
+enum { IGAB_KERNEL_AUTO = 0, IGAB_KERNEL_GENERIC = 1, IGAB_KERNEL_TENSOR = 2 };
+
+/* element trim flags, values of Dune::IGA::ElementTrimFlag (dune/iga/nurbspatch.hh:633-647) */
+enum { IGAB_TRIM_FULL = 0, IGAB_TRIM_EMPTY = 1, IGAB_TRIM_TRIMMED = 2 };
+
+/* assembly kinds for igab_assemble */
+enum { IGAB_ASM_POISSON = 0, IGAB_ASM_MASS = 1, IGAB_ASM_ELASTICITY = 2 };
+
+/* Output set of an evaluation; any member may be NULL (not computed / not stored). */
+typedef struct igab_eval_out {
+  double* N;
+  double* dN;
+  double* d2N;
+  double* x;
+  double* Jt;
+  double* H;
+  double* detJ;
+  double* JinvT;
+} igab_eval_out;
+
+/* ---- library ------------------------------------------------------------------------------------------------- */
+const char* igab_last_error_string(void);
+const char* igab_version(void);
+/* number of CUDA kernels this library has launched in this process (for benchmarks' gpu_launches) */
+int64_t igab_launch_count(void);
+/* pinned host memory for IGAB_HOST buffers that should transfer at full PCIe rate */
+igab_status igab_host_alloc(void** ptr, uint64_t bytes);
+igab_status igab_host_free(void* ptr);
+
+/* ---- patch handle -------------------------------------------------------------------------------------------------
+ * Replaces: NURBSPatchData (dune/iga/nurbspatchdata.hh:17-36) + the per-element state NURBSPatch / NURBSGeometry /
+ * NurbsLocalFiniteElement cache: unique knots (nurbspatch.hh:58-66), element->span (nurbspatch.hh:248-253,
+ * nurbsbasis.hh:355-360), scaling/offset (nurbsgeometry.hh:64-68, nurbsbasis.hh:363-365).
+ * knots[d] has nknots[d] entries (open knot vector, degree[d]+1 repeated end knots, else IGAB_INVALID_ARGUMENT);
+ * cp has prod(nknots[d]-degree[d]-1) rows of dimworld+1 doubles.  trimflags: NULL or one byte per element.
+ * Supported: dim 1..3, dim <= dimworld <= 3, degree 1..8 per direction.                                          */
+igab_status igab_patch_create(int dim, int dimworld, const int* degree, const int* nknots, const double* const* knots,
+                              const double* cp, const uint8_t* trimflags, igab_patch** out);
+void igab_patch_destroy(igab_patch* p);
+/* n_elem total and per direction (non-empty knot spans); nb = local basis size; ndof_untrimmed = prod n_d */
+igab_status igab_patch_sizes(const igab_patch* p, int64_t* n_elem, int32_t* n_elem_dir, int32_t* nb,
+                             int64_t* ndof_untrimmed);
+igab_status igab_patch_set_kernel(igab_patch* p, int kernel);
+/* replace the control net (same sizes) without rebuilding the handle, e.g. after a geometry update */
+igab_status igab_patch_update_control_points(igab_patch* p, const double* cp);
+
+/* Replaces: NURBSPatch::spanAndDirectionFromDirectIndex<0> (nurbspatch.hh:248-253) / NurbsLocalFiniteElement::bind
+ * (nurbsbasis.hh:355-365) for all elements.  span [n_elem][dim], bit-exact.                                      */
+igab_status igab_patch_spans(igab_patch* p, int32_t* span, igab_memspace space, void* stream);
+
+/* Replaces: NurbsPreBasis::createOriginalNodeIndices + prepareForTrim + indices (nurbsbasis.hh:552-615).
+ * dof [n_elem][nb]; entries of IGAB_TRIM_EMPTY elements whose DOF was dropped are -1; *ndof = size of the basis.   */
+igab_status igab_patch_dofmap(igab_patch* p, int32_t* dof, int64_t* ndof, igab_memspace space, void* stream);
+
+/* ---- batched evaluation -------------------------------------------------------------------------------------------
+ * Replaces, for every point of every element in [elem_begin, elem_end) at the tensor rule xi1d[d][0..nq1[d]):
+ * the user quadrature loop calling evaluateFunction / evaluateJacobian / partial (nurbsbasis.hh:77-108) and
+ * global / jacobianTransposed / integrationElement / jacobianInverseTransposed / secondDerivativeOfPosition
+ * (nurbsgeometry.hh:133-138,182-210,257-292); element iteration nurbsleafgridview.hh:147-155; rule
+ * nurbsgridentity.hh:120-141.  xi1d are HOST arrays in [0,1] (element-local).  deriv_order 0, 1 or 2 bounds what
+ * is computed (dN/Jt/detJ/JinvT need >= 1, d2N/H need 2).                                                        */
+igab_status igab_eval_tensor(igab_patch* p, int64_t elem_begin, int64_t elem_end, int deriv_order, const int* nq1,
+                             const double* const* xi1d, const igab_eval_out* out, igab_memspace out_space,
+                             void* stream);
+
+/* Same at arbitrary element-local points (trimmed-element rules, utils/fillquadraturerule.hh:8-19; probes):
+ * elem[npts] element direct index, xi[npts][dim]; inputs and outputs all in `space`.                             */
+igab_status igab_eval_points(igab_patch* p, int64_t npts, const int32_t* elem, const double* xi, int deriv_order,
+                             const igab_eval_out* out, igab_memspace space, void* stream);
+
+/* Replaces NurbsLocalBasis::partial for an arbitrary multi-index alpha (nurbsbasis.hh:99-108,667-677):
+ * out[npts][nb] = prod_d scale_d^alpha_d * d^alpha R_i.  prod(alpha_d+1) <= 64.                                    */
+igab_status igab_partial(igab_patch* p, int64_t npts, const int32_t* elem, const double* xi, const int* alpha,
+                         double* out, igab_memspace space, void* stream);
+
+/* ---- element matrices ---------------------------------------------------------------------------------------------
+ * Replaces the Python localAssembler loop, dune/python/test/poisson.py:37-81, generalised to B^T D B w detJ:
+ *   IGAB_ASM_POISSON    Ke[i][j] = sum_q w detJ grad R_i . grad R_j ; fe[i] = sum_q w detJ R_i fconst
+ *   IGAB_ASM_MASS       Ke[i][j] = sum_q w detJ R_i R_j
+ *   IGAB_ASM_ELASTICITY B = strain operator (Voigt xx,yy,xy | xx,yy,zz,yz,xz,xy), D row-major ns x ns (HOST),
+ *                       DOFs flat-interleaved i*dim+c (dune-functions PowerPreBasis, basis/__init__.py:53-67)
+ * Ke [n_el][n][n] row-major, n = nb or nb*dim; fe [n_el][n] or NULL.  w1d HOST weights of the tensor rule.        */
+igab_status igab_assemble(igab_patch* p, int kind, const double* D, double fconst, int64_t elem_begin,
+                          int64_t elem_end, const int* nq1, const double* const* xi1d, const double* const* w1d,
+                          double* Ke, double* fe, igab_memspace out_space, void* stream);
+
+/* ---- patch reductions ---------------------------------------------------------------------------------------------
+ * Replaces the user loop summing NURBSGeometry::volume() over elements (nurbsgeometry.hh:96-113,
+ * dune/iga/test/gridtests.cpp:338-341): result = sum_{e in range} sum_q detJ w.  Deterministic two-level tree sum.
+ * nccl_comm: NULL, or an ncclComm_t over the ranks sharing the patch -- then *result is the all-reduced sum
+ * (ncclAllReduce, ncclDouble, ncclSum) and is identical on all ranks.  *result is a HOST scalar.                */
+igab_status igab_reduce_volume(igab_patch* p, int64_t elem_begin, int64_t elem_end, const int* nq1,
+                               const double* const* xi1d, const double* const* w1d, double* result, void* nccl_comm,
+                               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IGAB200_H */

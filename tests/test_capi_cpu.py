@@ -1,0 +1,64 @@
+"""CPU-side checks of the C-ABI (-m "not gpu"): the in-tree library loads, exports every symbol include/igab200.h
+declares, validates arguments before touching CUDA, and fails loudly (no CPU fallback) without a device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import igab200  # noqa: F401
+from dune_iga_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "igab200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(igab_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = capi.lib()
+    names = declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(L, n), n
+    assert set(names) == set(capi.EXPORTS)
+    assert b"sm_100a" in L.igab_version()
+
+
+def test_only_cuda_code_in_the_library():
+    # the product must not link the oracle
+    import subprocess
+    out = subprocess.run(["ldd", capi.SO_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "libcudart" in out
+
+
+def test_argument_validation_before_cuda():
+    L = capi.lib()
+    h = C.c_void_p()
+    deg = (C.c_int * 1)(2)
+    nk = (C.c_int * 1)(5)
+    kn = np.array([0, 0, 1, 1, 1.0])
+    kp = (capi.dp * 1)(kn.ctypes.data_as(capi.dp))
+    cp = np.ones((2, 3))
+    # closed/short knot vector: the reference asserts open knot vectors (bsplinealgorithms.hh:98-99)
+    st = L.igab_patch_create(1, 2, deg, nk, kp, cp.ctypes.data_as(capi.dp), None, C.byref(h))
+    assert st == 1 and b"knot" in L.igab_last_error_string()
+    st = L.igab_patch_create(4, 4, deg, nk, kp, cp.ctypes.data_as(capi.dp), None, C.byref(h))
+    assert st == 1
+    assert L.igab_patch_sizes(None, None, None, None, None) == 1
+
+
+def test_no_cpu_fallback_without_device():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("device present")
+    except ImportError:
+        pass
+    with pytest.raises(capi.IgabError) as ei:
+        capi.Patch([1], [[0, 0, 1, 1]], [[0, 0, 1], [1, 0, 1]], 2)
+    assert ei.value.status in (3, 2)

@@ -1,0 +1,294 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI, against the oracle on the same seeded inputs,
+against the reference's own literals, and -- at sizes the oracle cannot reach -- through size-independent properties.
+
+Bar (BASELINE.json north_star): bit-exact for span indices and element-to-global DOF maps; <= 1e-12 relative (see
+parity_util.relerr) for basis values, derivatives, Jacobians, integration elements and element matrices.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import igab200  # noqa: F401
+import patches_for_tests as PFT
+import portbind as PT
+from dune_iga_b200 import capi
+from dune_iga_b200 import patchdata as PD
+from parity_util import TOL, oracle_for, port_for, relerr
+
+pytestmark = pytest.mark.gpu
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_literals.json")))
+NAMES = ["curve_p3", "plate_hole_p2", "cylinder_p3", "cylinder_p4", "torus_p2", "square_p3", "mixed_deg_3d"]
+EVAL_FIELDS = ("N", "dN", "d2N", "x", "Jt", "H", "detJ")
+
+
+def gpu_patch(spec, **kw):
+    return capi.Patch(spec["degree"], spec["knots"], spec["cp"], spec["dimworld"], **kw)
+
+
+def gauss(spec, extra=0):
+    return [PD.gaussLegendre01(p + 1 + extra)[0] for p in spec["degree"]]
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("kernel", [capi.KERNEL_GENERIC, capi.KERNEL_AUTO], ids=["generic", "auto"])
+def test_eval_tensor_matches_oracle(name, kernel):
+    spec = PFT.small_patch(name)
+    O, kind = oracle_for(spec)
+    P = gpu_patch(spec)
+    P.setKernel(kernel)
+    xi1d = gauss(spec)
+    ref = O.eval_tensor(xi1d, order=2, want=EVAL_FIELDS)
+    got = P.evalTensor(xi1d, order=2, want=EVAL_FIELDS)
+    for f in EVAL_FIELDS:
+        assert relerr(got[f], ref[f]) <= TOL, (f, kind, relerr(got[f], ref[f]))
+    # partition of unity and derivative sums (gridtests.cpp:787,804)
+    assert np.abs(got["N"].sum(1) - 1.0).max() < 1e-13
+    assert np.abs(got["dN"].sum(1)).max() < 1e-10 * max(1.0, np.abs(got["dN"]).max())
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_eval_tensor_order1_subrange_and_jinvt(name):
+    spec = PFT.small_patch(name)
+    Pp = port_for(spec)
+    P = gpu_patch(spec)
+    xi1d = gauss(spec, extra=1)  # a rule that is NOT p+1 points: exercises the general path
+    eb, ee = Pp.nelem // 3, Pp.nelem - 1
+    ref = Pp.eval_tensor(xi1d, order=1, elem_begin=eb, elem_end=ee)
+    got = P.evalTensor(xi1d, order=1, elem_begin=eb, elem_end=ee)
+    assert "d2N" not in got and "H" not in got
+    for f in ("N", "dN", "x", "Jt", "detJ", "JinvT"):
+        assert relerr(got[f], ref[f]) <= TOL, (f, relerr(got[f], ref[f]))
+    # empty range is legal
+    assert P.evalTensor(xi1d, order=1, elem_begin=2, elem_end=2)["N"].shape[0] == 0
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_integers_bit_exact(name):
+    spec = PFT.small_patch(name)
+    Pp = port_for(spec)
+    P = gpu_patch(spec)
+    assert P.nelem == Pp.nelem and P.nb == Pp.nb
+    assert np.array_equal(P.spans(), Pp.spans())
+    dof, n = P.dofmap()
+    dref, nref = Pp.dofmap()
+    assert n == nref and np.array_equal(dof, dref)
+
+
+def test_dofmap_trim_compaction_bit_exact():
+    spec = PFT.small_patch("square_p3", level=3)
+    Pp = port_for(spec)
+    rng = np.random.default_rng(5)
+    flags = rng.choice([0, 1, 2], size=Pp.nelem, p=[0.5, 0.3, 0.2]).astype(np.uint8)
+    flags[:9] = 1  # make sure a whole corner drops out
+    P = gpu_patch(spec, trimflags=flags)
+    dof, n = P.dofmap()
+    dref, nref = Pp.dofmap(flags)
+    assert n == nref and n < P.ndof_untrimmed
+    keep = flags != 1
+    assert np.array_equal(dof[keep], dref[keep])
+    assert np.array_equal(dof, dref)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_eval_points_corners_and_random(name):
+    """Arbitrary element-local points incl. element corners and corners +- 1e-8, the 13-point pattern of
+    checkJacobianAndPartialConsistency (gridtests.cpp:514-576)."""
+    spec = PFT.small_patch(name)
+    O, kind = oracle_for(spec)
+    P = gpu_patch(spec)
+    rng = np.random.default_rng(42)
+    n = 96
+    elem = rng.integers(0, P.nelem, n).astype(np.int32)
+    elem[:4] = [0, P.nelem - 1, 0, P.nelem - 1]
+    xi = rng.random((n, P.dim))
+    xi[0:2] = 0.0
+    xi[2:4] = 1.0
+    xi[4:12] = 1e-8
+    xi[12:20] = 1 - 1e-8
+    xi[20:28] = (rng.random((8, P.dim)) > 0.5).astype(float)  # random corners
+    ref = O.eval_points(elem, xi, order=2, want=EVAL_FIELDS)
+    got = P.evalPoints(elem, xi, order=2, want=EVAL_FIELDS)
+    for f in EVAL_FIELDS:
+        assert relerr(got[f], ref[f]) <= TOL, (f, kind, relerr(got[f], ref[f]))
+    # evaluateJacobian column d == partial(e_d) to 1e-14 (the reference's own consistency test)
+    for d in range(P.dim):
+        al = [0] * P.dim
+        al[d] = 1
+        part = P.partial(elem, xi, al)
+        assert np.abs(part - got["dN"][:, :, d]).max() <= 1e-14 * max(1.0, np.abs(part).max())
+    # second derivatives through partial as well
+    al = [0] * P.dim
+    al[0] = 2
+    assert relerr(P.partial(elem, xi, al), got["d2N"][:, :, 0]) <= 1e-13
+    assert np.all(np.isfinite(got["d2N"])) and np.all(np.isfinite(got["H"]))  # gridtests.cpp:1085-1124
+
+
+def test_reference_literals_through_cuda():
+    """The reference's known-answer vectors (Appendix B) replayed through the CUDA kernels."""
+    n = G["nurbs2d"]
+    w = np.ones((3, 7))
+    for i in range(3):
+        for j in range(3):
+            w[j, i] = n["weights_3x3_block"][i][j]
+    cp = np.zeros((21, 3))
+    cp[:, 2] = w.reshape(-1)
+    P = capi.Patch(n["degree"], n["knots"], cp, 2)
+    eps = 64 * np.finfo(float).eps
+    # element (0,0) spans [0,0.5] x [0,2]
+    for v in n["values"]:
+        xi = [v["u"][0] / 0.5, v["u"][1] / 2.0]
+        R = P.evalPoints([0], [xi], order=0, want=("N",))["N"][0]
+        assert np.abs(R - np.array(v["R"])).max() <= eps
+        assert abs(R.sum() - 1.0) <= eps
+    xi = [[0.0, 0.1 / 2.0]]
+    for key, val in n["derivatives_at_0_0.1"].items():
+        a, b = map(int, key.split(","))
+        got = P.partial([0], xi, [a, b])[0] / (0.5 ** a * 2.0 ** b)  # undo the element scaling: literals are d/du
+        val = np.array(val)
+        assert np.abs(got - val).max() <= 1e-13 * max(1.0, np.abs(val).max()), key
+    # 1-D B-spline literals: weights 1 => NURBS == B-spline; p=3 knots {0,0,0,0,.5,1,1,2,2,2,2}, u=1.45 in span [1,2]
+    c = G["bspline1d_ders"]
+    P1 = capi.Patch([3], [c["knots"]], np.ones((7, 2)), 1)
+    e = 2  # elements: [0,.5],[.5,1],[1,2]
+    assert P1.nelem == 3
+    for k in range(4):
+        got = P1.partial([e], [[0.45]], [k])[0]
+        assert np.abs(got - np.array(c["dN"][k])).max() <= 1e-13 * max(1.0, np.abs(c["dN"][k]).max())
+    # geometry literals (trimmedgridtests.cpp:38-186); single-element patches => xi == u
+    g = G["geometry_curve"]
+    Pc = capi.Patch(g["degree"], g["knots"], g["cp"], g["dimworld"])
+    for u, x in g["global"]:
+        assert np.abs(Pc.evalPoints([0], [u], order=0, want=("x",))["x"][0] - x).max() <= eps * 8
+    for u, J in g["jacobianTransposed"]:
+        assert np.abs(Pc.evalPoints([0], [u], order=1, want=("Jt",))["Jt"][0] - J).max() <= eps * 64
+    s = G["geometry_surface"]
+    cps = np.array([[s["cp_table_ij"][i][j] for i in range(3)] for j in range(3)], float).reshape(9, 4)
+    Ps = capi.Patch(s["degree"], s["knots"], cps, 3)
+    for u, x in s["global"]:
+        assert np.abs(Ps.evalPoints([0], [u], order=0, want=("x",))["x"][0] - x).max() <= eps * 4
+    for u, J in s["jacobianTransposed"]:
+        assert np.abs(Ps.evalPoints([0], [u], order=1, want=("Jt",))["Jt"][0] - J).max() <= eps * 4
+
+
+def test_torus_invariants_through_cuda():
+    """gridtests.cpp:338-363 on the GPU: area = 4 pi^2 r R (1e-4), Gauss-Bonnet (1e-5), curvature bounds."""
+    t = G["torus"]
+    spec = PFT.small_patch("torus_p2", level=2)
+    P = gpu_patch(spec)
+    x, w = PD.gaussLegendre01(3)
+    area = P.volume([x, x], [w, w])
+    assert abs(area - 4 * np.pi ** 2 * t["r"] * t["R"]) < t["area_tol"]
+    o = P.evalTensor([x, x], order=2, want=("Jt", "H", "detJ"))
+    J, H, det = o["Jt"], o["H"], o["detJ"]
+    nrm = np.cross(J[:, 0], J[:, 1])
+    nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    b00, b11, b01 = (H[:, 0] * nrm).sum(1), (H[:, 1] * nrm).sum(1), (H[:, 2] * nrm).sum(1)
+    g00, g11, g01 = (J[:, 0] ** 2).sum(1), (J[:, 1] ** 2).sum(1), (J[:, 0] * J[:, 1]).sum(1)
+    K = (b00 * b11 - b01 ** 2) / (g00 * g11 - g01 ** 2)
+    ww = np.tile(np.outer(w, w).reshape(-1), P.nelem)
+    assert abs((K * det * ww).sum()) < t["gauss_bonnet_tol"]
+    r, R = t["r"], t["R"]
+    assert K.min() >= -1 / (r * (R - r)) - 1e-8 and K.max() <= 1 / (r * (R + r)) + 1e-8
+
+
+@pytest.mark.parametrize("name,kind", [("plate_hole_p2", capi.ASM_POISSON), ("plate_hole_p2", capi.ASM_MASS),
+                                       ("plate_hole_p2", capi.ASM_ELASTICITY), ("cylinder_p3", capi.ASM_POISSON),
+                                       ("cylinder_p3", capi.ASM_ELASTICITY), ("cylinder_p4", capi.ASM_POISSON),
+                                       ("torus_p2", capi.ASM_POISSON), ("square_p3", capi.ASM_MASS)])
+def test_element_matrices_match_oracle(name, kind):
+    spec = PFT.small_patch(name)
+    Pp = port_for(spec)
+    P = gpu_patch(spec)
+    rule = [PD.gaussLegendre01(p + 1) for p in spec["degree"]]
+    xi1d, w1d = [r[0] for r in rule], [r[1] for r in rule]
+    D = None
+    if kind == capi.ASM_ELASTICITY:
+        E, nu = 1.0, 0.3
+        lam, mu = E * nu / ((1 + nu) * (1 - 2 * nu)), E / (2 * (1 + nu))
+        if P.dim == 2:
+            D = np.array([[lam + 2 * mu, lam, 0], [lam, lam + 2 * mu, 0], [0, 0, mu]])
+        else:
+            D = np.zeros((6, 6))
+            D[:3, :3] = lam
+            D[np.arange(3), np.arange(3)] = lam + 2 * mu
+            D[np.arange(3, 6), np.arange(3, 6)] = mu
+    ne = min(Pp.nelem, 24)
+    Kref, fref = Pp.assemble(kind, xi1d, w1d, D=D, fconst=1.5, elem_end=ne)
+    K, f = P.assemble(kind, xi1d, w1d, D=D, fconst=1.5, elem_end=ne)
+    assert relerr(K.reshape(ne, -1), Kref.reshape(ne, -1)) <= TOL, relerr(K.reshape(ne, -1), Kref.reshape(ne, -1))
+    assert relerr(f, fref) <= TOL
+    assert np.abs(K - K.transpose(0, 2, 1)).max() <= 1e-12 * np.abs(K).max()
+
+
+@pytest.mark.parametrize("name", ["plate_hole_p2", "cylinder_p3", "torus_p2"])
+def test_volume_matches_oracle_and_is_reproducible(name):
+    spec = PFT.small_patch(name)
+    Pp = port_for(spec)
+    P = gpu_patch(spec)
+    rule = [PD.gaussLegendre01(p + 1) for p in spec["degree"]]
+    xi1d, w1d = [r[0] for r in rule], [r[1] for r in rule]
+    v = P.volume(xi1d, w1d)
+    assert abs(v - Pp.volume(xi1d, w1d)) <= 1e-12 * abs(v)
+    assert P.volume(xi1d, w1d) == v  # deterministic tree: bitwise reproducible
+    half = P.nelem // 2
+    assert abs(P.volume(xi1d, w1d, 0, half) + P.volume(xi1d, w1d, half, P.nelem) - v) <= 1e-13 * abs(v)
+
+
+def test_full_size_properties_c1():
+    """BASELINE config 1 at full size (256 x 256 elements, p=2, 3x3 Gauss): properties that need no oracle run --
+    partition of unity, sum of gradients = 0, detJ > 0, area = 16 - pi/4, J consistent with finite differences of x,
+    plus the oracle on a random sample of elements."""
+    Pd = PD.plateWithHole(7, 8)
+    assert Pd.elementsPerDirection == [256, 256]
+    P = capi.Patch.fromPatchData(Pd)
+    x, w = PD.gaussLegendre01(3)
+    o = P.evalTensor([x, x], order=1, want=("N", "dN", "x", "Jt", "detJ"))
+    assert o["N"].shape == (256 * 256 * 9, 9)
+    assert np.abs(o["N"].sum(1) - 1).max() < 1e-13
+    assert np.abs(o["dN"].sum(1)).max() < 1e-12
+    assert o["detJ"].min() > 0
+    area = P.volume([x, x], [w, w])
+    assert abs(area - (16 - np.pi / 4)) < 1e-9
+    Pp = PT.PortPatch(Pd.degree, Pd.knotSpans, Pd.cp, 2)
+    rng = np.random.default_rng(3)
+    for e in rng.integers(0, P.nelem, 40):
+        ref = Pp.eval_tensor([x, x], order=1, elem_begin=int(e), elem_end=int(e) + 1)
+        sl = slice(int(e) * 9, int(e) * 9 + 9)
+        for f in ("N", "dN", "x", "Jt", "detJ"):
+            assert relerr(o[f][sl], ref[f]) <= TOL, f
+
+
+def test_device_pointers_in_place():
+    """IGAB_DEVICE outputs: results land in caller-owned device memory on the caller's stream."""
+    import torch
+    spec = PFT.small_patch("cylinder_p3")
+    P = gpu_patch(spec)
+    xi1d = gauss(spec)
+    npts = P.nelem * 64
+    sh = P.shapes(npts)
+    out = {f: torch.empty(sh[f], dtype=torch.float64, device="cuda") for f in ("N", "dN", "x", "Jt", "detJ")}
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        P.evalTensor(xi1d, order=1, want=tuple(out), out=out, stream=s.cuda_stream)
+    s.synchronize()
+    host = P.evalTensor(xi1d, order=1, want=tuple(out))
+    for f in out:
+        assert np.array_equal(out[f].cpu().numpy(), host[f]), f
+
+
+def test_error_behaviour():
+    spec = PFT.small_patch("plate_hole_p2")
+    P = gpu_patch(spec)
+    x = PD.gaussLegendre01(3)[0]
+    with pytest.raises(capi.IgabError) as ei:
+        P.evalTensor([x, x], elem_begin=0, elem_end=P.nelem + 1)
+    assert ei.value.status == 1
+    with pytest.raises(capi.IgabError):
+        P.evalPoints([P.nelem], [[0.5, 0.5]])
+    with pytest.raises(capi.IgabError):
+        P.evalTensor([x, x], order=3)
+    with pytest.raises(capi.IgabError):
+        P.partial([0], [[0.5, 0.5]], [70, 0])
