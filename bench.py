@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json): quadrature-point basis+Jacobian evaluations per
+second on config C2 (3-D thick-walled cylinder patch, p=3, 128^3 elements per GPU, 4^3 Gauss points; outputs N, dN, x,
+Jt, detJ for every point).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the evaluation over ALL 2,097,152 elements (134,217,728 points) owned by the rank, issued as
+element-block launches that write into a ring of device output buffers (the full output, 289 GB, does not fit HBM).
+Weak scaling: the N-GPU patch has 128 x 128 x 128N elements, rank r owns the k-slab [128r, 128r+128) (knot-span blocks,
+SURVEY.md 8e); knots / control net are replicated; no data-path collective.
+
+Prints ONE JSON line (rank 0).  torch is used only for device buffers, the stream handed to the C-ABI, CUDA events and
+torch.distributed plumbing; the compute is dune-iga_b200/libigab200.so.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P_DEG, NQ1, LEVEL = 3, 4, 7           # C2: p=3, 4^3 Gauss points, 2^7 = 128 elements per direction
+LAYERS_PER_LAUNCH = 8                 # k-layers of elements per launch (131,072 elements, 18 GB of output)
+FIELDS = ("N", "dN", "x", "Jt", "detJ")
+NB = (P_DEG + 1) ** 3
+NQ = NQ1 ** 3
+# algorithmic bytes per point, SURVEY.md 8(d): outputs written once + the element's control points read once / nq
+ALG_BYTES_PER_PT = 8 * (NB * (1 + 3) + 3 + 9 + 1) + 8 * NB * 4 // NQ
+
+
+def measured_peak_hbm():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+        "clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except Exception:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_patch(n_gpus):
+    import igab200  # noqa: F401
+    from dune_iga_b200 import patchdata as PD
+    extra = int(np.log2(n_gpus))
+    assert 2 ** extra == n_gpus, "gpus must be a power of two"
+    return PD.thickCylinder(P_DEG, (LEVEL, LEVEL, LEVEL + extra))
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref = the reference headers
+    compiled where they lie; falls back to the pinned C restatement), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import igab200  # noqa: F401
+    from dune_iga_b200 import patchdata as PD
+    import refbind as RF
+    import portbind as PT
+    pd = build_patch(args.gpus)
+    if RF.available():
+        O, kind = RF.RefPatch.create(pd.degree, pd.knotSpans, pd.cp, 3), "reference"
+    else:
+        O, kind = PT.PortPatch(pd.degree, pd.knotSpans, pd.cp, 3), "port"
+    xi = [PD.gaussLegendre01(NQ1)[0]] * 3
+    layers = 1  # 16,384 elements = 1,048,576 points per step
+    nel = 128 * 128 * layers
+    for _ in range(args.warmup):
+        O.eval_tensor(xi, order=1, elem_begin=0, elem_end=nel, want=FIELDS)
+    t0 = time.perf_counter()
+    threads = 1
+    for s in range(args.steps):
+        eb = (s % 64) * nel
+        threads = O.eval_tensor(xi, order=1, elem_begin=eb, elem_end=eb + nel, want=FIELDS)["threads"]
+    dt = time.perf_counter() - t0
+    val = args.steps * nel * NQ / dt
+    sample = "%d k-layer(s) of the C2 patch per step (%d elements, %d points), outputs %s" % (
+        layers, nel, nel * NQ, "+".join(FIELDS))
+    print(json.dumps({
+        "impl": "reference", "metric": "quad-pt basis+Jacobian evals/sec", "value": val, "unit": "points/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "points/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def config_dict(n):
+    return {"workload": "C2: 3-D thick-walled quarter cylinder NURBS patch p=3, 128x128x%d elements (128^3 per GPU), "
+                        "4^3 Gauss points, order-1 outputs N+dN+x+Jt+detJ" % (128 * n),
+            "elements_per_gpu": 128 ** 3, "points_per_gpu": 128 ** 3 * NQ, "bytes_per_point": ALG_BYTES_PER_PT,
+            "elements_per_launch": 128 * 128 * LAYERS_PER_LAUNCH,
+            "l2": "each launch writes 18 GB and reads a 72 MB control net: working set >> 126 MB L2, no flush needed",
+            "parallelism": "element k-slabs, %d rank(s), no collective" % n}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import igab200  # noqa: F401
+    from dune_iga_b200 import capi, patchdata as PD
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    pd = build_patch(world)
+    P = capi.Patch.fromPatchData(pd)
+    assert P.nelem == 128 * 128 * 128 * world
+    P.setKernel(capi.KERNEL_TENSOR)  # fail loudly if the tuned kernel is not the one running
+    gx = PD.gaussLegendre01(NQ1)[0]
+    xi = [gx, gx, gx]
+    el_per_launch = 128 * 128 * LAYERS_PER_LAUNCH
+    pts_per_launch = el_per_launch * NQ
+    launches_per_step = 128 // LAYERS_PER_LAUNCH
+    my_begin = rank * 128 ** 3
+    sh = P.shapes(pts_per_launch)
+    ring = [{f: torch.empty(sh[f], dtype=torch.float64, device="cuda") for f in FIELDS} for _ in range(2)]
+    stream = torch.cuda.current_stream()
+
+    def step(evs=None):
+        for j in range(launches_per_step):
+            eb = my_begin + j * el_per_launch
+            if evs is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream)
+                evs.append(e)
+            P.evalTensor(xi, order=1, elem_begin=eb, elem_end=eb + el_per_launch, want=FIELDS, out=ring[j & 1],
+                         stream=stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = capi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = []  # one event before every launch of the timed region -> per-launch durations of the dominant kernel
+    barrier()
+    t_wall0 = time.time()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step(evs)
+    ev1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    launches = capi.launch_count() - l0
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    evs.append(ev1)
+    per_launch = np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(len(evs) - 1)])
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    pts_per_step = 128 ** 3 * NQ * world
+    value = pts_per_step * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (eval_sf3d_kernel<3,4>, > 99 % of the step, profiles/launches_r01.csv):
+    # average launch duration over the timed region, CUDA events on the launch stream (each interval = 1 main kernel
+    # + 3 table kernels of ~6 us)
+    k_ms = float(per_launch.mean())
+    peak, peak_src = measured_peak_hbm()
+    achieved = ALG_BYTES_PER_PT * pts_per_launch / (k_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["eval_sf3d_p3q4_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "eval_sf3d_kernel<3,4>", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, copy read+write)",
+                "algorithmic_bytes_per_launch": ALG_BYTES_PER_PT * pts_per_launch, "ms_per_launch": k_ms,
+                "ms_per_launch_min_median_max": [float(per_launch.min()), float(np.median(per_launch)),
+                                                 float(per_launch.max())],
+                "launches_timed": int(len(per_launch))}
+
+    # ---- e2e through the C-ABI with HOST buffers (rank-local; control net H2D + all outputs D2H inside the region)
+    e2e = None
+    if not args.no_e2e:
+        e_layers = 2
+        e_el = 128 * 128 * e_layers
+        e_pts = e_el * NQ
+        hs = P.shapes(e_pts)
+        host = {f: capi.pinned_empty(hs[f]) for f in FIELDS}
+        cp_host = capi.pinned_empty(pd.cp.shape)
+        cp_host[...] = pd.cp
+        d2h = sum(int(np.prod(hs[f])) * 8 for f in FIELDS)
+        h2d = cp_host.nbytes
+
+        def e2e_step(s):
+            P.updateControlPoints(cp_host)
+            eb = my_begin + (s % 32) * e_el
+            P.evalTensor(xi, order=1, elem_begin=eb, elem_end=eb + e_el, want=FIELDS, out=host)
+            return float(host["detJ"][0])
+
+        e2e_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(3, min(args.steps, 5))
+        for s in range(n_e2e):
+            e2e_step(s)
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": e_pts * n_e2e * world / dt, "unit": "points/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h,
+               "sample": "%d k-layers per rank per e2e step (%d points), control net H2D + all outputs D2H to pinned "
+                         "host memory through igab_eval_tensor(IGAB_HOST); PCIe-bound" % (e_layers, e_pts)}
+        for f in FIELDS:
+            capi.pinned_free(host[f])
+        capi.pinned_free(cp_host)
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the reference's own headers (oracle/_ref), all host threads
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import refbind as RF
+        import portbind as PT
+        if RF.available():
+            O, kind = RF.RefPatch.create(pd.degree, pd.knotSpans, pd.cp, 3), "reference"
+        else:
+            O, kind = PT.PortPatch(pd.degree, pd.knotSpans, pd.cp, 3), "port"
+        c_layers = 4
+        c_el = 128 * 128 * c_layers
+        O.eval_tensor(xi, order=1, elem_begin=0, elem_end=128 * 16, want=FIELDS)  # warm
+        t0 = time.perf_counter()
+        r = O.eval_tensor(xi, order=1, elem_begin=0, elem_end=c_el, want=FIELDS)
+        dt = time.perf_counter() - t0
+        cpu = {"value": c_el * NQ / dt, "unit": "points/s", "cores": r["threads"], "kind": kind,
+               "sample": "%d k-layers of the same patch (%d elements, %d points), same outputs, %.1f s wall" % (
+                   c_layers, c_el, c_el * NQ, dt)}
+        del r
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "quad-pt basis+Jacobian evals/sec", "value": value, "unit": "points/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(world),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,61 @@
+// Univariate B-spline device routines shared by the kernels.
+//   ders1d_any: The NURBS Book A2.3 as the reference implements it, BsplineBasis1D::basisFunctionDerivatives,
+//               dune/iga/bsplinealgorithms.hh:148-222 (ndu triangle :161-173, a-rows :178-213, factors :216-220).
+#pragma once
+#include "igab_internal.cuh"
+
+namespace igab {
+
+constexpr int kPM = kMaxOrder1D;  // 9: row length of every univariate work array
+
+// values + derivatives 0..K of the p+1 non-zero B-splines of span sp at u.  dN[k*kPM + j].  K may exceed p (rows = 0).
+__device__ inline void ders1d_any(double u, const double* __restrict__ U, int p, int sp, int K, double* dN) {
+  double left[kPM], right[kPM], ndu[kPM][kPM], a[2][kPM];
+  ndu[0][0] = 1.0;
+  for (int j = 1; j <= p; ++j) {
+    left[j] = u - U[sp + 1 - j];
+    right[j] = U[sp + j] - u;
+    double saved = 0.0;
+    for (int r = 0; r < j; ++r) {
+      ndu[j][r] = right[r + 1] + left[j - r];
+      const double temp = ndu[r][j - 1] / ndu[j][r];
+      ndu[r][j] = saved + right[r + 1] * temp;
+      saved = left[j - r] * temp;
+    }
+    ndu[j][j] = saved;
+  }
+  for (int j = 0; j <= p; ++j) dN[j] = ndu[j][p];
+  for (int r = 0; r <= p; ++r) {
+    int s1 = 0, s2 = 1;
+    a[0][0] = 1.0;
+    for (int k = 1; k <= K; ++k) {
+      double d = 0.0;
+      const int rk = r - k, pk = p - k;
+      if (k <= p) {
+        if (r >= k) {
+          a[s2][0] = a[s1][0] / ndu[pk + 1][rk];
+          d = a[s2][0] * ndu[rk][pk];
+        }
+        const int j1 = (rk >= -1) ? 1 : -rk;
+        const int j2 = (r - 1 <= pk) ? k - 1 : p - r;
+        for (int j = j1; j <= j2; ++j) {
+          a[s2][j] = (a[s1][j] - a[s1][j - 1]) / ndu[pk + 1][rk + j];
+          d += a[s2][j] * ndu[rk + j][pk];
+        }
+        if (r <= pk) {
+          a[s2][k] = -a[s1][k - 1] / ndu[pk + 1][r];
+          d += a[s2][k] * ndu[r][pk];
+        }
+      }
+      dN[k * kPM + r] = d;
+      const int t = s1; s1 = s2; s2 = t;
+    }
+  }
+  int fac = p;
+  for (int k = 1; k <= K; ++k) {
+    for (int j = 0; j <= p; ++j) dN[k * kPM + j] *= fac;
+    fac *= (p - k);
+  }
+}
+
+}  // namespace igab

@@ -12,13 +12,14 @@
 //   local scaling   nurbsbasis.hh:88-95,101-107; nurbsgeometry.hh:365-378
 // HBM-bound on its stores (thread-per-point stores are sector-complete but not line-coalesced); the tuned tensor
 // kernel is the one measured against the roofline.
+#include "bspline_device.cuh"
 #include "igab_internal.cuh"
 
 namespace igab {
 
 namespace {
 
-constexpr int PM = kMaxOrder1D;  // 9
+constexpr int PM = kPM;  // 9
 
 __device__ __forceinline__ bool feq8(double a, double b) {
   // Dune::FloatCmp::eq default (relativeWeak, 8 eps) -- bsplinealgorithms.hh:104-108
@@ -417,55 +418,6 @@ igab_status launch_eval_generic(const PatchDev& P, const PointSource& src, long 
 // see oracle/igab_oracle.c igo_nurbs_ders for the one deviation from the reference's loop).
 namespace {
 constexpr int kMaxG = 64;
-
-__device__ void ders1d_any(double u, const double* __restrict__ U, int p, int sp, int K, double* dN /*[K+1][PM]*/) {
-  double left[PM], right[PM], ndu[PM][PM], a[2][PM];
-  ndu[0][0] = 1.0;
-  for (int j = 1; j <= p; ++j) {
-    left[j] = u - U[sp + 1 - j];
-    right[j] = U[sp + j] - u;
-    double saved = 0.0;
-    for (int r = 0; r < j; ++r) {
-      ndu[j][r] = right[r + 1] + left[j - r];
-      const double temp = ndu[r][j - 1] / ndu[j][r];
-      ndu[r][j] = saved + right[r + 1] * temp;
-      saved = left[j - r] * temp;
-    }
-    ndu[j][j] = saved;
-  }
-  for (int j = 0; j <= p; ++j) dN[j] = ndu[j][p];
-  for (int r = 0; r <= p; ++r) {
-    int s1 = 0, s2 = 1;
-    a[0][0] = 1.0;
-    for (int k = 1; k <= K; ++k) {
-      double d = 0.0;
-      const int rk = r - k, pk = p - k;
-      if (k <= p) {
-        if (r >= k) {
-          a[s2][0] = a[s1][0] / ndu[pk + 1][rk];
-          d = a[s2][0] * ndu[rk][pk];
-        }
-        const int j1 = (rk >= -1) ? 1 : -rk;
-        const int j2 = (r - 1 <= pk) ? k - 1 : p - r;
-        for (int j = j1; j <= j2; ++j) {
-          a[s2][j] = (a[s1][j] - a[s1][j - 1]) / ndu[pk + 1][rk + j];
-          d += a[s2][j] * ndu[rk + j][pk];
-        }
-        if (r <= pk) {
-          a[s2][k] = -a[s1][k - 1] / ndu[pk + 1][r];
-          d += a[s2][k] * ndu[r][pk];
-        }
-      }
-      dN[k * PM + r] = d;
-      const int t = s1; s1 = s2; s2 = t;
-    }
-  }
-  int fac = p;
-  for (int k = 1; k <= K; ++k) {
-    for (int j = 0; j <= p; ++j) dN[k * PM + j] *= fac;
-    fac *= (p - k);
-  }
-}
 
 __device__ __forceinline__ double binom_d(int n, int k) {
   double r = 1.0;

@@ -1,9 +1,442 @@
-// placeholder until the sum-factorised kernel lands
+// eval_tensor_sf.cu -- the tuned evaluation path for tensor quadrature rules (K1 + K2 of SURVEY.md 2).
+//
+// What it replaces: the user loop "for element: for gauss point: evaluateFunction / evaluateJacobian / global /
+// jacobianTransposed / integrationElement" (dune/iga/nurbsbasis.hh:77-96, dune/iga/nurbsgeometry.hh:133-138,182-203),
+// i.e. per point Nurbs<dim>::basisFunctionDerivatives (dune/iga/nurbsalgorithms.hh:193-250) + dim dots.
+//
+// B200 design (not a port of the per-point algorithm):
+//  K1  univariate tables: for every direction d, element e_d and abscissa q the p+1 non-zero B-splines and their first
+//      derivative (A2.3, bsplinealgorithms.hh:148-222), derivative pre-multiplied by the span length so that all later
+//      arithmetic is in element-local (xi) coordinates (nurbsbasis.hh:93-95, nurbsgeometry.hh:189-194).
+//      n_el_d * Q * (p+1) * 2 doubles per direction -- computed once per call, lives in L2.
+//  K2  one WARP per element, persistent over elements:
+//      (1) the element's (p+1)^3 control points (x,y,z,w) are fetched with 16-byte vector loads (rows of p+1
+//          consecutive points are contiguous) and kept in shared memory in homogeneous form (wx, wy, wz, w);
+//      (2) geometry by SUM FACTORISATION of the homogeneous net: G^(a)(q) = sum_i dN^(a)_i(q) (wP_i, w_i) for
+//          a in {0, e0, e1, e2}, three 1-D contractions through shared memory (O(p^4) instead of O(p^6) per element);
+//          then x = C/W, J_d = (C_d - W_d x)/W (quotient rule on the geometry), detJ = |det J|, J^-T;
+//      (3) basis functions: lane <-> basis function i (i = lane + 32 k), loop over the Q^3 points with the three
+//          univariate rows of the lane held in registers:  R_i = w_i N0 N1 N2 / W,
+//          dR_i/dxi_d = (w_i d_d(N0 N1 N2) - W_d R_i)/W  (nurbsalgorithms.hh:226-248 for |alpha| = 1);
+//      (4) stores: N as 256-byte coalesced rows straight from registers; dN [i][d]-interleaved rows are transposed
+//          through a 768-byte shared-memory slab so that every store instruction writes full 32-byte sectors of
+//          consecutive addresses; x / Jt / detJ / JinvT staged per 32 points and flushed as contiguous runs.
+//  The pass is bound by HBM writes (2,152 B per point at p=3, 4^3 points); FP64 work is ~15 DP instructions per
+//  (point, basis function), i.e. < 25 % of the DP pipe at the HBM roofline.
+#include "bspline_device.cuh"
 #include "igab_internal.cuh"
+
 namespace igab {
-bool eval_tensor_sf_supported(const PatchDev&, const int*, int, const EvalOutDev&) { return false; }
-igab_status launch_eval_tensor_sf(const PatchDev&, const PointSource&, long long, int, const EvalOutDev&, cudaStream_t) {
-  set_error("no sum-factorised kernel");
-  return IGAB_UNSUPPORTED;
+
+namespace {
+
+// ---- K1 ---------------------------------------------------------------------------------------------------------------
+// tab[d] layout: [e_d][q][i][a], a = 0 value, a = 1 d/dxi ; one thread per (e_d, q)
+__global__ void tables_kernel(PatchDev P, int d, int nq, const double* __restrict__ xi, double* __restrict__ tab) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P.nel[d] * nq) return;
+  const int e = t / nq, q = t % nq;
+  const int p = P.degree[d];
+  const int sp = P.spanTab[d][e];
+  const double* U = P.knots[d];
+  const double lo = U[sp], scale = U[sp + 1] - lo;
+  const double u = xi[q] * scale + lo;  // nurbsgeometry.hh:365-378
+  double dN[2 * kPM];
+  ders1d_any(u, U, p, sp, 1, dN);
+  double* o = tab + ((size_t)t * (p + 1)) * 2;
+  for (int i = 0; i <= p; ++i) {
+    o[2 * i] = dN[i];
+    o[2 * i + 1] = dN[kPM + i] * scale;
+  }
 }
+
+template <int P, int Q>
+struct Cfg {
+  static constexpr int NB1 = P + 1;
+  static constexpr int NB = NB1 * NB1 * NB1;
+  static constexpr int NQ = Q * Q * Q;
+  static constexpr int KS = (NB + 31) / 32;     // basis slots per lane
+  static constexpr int PS = (NQ + 31) / 32;     // point slots per lane
+  static constexpr int TAB = Q * NB1 * 2;       // doubles per direction
+  // shared-memory layout per warp (in doubles)
+  static constexpr int HS = 4 * NB1 + 1;        // stride of H over i12 = i1 + NB1 i2 (odd: conflict-free stage-1 reads)
+  static constexpr int S1C = NB1 * NB1 + 1;     // stride of S1 over c
+  static constexpr int S2S = NB1 | 1;           // stride of S2 over q01 (odd)
+  static constexpr int ev(int x) { return (x + 1) & ~1; }  // regions stay 16-byte aligned
+  static constexpr int SZ_T = 3 * TAB;
+  static constexpr int SZ_W = ev(NB);           // weights by local index
+  static constexpr int SZ_H = ev(NB1 * NB1 * HS);
+  static constexpr int SZ_S1 = 2 * Q * 4 * S1C;
+  static constexpr int SZ_G = 16 * NQ;          // [alpha(4)][c(4)][pt]
+  static constexpr int SZ_D = 2 * 96;           // dN transposition slabs
+  static constexpr int SZ_A = ev((SZ_H + SZ_S1) > (SZ_G) ? (SZ_H + SZ_S1) : (SZ_G));
+  static constexpr int SZ_S2 = 3 * 4 * Q * Q * S2S;
+  static constexpr int SZ_C = 4 * NQ;           // invW, W_0, W_1, W_2 per point
+  static constexpr int SZ_ST = 32 * 9;          // staging of one geometry field for 32 points
+  static constexpr int SZ_B = ev(SZ_S2 > (SZ_C + SZ_ST + SZ_D) ? SZ_S2 : (SZ_C + SZ_ST + SZ_D));
+  static constexpr int SZ_WARP = ev(SZ_T + SZ_W + SZ_A + SZ_B);
+};
+
+__device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+// coalesced copy of n doubles from shared memory to global memory by one warp
+__device__ __forceinline__ void warp_flush(double* __restrict__ dst, const double* __restrict__ src, int n, int lane) {
+  for (int j = lane; j < n; j += 32) dst[j] = src[j];
+}
+
+template <int P, int Q>
+__global__ void __launch_bounds__(128) eval_sf3d_kernel(PatchDev Pd, long long elem_begin, long long nelem,
+                                                        const double* __restrict__ tab0,
+                                                        const double* __restrict__ tab1,
+                                                        const double* __restrict__ tab2, EvalOutDev out) {
+  using C = Cfg<P, Q>;
+  constexpr int NB1 = C::NB1, NB = C::NB, NQ = C::NQ, Q2 = Q * Q;
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31;
+  const int warpInBlock = threadIdx.x >> 5;
+  double* const sT = smem + (size_t)warpInBlock * C::SZ_WARP;
+  double* const sW = sT + C::SZ_T;
+  double* const rA = sW + C::SZ_W;
+  double* const rB = rA + C::SZ_A;
+  double* const sH = rA;               // stage 1 input
+  double* const sS1 = rA + C::SZ_H;    // stage 1 output
+  double* const sG = rA;               // stage 3 output (H, S1 dead by then)
+  double* const sS2 = rB;              // stage 2 output
+  double* const sC = rB;               // after stage 3 (S2 dead)
+  double* const sSt = rB + C::SZ_C;
+  double* const sD = sSt + C::SZ_ST;
+
+  const long long warpsTotal = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long warpId = (long long)blockIdx.x * (blockDim.x >> 5) + warpInBlock;
+
+  for (long long el = warpId; el < nelem; el += warpsTotal) {
+    const long long e = elem_begin + el;
+    int e0, e1, e2;
+    {
+      long long h = e;
+      e0 = (int)(h % Pd.nel[0]); h /= Pd.nel[0];
+      e1 = (int)(h % Pd.nel[1]); h /= Pd.nel[1];
+      e2 = (int)h;
+    }
+    // ---- (0) univariate tables of this element -> shared
+    {
+      const double* t0 = tab0 + (size_t)e0 * C::TAB;
+      const double* t1 = tab1 + (size_t)e1 * C::TAB;
+      const double* t2 = tab2 + (size_t)e2 * C::TAB;
+      for (int j = lane; j < C::TAB; j += 32) {
+        sT[j] = __ldg(t0 + j);
+        sT[C::TAB + j] = __ldg(t1 + j);
+        sT[2 * C::TAB + j] = __ldg(t2 + j);
+      }
+    }
+    // ---- (1) control points -> homogeneous, shared  (netOfSpan: start = span - degree, nurbsalgorithms.hh:80-89)
+    {
+      const int b0 = Pd.spanTab[0][e0] - P, b1 = Pd.spanTab[1][e1] - P, b2 = Pd.spanTab[2][e2] - P;
+      const long long n0 = Pd.ncp[0], n1 = Pd.ncp[1];
+      const double2* cp2 = reinterpret_cast<const double2*>(Pd.cp);
+#pragma unroll
+      for (int k = 0; k < C::KS; ++k) {
+        const int i = lane + 32 * k;
+        if (i < NB) {
+          const int i0 = i % NB1, i12 = i / NB1, i1 = i12 % NB1, i2 = i12 / NB1;
+          const long long g = (b0 + i0) + n0 * ((b1 + i1) + n1 * (long long)(b2 + i2));
+          const double2 xy = __ldg(cp2 + 2 * g), zw = __ldg(cp2 + 2 * g + 1);
+          double* h = sH + i12 * C::HS + 4 * i0;
+          h[0] = xy.x * zw.y;
+          h[1] = xy.y * zw.y;
+          h[2] = zw.x * zw.y;
+          h[3] = zw.y;
+          sW[i] = zw.y;
+        }
+      }
+    }
+    __syncwarp();
+    // ---- (2a) stage 1: S1[a0][q0][c][i12] = sum_i0 T0[q0][i0][a0] H[i12][i0][c]
+    {
+      constexpr int NCOL = 4 * NB1 * NB1;
+      for (int col = lane; col < NCOL; col += 32) {
+        const int i12 = col % (NB1 * NB1), c = col / (NB1 * NB1);
+        double h[NB1];
+#pragma unroll
+        for (int i0 = 0; i0 < NB1; ++i0) h[i0] = sH[i12 * C::HS + 4 * i0 + c];
+#pragma unroll
+        for (int q0 = 0; q0 < Q; ++q0) {
+          double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+          for (int i0 = 0; i0 < NB1; ++i0) {
+            const double2 t = lds2(sT + (q0 * NB1 + i0) * 2);
+            a0 = fma(t.x, h[i0], a0);
+            a1 = fma(t.y, h[i0], a1);
+          }
+          sS1[((0 * Q + q0) * 4 + c) * C::S1C + i12] = a0;
+          sS1[((1 * Q + q0) * 4 + c) * C::S1C + i12] = a1;
+        }
+      }
+    }
+    __syncwarp();
+    // ---- (2b) stage 2: S2[a01][c][q0 + Q q1][i2] = sum_i1 T1[q1][i1][a1] S1[a0][q0][c][i1 + NB1 i2]
+    //      a01: 0 = (0,0), 1 = (1,0), 2 = (0,1)
+    {
+      constexpr int NCOL = 2 * Q * 4 * NB1;
+      for (int col = lane; col < NCOL; col += 32) {
+        int r = col;
+        const int i2 = r % NB1; r /= NB1;
+        const int c = r % 4; r /= 4;
+        const int q0 = r % Q;
+        const int a0 = r / Q;
+        double s[NB1];
+#pragma unroll
+        for (int i1 = 0; i1 < NB1; ++i1) s[i1] = sS1[((a0 * Q + q0) * 4 + c) * C::S1C + i1 + NB1 * i2];
+#pragma unroll
+        for (int q1 = 0; q1 < Q; ++q1) {
+          double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+          for (int i1 = 0; i1 < NB1; ++i1) {
+            const double2 t = lds2(sT + C::TAB + (q1 * NB1 + i1) * 2);
+            v0 = fma(t.x, s[i1], v0);
+            v1 = fma(t.y, s[i1], v1);
+          }
+          const int q01 = q0 + Q * q1;
+          if (a0 == 0) {
+            sS2[((0 * 4 + c) * Q2 + q01) * C::S2S + i2] = v0;
+            sS2[((2 * 4 + c) * Q2 + q01) * C::S2S + i2] = v1;
+          } else {
+            sS2[((1 * 4 + c) * Q2 + q01) * C::S2S + i2] = v0;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // ---- (2c) stage 3: G[alpha][c][q01 + Q^2 q2] = sum_i2 T2[q2][i2][a2] S2[a01][c][q01][i2]
+    //      alpha: 0 = value, 1 = d/dxi0, 2 = d/dxi1, 3 = d/dxi2
+    {
+      constexpr int NCOL = 3 * 4 * Q2;
+      for (int col = lane; col < NCOL; col += 32) {
+        int r = col;
+        const int q01 = r % Q2; r /= Q2;
+        const int c = r % 4;
+        const int a01 = r / 4;
+        double s[NB1];
+#pragma unroll
+        for (int i2 = 0; i2 < NB1; ++i2) s[i2] = sS2[((a01 * 4 + c) * Q2 + q01) * C::S2S + i2];
+#pragma unroll
+        for (int q2 = 0; q2 < Q; ++q2) {
+          double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+          for (int i2 = 0; i2 < NB1; ++i2) {
+            const double2 t = lds2(sT + 2 * C::TAB + (q2 * NB1 + i2) * 2);
+            v0 = fma(t.x, s[i2], v0);
+            v1 = fma(t.y, s[i2], v1);
+          }
+          const int pt = q01 + Q2 * q2;
+          if (a01 == 0) {
+            sG[(0 * 4 + c) * NQ + pt] = v0;
+            sG[(3 * 4 + c) * NQ + pt] = v1;
+          } else {
+            sG[(a01 * 4 + c) * NQ + pt] = v0;  // a01 = 1 -> alpha 1 ; a01 = 2 -> alpha 2
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // ---- (3) per point: x = C/W, J_d = (C_d - W_d x)/W, detJ, J^-T ; constants for (4)
+    const long long ptBase = el * NQ;
+#pragma unroll 1
+    for (int m = 0; m < C::PS; ++m) {
+      const int pt = lane + 32 * m;
+      const int nvalid = min(32, NQ - 32 * m);
+      double x[3], J[3][3], det = 0.0;
+      if (pt < NQ) {
+        const double W = sG[3 * NQ + pt];
+        const double invW = 1.0 / W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) x[c] = sG[c * NQ + pt] * invW;
+        double Wd[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          Wd[d] = sG[((d + 1) * 4 + 3) * NQ + pt];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) J[d][c] = (sG[((d + 1) * 4 + c) * NQ + pt] - Wd[d] * x[c]) * invW;
+        }
+        double* cst = sC + 4 * pt;
+        cst[0] = invW; cst[1] = Wd[0]; cst[2] = Wd[1]; cst[3] = Wd[2];
+        det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+              J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+      }
+      const long long p0 = ptBase + 32 * m;
+      if (out.x) {
+        if (pt < NQ) { sSt[3 * lane] = x[0]; sSt[3 * lane + 1] = x[1]; sSt[3 * lane + 2] = x[2]; }
+        __syncwarp();
+        warp_flush(out.x + p0 * 3, sSt, 3 * nvalid, lane);
+        __syncwarp();
+      }
+      if (out.Jt) {
+        if (pt < NQ) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) sSt[9 * lane + 3 * d + c] = J[d][c];
+        }
+        __syncwarp();
+        warp_flush(out.Jt + p0 * 9, sSt, 9 * nvalid, lane);
+        __syncwarp();
+      }
+      if (out.JinvT) {
+        if (pt < NQ) {
+          // J^-T [c][d] = cof(J)[d][c] / det  (square case of rightInvA, nurbsgeometry.hh:205-210)
+          const double id = 1.0 / det;
+          const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2],
+                       c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+          const double c10 = J[0][2] * J[2][1] - J[0][1] * J[2][2], c11 = J[0][0] * J[2][2] - J[0][2] * J[2][0],
+                       c12 = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+          const double c20 = J[0][1] * J[1][2] - J[0][2] * J[1][1], c21 = J[0][2] * J[1][0] - J[0][0] * J[1][2],
+                       c22 = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+          // inverse of J (as a matrix with rows d) is adj/det with adj[i][j] = cof[j][i]; JinvT[c][d] = inv(J)^T[c][d]
+          // = inv(J)[d][c] ... with Jt rows = d: JinvT = (Jt)^-1 transposed appropriately: JinvT[c][d] = cof[d][c]/det
+          double* s = sSt + 9 * lane;
+          s[0] = c00 * id; s[1] = c10 * id; s[2] = c20 * id;
+          s[3] = c01 * id; s[4] = c11 * id; s[5] = c21 * id;
+          s[6] = c02 * id; s[7] = c12 * id; s[8] = c22 * id;
+        }
+        __syncwarp();
+        warp_flush(out.JinvT + p0 * 9, sSt, 9 * nvalid, lane);
+        __syncwarp();
+      }
+      if (out.detJ && pt < NQ) out.detJ[p0 + lane] = fabs(det);
+    }
+    __syncwarp();
+    // ---- (4) basis functions
+    if (out.N || out.dN) {
+#pragma unroll 1
+      for (int k = 0; k < C::KS; ++k) {
+        const int i = lane + 32 * k;
+        const bool valid = i < NB;
+        const int ii = valid ? i : 0;
+        const int i0 = ii % NB1, i1 = (ii / NB1) % NB1, i2 = ii / (NB1 * NB1);
+        const double w = valid ? sW[ii] : 0.0;
+        double n0[Q], d0[Q], n1[Q], d1[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          const double2 a = lds2(sT + (q * NB1 + i0) * 2), b = lds2(sT + C::TAB + (q * NB1 + i1) * 2);
+          n0[q] = a.x; d0[q] = a.y; n1[q] = b.x; d1[q] = b.y;
+        }
+        const int nrow = min(32, NB - 32 * k);  // basis functions in this slot
+        double* gN = out.N ? out.N + ptBase * NB + i : nullptr;
+        double* gD = out.dN ? out.dN + (ptBase * NB + 32 * k) * 3 : nullptr;
+        int buf = 0;
+#pragma unroll 1
+        for (int q2 = 0; q2 < Q; ++q2) {
+          const double2 t2 = lds2(sT + 2 * C::TAB + (q2 * NB1 + i2) * 2);
+          const double wn2 = w * t2.x, wd2 = w * t2.y;
+#pragma unroll
+          for (int q1 = 0; q1 < Q; ++q1) {
+#pragma unroll
+            for (int q0 = 0; q0 < Q; ++q0) {
+              const int pt = q0 + Q * q1 + Q2 * q2;
+              const double2 ca = lds2(sC + 4 * pt), cb = lds2(sC + 4 * pt + 2);  // invW, W0 | W1, W2
+              const double t00 = n0[q0] * n1[q1];
+              const double A0 = t00 * wn2;
+              const double R = A0 * ca.x;
+              if (gN && valid) gN[(size_t)pt * NB] = R;
+              if (gD) {
+                const double A1 = (d0[q0] * n1[q1]) * wn2;
+                const double A2 = (n0[q0] * d1[q1]) * wn2;
+                const double A3 = t00 * wd2;
+                double* sd = sD + buf * 96;
+                sd[3 * lane + 0] = (A1 - ca.y * R) * ca.x;
+                sd[3 * lane + 1] = (A2 - cb.x * R) * ca.x;
+                sd[3 * lane + 2] = (A3 - cb.y * R) * ca.x;
+                __syncwarp();
+                double* g = gD + (size_t)pt * NB * 3;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                  const int j = lane + 32 * r;
+                  if (j < 3 * nrow) g[j] = sd[j];
+                }
+                buf ^= 1;
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int P, int Q>
+igab_status launch_cfg(const PatchDev& Pd, const PointSource& src, long long nelem, const EvalOutDev& out,
+                       cudaStream_t stream) {
+  using C = Cfg<P, Q>;
+  // K1
+  double* tab[3];
+  for (int d = 0; d < 3; ++d) {
+    const size_t n = (size_t)Pd.nel[d] * C::TAB;
+    IGAB_CUDA_TRY(cudaMallocAsync(&tab[d], n * sizeof(double), stream));
+    const int threads = 128, total = Pd.nel[d] * Q;
+    tables_kernel<<<(total + threads - 1) / threads, threads, 0, stream>>>(Pd, d, Q, src.xi1d[d], tab[d]);
+  }
+  count_launch(3);
+  // K2
+  constexpr int WARPS = 4;
+  const size_t smem = (size_t)WARPS * C::SZ_WARP * sizeof(double);
+  static bool configured = false;
+  static int blocksPerSm = 1, numSms = 148;
+  if (!configured) {
+    IGAB_CUDA_TRY(cudaFuncSetAttribute(eval_sf3d_kernel<P, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0;
+    IGAB_CUDA_TRY(cudaGetDevice(&dev));
+    IGAB_CUDA_TRY(cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, dev));
+    IGAB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, eval_sf3d_kernel<P, Q>, WARPS * 32, smem));
+    if (blocksPerSm < 1) blocksPerSm = 1;
+    configured = true;
+  }
+  long long blocks = (long long)numSms * blocksPerSm;  // persistent: grid = SMs x resident blocks
+  const long long need = (nelem + WARPS - 1) / WARPS;
+  if (blocks > need) blocks = need;
+  eval_sf3d_kernel<P, Q><<<(unsigned)blocks, WARPS * 32, smem, stream>>>(Pd, src.elem_begin, nelem, tab[0], tab[1],
+                                                                         tab[2], out);
+  count_launch();
+  IGAB_CUDA_TRY(cudaGetLastError());
+  for (int d = 0; d < 3; ++d) IGAB_CUDA_TRY(cudaFreeAsync(tab[d], stream));
+  return IGAB_OK;
+}
+
+struct Key {
+  int p, q;
+};
+bool uniform_cfg(const PatchDev& P, const int* nq1, Key* k) {
+  if (P.dim != 3 || P.dw != 3) return false;
+  if (P.degree[0] != P.degree[1] || P.degree[0] != P.degree[2]) return false;
+  if (nq1[0] != nq1[1] || nq1[0] != nq1[2]) return false;
+  k->p = P.degree[0];
+  k->q = nq1[0];
+  return true;
+}
+
+}  // namespace
+
+bool eval_tensor_sf_supported(const PatchDev& P, const int* nq1, int order, const EvalOutDev& out) {
+  Key k;
+  if (!uniform_cfg(P, nq1, &k)) return false;
+  if (out.d2N || out.H) return false;  // second derivatives: general kernel
+  (void)order;
+  return (k.p == 3 && k.q == 4) || (k.p == 2 && k.q == 3) || (k.p == 4 && k.q == 5);
+}
+
+igab_status launch_eval_tensor_sf(const PatchDev& P, const PointSource& src, long long nelem, int order,
+                                  const EvalOutDev& out, cudaStream_t stream) {
+  Key k;
+  if (!uniform_cfg(P, src.nq1, &k) || !eval_tensor_sf_supported(P, src.nq1, order, out)) {
+    set_error("eval_tensor: no sum-factorised kernel for this configuration");
+    return IGAB_UNSUPPORTED;
+  }
+  EvalOutDev o = out;
+  if (order < 1) o.dN = o.Jt = o.detJ = o.JinvT = nullptr;
+  if (k.p == 3 && k.q == 4) return launch_cfg<3, 4>(P, src, nelem, o, stream);
+  if (k.p == 2 && k.q == 3) return launch_cfg<2, 3>(P, src, nelem, o, stream);
+  return launch_cfg<4, 5>(P, src, nelem, o, stream);
+}
+
 }  // namespace igab
