@@ -244,8 +244,8 @@ __global__ void __launch_bounds__(1024) volume_final_kernel(int n, const double*
   if (threadIdx.x == 0) *result = sh[0];
 }
 
-igab_status eval_for(const PatchDev& P, long long eb, long long nel, const int* nq1, const double* const* xi1d_dev,
-                     const EvalOutDev& out, cudaStream_t stream) {
+igab_status eval_for(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, long long eb, long long nel,
+                     const int* nq1, const double* const* xi1d_dev, const EvalOutDev& out, cudaStream_t stream) {
   PointSource src{};
   src.tensor = 1;
   src.elem_begin = eb;
@@ -255,12 +255,12 @@ igab_status eval_for(const PatchDev& P, long long eb, long long nel, const int* 
     src.nq *= nq1[d];
     src.xi1d[d] = xi1d_dev[d];
   }
-  if (eval_tensor_sf_supported(P, nq1, 1, out)) return launch_eval_tensor_sf(P, src, nel, 1, out, stream);
+  if (eval_tensor_sf_supported(P, nq1, 1, out)) return launch_eval_tensor_sf(P, ws, src, xi1d_host, nel, 1, out, stream);
   return launch_eval_generic(P, src, nel * src.nq, 1, out, stream);
 }
 
 template <int DIM, int DW>
-igab_status assemble_dd(const PatchDev& P, int kind, const double* D_dev, double fconst, long long eb, long long nel,
+igab_status assemble_dd(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, int kind, const double* D_dev, double fconst, long long eb, long long nel,
                         const int* nq1, const double* const* xi, const double* const* w, double* Ke, double* fe,
                         cudaStream_t stream) {
   long long nq = 1;
@@ -286,7 +286,7 @@ igab_status assemble_dd(const PatchDev& P, int kind, const double* D_dev, double
     IGAB_CUDA_TRY(cudaMallocAsync(&A2, 8LL * m * kdim * n, stream));
     EvalOutDev o{};
     o.N = dNv; o.dN = ddN; o.detJ = ddet; o.JinvT = dJi;
-    igab_status st = eval_for(P, eb + c0, m, nq1, xi, o, stream);
+    igab_status st = eval_for(P, ws, xi1d_host, eb + c0, m, nq1, xi, o, stream);
     if (st) return st;
     if (kind == IGAB_ASM_ELASTICITY) {
       // zero the structural zeros of B once (bstack writes every entry of its rows, so nothing to clear)
@@ -323,20 +323,20 @@ igab_status assemble_dd(const PatchDev& P, int kind, const double* D_dev, double
 
 }  // namespace
 
-igab_status launch_assemble(const PatchDev& P, int kind, const double* D_dev, double fconst, long long elem_begin,
+igab_status launch_assemble(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, int kind, const double* D_dev, double fconst, long long elem_begin,
                             long long nelem, const int* nq1, const double* const* xi1d_dev,
                             const double* const* w1d_dev, double* Ke, double* fe, cudaStream_t stream) {
   switch (P.dim * 10 + P.dw) {
-    case 11: return assemble_dd<1, 1>(P, kind, D_dev, fconst, elem_begin, nelem, nq1, xi1d_dev, w1d_dev, Ke, fe, stream);
-    case 22: return assemble_dd<2, 2>(P, kind, D_dev, fconst, elem_begin, nelem, nq1, xi1d_dev, w1d_dev, Ke, fe, stream);
-    case 23: return assemble_dd<2, 3>(P, kind, D_dev, fconst, elem_begin, nelem, nq1, xi1d_dev, w1d_dev, Ke, fe, stream);
-    case 33: return assemble_dd<3, 3>(P, kind, D_dev, fconst, elem_begin, nelem, nq1, xi1d_dev, w1d_dev, Ke, fe, stream);
+    case 11: return assemble_dd<1, 1>(P, ws, xi1d_host, kind, D_dev, fconst, elem_begin, nelem, nq1, xi1d_dev, w1d_dev, Ke, fe, stream);
+    case 22: return assemble_dd<2, 2>(P, ws, xi1d_host, kind, D_dev, fconst, elem_begin, nelem, nq1, xi1d_dev, w1d_dev, Ke, fe, stream);
+    case 23: return assemble_dd<2, 3>(P, ws, xi1d_host, kind, D_dev, fconst, elem_begin, nelem, nq1, xi1d_dev, w1d_dev, Ke, fe, stream);
+    case 33: return assemble_dd<3, 3>(P, ws, xi1d_host, kind, D_dev, fconst, elem_begin, nelem, nq1, xi1d_dev, w1d_dev, Ke, fe, stream);
   }
   set_error("assemble: unsupported (dim, dimworld)");
   return IGAB_UNSUPPORTED;
 }
 
-igab_status launch_volume(const PatchDev& P, long long elem_begin, long long nelem, const int* nq1,
+igab_status launch_volume(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, long long elem_begin, long long nelem, const int* nq1,
                           const double* const* xi1d_dev, const double* const* w1d_dev, double* partial_dev,
                           int npartial, double* result_dev, cudaStream_t stream) {
   long long nq = 1;
@@ -350,7 +350,7 @@ igab_status launch_volume(const PatchDev& P, long long elem_begin, long long nel
   IGAB_CUDA_TRY(cudaMallocAsync(&ddet, 8 * npts, stream));
   EvalOutDev o{};
   o.detJ = ddet;
-  igab_status st = eval_for(P, elem_begin, nelem, nq1, xi1d_dev, o, stream);
+  igab_status st = eval_for(P, ws, xi1d_host, elem_begin, nelem, nq1, xi1d_dev, o, stream);
   if (st) return st;
   const int q0 = nq1[0], q1 = P.dim > 1 ? nq1[1] : 1, q2 = P.dim > 2 ? nq1[2] : 1;
   const int nblk = (int)std::min<long long>(npartial, (npts + 255) / 256);

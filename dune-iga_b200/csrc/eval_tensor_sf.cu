@@ -23,6 +23,9 @@
 //          consecutive addresses; x / Jt / detJ / JinvT staged per 32 points and flushed as contiguous runs.
 //  The pass is bound by HBM writes (2,152 B per point at p=3, 4^3 points); FP64 work is ~15 DP instructions per
 //  (point, basis function), i.e. < 25 % of the DP pipe at the HBM roofline.
+#include <algorithm>
+#include <cstdlib>
+
 #include "bspline_device.cuh"
 #include "igab_internal.cuh"
 
@@ -68,16 +71,42 @@ struct Cfg {
   static constexpr int SZ_H = ev(NB1 * NB1 * HS);
   static constexpr int SZ_S1 = 2 * Q * 4 * S1C;
   static constexpr int SZ_G = 16 * NQ;          // [alpha(4)][c(4)][pt]
-  static constexpr int SZ_D = 2 * 96;           // dN transposition slabs
+  // k-inner variant: all basis slots of a lane share (i0, i1) (32 % (p+1)^2 == 0, i.e. p = 3 or 1), so one point's
+  // complete dN row [nb][3] is produced at once and leaves through ONE async bulk store (TMA, UBLKCP) per point.
+  static constexpr bool KINNER = (32 % (NB1 * NB1) == 0) && (NB % 32 == 0);
+  static constexpr int NBUF = 4;                // ring depth of bulk-store slabs
+  static constexpr int SZ_D = KINNER ? NBUF * NB * 3 : 2 * 96;  // dN slabs (bulk ring | transposition double buffer)
   static constexpr int SZ_A = ev((SZ_H + SZ_S1) > (SZ_G) ? (SZ_H + SZ_S1) : (SZ_G));
   static constexpr int SZ_S2 = 3 * 4 * Q * Q * S2S;
   static constexpr int SZ_C = 4 * NQ;           // invW, W_0, W_1, W_2 per point
   static constexpr int SZ_ST = 32 * 9;          // staging of one geometry field for 32 points
-  static constexpr int SZ_B = ev(SZ_S2 > (SZ_C + SZ_ST + SZ_D) ? SZ_S2 : (SZ_C + SZ_ST + SZ_D));
+  static constexpr int SZ_STD = SZ_ST > SZ_D ? SZ_ST : SZ_D;  // geometry staging (phase 3) aliases the dN slabs (phase 4)
+  static constexpr int SZ_B = ev(SZ_S2 > (SZ_C + SZ_STD) ? SZ_S2 : (SZ_C + SZ_STD));
   static constexpr int SZ_WARP = ev(SZ_T + SZ_W + SZ_A + SZ_B);
 };
 
 __device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+// ---- async bulk copy shared -> global (TMA engine; SASS: UBLKCP), bulk-group completion
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_store_hint(void* gdst, const void* ssrc, unsigned bytes, unsigned long long pol) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(s),
+               "r"(bytes), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
 // coalesced copy of n doubles from shared memory to global memory by one warp
 __device__ __forceinline__ void warp_flush(double* __restrict__ dst, const double* __restrict__ src, int n, int lane) {
@@ -88,7 +117,8 @@ template <int P, int Q>
 __global__ void __launch_bounds__(128) eval_sf3d_kernel(PatchDev Pd, long long elem_begin, long long nelem,
                                                         const double* __restrict__ tab0,
                                                         const double* __restrict__ tab1,
-                                                        const double* __restrict__ tab2, EvalOutDev out) {
+                                                        const double* __restrict__ tab2, EvalOutDev out, int tune,
+                                                        unsigned int* __restrict__ counter) {
   using C = Cfg<P, Q>;
   constexpr int NB1 = C::NB1, NB = C::NB, NQ = C::NQ, Q2 = Q * Q;
   extern __shared__ __align__(16) double smem[];
@@ -104,12 +134,15 @@ __global__ void __launch_bounds__(128) eval_sf3d_kernel(PatchDev Pd, long long e
   double* const sS2 = rB;              // stage 2 output
   double* const sC = rB;               // after stage 3 (S2 dead)
   double* const sSt = rB + C::SZ_C;
-  double* const sD = sSt + C::SZ_ST;
+  double* const sD = sSt;              // phase 4 only (staging dead)
 
-  const long long warpsTotal = (long long)gridDim.x * (blockDim.x >> 5);
-  const long long warpId = (long long)blockIdx.x * (blockDim.x >> 5) + warpInBlock;
-
-  for (long long el = warpId; el < nelem; el += warpsTotal) {
+  // dynamic scheduling: every warp draws the next element from a global counter, so elements in flight stay
+  // consecutive (output streams stay compact) and slow SMs (far-die L2, DRAM channel contention) do not leave a tail
+  for (;;) {
+    unsigned int nxt = 0;
+    if (lane == 0) nxt = atomicAdd(counter, 1u);
+    const long long el = (long long)__shfl_sync(0xffffffffu, nxt, 0);
+    if (el >= nelem) break;
     const long long e = elem_begin + el;
     int e0, e1, e2;
     {
@@ -306,7 +339,83 @@ __global__ void __launch_bounds__(128) eval_sf3d_kernel(PatchDev Pd, long long e
     }
     __syncwarp();
     // ---- (4) basis functions
-    if (out.N || out.dN) {
+    if constexpr (C::KINNER) {
+      if (out.N || out.dN) {
+        constexpr int KS = C::KS;
+        const int i0 = lane % NB1, i1 = (lane / NB1) % NB1, i2b = lane / (NB1 * NB1);
+        constexpr int I2STEP = 32 / (NB1 * NB1);  // i2 of slot k = i2b + k * I2STEP
+        double w[KS];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) w[k] = sW[lane + 32 * k];
+        double n0[Q], d0[Q], n1[Q], d1[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          const double2 a = lds2(sT + (q * NB1 + i0) * 2), b = lds2(sT + C::TAB + (q * NB1 + i1) * 2);
+          n0[q] = a.x; d0[q] = a.y; n1[q] = b.x; d1[q] = b.y;
+        }
+        double* gN = out.N ? out.N + ptBase * NB + lane : nullptr;
+        double* gD = out.dN ? out.dN + ptBase * NB * 3 : nullptr;
+        // the bulk path needs 16-byte aligned global rows (row = NB*24 bytes, a multiple of 16 here)
+        const bool bulk = gD && ((reinterpret_cast<unsigned long long>(gD) & 15ull) == 0);
+        const unsigned long long pol = policy_evict_first();
+#pragma unroll 1
+        for (int q2 = 0; q2 < Q; ++q2) {
+          double wn2[KS], wd2[KS];
+#pragma unroll
+          for (int k = 0; k < KS; ++k) {
+            const double2 t2 = lds2(sT + 2 * C::TAB + (q2 * NB1 + i2b + k * I2STEP) * 2);
+            wn2[k] = w[k] * t2.x;
+            wd2[k] = w[k] * t2.y;
+          }
+#pragma unroll
+          for (int q1 = 0; q1 < Q; ++q1) {
+#pragma unroll
+            for (int q0 = 0; q0 < Q; ++q0) {
+              const int pt = q0 + Q * q1 + Q2 * q2;
+              const double2 ca = lds2(sC + 4 * pt), cb = lds2(sC + 4 * pt + 2);  // invW, W0 | W1, W2
+              const double t00 = n0[q0] * n1[q1], t10 = d0[q0] * n1[q1], t01 = n0[q0] * d1[q1];
+              double* sd = sD + ((q0 + Q * q1) % C::NBUF) * (NB * 3);
+              if (gD) {
+                if (bulk) {
+                  if (lane == 0) bulk_wait_read<C::NBUF - 1>();  // the slab written NBUF points ago has been read
+                }
+                __syncwarp();
+              }
+#pragma unroll
+              for (int k = 0; k < KS; ++k) {
+                const double R = (t00 * wn2[k]) * ca.x;
+                if (gN) { if (tune & 1) __stcs(gN + (size_t)pt * NB + 32 * k, R); else gN[(size_t)pt * NB + 32 * k] = R; }
+                if (gD) {
+                  double* o = sd + 3 * (lane + 32 * k);
+                  o[0] = (t10 * wn2[k] - ca.y * R) * ca.x;
+                  o[1] = (t01 * wn2[k] - cb.x * R) * ca.x;
+                  o[2] = (t00 * wd2[k] - cb.y * R) * ca.x;
+                }
+              }
+              if (gD) {
+                double* g = gD + (size_t)pt * NB * 3;
+                if (bulk) {
+                  fence_proxy_async_smem();  // generic-proxy writes -> visible to the async proxy
+                  __syncwarp();
+                  if (lane == 0) {
+                    if (tune & 1)
+                      bulk_store_hint(g, sd, NB * 3 * 8, pol);
+                    else
+                      bulk_store(g, sd, NB * 3 * 8);
+                    bulk_commit();
+                  }
+                } else {
+                  __syncwarp();
+                  for (int j = lane; j < NB * 3; j += 32) g[j] = sd[j];
+                }
+              }
+            }
+          }
+        }
+        if (bulk && lane == 0) bulk_wait_read<0>();  // slabs alias stage-2 scratch of the next element
+        __syncwarp();
+      }
+    } else if (out.N || out.dN) {
 #pragma unroll 1
       for (int k = 0; k < C::KS; ++k) {
         const int i = lane + 32 * k;
@@ -365,19 +474,45 @@ __global__ void __launch_bounds__(128) eval_sf3d_kernel(PatchDev Pd, long long e
   }
 }
 
+constexpr int kCounterRing = 64;
+
 template <int P, int Q>
-igab_status launch_cfg(const PatchDev& Pd, const PointSource& src, long long nelem, const EvalOutDev& out,
-                       cudaStream_t stream) {
+igab_status launch_cfg(const PatchDev& Pd, SfWorkspace& ws, const PointSource& src, const double* const* xi1d_host,
+                       long long nelem, const EvalOutDev& out, cudaStream_t stream) {
   using C = Cfg<P, Q>;
-  // K1
-  double* tab[3];
-  for (int d = 0; d < 3; ++d) {
-    const size_t n = (size_t)Pd.nel[d] * C::TAB;
-    IGAB_CUDA_TRY(cudaMallocAsync(&tab[d], n * sizeof(double), stream));
-    const int threads = 128, total = Pd.nel[d] * Q;
-    tables_kernel<<<(total + threads - 1) / threads, threads, 0, stream>>>(Pd, d, Q, src.xi1d[d], tab[d]);
+  if (nelem > 0x7fffffffLL) {
+    set_error("eval_tensor: more than 2^31 elements in one launch");
+    return IGAB_INVALID_ARGUMENT;
   }
-  count_launch(3);
+  // K1 (cached per handle: rebuilt only when the rule changes)
+  bool same = ws.valid && ws.stream == stream;
+  for (int d = 0; d < 3 && same; ++d) {
+    same = ws.nq1[d] == Q && (int)ws.xi[d].size() == Q;
+    for (int q = 0; q < Q && same; ++q) same = ws.xi[d][q] == xi1d_host[d][q];
+  }
+  if (!ws.counter) {
+    IGAB_CUDA_TRY(cudaMalloc(&ws.counter, sizeof(unsigned int) * kCounterRing));
+  }
+  if (!same) {
+    for (int d = 0; d < 3; ++d) {
+      const size_t n = (size_t)Pd.nel[d] * C::TAB;
+      if (ws.tabCap[d] < n) {
+        // stream-ordered: earlier launches on this stream may still read the old tables
+        if (ws.tab[d]) IGAB_CUDA_TRY(cudaFreeAsync(ws.tab[d], stream));
+        ws.tab[d] = nullptr;
+        ws.tabCap[d] = 0;
+        IGAB_CUDA_TRY(cudaMallocAsync(&ws.tab[d], n * sizeof(double), stream));
+        ws.tabCap[d] = n;
+      }
+      const int threads = 128, total = Pd.nel[d] * Q;
+      tables_kernel<<<(total + threads - 1) / threads, threads, 0, stream>>>(Pd, d, Q, src.xi1d[d], ws.tab[d]);
+      ws.nq1[d] = Q;
+      ws.xi[d].assign(xi1d_host[d], xi1d_host[d] + Q);
+    }
+    count_launch(3);
+    ws.valid = true;
+    ws.stream = stream;
+  }
   // K2
   constexpr int WARPS = 4;
   const size_t smem = (size_t)WARPS * C::SZ_WARP * sizeof(double);
@@ -392,14 +527,18 @@ igab_status launch_cfg(const PatchDev& Pd, const PointSource& src, long long nel
     if (blocksPerSm < 1) blocksPerSm = 1;
     configured = true;
   }
-  long long blocks = (long long)numSms * blocksPerSm;  // persistent: grid = SMs x resident blocks
+  int bps = blocksPerSm, tune = 0;
+  if (const char* e = getenv("IGAB_SF_BLOCKS_PER_SM")) bps = std::max(1, std::min(blocksPerSm, atoi(e)));  // tuning knob
+  if (const char* e = getenv("IGAB_SF_TUNE")) tune = atoi(e);
+  long long blocks = (long long)numSms * bps;  // persistent: grid = SMs x resident blocks
   const long long need = (nelem + WARPS - 1) / WARPS;
   if (blocks > need) blocks = need;
-  eval_sf3d_kernel<P, Q><<<(unsigned)blocks, WARPS * 32, smem, stream>>>(Pd, src.elem_begin, nelem, tab[0], tab[1],
-                                                                         tab[2], out);
+  unsigned int* ctr = ws.counter + (ws.counterSlot++ % kCounterRing);
+  IGAB_CUDA_TRY(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), stream));
+  eval_sf3d_kernel<P, Q><<<(unsigned)blocks, WARPS * 32, smem, stream>>>(Pd, src.elem_begin, nelem, ws.tab[0],
+                                                                         ws.tab[1], ws.tab[2], out, tune, ctr);
   count_launch();
   IGAB_CUDA_TRY(cudaGetLastError());
-  for (int d = 0; d < 3; ++d) IGAB_CUDA_TRY(cudaFreeAsync(tab[d], stream));
   return IGAB_OK;
 }
 
@@ -425,8 +564,16 @@ bool eval_tensor_sf_supported(const PatchDev& P, const int* nq1, int order, cons
   return (k.p == 3 && k.q == 4) || (k.p == 2 && k.q == 3) || (k.p == 4 && k.q == 5);
 }
 
-igab_status launch_eval_tensor_sf(const PatchDev& P, const PointSource& src, long long nelem, int order,
-                                  const EvalOutDev& out, cudaStream_t stream) {
+void free_sf_workspace(SfWorkspace& ws) {
+  for (int d = 0; d < kMaxDim; ++d)
+    if (ws.tab[d]) cudaFree(ws.tab[d]);
+  if (ws.counter) cudaFree(ws.counter);
+  ws = SfWorkspace();
+}
+
+igab_status launch_eval_tensor_sf(const PatchDev& P, SfWorkspace& ws, const PointSource& src,
+                                  const double* const* xi1d_host, long long nelem, int order, const EvalOutDev& out,
+                                  cudaStream_t stream) {
   Key k;
   if (!uniform_cfg(P, src.nq1, &k) || !eval_tensor_sf_supported(P, src.nq1, order, out)) {
     set_error("eval_tensor: no sum-factorised kernel for this configuration");
@@ -434,9 +581,9 @@ igab_status launch_eval_tensor_sf(const PatchDev& P, const PointSource& src, lon
   }
   EvalOutDev o = out;
   if (order < 1) o.dN = o.Jt = o.detJ = o.JinvT = nullptr;
-  if (k.p == 3 && k.q == 4) return launch_cfg<3, 4>(P, src, nelem, o, stream);
-  if (k.p == 2 && k.q == 3) return launch_cfg<2, 3>(P, src, nelem, o, stream);
-  return launch_cfg<4, 5>(P, src, nelem, o, stream);
+  if (k.p == 3 && k.q == 4) return launch_cfg<3, 4>(P, ws, src, xi1d_host, nelem, o, stream);
+  if (k.p == 2 && k.q == 3) return launch_cfg<2, 3>(P, ws, src, xi1d_host, nelem, o, stream);
+  return launch_cfg<4, 5>(P, ws, src, xi1d_host, nelem, o, stream);
 }
 
 }  // namespace igab

@@ -43,6 +43,19 @@ struct EvalOutDev {
   double *N, *dN, *d2N, *x, *Jt, *H, *detJ, *JinvT;
 };
 
+// Per-handle workspace of the sum-factorised tensor kernel: univariate tables of the last rule (K1 output) and the
+// element counter of the dynamic scheduler.  Rebuilt only when the rule changes.
+struct SfWorkspace {
+  double* tab[kMaxDim] = {nullptr, nullptr, nullptr};
+  size_t tabCap[kMaxDim] = {0, 0, 0};
+  int nq1[kMaxDim] = {0, 0, 0};
+  std::vector<double> xi[kMaxDim];
+  unsigned int* counter = nullptr;  // ring of counters, one per launch in flight
+  unsigned int counterSlot = 0;
+  bool valid = false;
+  cudaStream_t stream = nullptr;    // stream the tables were built on (rebuilt when the caller switches streams)
+};
+
 void set_error(const std::string& msg);
 igab_status cuda_fail(cudaError_t e, const char* what);
 void count_launch(int n = 1);
@@ -57,8 +70,11 @@ void count_launch(int n = 1);
 igab_status launch_eval_generic(const PatchDev& P, const PointSource& src, long long npts, int order,
                                 const EvalOutDev& out, cudaStream_t stream);
 // returns IGAB_UNSUPPORTED when no sum-factorised instantiation matches
-igab_status launch_eval_tensor_sf(const PatchDev& P, const PointSource& src, long long nelem, int order,
-                                  const EvalOutDev& out, cudaStream_t stream);
+// xi1d_host: the rule on the host (used to decide whether the cached tables are still valid)
+igab_status launch_eval_tensor_sf(const PatchDev& P, SfWorkspace& ws, const PointSource& src,
+                                  const double* const* xi1d_host, long long nelem, int order, const EvalOutDev& out,
+                                  cudaStream_t stream);
+void free_sf_workspace(SfWorkspace& ws);
 bool eval_tensor_sf_supported(const PatchDev& P, const int* nq1, int order, const EvalOutDev& out);
 igab_status launch_partial(const PatchDev& P, long long npts, const int* elem, const double* xi, const int* alpha,
                            double* out, cudaStream_t stream);
@@ -66,10 +82,10 @@ igab_status launch_spans(const PatchDev& P, int32_t* span, cudaStream_t stream);
 igab_status launch_dofmap(const PatchDev& P, int32_t* dof, cudaStream_t stream);
 igab_status launch_dof_compact(const PatchDev& P, const uint8_t* trim_dev, int32_t* dof, int32_t* scratch_used,
                                int32_t* scratch_map, long long ndof, long long* ndof_out_host, cudaStream_t stream);
-igab_status launch_assemble(const PatchDev& P, int kind, const double* D_dev, double fconst, long long elem_begin,
+igab_status launch_assemble(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, int kind, const double* D_dev, double fconst, long long elem_begin,
                             long long nelem, const int* nq1, const double* const* xi1d_dev,
                             const double* const* w1d_dev, double* Ke, double* fe, cudaStream_t stream);
-igab_status launch_volume(const PatchDev& P, long long elem_begin, long long nelem, const int* nq1,
+igab_status launch_volume(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, long long elem_begin, long long nelem, const int* nq1,
                           const double* const* xi1d_dev, const double* const* w1d_dev, double* partial_dev,
                           int npartial, double* result_dev, cudaStream_t stream);
 
@@ -91,6 +107,10 @@ struct igab_patch {
   long long ndof_untrimmed = 0;
   // small device scratch for quadrature rules (xi, w per direction), reused across calls
   double* d_rule = nullptr;  // [2][kMaxDim][kMaxRule]
+  igab::SfWorkspace sf;
+  // last rule staged in d_rule (skip the H2D copy when the caller passes the same rule again)
+  std::vector<double> rule_host;
+  cudaStream_t rule_stream = nullptr;
   // reduction scratch
   double* d_red = nullptr;
   int red_cap = 0;
