@@ -370,6 +370,12 @@ void igab_patch_destroy(igab_patch* p) {
   if (p->d_trim) cudaFree(p->d_trim);
   if (p->d_rule) cudaFree(p->d_rule);
   if (p->d_red) cudaFree(p->d_red);
+  for (int b = 0; b < 2; ++b) {
+    if (p->stage_buf[b]) cudaFree(p->stage_buf[b]);
+    if (p->stage_done[b]) cudaEventDestroy(p->stage_done[b]);
+    if (p->stage_copied[b]) cudaEventDestroy(p->stage_copied[b]);
+  }
+  if (p->stage_stream) cudaStreamDestroy(p->stage_stream);
   free_sf_workspace(p->sf);
   delete p;
 }
@@ -485,49 +491,56 @@ igab_status igab_eval_tensor(igab_patch* p, int64_t elem_begin, int64_t elem_end
   if (nel == 0 || bytes_pt == 0) return IGAB_OK;
   const long long chunkBytes = 512LL << 20;  // per buffer set
   const long long elChunk = std::max(1LL, std::min(nel, chunkBytes / (bytes_pt * nq)));
-  double* dbuf[2][8] = {};
-  cudaStream_t cstream = nullptr;
-  cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
-  cudaError_t e = cudaStreamCreateWithFlags(&cstream, cudaStreamNonBlocking);
-  for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
-    e = cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming);
-    for (int k = 0; k < 8 && e == cudaSuccess; ++k)
-      if (*out_field(&eff, k)) e = cudaMalloc(&dbuf[b][k], per_pt[k] * 8 * nq * elChunk);
+  const size_t needBytes = (size_t)(bytes_pt * nq * elChunk) + 8 * 16;
+  cudaError_t e = cudaSuccess;
+  if (!p->stage_stream) {
+    e = cudaStreamCreateWithFlags(&p->stage_stream, cudaStreamNonBlocking);
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+      e = cudaEventCreateWithFlags(&p->stage_done[b], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->stage_copied[b], cudaEventDisableTiming);
+    }
   }
-  if (e != cudaSuccess) st = cuda_fail(e, "eval_tensor host staging allocation");
+  if (e == cudaSuccess && p->stage_cap < needBytes) {
+    for (int b = 0; b < 2; ++b) {
+      if (p->stage_buf[b]) cudaFree(p->stage_buf[b]);
+      p->stage_buf[b] = nullptr;
+    }
+    p->stage_cap = 0;
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaMalloc(&p->stage_buf[b], needBytes);
+    if (e == cudaSuccess) p->stage_cap = needBytes;
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "eval_tensor host staging allocation");
+  cudaStream_t cstream = p->stage_stream;
   int b = 0;
   for (long long c0 = 0; c0 < nel && !st; c0 += elChunk, b ^= 1) {
     const long long n = std::min(elChunk, nel - c0);
     igab_eval_out dv{};
-    for (int k = 0; k < 8; ++k) *out_field(&dv, k) = dbuf[b][k];
-    if ((e = cudaStreamWaitEvent(stream, copied[b], 0)) != cudaSuccess) { st = cuda_fail(e, "wait copied"); break; }
+    {
+      double* cur = p->stage_buf[b];  // fields packed back to back (each a multiple of 8 bytes; keep 16-byte alignment)
+      for (int k = 0; k < 8; ++k)
+        if (*out_field(&eff, k)) {
+          *out_field(&dv, k) = cur;
+          cur += ((per_pt[k] * nq * elChunk + 1) & ~1LL);
+        }
+    }
+    if ((e = cudaStreamWaitEvent(stream, p->stage_copied[b], 0)) != cudaSuccess) { st = cuda_fail(e, "wait copied"); break; }
     st = run_eval_tensor_device(p, elem_begin + c0, elem_begin + c0 + n, deriv_order, nq1, xi1d, rule, dv, stream);
     if (st) break;
-    if ((e = cudaEventRecord(done[b], stream)) != cudaSuccess) { st = cuda_fail(e, "record done"); break; }
-    if ((e = cudaStreamWaitEvent(cstream, done[b], 0)) != cudaSuccess) { st = cuda_fail(e, "wait done"); break; }
+    if ((e = cudaEventRecord(p->stage_done[b], stream)) != cudaSuccess) { st = cuda_fail(e, "record done"); break; }
+    if ((e = cudaStreamWaitEvent(cstream, p->stage_done[b], 0)) != cudaSuccess) { st = cuda_fail(e, "wait done"); break; }
     for (int k = 0; k < 8; ++k) {
       double* h = *out_field(&eff, k);
       if (!h) continue;
-      e = cudaMemcpyAsync(h + per_pt[k] * nq * c0, dbuf[b][k], per_pt[k] * 8 * nq * n, cudaMemcpyDeviceToHost, cstream);
+      e = cudaMemcpyAsync(h + per_pt[k] * nq * c0, *out_field(&dv, k), per_pt[k] * 8 * nq * n, cudaMemcpyDeviceToHost, cstream);
       if (e != cudaSuccess) { st = cuda_fail(e, "eval_tensor D2H"); break; }
     }
     if (st) break;
-    if ((e = cudaEventRecord(copied[b], cstream)) != cudaSuccess) { st = cuda_fail(e, "record copied"); break; }
+    if ((e = cudaEventRecord(p->stage_copied[b], cstream)) != cudaSuccess) { st = cuda_fail(e, "record copied"); break; }
   }
-  if (cstream) {
-    e = cudaStreamSynchronize(cstream);
-    if (e != cudaSuccess && !st) st = cuda_fail(e, "sync copy stream");
-  }
+  e = cudaStreamSynchronize(cstream);
+  if (e != cudaSuccess && !st) st = cuda_fail(e, "sync copy stream");
   e = cudaStreamSynchronize(stream);
   if (e != cudaSuccess && !st) st = cuda_fail(e, "sync stream");
-  for (int bb = 0; bb < 2; ++bb) {
-    for (int k = 0; k < 8; ++k)
-      if (dbuf[bb][k]) cudaFree(dbuf[bb][k]);
-    if (done[bb]) cudaEventDestroy(done[bb]);
-    if (copied[bb]) cudaEventDestroy(copied[bb]);
-  }
-  if (cstream) cudaStreamDestroy(cstream);
   return st;
 }
 

@@ -111,6 +111,11 @@ struct igab_patch {
   // last rule staged in d_rule (skip the H2D copy when the caller passes the same rule again)
   std::vector<double> rule_host;
   cudaStream_t rule_stream = nullptr;
+  // persistent staging for IGAB_HOST outputs of igab_eval_tensor: two sets of device buffers, a copy stream, events
+  double* stage_buf[2] = {nullptr, nullptr};
+  size_t stage_cap = 0;  // bytes per set
+  cudaStream_t stage_stream = nullptr;
+  cudaEvent_t stage_done[2] = {nullptr, nullptr}, stage_copied[2] = {nullptr, nullptr};
   // reduction scratch
   double* d_red = nullptr;
   int red_cap = 0;

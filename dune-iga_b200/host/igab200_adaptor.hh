@@ -1,0 +1,409 @@
+// igab200_adaptor.hh -- header-only C++17 host adaptor that keeps the reference's METHOD NAMES, argument meaning and
+// error behaviour for the hot path, and forwards to the batched C-ABI (include/igab200.h) instead of evaluating one
+// point at a time on the CPU.  It is what NURBSGrid / NurbsPreBasis host code (which stays C++) would hold in place of
+// its per-point members; INTEGRATION.md shows the three-line changes in the reference that bind it.
+//
+//   reference type / method (file:line)                                   here
+//   NURBSPatchData                      dune/iga/nurbspatchdata.hh:17-36   igab::PatchData  (same three members)
+//   NurbsLocalBasis::evaluateFunction   dune/iga/nurbsbasis.hh:77-82       LocalBasis::evaluateFunction
+//   NurbsLocalBasis::evaluateJacobian   dune/iga/nurbsbasis.hh:87-96       LocalBasis::evaluateJacobian
+//   NurbsLocalBasis::partial            dune/iga/nurbsbasis.hh:99-108      LocalBasis::partial
+//   NurbsLocalBasis::order / size       dune/iga/nurbsbasis.hh:117-123     LocalBasis::order / size
+//   NurbsLocalFiniteElement::bind       dune/iga/nurbsbasis.hh:355-375     LocalView::bind(elementIndex)
+//   NurbsPreBasis::indices / size       dune/iga/nurbsbasis.hh:590-598,625 LocalView::index(i), PreBasis::size/dimension
+//   NURBSGeometry::global               dune/iga/nurbsgeometry.hh:133-138  Geometry::global
+//   NURBSGeometry::jacobianTransposed   dune/iga/nurbsgeometry.hh:182-196  Geometry::jacobianTransposed
+//   NURBSGeometry::integrationElement   dune/iga/nurbsgeometry.hh:200-203  Geometry::integrationElement
+//   NURBSGeometry::jacobianInverseTransposed  nurbsgeometry.hh:205-210     Geometry::jacobianInverseTransposed
+//   NURBSGeometry::volume               dune/iga/nurbsgeometry.hh:96-113   Geometry::volume
+//   NURBSGridEntity::getQuadratureRule  dune/iga/nurbsgridentity.hh:120-141 Patch::setQuadratureRule (rule is an input)
+//
+// How it works: Patch::setQuadratureRule(rule) evaluates EVERY point of EVERY element once on the GPU
+// (igab_eval_tensor) and keeps the result in host vectors.  bind(e) + evaluate*(xi) then return the cached row when xi
+// is a point of the rule (exact coordinate match -- the quadrature loop of dune/python/test/poisson.py:47-79 or
+// dune/iga/test/gridtests.cpp:338-360), and fall back to a single-point GPU call (igab_eval_points) otherwise.  There is
+// no CPU evaluation path.
+//
+// Generic over the vector types: anything with operator[] works (Dune::FieldVector / FieldMatrix when DUNE is there,
+// std::array in the tests), because DUNE itself is not available in this build environment.
+// Error behaviour: the reference asserts / throws (DUNE_THROW, std::logic_error); the adaptor throws igab::Error
+// carrying the igab_status and igab_last_error_string().
+#pragma once
+#include <array>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/igab200.h"
+
+namespace igab {
+
+struct Error : std::runtime_error {
+  igab_status status;
+  Error(igab_status s, const std::string& m) : std::runtime_error(m), status(s) {}
+};
+inline void check(igab_status s) {
+  if (s != IGAB_OK) throw Error(s, igab_last_error_string());
+}
+
+// Same members as Dune::IGA::NURBSPatchData; control points flat, first direction fastest, rows (x.., w).
+template <int dim, int dimworld>
+struct PatchData {
+  std::array<std::vector<double>, dim> knotSpans;
+  std::vector<double> controlPoints;  // [n][dimworld+1]
+  std::array<int, dim> degree;
+};
+
+template <int dim, int dimworld>
+class Patch : public std::enable_shared_from_this<Patch<dim, dimworld>> {
+public:
+  static constexpr int nh = dim * (dim + 1) / 2;
+
+  explicit Patch(const PatchData<dim, dimworld>& d, const std::vector<uint8_t>* trimFlags = nullptr) : data_(d) {
+    std::array<int, dim> nk;
+    std::array<const double*, dim> kp;
+    for (int i = 0; i < dim; ++i) {
+      nk[i] = (int)d.knotSpans[i].size();
+      kp[i] = d.knotSpans[i].data();
+    }
+    check(igab_patch_create(dim, dimworld, d.degree.data(), nk.data(), kp.data(), d.controlPoints.data(),
+                            trimFlags ? trimFlags->data() : nullptr, &h_));
+    int32_t nb = 0;
+    check(igab_patch_sizes(h_, &nElements_, nElDir_.data(), &nb, nullptr));
+    nb_ = nb;
+    dof_.resize((size_t)nElements_ * nb_);
+    check(igab_patch_dofmap(h_, dof_.data(), &nDofs_, IGAB_HOST, nullptr));
+  }
+  Patch(const Patch&) = delete;
+  Patch& operator=(const Patch&) = delete;
+  ~Patch() { igab_patch_destroy(h_); }
+
+  igab_patch* handle() const { return h_; }
+  int64_t size0() const { return nElements_; }  // number of elements (codim 0)
+  int localSize() const { return nb_; }
+  int64_t numDofs() const { return nDofs_; }
+  const PatchData<dim, dimworld>& patchData() const { return data_; }
+  const int32_t* dofsOf(int64_t e) const { return dof_.data() + (size_t)e * nb_; }
+
+  // The rule every untrimmed element uses (nurbsgridentity.hh:120-133): abscissae / weights per direction on [0,1].
+  // derivOrder 1: N, dN, x, Jt, detJ, JinvT are cached; 2 adds d2N, H.
+  void setQuadratureRule(const std::array<std::vector<double>, dim>& xi, const std::array<std::vector<double>, dim>& w,
+                         int derivOrder = 1) {
+    xi_ = xi;
+    w_ = w;
+    order_ = derivOrder;
+    nq_ = 1;
+    std::array<int, dim> nq1;
+    std::array<const double*, dim> xp;
+    for (int i = 0; i < dim; ++i) {
+      nq1[i] = (int)xi[i].size();
+      xp[i] = xi[i].data();
+      nq_ *= nq1[i];
+    }
+    const size_t npts = (size_t)nElements_ * nq_;
+    N_.resize(npts * nb_);
+    dN_.resize(npts * nb_ * dim);
+    x_.resize(npts * dimworld);
+    Jt_.resize(npts * dim * dimworld);
+    detJ_.resize(npts);
+    JinvT_.resize(npts * dim * dimworld);
+    igab_eval_out out{};
+    out.N = N_.data();
+    out.dN = dN_.data();
+    out.x = x_.data();
+    out.Jt = Jt_.data();
+    out.detJ = detJ_.data();
+    out.JinvT = JinvT_.data();
+    if (derivOrder >= 2) {
+      d2N_.resize(npts * nb_ * nh);
+      H_.resize(npts * nh * dimworld);
+      out.d2N = d2N_.data();
+      out.H = H_.data();
+    }
+    check(igab_eval_tensor(h_, 0, nElements_, derivOrder, nq1.data(), xp.data(), &out, IGAB_HOST, nullptr));
+    haveRule_ = true;
+  }
+  bool hasRule() const { return haveRule_; }
+  int64_t pointsPerElement() const { return nq_; }
+  // weight of rule point q (product of the 1-D weights, first direction fastest)
+  double weight(int64_t q) const {
+    double r = 1;
+    for (int i = 0; i < dim; ++i) {
+      r *= w_[i][q % (int64_t)w_[i].size()];
+      q /= (int64_t)w_[i].size();
+    }
+    return r;
+  }
+  template <class Local>
+  void position(int64_t q, Local& xi) const {
+    for (int i = 0; i < dim; ++i) {
+      xi[i] = xi_[i][q % (int64_t)xi_[i].size()];
+      q /= (int64_t)xi_[i].size();
+    }
+  }
+
+  // index of the rule point equal to `in`, or -1
+  template <class Local>
+  int64_t findRulePoint(const Local& in) const {
+    if (!haveRule_) return -1;
+    int64_t q = 0, stride = 1;
+    for (int i = 0; i < dim; ++i) {
+      int64_t hit = -1;
+      for (size_t k = 0; k < xi_[i].size(); ++k)
+        if (xi_[i][k] == in[i]) hit = (int64_t)k;
+      if (hit < 0) return -1;
+      q += hit * stride;
+      stride *= (int64_t)xi_[i].size();
+    }
+    return q;
+  }
+
+  // cached rows
+  const double* N(int64_t e, int64_t q) const { return N_.data() + ((size_t)e * nq_ + q) * nb_; }
+  const double* dN(int64_t e, int64_t q) const { return dN_.data() + ((size_t)e * nq_ + q) * nb_ * dim; }
+  const double* d2N(int64_t e, int64_t q) const { return d2N_.data() + ((size_t)e * nq_ + q) * nb_ * nh; }
+  const double* x(int64_t e, int64_t q) const { return x_.data() + ((size_t)e * nq_ + q) * dimworld; }
+  const double* Jt(int64_t e, int64_t q) const { return Jt_.data() + ((size_t)e * nq_ + q) * dim * dimworld; }
+  const double* H(int64_t e, int64_t q) const { return H_.data() + ((size_t)e * nq_ + q) * nh * dimworld; }
+  double detJ(int64_t e, int64_t q) const { return detJ_[(size_t)e * nq_ + q]; }
+  const double* JinvT(int64_t e, int64_t q) const { return JinvT_.data() + ((size_t)e * nq_ + q) * dim * dimworld; }
+  int derivOrder() const { return order_; }
+
+  // single point on the GPU (off-rule arguments)
+  template <class Local>
+  void evalPoint(int64_t e, const Local& in, int order, igab_eval_out& out) const {
+    const int32_t el = (int32_t)e;
+    double xi[dim];
+    for (int i = 0; i < dim; ++i) xi[i] = in[i];
+    check(igab_eval_points(h_, 1, &el, xi, order, &out, IGAB_HOST, nullptr));
+  }
+
+  // sum over elements of NURBSGeometry::volume() as in gridtests.cpp:338-341 (device reduction)
+  double volume() const {
+    std::array<int, dim> nq1;
+    std::array<const double*, dim> xp, wp;
+    for (int i = 0; i < dim; ++i) {
+      nq1[i] = (int)xi_[i].size();
+      xp[i] = xi_[i].data();
+      wp[i] = w_[i].data();
+    }
+    double r = 0;
+    check(igab_reduce_volume(h_, 0, nElements_, nq1.data(), xp.data(), wp.data(), &r, nullptr, nullptr));
+    return r;
+  }
+
+private:
+  PatchData<dim, dimworld> data_;
+  igab_patch* h_ = nullptr;
+  int64_t nElements_ = 0, nDofs_ = 0, nq_ = 0;
+  std::array<int32_t, 3> nElDir_{};
+  int nb_ = 0, order_ = 1;
+  bool haveRule_ = false;
+  std::array<std::vector<double>, dim> xi_, w_;
+  std::vector<int32_t> dof_;
+  std::vector<double> N_, dN_, d2N_, x_, Jt_, H_, detJ_, JinvT_;
+};
+
+// ---- NurbsLocalBasis -------------------------------------------------------------------------------------------------
+template <int dim, int dimworld>
+class LocalBasis {
+public:
+  LocalBasis() = default;
+  LocalBasis(const Patch<dim, dimworld>* p, int64_t e) : p_(p), e_(e) {}
+
+  // out[i] = R_i(in); Range is anything assignable from double through out[i][0] (FieldVector<R,1>) or out[i] (double)
+  template <class Domain, class Range>
+  void evaluateFunction(const Domain& in, std::vector<Range>& out) const {
+    out.resize(p_->localSize());
+    const int64_t q = p_->findRulePoint(in);
+    if (q >= 0) {
+      const double* r = p_->N(e_, q);
+      for (int i = 0; i < p_->localSize(); ++i) set1(out[i], r[i]);
+      return;
+    }
+    std::vector<double> tmp(p_->localSize());
+    igab_eval_out o{};
+    o.N = tmp.data();
+    p_->evalPoint(e_, in, 0, o);
+    for (int i = 0; i < p_->localSize(); ++i) set1(out[i], tmp[i]);
+  }
+
+  // out[i][0][j] = dR_i/dxi_j on the reference element (already scaled by the span length, nurbsbasis.hh:93-95)
+  template <class Domain, class JacobianRange>
+  void evaluateJacobian(const Domain& in, std::vector<JacobianRange>& out) const {
+    out.resize(p_->localSize());
+    const int64_t q = p_->findRulePoint(in);
+    std::vector<double> tmp;
+    const double* r;
+    if (q >= 0) {
+      r = p_->dN(e_, q);
+    } else {
+      tmp.resize((size_t)p_->localSize() * dim);
+      igab_eval_out o{};
+      o.dN = tmp.data();
+      p_->evalPoint(e_, in, 1, o);
+      r = tmp.data();
+    }
+    for (int i = 0; i < p_->localSize(); ++i)
+      for (int j = 0; j < dim; ++j) out[i][0][j] = r[i * dim + j];
+  }
+
+  // any mixed derivative (nurbsbasis.hh:99-108); orders with |alpha| <= 2 on a rule point come from the cache
+  template <class Domain, class Range>
+  void partial(const std::array<unsigned int, dim>& order, const Domain& in, std::vector<Range>& out) const {
+    out.resize(p_->localSize());
+    unsigned total = 0;
+    for (auto o : order) total += o;
+    if (total == 0) return evaluateFunction(in, out);
+    std::vector<double> tmp(p_->localSize());
+    const int32_t el = (int32_t)e_;
+    double xi[dim];
+    int al[dim];
+    for (int i = 0; i < dim; ++i) {
+      xi[i] = in[i];
+      al[i] = (int)order[i];
+    }
+    check(igab_partial(p_->handle(), 1, &el, xi, al, tmp.data(), IGAB_HOST, nullptr));
+    for (int i = 0; i < p_->localSize(); ++i) set1(out[i], tmp[i]);
+  }
+
+  unsigned int order() const {
+    int m = 0;
+    for (int d : p_->patchData().degree) m = d > m ? d : m;
+    return (unsigned)m;
+  }
+  std::size_t size() const { return (std::size_t)p_->localSize(); }
+
+private:
+  template <class T>
+  static auto set1(T& t, double v) -> decltype(t[0] = v, void()) { t[0] = v; }
+  static void set1(double& t, double v) { t = v; }
+  const Patch<dim, dimworld>* p_ = nullptr;
+  int64_t e_ = 0;
+};
+
+// ---- NURBSGeometry ---------------------------------------------------------------------------------------------------
+template <int dim, int dimworld>
+class Geometry {
+public:
+  using GlobalCoordinate = std::array<double, dimworld>;
+  using JacobianTransposed = std::array<std::array<double, dimworld>, dim>;
+  using JacobianInverseTransposed = std::array<std::array<double, dim>, dimworld>;
+  Geometry() = default;
+  Geometry(const Patch<dim, dimworld>* p, int64_t e) : p_(p), e_(e) {}
+
+  template <class Local>
+  GlobalCoordinate global(const Local& local) const {
+    GlobalCoordinate r;
+    const int64_t q = p_->findRulePoint(local);
+    if (q >= 0) {
+      for (int c = 0; c < dimworld; ++c) r[c] = p_->x(e_, q)[c];
+    } else {
+      igab_eval_out o{};
+      o.x = r.data();
+      p_->evalPoint(e_, local, 0, o);
+    }
+    return r;
+  }
+  template <class Local>
+  JacobianTransposed jacobianTransposed(const Local& local) const {
+    double buf[dim * dimworld];
+    const double* s = buf;
+    const int64_t q = p_->findRulePoint(local);
+    if (q >= 0)
+      s = p_->Jt(e_, q);
+    else {
+      igab_eval_out o{};
+      o.Jt = buf;
+      p_->evalPoint(e_, local, 1, o);
+    }
+    JacobianTransposed r;
+    for (int d = 0; d < dim; ++d)
+      for (int c = 0; c < dimworld; ++c) r[d][c] = s[d * dimworld + c];
+    return r;
+  }
+  template <class Local>
+  double integrationElement(const Local& local) const {
+    const int64_t q = p_->findRulePoint(local);
+    if (q >= 0) return p_->detJ(e_, q);
+    double r = 0;
+    igab_eval_out o{};
+    o.detJ = &r;
+    p_->evalPoint(e_, local, 1, o);
+    return r;
+  }
+  template <class Local>
+  JacobianInverseTransposed jacobianInverseTransposed(const Local& local) const {
+    double buf[dim * dimworld];
+    const double* s = buf;
+    const int64_t q = p_->findRulePoint(local);
+    if (q >= 0)
+      s = p_->JinvT(e_, q);
+    else {
+      igab_eval_out o{};
+      o.JinvT = buf;
+      p_->evalPoint(e_, local, 1, o);
+    }
+    JacobianInverseTransposed r;
+    for (int c = 0; c < dimworld; ++c)
+      for (int d = 0; d < dim; ++d) r[c][d] = s[c * dim + d];
+    return r;
+  }
+  // sum_q detJ w over the element's rule (nurbsgeometry.hh:96-113)
+  double volume() const {
+    double v = 0;
+    for (int64_t q = 0; q < p_->pointsPerElement(); ++q) v += p_->detJ(e_, q) * p_->weight(q);
+    return v;
+  }
+  int corners() const { return 1 << dim; }
+  GlobalCoordinate corner(int k) const {
+    std::array<double, dim> l;
+    for (int i = 0; i < dim; ++i) l[i] = (k & (1 << i)) ? 1 : 0;
+    return global(l);
+  }
+  GlobalCoordinate center() const {
+    std::array<double, dim> l;
+    l.fill(0.5);
+    return global(l);
+  }
+  bool affine() const { return false; }
+
+private:
+  const Patch<dim, dimworld>* p_ = nullptr;
+  int64_t e_ = 0;
+};
+
+// ---- LocalView of a NurbsBasis: bind(element) / index(i) / tree().finiteElement().localBasis() --------------------
+template <int dim, int dimworld>
+class LocalView {
+public:
+  explicit LocalView(std::shared_ptr<const Patch<dim, dimworld>> p) : p_(std::move(p)) {}
+  void bind(int64_t elementIndex) {
+    if (elementIndex < 0 || elementIndex >= p_->size0()) throw Error(IGAB_INVALID_ARGUMENT, "bind: no such element");
+    e_ = elementIndex;
+    bound_ = true;
+    lb_ = LocalBasis<dim, dimworld>(p_.get(), e_);
+  }
+  void unbind() { bound_ = false; }
+  std::size_t size() const { return (std::size_t)p_->localSize(); }
+  // NurbsPreBasis::indices (nurbsbasis.hh:590-598): flat global index of local DOF i
+  int32_t index(std::size_t i) const {
+    if (!bound_) throw Error(IGAB_INVALID_ARGUMENT, "This element is not bound!");  // assert at nurbsbasis.hh:379
+    return p_->dofsOf(e_)[i];
+  }
+  const LocalBasis<dim, dimworld>& localBasis() const {
+    if (!bound_) throw Error(IGAB_INVALID_ARGUMENT, "This element is not bound!");
+    return lb_;
+  }
+  Geometry<dim, dimworld> geometry() const { return Geometry<dim, dimworld>(p_.get(), e_); }
+
+private:
+  std::shared_ptr<const Patch<dim, dimworld>> p_;
+  LocalBasis<dim, dimworld> lb_;
+  int64_t e_ = 0;
+  bool bound_ = false;
+};
+
+}  // namespace igab

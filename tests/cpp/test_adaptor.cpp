@@ -1,0 +1,181 @@
+// Reads like the reference's own quadrature-loop tests (dune/iga/test/gridtests.cpp:338-360, 514-576 and
+// dune/python/test/poisson.py:37-81), but through the batched adaptor over the C-ABI.  Checks every value against the
+// plain-C oracle (oracle/igab_oracle.c, test infrastructure) linked into THIS test binary only.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <vector>
+
+#include "../../dune-iga_b200/host/igab200_adaptor.hh"
+
+extern "C" {
+typedef struct {
+  int dim, dimworld;
+  int degree[3];
+  int nknots[3];
+  const double* knots[3];
+  int ncp[3];
+  const double* cp;
+} igo_patch;
+int igo_eval_tensor(const igo_patch*, long, long, int, const int*, const double*, double*, double*, double*, double*,
+                    double*, double*, double*, double*, int);
+long igo_dofmap(const igo_patch*, const unsigned char*, int*);
+void igo_gauss01(int, double*, double*);
+void igo_partial(const igo_patch*, long, const int*, const double*, const int*, double*);
+int igo_assemble(const igo_patch*, int, const double*, double, long, long, const int*, const double*, const double*,
+                 double*, double*, int);
+}
+
+static int failures = 0;
+#define CHECK(c, ...)                   \
+  do {                                  \
+    if (!(c)) {                         \
+      ++failures;                       \
+      std::printf("FAIL %s:%d ", __FILE__, __LINE__); \
+      std::printf(__VA_ARGS__);         \
+      std::printf("\n");                \
+    }                                   \
+  } while (0)
+
+static bool close(double a, double b, double scale) { return std::fabs(a - b) <= 1e-12 * std::fmax(scale, 1e-300); }
+
+int main() {
+  constexpr int dim = 2, dw = 2;
+  // quarter plate with hole, p = (2,2), 2 x 1 elements (SURVEY.md 8d C1 coarse patch)
+  const double s = (1.0 + 1.0 / std::sqrt(2.0)) / 2.0, r2 = std::sqrt(2.0);
+  igab::PatchData<dim, dw> pd;
+  pd.degree = {2, 2};
+  pd.knotSpans = {std::vector<double>{0, 0, 0, .5, 1, 1, 1}, std::vector<double>{0, 0, 0, 1, 1, 1}};
+  pd.controlPoints = {-1, 0, 1,  -1, r2 - 1, s,  1 - r2, 1, s,  0, 1, 1,   -2.5, 0, 1,  -2.5, .75, 1,  -.75, 2.5, 1,
+                      0, 2.5, 1,   -4, 0, 1,  -4, 4, 1,  -4, 4, 1,  0, 4, 1};
+  auto patch = std::make_shared<igab::Patch<dim, dw>>(pd);
+  CHECK(patch->size0() == 2, "elements %ld", (long)patch->size0());
+  CHECK(patch->numDofs() == 12, "dofs %ld", (long)patch->numDofs());
+
+  std::array<std::vector<double>, dim> xi, w;
+  for (int d = 0; d < dim; ++d) {
+    xi[d].resize(3);
+    w[d].resize(3);
+    igo_gauss01(3, xi[d].data(), w[d].data());
+  }
+  patch->setQuadratureRule(xi, w, 1);
+
+  // oracle
+  igo_patch op{};
+  op.dim = dim; op.dimworld = dw;
+  for (int d = 0; d < dim; ++d) {
+    op.degree[d] = pd.degree[d];
+    op.nknots[d] = (int)pd.knotSpans[d].size();
+    op.knots[d] = pd.knotSpans[d].data();
+    op.ncp[d] = op.nknots[d] - op.degree[d] - 1;
+  }
+  op.cp = pd.controlPoints.data();
+  const int nq1[2] = {3, 3};
+  std::vector<double> xcat(xi[0]);
+  xcat.insert(xcat.end(), xi[1].begin(), xi[1].end());
+  std::vector<double> wcat(w[0]);
+  wcat.insert(wcat.end(), w[1].begin(), w[1].end());
+  const int nb = 9, nq = 9, ne = 2;
+  std::vector<double> oN(ne * nq * nb), odN(ne * nq * nb * 2), ox(ne * nq * 2), oJ(ne * nq * 4), odet(ne * nq), oJi(ne * nq * 4);
+  igo_eval_tensor(&op, 0, ne, 1, nq1, xcat.data(), oN.data(), odN.data(), nullptr, ox.data(), oJ.data(), nullptr,
+                  odet.data(), oJi.data(), 1);
+  std::vector<int> odof(ne * nb);
+  igo_dofmap(&op, nullptr, odof.data());
+  std::vector<double> oKe(ne * nb * nb), ofe(ne * nb);
+  igo_assemble(&op, 0, nullptr, 1.0, 0, ne, nq1, xcat.data(), wcat.data(), oKe.data(), ofe.data(), 1);
+
+  // the loop of poisson.py:37-127, written against the adaptor
+  igab::LocalView<dim, dw> localView(patch);
+  double area = 0;
+  for (int64_t e = 0; e < patch->size0(); ++e) {
+    localView.bind(e);
+    const auto& localBasis = localView.localBasis();
+    const auto geo = localView.geometry();
+    const std::size_t n = localBasis.size();
+    std::vector<double> localA(n * n, 0.0), localB(n, 0.0);
+    for (int64_t q = 0; q < patch->pointsPerElement(); ++q) {
+      std::array<double, dim> pos;
+      patch->position(q, pos);
+      std::vector<std::array<double, 1>> phi;
+      std::vector<std::array<std::array<double, dim>, 1>> phiRefGradient;
+      localBasis.evaluateFunction(pos, phi);
+      localBasis.evaluateJacobian(pos, phiRefGradient);
+      const auto JinvT = geo.jacobianInverseTransposed(pos);
+      const double integrationElement = geo.integrationElement(pos);
+      const auto posGlobal = geo.global(pos);
+      const auto Jt = geo.jacobianTransposed(pos);
+      const long pt = e * nq + q;
+      for (std::size_t i = 0; i < n; ++i) {
+        CHECK(close(phi[i][0], oN[pt * nb + i], 1.0), "N e=%ld q=%ld i=%zu", (long)e, (long)q, i);
+        for (int j = 0; j < dim; ++j)
+          CHECK(close(phiRefGradient[i][0][j], odN[(pt * nb + i) * 2 + j], 4.0), "dN");
+      }
+      for (int c = 0; c < dw; ++c) CHECK(close(posGlobal[c], ox[pt * 2 + c], 4.0), "x");
+      for (int d = 0; d < dim; ++d)
+        for (int c = 0; c < dw; ++c) {
+          CHECK(close(Jt[d][c], oJ[pt * 4 + d * 2 + c], 8.0), "Jt");
+          CHECK(close(JinvT[c][d], oJi[pt * 4 + c * 2 + d], 8.0), "JinvT");
+        }
+      CHECK(close(integrationElement, odet[pt], 8.0), "detJ");
+      std::vector<std::array<double, dim>> grad(n);
+      for (std::size_t i = 0; i < n; ++i)
+        for (int c = 0; c < dw; ++c) {
+          grad[i][c] = 0;
+          for (int d = 0; d < dim; ++d) grad[i][c] += JinvT[c][d] * phiRefGradient[i][0][d];
+        }
+      const double wq = patch->weight(q);
+      for (std::size_t i = 0; i < n; ++i) {
+        for (std::size_t j = 0; j < n; ++j)
+          localA[i * n + j] += wq * integrationElement * (grad[i][0] * grad[j][0] + grad[i][1] * grad[j][1]);
+        localB[i] += wq * integrationElement * phi[i][0] * 1.0;
+      }
+    }
+    for (std::size_t i = 0; i < n; ++i) {
+      CHECK(localView.index(i) == odof[e * nb + i], "dof map e=%ld i=%zu", (long)e, i);
+      CHECK(close(localB[i], ofe[e * nb + i], 1.0), "fe");
+      for (std::size_t j = 0; j < n; ++j) CHECK(close(localA[i * n + j], oKe[(e * nb + i) * nb + j], 10.0), "Ke");
+    }
+    area += geo.volume();
+  }
+  CHECK(std::fabs(area - patch->volume()) < 1e-13, "volume sum %g vs reduction %g", area, patch->volume());
+  CHECK(std::fabs(area - (16.0 - M_PI / 4.0)) < 2e-2, "area %g", area);  // coarse 2-element patch, 3x3 Gauss
+
+  // off-rule points: corners and corner +- 1e-8 (gridtests.cpp:514-576): evaluateJacobian[:,d] == partial(e_d) to 1e-14
+  localView.bind(1);
+  const double probes[5] = {0.0, 1e-8, 0.3, 1 - 1e-8, 1.0};
+  for (double a : probes)
+    for (double b : probes) {
+      std::array<double, dim> pos{a, b};
+      std::vector<std::array<std::array<double, dim>, 1>> J;
+      localView.localBasis().evaluateJacobian(pos, J);
+      for (int d = 0; d < dim; ++d) {
+        std::array<unsigned int, dim> order{};
+        order[d] = 1;
+        std::vector<std::array<double, 1>> part;
+        localView.localBasis().partial(order, pos, part);
+        for (std::size_t i = 0; i < J.size(); ++i)
+          CHECK(std::fabs(J[i][0][d] - part[i][0]) <= 1e-14 * std::fmax(1.0, std::fabs(part[i][0])), "J vs partial");
+      }
+    }
+  CHECK(localView.localBasis().order() == 2 && localView.localBasis().size() == 9, "order/size");
+
+  // error behaviour: unbound view, bad element, bad knot vector
+  igab::LocalView<dim, dw> v2(patch);
+  bool threw = false;
+  try { v2.index(0); } catch (const igab::Error&) { threw = true; }
+  CHECK(threw, "unbound index must throw");
+  threw = false;
+  try { v2.bind(99); } catch (const igab::Error&) { threw = true; }
+  CHECK(threw, "bind out of range must throw");
+  threw = false;
+  try {
+    auto bad = pd;
+    bad.knotSpans[0] = {0, 0, .5, 1, 1, 1, 1};
+    igab::Patch<dim, dw> pbad(bad);
+  } catch (const igab::Error& e) { threw = e.status == IGAB_INVALID_ARGUMENT; }
+  CHECK(threw, "closed knot vector must be rejected");
+
+  std::printf(failures ? "adaptor test: %d FAILURES\n" : "adaptor test: ok\n", failures);
+  return failures ? 1 : 0;
+}

@@ -29,3 +29,10 @@ t_fill = timeit(lambda: big.fill_(1.5))
 t_zero = timeit(lambda: big.zero_())
 print(json.dumps({"copy_GBs": 2 * a.numel() * 8 / t_copy / 1e6, "fill_GBs": big.numel() * 8 / t_fill / 1e6,
                   "memset_GBs": big.numel() * 8 / t_zero / 1e6}))
+
+# PCIe: pinned host <-> device, 2 GiB
+h = torch.empty(256 * 1024 ** 2, dtype=torch.float64).pin_memory()
+d = torch.empty_like(h, device="cuda")
+t_h2d = timeit(lambda: d.copy_(h, non_blocking=True), reps=3)
+t_d2h = timeit(lambda: h.copy_(d, non_blocking=True), reps=3)
+print(json.dumps({"h2d_GBs": h.numel() * 8 / t_h2d / 1e6, "d2h_GBs": h.numel() * 8 / t_d2h / 1e6}))
