@@ -114,13 +114,14 @@ def run_reference(args, rank, world):
     xi = [PD.gaussLegendre01(NQ1)[0]] * 3
     layers = 1  # 16,384 elements = 1,048,576 points per step
     nel = 128 * 128 * layers
+    ncpu = len(os.sched_getaffinity(0))  # torchrun exports OMP_NUM_THREADS=1: ask for every core explicitly
     for _ in range(args.warmup):
-        O.eval_tensor(xi, order=1, elem_begin=0, elem_end=nel, want=FIELDS)
+        O.eval_tensor(xi, order=1, elem_begin=0, elem_end=nel, want=FIELDS, nthreads=ncpu)
     t0 = time.perf_counter()
     threads = 1
     for s in range(args.steps):
         eb = (s % 64) * nel
-        threads = O.eval_tensor(xi, order=1, elem_begin=eb, elem_end=eb + nel, want=FIELDS)["threads"]
+        threads = O.eval_tensor(xi, order=1, elem_begin=eb, elem_end=eb + nel, want=FIELDS, nthreads=ncpu)["threads"]
     dt = time.perf_counter() - t0
     val = args.steps * nel * NQ / dt
     sample = "%d k-layer(s) of the C2 patch per step (%d elements, %d points), outputs %s" % (
@@ -300,9 +301,10 @@ def main():
             O, kind = PT.PortPatch(pd.degree, pd.knotSpans, pd.cp, 3), "port"
         c_layers = 4
         c_el = 128 * 128 * c_layers
-        O.eval_tensor(xi, order=1, elem_begin=0, elem_end=128 * 16, want=FIELDS)  # warm
+        ncpu = len(os.sched_getaffinity(0))
+        O.eval_tensor(xi, order=1, elem_begin=0, elem_end=128 * 16, want=FIELDS, nthreads=ncpu)  # warm
         t0 = time.perf_counter()
-        r = O.eval_tensor(xi, order=1, elem_begin=0, elem_end=c_el, want=FIELDS)
+        r = O.eval_tensor(xi, order=1, elem_begin=0, elem_end=c_el, want=FIELDS, nthreads=ncpu)
         dt = time.perf_counter() - t0
         cpu = {"value": c_el * NQ / dt, "unit": "points/s", "cores": r["threads"], "kind": kind,
                "sample": "%d k-layers of the same patch (%d elements, %d points), same outputs, %.1f s wall" % (

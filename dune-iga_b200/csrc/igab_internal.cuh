@@ -76,6 +76,11 @@ igab_status launch_eval_tensor_sf(const PatchDev& P, SfWorkspace& ws, const Poin
                                   cudaStream_t stream);
 void free_sf_workspace(SfWorkspace& ws);
 bool eval_tensor_sf_supported(const PatchDev& P, const int* nq1, int order, const EvalOutDev& out);
+// 2-D family (thread per point, compile-time degree / rule / order)
+bool eval_tensor_2d_supported(const PatchDev& P, const int* nq1, int order, const EvalOutDev& out);
+igab_status launch_eval_tensor_2d(const PatchDev& P, SfWorkspace& ws, const PointSource& src,
+                                  const double* const* xi1d_host, long long nelem, int order, const EvalOutDev& out,
+                                  cudaStream_t stream);
 igab_status launch_partial(const PatchDev& P, long long npts, const int* elem, const double* xi, const int* alpha,
                            double* out, cudaStream_t stream);
 igab_status launch_spans(const PatchDev& P, int32_t* span, cudaStream_t stream);

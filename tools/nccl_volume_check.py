@@ -1,0 +1,70 @@
+"""Multi-GPU check of the patch reduction fused with its NCCL all-reduce (run under torchrun on >= 2 GPUs):
+each rank reduces the volume of its element slab on its own GPU, igab_reduce_volume all-reduces the scalar through the
+process group's NCCL communicator... torch does not expose its ncclComm_t, so this script creates one with the
+NCCL C API (ncclGetUniqueId broadcast through torch.distributed)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import igab200  # noqa: E402,F401
+from dune_iga_b200 import capi, partition, patchdata as PD  # noqa: E402
+
+
+def nccl_lib():
+    import glob
+    import torch as _t
+    cands = glob.glob(os.path.join(os.path.dirname(_t.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so.2"))
+    return C.CDLL(cands[0] if cands else "libnccl.so.2", mode=C.RTLD_GLOBAL)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nccl = nccl_lib()
+    uid = (C.c_char * 128)()
+    if rank == 0:
+        assert nccl.ncclGetUniqueId(C.byref(uid)) == 0
+    t = torch.tensor(list(uid.raw), dtype=torch.uint8, device="cuda")
+    dist.broadcast(t, 0)
+    uid = (C.c_char * 128).from_buffer_copy(bytes(t.cpu().tolist()))
+    comm = C.c_void_p()
+
+    class UID(C.Structure):
+        _fields_ = [("internal", C.c_char * 128)]
+    u = UID()
+    C.memmove(C.byref(u), uid, 128)
+    nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UID, C.c_int]
+    assert nccl.ncclCommInitRank(C.byref(comm), world, u, rank) == 0
+
+    pd = PD.thickCylinder(3, (4, 4, 5))
+    P = capi.Patch.fromPatchData(pd)
+    eb, ee = partition.slab_range(pd.elementsPerDirection, world, rank)
+    x, w = PD.gaussLegendre01(4)
+    mine = P.volume([x] * 3, [w] * 3, eb, ee)
+    total = P.volume([x] * 3, [w] * 3, eb, ee, nccl_comm=comm)
+    whole = P.volume([x] * 3, [w] * 3)
+    exact = np.pi / 4 * (2.0 ** 2 - 1.0 ** 2) * 3.0
+    allv = [None] * world
+    dist.all_gather_object(allv, (mine, total))
+    if rank == 0:
+        print("ranks:", allv, "whole:", whole, "exact:", exact)
+        assert all(abs(v[1] - whole) <= 1e-12 * whole for v in allv)
+        assert len({v[1] for v in allv}) == 1
+        assert abs(sum(v[0] for v in allv) - whole) <= 1e-12 * whole
+        assert abs(whole - exact) < 1e-9
+        print("nccl volume check ok")
+    nccl.ncclCommDestroy.argtypes = [C.c_void_p]
+    nccl.ncclCommDestroy(comm)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
