@@ -205,6 +205,147 @@ __global__ void __launch_bounds__(128) contract_dmma_kernel(int n, int kdim, con
     }
 }
 
+// ---- (3c) fused Gram kernel for 3-D Poisson / mass at nb >= 33 (p >= 3): no B-stack in HBM ---------------------------
+// K_e[i][j] = sum_q w_q detJ_q sum_c G_q[c][i] G_q[c][j],  G_q = J_q^-T grad_xi R(q)   (poisson.py:58,64-77)
+// One block per element (persistent, grid-stride).  The quadrature points are consumed in chunks of 16 k-rows
+// (5 points x 3 gradient components + 1 zero row, or 16 points for the mass matrix).  Software pipeline, ONE
+// __syncthreads per chunk:   phase c = { issue the global loads of chunk c+1 (dN rows, coalesced) into registers;
+//                                        contract chunk c on the FP64 tensor cores (mma.sync.m8n8k4.f64, SASS DMMA)
+//                                        from shared buffer c&1 into register accumulators;
+//                                        turn the prefetched rows into physical gradients with J^-T and store them
+//                                        into buffer (c+1)&1;  stage J^-T / w detJ of chunk c+2 }.
+// The per-row scale w detJ is applied to the B-operand fragment, so only ONE stack lives in shared memory.
+// Each warp owns a 32 x (NBP/WARPS_N) block of K_e.
+template <int NBP, int WARPS_M, int WARPS_N, int NROW>
+__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gram_dmma_kernel(
+    int nb, int nq, long long nelem, int nq0, int nq1_, int nq2, const double* __restrict__ w0,
+    const double* __restrict__ w1, const double* __restrict__ w2, const double* __restrict__ N,
+    const double* __restrict__ dN, const double* __restrict__ detJ, const double* __restrict__ JinvT,
+    double* __restrict__ Ke) {
+  constexpr int KC = 16, LD = NBP + 4, NT = WARPS_M * WARPS_N * 32;
+  constexpr int TM = NBP / WARPS_M / 8, TN = NBP / WARPS_N / 8;  // 8x8 tiles per warp
+  constexpr int nrow = NROW, NV = NROW == 3 ? 3 : 1;
+  constexpr int MAXIT = ((KC / NROW) * NBP + NT - 1) / NT;
+  static_assert(NBP / WARPS_M == 32, "each warp owns 32 rows");
+  __shared__ double sA[2][KC][LD];
+  __shared__ double sS[3][KC];
+  __shared__ double sJ[3][KC][9];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wi = (warp / WARPS_N) * 32, wj = (warp % WARPS_N) * (NBP / WARPS_N);
+  constexpr int pts = KC / NROW;  // points per chunk (5 | 16)
+  const int nchunk = (nq + pts - 1) / pts;
+  constexpr int nitem = pts * NBP;
+  for (int idx = threadIdx.x; idx < 2 * KC * LD; idx += NT) (&sA[0][0][0])[idx] = 0.0;
+
+  // stage J^-T and w detJ of chunk ch of element e into ring slot ch % 3
+  auto stage_consts = [&](long long e, int ch) {
+    const int slot = ch % 3, q0c = ch * pts, npt = min(pts, nq - q0c);
+    if (nrow == 3 && threadIdx.x < pts * 9) {
+      const int ql = threadIdx.x / 9, k = threadIdx.x % 9;
+      sJ[slot][ql][k] = ql < npt ? JinvT[(e * nq + q0c + ql) * 9 + k] : 0.0;
+    } else if (threadIdx.x >= 64 && threadIdx.x < 64 + KC) {
+      const int k = threadIdx.x - 64, ql = k / nrow;
+      double sc = 0.0;
+      if (ql < npt && k < pts * nrow) {
+        int q = q0c + ql;
+        double w = w0[q % nq0];
+        q /= nq0;
+        w *= w1[q % nq1_];
+        q /= nq1_;
+        w *= w2[q % nq2];
+        sc = w * detJ[e * nq + q0c + ql];
+      }
+      sS[slot][k] = sc;
+    }
+  };
+  // global loads of one chunk into registers (3 doubles per item for gradients, 1 for the mass matrix)
+  auto prefetch = [&](long long e, int ch, double (&r)[MAXIT][NV]) {
+    const int q0c = ch * pts, npt = min(pts, nq - q0c);
+#pragma unroll
+    for (int m = 0; m < MAXIT; ++m) {
+      const int item = threadIdx.x + m * NT;
+      const int ql = item / NBP, i = item % NBP;
+      const bool live = item < nitem && ql < npt && i < nb;
+      const long long pt = e * nq + q0c + ql;
+      if constexpr (NROW == 3) {
+        const double* d = dN + (pt * nb + i) * 3;
+        r[m][0] = live ? d[0] : 0.0;
+        r[m][1] = live ? d[1] : 0.0;
+        r[m][2] = live ? d[2] : 0.0;
+      } else {
+        r[m][0] = live ? N[pt * nb + i] : 0.0;
+      }
+    }
+  };
+  auto build = [&](int ch, const double (&r)[MAXIT][NV]) {
+    const int buf = ch & 1, slot = ch % 3;
+#pragma unroll
+    for (int m = 0; m < MAXIT; ++m) {
+      const int item = threadIdx.x + m * NT;
+      if (item < nitem) {
+        const int ql = item / NBP, i = item % NBP;
+        if constexpr (NROW == 3) {
+          const double* J = sJ[slot][ql];
+          sA[buf][3 * ql + 0][i] = J[0] * r[m][0] + J[1] * r[m][1] + J[2] * r[m][2];
+          sA[buf][3 * ql + 1][i] = J[3] * r[m][0] + J[4] * r[m][1] + J[5] * r[m][2];
+          sA[buf][3 * ql + 2][i] = J[6] * r[m][0] + J[7] * r[m][1] + J[8] * r[m][2];
+        } else {
+          sA[buf][ql][i] = r[m][0];
+        }
+      }
+    }
+  };
+
+  for (long long e = blockIdx.x; e < nelem; e += gridDim.x) {
+    double c[TM][TN][2];
+#pragma unroll
+    for (int a = 0; a < TM; ++a)
+#pragma unroll
+      for (int b = 0; b < TN; ++b) c[a][b][0] = c[a][b][1] = 0.0;
+    double r[MAXIT][NV];
+    // prologue: constants of chunks 0, 1; stack of chunk 0
+    stage_consts(e, 0);
+    __syncthreads();  // also orders the previous element's last DMMA reads before buffers are rewritten
+    if (nchunk > 1) stage_consts(e, 1);
+    prefetch(e, 0, r);
+    build(0, r);
+    __syncthreads();
+    for (int ch = 0; ch < nchunk; ++ch) {
+      const bool more = ch + 1 < nchunk;
+      if (more) prefetch(e, ch + 1, r);
+      if (ch + 2 < nchunk) stage_consts(e, ch + 2);
+      const int buf = ch & 1, slot = ch % 3;
+#pragma unroll
+      for (int ks = 0; ks < KC; ks += 4) {
+        double af[TM], bf[TN];
+        const double sc = sS[slot][ks + t];
+#pragma unroll
+        for (int a = 0; a < TM; ++a) af[a] = sA[buf][ks + t][wi + 8 * a + g];
+#pragma unroll
+        for (int b = 0; b < TN; ++b) bf[b] = sA[buf][ks + t][wj + 8 * b + g] * sc;
+#pragma unroll
+        for (int a = 0; a < TM; ++a)
+#pragma unroll
+          for (int b = 0; b < TN; ++b) dmma8x8x4(c[a][b][0], c[a][b][1], af[a], bf[b]);
+      }
+      if (more) build(ch + 1, r);
+      __syncthreads();
+    }
+    double* K = Ke + e * (long long)nb * nb;
+#pragma unroll
+    for (int a = 0; a < TM; ++a)
+#pragma unroll
+      for (int b = 0; b < TN; ++b) {
+        const int i = wi + 8 * a + g, j = wj + 8 * b + 2 * t;
+        if (i < nb) {
+          if (j < nb) K[(long long)i * nb + j] = c[a][b][0];
+          if (j + 1 < nb) K[(long long)i * nb + j + 1] = c[a][b][1];
+        }
+      }
+  }
+}
+
 // ---- K6: deterministic volume reduction -----------------------------------------------------------------------------
 // partial[b] = sum over a fixed contiguous slice of points of detJ*w (sequential per thread, fixed tree per block);
 // result = fixed-order sum of the partials.  Same launch geometry => bitwise reproducible.
@@ -272,8 +413,10 @@ igab_status assemble_dd(const PatchDev& P, SfWorkspace& ws, const double* const*
   const int nrow = kind == IGAB_ASM_MASS ? 1 : (kind == IGAB_ASM_POISSON ? DW : (DIM == 2 ? 3 : 6));
   const int kdim = (int)nq * nrow;
   // element chunks bounded by scratch (A1 + A2 dominate)
-  const long long perEl = 8LL * (2LL * kdim * n + nq * (nb + nb * DIM + 1 + DIM * DW));
-  const long long chunk = std::max(1LL, std::min(nel, (2LL << 30) / perEl));
+  // fused Gram path: 3-D Poisson / mass with a local basis of 33..128 functions (p = 3, 4): no B-stack in HBM
+  const bool gram = DIM == 3 && DW == 3 && kind != IGAB_ASM_ELASTICITY && nb > 32 && nb <= 128;
+  const long long perEl = 8LL * ((gram ? 0LL : 2LL * kdim * n) + nq * (nb + nb * DIM + 1 + DIM * DW));
+  const long long chunk = std::max(1LL, std::min(nel, (4LL << 30) / perEl));
   const int q0 = nq1[0], q1 = DIM > 1 ? nq1[1] : 1, q2 = DIM > 2 ? nq1[2] : 1;
   for (long long c0 = 0; c0 < nel; c0 += chunk) {
     const long long m = std::min(chunk, nel - c0);
@@ -283,31 +426,52 @@ igab_status assemble_dd(const PatchDev& P, SfWorkspace& ws, const double* const*
     IGAB_CUDA_TRY(cudaMallocAsync(&ddN, 8 * npts * nb * DIM, stream));
     IGAB_CUDA_TRY(cudaMallocAsync(&ddet, 8 * npts, stream));
     IGAB_CUDA_TRY(cudaMallocAsync(&dJi, 8 * npts * DIM * DW, stream));
-    IGAB_CUDA_TRY(cudaMallocAsync(&A1, 8LL * m * kdim * n, stream));
-    IGAB_CUDA_TRY(cudaMallocAsync(&A2, 8LL * m * kdim * n, stream));
+    if (!gram) {
+      IGAB_CUDA_TRY(cudaMallocAsync(&A1, 8LL * m * kdim * n, stream));
+      IGAB_CUDA_TRY(cudaMallocAsync(&A2, 8LL * m * kdim * n, stream));
+    }
     EvalOutDev o{};
     o.N = dNv; o.dN = ddN; o.detJ = ddet; o.JinvT = dJi;
     igab_status st = eval_for(P, ws, xi1d_host, eb + c0, m, nq1, xi, o, stream);
     if (st) return st;
-    if (kind == IGAB_ASM_ELASTICITY) {
-      // zero the structural zeros of B once (bstack writes every entry of its rows, so nothing to clear)
-    }
-    {
+    double* K = Ke + (long long)c0 * n * n;
+    if (gram) {
+      static int sms = 0;
+      if (!sms) {
+        int dev = 0;
+        IGAB_CUDA_TRY(cudaGetDevice(&dev));
+        IGAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      }
+      const bool mass = kind == IGAB_ASM_MASS;
+      if (nb > 64) {
+        const unsigned grid = (unsigned)std::min<long long>(m, sms);
+        if (mass)
+          gram_dmma_kernel<128, 4, 2, 1><<<grid, 256, 0, stream>>>(nb, (int)nq, m, q0, q1, q2, w[0], w[1], w[2], dNv, ddN, ddet, dJi, K);
+        else
+          gram_dmma_kernel<128, 4, 2, 3><<<grid, 256, 0, stream>>>(nb, (int)nq, m, q0, q1, q2, w[0], w[1], w[2], dNv, ddN, ddet, dJi, K);
+      } else {
+        const unsigned grid = (unsigned)std::min<long long>(m, 2LL * sms);
+        if (mass)
+          gram_dmma_kernel<64, 2, 2, 1><<<grid, 128, 0, stream>>>(nb, (int)nq, m, q0, q1, q2, w[0], w[1], w[2], dNv, ddN, ddet, dJi, K);
+        else
+          gram_dmma_kernel<64, 2, 2, 3><<<grid, 128, 0, stream>>>(nb, (int)nq, m, q0, q1, q2, w[0], w[1], w[2], dNv, ddN, ddet, dJi, K);
+      }
+      count_launch();
+    } else {
       const long long tot = npts * nb;
       bstack_kernel<DIM, DW><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(
           kind, npts, nb, nq, q0, q1, q2, w[0], w[DIM > 1 ? 1 : 0], w[DIM > 2 ? 2 : 0], dNv, ddN, ddet, dJi, D_dev, A1, A2,
           nrow, n);
       count_launch();
+      if (n >= 32) {
+        dim3 grid((n + 63) / 64, (n + 63) / 64, (unsigned)m);
+        contract_dmma_kernel<<<grid, 128, 0, stream>>>(n, kdim, A1, A2, K);
+      } else {
+        dim3 grid((n + 31) / 32, (n + 31) / 32, (unsigned)m);
+        contract_fma_kernel<<<grid, 256, 0, stream>>>(n, kdim, A1, A2, K);
+      }
+      count_launch();
     }
-    double* K = Ke + (long long)c0 * n * n;
-    if (n >= 32) {
-      dim3 grid((n + 63) / 64, (n + 63) / 64, (unsigned)m);
-      contract_dmma_kernel<<<grid, 128, 0, stream>>>(n, kdim, A1, A2, K);
-    } else {
-      dim3 grid((n + 31) / 32, (n + 31) / 32, (unsigned)m);
-      contract_fma_kernel<<<grid, 256, 0, stream>>>(n, kdim, A1, A2, K);
-    }
-    count_launch();
     if (fe) {
       const long long tot = m * nb;
       load_kernel<DIM><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(m, nb, ncomp, nq, q0, q1, q2, w[0],
@@ -317,7 +481,9 @@ igab_status assemble_dd(const PatchDev& P, SfWorkspace& ws, const double* const*
     }
     IGAB_CUDA_TRY(cudaGetLastError());
     cudaFreeAsync(dNv, stream); cudaFreeAsync(ddN, stream); cudaFreeAsync(ddet, stream);
-    cudaFreeAsync(dJi, stream); cudaFreeAsync(A1, stream); cudaFreeAsync(A2, stream);
+    cudaFreeAsync(dJi, stream);
+    if (A1) cudaFreeAsync(A1, stream);
+    if (A2) cudaFreeAsync(A2, stream);
   }
   return IGAB_OK;
 }

@@ -334,6 +334,15 @@ igab_status igab_patch_create(int dim, int dimworld, const int* degree, const in
     delete p;
     return st;
   }
+  {
+    // keep stream-ordered scratch (cudaMallocAsync) cached in the pool instead of returning it to the driver at every
+    // synchronisation: the assembly / reduction paths allocate per call
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, p->device) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
   auto fail = [&](cudaError_t err, const char* what) {
     igab_status st = cuda_fail(err, what);
     igab_patch_destroy(p);
