@@ -1,0 +1,142 @@
+"""GPU tests at BASELINE.json's full sizes (-m gpu): the oracle cannot reach these sizes in seconds, so the whole
+output is checked on the device through size-independent properties (partition of unity, gradient sums, exact radius of
+the cylinder map, detJ == |det J|, volume in closed form, scaling / linearity of the geometry, run-to-run bitwise
+reproducibility), and a random sample of elements is compared with the oracle."""
+import numpy as np
+import pytest
+
+import igab200  # noqa: F401
+import portbind as PT
+from dune_iga_b200 import capi, patchdata as PD, quadrature as Q
+from parity_util import TOL, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def dev_out(P, npts, fields):
+    import torch
+    sh = P.shapes(npts)
+    return {f: torch.empty(sh[f], dtype=torch.float64, device="cuda") for f in fields}
+
+
+def test_c2_full_patch_properties():
+    import torch
+    pd = PD.thickCylinder(3, (7, 7, 7))  # 128^3 elements, 131^3 control points
+    P = capi.Patch.fromPatchData(pd)
+    P.setKernel(capi.KERNEL_TENSOR)
+    assert P.nelem == 128 ** 3
+    x1, w1 = Q.gaussLegendre01(4)
+    xi, w = [x1] * 3, [w1] * 3
+    fields = ("N", "dN", "x", "Jt", "detJ")
+    layers = 4
+    nel = 128 * 128 * layers
+    npts = nel * 64
+    out = dev_out(P, npts, fields)
+    s = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(0)
+    Pp = PT.PortPatch(pd.degree, pd.knotSpans, pd.cp, 3)
+    for k0 in (0, 62, 124):  # first, middle, last slab of elements
+        eb = 128 * 128 * k0
+        P.evalTensor(xi, order=1, elem_begin=eb, elem_end=eb + nel, want=fields, out=out, stream=s)
+        torch.cuda.synchronize()
+        assert float((out["N"].sum(1) - 1).abs().max()) < 2e-14
+        assert float(out["dN"].sum(1).abs().max()) < 1e-11
+        assert float(out["detJ"].min()) > 0
+        r = torch.hypot(out["x"][:, 0], out["x"][:, 1])
+        assert float(r.min()) >= 1 - 1e-12 and float(r.max()) <= 2 + 1e-12
+        # radius is affine in the radial parameter and z in the axial one: check against the rule's coordinates
+        det = torch.linalg.det(out["Jt"])
+        assert float((det.abs() - out["detJ"]).abs().max() / out["detJ"].max()) < 1e-13
+        # bitwise reproducible
+        ref = {f: out[f].clone() for f in fields}
+        P.evalTensor(xi, order=1, elem_begin=eb, elem_end=eb + nel, want=fields, out=out, stream=s)
+        torch.cuda.synchronize()
+        assert all(torch.equal(ref[f], out[f]) for f in fields)
+        # oracle on a random sample of elements of this slab
+        for e in rng.integers(eb, eb + nel, 6):
+            o = Pp.eval_tensor(xi, order=1, elem_begin=int(e), elem_end=int(e) + 1, want=fields)
+            sl = slice((int(e) - eb) * 64, (int(e) - eb + 1) * 64)
+            for f in fields:
+                assert relerr(out[f][sl].cpu().numpy(), o[f]) <= TOL, (f, int(e))
+    # closed-form volume of the quarter cylinder shell: pi/4 (r_o^2 - r_i^2) L
+    vol = P.volume(xi, w)
+    assert abs(vol - np.pi / 4 * 3.0 * 3.0) < 1e-11
+    # scaling the control net by 2 doubles x and J, multiplies detJ by 8, leaves N untouched
+    P.evalTensor(xi, order=1, elem_begin=0, elem_end=nel, want=fields, out=out, stream=s)
+    torch.cuda.synchronize()
+    base = {f: out[f].clone() for f in fields}
+    cp2 = pd.cp.copy()
+    cp2[:, :3] *= 2.0
+    P.updateControlPoints(cp2)
+    P.evalTensor(xi, order=1, elem_begin=0, elem_end=nel, want=fields, out=out, stream=s)
+    torch.cuda.synchronize()
+    assert torch.equal(out["N"], base["N"]) and torch.equal(out["dN"], base["dN"])
+    assert torch.equal(out["x"], 2 * base["x"]) and torch.equal(out["Jt"], 2 * base["Jt"])
+    assert float((out["detJ"] - 8 * base["detJ"]).abs().max() / base["detJ"].max()) < 1e-14
+
+
+def test_c4_full_torus_shell():
+    """1024 x 1024 elements, 4 x 4 Gauss, second derivatives: torus area and Gauss-Bonnet on the device
+    (gridtests.cpp:338-363 at config-C4 size)."""
+    import torch
+    pd = PD.torusSurface(8)
+    P = capi.Patch.fromPatchData(pd)
+    assert P.nelem == 1024 * 1024
+    x1, w1 = Q.gaussLegendre01(4)
+    fields = ("N", "d2N", "Jt", "H", "detJ")
+    out = dev_out(P, P.nelem * 16, fields)
+    P.evalTensor([x1, x1], order=2, want=fields, out=out, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ww = torch.from_numpy(np.outer(w1, w1).reshape(-1)).cuda().repeat(P.nelem)
+    area = float((out["detJ"] * ww).sum())
+    assert abs(area - 4 * np.pi ** 2 * 1.0 * 2.0) < 1e-9
+    J, H = out["Jt"], out["H"]
+    nrm = torch.linalg.cross(J[:, 0], J[:, 1])
+    nrm = nrm / nrm.norm(dim=1, keepdim=True)
+    b00, b11, b01 = (H[:, 0] * nrm).sum(1), (H[:, 1] * nrm).sum(1), (H[:, 2] * nrm).sum(1)
+    g00, g11, g01 = (J[:, 0] ** 2).sum(1), (J[:, 1] ** 2).sum(1), (J[:, 0] * J[:, 1]).sum(1)
+    K = (b00 * b11 - b01 ** 2) / (g00 * g11 - g01 ** 2)
+    assert abs(float((K * out["detJ"] * ww).sum())) < 1e-8
+    assert float(K.min()) >= -1.0 - 1e-8 and float(K.max()) <= 1 / 3.0 + 1e-8
+    assert float((out["N"].sum(1) - 1).abs().max()) < 2e-14
+    assert float(out["d2N"].sum(1).abs().max()) < 1e-6 * float(out["d2N"].abs().max())
+
+
+def test_c5_trimmed_batches():
+    """Config C5: tensor rule on full elements + per-element point lists on trimmed elements (fillquadraturerule
+    format).  Square plate [0,1]^2, p=3, hole of radius 0.25 at the centre triangulated per element."""
+    # unit weights: the map is the identity on [0,1]^2, so trimmed areas are known in closed form
+    pd = PD.NurbsPatchData([[0, 0, 1, 1], [0, 0, 1, 1]], [(0, 0, 1), (1, 0, 1), (0, 1, 1), (1, 1, 1)], [1, 1], 2)
+    pd = pd.degreeElevate(0, 2).degreeElevate(1, 2).globalRefine(5)  # p = 3, 32 x 32 elements
+    P = capi.Patch.fromPatchData(pd)
+    Pp = PT.PortPatch(pd.degree, pd.knotSpans, pd.cp, 2)
+    n = 32
+    rng = np.random.default_rng(42)
+    # synthetic trimmed elements: random sub-triangulations covering a known fraction of each chosen element
+    chosen = np.sort(rng.choice(n * n, 60, replace=False))
+    tris, frac = {}, {}
+    for e in chosen:
+        c = rng.uniform(0.3, 0.7, 2)
+        # fan of 4 triangles around an interior point covers the whole element; drop one => known area
+        corners = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], float)
+        fan = [np.array([c, corners[k], corners[(k + 1) % 4]]) for k in range(4)]
+        keep = fan[:3]
+        tris[int(e)] = np.array(keep)
+        frac[int(e)] = sum(0.5 * abs((t[1] - t[0])[0] * (t[2] - t[0])[1] - (t[1] - t[0])[1] * (t[2] - t[0])[0]) for t in keep)
+    elem, xi, w, off = Q.trimmedBatch(tris, order=4)
+    got = P.evalPoints(elem, xi, order=1, want=("N", "dN", "x", "Jt", "detJ"))
+    ref = Pp.eval_points(elem, xi, order=1, want=("N", "dN", "x", "Jt", "detJ"))
+    for f in ("N", "dN", "x", "Jt", "detJ"):
+        assert relerr(got[f], ref[f]) <= TOL, f
+    # the plate is the identity map scaled by 1/32 per element: area of the trimmed part = frac / n^2
+    for k, e in enumerate(sorted(tris)):
+        a = (got["detJ"][off[k]:off[k + 1]] * w[off[k]:off[k + 1]]).sum()
+        assert abs(a - frac[e] / n ** 2) < 1e-13 * frac[e] / n ** 2
+    # trim flags: empty elements drop out of the DOF map, trimmed ones stay
+    flags = np.zeros(n * n, np.uint8)
+    flags[chosen] = 2
+    flags[:n] = 1
+    Pt = capi.Patch(pd.degree, pd.knotSpans, pd.cp, 2, trimflags=flags)
+    dof, nd = Pt.dofmap()
+    dref, nref = Pp.dofmap(flags)
+    assert nd == nref and np.array_equal(dof, dref)
