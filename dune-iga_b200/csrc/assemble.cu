@@ -216,23 +216,34 @@ __global__ void __launch_bounds__(128) contract_dmma_kernel(int n, int kdim, con
 //                                        into buffer (c+1)&1;  stage J^-T / w detJ of chunk c+2 }.
 // The per-row scale w detJ is applied to the B-operand fragment, so only ONE stack lives in shared memory.
 // Each warp owns a 32 x (NBP/WARPS_N) block of K_e.
-template <int NBP, int WARPS_M, int WARPS_N, int NROW>
-__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gram_dmma_kernel(
+template <int NBP, int NROW, int MINB>
+__global__ void __launch_bounds__((NBP / 32) * (NBP / 32 + 1) / 2 * 32, MINB) gram_dmma_kernel(
     int nb, int nq, long long nelem, int nq0, int nq1_, int nq2, const double* __restrict__ w0,
     const double* __restrict__ w1, const double* __restrict__ w2, const double* __restrict__ N,
     const double* __restrict__ dN, const double* __restrict__ detJ, const double* __restrict__ JinvT,
     double* __restrict__ Ke) {
-  constexpr int KC = 16, LD = NBP + 4, NT = WARPS_M * WARPS_N * 32;
-  constexpr int TM = NBP / WARPS_M / 8, TN = NBP / WARPS_N / 8;  // 8x8 tiles per warp
+  // K_e is symmetric: only the NBLK (NBLK+1)/2 upper 32 x 32 blocks are contracted, one warp each; the strictly upper
+  // blocks are mirrored on the way out.
+  constexpr int NBLK = NBP / 32, NUP = NBLK * (NBLK + 1) / 2;
+  constexpr int KC = 16, LD = NBP + 4, NT = NUP * 32;
+  constexpr int TM = 4, TN = 4;  // 8x8 tiles per warp
   constexpr int nrow = NROW, NV = NROW == 3 ? 3 : 1;
   constexpr int MAXIT = ((KC / NROW) * NBP + NT - 1) / NT;
-  static_assert(NBP / WARPS_M == 32, "each warp owns 32 rows");
   __shared__ double sA[2][KC][LD];
   __shared__ double sS[3][KC];
   __shared__ double sJ[3][KC][9];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int wi = (warp / WARPS_N) * 32, wj = (warp % WARPS_N) * (NBP / WARPS_N);
+  int bi = 0, bj = 0;
+  {
+    int w = warp;  // row-major enumeration of the upper blocks: (0,0) (0,1) .. (0,NBLK-1) (1,1) ..
+    while (w >= NBLK - bi) {
+      w -= NBLK - bi;
+      ++bi;
+    }
+    bj = bi + w;
+  }
+  const int wi = bi * 32, wj = bj * 32;
   constexpr int pts = KC / NROW;  // points per chunk (5 | 16)
   const int nchunk = (nq + pts - 1) / pts;
   constexpr int nitem = pts * NBP;
@@ -341,6 +352,10 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) gram_dmma_kernel(
         if (i < nb) {
           if (j < nb) K[(long long)i * nb + j] = c[a][b][0];
           if (j + 1 < nb) K[(long long)i * nb + j + 1] = c[a][b][1];
+          if (bi != bj) {  // mirror
+            if (j < nb) K[(long long)j * nb + i] = c[a][b][0];
+            if (j + 1 < nb) K[(long long)(j + 1) * nb + i] = c[a][b][1];
+          }
         }
       }
   }
@@ -444,17 +459,17 @@ igab_status assemble_dd(const PatchDev& P, SfWorkspace& ws, const double* const*
       }
       const bool mass = kind == IGAB_ASM_MASS;
       if (nb > 64) {
-        const unsigned grid = (unsigned)std::min<long long>(m, sms);
-        if (mass)
-          gram_dmma_kernel<128, 4, 2, 1><<<grid, 256, 0, stream>>>(nb, (int)nq, m, q0, q1, q2, w[0], w[1], w[2], dNv, ddN, ddet, dJi, K);
-        else
-          gram_dmma_kernel<128, 4, 2, 3><<<grid, 256, 0, stream>>>(nb, (int)nq, m, q0, q1, q2, w[0], w[1], w[2], dNv, ddN, ddet, dJi, K);
-      } else {
         const unsigned grid = (unsigned)std::min<long long>(m, 2LL * sms);
         if (mass)
-          gram_dmma_kernel<64, 2, 2, 1><<<grid, 128, 0, stream>>>(nb, (int)nq, m, q0, q1, q2, w[0], w[1], w[2], dNv, ddN, ddet, dJi, K);
+          gram_dmma_kernel<128, 1, 2><<<grid, 320, 0, stream>>>(nb, (int)nq, m, q0, q1, q2, w[0], w[1], w[2], dNv, ddN, ddet, dJi, K);
         else
-          gram_dmma_kernel<64, 2, 2, 3><<<grid, 128, 0, stream>>>(nb, (int)nq, m, q0, q1, q2, w[0], w[1], w[2], dNv, ddN, ddet, dJi, K);
+          gram_dmma_kernel<128, 3, 2><<<grid, 320, 0, stream>>>(nb, (int)nq, m, q0, q1, q2, w[0], w[1], w[2], dNv, ddN, ddet, dJi, K);
+      } else {
+        const unsigned grid = (unsigned)std::min<long long>(m, 4LL * sms);
+        if (mass)
+          gram_dmma_kernel<64, 1, 4><<<grid, 96, 0, stream>>>(nb, (int)nq, m, q0, q1, q2, w[0], w[1], w[2], dNv, ddN, ddet, dJi, K);
+        else
+          gram_dmma_kernel<64, 3, 4><<<grid, 96, 0, stream>>>(nb, (int)nq, m, q0, q1, q2, w[0], w[1], w[2], dNv, ddN, ddet, dJi, K);
       }
       count_launch();
     } else {
