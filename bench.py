@@ -145,6 +145,74 @@ def config_dict(n):
             "parallelism": "element k-slabs, %d rank(s), no collective" % n}
 
 
+def measured_fp64_peak():
+    """DMMA / DFMA TFLOP/s of this GPU from tools/fp64_peak (built by __graft_entry__.build()); the driver's
+    MEASURED_PEAKS.json holds no FP64 figure."""
+    exe = os.path.join(ROOT, "tools", "fp64_peak")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+        dmma = max(float(l.split()[-2]) for l in out.splitlines() if l.startswith("DMMA"))
+        dfma = max(float(l.split()[-2]) for l in out.splitlines() if l.startswith("DFMA"))
+        return dmma, dfma, "measured live by tools/fp64_peak (mma.sync.m8n8k4.f64 / DFMA loops)"
+    except Exception:
+        return 37.0, 34.0, "fallback: tools/fp64_peak measured on this pool in round 1"
+
+
+def bench_assembly(args, rank, world, local, barrier, dist):
+    import torch
+    import igab200  # noqa: F401
+    from dune_iga_b200 import capi, patchdata as PD
+    p, nq1, lev = 4, 5, 6
+    extra = int(np.log2(world))
+    pd = PD.thickCylinder(p, (lev, lev, lev + extra))
+    P = capi.Patch.fromPatchData(pd)
+    x, w = PD.gaussLegendre01(nq1)
+    xi, ww = [x] * 3, [w] * 3
+    n = (p + 1) ** 3
+    per_call = 64 * 64 * 4  # 16,384 elements = 2.05 GB of element matrices per call
+    calls = 64 // 4
+    my_begin = rank * 64 ** 3
+    ring = [torch.empty((per_call, n, n), dtype=torch.float64, device="cuda") for _ in range(2)]
+    stream = torch.cuda.current_stream()
+
+    def one_pass():
+        for j in range(calls):
+            eb = my_begin + j * per_call
+            P.assemble(capi.ASM_POISSON, xi, ww, elem_begin=eb, elem_end=eb + per_call, Ke=ring[j & 1], fe=None,
+                       stream=stream.cuda_stream)
+
+    one_pass()
+    barrier()
+    l0 = capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    npass = 3
+    e0.record(stream)
+    for _ in range(npass):
+        one_pass()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    nel = 64 ** 3 * world * npass
+    flops_el = 125 * (2 * 3 * n * n + 2 * 9 * n)  # SURVEY.md 8(d): nq (2 s n^2 + 2 s^2 n)
+    dmma, dfma, src = measured_fp64_peak() if rank == 0 else (37.0, 34.0, "")
+    achieved = flops_el * nel / world / (ms * 1e-3) / 1e12  # per GPU
+    del ring
+    return {"metric": "element matrices/sec", "value": nel / (ms * 1e-3), "unit": "elements/s",
+            "config": {"workload": "C3: 3-D Poisson stiffness p=4 (n=125), 5^3 Gauss, 64x64x%d elements (64^3 per GPU)"
+                                   % (64 * world)},
+            "ms_per_pass": ms / npass, "gpu_launches": int(capi.launch_count() - l0),
+            "roofline": {"bound": "tensor", "kernel": "gram_dmma_kernel<128,3,2> (+ eval_sf3d_kernel<4,5>)",
+                         "achieved": achieved, "peak": dmma, "unit": "TFLOP/s", "frac": achieved / dmma,
+                         "traffic": None, "peak_source": src, "dfma_peak": dfma,
+                         "algorithmic_flops_per_element": flops_el,
+                         "note": "algorithmic flops of the dense B^T D B; the kernel contracts only the upper blocks of "
+                                 "the symmetric matrix (0.625 x the flops) and the time includes the evaluation kernel"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -153,6 +221,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-assembly", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -311,12 +380,18 @@ def main():
                    c_layers, c_el, c_el * NQ, dt)}
         del r
 
+    # ---- second half of BASELINE.json's metric: element matrices/sec (config C3: p=4 Poisson stiffness, 5^3 Gauss,
+    # FP64 tensor-core contraction), each rank assembling its own slab of a 64 x 64 x 64N patch
+    assembly = None
+    if not args.no_assembly:
+        assembly = bench_assembly(args, rank, world, local, barrier, dist if world > 1 else None)
+
     if rank == 0:
         print(json.dumps({
             "metric": "quad-pt basis+Jacobian evals/sec", "value": value, "unit": "points/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(world),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}))
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "assembly": assembly}))
     if world > 1:
         dist.destroy_process_group()
 
