@@ -446,7 +446,8 @@ igab_status assemble_dd(const PatchDev& P, SfWorkspace& ws, const double* const*
       IGAB_CUDA_TRY(cudaMallocAsync(&A2, 8LL * m * kdim * n, stream));
     }
     EvalOutDev o{};
-    o.N = dNv; o.dN = ddN; o.detJ = ddet; o.JinvT = dJi;
+    // N is only needed for the mass matrix and the load vector
+    o.N = (kind == IGAB_ASM_MASS || fe) ? dNv : nullptr; o.dN = (kind == IGAB_ASM_MASS) ? nullptr : ddN; o.detJ = ddet; o.JinvT = (kind == IGAB_ASM_MASS) ? nullptr : dJi;
     igab_status st = eval_for(P, ws, xi1d_host, eb + c0, m, nq1, xi, o, stream);
     if (st) return st;
     double* K = Ke + (long long)c0 * n * n;

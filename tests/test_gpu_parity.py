@@ -292,3 +292,50 @@ def test_error_behaviour():
         P.evalTensor([x, x], order=3)
     with pytest.raises(capi.IgabError):
         P.partial([0], [[0.5, 0.5]], [70, 0])
+
+
+def test_degree_elevation_invariance_through_cuda():
+    """testCurveHigherOrderDerivatives / testSurfaceHigherOrderDerivatives (gridtests.cpp:1177-1200,1285-1337):
+    position, Jacobian and Hessian are invariant under degree elevation (1e-10 / 1e-8 there)."""
+    c = G["degree_elevate_curve"]
+    base = PD.NurbsPatchData(c["knots"], c["cp"], c["degree"], c["dimworld"])
+    u = np.linspace(0, 1, 21)
+
+    def sample(pd):
+        P = capi.Patch.fromPatchData(pd)
+        # two elements [0,.5],[.5,1]: map patch coordinate u to (element, xi)
+        el = np.minimum((u * 2).astype(np.int32), 1)
+        xi = (u * 2 - el).reshape(-1, 1)
+        o = P.evalPoints(el, xi, order=2, want=("x", "Jt", "H"))
+        # undo the element scaling (span length 0.5) to compare in patch coordinates
+        return o["x"], o["Jt"] / 0.5, o["H"] / 0.25
+
+    x0, J0, H0 = sample(base)
+    for t in range(1, 5):
+        x1, J1, H1 = sample(base.degreeElevate(0, t))
+        assert np.abs(x1 - x0).max() < 1e-10 and np.abs(J1 - J0).max() < 1e-10 and np.abs(H1 - H0).max() < 1e-8
+    # surface: torus, elevate both directions
+    s0 = PD.torusSurface(0)
+    s1 = s0.degreeElevate(0, 1).degreeElevate(1, 2)
+    rng = np.random.default_rng(3)
+    el = rng.integers(0, 16, 9).astype(np.int32)
+    xi = rng.random((9, 2))
+    a = capi.Patch.fromPatchData(s0).evalPoints(el, xi, order=2, want=("x", "Jt", "H"))
+    b = capi.Patch.fromPatchData(s1).evalPoints(el, xi, order=2, want=("x", "Jt", "H"))
+    for f, tol in (("x", 1e-10), ("Jt", 1e-10), ("H", 1e-8)):
+        assert np.abs(a[f] - b[f]).max() < tol, f
+
+
+def test_flat_plate_second_derivatives():
+    """testPlate (gridtests.cpp:1085-1124): on a flat plate in R^3 every N, dN, d2N is finite at the element corners and
+    the out-of-plane components of the Hessian vanish."""
+    pd = PD.NurbsPatchData([[0, 0, 0, 1, 1, 1], [0, 0, 0, 1, 1, 1]],
+                           [(x, y, 0.0, 1.0) for y in (0, .5, 1) for x in (0, .5, 1)], [2, 2], 3).globalRefine(1)
+    P = capi.Patch.fromPatchData(pd)
+    corners = np.array([[a, b] for a in (0.0, 1.0) for b in (0.0, 1.0)])
+    for e in range(P.nelem):
+        o = P.evalPoints([e] * 4, corners, order=2)
+        for f in ("N", "dN", "d2N"):
+            assert np.all(np.isfinite(o[f]))
+        assert np.abs(o["H"][:, :, 2]).max() == 0.0
+        assert np.abs(o["Jt"][:, :, 2]).max() == 0.0
