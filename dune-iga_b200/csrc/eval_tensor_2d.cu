@@ -43,6 +43,71 @@ __global__ void tables2d_kernel(PatchDev P, int d, int nq, int order, const doub
   }
 }
 
+// A2.3 (bsplinealgorithms.hh:148-222) with compile-time degree and order: fully unrolled, everything in registers.
+// out[k][i] = k-th derivative w.r.t. the ELEMENT-LOCAL coordinate (scaled by span length^k).
+template <int P, int K>
+__device__ __forceinline__ void ders1d_reg(double u, const double* __restrict__ U, int sp, double scale,
+                                           double (&out)[K + 1][P + 1]) {
+  double left[P + 1], right[P + 1], ndu[P + 1][P + 1];
+  ndu[0][0] = 1.0;
+#pragma unroll
+  for (int j = 1; j <= P; ++j) {
+    left[j] = u - U[sp + 1 - j];
+    right[j] = U[sp + j] - u;
+    double saved = 0.0;
+#pragma unroll
+    for (int r = 0; r < j; ++r) {
+      ndu[j][r] = right[r + 1] + left[j - r];
+      const double temp = ndu[r][j - 1] / ndu[j][r];
+      ndu[r][j] = saved + right[r + 1] * temp;
+      saved = left[j - r] * temp;
+    }
+    ndu[j][j] = saved;
+  }
+#pragma unroll
+  for (int j = 0; j <= P; ++j) out[0][j] = ndu[j][P];
+  if constexpr (K >= 1) {
+#pragma unroll
+    for (int r = 0; r <= P; ++r) {
+      double a[2][P + 1];
+      a[0][0] = 1.0;
+#pragma unroll
+      for (int k = 1; k <= K; ++k) {
+        const int s1 = (k - 1) & 1, s2 = k & 1;
+        double d = 0.0;
+        const int rk = r - k, pk = P - k;
+        if (k <= P) {
+          if (r >= k) {
+            a[s2][0] = a[s1][0] / ndu[pk + 1][rk];
+            d = a[s2][0] * ndu[rk][pk];
+          }
+          const int j1 = (rk >= -1) ? 1 : -rk;
+          const int j2 = (r - 1 <= pk) ? k - 1 : P - r;
+#pragma unroll
+          for (int j = 1; j <= K; ++j)
+            if (j >= j1 && j <= j2) {
+              a[s2][j] = (a[s1][j] - a[s1][j - 1]) / ndu[pk + 1][rk + j];
+              d += a[s2][j] * ndu[rk + j][pk];
+            }
+          if (r <= pk) {
+            a[s2][k] = -a[s1][k - 1] / ndu[pk + 1][r];
+            d += a[s2][k] * ndu[r][pk];
+          }
+        }
+        out[k][r] = d;
+      }
+    }
+    double fac = P, sc = scale;
+#pragma unroll
+    for (int k = 1; k <= K; ++k) {
+#pragma unroll
+      for (int j = 0; j <= P; ++j) out[k][j] *= fac * sc;
+      fac *= (P - k);
+      sc *= scale;
+    }
+  }
+}
+
 template <int DW, int P, int Q, int ORDER>
 struct Cfg2 {
   static constexpr int NB1 = P + 1, NB = NB1 * NB1, NQ = Q * Q, NH = 3;
@@ -73,9 +138,12 @@ __device__ __forceinline__ void flush_field(double* __restrict__ slab, const dou
   __syncwarp();
 }
 
-template <int DW, int P, int Q, int ORDER>
+// LIST = false: tensor rule, univariate rows from the K1 tables.  LIST = true: arbitrary element-local points (trimmed
+// batches, utils/fillquadraturerule.hh:8-19): rows computed per point with ders1d_reg.
+template <int DW, int P, int Q, int ORDER, bool LIST>
 __global__ void __launch_bounds__(128) eval_2d_kernel(PatchDev Pd, long long elem_begin, long long npts,
                                                       const double* __restrict__ tab0, const double* __restrict__ tab1,
+                                                      const int* __restrict__ elemList, const double* __restrict__ xiList,
                                                       EvalOutDev out) {
   using C = Cfg2<DW, P, Q, ORDER>;
   constexpr int NB1 = C::NB1, NB = C::NB, NQ = C::NQ, NA = C::NA, A1 = C::A1, NH = C::NH;
@@ -88,13 +156,20 @@ __global__ void __launch_bounds__(128) eval_2d_kernel(PatchDev Pd, long long ele
   const bool valid = pt < npts;
   const int nvalid = (int)min(32LL, npts - pt0);
   const long long ptc = valid ? pt : npts - 1;
-  const long long e = elem_begin + ptc / NQ;
-  const int q = (int)(ptc % NQ), q0 = q % Q, q1 = q / Q;
+  const long long e = LIST ? (long long)elemList[ptc] : elem_begin + ptc / (NQ > 0 ? NQ : 1);
   const int e0 = (int)(e % Pd.nel[0]), e1 = (int)(e / Pd.nel[0]);
 
   // univariate rows of this point
   double n0[A1][NB1], n1[A1][NB1];
-  {
+  if constexpr (LIST) {
+    const int s0 = Pd.spanTab[0][e0], s1 = Pd.spanTab[1][e1];
+    const double* U0 = Pd.knots[0];
+    const double* U1 = Pd.knots[1];
+    const double lo0 = U0[s0], sc0 = U0[s0 + 1] - lo0, lo1 = U1[s1], sc1 = U1[s1 + 1] - lo1;
+    ders1d_reg<P, ORDER>(xiList[ptc * 2] * sc0 + lo0, U0, s0, sc0, n0);
+    ders1d_reg<P, ORDER>(xiList[ptc * 2 + 1] * sc1 + lo1, U1, s1, sc1, n1);
+  } else {
+    const int q = (int)(ptc % (NQ > 0 ? NQ : 1)), q0 = q % (Q > 0 ? Q : 1), q1 = q / (Q > 0 ? Q : 1);
     const double* t0 = tab0 + ((size_t)e0 * Q + q0) * NB1 * A1;
     const double* t1 = tab1 + ((size_t)e1 * Q + q1) * NB1 * A1;
 #pragma unroll
@@ -281,7 +356,7 @@ igab_status launch_2d(const PatchDev& Pd, SfWorkspace& ws, const PointSource& sr
   const size_t smem = (size_t)WARPS * C::SLAB * sizeof(double);
   static bool configured = false;
   if (!configured) {
-    IGAB_CUDA_TRY(cudaFuncSetAttribute(eval_2d_kernel<DW, P, Q, ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IGAB_CUDA_TRY(cudaFuncSetAttribute(eval_2d_kernel<DW, P, Q, ORDER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const long long blocks = (npts + WARPS * 32 - 1) / (WARPS * 32);
@@ -289,8 +364,8 @@ igab_status launch_2d(const PatchDev& Pd, SfWorkspace& ws, const PointSource& sr
     set_error("eval_tensor: too many points for one launch");
     return IGAB_INVALID_ARGUMENT;
   }
-  eval_2d_kernel<DW, P, Q, ORDER><<<(unsigned)blocks, WARPS * 32, smem, stream>>>(Pd, src.elem_begin, npts, ws.tab[0],
-                                                                                 ws.tab[1], out);
+  eval_2d_kernel<DW, P, Q, ORDER, false><<<(unsigned)blocks, WARPS * 32, smem, stream>>>(
+      Pd, src.elem_begin, npts, ws.tab[0], ws.tab[1], nullptr, nullptr, out);
   count_launch();
   IGAB_CUDA_TRY(cudaGetLastError());
   return IGAB_OK;
@@ -307,7 +382,67 @@ igab_status dispatch_pq(int p, int q, const PatchDev& Pd, SfWorkspace& ws, const
   return IGAB_UNSUPPORTED;
 }
 
+template <int DW, int P, int ORDER>
+igab_status launch_list(const PatchDev& Pd, const PointSource& src, long long npts, const EvalOutDev& out,
+                        cudaStream_t stream) {
+  using C = Cfg2<DW, P, 0, ORDER>;
+  constexpr int WARPS = 4;
+  const size_t smem = (size_t)WARPS * C::SLAB * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    IGAB_CUDA_TRY(cudaFuncSetAttribute(eval_2d_kernel<DW, P, 0, ORDER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const long long blocks = (npts + WARPS * 32 - 1) / (WARPS * 32);
+  if (blocks > 0x7fffffffLL) {
+    set_error("eval_points: too many points for one launch");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  eval_2d_kernel<DW, P, 0, ORDER, true><<<(unsigned)blocks, WARPS * 32, smem, stream>>>(Pd, 0, npts, nullptr, nullptr,
+                                                                                       src.elem, src.xi, out);
+  count_launch();
+  IGAB_CUDA_TRY(cudaGetLastError());
+  return IGAB_OK;
+}
+
+template <int DW, int ORDER>
+igab_status dispatch_list(int p, const PatchDev& Pd, const PointSource& src, long long npts, const EvalOutDev& out,
+                          cudaStream_t stream) {
+  if (p == 1) return launch_list<DW, 1, ORDER>(Pd, src, npts, out, stream);
+  if (p == 2) return launch_list<DW, 2, ORDER>(Pd, src, npts, out, stream);
+  if (p == 3) return launch_list<DW, 3, ORDER>(Pd, src, npts, out, stream);
+  set_error("eval_points: no 2-D list kernel for this degree");
+  return IGAB_UNSUPPORTED;
+}
+
 }  // namespace
+
+bool eval_points_2d_supported(const PatchDev& P) {
+  return P.dim == 2 && (P.dw == 2 || P.dw == 3) && P.degree[0] == P.degree[1] && P.degree[0] >= 1 && P.degree[0] <= 3;
+}
+
+igab_status launch_eval_points_2d(const PatchDev& P, const PointSource& src, long long npts, int order,
+                                  const EvalOutDev& out, cudaStream_t stream) {
+  if (!eval_points_2d_supported(P)) {
+    set_error("eval_points: no 2-D list kernel for this configuration");
+    return IGAB_UNSUPPORTED;
+  }
+  EvalOutDev o = out;
+  int ord = 0;
+  if (order >= 1 && (o.dN || o.Jt || o.detJ || o.JinvT)) ord = 1;
+  if (order >= 2 && (o.d2N || o.H)) ord = 2;
+  if (ord < 2) o.d2N = o.H = nullptr;
+  if (ord < 1) o.dN = o.Jt = o.detJ = o.JinvT = nullptr;
+  const int p = P.degree[0];
+  if (P.dw == 2) {
+    if (ord == 0) return dispatch_list<2, 0>(p, P, src, npts, o, stream);
+    if (ord == 1) return dispatch_list<2, 1>(p, P, src, npts, o, stream);
+    return dispatch_list<2, 2>(p, P, src, npts, o, stream);
+  }
+  if (ord == 0) return dispatch_list<3, 0>(p, P, src, npts, o, stream);
+  if (ord == 1) return dispatch_list<3, 1>(p, P, src, npts, o, stream);
+  return dispatch_list<3, 2>(p, P, src, npts, o, stream);
+}
 
 bool eval_tensor_2d_supported(const PatchDev& P, const int* nq1, int order, const EvalOutDev& out) {
   (void)out;

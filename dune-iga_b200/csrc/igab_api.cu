@@ -571,6 +571,8 @@ igab_status igab_eval_points(igab_patch* p, int64_t npts, const int32_t* elem, c
   if (space == IGAB_DEVICE) {
     src.elem = elem;
     src.xi = xi;
+    if (p->kernel_mode != IGAB_KERNEL_GENERIC && eval_points_2d_supported(p->dev))
+      return launch_eval_points_2d(p->dev, src, npts, deriv_order, to_dev(eff), stream);
     return launch_eval_generic(p->dev, src, npts, deriv_order, to_dev(eff), stream);
   }
   for (long long k = 0; k < npts; ++k)
@@ -595,7 +597,10 @@ igab_status igab_eval_points(igab_patch* p, int64_t npts, const int32_t* elem, c
     src.xi = d_xi;
     igab_eval_out dv{};
     for (int k = 0; k < 8; ++k) *out_field(&dv, k) = dbuf[k];
-    st = launch_eval_generic(p->dev, src, npts, deriv_order, to_dev(dv), stream);
+    if (p->kernel_mode != IGAB_KERNEL_GENERIC && eval_points_2d_supported(p->dev))
+      st = launch_eval_points_2d(p->dev, src, npts, deriv_order, to_dev(dv), stream);
+    else
+      st = launch_eval_generic(p->dev, src, npts, deriv_order, to_dev(dv), stream);
   }
   for (int k = 0; k < 8 && !st; ++k)
     if (dbuf[k]) {

@@ -76,6 +76,10 @@ igab_status launch_eval_tensor_sf(const PatchDev& P, SfWorkspace& ws, const Poin
                                   cudaStream_t stream);
 void free_sf_workspace(SfWorkspace& ws);
 bool eval_tensor_sf_supported(const PatchDev& P, const int* nq1, int order, const EvalOutDev& out);
+// 2-D point lists (trimmed batches): per-point univariate rows in registers
+bool eval_points_2d_supported(const PatchDev& P);
+igab_status launch_eval_points_2d(const PatchDev& P, const PointSource& src, long long npts, int order,
+                                  const EvalOutDev& out, cudaStream_t stream);
 // 2-D family (thread per point, compile-time degree / rule / order)
 bool eval_tensor_2d_supported(const PatchDev& P, const int* nq1, int order, const EvalOutDev& out);
 igab_status launch_eval_tensor_2d(const PatchDev& P, SfWorkspace& ws, const PointSource& src,
