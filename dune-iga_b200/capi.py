@@ -22,7 +22,8 @@ FIELDS = ("N", "dN", "d2N", "x", "Jt", "H", "detJ", "JinvT")
 EXPORTS = ("igab_last_error_string", "igab_version", "igab_launch_count", "igab_host_alloc", "igab_host_free",
            "igab_patch_create", "igab_patch_destroy", "igab_patch_sizes", "igab_patch_set_kernel",
            "igab_patch_update_control_points", "igab_patch_spans", "igab_patch_dofmap", "igab_eval_tensor",
-           "igab_eval_points", "igab_partial", "igab_assemble", "igab_reduce_volume")
+           "igab_eval_points", "igab_partial", "igab_assemble", "igab_reduce_volume", "igab_csr_pattern",
+           "igab_csr_assemble")
 
 
 class EvalOut(C.Structure):
@@ -63,6 +64,10 @@ def lib():
         L.igab_partial.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, ip, C.c_void_p, C.c_int, C.c_void_p]
         L.igab_assemble.argtypes = [C.c_void_p, C.c_int, dp, C.c_double, C.c_int64, C.c_int64, ip, C.POINTER(dp),
                                     C.POINTER(dp), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.igab_csr_pattern.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p,
+                                       C.c_void_p, C.c_int, C.c_void_p]
+        L.igab_csr_assemble.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_int, C.c_void_p]
         L.igab_reduce_volume.argtypes = [C.c_void_p, C.c_int64, C.c_int64, ip, C.POINTER(dp), C.POINTER(dp),
                                          C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
         _lib = L
@@ -265,6 +270,37 @@ class Patch:
         _check(lib().igab_assemble(self.h, kind, Dm.ctypes.data_as(dp) if Dm is not None else None, fconst,
                                    elem_begin, elem_end, nq1.ctypes.data_as(ip), xp, wp, ka, fa, ks, stream))
         return Ke, fe
+
+    # ---- global sparse matrix
+    def csrPattern(self, ncomp=1):
+        """(rowptr int64 [nrows+1], colidx int32 [nnz]) of the global matrix; replaces the lil_matrix of poisson.py:87."""
+        nr, nnz = C.c_int64(), C.c_int64()
+        _check(lib().igab_csr_pattern(self.h, ncomp, C.byref(nr), C.byref(nnz), None, None, HOST, None))
+        rowptr = np.empty(nr.value + 1, dtype=np.int64)
+        colidx = np.empty(nnz.value, dtype=np.int32)
+        _check(lib().igab_csr_pattern(self.h, ncomp, C.byref(nr), C.byref(nnz), rowptr.ctypes.data, colidx.ctypes.data,
+                                      HOST, None))
+        return rowptr, colidx
+
+    def csrAssemble(self, Ke, ncomp=1, elem_begin=0, elem_end=None, values=None, accumulate=False, stream=None):
+        """values[nnz] (+)= gather of the element matrices Ke of elements [elem_begin, elem_end) (poisson.py:113-125)."""
+        if elem_end is None:
+            elem_end = self.nelem
+        ka, ks = _ptr(Ke)
+        if values is None:
+            nr, nnz = C.c_int64(), C.c_int64()
+            _check(lib().igab_csr_pattern(self.h, ncomp, C.byref(nr), C.byref(nnz), None, None, HOST, None))
+            if ks == HOST:
+                values = np.zeros(nnz.value)
+            else:
+                import torch
+                values = torch.zeros(nnz.value, dtype=torch.float64, device=Ke.device)
+        va, vs = _ptr(values)
+        if vs != ks:
+            raise ValueError("Ke and values must live in the same memory space")
+        _check(lib().igab_csr_assemble(self.h, ncomp, elem_begin, elem_end, ka, None, va, 1 if accumulate else 0, ks,
+                                       stream))
+        return values
 
     def volume(self, xi1d, w1d, elem_begin=0, elem_end=None, nccl_comm=None, stream=None):
         if elem_end is None:

@@ -1,0 +1,245 @@
+// csr.cu -- global sparse matrix from element matrices: CSR pattern of the tensor-product NURBS basis and
+// a deterministic gather assembly.  Functional spec: the scatter loop of dune/python/test/poisson.py:113-125 with the
+// DOF numbering of NurbsPreBasis::createOriginalNodeIndices (dune/iga/nurbsbasis.hh:572-584).
+//
+// Row g = (g_0, g_1, g_2) couples with h iff |g_d - h_d| <= p_d in every direction, so a row's columns are the box
+// [max(0, g_d - p_d), min(n_d - 1, g_d + p_d)]: row length and the position of a column inside the row are closed-form.
+// One warp per row, lanes over the row's non-zeros; every non-zero gathers the contributions Ke[e][i][j] of the (at
+// most prod (p_d + 1)) elements whose local bases contain both DOFs, in a fixed order -- no atomics.
+#include "igab_internal.cuh"
+
+namespace igab {
+
+namespace {
+
+struct CsrGeom {
+  int dim, ncomp;
+  int p[kMaxDim], n[kMaxDim], nel[kMaxDim];
+  const int* elemOfFirst[kMaxDim];  // first-DOF index f_d -> element e_d (or -1): inverse of span - degree
+  int nb;
+};
+
+__device__ __forceinline__ void row_box(const CsrGeom& G, long long g, int* gd, int* lo, int* len) {
+  for (int d = 0; d < G.dim; ++d) {
+    gd[d] = (int)(g % G.n[d]);
+    g /= G.n[d];
+    lo[d] = max(0, gd[d] - G.p[d]);
+    const int hi = min(G.n[d] - 1, gd[d] + G.p[d]);
+    len[d] = hi - lo[d] + 1;
+  }
+  for (int d = G.dim; d < kMaxDim; ++d) { gd[d] = 0; lo[d] = 0; len[d] = 1; }
+}
+
+// row lengths (one thread per scalar DOF); the host turns them into rowptr with a prefix sum
+__global__ void csr_rowlen_kernel(CsrGeom G, long long ndof, long long* __restrict__ rowlen) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ndof) return;
+  int gd[kMaxDim], lo[kMaxDim], len[kMaxDim];
+  row_box(G, g, gd, lo, len);
+  const long long l = (long long)len[0] * len[1] * len[2] * G.ncomp;
+  for (int c = 0; c < G.ncomp; ++c) rowlen[g * G.ncomp + c] = l;
+}
+
+__global__ void csr_colidx_kernel(CsrGeom G, long long nrows, const long long* __restrict__ rowptr,
+                                  int32_t* __restrict__ colidx) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  int gd[kMaxDim], lo[kMaxDim], len[kMaxDim];
+  row_box(G, row / G.ncomp, gd, lo, len);
+  const long long base = rowptr[row];
+  const int nn = len[0] * len[1] * len[2] * G.ncomp;
+  for (int k = lane; k < nn; k += 32) {
+    const int d = k % G.ncomp;
+    int kk = k / G.ncomp;
+    const int c0 = lo[0] + kk % len[0];
+    kk /= len[0];
+    const int c1 = lo[1] + kk % len[1];
+    const int c2 = lo[2] + kk / len[1];
+    const long long h = c0 + (long long)G.n[0] * (c1 + (long long)(G.dim > 1 ? G.n[1] : 1) * c2);
+    colidx[base + k] = (int32_t)(h * G.ncomp + d);
+  }
+}
+
+__global__ void csr_gather_kernel(CsrGeom G, long long nrows, long long elem_begin, long long elem_end,
+                                  const double* __restrict__ Ke, const long long* __restrict__ rowptr,
+                                  double* __restrict__ values, int accumulate) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  int gd[kMaxDim], lo[kMaxDim], len[kMaxDim];
+  row_box(G, row / G.ncomp, gd, lo, len);
+  const int c = (int)(row % G.ncomp);
+  const long long base = rowptr[row];
+  const int nn = len[0] * len[1] * len[2] * G.ncomp;
+  const long long n = (long long)G.nb * G.ncomp;
+  const int o0 = G.p[0] + 1, o1 = G.dim > 1 ? G.p[1] + 1 : 1;
+  for (int k = lane; k < nn; k += 32) {
+    const int d = k % G.ncomp;
+    int kk = k / G.ncomp;
+    int hd[kMaxDim];
+    hd[0] = lo[0] + kk % len[0];
+    kk /= len[0];
+    hd[1] = lo[1] + kk % len[1];
+    hd[2] = lo[2] + kk / len[1];
+    int fa[kMaxDim], fb[kMaxDim];  // range of first-DOF indices of the elements that contain both g and h
+    for (int q = 0; q < kMaxDim; ++q) {
+      if (q < G.dim) {
+        fa[q] = max(max(gd[q], hd[q]) - G.p[q], 0);
+        fb[q] = min(min(gd[q], hd[q]), G.n[q] - 1 - G.p[q]);
+      } else {
+        fa[q] = fb[q] = 0;
+      }
+    }
+    double acc = 0.0;
+    for (int f2 = fa[2]; f2 <= fb[2]; ++f2) {
+      const int e2 = G.dim > 2 ? G.elemOfFirst[2][f2] : 0;
+      if (e2 < 0) continue;
+      for (int f1 = fa[1]; f1 <= fb[1]; ++f1) {
+        const int e1 = G.dim > 1 ? G.elemOfFirst[1][f1] : 0;
+        if (e1 < 0) continue;
+        for (int f0 = fa[0]; f0 <= fb[0]; ++f0) {
+          const int e0 = G.elemOfFirst[0][f0];
+          if (e0 < 0) continue;
+          const long long e = e0 + (long long)G.nel[0] * (e1 + (long long)(G.dim > 1 ? G.nel[1] : 1) * e2);
+          if (e < elem_begin || e >= elem_end) continue;
+          const int i = (gd[0] - f0) + o0 * ((gd[1] - f1) + o1 * (gd[2] - f2));
+          const int j = (hd[0] - f0) + o0 * ((hd[1] - f1) + o1 * (hd[2] - f2));
+          acc += Ke[(e - elem_begin) * n * n + (long long)(i * G.ncomp + c) * n + (j * G.ncomp + d)];
+        }
+      }
+    }
+    if (accumulate)
+      values[base + k] += acc;
+    else
+      values[base + k] = acc;
+  }
+}
+
+igab_status make_geom(igab_patch* p, int ncomp, CsrGeom* G) {
+  if (ncomp < 1 || ncomp > 3) {
+    set_error("csr: ncomp must be 1..3");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  if (p->d_trim) {
+    set_error("csr: trimmed patches (compacted DOF numbering) are not supported yet");
+    return IGAB_UNSUPPORTED;
+  }
+  const PatchDev& D = p->dev;
+  for (int d = 0; d < D.dim; ++d) {
+    if (!p->d_elem_of_first[d]) {
+      const int nf = D.ncp[d] - D.degree[d];  // possible first-DOF indices 0 .. n_d - p_d - 1
+      std::vector<int> tab(nf, -1);
+      for (int e = 0; e < D.nel[d]; ++e) tab[p->hspan[d][e] - D.degree[d]] = e;
+      IGAB_CUDA_TRY(cudaMalloc(&p->d_elem_of_first[d], sizeof(int) * nf));
+      IGAB_CUDA_TRY(cudaMemcpy(p->d_elem_of_first[d], tab.data(), sizeof(int) * nf, cudaMemcpyHostToDevice));
+    }
+  }
+  G->dim = D.dim;
+  G->ncomp = ncomp;
+  G->nb = D.nb;
+  for (int d = 0; d < kMaxDim; ++d) {
+    G->p[d] = d < D.dim ? D.degree[d] : 0;
+    G->n[d] = d < D.dim ? D.ncp[d] : 1;
+    G->nel[d] = d < D.dim ? D.nel[d] : 1;
+    G->elemOfFirst[d] = d < D.dim ? p->d_elem_of_first[d] : nullptr;
+  }
+  return IGAB_OK;
+}
+
+}  // namespace
+
+igab_status csr_pattern(igab_patch* p, int ncomp, int64_t* nrows_out, int64_t* nnz_out, int64_t* rowptr, int32_t* colidx,
+                        igab_memspace space, cudaStream_t stream) {
+  CsrGeom G;
+  igab_status st = make_geom(p, ncomp, &G);
+  if (st) return st;
+  const long long ndof = p->ndof_untrimmed, nrows = ndof * ncomp;
+  // row pointer: closed-form row lengths, host prefix sum (cached in the handle)
+  if ((long long)p->csr_rowptr_host.size() != nrows + 1 || p->csr_ncomp != ncomp) {
+    long long* d_len = nullptr;
+    IGAB_CUDA_TRY(cudaMalloc(&d_len, sizeof(long long) * nrows));
+    csr_rowlen_kernel<<<(unsigned)((ndof + 255) / 256), 256, 0, stream>>>(G, ndof, d_len);
+    count_launch();
+    std::vector<long long> len(nrows);
+    cudaError_t e = cudaMemcpyAsync(len.data(), d_len, sizeof(long long) * nrows, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(d_len);
+    if (e != cudaSuccess) return cuda_fail(e, "csr row lengths");
+    p->csr_rowptr_host.assign(nrows + 1, 0);
+    for (long long r = 0; r < nrows; ++r) p->csr_rowptr_host[r + 1] = p->csr_rowptr_host[r] + len[r];
+    p->csr_ncomp = ncomp;
+    if (p->d_csr_rowptr) cudaFree(p->d_csr_rowptr);
+    p->d_csr_rowptr = nullptr;
+    IGAB_CUDA_TRY(cudaMalloc(&p->d_csr_rowptr, sizeof(long long) * (nrows + 1)));
+    IGAB_CUDA_TRY(cudaMemcpy(p->d_csr_rowptr, p->csr_rowptr_host.data(), sizeof(long long) * (nrows + 1), cudaMemcpyHostToDevice));
+  }
+  const long long nnz = p->csr_rowptr_host[nrows];
+  if (nrows_out) *nrows_out = nrows;
+  if (nnz_out) *nnz_out = nnz;
+  if (nnz > 0x7fffffffLL * 64LL) {
+    set_error("csr: pattern too large");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  if (rowptr) {
+    if (space == IGAB_HOST)
+      std::copy(p->csr_rowptr_host.begin(), p->csr_rowptr_host.end(), rowptr);
+    else
+      IGAB_CUDA_TRY(cudaMemcpyAsync(rowptr, p->d_csr_rowptr, sizeof(long long) * (nrows + 1), cudaMemcpyDeviceToDevice, stream));
+  }
+  if (colidx) {
+    int32_t* d_col = colidx;
+    if (space == IGAB_HOST) IGAB_CUDA_TRY(cudaMalloc(&d_col, sizeof(int32_t) * nnz));
+    const long long threads = nrows * 32;
+    csr_colidx_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(G, nrows, p->d_csr_rowptr, d_col);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && space == IGAB_HOST) {
+      e = cudaMemcpyAsync(colidx, d_col, sizeof(int32_t) * nnz, cudaMemcpyDeviceToHost, stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    }
+    if (space == IGAB_HOST) cudaFree(d_col);
+    if (e != cudaSuccess) return cuda_fail(e, "csr column indices");
+  }
+  return IGAB_OK;
+}
+
+igab_status csr_assemble(igab_patch* p, int ncomp, long long eb, long long ee, const double* Ke, const int64_t* rowptr,
+                         double* values, int accumulate, igab_memspace space, cudaStream_t stream) {
+  CsrGeom G;
+  igab_status st = make_geom(p, ncomp, &G);
+  if (st) return st;
+  int64_t nrows = 0, nnz = 0;
+  if ((st = csr_pattern(p, ncomp, &nrows, &nnz, nullptr, nullptr, IGAB_HOST, stream))) return st;
+  (void)rowptr;  // the handle's own copy is used; the argument documents which pattern `values` belongs to
+  const long long n = (long long)p->dev.nb * ncomp, nel = ee - eb;
+  const double* dK = Ke;
+  double* dV = values;
+  if (space == IGAB_HOST) {
+    double* tK = nullptr;
+    IGAB_CUDA_TRY(cudaMalloc(&tK, sizeof(double) * std::max(1LL, nel * n * n)));
+    IGAB_CUDA_TRY(cudaMalloc(&dV, sizeof(double) * nnz));
+    cudaError_t e = cudaMemcpyAsync(tK, Ke, sizeof(double) * nel * n * n, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess && accumulate) e = cudaMemcpyAsync(dV, values, sizeof(double) * nnz, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) {
+      cudaFree(tK);
+      cudaFree(dV);
+      return cuda_fail(e, "csr staging");
+    }
+    dK = tK;
+  }
+  const long long threads = nrows * 32;
+  csr_gather_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(G, nrows, eb, ee, dK, p->d_csr_rowptr, dV, accumulate);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (space == IGAB_HOST) {
+    if (e == cudaSuccess) e = cudaMemcpyAsync(values, dV, sizeof(double) * nnz, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(const_cast<double*>(dK));
+    cudaFree(dV);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "csr gather");
+  return IGAB_OK;
+}
+
+}  // namespace igab

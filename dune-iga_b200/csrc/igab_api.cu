@@ -387,6 +387,9 @@ void igab_patch_destroy(igab_patch* p) {
     if (p->stage_copied[b]) cudaEventDestroy(p->stage_copied[b]);
   }
   if (p->stage_stream) cudaStreamDestroy(p->stage_stream);
+  for (int d = 0; d < kMaxDim; ++d)
+    if (p->d_elem_of_first[d]) cudaFree(p->d_elem_of_first[d]);
+  if (p->d_csr_rowptr) cudaFree(p->d_csr_rowptr);
   free_sf_workspace(p->sf);
   delete p;
 }
@@ -726,6 +729,26 @@ igab_status igab_assemble(igab_patch* p, int kind, const double* D, double fcons
   if (dF) cudaFree(dF);
   if (d_D) cudaFree(d_D);
   return st;
+}
+
+// ---- global CSR -----------------------------------------------------------------------------------------------------
+igab_status igab_csr_pattern(igab_patch* p, int ncomp, int64_t* nrows, int64_t* nnz, int64_t* rowptr, int32_t* colidx,
+                             igab_memspace space, void* stream) {
+  if (!p) return IGAB_INVALID_ARGUMENT;
+  return csr_pattern(p, ncomp, nrows, nnz, rowptr, colidx, space, (cudaStream_t)stream);
+}
+igab_status igab_csr_assemble(igab_patch* p, int ncomp, int64_t elem_begin, int64_t elem_end, const double* Ke,
+                              const int64_t* rowptr, double* values, int accumulate, igab_memspace space,
+                              void* stream) {
+  if (!p || !Ke || !values) {
+    set_error("csr_assemble: null argument");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  if (elem_begin < 0 || elem_end < elem_begin || elem_end > p->dev.nelem) {
+    set_error("csr_assemble: element range outside [0, n_elem]");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  return csr_assemble(p, ncomp, elem_begin, elem_end, Ke, rowptr, values, accumulate, space, (cudaStream_t)stream);
 }
 
 // ---- reductions -----------------------------------------------------------------------------------------------------

@@ -98,6 +98,11 @@ igab_status launch_volume(const PatchDev& P, SfWorkspace& ws, const double* cons
                           const double* const* xi1d_dev, const double* const* w1d_dev, double* partial_dev,
                           int npartial, double* result_dev, cudaStream_t stream);
 
+igab_status csr_pattern(igab_patch* p, int ncomp, int64_t* nrows, int64_t* nnz, int64_t* rowptr, int32_t* colidx,
+                        igab_memspace space, cudaStream_t stream);
+igab_status csr_assemble(igab_patch* p, int ncomp, long long eb, long long ee, const double* Ke, const int64_t* rowptr,
+                         double* values, int accumulate, igab_memspace space, cudaStream_t stream);
+
 }  // namespace igab
 
 // The host-side object behind the opaque handle.
@@ -125,6 +130,11 @@ struct igab_patch {
   size_t stage_cap = 0;  // bytes per set
   cudaStream_t stage_stream = nullptr;
   cudaEvent_t stage_done[2] = {nullptr, nullptr}, stage_copied[2] = {nullptr, nullptr};
+  // CSR of the global matrix: first-DOF -> element tables, cached row pointer
+  int* d_elem_of_first[igab::kMaxDim] = {nullptr, nullptr, nullptr};
+  std::vector<long long> csr_rowptr_host;
+  long long* d_csr_rowptr = nullptr;
+  int csr_ncomp = 0;
   // reduction scratch
   double* d_red = nullptr;
   int red_cap = 0;

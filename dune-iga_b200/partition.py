@@ -43,3 +43,58 @@ def interface_dofs(dofmap, ranges):
         both = np.intersect1d(a[a >= 0], b[b >= 0])
         out.append(both)
     return out
+
+
+# ---- interface rows of the assembled global matrix (north star: "NCCL ... for the interface rows") ---------------------
+def element_first_dofs(U, p):
+    """First global DOF index (per direction) of every element: span - p with span = findSpanCorrected(p, uq[e], U, e)
+    (dune/iga/nurbsbasis.hh:355-360,576)."""
+    from .patchdata import uniqueKnots
+    U = np.asarray(U, float)
+    uq = uniqueKnots(U)
+    spans = np.searchsorted(U, uq[:-1], side="right") - 1
+    return spans - p
+
+
+def interface_row_ranges(pd, world, ncomp=1):
+    """For the slab partition of `pd` over `world` ranks: per cut c (between rank c and c+1) the contiguous global row
+    range [row_begin, row_end) of the DOF layers that elements on BOTH sides touch (p layers of n_0 x n_1 functions
+    for simple knots).  Rows are numbered g*ncomp + comp with g first-direction-fastest."""
+    nel = pd.elementsPerDirection
+    last = pd.patchDim - 1
+    first = element_first_dofs(pd.knotSpans[last], pd.degree[last])
+    per_layer = int(np.prod(pd.ncp[:last])) if last > 0 else 1
+    cuts = []
+    for r in range(world - 1):
+        eb, ee = slab_range(nel, world, r)
+        per_el_layer = int(np.prod(nel[:last])) if last > 0 else 1
+        l_end = ee // per_el_layer  # first element layer of rank r+1
+        if l_end <= 0 or l_end >= nel[last]:
+            cuts.append((0, 0))
+            continue
+        lo = int(first[l_end])                           # lowest DOF layer the right side touches
+        hi = int(first[l_end - 1]) + pd.degree[last]     # highest DOF layer the left side touches
+        cuts.append((lo * per_layer * ncomp, (hi + 1) * per_layer * ncomp))
+    return cuts
+
+
+def exchange_interface_rows(values, rowptr, cuts, rank, world, dist):
+    """In place: add the neighbour's partial sums on the interface rows (both sides end up with the complete rows).
+    `values` is a torch tensor (CUDA with the nccl backend, CPU with gloo); one send/recv pair per cut."""
+    import torch
+    ops, bufs = [], []
+    for c, (r0, r1) in enumerate(cuts):
+        if r1 <= r0 or rank not in (c, c + 1):
+            continue
+        peer = c + 1 if rank == c else c
+        a, b = int(rowptr[r0]), int(rowptr[r1])
+        recv = torch.empty(b - a, dtype=values.dtype, device=values.device)
+        send = values[a:b].clone()
+        ops += [dist.P2POp(dist.isend, send, peer), dist.P2POp(dist.irecv, recv, peer)]
+        bufs.append((a, b, recv, send))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for a, b, recv, _ in bufs:
+        values[a:b] += recv
+    return values

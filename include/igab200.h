@@ -146,6 +146,24 @@ igab_status igab_assemble(igab_patch* p, int kind, const double* D, double fcons
                           int64_t elem_end, const int* nq1, const double* const* xi1d, const double* const* w1d,
                           double* Ke, double* fe, igab_memspace out_space, void* stream);
 
+/* ---- global sparse matrix (CSR) ---------------------------------------------------------------------------------------
+ * Replaces the scatter loop of globalAssembler, dune/python/test/poisson.py:113-125 (A[gi,gj] += localA[i,j] through
+ * localView.index), for the tensor-product DOF numbering of NurbsPreBasis (nurbsbasis.hh:572-584): row g couples
+ * with the DOFs within +-degree in every direction.  ncomp > 1: vector-valued basis, flat-interleaved numbering
+ * g*ncomp + c (dune-functions PowerPreBasis, python/dune/iga/basis/__init__.py:53-67).  Untrimmed patches only
+ * (IGAB_UNSUPPORTED when trim flags were given).
+ *   igab_csr_pattern : *nrows = ndof*ncomp, *nnz; rowptr[nrows+1] (int64) and colidx[nnz] (int32) may be NULL to
+ *                      query the sizes first.  Columns ascending within a row.
+ *   igab_csr_assemble: values[nnz] (+)= sum over the elements [elem_begin, elem_end) of Ke[e - elem_begin][i][j];
+ *                      a GATHER per non-zero in a fixed element order: no atomics, bitwise reproducible.  Rows of
+ *                      DOFs that other element ranges also touch receive only this range's share -- ranks exchange
+ *                      and add those interface rows (contiguous value ranges, see dune-iga_b200/partition.py).       */
+igab_status igab_csr_pattern(igab_patch* p, int ncomp, int64_t* nrows, int64_t* nnz, int64_t* rowptr, int32_t* colidx,
+                             igab_memspace space, void* stream);
+igab_status igab_csr_assemble(igab_patch* p, int ncomp, int64_t elem_begin, int64_t elem_end, const double* Ke,
+                              const int64_t* rowptr, double* values, int accumulate, igab_memspace space,
+                              void* stream);
+
 /* ---- patch reductions ---------------------------------------------------------------------------------------------
  * Replaces the user loop summing NURBSGeometry::volume() over elements (nurbsgeometry.hh:96-113,
  * dune/iga/test/gridtests.cpp:338-341): result = sum_{e in range} sum_q detJ w.  Deterministic two-level tree sum.

@@ -74,3 +74,58 @@ def test_partition_helpers():
     assert b[0] == 0 and b[-1] == 100 and all(b[i] <= b[i + 1] for i in range(4))
     loads = [counts[b[i]:b[i + 1]].sum() for i in range(4)]
     assert max(loads) - min(loads) <= 2 * 120
+
+
+def _csr_worker(rank, world, port, q):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import igab200  # noqa: F401
+    import patches_for_tests as PFT
+    import portbind as PT
+    from dune_iga_b200 import partition, patchdata as PD
+    spec = PFT.small_patch("plate_hole_p2", level=2)
+    pd = spec["patch"]
+    P = PT.PortPatch(pd.degree, pd.knotSpans, pd.cp, 2)
+    x, w = PD.gaussLegendre01(3)
+    Ke, _ = P.assemble(0, [x, x], [w, w])
+    dof, n = P.dofmap()
+    # dense stand-in for the device CSR gather on this GPU-less box: full band pattern, row-major
+    rowptr = np.arange(n + 1) * n
+    eb, ee = partition.slab_range(pd.elementsPerDirection, world, rank)
+    mine = np.zeros((n, n))
+    for e in range(eb, ee):
+        np.add.at(mine, (dof[e][:, None], dof[e][None, :]), Ke[e])
+    full = np.zeros((n, n))
+    for e in range(P.nelem):
+        np.add.at(full, (dof[e][:, None], dof[e][None, :]), Ke[e])
+    cuts = partition.interface_row_ranges(pd, world)
+    vals = torch.from_numpy(mine.reshape(-1).copy())
+    partition.exchange_interface_rows(vals, rowptr, cuts, rank, world, dist)
+    got = vals.numpy().reshape(n, n)
+    # rows of the DOF layers this rank touches are now complete
+    touched = np.unique(dof[eb:ee])
+    err = np.abs(got[touched] - full[touched]).max() / np.abs(full).max()
+    q.put((rank, cuts, float(err), pd.ncp, pd.degree))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_interface_rows_exchange_two_ranks():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_csr_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, cuts, err, ncp, deg in res:
+        assert err < 1e-14
+        (r0, r1), = cuts
+        assert (r1 - r0) == deg[1] * ncp[0]  # p layers of n_0 basis functions
