@@ -8,6 +8,8 @@
 // Round-1 structure: (1) evaluation kernel (tensor sum-factorised or general) -> N, dN, detJ, JinvT in stream-ordered
 // scratch, (2) B-stack kernel, (3) contraction kernel: FP64 tensor-core DMMA (mma.sync.m8n8k4.f64) for n >= 32,
 // shared-memory FMA tiles below that.
+#include <cstdlib>
+
 #include "igab_internal.cuh"
 
 namespace igab {
@@ -420,6 +422,8 @@ template <int DIM, int DW>
 igab_status assemble_dd(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, int kind, const double* D_dev, double fconst, long long eb, long long nel,
                         const int* nq1, const double* const* xi, const double* const* w, double* Ke, double* fe,
                         cudaStream_t stream) {
+  if (!getenv("IGAB_NO_FUSED_ASSEMBLY") && gram_fused_supported(P, kind, nq1))
+    return launch_gram_fused(P, ws, xi1d_host, xi, w, kind, fconst, eb, nel, nq1, Ke, fe, stream);
   long long nq = 1;
   for (int d = 0; d < DIM; ++d) nq *= nq1[d];
   const int nb = P.nb;

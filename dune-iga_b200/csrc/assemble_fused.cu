@@ -1,0 +1,376 @@
+// assemble_fused.cu -- fully fused element-matrix kernel for 3-D Poisson / mass at p = 3, 4 (BASELINE config C3):
+// evaluation AND contraction in one kernel, nothing but K_e (and f_e) leaves the SM.
+//
+// Functional spec: localAssembler of dune/python/test/poisson.py:37-81 (per point: evaluateJacobian, geometry
+// jacobianInverseTransposed / integrationElement, grad_i = J^-T dphi_i, A[i][j] += w detJ grad_i . grad_j).
+//
+// One block per element (grid-stride, two blocks resident per SM):
+//   (1) univariate K1 tables of the element and its (p+1)^3 control points -> shared memory (homogeneous form);
+//   (2) geometry of ALL quadrature points by sum factorisation with the whole block (as eval_tensor_sf.cu, O(p^4));
+//       per point: 1/W, dW/dxi, J^-T, w detJ kept in shared memory;
+//   (3) the quadrature points are consumed in chunks of 16 k-rows (5 points x 3 gradient components + 1 zero row; 16
+//       points for the mass matrix): physical gradients G_q[c][i] of the chunk are built in shared memory straight from
+//       the tables (rational basis + quotient rule, nurbsalgorithms.hh:226-248), double-buffered, ONE __syncthreads
+//       per chunk, and contracted on the FP64 tensor cores (mma.sync.m8n8k4.f64, SASS DMMA) into register
+//       accumulators.  K_e is symmetric: only the upper 32x32 blocks are contracted (one warp each) and mirrored
+//       on the way out.
+#include <algorithm>
+
+#include "igab_internal.cuh"
+
+namespace igab {
+
+namespace {
+
+__device__ __forceinline__ void dmma8x8x4_f(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double2 lds2f(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+template <int P, int Q>
+struct FCfg {
+  static constexpr int NB1 = P + 1, NB = NB1 * NB1 * NB1, NQ = Q * Q * Q, Q2 = Q * Q;
+  static constexpr int NBP = (NB + 31) / 32 * 32;
+  static constexpr int NBLK = NBP / 32, NUP = NBLK * (NBLK + 1) / 2, NT = NUP * 32;
+  static constexpr int TAB = Q * NB1 * 2;
+  static constexpr int HS = 4 * NB1 + 1, S1C = NB1 * NB1 + 1, S2S = NB1 | 1;
+  static constexpr int ev(int x) { return (x + 1) & ~1; }
+  static constexpr int SZ_T = 3 * TAB;
+  static constexpr int SZ_W = ev(NBP);
+  static constexpr int SZ_H = ev(NB1 * NB1 * HS);
+  static constexpr int SZ_S1 = 2 * Q * 4 * S1C;
+  static constexpr int SZ_G = 16 * NQ;
+  static constexpr int SZ_A = ev((SZ_H + SZ_S1) > SZ_G ? (SZ_H + SZ_S1) : SZ_G);
+  static constexpr int SZ_S2 = ev(3 * 4 * Q2 * S2S);
+  static constexpr int CS = 16;  // doubles per point: 1/W, W_0..2, J^-T[9], w detJ, pad
+  static constexpr int SZ_C = CS * NQ;
+  static constexpr int KC = 16, LD = NBP + 4;
+  static constexpr int SZ_SA = 2 * KC * LD;
+  static constexpr int SZ_TOTAL = SZ_T + SZ_W + SZ_A + SZ_S2 + SZ_C + SZ_SA;
+};
+
+template <int P, int Q, int NROW>
+__global__ void __launch_bounds__(FCfg<P, Q>::NT, 2) gram_fused_kernel(
+    PatchDev Pd, long long elem_begin, long long nelem, const double* __restrict__ tab0,
+    const double* __restrict__ tab1, const double* __restrict__ tab2, const double* __restrict__ w0,
+    const double* __restrict__ w1, const double* __restrict__ w2, double fconst, double* __restrict__ Ke,
+    double* __restrict__ fe) {
+  using C = FCfg<P, Q>;
+  constexpr int NB1 = C::NB1, NB = C::NB, NQ = C::NQ, Q2 = C::Q2, NBP = C::NBP, NT = C::NT, KC = C::KC, LD = C::LD;
+  constexpr int CS = C::CS;
+  constexpr int pts = KC / NROW, nchunk = (NQ + pts - 1) / pts;
+  extern __shared__ __align__(16) double fsm[];
+  double* const sT = fsm;
+  double* const sW = sT + C::SZ_T;
+  double* const rA = sW + C::SZ_W;
+  double* const sS2 = rA + C::SZ_A;
+  double* const sC = sS2 + C::SZ_S2;
+  double* const sA = sC + C::SZ_C;  // [2][KC][LD]
+  double* const sH = rA;
+  double* const sS1 = rA + C::SZ_H;
+  double* const sG = rA;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  int bi = 0, bj = 0;
+  {
+    int w = warp;
+    while (w >= C::NBLK - bi) {
+      w -= C::NBLK - bi;
+      ++bi;
+    }
+    bj = bi + w;
+  }
+  const int wi = bi * 32, wj = bj * 32;
+  for (int idx = tid; idx < C::SZ_SA; idx += NT) sA[idx] = 0.0;  // zero rows / padding columns stay zero
+  for (int idx = tid; idx < C::SZ_W; idx += NT) sW[idx] = 0.0;
+
+  for (long long el = blockIdx.x; el < nelem; el += gridDim.x) {
+    const long long e = elem_begin + el;
+    int e0, e1, e2;
+    {
+      long long h = e;
+      e0 = (int)(h % Pd.nel[0]); h /= Pd.nel[0];
+      e1 = (int)(h % Pd.nel[1]); h /= Pd.nel[1];
+      e2 = (int)h;
+    }
+    __syncthreads();  // previous element done with every buffer
+    // ---- (1) tables and control points
+    for (int j = tid; j < C::TAB; j += NT) {
+      sT[j] = __ldg(tab0 + (size_t)e0 * C::TAB + j);
+      sT[C::TAB + j] = __ldg(tab1 + (size_t)e1 * C::TAB + j);
+      sT[2 * C::TAB + j] = __ldg(tab2 + (size_t)e2 * C::TAB + j);
+    }
+    {
+      const int b0 = Pd.spanTab[0][e0] - P, b1 = Pd.spanTab[1][e1] - P, b2 = Pd.spanTab[2][e2] - P;
+      const long long n0 = Pd.ncp[0], n1 = Pd.ncp[1];
+      const double2* cp2 = reinterpret_cast<const double2*>(Pd.cp);
+      for (int i = tid; i < NB; i += NT) {
+        const int i0 = i % NB1, i12 = i / NB1, i1 = i12 % NB1, i2 = i12 / NB1;
+        const long long gi = (b0 + i0) + n0 * ((b1 + i1) + n1 * (long long)(b2 + i2));
+        const double2 xy = __ldg(cp2 + 2 * gi), zw = __ldg(cp2 + 2 * gi + 1);
+        double* h = sH + i12 * C::HS + 4 * i0;
+        h[0] = xy.x * zw.y; h[1] = xy.y * zw.y; h[2] = zw.x * zw.y; h[3] = zw.y;
+        sW[i] = zw.y;
+      }
+    }
+    __syncthreads();
+    // ---- (2) geometry: three 1-D contractions of the homogeneous net (see eval_tensor_sf.cu for the layout)
+    for (int col = tid; col < 4 * NB1 * NB1; col += NT) {
+      const int i12 = col % (NB1 * NB1), c = col / (NB1 * NB1);
+      double h[NB1];
+#pragma unroll
+      for (int i0 = 0; i0 < NB1; ++i0) h[i0] = sH[i12 * C::HS + 4 * i0 + c];
+#pragma unroll
+      for (int q0 = 0; q0 < Q; ++q0) {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int i0 = 0; i0 < NB1; ++i0) {
+          const double2 tt = lds2f(sT + (q0 * NB1 + i0) * 2);
+          a0 = fma(tt.x, h[i0], a0);
+          a1 = fma(tt.y, h[i0], a1);
+        }
+        sS1[((0 * Q + q0) * 4 + c) * C::S1C + i12] = a0;
+        sS1[((1 * Q + q0) * 4 + c) * C::S1C + i12] = a1;
+      }
+    }
+    __syncthreads();
+    for (int col = tid; col < 2 * Q * 4 * NB1; col += NT) {
+      int r = col;
+      const int i2 = r % NB1; r /= NB1;
+      const int c = r % 4; r /= 4;
+      const int q0 = r % Q;
+      const int a0 = r / Q;
+      double s[NB1];
+#pragma unroll
+      for (int i1 = 0; i1 < NB1; ++i1) s[i1] = sS1[((a0 * Q + q0) * 4 + c) * C::S1C + i1 + NB1 * i2];
+#pragma unroll
+      for (int q1 = 0; q1 < Q; ++q1) {
+        double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+        for (int i1 = 0; i1 < NB1; ++i1) {
+          const double2 tt = lds2f(sT + C::TAB + (q1 * NB1 + i1) * 2);
+          v0 = fma(tt.x, s[i1], v0);
+          v1 = fma(tt.y, s[i1], v1);
+        }
+        const int q01 = q0 + Q * q1;
+        if (a0 == 0) {
+          sS2[((0 * 4 + c) * Q2 + q01) * C::S2S + i2] = v0;
+          sS2[((2 * 4 + c) * Q2 + q01) * C::S2S + i2] = v1;
+        } else {
+          sS2[((1 * 4 + c) * Q2 + q01) * C::S2S + i2] = v0;
+        }
+      }
+    }
+    __syncthreads();
+    for (int col = tid; col < 3 * 4 * Q2; col += NT) {
+      int r = col;
+      const int q01 = r % Q2; r /= Q2;
+      const int c = r % 4;
+      const int a01 = r / 4;
+      double s[NB1];
+#pragma unroll
+      for (int i2 = 0; i2 < NB1; ++i2) s[i2] = sS2[((a01 * 4 + c) * Q2 + q01) * C::S2S + i2];
+#pragma unroll
+      for (int q2 = 0; q2 < Q; ++q2) {
+        double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+        for (int i2 = 0; i2 < NB1; ++i2) {
+          const double2 tt = lds2f(sT + 2 * C::TAB + (q2 * NB1 + i2) * 2);
+          v0 = fma(tt.x, s[i2], v0);
+          v1 = fma(tt.y, s[i2], v1);
+        }
+        const int pt = q01 + Q2 * q2;
+        if (a01 == 0) {
+          sG[(0 * 4 + c) * NQ + pt] = v0;
+          sG[(3 * 4 + c) * NQ + pt] = v1;
+        } else {
+          sG[(a01 * 4 + c) * NQ + pt] = v0;
+        }
+      }
+    }
+    __syncthreads();
+    // per point: x = C/W, J_d = (C_d - W_d x)/W, detJ, J^-T (cofactors / det), w detJ
+    for (int pt = tid; pt < NQ; pt += NT) {
+      const double W = sG[3 * NQ + pt], invW = 1.0 / W;
+      double x[3], J[3][3], Wd[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) x[c] = sG[c * NQ + pt] * invW;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        Wd[d] = sG[((d + 1) * 4 + 3) * NQ + pt];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) J[d][c] = (sG[((d + 1) * 4 + c) * NQ + pt] - Wd[d] * x[c]) * invW;
+      }
+      const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2],
+                   c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+      const double c10 = J[0][2] * J[2][1] - J[0][1] * J[2][2], c11 = J[0][0] * J[2][2] - J[0][2] * J[2][0],
+                   c12 = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+      const double c20 = J[0][1] * J[1][2] - J[0][2] * J[1][1], c21 = J[0][2] * J[1][0] - J[0][0] * J[1][2],
+                   c22 = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+      const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02, id = 1.0 / det;
+      int q = pt;
+      double w = w0[q % Q];
+      q /= Q;
+      w *= w1[q % Q];
+      w *= w2[q / Q];
+      double* o = sC + CS * pt;
+      o[0] = invW; o[1] = Wd[0]; o[2] = Wd[1]; o[3] = Wd[2];
+      // J^-T[c][d] = cof[d][c] / det
+      o[4] = c00 * id; o[5] = c10 * id; o[6] = c20 * id;
+      o[7] = c01 * id; o[8] = c11 * id; o[9] = c21 * id;
+      o[10] = c02 * id; o[11] = c12 * id; o[12] = c22 * id;
+      o[13] = w * fabs(det);
+    }
+    __syncthreads();
+
+    // ---- (3) chunked Gram contraction
+    auto build = [&](int ch) {
+      double* A = sA + (ch & 1) * KC * LD;
+      for (int item = tid; item < pts * NBP; item += NT) {
+        const int ql = item / NBP, i = item % NBP;
+        const int pt = ch * pts + ql;
+        double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+        if (pt < NQ && i < NB) {
+          const int i0 = i % NB1, i1 = (i / NB1) % NB1, i2 = i / (NB1 * NB1);
+          const int q0 = pt % Q, q1 = (pt / Q) % Q, q2 = pt / Q2;
+          const double2 a = lds2f(sT + (q0 * NB1 + i0) * 2), b = lds2f(sT + C::TAB + (q1 * NB1 + i1) * 2),
+                        c = lds2f(sT + 2 * C::TAB + (q2 * NB1 + i2) * 2);
+          const double* k = sC + CS * pt;
+          const double w = sW[i], invW = k[0];
+          const double t00 = a.x * b.x, wn2 = w * c.x;
+          const double R = t00 * wn2 * invW;
+          if constexpr (NROW == 1) {
+            r0 = R;
+          } else {
+            const double d0 = (a.y * b.x * wn2 - k[1] * R) * invW;
+            const double d1 = (a.x * b.y * wn2 - k[2] * R) * invW;
+            const double d2 = (t00 * (w * c.y) - k[3] * R) * invW;
+            r0 = k[4] * d0 + k[5] * d1 + k[6] * d2;
+            r1 = k[7] * d0 + k[8] * d1 + k[9] * d2;
+            r2 = k[10] * d0 + k[11] * d1 + k[12] * d2;
+          }
+        }
+        if constexpr (NROW == 1) {
+          A[ql * LD + i] = r0;
+        } else {
+          A[(3 * ql + 0) * LD + i] = r0;
+          A[(3 * ql + 1) * LD + i] = r1;
+          A[(3 * ql + 2) * LD + i] = r2;
+        }
+      }
+    };
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    build(0);
+    __syncthreads();
+#pragma unroll 1
+    for (int ch = 0; ch < nchunk; ++ch) {
+      const double* A = sA + (ch & 1) * KC * LD;
+#pragma unroll
+      for (int ks = 0; ks < KC; ks += 4) {
+        const int k = ks + t, pt = ch * pts + k / NROW;
+        const double sc = (k < pts * NROW && pt < NQ) ? sC[CS * pt + 13] : 0.0;
+        double af[4], bf[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) af[a] = A[k * LD + wi + 8 * a + g];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bf[b] = A[k * LD + wj + 8 * b + g] * sc;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) dmma8x8x4_f(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+      }
+      if (ch + 1 < nchunk) build(ch + 1);
+      __syncthreads();
+    }
+    double* K = Ke + el * (long long)NB * NB;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int i = wi + 8 * a + g, j = wj + 8 * b + 2 * t;
+        if (i < NB) {
+          if (j < NB) K[(long long)i * NB + j] = acc[a][b][0];
+          if (j + 1 < NB) K[(long long)i * NB + j + 1] = acc[a][b][1];
+          if (bi != bj) {
+            if (j < NB) K[(long long)j * NB + i] = acc[a][b][0];
+            if (j + 1 < NB) K[(long long)(j + 1) * NB + i] = acc[a][b][1];
+          }
+        }
+      }
+    // ---- load vector f_e[i] = sum_q w detJ R_i fconst  (poisson.py:79)
+    if (fe) {
+      for (int i = tid; i < NB; i += NT) {
+        const int i0 = i % NB1, i1 = (i / NB1) % NB1, i2 = i / (NB1 * NB1);
+        const double w = sW[i];
+        double s = 0.0;
+        for (int pt = 0; pt < NQ; ++pt) {
+          const int q0 = pt % Q, q1 = (pt / Q) % Q, q2 = pt / Q2;
+          const double R = sT[(q0 * NB1 + i0) * 2] * sT[C::TAB + (q1 * NB1 + i1) * 2] *
+                           (w * sT[2 * C::TAB + (q2 * NB1 + i2) * 2]) * sC[CS * pt];
+          s += sC[CS * pt + 13] * R * fconst;
+        }
+        fe[el * NB + i] = s;
+      }
+    }
+  }
+}
+
+template <int P, int Q>
+igab_status launch_pq(const PatchDev& Pd, SfWorkspace& ws, bool mass, double fconst, long long eb, long long nel,
+                      const double* const* w_dev, double* Ke, double* fe, cudaStream_t stream) {
+  using C = FCfg<P, Q>;
+  const size_t smem = (size_t)C::SZ_TOTAL * sizeof(double);
+  static bool configured = false;
+  static int sms = 148, bps = 2;
+  if (!configured) {
+    IGAB_CUDA_TRY(cudaFuncSetAttribute(gram_fused_kernel<P, Q, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IGAB_CUDA_TRY(cudaFuncSetAttribute(gram_fused_kernel<P, Q, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0;
+    IGAB_CUDA_TRY(cudaGetDevice(&dev));
+    IGAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    IGAB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, gram_fused_kernel<P, Q, 3>, C::NT, smem));
+    if (bps < 1) bps = 1;
+    configured = true;
+  }
+  const unsigned grid = (unsigned)std::min<long long>(nel, (long long)bps * sms);  // persistent, grid-stride
+  if (mass)
+    gram_fused_kernel<P, Q, 1><<<grid, C::NT, smem, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],
+                                                             w_dev[1], w_dev[2], fconst, Ke, fe);
+  else
+    gram_fused_kernel<P, Q, 3><<<grid, C::NT, smem, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],
+                                                             w_dev[1], w_dev[2], fconst, Ke, fe);
+  count_launch();
+  IGAB_CUDA_TRY(cudaGetLastError());
+  return IGAB_OK;
+}
+
+}  // namespace
+
+bool gram_fused_supported(const PatchDev& P, int kind, const int* nq1) {
+  if (P.dim != 3 || P.dw != 3 || kind == IGAB_ASM_ELASTICITY) return false;
+  if (P.degree[0] != P.degree[1] || P.degree[0] != P.degree[2]) return false;
+  if (nq1[0] != nq1[1] || nq1[0] != nq1[2]) return false;
+  return (P.degree[0] == 3 && nq1[0] == 4) || (P.degree[0] == 4 && nq1[0] == 5);
+}
+
+igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host,
+                              const double* const* xi1d_dev, const double* const* w1d_dev, int kind, double fconst,
+                              long long eb, long long nel, const int* nq1, double* Ke, double* fe, cudaStream_t stream) {
+  if (!gram_fused_supported(P, kind, nq1)) {
+    set_error("assemble: no fused kernel for this configuration");
+    return IGAB_UNSUPPORTED;
+  }
+  igab_status st = ensure_tables3d(P, ws, nq1[0], xi1d_dev, xi1d_host, stream);
+  if (st) return st;
+  const bool mass = kind == IGAB_ASM_MASS;
+  if (P.degree[0] == 3) return launch_pq<3, 4>(P, ws, mass, fconst, eb, nel, w1d_dev, Ke, fe, stream);
+  return launch_pq<4, 5>(P, ws, mass, fconst, eb, nel, w1d_dev, Ke, fe, stream);
+}
+
+}  // namespace igab

@@ -476,15 +476,12 @@ __global__ void __launch_bounds__(128) eval_sf3d_kernel(PatchDev Pd, long long e
 
 constexpr int kCounterRing = 64;
 
-template <int P, int Q>
-igab_status launch_cfg(const PatchDev& Pd, SfWorkspace& ws, const PointSource& src, const double* const* xi1d_host,
-                       long long nelem, const EvalOutDev& out, cudaStream_t stream) {
-  using C = Cfg<P, Q>;
-  if (nelem > 0x7fffffffLL) {
-    set_error("eval_tensor: more than 2^31 elements in one launch");
-    return IGAB_INVALID_ARGUMENT;
-  }
-  // K1 (cached per handle: rebuilt only when the rule changes)
+}  // namespace
+
+// K1 for 3-D patches (cached per handle: rebuilt only when the rule or the stream changes); table layout
+// [e_d][q][i][a], a = 0 value, a = 1 d/dxi.  Shared by the evaluation kernel and the fused assembly kernel.
+igab_status ensure_tables3d(const PatchDev& Pd, SfWorkspace& ws, int Q, const double* const* xi1d_dev,
+                            const double* const* xi1d_host, cudaStream_t stream) {
   bool same = ws.valid && ws.stream == stream;
   for (int d = 0; d < 3 && same; ++d) {
     same = ws.nq1[d] == Q && (int)ws.xi[d].size() == Q;
@@ -493,26 +490,40 @@ igab_status launch_cfg(const PatchDev& Pd, SfWorkspace& ws, const PointSource& s
   if (!ws.counter) {
     IGAB_CUDA_TRY(cudaMalloc(&ws.counter, sizeof(unsigned int) * kCounterRing));
   }
-  if (!same) {
-    for (int d = 0; d < 3; ++d) {
-      const size_t n = (size_t)Pd.nel[d] * C::TAB;
-      if (ws.tabCap[d] < n) {
-        // stream-ordered: earlier launches on this stream may still read the old tables
-        if (ws.tab[d]) IGAB_CUDA_TRY(cudaFreeAsync(ws.tab[d], stream));
-        ws.tab[d] = nullptr;
-        ws.tabCap[d] = 0;
-        IGAB_CUDA_TRY(cudaMallocAsync(&ws.tab[d], n * sizeof(double), stream));
-        ws.tabCap[d] = n;
-      }
-      const int threads = 128, total = Pd.nel[d] * Q;
-      tables_kernel<<<(total + threads - 1) / threads, threads, 0, stream>>>(Pd, d, Q, src.xi1d[d], ws.tab[d]);
-      ws.nq1[d] = Q;
-      ws.xi[d].assign(xi1d_host[d], xi1d_host[d] + Q);
+  if (same) return IGAB_OK;
+  for (int d = 0; d < 3; ++d) {
+    const size_t n = (size_t)Pd.nel[d] * Q * (Pd.degree[d] + 1) * 2;
+    if (ws.tabCap[d] < n) {
+      // stream-ordered: earlier launches on this stream may still read the old tables
+      if (ws.tab[d]) IGAB_CUDA_TRY(cudaFreeAsync(ws.tab[d], stream));
+      ws.tab[d] = nullptr;
+      ws.tabCap[d] = 0;
+      IGAB_CUDA_TRY(cudaMallocAsync(&ws.tab[d], n * sizeof(double), stream));
+      ws.tabCap[d] = n;
     }
-    count_launch(3);
-    ws.valid = true;
-    ws.stream = stream;
+    const int threads = 128, total = Pd.nel[d] * Q;
+    tables_kernel<<<(total + threads - 1) / threads, threads, 0, stream>>>(Pd, d, Q, xi1d_dev[d], ws.tab[d]);
+    ws.nq1[d] = Q;
+    ws.xi[d].assign(xi1d_host[d], xi1d_host[d] + Q);
   }
+  count_launch(3);
+  ws.valid = true;
+  ws.stream = stream;
+  return IGAB_OK;
+}
+
+namespace {
+
+template <int P, int Q>
+igab_status launch_cfg(const PatchDev& Pd, SfWorkspace& ws, const PointSource& src, const double* const* xi1d_host,
+                       long long nelem, const EvalOutDev& out, cudaStream_t stream) {
+  using C = Cfg<P, Q>;
+  if (nelem > 0x7fffffffLL) {
+    set_error("eval_tensor: more than 2^31 elements in one launch");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  igab_status st = ensure_tables3d(Pd, ws, Q, src.xi1d, xi1d_host, stream);
+  if (st) return st;
   // K2
   constexpr int WARPS = 4;
   const size_t smem = (size_t)WARPS * C::SZ_WARP * sizeof(double);

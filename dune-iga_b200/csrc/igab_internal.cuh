@@ -75,6 +75,13 @@ igab_status launch_eval_tensor_sf(const PatchDev& P, SfWorkspace& ws, const Poin
                                   const double* const* xi1d_host, long long nelem, int order, const EvalOutDev& out,
                                   cudaStream_t stream);
 void free_sf_workspace(SfWorkspace& ws);
+igab_status ensure_tables3d(const PatchDev& Pd, SfWorkspace& ws, int Q, const double* const* xi1d_dev,
+                            const double* const* xi1d_host, cudaStream_t stream);
+// fully fused element matrices (3-D Poisson / mass, p = 3, 4)
+bool gram_fused_supported(const PatchDev& P, int kind, const int* nq1);
+igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host,
+                              const double* const* xi1d_dev, const double* const* w1d_dev, int kind, double fconst,
+                              long long eb, long long nel, const int* nq1, double* Ke, double* fe, cudaStream_t stream);
 bool eval_tensor_sf_supported(const PatchDev& P, const int* nq1, int order, const EvalOutDev& out);
 // 2-D point lists (trimmed batches): per-point univariate rows in registers
 bool eval_points_2d_supported(const PatchDev& P);
