@@ -419,11 +419,11 @@ igab_status eval_for(const PatchDev& P, SfWorkspace& ws, const double* const* xi
 }
 
 template <int DIM, int DW>
-igab_status assemble_dd(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, int kind, const double* D_dev, double fconst, long long eb, long long nel,
+igab_status assemble_dd(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, int kind, const double* D_host, const double* D_dev, double fconst, long long eb, long long nel,
                         const int* nq1, const double* const* xi, const double* const* w, double* Ke, double* fe,
                         cudaStream_t stream) {
   if (!getenv("IGAB_NO_FUSED_ASSEMBLY") && gram_fused_supported(P, kind, nq1))
-    return launch_gram_fused(P, ws, xi1d_host, xi, w, kind, fconst, eb, nel, nq1, Ke, fe, stream);
+    return launch_gram_fused(P, ws, xi1d_host, xi, w, kind, fconst, eb, nel, nq1, Ke, fe, stream, D_host);
   long long nq = 1;
   for (int d = 0; d < DIM; ++d) nq *= nq1[d];
   const int nb = P.nb;
@@ -510,14 +510,14 @@ igab_status assemble_dd(const PatchDev& P, SfWorkspace& ws, const double* const*
 
 }  // namespace
 
-igab_status launch_assemble(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, int kind, const double* D_dev, double fconst, long long elem_begin,
+igab_status launch_assemble(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, int kind, const double* D_host, const double* D_dev, double fconst, long long elem_begin,
                             long long nelem, const int* nq1, const double* const* xi1d_dev,
                             const double* const* w1d_dev, double* Ke, double* fe, cudaStream_t stream) {
   switch (P.dim * 10 + P.dw) {
-    case 11: return assemble_dd<1, 1>(P, ws, xi1d_host, kind, D_dev, fconst, elem_begin, nelem, nq1, xi1d_dev, w1d_dev, Ke, fe, stream);
-    case 22: return assemble_dd<2, 2>(P, ws, xi1d_host, kind, D_dev, fconst, elem_begin, nelem, nq1, xi1d_dev, w1d_dev, Ke, fe, stream);
-    case 23: return assemble_dd<2, 3>(P, ws, xi1d_host, kind, D_dev, fconst, elem_begin, nelem, nq1, xi1d_dev, w1d_dev, Ke, fe, stream);
-    case 33: return assemble_dd<3, 3>(P, ws, xi1d_host, kind, D_dev, fconst, elem_begin, nelem, nq1, xi1d_dev, w1d_dev, Ke, fe, stream);
+    case 11: return assemble_dd<1, 1>(P, ws, xi1d_host, kind, D_host, D_dev, fconst, elem_begin, nelem, nq1, xi1d_dev, w1d_dev, Ke, fe, stream);
+    case 22: return assemble_dd<2, 2>(P, ws, xi1d_host, kind, D_host, D_dev, fconst, elem_begin, nelem, nq1, xi1d_dev, w1d_dev, Ke, fe, stream);
+    case 23: return assemble_dd<2, 3>(P, ws, xi1d_host, kind, D_host, D_dev, fconst, elem_begin, nelem, nq1, xi1d_dev, w1d_dev, Ke, fe, stream);
+    case 33: return assemble_dd<3, 3>(P, ws, xi1d_host, kind, D_host, D_dev, fconst, elem_begin, nelem, nq1, xi1d_dev, w1d_dev, Ke, fe, stream);
   }
   set_error("assemble: unsupported (dim, dimworld)");
   return IGAB_UNSUPPORTED;

@@ -51,6 +51,160 @@ struct FCfg {
   static constexpr int SZ_TOTAL = SZ_T + SZ_W + SZ_A + SZ_S2 + SZ_C + SZ_SA;
 };
 
+// Steps (1)+(2) for one element, executed by the whole block (NT threads): tables + control points -> shared, geometry
+// of all quadrature points by sum factorisation, per-point constants sC[pt][16] = {1/W, dW/dxi_0..2, J^-T[3][3] row-major
+// [c][d], w detJ}.  Ends with a __syncthreads().
+template <int P, int Q, int NT>
+__device__ __forceinline__ void element_prepare(const PatchDev& Pd, long long e, const double* __restrict__ tab0,
+                                                const double* __restrict__ tab1, const double* __restrict__ tab2,
+                                                const double* __restrict__ w0, const double* __restrict__ w1,
+                                                const double* __restrict__ w2, double* sT, double* sW, double* rA,
+                                                double* sS2, double* sC) {
+  using C = FCfg<P, Q>;
+  constexpr int NB1 = C::NB1, NB = C::NB, NQ = C::NQ, Q2 = C::Q2, CS = C::CS;
+  double* const sH = rA;
+  double* const sS1 = rA + C::SZ_H;
+  double* const sG = rA;
+  const int tid = threadIdx.x;
+  int e0, e1, e2;
+  {
+    long long h = e;
+    e0 = (int)(h % Pd.nel[0]); h /= Pd.nel[0];
+    e1 = (int)(h % Pd.nel[1]); h /= Pd.nel[1];
+    e2 = (int)h;
+  }
+  __syncthreads();  // previous element done with every buffer
+  // ---- (1) tables and control points
+  for (int j = tid; j < C::TAB; j += NT) {
+    sT[j] = __ldg(tab0 + (size_t)e0 * C::TAB + j);
+    sT[C::TAB + j] = __ldg(tab1 + (size_t)e1 * C::TAB + j);
+    sT[2 * C::TAB + j] = __ldg(tab2 + (size_t)e2 * C::TAB + j);
+  }
+  {
+    const int b0 = Pd.spanTab[0][e0] - P, b1 = Pd.spanTab[1][e1] - P, b2 = Pd.spanTab[2][e2] - P;
+    const long long n0 = Pd.ncp[0], n1 = Pd.ncp[1];
+    const double2* cp2 = reinterpret_cast<const double2*>(Pd.cp);
+    for (int i = tid; i < NB; i += NT) {
+      const int i0 = i % NB1, i12 = i / NB1, i1 = i12 % NB1, i2 = i12 / NB1;
+      const long long gi = (b0 + i0) + n0 * ((b1 + i1) + n1 * (long long)(b2 + i2));
+      const double2 xy = __ldg(cp2 + 2 * gi), zw = __ldg(cp2 + 2 * gi + 1);
+      double* h = sH + i12 * C::HS + 4 * i0;
+      h[0] = xy.x * zw.y; h[1] = xy.y * zw.y; h[2] = zw.x * zw.y; h[3] = zw.y;
+      sW[i] = zw.y;
+    }
+  }
+  __syncthreads();
+  // ---- (2) geometry: three 1-D contractions of the homogeneous net (see eval_tensor_sf.cu for the layout)
+  for (int col = tid; col < 4 * NB1 * NB1; col += NT) {
+    const int i12 = col % (NB1 * NB1), c = col / (NB1 * NB1);
+    double h[NB1];
+#pragma unroll
+    for (int i0 = 0; i0 < NB1; ++i0) h[i0] = sH[i12 * C::HS + 4 * i0 + c];
+#pragma unroll
+    for (int q0 = 0; q0 < Q; ++q0) {
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int i0 = 0; i0 < NB1; ++i0) {
+        const double2 tt = lds2f(sT + (q0 * NB1 + i0) * 2);
+        a0 = fma(tt.x, h[i0], a0);
+        a1 = fma(tt.y, h[i0], a1);
+      }
+      sS1[((0 * Q + q0) * 4 + c) * C::S1C + i12] = a0;
+      sS1[((1 * Q + q0) * 4 + c) * C::S1C + i12] = a1;
+    }
+  }
+  __syncthreads();
+  for (int col = tid; col < 2 * Q * 4 * NB1; col += NT) {
+    int r = col;
+    const int i2 = r % NB1; r /= NB1;
+    const int c = r % 4; r /= 4;
+    const int q0 = r % Q;
+    const int a0 = r / Q;
+    double s[NB1];
+#pragma unroll
+    for (int i1 = 0; i1 < NB1; ++i1) s[i1] = sS1[((a0 * Q + q0) * 4 + c) * C::S1C + i1 + NB1 * i2];
+#pragma unroll
+    for (int q1 = 0; q1 < Q; ++q1) {
+      double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+      for (int i1 = 0; i1 < NB1; ++i1) {
+        const double2 tt = lds2f(sT + C::TAB + (q1 * NB1 + i1) * 2);
+        v0 = fma(tt.x, s[i1], v0);
+        v1 = fma(tt.y, s[i1], v1);
+      }
+      const int q01 = q0 + Q * q1;
+      if (a0 == 0) {
+        sS2[((0 * 4 + c) * Q2 + q01) * C::S2S + i2] = v0;
+        sS2[((2 * 4 + c) * Q2 + q01) * C::S2S + i2] = v1;
+      } else {
+        sS2[((1 * 4 + c) * Q2 + q01) * C::S2S + i2] = v0;
+      }
+    }
+  }
+  __syncthreads();
+  for (int col = tid; col < 3 * 4 * Q2; col += NT) {
+    int r = col;
+    const int q01 = r % Q2; r /= Q2;
+    const int c = r % 4;
+    const int a01 = r / 4;
+    double s[NB1];
+#pragma unroll
+    for (int i2 = 0; i2 < NB1; ++i2) s[i2] = sS2[((a01 * 4 + c) * Q2 + q01) * C::S2S + i2];
+#pragma unroll
+    for (int q2 = 0; q2 < Q; ++q2) {
+      double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+      for (int i2 = 0; i2 < NB1; ++i2) {
+        const double2 tt = lds2f(sT + 2 * C::TAB + (q2 * NB1 + i2) * 2);
+        v0 = fma(tt.x, s[i2], v0);
+        v1 = fma(tt.y, s[i2], v1);
+      }
+      const int pt = q01 + Q2 * q2;
+      if (a01 == 0) {
+        sG[(0 * 4 + c) * NQ + pt] = v0;
+        sG[(3 * 4 + c) * NQ + pt] = v1;
+      } else {
+        sG[(a01 * 4 + c) * NQ + pt] = v0;
+      }
+    }
+  }
+  __syncthreads();
+  // per point: x = C/W, J_d = (C_d - W_d x)/W, detJ, J^-T (cofactors / det), w detJ
+  for (int pt = tid; pt < NQ; pt += NT) {
+    const double W = sG[3 * NQ + pt], invW = 1.0 / W;
+    double x[3], J[3][3], Wd[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) x[c] = sG[c * NQ + pt] * invW;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      Wd[d] = sG[((d + 1) * 4 + 3) * NQ + pt];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) J[d][c] = (sG[((d + 1) * 4 + c) * NQ + pt] - Wd[d] * x[c]) * invW;
+    }
+    const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2],
+                 c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    const double c10 = J[0][2] * J[2][1] - J[0][1] * J[2][2], c11 = J[0][0] * J[2][2] - J[0][2] * J[2][0],
+                 c12 = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+    const double c20 = J[0][1] * J[1][2] - J[0][2] * J[1][1], c21 = J[0][2] * J[1][0] - J[0][0] * J[1][2],
+                 c22 = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02, id = 1.0 / det;
+    int q = pt;
+    double w = w0[q % Q];
+    q /= Q;
+    w *= w1[q % Q];
+    w *= w2[q / Q];
+    double* o = sC + CS * pt;
+    o[0] = invW; o[1] = Wd[0]; o[2] = Wd[1]; o[3] = Wd[2];
+    // J^-T[c][d] = cof[d][c] / det
+    o[4] = c00 * id; o[5] = c10 * id; o[6] = c20 * id;
+    o[7] = c01 * id; o[8] = c11 * id; o[9] = c21 * id;
+    o[10] = c02 * id; o[11] = c12 * id; o[12] = c22 * id;
+    o[13] = w * fabs(det);
+  }
+  __syncthreads();
+
+}
+
 template <int P, int Q, int NROW>
 __global__ void __launch_bounds__(FCfg<P, Q>::NT, 2) gram_fused_kernel(
     PatchDev Pd, long long elem_begin, long long nelem, const double* __restrict__ tab0,
@@ -68,9 +222,6 @@ __global__ void __launch_bounds__(FCfg<P, Q>::NT, 2) gram_fused_kernel(
   double* const sS2 = rA + C::SZ_A;
   double* const sC = sS2 + C::SZ_S2;
   double* const sA = sC + C::SZ_C;  // [2][KC][LD]
-  double* const sH = rA;
-  double* const sS1 = rA + C::SZ_H;
-  double* const sG = rA;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   int bi = 0, bj = 0;
@@ -88,142 +239,7 @@ __global__ void __launch_bounds__(FCfg<P, Q>::NT, 2) gram_fused_kernel(
 
   for (long long el = blockIdx.x; el < nelem; el += gridDim.x) {
     const long long e = elem_begin + el;
-    int e0, e1, e2;
-    {
-      long long h = e;
-      e0 = (int)(h % Pd.nel[0]); h /= Pd.nel[0];
-      e1 = (int)(h % Pd.nel[1]); h /= Pd.nel[1];
-      e2 = (int)h;
-    }
-    __syncthreads();  // previous element done with every buffer
-    // ---- (1) tables and control points
-    for (int j = tid; j < C::TAB; j += NT) {
-      sT[j] = __ldg(tab0 + (size_t)e0 * C::TAB + j);
-      sT[C::TAB + j] = __ldg(tab1 + (size_t)e1 * C::TAB + j);
-      sT[2 * C::TAB + j] = __ldg(tab2 + (size_t)e2 * C::TAB + j);
-    }
-    {
-      const int b0 = Pd.spanTab[0][e0] - P, b1 = Pd.spanTab[1][e1] - P, b2 = Pd.spanTab[2][e2] - P;
-      const long long n0 = Pd.ncp[0], n1 = Pd.ncp[1];
-      const double2* cp2 = reinterpret_cast<const double2*>(Pd.cp);
-      for (int i = tid; i < NB; i += NT) {
-        const int i0 = i % NB1, i12 = i / NB1, i1 = i12 % NB1, i2 = i12 / NB1;
-        const long long gi = (b0 + i0) + n0 * ((b1 + i1) + n1 * (long long)(b2 + i2));
-        const double2 xy = __ldg(cp2 + 2 * gi), zw = __ldg(cp2 + 2 * gi + 1);
-        double* h = sH + i12 * C::HS + 4 * i0;
-        h[0] = xy.x * zw.y; h[1] = xy.y * zw.y; h[2] = zw.x * zw.y; h[3] = zw.y;
-        sW[i] = zw.y;
-      }
-    }
-    __syncthreads();
-    // ---- (2) geometry: three 1-D contractions of the homogeneous net (see eval_tensor_sf.cu for the layout)
-    for (int col = tid; col < 4 * NB1 * NB1; col += NT) {
-      const int i12 = col % (NB1 * NB1), c = col / (NB1 * NB1);
-      double h[NB1];
-#pragma unroll
-      for (int i0 = 0; i0 < NB1; ++i0) h[i0] = sH[i12 * C::HS + 4 * i0 + c];
-#pragma unroll
-      for (int q0 = 0; q0 < Q; ++q0) {
-        double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-        for (int i0 = 0; i0 < NB1; ++i0) {
-          const double2 tt = lds2f(sT + (q0 * NB1 + i0) * 2);
-          a0 = fma(tt.x, h[i0], a0);
-          a1 = fma(tt.y, h[i0], a1);
-        }
-        sS1[((0 * Q + q0) * 4 + c) * C::S1C + i12] = a0;
-        sS1[((1 * Q + q0) * 4 + c) * C::S1C + i12] = a1;
-      }
-    }
-    __syncthreads();
-    for (int col = tid; col < 2 * Q * 4 * NB1; col += NT) {
-      int r = col;
-      const int i2 = r % NB1; r /= NB1;
-      const int c = r % 4; r /= 4;
-      const int q0 = r % Q;
-      const int a0 = r / Q;
-      double s[NB1];
-#pragma unroll
-      for (int i1 = 0; i1 < NB1; ++i1) s[i1] = sS1[((a0 * Q + q0) * 4 + c) * C::S1C + i1 + NB1 * i2];
-#pragma unroll
-      for (int q1 = 0; q1 < Q; ++q1) {
-        double v0 = 0.0, v1 = 0.0;
-#pragma unroll
-        for (int i1 = 0; i1 < NB1; ++i1) {
-          const double2 tt = lds2f(sT + C::TAB + (q1 * NB1 + i1) * 2);
-          v0 = fma(tt.x, s[i1], v0);
-          v1 = fma(tt.y, s[i1], v1);
-        }
-        const int q01 = q0 + Q * q1;
-        if (a0 == 0) {
-          sS2[((0 * 4 + c) * Q2 + q01) * C::S2S + i2] = v0;
-          sS2[((2 * 4 + c) * Q2 + q01) * C::S2S + i2] = v1;
-        } else {
-          sS2[((1 * 4 + c) * Q2 + q01) * C::S2S + i2] = v0;
-        }
-      }
-    }
-    __syncthreads();
-    for (int col = tid; col < 3 * 4 * Q2; col += NT) {
-      int r = col;
-      const int q01 = r % Q2; r /= Q2;
-      const int c = r % 4;
-      const int a01 = r / 4;
-      double s[NB1];
-#pragma unroll
-      for (int i2 = 0; i2 < NB1; ++i2) s[i2] = sS2[((a01 * 4 + c) * Q2 + q01) * C::S2S + i2];
-#pragma unroll
-      for (int q2 = 0; q2 < Q; ++q2) {
-        double v0 = 0.0, v1 = 0.0;
-#pragma unroll
-        for (int i2 = 0; i2 < NB1; ++i2) {
-          const double2 tt = lds2f(sT + 2 * C::TAB + (q2 * NB1 + i2) * 2);
-          v0 = fma(tt.x, s[i2], v0);
-          v1 = fma(tt.y, s[i2], v1);
-        }
-        const int pt = q01 + Q2 * q2;
-        if (a01 == 0) {
-          sG[(0 * 4 + c) * NQ + pt] = v0;
-          sG[(3 * 4 + c) * NQ + pt] = v1;
-        } else {
-          sG[(a01 * 4 + c) * NQ + pt] = v0;
-        }
-      }
-    }
-    __syncthreads();
-    // per point: x = C/W, J_d = (C_d - W_d x)/W, detJ, J^-T (cofactors / det), w detJ
-    for (int pt = tid; pt < NQ; pt += NT) {
-      const double W = sG[3 * NQ + pt], invW = 1.0 / W;
-      double x[3], J[3][3], Wd[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) x[c] = sG[c * NQ + pt] * invW;
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        Wd[d] = sG[((d + 1) * 4 + 3) * NQ + pt];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) J[d][c] = (sG[((d + 1) * 4 + c) * NQ + pt] - Wd[d] * x[c]) * invW;
-      }
-      const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2],
-                   c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
-      const double c10 = J[0][2] * J[2][1] - J[0][1] * J[2][2], c11 = J[0][0] * J[2][2] - J[0][2] * J[2][0],
-                   c12 = J[0][1] * J[2][0] - J[0][0] * J[2][1];
-      const double c20 = J[0][1] * J[1][2] - J[0][2] * J[1][1], c21 = J[0][2] * J[1][0] - J[0][0] * J[1][2],
-                   c22 = J[0][0] * J[1][1] - J[0][1] * J[1][0];
-      const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02, id = 1.0 / det;
-      int q = pt;
-      double w = w0[q % Q];
-      q /= Q;
-      w *= w1[q % Q];
-      w *= w2[q / Q];
-      double* o = sC + CS * pt;
-      o[0] = invW; o[1] = Wd[0]; o[2] = Wd[1]; o[3] = Wd[2];
-      // J^-T[c][d] = cof[d][c] / det
-      o[4] = c00 * id; o[5] = c10 * id; o[6] = c20 * id;
-      o[7] = c01 * id; o[8] = c11 * id; o[9] = c21 * id;
-      o[10] = c02 * id; o[11] = c12 * id; o[12] = c22 * id;
-      o[13] = w * fabs(det);
-    }
-    __syncthreads();
+    element_prepare<P, Q, NT>(Pd, e, tab0, tab1, tab2, w0, w1, w2, sT, sW, rA, sS2, sC);
 
     // ---- (3) chunked Gram contraction
     auto build = [&](int ch) {
@@ -321,6 +337,220 @@ __global__ void __launch_bounds__(FCfg<P, Q>::NT, 2) gram_fused_kernel(
   }
 }
 
+// ---- fused linear-elasticity element matrices (3-D, vector-valued basis, DOFs interleaved i*3 + a) ---------------------
+// K[(i,a),(j,b)] = sum_q w detJ sum_{r,t} B[r][(i,a)] D[r][t] B[t][(j,b)] with the Voigt strain operator B.  Every column
+// of B is a selection of the physical gradient G_c[i], so
+//     K[(i,a),(j,b)] = sum_{c,c'} Cf[a][c][b][c'] M^{cc'}[i][j],   M^{cc'}[i][j] = sum_q w detJ G_c[q][i] G_c'[q][j],
+// with Cf = S^T D S folded on the host (81 numbers).  The nine Gram blocks M^{cc'} are what the tensor cores contract:
+// 9 x 2 n_b^2 n_q flops instead of the 2 (6 n_q)(3 n_b)^2 of the dense B^T D B -- six times less work for the same K_e.
+// One block (9 warps) per element; for every upper 32x32 block pair (bi <= bj) of the (i,j) plane warp (c,c') owns
+// M^{cc'}; the gradients of 16 points at a time are built in shared memory from the tables; the nine blocks are then
+// combined with Cf through shared memory and written as contiguous rows, the mirror block with the transposed
+// coefficients (no symmetry of D is assumed).
+struct ElasCoef {
+  double cf[81];  // [a][c][b][c']
+};
+
+template <int P, int Q>
+struct ECfg {
+  using F = FCfg<P, Q>;
+  static constexpr int NT = 9 * 32;
+  static constexpr int KC = 16, LD = F::NBP + 4;
+  static constexpr int SZ_GS = 3 * KC * LD;
+  static constexpr int MS = 33;                 // row stride of a staged 32x32 block
+  static constexpr int SZ_M = 9 * 32 * MS;
+  static constexpr int SZ_R2 = (F::SZ_A + F::SZ_S2 + SZ_GS) > SZ_M ? (F::SZ_A + F::SZ_S2 + SZ_GS) : SZ_M;
+  static constexpr int SZ_TOTAL = F::SZ_T + F::SZ_W + F::SZ_C + SZ_R2;
+};
+
+template <int P, int Q>
+__global__ void __launch_bounds__(ECfg<P, Q>::NT, 2) elasticity_fused_kernel(
+    PatchDev Pd, long long elem_begin, long long nelem, const double* __restrict__ tab0,
+    const double* __restrict__ tab1, const double* __restrict__ tab2, const double* __restrict__ w0,
+    const double* __restrict__ w1, const double* __restrict__ w2, ElasCoef coef, double fconst,
+    double* __restrict__ Ke, double* __restrict__ fe) {
+  using C = FCfg<P, Q>;
+  using E = ECfg<P, Q>;
+  constexpr int NB1 = C::NB1, NB = C::NB, NQ = C::NQ, Q2 = C::Q2, NBP = C::NBP, CS = C::CS;
+  constexpr int NT = E::NT, KC = E::KC, LD = E::LD, MS = E::MS, NBLK = C::NBLK;
+  constexpr int nchunk = (NQ + KC - 1) / KC;
+  constexpr int N3 = 3 * NB;
+  extern __shared__ __align__(16) double esm[];
+  double* const sT = esm;
+  double* const sW = sT + C::SZ_T;
+  double* const sC = sW + C::SZ_W;
+  double* const rA = sC + C::SZ_C;
+  double* const sS2 = rA + C::SZ_A;
+  double* const sGs = sS2 + C::SZ_S2;  // [3][KC][LD]
+  double* const sM = rA;               // [9][32][MS], after the contraction of a block pair
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wc = warp / 3, wcp = warp % 3;  // this warp's (c, c')
+  for (int idx = tid; idx < C::SZ_W; idx += NT) sW[idx] = 0.0;
+
+  for (long long el = blockIdx.x; el < nelem; el += gridDim.x) {
+    const long long e = elem_begin + el;
+    element_prepare<P, Q, NT>(Pd, e, tab0, tab1, tab2, w0, w1, w2, sT, sW, rA, sS2, sC);
+    double* K = Ke + el * (long long)N3 * N3;
+    for (int bi = 0; bi < NBLK; ++bi)
+      for (int bj = bi; bj < NBLK; ++bj) {
+        double acc[4][4][2];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+        const int ncolblk = (bi == bj) ? 1 : 2;
+#pragma unroll 1
+        for (int ch = 0; ch < nchunk; ++ch) {
+          __syncthreads();  // previous chunk (or the previous block pair's staging) fully consumed
+          // gradients of 16 points for the columns of blocks bi and bj
+          for (int item = tid; item < KC * 32 * ncolblk; item += NT) {
+            const int ql = item / (32 * ncolblk), r = item % (32 * ncolblk);
+            const int i = (r < 32 ? bi * 32 : bj * 32 - 32) + r;
+            const int pt = ch * KC + ql;
+            double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+            if (pt < NQ && i < NB) {
+              const int i0 = i % NB1, i1 = (i / NB1) % NB1, i2 = i / (NB1 * NB1);
+              const int q0 = pt % Q, q1 = (pt / Q) % Q, q2 = pt / Q2;
+              const double2 a = lds2f(sT + (q0 * NB1 + i0) * 2), b = lds2f(sT + C::TAB + (q1 * NB1 + i1) * 2),
+                            c = lds2f(sT + 2 * C::TAB + (q2 * NB1 + i2) * 2);
+              const double* k = sC + CS * pt;
+              const double w = sW[i], invW = k[0];
+              const double t00 = a.x * b.x, wn2 = w * c.x;
+              const double R = t00 * wn2 * invW;
+              const double d0 = (a.y * b.x * wn2 - k[1] * R) * invW;
+              const double d1 = (a.x * b.y * wn2 - k[2] * R) * invW;
+              const double d2 = (t00 * (w * c.y) - k[3] * R) * invW;
+              r0 = k[4] * d0 + k[5] * d1 + k[6] * d2;
+              r1 = k[7] * d0 + k[8] * d1 + k[9] * d2;
+              r2 = k[10] * d0 + k[11] * d1 + k[12] * d2;
+            }
+            sGs[(0 * KC + ql) * LD + i] = r0;
+            sGs[(1 * KC + ql) * LD + i] = r1;
+            sGs[(2 * KC + ql) * LD + i] = r2;
+          }
+          __syncthreads();
+          const double* Ga = sGs + wc * KC * LD;
+          const double* Gb = sGs + wcp * KC * LD;
+#pragma unroll
+          for (int ks = 0; ks < KC; ks += 4) {
+            const int k = ks + t, pt = ch * KC + k;
+            const double sc = pt < NQ ? sC[CS * pt + 13] : 0.0;
+            double af[4], bf[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) af[a] = Ga[k * LD + bi * 32 + 8 * a + g];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bf[b] = Gb[k * LD + bj * 32 + 8 * b + g] * sc;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int b = 0; b < 4; ++b) dmma8x8x4_f(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+          }
+        }
+        __syncthreads();  // all warps done reading the chunk buffer; it is reused as staging
+        {
+          double* M = sM + warp * 32 * MS;  // block (c, c')
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              M[(8 * a + g) * MS + 8 * b + 2 * t] = acc[a][b][0];
+              M[(8 * a + g) * MS + 8 * b + 2 * t + 1] = acc[a][b][1];
+            }
+        }
+        __syncthreads();
+        // combine: direct block rows (i,a), columns (j,b); lanes over j -> contiguous 3-double groups per row
+        for (int item = tid; item < 32 * 32; item += NT) {
+          const int il = item / 32, jl = item % 32;
+          const int i = bi * 32 + il, j = bj * 32 + jl;
+          if (i < NB && j < NB) {
+            double m[9];
+#pragma unroll
+            for (int pr = 0; pr < 9; ++pr) m[pr] = sM[(pr * 32 + il) * MS + jl];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+              for (int b = 0; b < 3; ++b) {
+                double v = 0.0;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                  for (int cp = 0; cp < 3; ++cp) v = fma(coef.cf[((a * 3 + c) * 3 + b) * 3 + cp], m[c * 3 + cp], v);
+                K[(long long)(3 * i + a) * N3 + 3 * j + b] = v;
+              }
+          }
+        }
+        if (bi != bj) {
+          // mirror block: K[(j,b),(i,a)] = sum Cf[b][c'][a][c] M^{cc'}[i][j]; lanes over i -> contiguous rows
+          for (int item = tid; item < 32 * 32; item += NT) {
+            const int jl = item / 32, il = item % 32;
+            const int i = bi * 32 + il, j = bj * 32 + jl;
+            if (i < NB && j < NB) {
+              double m[9];
+#pragma unroll
+              for (int pr = 0; pr < 9; ++pr) m[pr] = sM[(pr * 32 + il) * MS + jl];
+#pragma unroll
+              for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                  double v = 0.0;
+#pragma unroll
+                  for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int cp = 0; cp < 3; ++cp) v = fma(coef.cf[((b * 3 + cp) * 3 + a) * 3 + c], m[c * 3 + cp], v);
+                  K[(long long)(3 * j + b) * N3 + 3 * i + a] = v;
+                }
+            }
+          }
+        }
+      }
+    if (fe) {
+      for (int i = tid; i < NB; i += NT) {
+        const int i0 = i % NB1, i1 = (i / NB1) % NB1, i2 = i / (NB1 * NB1);
+        const double w = sW[i];
+        double s = 0.0;
+        for (int pt = 0; pt < NQ; ++pt) {
+          const int q0 = pt % Q, q1 = (pt / Q) % Q, q2 = pt / Q2;
+          const double R = sT[(q0 * NB1 + i0) * 2] * sT[C::TAB + (q1 * NB1 + i1) * 2] *
+                           (w * sT[2 * C::TAB + (q2 * NB1 + i2) * 2]) * sC[CS * pt];
+          s += sC[CS * pt + 13] * R * fconst;
+        }
+        fe[el * N3 + 3 * i] = fe[el * N3 + 3 * i + 1] = fe[el * N3 + 3 * i + 2] = s;
+      }
+    }
+  }
+}
+
+template <int P, int Q>
+igab_status launch_elas(const PatchDev& Pd, SfWorkspace& ws, const double* D_host, double fconst, long long eb,
+                        long long nel, const double* const* w_dev, double* Ke, double* fe, cudaStream_t stream) {
+  using E = ECfg<P, Q>;
+  // Cf[a][c][b][c'] = sum_{r,t} S[r][a][c] D[r][t] S[t][b][c'], S = Voigt selector (xx,yy,zz,yz,xz,xy; engineering shear)
+  static const int S[9][3] = {{0, 0, 0}, {1, 1, 1}, {2, 2, 2}, {3, 1, 2}, {3, 2, 1}, {4, 0, 2}, {4, 2, 0}, {5, 0, 1}, {5, 1, 0}};
+  ElasCoef coef;
+  for (double& v : coef.cf) v = 0.0;
+  for (auto& s1 : S)
+    for (auto& s2 : S) coef.cf[((s1[1] * 3 + s1[2]) * 3 + s2[1]) * 3 + s2[2]] += D_host[s1[0] * 6 + s2[0]];
+  const size_t smem = (size_t)E::SZ_TOTAL * sizeof(double);
+  static bool configured = false;
+  static int sms = 148, bps = 1;
+  if (!configured) {
+    IGAB_CUDA_TRY(cudaFuncSetAttribute(elasticity_fused_kernel<P, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0;
+    IGAB_CUDA_TRY(cudaGetDevice(&dev));
+    IGAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    IGAB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, elasticity_fused_kernel<P, Q>, E::NT, smem));
+    if (bps < 1) bps = 1;
+    configured = true;
+  }
+  const unsigned grid = (unsigned)std::min<long long>(nel, (long long)bps * sms);
+  elasticity_fused_kernel<P, Q><<<grid, E::NT, smem, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],
+                                                               w_dev[1], w_dev[2], coef, fconst, Ke, fe);
+  count_launch();
+  IGAB_CUDA_TRY(cudaGetLastError());
+  return IGAB_OK;
+}
+
 template <int P, int Q>
 igab_status launch_pq(const PatchDev& Pd, SfWorkspace& ws, bool mass, double fconst, long long eb, long long nel,
                       const double* const* w_dev, double* Ke, double* fe, cudaStream_t stream) {
@@ -353,7 +583,7 @@ igab_status launch_pq(const PatchDev& Pd, SfWorkspace& ws, bool mass, double fco
 }  // namespace
 
 bool gram_fused_supported(const PatchDev& P, int kind, const int* nq1) {
-  if (P.dim != 3 || P.dw != 3 || kind == IGAB_ASM_ELASTICITY) return false;
+  if (P.dim != 3 || P.dw != 3) return false;
   if (P.degree[0] != P.degree[1] || P.degree[0] != P.degree[2]) return false;
   if (nq1[0] != nq1[1] || nq1[0] != nq1[2]) return false;
   return (P.degree[0] == 3 && nq1[0] == 4) || (P.degree[0] == 4 && nq1[0] == 5);
@@ -361,13 +591,22 @@ bool gram_fused_supported(const PatchDev& P, int kind, const int* nq1) {
 
 igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host,
                               const double* const* xi1d_dev, const double* const* w1d_dev, int kind, double fconst,
-                              long long eb, long long nel, const int* nq1, double* Ke, double* fe, cudaStream_t stream) {
+                              long long eb, long long nel, const int* nq1, double* Ke, double* fe, cudaStream_t stream,
+                              const double* D_host) {
   if (!gram_fused_supported(P, kind, nq1)) {
     set_error("assemble: no fused kernel for this configuration");
     return IGAB_UNSUPPORTED;
   }
   igab_status st = ensure_tables3d(P, ws, nq1[0], xi1d_dev, xi1d_host, stream);
   if (st) return st;
+  if (kind == IGAB_ASM_ELASTICITY) {
+    if (!D_host) {
+      set_error("assemble: elasticity needs the 6x6 D matrix");
+      return IGAB_INVALID_ARGUMENT;
+    }
+    if (P.degree[0] == 3) return launch_elas<3, 4>(P, ws, D_host, fconst, eb, nel, w1d_dev, Ke, fe, stream);
+    return launch_elas<4, 5>(P, ws, D_host, fconst, eb, nel, w1d_dev, Ke, fe, stream);
+  }
   const bool mass = kind == IGAB_ASM_MASS;
   if (P.degree[0] == 3) return launch_pq<3, 4>(P, ws, mass, fconst, eb, nel, w1d_dev, Ke, fe, stream);
   return launch_pq<4, 5>(P, ws, mass, fconst, eb, nel, w1d_dev, Ke, fe, stream);

@@ -701,7 +701,7 @@ igab_status igab_assemble(igab_patch* p, int kind, const double* D, double fcons
     }
   }
   if (out_space == IGAB_DEVICE) {
-    st = launch_assemble(p->dev, p->sf, xi1d, kind, d_D, fconst, elem_begin, nel, nq1, rule.xi, rule.w, Ke, fe, stream);
+    st = launch_assemble(p->dev, p->sf, xi1d, kind, D, d_D, fconst, elem_begin, nel, nq1, rule.xi, rule.w, Ke, fe, stream);
     if (d_D) {
       cudaStreamSynchronize(stream);
       cudaFree(d_D);
@@ -717,7 +717,7 @@ igab_status igab_assemble(igab_patch* p, int kind, const double* D, double fcons
   if (e != cudaSuccess) st = cuda_fail(e, "assemble staging");
   for (long long c0 = 0; c0 < nel && !st; c0 += elChunk) {
     const long long m = std::min(elChunk, nel - c0);
-    st = launch_assemble(p->dev, p->sf, xi1d, kind, d_D, fconst, elem_begin + c0, m, nq1, rule.xi, rule.w, dK, dF, stream);
+    st = launch_assemble(p->dev, p->sf, xi1d, kind, D, d_D, fconst, elem_begin + c0, m, nq1, rule.xi, rule.w, dK, dF, stream);
     if (st) break;
     e = cudaMemcpyAsync(Ke + (long long)n * n * c0, dK, keBytes * m, cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess && fe) e = cudaMemcpyAsync(fe + (long long)n * c0, dF, 8LL * n * m, cudaMemcpyDeviceToHost, stream);

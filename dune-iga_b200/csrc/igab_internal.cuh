@@ -81,7 +81,8 @@ igab_status ensure_tables3d(const PatchDev& Pd, SfWorkspace& ws, int Q, const do
 bool gram_fused_supported(const PatchDev& P, int kind, const int* nq1);
 igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host,
                               const double* const* xi1d_dev, const double* const* w1d_dev, int kind, double fconst,
-                              long long eb, long long nel, const int* nq1, double* Ke, double* fe, cudaStream_t stream);
+                              long long eb, long long nel, const int* nq1, double* Ke, double* fe, cudaStream_t stream,
+                              const double* D_host);
 bool eval_tensor_sf_supported(const PatchDev& P, const int* nq1, int order, const EvalOutDev& out);
 // 2-D point lists (trimmed batches): per-point univariate rows in registers
 bool eval_points_2d_supported(const PatchDev& P);
@@ -98,7 +99,7 @@ igab_status launch_spans(const PatchDev& P, int32_t* span, cudaStream_t stream);
 igab_status launch_dofmap(const PatchDev& P, int32_t* dof, cudaStream_t stream);
 igab_status launch_dof_compact(const PatchDev& P, const uint8_t* trim_dev, int32_t* dof, int32_t* scratch_used,
                                int32_t* scratch_map, long long ndof, long long* ndof_out_host, cudaStream_t stream);
-igab_status launch_assemble(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, int kind, const double* D_dev, double fconst, long long elem_begin,
+igab_status launch_assemble(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, int kind, const double* D_host, const double* D_dev, double fconst, long long elem_begin,
                             long long nelem, const int* nq1, const double* const* xi1d_dev,
                             const double* const* w1d_dev, double* Ke, double* fe, cudaStream_t stream);
 igab_status launch_volume(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, long long elem_begin, long long nelem, const int* nq1,

@@ -99,7 +99,7 @@ def main():
             rule = [PD.gaussLegendre01(5)] * 3
             xi, w = [r[0] for r in rule], [r[1] for r in rule]
             n = P.nb * (3 if kind == capi.ASM_ELASTICITY else 1)
-            nel = 4096 if kind == capi.ASM_POISSON else 512
+            nel = 4736 if kind == capi.ASM_POISSON else 2368  # multiples of 2 x 148 resident blocks
             Ke = torch.empty((nel, n, n), dtype=torch.float64, device="cuda")
             D = None
             if kind == capi.ASM_ELASTICITY:
