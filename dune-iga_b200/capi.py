@@ -23,7 +23,7 @@ EXPORTS = ("igab_last_error_string", "igab_version", "igab_launch_count", "igab_
            "igab_patch_create", "igab_patch_destroy", "igab_patch_sizes", "igab_patch_set_kernel",
            "igab_patch_update_control_points", "igab_patch_spans", "igab_patch_dofmap", "igab_eval_tensor",
            "igab_eval_points", "igab_partial", "igab_assemble", "igab_reduce_volume", "igab_csr_pattern",
-           "igab_csr_assemble")
+           "igab_csr_assemble", "igab_eval_faces")
 
 
 class EvalOut(C.Structure):
@@ -68,6 +68,8 @@ def lib():
                                        C.c_void_p, C.c_int, C.c_void_p]
         L.igab_csr_assemble.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_int, C.c_int, C.c_void_p]
+        L.igab_eval_faces.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, ip, C.POINTER(dp), C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.igab_reduce_volume.argtypes = [C.c_void_p, C.c_int64, C.c_int64, ip, C.POINTER(dp), C.POINTER(dp),
                                          C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
         _lib = L
@@ -270,6 +272,21 @@ class Patch:
         _check(lib().igab_assemble(self.h, kind, Dm.ctypes.data_as(dp) if Dm is not None else None, fconst,
                                    elem_begin, elem_end, nq1.ctypes.data_as(ip), xp, wp, ka, fa, ks, stream))
         return Ke, fe
+
+    # ---- faces
+    def evalFaces(self, elem, face, xi1d):
+        """Position, UNIT outer normal and integration element at the face rule xi1d (dim-1 arrays) of faces
+        face[k] = 2*d+s of elements elem[k]  (nurbsintersection.hh:86-160)."""
+        elem, face = _i32(elem), _i32(face)
+        arrs, ptrs = _rule_arrays(xi1d)
+        nqf1 = _i32([len(a) for a in arrs])
+        npts = len(elem) * int(np.prod(nqf1))
+        x = np.empty((npts, self.dimworld))
+        nrm = np.empty((npts, self.dimworld))
+        dS = np.empty(npts)
+        _check(lib().igab_eval_faces(self.h, len(elem), elem.ctypes.data, face.ctypes.data, nqf1.ctypes.data_as(ip),
+                                     ptrs, x.ctypes.data, nrm.ctypes.data, dS.ctypes.data, HOST, None))
+        return dict(x=x, normal=nrm, dS=dS)
 
     # ---- global sparse matrix
     def csrPattern(self, ncomp=1):

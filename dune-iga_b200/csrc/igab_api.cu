@@ -731,6 +731,67 @@ igab_status igab_assemble(igab_patch* p, int kind, const double* D, double fcons
   return st;
 }
 
+// ---- faces -----------------------------------------------------------------------------------------------------------
+igab_status igab_eval_faces(igab_patch* p, int64_t nfaces, const int32_t* elem, const int32_t* face, const int* nqf1,
+                            const double* const* xi1d, double* x, double* normal, double* dS, igab_memspace space,
+                            void* stream_) {
+  if (!p || nfaces < 0 || !nqf1 || !xi1d || (nfaces > 0 && (!elem || !face))) {
+    set_error("eval_faces: null argument");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int dim = p->dev.dim, dw = p->dev.dw;
+  if (dim < 2) {
+    set_error("eval_faces: needs a 2-D or 3-D patch");
+    return IGAB_UNSUPPORTED;
+  }
+  // the face rule is staged like an element rule (unused last direction padded with one point)
+  int nq1[kMaxDim] = {1, 1, 1};
+  const double one = 0.0;
+  const double* xs[kMaxDim] = {&one, &one, &one};
+  for (int d = 0; d < dim - 1; ++d) {
+    nq1[d] = nqf1[d];
+    xs[d] = xi1d[d];
+  }
+  RuleDev rule;
+  igab_status st = stage_rule(p, nq1, xs, nullptr, &rule, stream);
+  if (st) return st;
+  if (nfaces == 0) return IGAB_OK;
+  const int nqf = nq1[0] * (dim == 3 ? nq1[1] : 1);
+  const long long npts = nfaces * nqf;
+  if (space == IGAB_DEVICE) return eval_faces_device(p, nfaces, elem, face, nq1, rule.xi, x, normal, dS, stream);
+  for (long long k = 0; k < nfaces; ++k)
+    if (elem[k] < 0 || elem[k] >= p->dev.nelem || face[k] < 0 || face[k] >= 2 * dim) {
+      set_error("eval_faces: element or face index out of range");
+      return IGAB_INVALID_ARGUMENT;
+    }
+  int *d_el = nullptr, *d_fc = nullptr;
+  double *d_x = nullptr, *d_n = nullptr, *d_s = nullptr;
+  cudaError_t e = cudaMalloc(&d_el, sizeof(int) * nfaces);
+  if (e == cudaSuccess) e = cudaMalloc(&d_fc, sizeof(int) * nfaces);
+  if (e == cudaSuccess && x) e = cudaMalloc(&d_x, sizeof(double) * npts * dw);
+  if (e == cudaSuccess && normal) e = cudaMalloc(&d_n, sizeof(double) * npts * dw);
+  if (e == cudaSuccess && dS) e = cudaMalloc(&d_s, sizeof(double) * npts);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_el, elem, sizeof(int) * nfaces, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_fc, face, sizeof(int) * nfaces, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) st = cuda_fail(e, "eval_faces staging");
+  if (!st) st = eval_faces_device(p, nfaces, d_el, d_fc, nq1, rule.xi, d_x, d_n, d_s, stream);
+  if (!st) {
+    if (x) e = cudaMemcpyAsync(x, d_x, sizeof(double) * npts * dw, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && normal) e = cudaMemcpyAsync(normal, d_n, sizeof(double) * npts * dw, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && dS) e = cudaMemcpyAsync(dS, d_s, sizeof(double) * npts, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) st = cuda_fail(e, "eval_faces D2H");
+  }
+  cudaStreamSynchronize(stream);
+  if (d_el) cudaFree(d_el);
+  if (d_fc) cudaFree(d_fc);
+  if (d_x) cudaFree(d_x);
+  if (d_n) cudaFree(d_n);
+  if (d_s) cudaFree(d_s);
+  return st;
+}
+
 // ---- global CSR -----------------------------------------------------------------------------------------------------
 igab_status igab_csr_pattern(igab_patch* p, int ncomp, int64_t* nrows, int64_t* nnz, int64_t* rowptr, int32_t* colidx,
                              igab_memspace space, void* stream) {

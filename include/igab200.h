@@ -146,6 +146,17 @@ igab_status igab_assemble(igab_patch* p, int kind, const double* D, double fcons
                           int64_t elem_end, const int* nq1, const double* const* xi1d, const double* const* w1d,
                           double* Ke, double* fe, igab_memspace out_space, void* stream);
 
+/* ---- element faces (boundary / intersection integrals) -----------------------------------------------------------------
+ * Replaces, for nfaces faces x the tensor rule of dimension dim-1: NURBSintersection::geometry().global /
+ * integrationElement and outerNormal / unitOuterNormal / integrationOuterNormal (dune/iga/nurbsintersection.hh:86-160;
+ * sub-entity geometry nurbsgeometry.hh:294-303).  face[k] = 2*d + s (DUNE cube numbering: xi_d fixed to s) of element
+ * elem[k]; the rule's coordinates fill the free directions in increasing order, first one fastest.
+ * Outputs per point (nullable): x [pt][dimworld], normal [pt][dimworld] = UNIT outer normal, dS [pt] = integration
+ * element of the face; integrationOuterNormal = normal * dS.  dim 2 or 3.  elem / face / outputs live in `space`. */
+igab_status igab_eval_faces(igab_patch* p, int64_t nfaces, const int32_t* elem, const int32_t* face, const int* nqf1,
+                            const double* const* xi1d, double* x, double* normal, double* dS, igab_memspace space,
+                            void* stream);
+
 /* ---- global sparse matrix (CSR) ---------------------------------------------------------------------------------------
  * Replaces the scatter loop of globalAssembler, dune/python/test/poisson.py:113-125 (A[gi,gj] += localA[i,j] through
  * localView.index), for the tensor-product DOF numbering of NurbsPreBasis (nurbsbasis.hh:572-584): row g couples

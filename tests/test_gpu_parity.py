@@ -380,3 +380,97 @@ def test_global_csr_matches_scatter_of_oracle(name, kind):
     v2 = P.csrAssemble(K[half:], ncomp, half, P.nelem, values=v2, accumulate=True)
     assert np.abs(v2 - vals).max() <= 1e-13 * np.abs(vals).max()
     assert np.array_equal(P.csrAssemble(K, ncomp), vals)
+
+
+def _faces_reference(O, dim, dw, elem, face, xif):
+    """numpy restatement of NURBSintersection::outerNormal / unitOuterNormal and the face integration element
+    (dune/iga/nurbsintersection.hh:86-160) on top of the ORACLE's x and J^T at the face points."""
+    nqf = xif.shape[0]
+    el = np.repeat(elem, nqf)
+    fc = np.repeat(face, nqf)
+    xi = np.zeros((len(el), dim))
+    for k in range(len(el)):
+        fd, side = fc[k] >> 1, fc[k] & 1
+        free = [d for d in range(dim) if d != fd]
+        xi[k, fd] = side
+        for m, d in enumerate(free):
+            xi[k, d] = xif[k % nqf, m]
+    o = O.eval_points(el, xi, order=1, want=("x", "Jt"))
+    J = o["Jt"]
+    n = np.zeros((len(el), dw))
+    ds = np.zeros(len(el))
+    for k in range(len(el)):
+        fi, fd = fc[k], fc[k] >> 1
+        if dim == 2 and dw == 2:
+            T = J[k, 1 - fd]
+            n[k] = (-T[1], T[0]) if fi in (0, 3) else (T[1], -T[0])
+            ds[k] = np.linalg.norm(T)
+        elif dim == 2:
+            N = np.cross(J[k, 0], J[k, 1])
+            n[k] = {0: np.cross(N, J[k, 1]), 1: np.cross(J[k, 1], N), 2: np.cross(J[k, 0], N), 3: np.cross(N, J[k, 0])}[fi]
+            ds[k] = np.linalg.norm(J[k, 1 - fd])
+        else:
+            free = [d for d in range(3) if d != fd]
+            T0, T1 = J[k, free[0]], J[k, free[1]]
+            n[k] = np.cross(T1, T0) if fi in (0, 3, 4) else np.cross(T0, T1)
+            ds[k] = np.linalg.norm(np.cross(T0, T1))
+    n /= np.linalg.norm(n, axis=1)[:, None]
+    return o["x"], n, ds
+
+
+@pytest.mark.parametrize("name", ["plate_hole_p2", "torus_p2", "cylinder_p3", "mixed_deg_3d"])
+def test_faces_match_reference_formulas(name):
+    spec = PFT.small_patch(name)
+    O, _ = oracle_for(spec)
+    P = gpu_patch(spec)
+    dim, dw = P.dim, P.dimworld
+    rng = np.random.default_rng(11)
+    nf = 40
+    elem = rng.integers(0, P.nelem, nf).astype(np.int32)
+    face = rng.integers(0, 2 * dim, nf).astype(np.int32)
+    x1 = PD.gaussLegendre01(3)[0]
+    if dim == 2:
+        xif = x1.reshape(-1, 1)
+        rule = [x1]
+    else:
+        xif = np.array([[x1[q % 3], x1[q // 3]] for q in range(9)])
+        rule = [x1, x1]
+    got = P.evalFaces(elem, face, rule)
+    xr, nr, dsr = _faces_reference(O, dim, dw, elem, face, xif)
+    assert relerr(got["x"], xr) <= TOL
+    assert np.abs(got["normal"] - nr).max() <= 1e-12
+    assert relerr(got["dS"].reshape(-1, 1), dsr.reshape(-1, 1)) <= TOL
+
+
+def test_cylinder_boundary_normals_and_divergence_theorem():
+    """Thick quarter cylinder: radial normals on the curved faces, +-e_z on the end caps, area of the outer face, and
+    sum over the boundary of x.n dS = 3 * volume."""
+    pd = PD.thickCylinder(3, (2, 2, 2))  # 4 x 4 x 4 elements
+    P = capi.Patch.fromPatchData(pd)
+    n = 4
+    x1, w1 = PD.gaussLegendre01(4)
+    ww = np.outer(w1, w1).reshape(-1)  # first free direction fastest
+    total = 0.0
+    # the reference's cross-product formulas (nurbsintersection.hh:139-152) give the OUTER normal for a positively
+    # oriented parametrisation; (angle, radius, axis) is left-handed, so every normal comes out flipped: orient = -1
+    orient = np.sign(np.linalg.det(P.evalPoints([0], [[.5, .5, .5]], order=1, want=("Jt",))["Jt"][0]))
+    assert orient == -1.0
+    for d in range(3):
+        for s in (0, 1):
+            idx = [np.arange(n)] * 3
+            idx[d] = np.array([0 if s == 0 else n - 1])
+            e0, e1, e2 = np.meshgrid(idx[0], idx[1], idx[2], indexing="ij")
+            elem = (e0 + n * (e1 + n * e2)).reshape(-1).astype(np.int32)
+            face = np.full(len(elem), 2 * d + s, np.int32)
+            o = P.evalFaces(elem, face, [x1, x1])
+            w = np.tile(ww, len(elem))
+            total += orient * ((o["x"] * o["normal"]).sum(1) * o["dS"] * w).sum()
+            r = np.hypot(o["x"][:, 0], o["x"][:, 1])
+            if d == 1:  # radial direction: inner (s=0) and outer (s=1) curved faces
+                radial = np.stack([o["x"][:, 0] / r, o["x"][:, 1] / r, 0 * r], 1)
+                assert np.abs(orient * o["normal"] - (radial if s == 1 else -radial)).max() < 1e-12
+                assert abs((o["dS"] * w).sum() - np.pi / 2 * (2.0 if s == 1 else 1.0) * 3.0) < 1e-10
+            if d == 2:
+                assert np.abs(orient * o["normal"] - np.array([0, 0, 1.0 if s == 1 else -1.0])).max() < 1e-12
+    vol = np.pi / 4 * 3.0 * 3.0
+    assert abs(total - 3 * vol) < 1e-9
