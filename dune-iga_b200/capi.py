@@ -23,7 +23,7 @@ EXPORTS = ("igab_last_error_string", "igab_version", "igab_launch_count", "igab_
            "igab_patch_create", "igab_patch_destroy", "igab_patch_sizes", "igab_patch_set_kernel",
            "igab_patch_update_control_points", "igab_patch_spans", "igab_patch_dofmap", "igab_eval_tensor",
            "igab_eval_points", "igab_partial", "igab_assemble", "igab_reduce_volume", "igab_csr_pattern",
-           "igab_csr_assemble", "igab_eval_faces")
+           "igab_csr_assemble", "igab_eval_faces", "igab_refine_apply")
 
 
 class EvalOut(C.Structure):
@@ -70,6 +70,8 @@ def lib():
                                         C.c_int, C.c_int, C.c_void_p]
         L.igab_eval_faces.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, ip, C.POINTER(dp), C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.igab_refine_apply.argtypes = [C.c_int, C.c_int, ip, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, dp, dp,
+                                        dp]
         L.igab_reduce_volume.argtypes = [C.c_void_p, C.c_int64, C.c_int64, ip, C.POINTER(dp), C.POINTER(dp),
                                          C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
         _lib = L
@@ -110,6 +112,41 @@ def _rule_arrays(rule1d):
     arrs = [_f64(x) for x in rule1d]
     ptrs = (dp * len(arrs))(*[a.ctypes.data_as(dp) for a in arrs])
     return arrs, ptrs
+
+
+def banded(T, tol=0.0):
+    """Row-banded form (first, len, coef[n_new, maxlen]) of a dense 1-D refinement operator T."""
+    T = np.asarray(T, float)
+    nz = np.abs(T) > tol
+    first = np.argmax(nz, axis=1).astype(np.int32)
+    last = (T.shape[1] - 1 - np.argmax(nz[:, ::-1], axis=1)).astype(np.int32)
+    ln = (last - first + 1).astype(np.int32)
+    maxlen = int(ln.max())
+    coef = np.zeros((T.shape[0], maxlen))
+    for i in range(T.shape[0]):
+        coef[i, :ln[i]] = T[i, first[i]:first[i] + ln[i]]
+    return first, ln, coef
+
+
+def refineApply(pd, direction, T, newKnots, newDegree=None):
+    """GPU version of patchdata._apply_along: apply the 1-D operator T to the control net of `pd` along `direction`
+    (knotRefinement / degreeElevate, nurbsalgorithms.hh:264-528) and return the new NurbsPatchData."""
+    from .patchdata import NurbsPatchData
+    first, ln, coef = banded(T)
+    ncp = _i32(pd.ncp)
+    cp_in = _f64(pd.cp)
+    ncp_new = list(pd.ncp)
+    ncp_new[direction] = T.shape[0]
+    cp_out = np.empty((int(np.prod(ncp_new)), pd.dimworld + 1))
+    _check(lib().igab_refine_apply(pd.patchDim, pd.dimworld, ncp.ctypes.data_as(ip), direction, T.shape[0],
+                                   coef.shape[1], first.ctypes.data, ln.ctypes.data, coef.ctypes.data_as(dp),
+                                   cp_in.ctypes.data_as(dp), cp_out.ctypes.data_as(dp)))
+    knots = [k.copy() for k in pd.knotSpans]
+    knots[direction] = np.asarray(newKnots, float)
+    deg = list(pd.degree)
+    if newDegree is not None:
+        deg[direction] = newDegree
+    return NurbsPatchData(knots, cp_out, deg, pd.dimworld)
 
 
 def pinned_empty(shape, dtype=np.float64):

@@ -731,6 +731,52 @@ igab_status igab_assemble(igab_patch* p, int kind, const double* D, double fcons
   return st;
 }
 
+// ---- refinement -------------------------------------------------------------------------------------------------------
+igab_status igab_refine_apply(int dim, int dimworld, const int* ncp_old, int direction, int n_new, int maxlen,
+                              const int32_t* first, const int32_t* len, const double* coef, const double* cp_in,
+                              double* cp_out) {
+  if (dim < 1 || dim > kMaxDim || dimworld < 1 || dimworld > 3 || !ncp_old || direction < 0 || direction >= dim ||
+      n_new < 1 || maxlen < 1 || !first || !len || !coef || !cp_in || !cp_out) {
+    set_error("refine_apply: invalid argument");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  long long nin = 1, nout = 1;
+  for (int d = 0; d < dim; ++d) {
+    nin *= ncp_old[d];
+    nout *= (d == direction) ? n_new : ncp_old[d];
+  }
+  for (int i = 0; i < n_new; ++i)
+    if (len[i] < 0 || len[i] > maxlen || first[i] < 0 || first[i] + len[i] > ncp_old[direction]) {
+      set_error("refine_apply: operator row outside the old net");
+      return IGAB_INVALID_ARGUMENT;
+    }
+  int *d_first = nullptr, *d_len = nullptr;
+  double *d_coef = nullptr, *d_in = nullptr, *d_out = nullptr;
+  const size_t row = sizeof(double) * (dimworld + 1);
+  igab_status st = IGAB_OK;
+  cudaError_t e = cudaMalloc(&d_first, sizeof(int) * n_new);
+  if (e == cudaSuccess) e = cudaMalloc(&d_len, sizeof(int) * n_new);
+  if (e == cudaSuccess) e = cudaMalloc(&d_coef, sizeof(double) * n_new * maxlen);
+  if (e == cudaSuccess) e = cudaMalloc(&d_in, row * nin);
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, row * nout);
+  if (e == cudaSuccess) e = cudaMemcpy(d_first, first, sizeof(int) * n_new, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_len, len, sizeof(int) * n_new, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_coef, coef, sizeof(double) * n_new * maxlen, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_in, cp_in, row * nin, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) st = cuda_fail(e, "refine_apply staging");
+  if (!st) st = refine_apply(dim, dimworld, ncp_old, direction, n_new, maxlen, d_first, d_len, d_coef, d_in, d_out, nullptr);
+  if (!st) {
+    e = cudaMemcpy(cp_out, d_out, row * nout, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) st = cuda_fail(e, "refine_apply D2H");
+  }
+  if (d_first) cudaFree(d_first);
+  if (d_len) cudaFree(d_len);
+  if (d_coef) cudaFree(d_coef);
+  if (d_in) cudaFree(d_in);
+  if (d_out) cudaFree(d_out);
+  return st;
+}
+
 // ---- faces -----------------------------------------------------------------------------------------------------------
 igab_status igab_eval_faces(igab_patch* p, int64_t nfaces, const int32_t* elem, const int32_t* face, const int* nqf1,
                             const double* const* xi1d, double* x, double* normal, double* dS, igab_memspace space,

@@ -106,6 +106,8 @@ igab_status launch_volume(const PatchDev& P, SfWorkspace& ws, const double* cons
                           const double* const* xi1d_dev, const double* const* w1d_dev, double* partial_dev,
                           int npartial, double* result_dev, cudaStream_t stream);
 
+igab_status refine_apply(int dim, int dw, const int* ncp_old, int direction, int n_new, int maxlen, const int* first,
+                         const int* len, const double* coef, const double* cp_in, double* cp_out, cudaStream_t stream);
 igab_status eval_faces_device(igab_patch* p, long long nfaces, const int* elem, const int* face, const int* nqf1,
                               const double* const* xi_dev, double* x, double* normal, double* dS, cudaStream_t stream);
 igab_status csr_pattern(igab_patch* p, int ncomp, int64_t* nrows, int64_t* nnz, int64_t* rowptr, int32_t* colidx,

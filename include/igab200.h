@@ -146,6 +146,15 @@ igab_status igab_assemble(igab_patch* p, int kind, const double* D, double fcons
                           int64_t elem_end, const int* nq1, const double* const* xi1d, const double* const* w1d,
                           double* Ke, double* fe, igab_memspace out_space, void* stream);
 
+/* ---- refinement of the control net -----------------------------------------------------------------------------------
+ * Replaces the control-net part of knotRefinement / degreeElevate (dune/iga/nurbsalgorithms.hh:264-528) for one
+ * direction: new net = T applied along `direction` in homogeneous coordinates.  T (n_new x ncp_old[direction]) is given
+ * row-banded: row i has len[i] <= maxlen coefficients coef[i*maxlen + k] for the old indices first[i] + k.  All arrays
+ * HOST; cp_in has prod(ncp_old) rows, cp_out prod(ncp_new) rows of dimworld+1 doubles, first direction fastest.     */
+igab_status igab_refine_apply(int dim, int dimworld, const int* ncp_old, int direction, int n_new, int maxlen,
+                              const int32_t* first, const int32_t* len, const double* coef, const double* cp_in,
+                              double* cp_out);
+
 /* ---- element faces (boundary / intersection integrals) -----------------------------------------------------------------
  * Replaces, for nfaces faces x the tensor rule of dimension dim-1: NURBSintersection::geometry().global /
  * integrationElement and outerNormal / unitOuterNormal / integrationOuterNormal (dune/iga/nurbsintersection.hh:86-160;

@@ -474,3 +474,33 @@ def test_cylinder_boundary_normals_and_divergence_theorem():
                 assert np.abs(orient * o["normal"] - np.array([0, 0, 1.0 if s == 1 else -1.0])).max() < 1e-12
     vol = np.pi / 4 * 3.0 * 3.0
     assert abs(total - 3 * vol) < 1e-9
+
+
+def test_refinement_on_gpu_matches_host_and_reference():
+    """igab_refine_apply (control-net side of knotRefinement / degreeElevate, nurbsalgorithms.hh:264-528) against the
+    host operators and, when available, the reference's own refinement code."""
+    import refbind as RF
+    cw = 1.0 / np.sqrt(2.0)
+    cp0 = []
+    for z in (0.0, 3.0):
+        for r in (1.0, 2.0):
+            cp0 += [(r, 0, z, 1.0), (r, r, z, cw), (0, r, z, 1.0)]
+    P0 = PD.NurbsPatchData([[0, 0, 0, 1, 1, 1], [0, 0, 1, 1], [0, 0, 1, 1]], cp0, [2, 1, 1], 3)  # coarse (2,1,1)
+    cur_gpu, cur_host = P0, P0
+    for d, t in ((0, 1), (1, 2), (2, 2)):  # elevate to (3,3,3)
+        U, E = PD.degreeElevationOperator(cur_host.knotSpans[d], cur_host.degree[d], t)
+        cur_gpu = capi.refineApply(cur_gpu, d, E, U, cur_gpu.degree[d] + t)
+        cur_host = cur_host.degreeElevate(d, t)
+    for d in range(3):  # refine 2^3 per direction
+        nk = PD.generateRefinedKnots(cur_host.knotSpans, d, 3)
+        U, T = PD.knotInsertionOperator(cur_host.knotSpans[d], cur_host.degree[d], nk)
+        cur_gpu = capi.refineApply(cur_gpu, d, T, U)
+        cur_host = cur_host.knotRefinement(nk, d)
+    assert cur_gpu.ncp == cur_host.ncp == [11, 11, 11]
+    assert np.abs(cur_gpu.cp - cur_host.cp).max() <= 1e-14
+    if RF.available():
+        R = RF.RefPatch.create([2, 1, 1], [[0, 0, 0, 1, 1, 1], [0, 0, 1, 1], [0, 0, 1, 1]], cp0, 3)
+        R = R.degree_elevate(0, 1).degree_elevate(1, 2).degree_elevate(2, 2)
+        for d in range(3):
+            R = R.refine_uniform(d, 3)
+        assert np.abs(cur_gpu.cp - R.cp).max() <= 1e-12
