@@ -524,8 +524,8 @@ igab_status launch_cfg(const PatchDev& Pd, SfWorkspace& ws, const PointSource& s
   }
   igab_status st = ensure_tables3d(Pd, ws, Q, src.xi1d, xi1d_host, stream);
   if (st) return st;
-  // K2
-  constexpr int WARPS = 4;
+  // K2: warps per block chosen so that at least three blocks fit the 227 KB of shared memory of an SM
+  constexpr int WARPS = (C::SZ_WARP * 8 * 4 * 3 <= 225 * 1024) ? 4 : ((C::SZ_WARP * 8 * 2 * 3 <= 225 * 1024) ? 2 : 1);
   const size_t smem = (size_t)WARPS * C::SZ_WARP * sizeof(double);
   static bool configured = false;
   static int blocksPerSm = 1, numSms = 148;
@@ -572,7 +572,7 @@ bool eval_tensor_sf_supported(const PatchDev& P, const int* nq1, int order, cons
   if (!uniform_cfg(P, nq1, &k)) return false;
   if (out.d2N || out.H) return false;  // second derivatives: general kernel
   (void)order;
-  return (k.p == 3 && k.q == 4) || (k.p == 2 && k.q == 3) || (k.p == 4 && k.q == 5);
+  return (k.p == 3 && (k.q == 4 || k.q == 5)) || (k.p == 2 && (k.q == 3 || k.q == 4)) || (k.p == 4 && k.q == 5);
 }
 
 void free_sf_workspace(SfWorkspace& ws) {
@@ -593,7 +593,9 @@ igab_status launch_eval_tensor_sf(const PatchDev& P, SfWorkspace& ws, const Poin
   EvalOutDev o = out;
   if (order < 1) o.dN = o.Jt = o.detJ = o.JinvT = nullptr;
   if (k.p == 3 && k.q == 4) return launch_cfg<3, 4>(P, ws, src, xi1d_host, nelem, o, stream);
+  if (k.p == 3 && k.q == 5) return launch_cfg<3, 5>(P, ws, src, xi1d_host, nelem, o, stream);
   if (k.p == 2 && k.q == 3) return launch_cfg<2, 3>(P, ws, src, xi1d_host, nelem, o, stream);
+  if (k.p == 2 && k.q == 4) return launch_cfg<2, 4>(P, ws, src, xi1d_host, nelem, o, stream);
   return launch_cfg<4, 5>(P, ws, src, xi1d_host, nelem, o, stream);
 }
 

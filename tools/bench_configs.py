@@ -65,6 +65,14 @@ def main():
     if "C3e" in which:
         eval_config("C3 evaluation part: 3-D cylinder p=4 64^3, 5^3 Gauss, order 1 (2 k-layers per launch)",
                     PD.thickCylinder(4, (6, 6, 6)), [5, 5, 5], 1, ("N", "dN", "x", "Jt", "detJ"), el_chunk=64 * 64 * 2)
+    if "X" in which:  # beyond the five named configs
+        eval_config("X1 3-D cylinder p=2 128^3 (16 k-layers), 3^3 Gauss, order 1", PD.thickCylinder(2, (7, 7, 7)), [3, 3, 3], 1,
+                    ("N", "dN", "x", "Jt", "detJ"), el_chunk=128 * 128 * 16)
+        eval_config("X2 3-D cylinder p=3 64^3 (8 k-layers), 4^3 Gauss, order 2 (general kernel)", PD.thickCylinder(3, (6, 6, 6)), [4, 4, 4], 2,
+                    ("N", "dN", "d2N", "x", "Jt", "H", "detJ"), el_chunk=64 * 64 * 8)
+        eval_config("X3 3-D cylinder p=3 64^3 (8 k-layers), 5^3 Gauss, order 1 (general kernel: rule != p+1)", PD.thickCylinder(3, (6, 6, 6)),
+                    [5, 5, 5], 1, ("N", "dN", "x", "Jt", "detJ"), el_chunk=64 * 64 * 8)
+        eval_config("X4 2-D plate p=2 1024^2, 3x3 Gauss, detJ only (volume path)", PD.plateWithHole(9, 10), [3, 3], 1, ("detJ",))
     if "C4" in which:
         eval_config("C4 torus shell p=2 in R^3 1024x1024, 4x4 Gauss, order 2", PD.torusSurface(8), [4, 4], 2,
                     ("N", "dN", "d2N", "x", "Jt", "H", "detJ"))
