@@ -413,6 +413,7 @@ igab_status eval_for(const PatchDev& P, SfWorkspace& ws, const double* const* xi
     src.nq *= nq1[d];
     src.xi1d[d] = xi1d_dev[d];
   }
+  if (eval_tensor_blk_supported(P, nq1, 1, out)) return launch_eval_tensor_blk(P, ws, src, xi1d_host, nel, 1, out, stream);
   if (eval_tensor_sf_supported(P, nq1, 1, out)) return launch_eval_tensor_sf(P, ws, src, xi1d_host, nel, 1, out, stream);
   if (eval_tensor_2d_supported(P, nq1, 1, out)) return launch_eval_tensor_2d(P, ws, src, xi1d_host, nel, 1, out, stream);
   return launch_eval_generic(P, src, nel * src.nq, 1, out, stream);

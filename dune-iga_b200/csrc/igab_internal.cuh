@@ -84,6 +84,11 @@ igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* 
                               long long eb, long long nel, const int* nq1, double* Ke, double* fe, cudaStream_t stream,
                               const double* D_host);
 bool eval_tensor_sf_supported(const PatchDev& P, const int* nq1, int order, const EvalOutDev& out);
+// 3-D, large local bases (p = 4): one block per element
+bool eval_tensor_blk_supported(const PatchDev& P, const int* nq1, int order, const EvalOutDev& out);
+igab_status launch_eval_tensor_blk(const PatchDev& P, SfWorkspace& ws, const PointSource& src,
+                                   const double* const* xi1d_host, long long nelem, int order, const EvalOutDev& out,
+                                   cudaStream_t stream);
 // 2-D point lists (trimmed batches): per-point univariate rows in registers
 bool eval_points_2d_supported(const PatchDev& P);
 igab_status launch_eval_points_2d(const PatchDev& P, const PointSource& src, long long npts, int order,
