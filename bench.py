@@ -358,6 +358,39 @@ def main():
             capi.pinned_free(host[f])
         capi.pinned_free(cp_host)
 
+    # ---- the same end-to-end call chain when the consumer lives on the GPU (the assembly kernels): control net H2D,
+    # the full evaluation pass with outputs left in HBM, one patch-level reduction (volume) read back to the host
+    e2e_dev = None
+    if not args.no_e2e:
+        gw = PD.gaussLegendre01(NQ1)[1]
+        cp_host = capi.pinned_empty(pd.cp.shape)
+        cp_host[...] = pd.cp
+
+        def e2e_dev_step():
+            P.updateControlPoints(cp_host)
+            step()
+            return P.volume(xi, [gw, gw, gw], my_begin, my_begin + 128 ** 3, stream=stream.cuda_stream)
+
+        vol = e2e_dev_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_dev = 3
+        for _ in range(n_dev):
+            vol = e2e_dev_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e_dev = {"value": 128 ** 3 * NQ * world * n_dev / dt, "unit": "points/s",
+                   "h2d_bytes_per_step": int(cp_host.nbytes), "d2h_bytes_per_step": 8,
+                   "result": "slab volume %.12f (exact pi/4*(r_o^2-r_i^2)*L/%d = %.12f)" % (
+                       vol, 1, np.pi / 4 * 3.0 * 3.0 / world),
+                   "note": "all 134,217,728 points per rank evaluated per step with N+dN+x+Jt+detJ written to HBM (ring "
+                           "buffers) for a device-side consumer; only the reduction crosses PCIe"}
+        capi.pinned_free(cp_host)
+
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference's own headers (oracle/_ref), all host threads
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -391,7 +424,7 @@ def main():
             "metric": "quad-pt basis+Jacobian evals/sec", "value": value, "unit": "points/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(world),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "assembly": assembly}))
+            "clocks": clocks, "e2e": e2e, "e2e_device_consumer": e2e_dev, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "assembly": assembly}))
     if world > 1:
         dist.destroy_process_group()
 
