@@ -504,3 +504,18 @@ def test_refinement_on_gpu_matches_host_and_reference():
         for d in range(3):
             R = R.refine_uniform(d, 3)
         assert np.abs(cur_gpu.cp - R.cp).max() <= 1e-12
+
+
+@pytest.mark.parametrize("name", ["cylinder_p3", "cylinder_p4", "plate_hole_p2", "torus_p2"])
+@pytest.mark.parametrize("want", [("N",), ("dN",), ("detJ",), ("x", "JinvT"), ("Jt", "N"), ("dN", "detJ", "JinvT")])
+def test_output_subsets(name, want):
+    """Any subset of the output set may be requested (nullable members of igab_eval_out)."""
+    spec = PFT.small_patch(name)
+    Pp = port_for(spec)
+    P = gpu_patch(spec)
+    xi1d = gauss(spec)
+    ref = Pp.eval_tensor(xi1d, order=1, want=want)
+    got = P.evalTensor(xi1d, order=1, want=want)
+    assert set(got) == set(want)
+    for f in want:
+        assert relerr(got[f], ref[f]) <= TOL, f
