@@ -10,6 +10,7 @@
 #include <cstdlib>
 
 #include "igab_internal.cuh"
+#include "sf_geometry.cuh"
 
 namespace igab {
 
@@ -52,9 +53,7 @@ __global__ void __launch_bounds__(BCfg<P, Q>::NT) eval_sf3d_blk_kernel(PatchDev 
   double* const sW = sT + C::SZ_T;
   double* const rA = sW + C::SZ_W;
   double* const rB = rA + C::SZ_A;
-  double* const sH = rA;
-  double* const sS1 = rA + C::SZ_H;
-  double* const sG = rA;
+  double* const sG = rA;  // output of sf_contract
   double* const sS2 = rB;
   double* const sC = rB;
   double* const sSt = rB + C::SZ_C;
@@ -75,99 +74,8 @@ __global__ void __launch_bounds__(BCfg<P, Q>::NT) eval_sf3d_blk_kernel(PatchDev 
       e1 = (int)(h % Pd.nel[1]); h /= Pd.nel[1];
       e2 = (int)h;
     }
-    for (int j = tid; j < C::TAB; j += NT) {
-      sT[j] = __ldg(tab0 + (size_t)e0 * C::TAB + j);
-      sT[C::TAB + j] = __ldg(tab1 + (size_t)e1 * C::TAB + j);
-      sT[2 * C::TAB + j] = __ldg(tab2 + (size_t)e2 * C::TAB + j);
-    }
-    {
-      const int b0 = Pd.spanTab[0][e0] - P, b1 = Pd.spanTab[1][e1] - P, b2 = Pd.spanTab[2][e2] - P;
-      const long long n0 = Pd.ncp[0], n1 = Pd.ncp[1];
-      const double2* cp2 = reinterpret_cast<const double2*>(Pd.cp);
-      for (int i = tid; i < NB; i += NT) {
-        const int i0 = i % NB1, i12 = i / NB1, i1 = i12 % NB1, i2 = i12 / NB1;
-        const long long gi = (b0 + i0) + n0 * ((b1 + i1) + n1 * (long long)(b2 + i2));
-        const double2 xy = __ldg(cp2 + 2 * gi), zw = __ldg(cp2 + 2 * gi + 1);
-        double* h = sH + i12 * C::HS + 4 * i0;
-        h[0] = xy.x * zw.y; h[1] = xy.y * zw.y; h[2] = zw.x * zw.y; h[3] = zw.y;
-        sW[i] = zw.y;
-      }
-    }
-    __syncthreads();
-    for (int col = tid; col < 4 * NB1 * NB1; col += NT) {
-      const int i12 = col % (NB1 * NB1), c = col / (NB1 * NB1);
-      double h[NB1];
-#pragma unroll
-      for (int i0 = 0; i0 < NB1; ++i0) h[i0] = sH[i12 * C::HS + 4 * i0 + c];
-#pragma unroll
-      for (int q0 = 0; q0 < Q; ++q0) {
-        double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-        for (int i0 = 0; i0 < NB1; ++i0) {
-          const double2 tt = lds2b(sT + (q0 * NB1 + i0) * 2);
-          a0 = fma(tt.x, h[i0], a0);
-          a1 = fma(tt.y, h[i0], a1);
-        }
-        sS1[((0 * Q + q0) * 4 + c) * C::S1C + i12] = a0;
-        sS1[((1 * Q + q0) * 4 + c) * C::S1C + i12] = a1;
-      }
-    }
-    __syncthreads();
-    for (int col = tid; col < 2 * Q * 4 * NB1; col += NT) {
-      int r = col;
-      const int i2 = r % NB1; r /= NB1;
-      const int c = r % 4; r /= 4;
-      const int q0 = r % Q;
-      const int a0 = r / Q;
-      double s[NB1];
-#pragma unroll
-      for (int i1 = 0; i1 < NB1; ++i1) s[i1] = sS1[((a0 * Q + q0) * 4 + c) * C::S1C + i1 + NB1 * i2];
-#pragma unroll
-      for (int q1 = 0; q1 < Q; ++q1) {
-        double v0 = 0.0, v1 = 0.0;
-#pragma unroll
-        for (int i1 = 0; i1 < NB1; ++i1) {
-          const double2 tt = lds2b(sT + C::TAB + (q1 * NB1 + i1) * 2);
-          v0 = fma(tt.x, s[i1], v0);
-          v1 = fma(tt.y, s[i1], v1);
-        }
-        const int q01 = q0 + Q * q1;
-        if (a0 == 0) {
-          sS2[((0 * 4 + c) * Q2 + q01) * C::S2S + i2] = v0;
-          sS2[((2 * 4 + c) * Q2 + q01) * C::S2S + i2] = v1;
-        } else {
-          sS2[((1 * 4 + c) * Q2 + q01) * C::S2S + i2] = v0;
-        }
-      }
-    }
-    __syncthreads();
-    for (int col = tid; col < 3 * 4 * Q2; col += NT) {
-      int r = col;
-      const int q01 = r % Q2; r /= Q2;
-      const int c = r % 4;
-      const int a01 = r / 4;
-      double s[NB1];
-#pragma unroll
-      for (int i2 = 0; i2 < NB1; ++i2) s[i2] = sS2[((a01 * 4 + c) * Q2 + q01) * C::S2S + i2];
-#pragma unroll
-      for (int q2 = 0; q2 < Q; ++q2) {
-        double v0 = 0.0, v1 = 0.0;
-#pragma unroll
-        for (int i2 = 0; i2 < NB1; ++i2) {
-          const double2 tt = lds2b(sT + 2 * C::TAB + (q2 * NB1 + i2) * 2);
-          v0 = fma(tt.x, s[i2], v0);
-          v1 = fma(tt.y, s[i2], v1);
-        }
-        const int pt = q01 + Q2 * q2;
-        if (a01 == 0) {
-          sG[(0 * 4 + c) * NQ + pt] = v0;
-          sG[(3 * 4 + c) * NQ + pt] = v1;
-        } else {
-          sG[(a01 * 4 + c) * NQ + pt] = v0;
-        }
-      }
-    }
-    __syncthreads();
+    sf_load<P, Q, NT>(Pd, tid, e0, e1, e2, tab0, tab1, tab2, sT, sW, rA);
+    sf_contract<P, Q, NT>(tid, sT, rA, sS2);
     // ---- per point (one per thread when NQ <= NT, else strided): geometry in registers, constants for phase 4
     const long long ptBase = el * NQ;
     constexpr int PPT = (NQ + NT - 1) / NT;

@@ -28,6 +28,7 @@
 
 #include "bspline_device.cuh"
 #include "igab_internal.cuh"
+#include "sf_geometry.cuh"
 
 namespace igab {
 
@@ -151,127 +152,9 @@ __global__ void __launch_bounds__(128) eval_sf3d_kernel(PatchDev Pd, long long e
       e1 = (int)(h % Pd.nel[1]); h /= Pd.nel[1];
       e2 = (int)h;
     }
-    // ---- (0) univariate tables of this element -> shared
-    {
-      const double* t0 = tab0 + (size_t)e0 * C::TAB;
-      const double* t1 = tab1 + (size_t)e1 * C::TAB;
-      const double* t2 = tab2 + (size_t)e2 * C::TAB;
-      for (int j = lane; j < C::TAB; j += 32) {
-        sT[j] = __ldg(t0 + j);
-        sT[C::TAB + j] = __ldg(t1 + j);
-        sT[2 * C::TAB + j] = __ldg(t2 + j);
-      }
-    }
-    // ---- (1) control points -> homogeneous, shared  (netOfSpan: start = span - degree, nurbsalgorithms.hh:80-89)
-    {
-      const int b0 = Pd.spanTab[0][e0] - P, b1 = Pd.spanTab[1][e1] - P, b2 = Pd.spanTab[2][e2] - P;
-      const long long n0 = Pd.ncp[0], n1 = Pd.ncp[1];
-      const double2* cp2 = reinterpret_cast<const double2*>(Pd.cp);
-#pragma unroll
-      for (int k = 0; k < C::KS; ++k) {
-        const int i = lane + 32 * k;
-        if (i < NB) {
-          const int i0 = i % NB1, i12 = i / NB1, i1 = i12 % NB1, i2 = i12 / NB1;
-          const long long g = (b0 + i0) + n0 * ((b1 + i1) + n1 * (long long)(b2 + i2));
-          const double2 xy = __ldg(cp2 + 2 * g), zw = __ldg(cp2 + 2 * g + 1);
-          double* h = sH + i12 * C::HS + 4 * i0;
-          h[0] = xy.x * zw.y;
-          h[1] = xy.y * zw.y;
-          h[2] = zw.x * zw.y;
-          h[3] = zw.y;
-          sW[i] = zw.y;
-        }
-      }
-    }
-    __syncwarp();
-    // ---- (2a) stage 1: S1[a0][q0][c][i12] = sum_i0 T0[q0][i0][a0] H[i12][i0][c]
-    {
-      constexpr int NCOL = 4 * NB1 * NB1;
-      for (int col = lane; col < NCOL; col += 32) {
-        const int i12 = col % (NB1 * NB1), c = col / (NB1 * NB1);
-        double h[NB1];
-#pragma unroll
-        for (int i0 = 0; i0 < NB1; ++i0) h[i0] = sH[i12 * C::HS + 4 * i0 + c];
-#pragma unroll
-        for (int q0 = 0; q0 < Q; ++q0) {
-          double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-          for (int i0 = 0; i0 < NB1; ++i0) {
-            const double2 t = lds2(sT + (q0 * NB1 + i0) * 2);
-            a0 = fma(t.x, h[i0], a0);
-            a1 = fma(t.y, h[i0], a1);
-          }
-          sS1[((0 * Q + q0) * 4 + c) * C::S1C + i12] = a0;
-          sS1[((1 * Q + q0) * 4 + c) * C::S1C + i12] = a1;
-        }
-      }
-    }
-    __syncwarp();
-    // ---- (2b) stage 2: S2[a01][c][q0 + Q q1][i2] = sum_i1 T1[q1][i1][a1] S1[a0][q0][c][i1 + NB1 i2]
-    //      a01: 0 = (0,0), 1 = (1,0), 2 = (0,1)
-    {
-      constexpr int NCOL = 2 * Q * 4 * NB1;
-      for (int col = lane; col < NCOL; col += 32) {
-        int r = col;
-        const int i2 = r % NB1; r /= NB1;
-        const int c = r % 4; r /= 4;
-        const int q0 = r % Q;
-        const int a0 = r / Q;
-        double s[NB1];
-#pragma unroll
-        for (int i1 = 0; i1 < NB1; ++i1) s[i1] = sS1[((a0 * Q + q0) * 4 + c) * C::S1C + i1 + NB1 * i2];
-#pragma unroll
-        for (int q1 = 0; q1 < Q; ++q1) {
-          double v0 = 0.0, v1 = 0.0;
-#pragma unroll
-          for (int i1 = 0; i1 < NB1; ++i1) {
-            const double2 t = lds2(sT + C::TAB + (q1 * NB1 + i1) * 2);
-            v0 = fma(t.x, s[i1], v0);
-            v1 = fma(t.y, s[i1], v1);
-          }
-          const int q01 = q0 + Q * q1;
-          if (a0 == 0) {
-            sS2[((0 * 4 + c) * Q2 + q01) * C::S2S + i2] = v0;
-            sS2[((2 * 4 + c) * Q2 + q01) * C::S2S + i2] = v1;
-          } else {
-            sS2[((1 * 4 + c) * Q2 + q01) * C::S2S + i2] = v0;
-          }
-        }
-      }
-    }
-    __syncwarp();
-    // ---- (2c) stage 3: G[alpha][c][q01 + Q^2 q2] = sum_i2 T2[q2][i2][a2] S2[a01][c][q01][i2]
-    //      alpha: 0 = value, 1 = d/dxi0, 2 = d/dxi1, 3 = d/dxi2
-    {
-      constexpr int NCOL = 3 * 4 * Q2;
-      for (int col = lane; col < NCOL; col += 32) {
-        int r = col;
-        const int q01 = r % Q2; r /= Q2;
-        const int c = r % 4;
-        const int a01 = r / 4;
-        double s[NB1];
-#pragma unroll
-        for (int i2 = 0; i2 < NB1; ++i2) s[i2] = sS2[((a01 * 4 + c) * Q2 + q01) * C::S2S + i2];
-#pragma unroll
-        for (int q2 = 0; q2 < Q; ++q2) {
-          double v0 = 0.0, v1 = 0.0;
-#pragma unroll
-          for (int i2 = 0; i2 < NB1; ++i2) {
-            const double2 t = lds2(sT + 2 * C::TAB + (q2 * NB1 + i2) * 2);
-            v0 = fma(t.x, s[i2], v0);
-            v1 = fma(t.y, s[i2], v1);
-          }
-          const int pt = q01 + Q2 * q2;
-          if (a01 == 0) {
-            sG[(0 * 4 + c) * NQ + pt] = v0;
-            sG[(3 * 4 + c) * NQ + pt] = v1;
-          } else {
-            sG[(a01 * 4 + c) * NQ + pt] = v0;  // a01 = 1 -> alpha 1 ; a01 = 2 -> alpha 2
-          }
-        }
-      }
-    }
-    __syncwarp();
+    // ---- (0)-(2): tables + control points -> shared, geometry by sum factorisation (sf_geometry.cuh)
+    sf_load<P, Q, 32>(Pd, lane, e0, e1, e2, tab0, tab1, tab2, sT, sW, rA);
+    sf_contract<P, Q, 32>(lane, sT, rA, sS2);
     // ---- (3) per point: x = C/W, J_d = (C_d - W_d x)/W, detJ, J^-T ; constants for (4)
     const long long ptBase = el * NQ;
 #pragma unroll 1
