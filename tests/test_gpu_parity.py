@@ -519,3 +519,27 @@ def test_output_subsets(name, want):
     assert set(got) == set(want)
     for f in want:
         assert relerr(got[f], ref[f]) <= TOL, f
+
+
+@pytest.mark.parametrize("name", ["cylinder_p3", "cylinder_p4", "square_p3"])
+def test_misaligned_device_outputs(name):
+    """Device output pointers that are only 8-byte aligned (views at an odd double offset): the 16-byte paths
+    (TMA bulk stores, vector stores) must fall back, results unchanged."""
+    import torch
+    spec = PFT.small_patch(name)
+    P = gpu_patch(spec)
+    xi1d = gauss(spec)
+    nq = int(np.prod([len(x) for x in xi1d]))
+    npts = P.nelem * nq
+    sh = P.shapes(npts)
+    fields = ("N", "dN", "x", "Jt", "detJ", "JinvT")
+    host = P.evalTensor(xi1d, order=1, want=fields)
+    out = {}
+    for f in fields:
+        buf = torch.empty(int(np.prod(sh[f])) + 1, dtype=torch.float64, device="cuda")
+        out[f] = buf[1:].view(sh[f])
+        assert out[f].data_ptr() % 16 == 8
+    P.evalTensor(xi1d, order=1, want=fields, out=out, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for f in fields:
+        assert np.array_equal(out[f].cpu().numpy(), host[f]), f
