@@ -15,6 +15,7 @@
 //       accumulators.  K_e is symmetric: only the upper 32x32 blocks are contracted (one warp each) and mirrored
 //       on the way out.
 #include <algorithm>
+#include <type_traits>
 
 #include "igab_internal.cuh"
 #include "sf_geometry.cuh"
@@ -34,7 +35,9 @@ template <int P, int Q>
 struct FCfg {
   static constexpr int NB1 = P + 1, NB = NB1 * NB1 * NB1, NQ = Q * Q * Q, Q2 = Q * Q;
   static constexpr int NBP = (NB + 31) / 32 * 32;
-  static constexpr int NBLK = NBP / 32, NUP = NBLK * (NBLK + 1) / 2, NT = NUP * 32;
+  static constexpr int NBLK = NBP / 32;            // 32-wide blocks (elasticity kernel)
+  static constexpr int NTR = NBP / 8, NW = NTR / 2;  // 8-wide tile rows; warp w owns tile rows w and NTR-1-w
+  static constexpr int NT = NW * 32;
   static constexpr int TAB = Q * NB1 * 2;
   static constexpr int HS = 4 * NB1 + 1, S1C = NB1 * NB1 + 1, S2S = NB1 | 1;
   static constexpr int ev(int x) { return (x + 1) & ~1; }
@@ -45,7 +48,7 @@ struct FCfg {
   static constexpr int SZ_G = 16 * NQ;
   static constexpr int SZ_A = ev((SZ_H + SZ_S1) > SZ_G ? (SZ_H + SZ_S1) : SZ_G);
   static constexpr int SZ_S2 = ev(3 * 4 * Q2 * S2S);
-  static constexpr int CS = 16;  // doubles per point: 1/W, W_0..2, J^-T[9], w detJ, pad
+  static constexpr int CS = 16;  // doubles per point: 1/W, W_0..2, J^-T[9], w detJ, sqrt(w detJ), pad
   static constexpr int SZ_C = CS * NQ;
   static constexpr int KC = 16, LD = NBP + 4;
   static constexpr int SZ_SA = 2 * KC * LD;
@@ -108,10 +111,23 @@ __device__ __forceinline__ void element_prepare(const PatchDev& Pd, long long e,
     o[7] = c01 * id; o[8] = c11 * id; o[9] = c21 * id;
     o[10] = c02 * id; o[11] = c12 * id; o[12] = c22 * id;
     o[13] = w * fabs(det);
+    o[14] = sqrt(o[13]);  // rows of the gradient stack are pre-scaled by sqrt(w detJ): K = A^T A, no scaling in the MMA loop
   }
   __syncthreads();
 
 }
+
+// Warp w of the Gram kernel owns the upper-triangular parts of tile rows RA = w and RB = NTR-1-w of the symmetric
+// matrix (8x8 DMMA tiles): (NTR - w) + (w + 1) = NTR + 1 tiles for EVERY warp -- perfectly balanced over the four
+// SM sub-partitions.  Slot s of a warp is tile (RA, w + s) for s < NTR - w and tile (RB, s - 1) after that; one code
+// path for all warps (row / column of a slot are warp-uniform run-time values, the accumulator index is static).
+template <int NTR>
+struct TileSlot {
+  int w, na, ra, rb;
+  __device__ __forceinline__ explicit TileSlot(int warp) : w(warp), na(NTR - warp), ra(warp), rb(NTR - 1 - warp) {}
+  __device__ __forceinline__ int row(int s) const { return s < na ? ra : rb; }
+  __device__ __forceinline__ int col(int s) const { return s < na ? w + s : s - 1; }
+};
 
 template <int P, int Q, int NROW>
 __global__ void __launch_bounds__(FCfg<P, Q>::NT, 2) gram_fused_kernel(
@@ -132,16 +148,6 @@ __global__ void __launch_bounds__(FCfg<P, Q>::NT, 2) gram_fused_kernel(
   double* const sA = sC + C::SZ_C;  // [2][KC][LD]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  int bi = 0, bj = 0;
-  {
-    int w = warp;
-    while (w >= C::NBLK - bi) {
-      w -= C::NBLK - bi;
-      ++bi;
-    }
-    bj = bi + w;
-  }
-  const int wi = bi * 32, wj = bj * 32;
   for (int idx = tid; idx < C::SZ_SA; idx += NT) sA[idx] = 0.0;  // zero rows / padding columns stay zero
   for (int idx = tid; idx < C::SZ_W; idx += NT) sW[idx] = 0.0;
 
@@ -165,12 +171,13 @@ __global__ void __launch_bounds__(FCfg<P, Q>::NT, 2) gram_fused_kernel(
           const double w = sW[i], invW = k[0];
           const double t00 = a.x * b.x, wn2 = w * c.x;
           const double R = t00 * wn2 * invW;
+          const double sq = k[14];
           if constexpr (NROW == 1) {
-            r0 = R;
+            r0 = R * sq;
           } else {
-            const double d0 = (a.y * b.x * wn2 - k[1] * R) * invW;
-            const double d1 = (a.x * b.y * wn2 - k[2] * R) * invW;
-            const double d2 = (t00 * (w * c.y) - k[3] * R) * invW;
+            const double d0 = (a.y * b.x * wn2 - k[1] * R) * invW * sq;
+            const double d1 = (a.x * b.y * wn2 - k[2] * R) * invW * sq;
+            const double d2 = (t00 * (w * c.y) - k[3] * R) * invW * sq;
             r0 = k[4] * d0 + k[5] * d1 + k[6] * d2;
             r1 = k[7] * d0 + k[8] * d1 + k[9] * d2;
             r2 = k[10] * d0 + k[11] * d1 + k[12] * d2;
@@ -185,11 +192,15 @@ __global__ void __launch_bounds__(FCfg<P, Q>::NT, 2) gram_fused_kernel(
         }
       }
     };
-    double acc[4][4][2];
+    constexpr int NS = C::NTR + 1;  // tiles per warp
+    const TileSlot<C::NTR> slot(warp);
+    double acc[NS][2];
+    int colOff[NS];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    for (int sl = 0; sl < NS; ++sl) {
+      acc[sl][0] = acc[sl][1] = 0.0;
+      colOff[sl] = 8 * slot.col(sl);
+    }
     build(0);
     __syncthreads();
 #pragma unroll 1
@@ -197,36 +208,28 @@ __global__ void __launch_bounds__(FCfg<P, Q>::NT, 2) gram_fused_kernel(
       const double* A = sA + (ch & 1) * KC * LD;
 #pragma unroll
       for (int ks = 0; ks < KC; ks += 4) {
-        const int k = ks + t, pt = ch * pts + k / NROW;
-        const double sc = (k < pts * NROW && pt < NQ) ? sC[CS * pt + 13] : 0.0;
-        double af[4], bf[4];
+        const double* Ak = A + (ks + t) * LD + g;  // rows beyond the chunk's points are zero
+        const double aA = Ak[8 * slot.ra], aB = Ak[8 * slot.rb];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) af[a] = A[k * LD + wi + 8 * a + g];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) bf[b] = A[k * LD + wj + 8 * b + g] * sc;
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) dmma8x8x4_f(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        for (int sl = 0; sl < NS; ++sl) dmma8x8x4_f(acc[sl][0], acc[sl][1], sl < slot.na ? aA : aB, Ak[colOff[sl]]);
       }
       if (ch + 1 < nchunk) build(ch + 1);
       __syncthreads();
     }
     double* K = Ke + el * (long long)NB * NB;
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int i = wi + 8 * a + g, j = wj + 8 * b + 2 * t;
-        if (i < NB) {
-          if (j < NB) K[(long long)i * NB + j] = acc[a][b][0];
-          if (j + 1 < NB) K[(long long)i * NB + j + 1] = acc[a][b][1];
-          if (bi != bj) {
-            if (j < NB) K[(long long)j * NB + i] = acc[a][b][0];
-            if (j + 1 < NB) K[(long long)(j + 1) * NB + i] = acc[a][b][1];
-          }
+    for (int sl = 0; sl < NS; ++sl) {
+      const int r = slot.row(sl), c = slot.col(sl);
+      const int i = 8 * r + g, j = 8 * c + 2 * t;
+      if (i < NB) {
+        if (j < NB) K[(long long)i * NB + j] = acc[sl][0];
+        if (j + 1 < NB) K[(long long)i * NB + j + 1] = acc[sl][1];
+        if (r != c) {  // mirror the off-diagonal tile
+          if (j < NB) K[(long long)j * NB + i] = acc[sl][0];
+          if (j + 1 < NB) K[(long long)(j + 1) * NB + i] = acc[sl][1];
         }
       }
+    }
     // ---- load vector f_e[i] = sum_q w detJ R_i fconst  (poisson.py:79)
     if (fe) {
       for (int i = tid; i < NB; i += NT) {
@@ -326,9 +329,10 @@ __global__ void __launch_bounds__(ECfg<P, Q>::NT, 2) elasticity_fused_kernel(
               const double w = sW[i], invW = k[0];
               const double t00 = a.x * b.x, wn2 = w * c.x;
               const double R = t00 * wn2 * invW;
-              const double d0 = (a.y * b.x * wn2 - k[1] * R) * invW;
-              const double d1 = (a.x * b.y * wn2 - k[2] * R) * invW;
-              const double d2 = (t00 * (w * c.y) - k[3] * R) * invW;
+              const double sq = k[14];
+              const double d0 = (a.y * b.x * wn2 - k[1] * R) * invW * sq;
+              const double d1 = (a.x * b.y * wn2 - k[2] * R) * invW * sq;
+              const double d2 = (t00 * (w * c.y) - k[3] * R) * invW * sq;
               r0 = k[4] * d0 + k[5] * d1 + k[6] * d2;
               r1 = k[7] * d0 + k[8] * d1 + k[9] * d2;
               r2 = k[10] * d0 + k[11] * d1 + k[12] * d2;
@@ -342,13 +346,12 @@ __global__ void __launch_bounds__(ECfg<P, Q>::NT, 2) elasticity_fused_kernel(
           const double* Gb = sGs + wcp * KC * LD;
 #pragma unroll
           for (int ks = 0; ks < KC; ks += 4) {
-            const int k = ks + t, pt = ch * KC + k;
-            const double sc = pt < NQ ? sC[CS * pt + 13] : 0.0;
+            const int k = ks + t;  // rows of points beyond the rule are zero
             double af[4], bf[4];
 #pragma unroll
             for (int a = 0; a < 4; ++a) af[a] = Ga[k * LD + bi * 32 + 8 * a + g];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) bf[b] = Gb[k * LD + bj * 32 + 8 * b + g] * sc;
+            for (int b = 0; b < 4; ++b) bf[b] = Gb[k * LD + bj * 32 + 8 * b + g];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
