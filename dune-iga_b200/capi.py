@@ -16,6 +16,7 @@ _lib = None
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)
 HOST, DEVICE = 0, 1
+OK, INVALID_ARGUMENT, OUT_OF_MEMORY, CUDA_ERROR, NCCL_ERROR, UNSUPPORTED = range(6)
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TENSOR = 0, 1, 2
 ASM_POISSON, ASM_MASS, ASM_ELASTICITY = 0, 1, 2
 FIELDS = ("N", "dN", "d2N", "x", "Jt", "H", "detJ", "JinvT")
@@ -23,7 +24,7 @@ EXPORTS = ("igab_last_error_string", "igab_version", "igab_launch_count", "igab_
            "igab_patch_create", "igab_patch_destroy", "igab_patch_sizes", "igab_patch_set_kernel",
            "igab_patch_update_control_points", "igab_patch_spans", "igab_patch_dofmap", "igab_eval_tensor",
            "igab_eval_points", "igab_partial", "igab_assemble", "igab_reduce_volume", "igab_csr_pattern",
-           "igab_csr_assemble", "igab_eval_faces", "igab_refine_apply")
+           "igab_csr_assemble", "igab_eval_faces", "igab_refine_apply", "igab_surface_forms", "igab_geometry_local")
 
 
 class EvalOut(C.Structure):
@@ -70,6 +71,9 @@ def lib():
                                         C.c_int, C.c_int, C.c_void_p]
         L.igab_eval_faces.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, ip, C.POINTER(dp), C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.igab_surface_forms.argtypes = [C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p]
+        L.igab_geometry_local.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                          C.c_void_p]
         L.igab_refine_apply.argtypes = [C.c_int, C.c_int, ip, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, dp, dp,
                                         dp]
         L.igab_reduce_volume.argtypes = [C.c_void_p, C.c_int64, C.c_int64, ip, C.POINTER(dp), C.POINTER(dp),
@@ -325,6 +329,18 @@ class Patch:
                                      ptrs, x.ctypes.data, nrm.ctypes.data, dS.ctypes.data, HOST, None))
         return dict(x=x, normal=nrm, dS=dS)
 
+    # ---- inverse map
+    def local(self, elem, xglobal):
+        """Element-local coordinates of the points of elements elem[k] that map to / lie closest to xglobal[k]
+        (NURBSGeometry::local, nurbsgeometry.hh:145-176).  Returns (xi [npts][dim], flag [npts])."""
+        elem = _i32(elem)
+        X = _f64(xglobal).reshape(len(elem), self.dimworld)
+        xi = np.empty((len(elem), self.dim))
+        flag = np.empty(len(elem), dtype=np.int32)
+        _check(lib().igab_geometry_local(self.h, len(elem), elem.ctypes.data, X.ctypes.data, xi.ctypes.data,
+                                         flag.ctypes.data, HOST, None))
+        return xi, flag
+
     # ---- global sparse matrix
     def csrPattern(self, ncomp=1):
         """(rowptr int64 [nrows+1], colidx int32 [nnz]) of the global matrix; replaces the lil_matrix of poisson.py:87."""
@@ -366,3 +382,31 @@ class Patch:
         _check(lib().igab_reduce_volume(self.h, elem_begin, elem_end, nq1.ctypes.data_as(ip), xp, wp, C.byref(r),
                                         nccl_comm, stream))
         return r.value
+
+
+def surfaceForms(Jt, H=None, want=("normal", "unitNormal", "metric", "secondFF", "gaussK"), stream=None):
+    """normal / unitNormal / metric / secondFundamentalForm / gaussianCurvature (nurbsgeometry.hh:216-255) for every
+    point of the Jt [npts][dim][dimworld] (and H [npts][nh][dimworld]) arrays an evaluation call returned.  numpy
+    arrays are staged through the device; CUDA tensors are processed in place (outputs are torch tensors)."""
+    if isinstance(Jt, np.ndarray):
+        Jt = _f64(Jt)
+        H = _f64(H) if H is not None else None
+    ja, space = _ptr(Jt)
+    npts, dim, dw = tuple(Jt.shape)
+    ha = _ptr(H)[0] if H is not None else None
+    shapes = dict(normal=(npts, 3), unitNormal=(npts, 3), metric=(npts, dim, dim), secondFF=(npts, 2, 2),
+                  gaussK=(npts,))
+    out, ptrs = {}, {}
+    for k, shp in shapes.items():
+        if k not in want:
+            ptrs[k] = None
+            continue
+        if space == HOST:
+            out[k] = np.empty(shp)
+        else:
+            import torch
+            out[k] = torch.empty(shp, dtype=torch.float64, device=Jt.device)
+        ptrs[k] = _ptr(out[k])[0]
+    _check(lib().igab_surface_forms(dim, dw, npts, ja, ha, ptrs["normal"], ptrs["unitNormal"], ptrs["metric"],
+                                    ptrs["secondFF"], ptrs["gaussK"], space, stream))
+    return out

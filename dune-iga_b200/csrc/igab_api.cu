@@ -841,6 +841,91 @@ igab_status igab_eval_faces(igab_patch* p, int64_t nfaces, const int32_t* elem, 
   return st;
 }
 
+// ---- differential geometry of surfaces ---------------------------------------------------------------------------------
+igab_status igab_surface_forms(int dim, int dimworld, int64_t npts, const double* Jt, const double* H, double* normal,
+                               double* unit_normal, double* metric, double* second_ff, double* gauss_k,
+                               igab_memspace space, void* stream_) {
+  if (npts < 0 || (npts > 0 && !Jt)) {
+    set_error("surface_forms: null argument");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  if (dim < 1 || dim > 3 || dimworld < dim || dimworld > 3) {
+    set_error("surface_forms: unsupported (dim, dimworld)");
+    return IGAB_UNSUPPORTED;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (space == IGAB_DEVICE)
+    return surface_forms_device(dim, dimworld, npts, Jt, H, normal, unit_normal, metric, second_ff, gauss_k, stream);
+  if (npts == 0) return IGAB_OK;
+  // host arrays: one device block [Jt | H | normal | unit | metric | b | K]
+  const size_t nh = (size_t)dim * (dim + 1) / 2;
+  const size_t len[7] = {(size_t)dim * dimworld, H ? nh * dimworld : 0, normal ? 3u : 0u, unit_normal ? 3u : 0u,
+                         metric ? (size_t)dim * dim : 0, second_ff ? 4u : 0u, gauss_k ? 1u : 0u};
+  size_t off[8] = {0};
+  for (int k = 0; k < 7; ++k) off[k + 1] = off[k] + len[k] * (size_t)npts;
+  double* d = nullptr;
+  IGAB_CUDA_TRY(cudaMalloc(&d, off[7] * sizeof(double)));
+  auto part = [&](int k) { return len[k] ? d + off[k] : nullptr; };
+  cudaError_t e = cudaMemcpyAsync(d + off[0], Jt, len[0] * npts * sizeof(double), cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess && H) e = cudaMemcpyAsync(d + off[1], H, len[1] * npts * sizeof(double), cudaMemcpyHostToDevice, stream);
+  igab_status st = e == cudaSuccess ? IGAB_OK : cuda_fail(e, "surface_forms H2D");
+  if (!st) st = surface_forms_device(dim, dimworld, npts, part(0), part(1), part(2), part(3), part(4), part(5), part(6), stream);
+  if (!st) {
+    double* host[7] = {nullptr, nullptr, normal, unit_normal, metric, second_ff, gauss_k};
+    for (int k = 2; k < 7 && e == cudaSuccess; ++k)
+      if (host[k]) e = cudaMemcpyAsync(host[k], d + off[k], len[k] * npts * sizeof(double), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) st = cuda_fail(e, "surface_forms D2H");
+  }
+  cudaStreamSynchronize(stream);
+  cudaFree(d);
+  return st;
+}
+
+// ---- inverse of the element map ---------------------------------------------------------------------------------------
+igab_status igab_geometry_local(igab_patch* p, int64_t npts, const int32_t* elem, const double* xglobal, double* xi,
+                                int32_t* flag, igab_memspace space, void* stream_) {
+  if (!p || npts < 0 || (npts > 0 && (!elem || !xglobal || !xi))) {
+    set_error("geometry_local: null argument");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int dim = p->dev.dim, dw = p->dev.dw;
+  if (dim != dw && dim > 2) {
+    set_error("geometry_local: closest-point projection exists for curves and surfaces only");
+    return IGAB_UNSUPPORTED;
+  }
+  if (space == IGAB_DEVICE) return geometry_local_device(p->dev, npts, elem, xglobal, xi, flag, stream);
+  if (npts == 0) return IGAB_OK;
+  for (long long k = 0; k < npts; ++k)
+    if (elem[k] < 0 || elem[k] >= p->dev.nelem) {
+      set_error("geometry_local: element index out of range");
+      return IGAB_INVALID_ARGUMENT;
+    }
+  int *d_el = nullptr, *d_fl = nullptr;
+  double *d_x = nullptr, *d_xi = nullptr;
+  cudaError_t e = cudaMalloc(&d_el, sizeof(int) * npts);
+  if (e == cudaSuccess) e = cudaMalloc(&d_fl, sizeof(int) * npts);
+  if (e == cudaSuccess) e = cudaMalloc(&d_x, sizeof(double) * npts * dw);
+  if (e == cudaSuccess) e = cudaMalloc(&d_xi, sizeof(double) * npts * dim);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_el, elem, sizeof(int) * npts, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_x, xglobal, sizeof(double) * npts * dw, cudaMemcpyHostToDevice, stream);
+  igab_status st = e == cudaSuccess ? IGAB_OK : cuda_fail(e, "geometry_local staging");
+  if (!st) st = geometry_local_device(p->dev, npts, d_el, d_x, d_xi, d_fl, stream);
+  if (!st) {
+    e = cudaMemcpyAsync(xi, d_xi, sizeof(double) * npts * dim, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && flag) e = cudaMemcpyAsync(flag, d_fl, sizeof(int) * npts, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) st = cuda_fail(e, "geometry_local D2H");
+  }
+  cudaStreamSynchronize(stream);
+  if (d_el) cudaFree(d_el);
+  if (d_fl) cudaFree(d_fl);
+  if (d_x) cudaFree(d_x);
+  if (d_xi) cudaFree(d_xi);
+  return st;
+}
+
 // ---- global CSR -----------------------------------------------------------------------------------------------------
 igab_status igab_csr_pattern(igab_patch* p, int ncomp, int64_t* nrows, int64_t* nnz, int64_t* rowptr, int32_t* colidx,
                              igab_memspace space, void* stream) {

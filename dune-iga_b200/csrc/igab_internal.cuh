@@ -115,6 +115,11 @@ igab_status refine_apply(int dim, int dw, const int* ncp_old, int direction, int
                          const int* len, const double* coef, const double* cp_in, double* cp_out, cudaStream_t stream);
 igab_status eval_faces_device(igab_patch* p, long long nfaces, const int* elem, const int* face, const int* nqf1,
                               const double* const* xi_dev, double* x, double* normal, double* dS, cudaStream_t stream);
+igab_status geometry_local_device(const PatchDev& P, long long npts, const int* elem, const double* xg, double* xi,
+                                  int* flag, cudaStream_t stream);
+igab_status surface_forms_device(int dim, int dw, long long npts, const double* Jt, const double* H, double* normal,
+                                 double* unitNormal, double* metric, double* secondFF, double* gaussK,
+                                 cudaStream_t stream);
 igab_status csr_pattern(igab_patch* p, int ncomp, int64_t* nrows, int64_t* nnz, int64_t* rowptr, int32_t* colidx,
                         igab_memspace space, cudaStream_t stream);
 igab_status csr_assemble(igab_patch* p, int ncomp, long long eb, long long ee, const double* Ke, const int64_t* rowptr,

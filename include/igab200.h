@@ -166,6 +166,29 @@ igab_status igab_eval_faces(igab_patch* p, int64_t nfaces, const int32_t* elem, 
                             const double* const* xi1d, double* x, double* normal, double* dS, igab_memspace space,
                             void* stream);
 
+/* ---- differential geometry of surfaces ---------------------------------------------------------------------------------
+ * Replaces, batched over npts points, NURBSGeometry::normal / unitNormal (dune/iga/nurbsgeometry.hh:216-228), metric
+ * (:238-243), secondFundamentalForm (:245-255) and gaussianCurvature (:230-236).  Inputs are the arrays written by
+ * igab_eval_tensor / igab_eval_points: Jt [npts][dim][dimworld], H [npts][dim(dim+1)/2][dimworld] (rows uu, vv, uv;
+ * needed for second_ff / gauss_k only).  Outputs (nullable): normal [npts][3] = J0 x J1, unit_normal [npts][3],
+ * metric [npts][dim][dim] = J J^T, second_ff [npts][2][2] = H_ab . n, gauss_k [npts] = det(second_ff) / det(metric).
+ * metric works for every (dim, dimworld); the others need dim 2, dimworld 3 as in the reference (IGAB_UNSUPPORTED
+ * otherwise).  All arrays live in `space`.                                                                          */
+igab_status igab_surface_forms(int dim, int dimworld, int64_t npts, const double* Jt, const double* H, double* normal,
+                               double* unit_normal, double* metric, double* second_ff, double* gauss_k,
+                               igab_memspace space, void* stream);
+
+/* ---- inverse of the element map ---------------------------------------------------------------------------------------
+ * Replaces NURBSGeometry::local (dune/iga/nurbsgeometry.hh:145-176), batched: for point k, the element-local
+ * coordinates xi[k][dim] in [0,1]^dim of the point of element elem[k] that maps to (dim == dimworld: Newton) or lies
+ * closest to (curves / surfaces in a larger space: closestPointProjectionByTrustRegion,
+ * dune/iga/geometry/closestpointprojection.hh) xglobal[k][dimworld].  As in the reference the iterate is clamped to
+ * the element, and a singular Jacobian returns DBL_MAX in every coordinate.  flag[k] (nullable): 0 ok, 1 singular
+ * matrix, 2 no energy-decreasing direction (the reference throws Dune::MathError; xi = NaN), 3 Newton iteration cap
+ * (100; the reference has none).  All arrays live in `space`.                                                       */
+igab_status igab_geometry_local(igab_patch* p, int64_t npts, const int32_t* elem, const double* xglobal, double* xi,
+                                int32_t* flag, igab_memspace space, void* stream);
+
 /* ---- global sparse matrix (CSR) ---------------------------------------------------------------------------------------
  * Replaces the scatter loop of globalAssembler, dune/python/test/poisson.py:113-125 (A[gi,gj] += localA[i,j] through
  * localView.index), for the tensor-product DOF numbering of NurbsPreBasis (nurbsbasis.hh:572-584): row g couples

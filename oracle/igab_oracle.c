@@ -699,6 +699,187 @@ void igo_trimmed_rule(long ntri, const double* tri, int nrp, const double* ref_p
   }
 }
 
+/* ---- a17 extras: NURBSGeometry::normal / unitNormal / metric / secondFundamentalForm / gaussianCurvature -------
+ * dune/iga/nurbsgeometry.hh:216-255.  Jt [npts][dim][dw], H [npts][nh][dw] (rows uu, vv, uv); outputs nullable.
+ * normal = J0 x J1, unit = normal / |normal|, metric = J J^T (MatrixHelper::AAT), b_ab = H_ab . unit,
+ * K = det(b) / det(metric).  Pinned integrally by Gauss-Bonnet on the torus (gridtests.cpp:348-363).              */
+void igo_surface_forms(int dim, int dw, long npts, const double* Jt, const double* H, double* normal, double* unit,
+                       double* metric, double* secondff, double* gaussK) {
+  for (long t = 0; t < npts; ++t) {
+    const double* J = Jt + t * dim * dw;
+    double g[9];
+    for (int a = 0; a < dim; ++a)
+      for (int b = 0; b < dim; ++b) {
+        double s = 0;
+        for (int c = 0; c < dw; ++c) s += J[a * dw + c] * J[b * dw + c];
+        g[a * dim + b] = s;
+      }
+    if (metric) for (int q = 0; q < dim * dim; ++q) metric[t * dim * dim + q] = g[q];
+    if (dim == 2 && dw == 3) {
+      const double N[3] = {J[1] * J[5] - J[2] * J[4], J[2] * J[3] - J[0] * J[5], J[0] * J[4] - J[1] * J[3]};
+      const double len = sqrt(N[0] * N[0] + N[1] * N[1] + N[2] * N[2]);
+      const double n[3] = {N[0] / len, N[1] / len, N[2] / len};
+      if (normal) for (int c = 0; c < 3; ++c) normal[t * 3 + c] = N[c];
+      if (unit) for (int c = 0; c < 3; ++c) unit[t * 3 + c] = n[c];
+      if (H && (secondff || gaussK)) {
+        double b[3];
+        for (int r = 0; r < 3; ++r) b[r] = H[(t * 3 + r) * 3] * n[0] + H[(t * 3 + r) * 3 + 1] * n[1] + H[(t * 3 + r) * 3 + 2] * n[2];
+        if (secondff) { secondff[t * 4] = b[0]; secondff[t * 4 + 1] = secondff[t * 4 + 2] = b[2]; secondff[t * 4 + 3] = b[1]; }
+        if (gaussK) gaussK[t] = (b[0] * b[1] - b[2] * b[2]) / (g[0] * g[3] - g[1] * g[2]);
+      }
+    }
+  }
+}
+
+/* ---- NURBSGeometry::local (dune/iga/nurbsgeometry.hh:145-176): inverse of the ELEMENT map, xi in [0,1]^dim ----------
+ * dim == dimworld: Newton from xi = 0.5, step dx = (Jt Jt^T)^-1 Jt (x(xi) - X) (MatrixHelper::xTRightInvA), clamp to
+ *   [0,1] and stop when every coordinate sits on the boundary, else iterate while |dx|^2 > 16 eps; a singular Jacobian
+ *   returns numeric_limits::max() in every coordinate (flag 1).
+ * dim < dimworld (curves, surfaces): closestPointProjectionByTrustRegion, dune/iga/geometry/closestpointprojection.hh:
+ *   minimise 0.5 |x(u) - X|^2 with Newton steps H du = -R limited to 1/4 of the domain, step halving while the
+ *   energy grows (20 tries, then the reference throws MathError -> flag 2, xi = NaN), at most 100 iterations,
+ *   stop when |R| < 1e-10 or when the clamped iterate sits on the boundary in every coordinate.
+ * flag (nullable): 0 converged, 1 singular, 2 no descent direction, 3 iteration cap of the Newton branch (the
+ * reference would loop forever).                                                                                */
+static void geo012(const igo_patch* P, const int* span, const double* loc, const double* xi, int order, double* x,
+                   double* J, double* H, double* work) {
+  eval_point(P, span, loc, xi, order, 0, 0, 0, x, order >= 1 ? J : 0, order >= 2 ? H : 0, 0, 0, work);
+}
+static int solve_small(int n, const double* A, const double* b, double* y) {
+  if (n == 1) { if (A[0] == 0.0) return 0; y[0] = b[0] / A[0]; return 1; }
+  if (n == 2) {
+    const double det = A[0] * A[3] - A[1] * A[2];
+    if (det == 0.0) return 0;
+    y[0] = (A[3] * b[0] - A[1] * b[1]) / det;
+    y[1] = (A[0] * b[1] - A[2] * b[0]) / det;
+    return 1;
+  }
+  const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
+  const double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
+  if (det == 0.0) return 0;
+  const double i00 = c00, i01 = A[2] * A[7] - A[1] * A[8], i02 = A[1] * A[5] - A[2] * A[4];
+  const double i10 = c01, i11 = A[0] * A[8] - A[2] * A[6], i12 = A[2] * A[3] - A[0] * A[5];
+  const double i20 = c02, i21 = A[1] * A[6] - A[0] * A[7], i22 = A[0] * A[4] - A[1] * A[3];
+  y[0] = (i00 * b[0] + i01 * b[1] + i02 * b[2]) / det;
+  y[1] = (i10 * b[0] + i11 * b[1] + i12 * b[2]) / det;
+  y[2] = (i20 * b[0] + i21 * b[1] + i22 * b[2]) / det;
+  return 1;
+}
+static int clamp_all_boundaries(int dim, double* u) {
+  int cnt = 0;
+  for (int j = 0; j < dim; ++j) {
+    u[j] = u[j] < 0.0 ? 0.0 : (u[j] > 1.0 ? 1.0 : u[j]);
+    if (u[j] == 0.0 || u[j] == 1.0) ++cnt;
+  }
+  return cnt == dim;
+}
+int igo_geometry_local(const igo_patch* P, long npts, const int* elem, const double* xglobal, double* xi_out, int* flag) {
+  const int dim = P->dim, dw = P->dimworld, nb = nb_of(P), nh = dim * (dim + 1) / 2;
+  if (dim != dw && dim > 2) return 1;
+  int nel[MAXDIM]; int* tab[MAXDIM];
+  igo_span_tables(P, nel, tab);
+  double* loc = (double*)malloc(sizeof(double) * nb * (dw + 1));
+  double* work = (double*)malloc(sizeof(double) * 27 * nb);
+  for (long pt = 0; pt < npts; ++pt) {
+    int span[MAXDIM];
+    element_span(P, nel, tab, elem[pt], span);
+    gather_cp(P, span, loc);
+    const double* X = xglobal + pt * dw;
+    double u[MAXDIM], x[3], J[9], H[18];
+    int fl = 0;
+    for (int d = 0; d < dim; ++d) u[d] = 0.5;
+    if (dim == dw) {
+      const double tol = 16.0 * 2.220446049250313e-16;
+      int it = 0;
+      for (;;) {
+        geo012(P, span, loc, u, 1, x, J, H, work);
+        double dg[3], G[9], rhs[3], dx[3];
+        for (int c = 0; c < dw; ++c) dg[c] = x[c] - X[c];
+        for (int a = 0; a < dim; ++a) {
+          double s = 0;
+          for (int c = 0; c < dw; ++c) s += J[a * dw + c] * dg[c];
+          rhs[a] = s;
+          for (int b = 0; b < dim; ++b) { double q = 0; for (int c = 0; c < dw; ++c) q += J[a * dw + c] * J[b * dw + c]; G[a * dim + b] = q; }
+        }
+        if (!solve_small(dim, G, rhs, dx)) { fl = 1; for (int d = 0; d < dim; ++d) u[d] = 1.7976931348623157e308; break; }
+        double n2 = 0;
+        for (int d = 0; d < dim; ++d) { u[d] -= dx[d]; n2 += dx[d] * dx[d]; }
+        if (clamp_all_boundaries(dim, u)) break;
+        if (!(n2 > tol)) break;
+        if (++it >= 100) { fl = 3; break; }
+      }
+    } else {
+      const double tol = 1e-10, domainFraction = 0.25;
+      double R[2], HV[4], energyVal, oldEnergy;
+#define IGO_EGH()                                                                                   \
+  do {                                                                                              \
+    geo012(P, span, loc, u, 2, x, J, H, work);                                                      \
+    double dist[3], e2 = 0;                                                                         \
+    for (int c = 0; c < dw; ++c) { dist[c] = x[c] - X[c]; e2 += dist[c] * dist[c]; }                \
+    for (int a = 0; a < dim; ++a) {                                                                 \
+      double s = 0;                                                                                 \
+      for (int c = 0; c < dw; ++c) s += J[a * dw + c] * dist[c];                                    \
+      R[a] = s;                                                                                     \
+      for (int b = 0; b < dim; ++b) { double q = 0; for (int c = 0; c < dw; ++c) q += J[a * dw + c] * J[b * dw + c]; HV[a * dim + b] = q; } \
+    }                                                                                               \
+    double dd[3];                                                                                   \
+    for (int r = 0; r < nh; ++r) { double s = 0; for (int c = 0; c < dw; ++c) s += H[r * dw + c] * dist[c]; dd[r] = s; } \
+    for (int a = 0; a < dim; ++a) HV[a * dim + a] += dd[a];                                         \
+    if (dim == 2) { HV[1] += dd[2]; HV[2] += dd[2]; }                                               \
+    oldEnergy = 0.5 * e2;                                                                           \
+  } while (0)
+#define IGO_ENERGY(res)                                                                             \
+  do {                                                                                              \
+    geo012(P, span, loc, u, 0, x, J, H, work);                                                      \
+    double e2 = 0;                                                                                  \
+    for (int c = 0; c < dw; ++c) e2 += (x[c] - X[c]) * (x[c] - X[c]);                               \
+    res = 0.5 * e2;                                                                                 \
+  } while (0)
+      IGO_EGH();
+      energyVal = oldEnergy;
+      for (int i = 0; i < 100 && !fl; ++i) {
+        double du[2], mR[2] = {-R[0], dim == 2 ? -R[1] : 0.0};
+        if (!solve_small(dim, HV, mR, du)) { fl = 1; break; }
+        double duNorm = 0;
+        for (int d = 0; d < dim; ++d) duNorm += du[d] * du[d];
+        duNorm = sqrt(duNorm);
+        if (duNorm > domainFraction) for (int d = 0; d < dim; ++d) du[d] *= domainFraction / duNorm;
+        double kappa = 0;
+        for (int a = 0; a < dim; ++a) { double s = 0; for (int b = 0; b < dim; ++b) s += HV[a * dim + b] * du[b]; kappa += du[a] * s; }
+        const int isPD = kappa > 0.0;
+        double uold[2] = {u[0], dim == 2 ? u[1] : 0.0};
+        IGO_ENERGY(oldEnergy);
+        for (int d = 0; d < dim; ++d) u[d] += du[d];
+        if (clamp_all_boundaries(dim, u)) break;
+        for (int j = 0; j < 20; ++j) {
+          IGO_ENERGY(energyVal);
+          if (energyVal > oldEnergy && duNorm > 1e-8) {
+            const double sf = ldexp(1.0, j + 1);
+            for (int d = 0; d < dim; ++d) u[d] = isPD ? uold[d] + du[d] / sf : uold[d] - du[d] / sf;
+          } else
+            break;
+          if (j == 19) fl = 2;
+        }
+        if (fl) break;
+        IGO_EGH();
+        double rn = 0;
+        for (int d = 0; d < dim; ++d) rn += R[d] * R[d];
+        if (sqrt(rn) < tol) break;
+      }
+#undef IGO_EGH
+#undef IGO_ENERGY
+      (void)energyVal;
+      if (fl == 2 || fl == 1) for (int d = 0; d < dim; ++d) u[d] = NAN;
+      else for (int d = 0; d < dim; ++d) u[d] = u[d] < 0.0 ? 0.0 : (u[d] > 1.0 ? 1.0 : u[d]);
+    }
+    for (int d = 0; d < dim; ++d) xi_out[pt * dim + d] = u[d];
+    if (flag) flag[pt] = fl;
+  }
+  free(loc); free(work);
+  for (int d = 0; d < dim; ++d) free(tab[d]);
+  return 0;
+}
+
 int igo_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

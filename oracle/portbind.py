@@ -55,6 +55,9 @@ def lib():
         L.igo_assemble.restype = C.c_int
         L.igo_assemble.argtypes = [PP, C.c_int, dp, C.c_double, C.c_long, C.c_long, ip, dp, dp, dp, dp, C.c_int]
         L.igo_trimmed_rule.argtypes = [C.c_long, dp, C.c_int, dp, dp, dp, dp]
+        L.igo_surface_forms.argtypes = [C.c_int, C.c_int, C.c_long] + [dp] * 7
+        L.igo_geometry_local.restype = C.c_int
+        L.igo_geometry_local.argtypes = [PP, C.c_long, ip, dp, dp, ip]
         L.igo_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -184,6 +187,17 @@ class PortPatch:
         lib().igo_partial(C.byref(self.c), len(elem), _i(elem), _d(xi), _i(_i32(alpha)), _d(out))
         return out
 
+    def local(self, elem, xglobal):
+        """NURBSGeometry::local per point (nurbsgeometry.hh:145-176): element-local xi and a flag per point."""
+        elem = _i32(elem)
+        X = _f64(xglobal).reshape(len(elem), self.dimworld)
+        xi = np.empty((len(elem), self.dim))
+        flag = np.empty(len(elem), np.int32)
+        rc = lib().igo_geometry_local(C.byref(self.c), len(elem), _i(elem), _d(X), _d(xi), _i(flag))
+        if rc:
+            raise ValueError("local: unsupported (dim, dimworld)")
+        return xi, flag
+
     def volume(self, xi1d, w1d, nthreads=0):
         nq1 = _i32([len(x) for x in xi1d])
         return lib().igo_volume(C.byref(self.c), _i(nq1), _d(_f64(np.concatenate(xi1d))),
@@ -236,6 +250,18 @@ def trimmed_rule(tri, ref_pts, ref_w):
     xi, w = np.empty((n, 2)), np.empty(n)
     lib().igo_trimmed_rule(tri.shape[0], _d(tri), len(ref_w), _d(ref_pts), _d(ref_w), _d(xi), _d(w))
     return xi, w
+
+
+def surface_forms(Jt, H=None, want=("normal", "unitNormal", "metric", "secondFF", "gaussK")):
+    """nurbsgeometry.hh:216-255 from Jt [npts][dim][dw] and H [npts][nh][dw]."""
+    Jt = _f64(Jt)
+    npts, dim, dw = Jt.shape
+    H = _f64(H) if H is not None else None
+    shapes = dict(normal=(npts, 3), unitNormal=(npts, 3), metric=(npts, dim, dim), secondFF=(npts, 2, 2), gaussK=(npts,))
+    out = {k: (np.empty(shapes[k]) if k in want else None) for k in shapes}
+    lib().igo_surface_forms(dim, dw, npts, _d(Jt), _d(H), _d(out["normal"]), _d(out["unitNormal"]), _d(out["metric"]),
+                            _d(out["secondFF"]), _d(out["gaussK"]))
+    return {k: v for k, v in out.items() if v is not None}
 
 
 def max_threads():

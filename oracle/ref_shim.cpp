@@ -422,6 +422,29 @@ void oref_patchgeo_012(void* h, const double* u, double* pos, double* Jt, double
   });
 }
 
+// NURBSPatchGeometry::local (dune/iga/nurbspatchgeometry.hh:126-158): Newton for dim == dimworld, the trust-region
+// closest-point projection (dune/iga/geometry/closestpointprojection.hh) for curves and surfaces in a larger space.
+// Returns 0, or 1 when the reference threw (Dune::MathError: no energy-decreasing direction / singular matrix).
+int oref_patchgeo_local(void* h, const double* xglobal, double* u) {
+  return dispatch(static_cast<PatchBase*>(h), [&](auto* P) {
+    constexpr int dim = std::remove_pointer_t<decltype(P)>::Data::patchDim;
+    constexpr int dw  = std::remove_pointer_t<decltype(P)>::Data::dimworld;
+    if constexpr (dim == dw || dim <= 2) {
+      NURBSPatchGeometry<dim, dw> geo(P->data);
+      FieldVector<double, dw> g;
+      for (int j = 0; j < dw; ++j) g[j] = xglobal[j];
+      try {
+        auto r = geo.local(g);
+        for (int d = 0; d < dim; ++d) u[d] = r[d];
+      } catch (...) {
+        return 1;
+      }
+      return 0;
+    } else
+      return 2;
+  });
+}
+
 double oref_patchgeo_volume(void* h, int scaleOrder) {
   return dispatch(static_cast<PatchBase*>(h), [&](auto* P) {
     constexpr int dim = std::remove_pointer_t<decltype(P)>::Data::patchDim;

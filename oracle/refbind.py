@@ -52,6 +52,8 @@ def lib():
         L.oref_patchgeo_detj.restype = C.c_double
         L.oref_patchgeo_detj.argtypes = [C.c_void_p, dp]
         L.oref_patchgeo_012.argtypes = [C.c_void_p, dp, dp, dp, dp]
+        L.oref_patchgeo_local.restype = C.c_int
+        L.oref_patchgeo_local.argtypes = [C.c_void_p, dp, dp]
         L.oref_patchgeo_volume.restype = C.c_double
         L.oref_patchgeo_volume.argtypes = [C.c_void_p, C.c_int]
         L.oref_eval_tensor.restype = C.c_int
@@ -176,6 +178,12 @@ class RefPatch:
 
     def volume(self, scale_order=1):
         return lib().oref_patchgeo_volume(self.h, scale_order)
+
+    def geo_local(self, xglobal):
+        """NURBSPatchGeometry::local (nurbspatchgeometry.hh:126-158); patch coordinates.  None when the reference threw."""
+        out = np.empty(self.dim)
+        rc = lib().oref_patchgeo_local(self.h, _d(_f64(xglobal)), _d(out))
+        return out if rc == 0 else None
 
     def _alloc(self, npts, order, want):
         nh = self.dim * (self.dim + 1) // 2

@@ -80,7 +80,9 @@ out["geometry_curve"] = {
     "global": [[[0.0], [-4, -4]], [[0.5], [-1.32, 0.72]], [[1.0], [4, 4]],
                [[0.25], [-2.7607655502392343, 0.4688995215311005]],
                [[0.4], [-1.9854368932038828, 0.7669902912621357]]],
-    "jacobianTransposed": [[[0.0], [[7.5, 51]]], [[0.5], [[7.4496, -0.9216]]]]}
+    "jacobianTransposed": [[[0.0], [[7.5, 51]]], [[0.5], [[7.4496, -0.9216]]]],
+    # geometry.local(x) == u (trimmedgridtests.cpp:90-95)
+    "local": [[[-4, -4], [0.0]], [[-1.32, 0.72], [0.5]]]}
 out["geometry_surface"] = {
     "cite": "trimmedgridtests.cpp:112-186", "degree": [2, 2], "knots": [[0, 0, 0, 1, 1, 1], [0, 0, 0, 1, 1, 1]],
     "dimworld": 3,
@@ -90,7 +92,9 @@ out["geometry_surface"] = {
                     [[0, 2, 1, 1], [1, 2, 2, 1], [2, 2, 2, 1]]],
     "global": [[[0.5, 0.5], [1.0, 1.0, 0.75]], [[0, 0], [0, 0, 1]], [[0, 1], [2, 0, 2]]],
     "jacobianTransposed": [[[0.5, 0.5], [[0.0, 2.0, 0.5], [2.0, 0.0, 0.5]]]],
-    "corners": [[0, 0, 1], [0, 2, 1], [2, 0, 2], [2, 2, 2]]}
+    "corners": [[0, 0, 1], [0, 2, 1], [2, 0, 2], [2, 2, 2]],
+    # geometry.local(x) == u (trimmedgridtests.cpp:157-162)
+    "local": [[[1.0, 1.0, 0.75], [0.5, 0.5]], [[2, 0, 2], [0, 1]]]}
 
 # --- degreeElevate by 2 of a p=2 rational curve (gridtests.cpp:1136-1166,1203-1221), tolerance 1e-10
 out["degree_elevate_curve"] = {

@@ -543,3 +543,102 @@ def test_misaligned_device_outputs(name):
     torch.cuda.synchronize()
     for f in fields:
         assert np.array_equal(out[f].cpu().numpy(), host[f]), f
+
+
+def test_surface_forms_match_oracle_and_gauss_bonnet():
+    """normal / unitNormal / metric / secondFundamentalForm / gaussianCurvature (nurbsgeometry.hh:216-255) on the device
+    from the Jt / H arrays of the evaluation kernel: oracle parity, Gauss-Bonnet (gridtests.cpp:348-363), host and
+    device-resident arrays give the same bits."""
+    import torch
+    t = G["torus"]
+    spec = PFT.small_patch("torus_p2", level=2)
+    P = gpu_patch(spec)
+    x, w = PD.gaussLegendre01(3)
+    o = P.evalTensor([x, x], order=2, want=("Jt", "H", "detJ"))
+    got = capi.surfaceForms(o["Jt"], o["H"])
+    ref = PT.surface_forms(o["Jt"], o["H"])
+    for k in ("normal", "unitNormal", "metric", "secondFF", "gaussK"):
+        assert relerr(got[k], ref[k]) <= TOL, (k, relerr(got[k], ref[k]))
+    ww = np.tile(np.outer(w, w).reshape(-1), P.nelem)
+    assert abs((got["gaussK"] * o["detJ"] * ww).sum()) < t["gauss_bonnet_tol"]
+    dev = capi.surfaceForms(torch.from_numpy(o["Jt"]).cuda(), torch.from_numpy(o["H"]).cuda())
+    torch.cuda.synchronize()
+    for k in got:
+        assert np.array_equal(dev[k].cpu().numpy(), got[k]), k
+    # metric alone works for every (dim, dimworld); the surface quantities do not
+    spec3 = PFT.small_patch("cylinder_p3")
+    P3 = gpu_patch(spec3)
+    g3 = gauss(spec3)
+    J3 = P3.evalTensor(g3, order=1, want=("Jt",))["Jt"]
+    m3 = capi.surfaceForms(J3, want=("metric",))["metric"]
+    assert relerr(m3, np.einsum("pac,pbc->pab", J3, J3)) <= TOL
+    with pytest.raises(capi.IgabError) as ei:
+        capi.surfaceForms(J3, want=("normal",))
+    assert ei.value.status == capi.UNSUPPORTED
+    with pytest.raises(capi.IgabError):
+        capi.surfaceForms(o["Jt"], None, want=("gaussK",))
+
+
+def _literal_patches():
+    c = G["geometry_curve"]
+    s = G["geometry_surface"]
+    cps = np.array([[s["cp_table_ij"][i][j] for i in range(3)] for j in range(3)], float).reshape(9, 4)
+    return (c, np.array(c["cp"], float)), (s, cps)
+
+
+def test_geometry_local_literals_through_cuda():
+    """trimmedgridtests.cpp:90-95,157-162: geometry.local(x) == u for the curve and the surface."""
+    for spec, cp in _literal_patches():
+        P = capi.Patch(spec["degree"], spec["knots"], cp, spec["dimworld"])
+        for x, u in spec["local"]:
+            xi, flag = P.local([0], [x])
+            assert flag[0] == 0 and np.abs(xi[0] - np.array(u, float)).max() <= 64 * np.finfo(float).eps, (x, u, xi)
+
+
+@pytest.mark.parametrize("name", ["square_p3", "cylinder_p3", "curve_p3", "torus_p2", "mixed_deg_3d"])
+def test_geometry_local_matches_oracle(name):
+    """Batched NURBSGeometry::local on the device vs the port oracle: images of random element-local points (round trip,
+    gridtests.cpp:1085-1100: corners to 1e-14) and, for curves / surfaces, off-manifold targets through the trust-region
+    projection (closestpointprojection.hh).  Tolerance on xi: 1e-12 where the iteration converged quadratically; the
+    projection stops at |grad E| < 1e-10, so off-manifold targets are compared at 1e-8 with a median <= 1e-13."""
+    spec = PFT.small_patch(name)
+    Pp = port_for(spec)
+    P = gpu_patch(spec)
+    rng = np.random.default_rng(17)
+    dim, dw = Pp.dim, Pp.dimworld
+    corners = np.array([[(k >> d) & 1 for d in range(dim)] for k in range(2 ** dim)], float)
+    per = len(corners) + 4
+    elem = np.repeat(np.arange(Pp.nelem, dtype=np.int32), per)
+    xi = np.concatenate([np.concatenate([corners, rng.uniform(0.05, 0.95, (4, dim))]) for _ in range(Pp.nelem)])
+    X = Pp.eval_points(elem, xi, order=0, want=("x",))["x"]
+    got, flag = P.local(elem, X)
+    ref, rflag = Pp.local(elem, X)
+    assert np.array_equal(flag, rflag) and (flag == 0).all()
+    assert np.abs(got - ref).max() <= 1e-12
+    if name != "torus_p2":  # the torus parametrisation is periodic: corners of neighbouring elements share images
+        assert np.abs(got - xi).max() <= (1e-12 if dim == dw else 1e-9)
+    if dim < dw:
+        Xo = X + rng.normal(0, 0.05, X.shape)
+        got, flag = P.local(elem, Xo)
+        ref, rflag = Pp.local(elem, Xo)
+        same = flag == rflag
+        assert same.mean() >= 0.98
+        ok = same & (flag == 0)
+        d = np.abs(got[ok] - ref[ok])
+        assert d.max() <= 1e-8 and np.median(d) <= 1e-13, (d.max(), np.median(d))
+        assert np.isnan(got[flag == 2]).all()
+
+
+def test_geometry_local_errors_and_singular_jacobian():
+    spec = PFT.small_patch("square_p3")
+    P = gpu_patch(spec)
+    with pytest.raises(capi.IgabError) as ei:
+        P.local([P.nelem], [[0.0, 0.0]])
+    assert ei.value.status == capi.INVALID_ARGUMENT
+    xi, flag = P.local(np.zeros(0, np.int32), np.zeros((0, 2)))
+    assert xi.shape == (0, 2)
+    # a degenerate element (all control points equal): singular Jacobian -> numeric_limits::max (nurbsgeometry.hh:163-164)
+    k = [0, 0, 1, 1.0]
+    Pd = capi.Patch([1, 1], [k, k], np.array([[1, 1, 1.0]] * 4), 2)
+    xi, flag = Pd.local([0], [[2.0, 2.0]])
+    assert flag[0] == 1 and (xi[0] == np.finfo(float).max).all()

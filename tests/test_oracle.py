@@ -211,3 +211,91 @@ def test_assembly_port_properties():
     Me, _ = P.assemble(1, [x, x], [w, w])
     assert abs(Me.sum() - P.volume([x, x], [w, w])) < 1e-12
     assert abs(fe.sum() - P.volume([x, x], [w, w])) < 1e-12
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_geometry_local_literals(impl):
+    """trimmedgridtests.cpp:90-95,157-162: geometry.local(x) of the curve and the surface.  The port restates the
+    element-level NURBSGeometry::local, which coincides with the patch-level one on these one-element patches."""
+    c = G["geometry_curve"]
+    s = G["geometry_surface"]
+    cp = np.array([[s["cp_table_ij"][i][j] for i in range(3)] for j in range(3)], float).reshape(9, 4)
+    for spec, cpn in ((c, c["cp"]), (s, cp)):
+        P = make(impl, spec["degree"], spec["knots"], cpn, spec["dimworld"])
+        for x, u in spec["local"]:
+            got = P.local([0], [x])[0][0] if impl == "port" else P.geo_local(x)
+            assert close(got, u), (x, u, got)
+
+
+@needs_ref
+def test_geometry_local_port_matches_reference():
+    """NURBSPatchGeometry::local compiled from the reference vs the port, seeded targets on one-element patches:
+    Newton branch (2-D in 2-D, 3-D in 3-D) and trust-region projection (curve in 2-D, surface in 3-D)."""
+    rng = np.random.default_rng(11)
+    c = G["geometry_curve"]
+    s = G["geometry_surface"]
+    cps = np.array([[s["cp_table_ij"][i][j] for i in range(3)] for j in range(3)], float).reshape(9, 4)
+    k2 = [0, 0, 0, 1, 1, 1.0]
+    quad = np.array([[x + 0.2 * y * y, y + 0.1 * x * y, 1 + 0.3 * x * (1 - y)] for y in (0, .5, 1) for x in (0, .6, 1)])
+    hexa = np.array([[x + 0.1 * z, y + 0.2 * x * z, z + 0.1 * y * y, 1 + 0.2 * x * y * z]
+                     for z in (0, .5, 1) for y in (0, .5, 1) for x in (0, .4, 1)])
+    cases = [(c["degree"], c["knots"], np.array(c["cp"], float), 2, (-5, 5)),
+             (s["degree"], s["knots"], cps, 3, (-0.5, 2.5)),
+             ([2, 2], [k2, k2], quad, 2, (-0.2, 1.3)),
+             ([2, 2, 2], [k2, k2, k2], hexa, 3, (-0.1, 1.2))]
+    for degree, knots, cp, dw, (lo, hi) in cases:
+        Pp = PT.PortPatch(degree, knots, cp, dw)
+        Pr = RF.RefPatch.create(degree, knots, cp, dw)
+        X = rng.uniform(lo, hi, (120, dw))
+        if len(degree) == dw:
+            # Newton branch: targets inside the image only -- the reference's patch-level loop has no iteration cap and
+            # does not terminate for points it cannot reach (nurbspatchgeometry.hh:136-155)
+            X = np.array([Pr.geo_global(u) for u in rng.uniform(0, 1, (120, dw))])
+        xi, flag = Pp.local(np.zeros(len(X), np.int32), X)
+        ref = [Pr.geo_local(x) for x in X]
+        threw = np.array([r is None for r in ref])
+        # failures (MathError in the reference) coincide up to comparisons that sit on a rounding boundary
+        assert (threw != (flag != 0)).sum() <= 2
+        ok = ~threw & (flag == 0)
+        assert ok.sum() >= 40
+        d = np.abs(xi[ok] - np.array([r for r, o in zip(ref, ok) if o]))
+        assert d.max() <= 1e-9, d.max()
+        assert np.median(d) <= 1e-14
+
+
+def test_geometry_local_round_trip_port():
+    """gridtests.cpp:1085-1100: local(global(corner)) == corner to 1e-14, here for corners and interior points of every
+    element of a perturbed square and of the cylinder solid (the plate with a hole has a singular corner, where Newton
+    converges only linearly)."""
+    rng = np.random.default_rng(5)
+    for name in ("square_p3", "cylinder_p3"):
+        spec = PFT.small_patch(name)
+        P = PT.PortPatch(spec["degree"], spec["knots"], spec["cp"], spec["dimworld"])
+        dim = P.dim
+        corners = np.array([[(k >> d) & 1 for d in range(dim)] for k in range(2 ** dim)], float)
+        elem = np.repeat(np.arange(P.nelem, dtype=np.int32), len(corners) + 3)
+        xi = np.concatenate([np.concatenate([corners, rng.uniform(0.05, 0.95, (3, dim))]) for _ in range(P.nelem)])
+        X = P.eval_points(elem, xi, order=0, want=("x",))["x"]
+        got, flag = P.local(elem, X)
+        assert (flag == 0).all()
+        assert np.abs(got - xi).max() < 1e-12
+
+
+def test_surface_forms_port_on_torus_and_sphere_like_patch():
+    """nurbsgeometry.hh:216-255 through the port: Gauss-Bonnet on the torus (gridtests.cpp:348-363), unit normals
+    orthogonal to both tangents, metric = J J^T, and K = 1/R^2 on a surface of revolution that is a sphere."""
+    t = G["torus"]
+    spec = PFT.small_patch("torus_p2", level=2)
+    Pp = PT.PortPatch(spec["degree"], spec["knots"], spec["cp"], 3)
+    x, w = PT.gauss01(3)
+    o = Pp.eval_tensor([x, x], order=2)
+    f = PT.surface_forms(o["Jt"], o["H"])
+    ww = np.tile(np.outer(w, w).reshape(-1), Pp.nelem)
+    assert abs((f["gaussK"] * o["detJ"] * ww).sum()) < t["gauss_bonnet_tol"]
+    assert np.abs((f["unitNormal"][:, None, :] * o["Jt"]).sum(2)).max() < 1e-13
+    assert np.abs(np.linalg.norm(f["unitNormal"], axis=1) - 1).max() < 1e-14
+    assert np.abs(f["metric"] - np.einsum("pac,pbc->pab", o["Jt"], o["Jt"])).max() < 1e-13
+    assert np.abs(np.sqrt(np.linalg.det(f["metric"])) - o["detJ"]).max() < 1e-12
+    assert np.abs(f["secondFF"][:, 0, 1] - f["secondFF"][:, 1, 0]).max() == 0.0
+    r, R = t["r"], t["R"]
+    assert f["gaussK"].min() >= -1 / (r * (R - r)) - 1e-8 and f["gaussK"].max() <= 1 / (r * (R + r)) + 1e-8
