@@ -16,6 +16,9 @@
 //   NURBSGeometry::integrationElement   dune/iga/nurbsgeometry.hh:200-203  Geometry::integrationElement
 //   NURBSGeometry::jacobianInverseTransposed  nurbsgeometry.hh:205-210     Geometry::jacobianInverseTransposed
 //   NURBSGeometry::volume               dune/iga/nurbsgeometry.hh:96-113   Geometry::volume
+//   NURBSGeometry::local                dune/iga/nurbsgeometry.hh:145-176  Geometry::local
+//   NURBSGeometry::secondDerivativeOfPosition / zeroFirstAndSecond...  :257-354  same names
+//   NURBSGeometry::normal/unitNormal/metric/secondFundamentalForm/gaussianCurvature  :216-255  same names
 //   NURBSGridEntity::getQuadratureRule  dune/iga/nurbsgridentity.hh:120-141 Patch::setQuadratureRule (rule is an input)
 //
 // How it works: Patch::setQuadratureRule(rule) evaluates EVERY point of EVERY element once on the GPU
@@ -34,6 +37,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/igab200.h"
@@ -357,6 +361,100 @@ public:
     for (int64_t q = 0; q < p_->pointsPerElement(); ++q) v += p_->detJ(e_, q) * p_->weight(q);
     return v;
   }
+  // J = (J^T)^T and its pseudo-inverse (nurbsgeometry.hh:198,212-214)
+  template <class Local>
+  std::array<std::array<double, dim>, dimworld> jacobian(const Local& local) const {
+    const auto jt = jacobianTransposed(local);
+    std::array<std::array<double, dim>, dimworld> r;
+    for (int c = 0; c < dimworld; ++c)
+      for (int d = 0; d < dim; ++d) r[c][d] = jt[d][c];
+    return r;
+  }
+  template <class Local>
+  JacobianTransposed jacobianInverse(const Local& local) const {
+    const auto jit = jacobianInverseTransposed(local);
+    JacobianTransposed r;
+    for (int d = 0; d < dim; ++d)
+      for (int c = 0; c < dimworld; ++c) r[d][c] = jit[c][d];
+    return r;
+  }
+  // rows [uu, vv(, ww), uv(, uw, vw)] of d^2 x / d xi^2 (nurbsgeometry.hh:257-292)
+  using Hessian = std::array<std::array<double, dimworld>, dim*(dim + 1) / 2>;
+  template <class Local>
+  Hessian secondDerivativeOfPosition(const Local& local) const {
+    constexpr int nh = dim * (dim + 1) / 2;
+    double buf[nh * dimworld];
+    const double* s = buf;
+    const int64_t q = p_->derivOrder() >= 2 ? p_->findRulePoint(local) : -1;
+    if (q >= 0)
+      s = p_->H(e_, q);
+    else {
+      igab_eval_out o{};
+      o.H = buf;
+      p_->evalPoint(e_, local, 2, o);
+    }
+    Hessian r;
+    for (int k = 0; k < nh; ++k)
+      for (int c = 0; c < dimworld; ++c) r[k][c] = s[k * dimworld + c];
+    return r;
+  }
+  // nurbsgeometry.hh:304-354
+  template <class Local>
+  std::tuple<GlobalCoordinate, JacobianTransposed, Hessian> zeroFirstAndSecondDerivativeOfPosition(
+      const Local& local) const {
+    return {global(local), jacobianTransposed(local), secondDerivativeOfPosition(local)};
+  }
+
+  // differential geometry of surfaces (nurbsgeometry.hh:216-255), evaluated on the device from J^T and H
+  template <class Local>
+  GlobalCoordinate normal(const Local& local) const {
+    static_assert(dim == 2 && dimworld == 3, "normal: surfaces in R^3 only");
+    GlobalCoordinate r;
+    forms(local, false, r.data(), nullptr, nullptr, nullptr, nullptr);
+    return r;
+  }
+  template <class Local>
+  GlobalCoordinate unitNormal(const Local& local) const {
+    static_assert(dim == 2 && dimworld == 3, "unitNormal: surfaces in R^3 only");
+    GlobalCoordinate r;
+    forms(local, false, nullptr, r.data(), nullptr, nullptr, nullptr);
+    return r;
+  }
+  template <class Local>
+  std::array<std::array<double, dim>, dim> metric(const Local& local) const {
+    std::array<std::array<double, dim>, dim> r;
+    forms(local, false, nullptr, nullptr, &r[0][0], nullptr, nullptr);
+    return r;
+  }
+  template <class Local>
+  std::array<std::array<double, 2>, 2> secondFundamentalForm(const Local& local) const {
+    static_assert(dim == 2 && dimworld == 3, "secondFundamentalForm: surfaces in R^3 only");
+    std::array<std::array<double, 2>, 2> r;
+    forms(local, true, nullptr, nullptr, nullptr, &r[0][0], nullptr);
+    return r;
+  }
+  template <class Local>
+  double gaussianCurvature(const Local& local) const {
+    static_assert(dim == 2 && dimworld == 3, "gaussianCurvature: surfaces in R^3 only");
+    double r = 0;
+    forms(local, true, nullptr, nullptr, nullptr, nullptr, &r);
+    return r;
+  }
+
+  // inverse map (nurbsgeometry.hh:145-176): Newton for dim == dimworld, closest-point projection otherwise; the
+  // reference's MathError ("no energy decreasing direction") becomes igab::Error
+  template <class Global>
+  std::array<double, dim> local(const Global& global) const {
+    double X[dimworld];
+    for (int c = 0; c < dimworld; ++c) X[c] = global[c];
+    std::array<double, dim> r;
+    const int32_t el = (int32_t)e_;
+    int32_t flag = 0;
+    check(igab_geometry_local(p_->handle(), 1, &el, X, r.data(), &flag, IGAB_HOST, nullptr));
+    if (flag == 2) throw Error(IGAB_OK, "local: no energy-decreasing direction (Dune::MathError in the reference)");
+    return r;
+  }
+
   int corners() const { return 1 << dim; }
   GlobalCoordinate corner(int k) const {
     std::array<double, dim> l;
@@ -371,6 +469,14 @@ public:
   bool affine() const { return false; }
 
 private:
+  template <class Local>
+  void forms(const Local& local, bool needH, double* n, double* un, double* g, double* b, double* K) const {
+    const auto jt = jacobianTransposed(local);
+    Hessian h{};
+    if (needH) h = secondDerivativeOfPosition(local);
+    check(igab_surface_forms(dim, dimworld, 1, &jt[0][0], needH ? &h[0][0] : nullptr, n, un, g, b, K, IGAB_HOST,
+                             nullptr));
+  }
   const Patch<dim, dimworld>* p_ = nullptr;
   int64_t e_ = 0;
 };

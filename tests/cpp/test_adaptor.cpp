@@ -176,6 +176,53 @@ int main() {
   } catch (const igab::Error& e) { threw = e.status == IGAB_INVALID_ARGUMENT; }
   CHECK(threw, "closed knot vector must be rejected");
 
+  // Geometry::local round trip on the plate (gridtests.cpp:1085-1100, away from the degenerate corner)
+  {
+    igab::Geometry<dim, dw> geo(patch.get(), 0);
+    const std::array<double, dim> xi{0.3, 0.6};
+    const auto X = geo.global(xi);
+    const auto back = geo.local(X);
+    CHECK(std::fabs(back[0] - xi[0]) < 1e-13 && std::fabs(back[1] - xi[1]) < 1e-13, "local(global(xi)) %g %g", back[0], back[1]);
+    const auto J = geo.jacobian(xi);
+    const auto Jt2 = geo.jacobianTransposed(xi);
+    CHECK(J[1][0] == Jt2[0][1], "jacobian is the transpose");
+    const auto g = geo.metric(xi);
+    CHECK(std::fabs(g[0][1] - (Jt2[0][0] * Jt2[1][0] + Jt2[0][1] * Jt2[1][1])) < 1e-13, "metric");
+  }
+  // surface of trimmedgridtests.cpp:112-186: literals of local(), plus the surface forms
+  {
+    igab::PatchData<2, 3> sd;
+    sd.degree = {2, 2};
+    sd.knotSpans[0] = sd.knotSpans[1] = {0, 0, 0, 1, 1, 1};
+    const double tab[3][3][3] = {{{0, 0, 1}, {1, 0, 1}, {2, 0, 2}}, {{0, 1, 0}, {1, 1, 0}, {2, 1, 0}}, {{0, 2, 1}, {1, 2, 2}, {2, 2, 2}}};
+    for (int j = 0; j < 3; ++j)
+      for (int i = 0; i < 3; ++i) {
+        for (int c = 0; c < 3; ++c) sd.controlPoints.push_back(tab[i][j][c]);
+        sd.controlPoints.push_back(1.0);
+      }
+    auto sp = std::make_shared<igab::Patch<2, 3>>(sd);
+    igab::Geometry<2, 3> geo(sp.get(), 0);
+    const auto u1 = geo.local(std::array<double, 3>{1.0, 1.0, 0.75});
+    CHECK(std::fabs(u1[0] - 0.5) < 1e-14 && std::fabs(u1[1] - 0.5) < 1e-14, "surface local u1 %g %g", u1[0], u1[1]);
+    const auto u2 = geo.local(std::array<double, 3>{2, 0, 2});
+    CHECK(u2[0] == 0.0 && u2[1] == 1.0, "surface local u2 %g %g", u2[0], u2[1]);
+    const std::array<double, 2> mid{0.5, 0.5};
+    const auto Jt = geo.jacobianTransposed(mid);  // {0,2,.5},{2,0,.5}
+    const auto N = geo.normal(mid);
+    CHECK(std::fabs(N[0] - 1.0) < 1e-14 && std::fabs(N[1] - 1.0) < 1e-14 && std::fabs(N[2] + 4.0) < 1e-14, "normal %g %g %g", N[0], N[1], N[2]);
+    const auto n = geo.unitNormal(mid);
+    CHECK(std::fabs(n[0] * n[0] + n[1] * n[1] + n[2] * n[2] - 1.0) < 1e-15, "unit normal");
+    CHECK(std::fabs(n[0] * Jt[0][0] + n[1] * Jt[0][1] + n[2] * Jt[0][2]) < 1e-15, "normal orthogonal to tangent");
+    const auto H = geo.secondDerivativeOfPosition(mid);
+    const auto b = geo.secondFundamentalForm(mid);
+    CHECK(std::fabs(b[0][1] - (H[2][0] * n[0] + H[2][1] * n[1] + H[2][2] * n[2])) < 1e-14 && b[0][1] == b[1][0], "second fundamental form");
+    const auto g = geo.metric(mid);
+    const double K = geo.gaussianCurvature(mid);
+    CHECK(std::fabs(K - (b[0][0] * b[1][1] - b[0][1] * b[1][0]) / (g[0][0] * g[1][1] - g[0][1] * g[1][0])) < 1e-14, "gaussian curvature");
+    auto [x0, J0, H0] = geo.zeroFirstAndSecondDerivativeOfPosition(mid);
+    CHECK(std::fabs(x0[2] - 0.75) < 1e-15 && J0[0][1] == Jt[0][1] && H0[0][0] == H[0][0], "zeroFirstAndSecondDerivativeOfPosition");
+  }
+
   std::printf(failures ? "adaptor test: %d FAILURES\n" : "adaptor test: ok\n", failures);
   return failures ? 1 : 0;
 }
