@@ -24,7 +24,7 @@ EXPORTS = ("igab_last_error_string", "igab_version", "igab_launch_count", "igab_
            "igab_patch_create", "igab_patch_destroy", "igab_patch_sizes", "igab_patch_set_kernel",
            "igab_patch_update_control_points", "igab_patch_spans", "igab_patch_dofmap", "igab_eval_tensor",
            "igab_eval_points", "igab_partial", "igab_assemble", "igab_reduce_volume", "igab_csr_pattern",
-           "igab_csr_assemble", "igab_eval_faces", "igab_refine_apply", "igab_surface_forms", "igab_geometry_local")
+           "igab_csr_assemble", "igab_eval_faces", "igab_refine_apply", "igab_surface_forms", "igab_geometry_local", "igab_reduce_norms")
 
 
 class EvalOut(C.Structure):
@@ -74,6 +74,8 @@ def lib():
         L.igab_surface_forms.argtypes = [C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p]
         L.igab_geometry_local.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                           C.c_void_p]
+        L.igab_reduce_norms.argtypes = [C.c_void_p, C.c_int64, C.c_int64, ip, C.POINTER(dp), C.POINTER(dp), C.c_void_p,
+                                        C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
         L.igab_refine_apply.argtypes = [C.c_int, C.c_int, ip, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, dp, dp,
                                         dp]
         L.igab_reduce_volume.argtypes = [C.c_void_p, C.c_int64, C.c_int64, ip, C.POINTER(dp), C.POINTER(dp),
@@ -382,6 +384,22 @@ class Patch:
         _check(lib().igab_reduce_volume(self.h, elem_begin, elem_end, nq1.ctypes.data_as(ip), xp, wp, C.byref(r),
                                         nccl_comm, stream))
         return r.value
+
+    def norms(self, xi1d, w1d, u, ncomp=1, elem_begin=0, elem_end=None, nccl_comm=None, stream=None):
+        """(sum w detJ |u_h|^2, sum w detJ |grad u_h|^2) of the discrete field with coefficients u [ndof*ncomp] (numpy
+        or CUDA tensor) over the elements [elem_begin, elem_end): squared L2 norm and energy, one fused pass."""
+        if elem_end is None:
+            elem_end = self.nelem
+        if isinstance(u, np.ndarray):
+            u = _f64(u)
+        ua, us = _ptr(u)
+        xa, xp = _rule_arrays(xi1d)
+        wa, wp = _rule_arrays(w1d)
+        nq1 = _i32([len(a) for a in xa])
+        r = (C.c_double * 2)()
+        _check(lib().igab_reduce_norms(self.h, elem_begin, elem_end, nq1.ctypes.data_as(ip), xp, wp, ua, ncomp, us, r,
+                                       nccl_comm, stream))
+        return np.array([r[0], r[1]])
 
 
 def surfaceForms(Jt, H=None, want=("normal", "unitNormal", "metric", "secondFF", "gaussK"), stream=None):

@@ -384,6 +384,7 @@ void igab_patch_destroy(igab_patch* p) {
   if (p->d_trim) cudaFree(p->d_trim);
   if (p->d_rule) cudaFree(p->d_rule);
   if (p->d_red) cudaFree(p->d_red);
+  if (p->d_norm) cudaFree(p->d_norm);
   for (int b = 0; b < 2; ++b) {
     if (p->stage_buf[b]) cudaFree(p->stage_buf[b]);
     if (p->stage_done[b]) cudaEventDestroy(p->stage_done[b]);
@@ -1001,6 +1002,57 @@ igab_status igab_reduce_volume(igab_patch* p, int64_t elem_begin, int64_t elem_e
     }
   }
   IGAB_CUDA_TRY(cudaMemcpyAsync(result, res_dev, sizeof(double), cudaMemcpyDeviceToHost, stream));
+  IGAB_CUDA_TRY(cudaStreamSynchronize(stream));
+  return IGAB_OK;
+}
+
+igab_status igab_reduce_norms(igab_patch* p, int64_t elem_begin, int64_t elem_end, const int* nq1,
+                              const double* const* xi1d, const double* const* w1d, const double* u, int ncomp,
+                              igab_memspace u_space, double* result, void* nccl_comm, void* stream_) {
+  if (!p || !nq1 || !xi1d || !w1d || !u || !result) {
+    set_error("reduce_norms: null argument");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  if (elem_begin < 0 || elem_end < elem_begin || elem_end > p->dev.nelem) {
+    set_error("reduce_norms: element range outside [0, n_elem]");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  if (!p->htrim.empty()) {
+    set_error("reduce_norms: trimmed patches are not supported (compacted DOF numbering)");
+    return IGAB_UNSUPPORTED;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RuleDev rule;
+  igab_status st = stage_rule(p, nq1, xi1d, w1d, &rule, stream);
+  if (st) return st;
+  const int npartial = 1024;
+  if (!p->d_norm) IGAB_CUDA_TRY(cudaMalloc(&p->d_norm, sizeof(double) * (2 * npartial + 2)));
+  double* res_dev = p->d_norm + 2 * npartial;
+  const double* u_dev = u;
+  double* u_tmp = nullptr;
+  if (u_space == IGAB_HOST) {
+    const size_t bytes = sizeof(double) * (size_t)p->ndof_untrimmed * ncomp;
+    IGAB_CUDA_TRY(cudaMallocAsync(&u_tmp, bytes, stream));
+    IGAB_CUDA_TRY(cudaMemcpyAsync(u_tmp, u, bytes, cudaMemcpyHostToDevice, stream));
+    u_dev = u_tmp;
+  }
+  st = launch_norms(p->dev, elem_begin, elem_end - elem_begin, nq1, rule.xi, rule.w, u_dev, ncomp, p->d_norm, npartial,
+                    res_dev, stream);
+  if (u_tmp) cudaFreeAsync(u_tmp, stream);
+  if (st) return st;
+  if (nccl_comm) {
+    nccl_allreduce_fn ar = resolve_nccl_allreduce();
+    if (!ar) {
+      set_error("reduce_norms: NCCL communicator given but libnccl.so.2 could not be resolved");
+      return IGAB_NCCL_ERROR;
+    }
+    const int rc = ar(res_dev, res_dev, 2, 8, 0, nccl_comm, stream);  // ncclDouble, ncclSum
+    if (rc != 0) {
+      set_error("reduce_norms: ncclAllReduce failed with code " + std::to_string(rc));
+      return IGAB_NCCL_ERROR;
+    }
+  }
+  IGAB_CUDA_TRY(cudaMemcpyAsync(result, res_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
   IGAB_CUDA_TRY(cudaStreamSynchronize(stream));
   return IGAB_OK;
 }

@@ -115,6 +115,9 @@ igab_status refine_apply(int dim, int dw, const int* ncp_old, int direction, int
                          const int* len, const double* coef, const double* cp_in, double* cp_out, cudaStream_t stream);
 igab_status eval_faces_device(igab_patch* p, long long nfaces, const int* elem, const int* face, const int* nqf1,
                               const double* const* xi_dev, double* x, double* normal, double* dS, cudaStream_t stream);
+igab_status launch_norms(const PatchDev& P, long long elem_begin, long long nelem, const int* nq1,
+                         const double* const* xi1d_dev, const double* const* w1d_dev, const double* u_dev, int ncomp,
+                         double* partial_dev, int npartial, double* result_dev, cudaStream_t stream);
 igab_status geometry_local_device(const PatchDev& P, long long npts, const int* elem, const double* xg, double* xi,
                                   int* flag, cudaStream_t stream);
 igab_status surface_forms_device(int dim, int dw, long long npts, const double* Jt, const double* H, double* normal,
@@ -160,4 +163,5 @@ struct igab_patch {
   // reduction scratch
   double* d_red = nullptr;
   int red_cap = 0;
+  double* d_norm = nullptr;
 };

@@ -216,6 +216,17 @@ igab_status igab_reduce_volume(igab_patch* p, int64_t elem_begin, int64_t elem_e
                                const double* const* xi1d, const double* const* w1d, double* result, void* nccl_comm,
                                void* stream);
 
+/* L2 norm and energy (H1 seminorm) of a discrete field u_h = sum_i R_i u_i, fused evaluation + reduction:
+ *   result[0] = sum_q w detJ |u_h|^2 (= u^T M u),  result[1] = sum_q w detJ |grad u_h|^2 (= u^T K u of the Poisson
+ * operator), with R_i / dR_i as evaluateFunction / evaluateJacobian (nurbsbasis.hh:77-96), detJ = integrationElement and
+ * grad = jacobianInverseTransposed * d/dxi (nurbsgeometry.hh:200-210) -- the per-point quantities of the loop
+ * dune/python/test/poisson.py:47-79.  u [ndof*ncomp] in `u_space`, indexed g*ncomp + c with the DOF numbering of
+ * igab_patch_dofmap (untrimmed patches; IGAB_UNSUPPORTED with trim flags), ncomp <= 3.  result[2] is HOST memory.
+ * Deterministic (fixed two-level tree); nccl_comm as in igab_reduce_volume (both sums all-reduced).                   */
+igab_status igab_reduce_norms(igab_patch* p, int64_t elem_begin, int64_t elem_end, const int* nq1,
+                              const double* const* xi1d, const double* const* w1d, const double* u, int ncomp,
+                              igab_memspace u_space, double* result, void* nccl_comm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

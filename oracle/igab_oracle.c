@@ -880,6 +880,53 @@ int igo_geometry_local(const igo_patch* P, long npts, const int* elem, const dou
   return 0;
 }
 
+/* ---- patch-level field norms (north_star: "patch-level reductions (volume, L2/energy norms)") --------------------
+ * u_h = sum_i R_i u_{g(e,i)}: result[0] = sum_q w detJ |u_h|^2, result[1] = sum_q w detJ |J^-T grad_xi u_h|^2, formed per
+ * point exactly as the loop of dune/python/test/poisson.py:47-79 forms its ingredients (evaluateFunction,
+ * evaluateJacobian, jacobianInverseTransposed, integrationElement).  u [ndof][ncomp], DOF numbering of igo_dofmap.   */
+int igo_norms(const igo_patch* P, long elem_begin, long elem_end, const int* nq1, const double* xi1d, const double* w1d,
+              const double* u, int ncomp, double* result) {
+  const int dim = P->dim, dw = P->dimworld, nb = nb_of(P);
+  int nel[MAXDIM]; int* tab[MAXDIM];
+  igo_span_tables(P, nel, tab);
+  long nq = 1; const double* xid[MAXDIM]; const double* wd[MAXDIM];
+  { long off = 0; for (int d = 0; d < dim; ++d) { xid[d] = xi1d + off; wd[d] = w1d + off; off += nq1[d]; nq *= nq1[d]; } }
+  long nelem_all = 1; for (int d = 0; d < dim; ++d) nelem_all *= nel[d];
+  int* dof = (int*)malloc(sizeof(int) * nelem_all * nb);
+  igo_dofmap(P, 0, dof);
+  double* loc = (double*)malloc(sizeof(double) * nb * (dw + 1));
+  double* work = (double*)malloc(sizeof(double) * 27 * nb);
+  double* N = (double*)malloc(sizeof(double) * nb);
+  double* dN = (double*)malloc(sizeof(double) * nb * dim);
+  long double l2 = 0, en = 0;
+  for (long e = elem_begin; e < elem_end; ++e) {
+    int span[MAXDIM];
+    element_span(P, nel, tab, e, span);
+    gather_cp(P, span, loc);
+    for (long q = 0; q < nq; ++q) {
+      double xi[MAXDIM], wq = 1.0, detJ, JinvT[9]; long hq = q;
+      for (int d = 0; d < dim; ++d) { xi[d] = xid[d][hq % nq1[d]]; wq *= wd[d][hq % nq1[d]]; hq /= nq1[d]; }
+      eval_point(P, span, loc, xi, 1, N, dN, 0, 0, 0, 0, &detJ, JinvT, work);
+      for (int c = 0; c < ncomp; ++c) {
+        double uh = 0, gxi[MAXDIM] = {0, 0, 0};
+        for (int i = 0; i < nb; ++i) {
+          const double ui = u[(long)dof[e * nb + i] * ncomp + c];
+          uh += N[i] * ui;
+          for (int d = 0; d < dim; ++d) gxi[d] += dN[i * dim + d] * ui;
+        }
+        double g2 = 0;
+        for (int k = 0; k < dw; ++k) { double gk = 0; for (int d = 0; d < dim; ++d) gk += JinvT[k * dim + d] * gxi[d]; g2 += gk * gk; }
+        l2 += (long double)(wq * detJ * uh * uh);
+        en += (long double)(wq * detJ * g2);
+      }
+    }
+  }
+  result[0] = (double)l2; result[1] = (double)en;
+  free(dof); free(loc); free(work); free(N); free(dN);
+  for (int d = 0; d < dim; ++d) free(tab[d]);
+  return 0;
+}
+
 int igo_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -58,6 +58,8 @@ def lib():
         L.igo_surface_forms.argtypes = [C.c_int, C.c_int, C.c_long] + [dp] * 7
         L.igo_geometry_local.restype = C.c_int
         L.igo_geometry_local.argtypes = [PP, C.c_long, ip, dp, dp, ip]
+        L.igo_norms.restype = C.c_int
+        L.igo_norms.argtypes = [PP, C.c_long, C.c_long, ip, dp, dp, dp, C.c_int, dp]
         L.igo_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -185,6 +187,16 @@ class PortPatch:
         xi = _f64(xi).reshape(len(elem), self.dim)
         out = np.empty((len(elem), self.nb))
         lib().igo_partial(C.byref(self.c), len(elem), _i(elem), _d(xi), _i(_i32(alpha)), _d(out))
+        return out
+
+    def norms(self, xi1d, w1d, u, ncomp=1, elem_begin=0, elem_end=None):
+        """(sum w detJ |u_h|^2, sum w detJ |grad u_h|^2) over the elements [elem_begin, elem_end)."""
+        if elem_end is None:
+            elem_end = self.nelem
+        nq1 = _i32([len(x) for x in xi1d])
+        out = np.empty(2)
+        lib().igo_norms(C.byref(self.c), elem_begin, elem_end, _i(nq1), _d(_f64(np.concatenate(xi1d))),
+                        _d(_f64(np.concatenate(w1d))), _d(_f64(u)), ncomp, _d(out))
         return out
 
     def local(self, elem, xglobal):

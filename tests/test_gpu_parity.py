@@ -652,3 +652,68 @@ def test_geometry_local_errors_and_singular_jacobian():
     Pd = capi.Patch([1, 1], [k, k], np.array([[1, 1, 1.0]] * 4), 2)
     xi, flag = Pd.local([0], [[2.0, 2.0]])
     assert flag[0] == 1 and (xi[0] == np.finfo(float).max).all()
+
+
+@pytest.mark.parametrize("name,ncomp", [("curve_p3", 1), ("plate_hole_p2", 2), ("cylinder_p3", 1), ("cylinder_p4", 3),
+                                        ("torus_p2", 1), ("mixed_deg_3d", 2)])
+def test_field_norms_match_oracle(name, ncomp):
+    """igab_reduce_norms (fused evaluation + deterministic reduction) vs the port oracle's per-point loop: squared L2
+    norm and energy of a random field, whole patch and a sub-range; device-resident coefficients give the same bits;
+    two calls give the same bits."""
+    import torch
+    spec = PFT.small_patch(name)
+    Pp = port_for(spec)
+    P = gpu_patch(spec)
+    rule = [PD.gaussLegendre01(p + 1) for p in spec["degree"]]
+    xi1d, w1d = [r[0] for r in rule], [r[1] for r in rule]
+    rng = np.random.default_rng(23)
+    u = rng.normal(size=(Pp.cp.shape[0], ncomp))
+    ref = Pp.norms(xi1d, w1d, u, ncomp=ncomp)
+    got = P.norms(xi1d, w1d, u, ncomp=ncomp)
+    assert np.abs(got - ref).max() <= TOL * np.abs(ref).max(), (got, ref)
+    assert np.array_equal(got, P.norms(xi1d, w1d, u, ncomp=ncomp))
+    assert np.array_equal(got, P.norms(xi1d, w1d, torch.from_numpy(u).cuda(), ncomp=ncomp))
+    eb, ee = Pp.nelem // 3, Pp.nelem - 1
+    ref = Pp.norms(xi1d, w1d, u, ncomp=ncomp, elem_begin=eb, elem_end=ee)
+    got = P.norms(xi1d, w1d, u, ncomp=ncomp, elem_begin=eb, elem_end=ee)
+    assert np.abs(got - ref).max() <= TOL * np.abs(ref).max()
+    assert (P.norms(xi1d, w1d, u, ncomp=ncomp, elem_begin=2, elem_end=2) == 0).all()
+    # constant field: L2^2 = volume, energy = 0
+    one = P.norms(xi1d, w1d, np.ones(Pp.cp.shape[0]))
+    assert abs(one[0] - P.volume(xi1d, w1d)) <= 1e-13 * one[0] and abs(one[1]) <= 1e-18 * max(1.0, one[0])
+
+
+def test_field_norms_are_the_quadratic_forms_of_the_assembled_matrices():
+    """energy = u^T K u and L2^2 = u^T M u with K, M gathered into the global CSR by the CUDA path itself."""
+    spec = PFT.small_patch("cylinder_p3")
+    P = gpu_patch(spec)
+    rule = [PD.gaussLegendre01(p + 1) for p in spec["degree"]]
+    xi1d, w1d = [r[0] for r in rule], [r[1] for r in rule]
+    rowptr, colidx = P.csrPattern()
+    u = np.random.default_rng(3).normal(size=len(rowptr) - 1)
+    got = P.norms(xi1d, w1d, u)
+    for kind, val in ((capi.ASM_MASS, got[0]), (capi.ASM_POISSON, got[1])):
+        Ke, _ = P.assemble(kind, xi1d, w1d, want_fe=False)
+        vals = P.csrAssemble(Ke)
+        Au = np.add.reduceat(vals * u[colidx], rowptr[:-1])
+        assert abs(u @ Au - val) <= 1e-11 * abs(val)
+
+
+def test_field_norms_errors():
+    spec = PFT.small_patch("plate_hole_p2")
+    rule = [PD.gaussLegendre01(3) for _ in range(2)]
+    xi1d, w1d = [r[0] for r in rule], [r[1] for r in rule]
+    P = gpu_patch(spec)
+    n = P.dofmap()[1]
+    with pytest.raises(capi.IgabError) as ei:
+        P.norms(xi1d, w1d, np.zeros((n, 4)), ncomp=4)
+    assert ei.value.status == capi.INVALID_ARGUMENT
+    with pytest.raises(capi.IgabError) as ei:
+        P.norms(xi1d, w1d, np.zeros(n), elem_begin=0, elem_end=P.nelem + 1)
+    assert ei.value.status == capi.INVALID_ARGUMENT
+    flags = np.zeros(P.nelem, np.uint8)
+    flags[0] = 1
+    Pt = gpu_patch(spec, trimflags=flags)
+    with pytest.raises(capi.IgabError) as ei:
+        Pt.norms(xi1d, w1d, np.zeros(n))
+    assert ei.value.status == capi.UNSUPPORTED

@@ -299,3 +299,36 @@ def test_surface_forms_port_on_torus_and_sphere_like_patch():
     assert np.abs(f["secondFF"][:, 0, 1] - f["secondFF"][:, 1, 0]).max() == 0.0
     r, R = t["r"], t["R"]
     assert f["gaussK"].min() >= -1 / (r * (R - r)) - 1e-8 and f["gaussK"].max() <= 1 / (r * (R + r)) + 1e-8
+
+
+def test_field_norms_port_properties():
+    """igo_norms: u = 1 -> (volume, 0); u = x-coordinate of the control net on a polynomial patch -> (int x^2, volume);
+    and the quadratic forms u^T M u / u^T K u of the element matrices of the same rule."""
+    spec = PFT.small_patch("square_p3")  # unit weights: the field with coefficients P_i reproduces x
+    Pp = PT.PortPatch(spec["degree"], spec["knots"], spec["cp"], spec["dimworld"])
+    rule = [PT.gauss01(p + 1) for p in spec["degree"]]
+    xi1d, w1d = [r[0] for r in rule], [r[1] for r in rule]
+    vol = Pp.volume(xi1d, w1d)
+    ndof = Pp.cp.shape[0]
+    n1 = Pp.norms(xi1d, w1d, np.ones(ndof))
+    assert abs(n1[0] - vol) < 1e-13 * vol and abs(n1[1]) < 1e-20
+    nx = Pp.norms(xi1d, w1d, Pp.cp[:, 0].copy())
+    o = Pp.eval_tensor(xi1d, order=1, want=("x", "detJ"))
+    ww = np.tile(np.outer(w1d[1], w1d[0]).reshape(-1), Pp.nelem)
+    assert abs(nx[0] - (o["x"][:, 0] ** 2 * o["detJ"] * ww).sum()) < 1e-13
+    assert abs(nx[1] - vol) < 1e-12 * vol
+    rng = np.random.default_rng(2)
+    u = rng.normal(size=ndof)
+    dof, _ = Pp.dofmap()
+    Ke, _ = Pp.assemble(0, xi1d, w1d, want_fe=False)
+    Me, _ = Pp.assemble(1, xi1d, w1d, want_fe=False)
+    ue = u[dof]
+    nu = Pp.norms(xi1d, w1d, u)
+    assert abs(nu[0] - np.einsum("ei,eij,ej->", ue, Me, ue)) < 1e-12 * nu[0]
+    assert abs(nu[1] - np.einsum("ei,eij,ej->", ue, Ke, ue)) < 1e-12 * nu[1]
+    # two components, sub-range: additivity
+    u2 = rng.normal(size=(ndof, 2))
+    h = Pp.nelem // 2
+    full = Pp.norms(xi1d, w1d, u2, ncomp=2)
+    parts = Pp.norms(xi1d, w1d, u2, ncomp=2, elem_end=h) + Pp.norms(xi1d, w1d, u2, ncomp=2, elem_begin=h)
+    assert np.abs(full - parts).max() < 1e-12 * full.max()

@@ -61,6 +61,19 @@ def main():
         assert abs(sum(v[0] for v in allv) - whole) <= 1e-12 * whole
         assert abs(whole - exact) < 1e-9
         print("nccl volume check ok")
+    # field norms: slab partial sums all-reduced inside igab_reduce_norms vs the whole-patch call
+    u = np.random.default_rng(7).normal(size=P.dofmap()[1])
+    mine_n = P.norms([x] * 3, [w] * 3, u, elem_begin=eb, elem_end=ee)
+    total_n = P.norms([x] * 3, [w] * 3, u, elem_begin=eb, elem_end=ee, nccl_comm=comm)
+    whole_n = P.norms([x] * 3, [w] * 3, u)
+    alln = [None] * world
+    dist.all_gather_object(alln, (mine_n.tolist(), total_n.tolist()))
+    if rank == 0:
+        print("norms ranks:", alln, "whole:", whole_n)
+        assert all(np.abs(np.array(v[1]) - whole_n).max() <= 1e-12 * whole_n.max() for v in alln)
+        assert len({tuple(v[1]) for v in alln}) == 1
+        assert np.abs(sum(np.array(v[0]) for v in alln) - whole_n).max() <= 1e-12 * whole_n.max()
+        print("nccl norms check ok")
     nccl.ncclCommDestroy.argtypes = [C.c_void_p]
     nccl.ncclCommDestroy(comm)
     dist.destroy_process_group()
