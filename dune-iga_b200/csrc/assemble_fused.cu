@@ -48,7 +48,7 @@ struct FCfg {
   static constexpr int SZ_G = 16 * NQ;
   static constexpr int SZ_A = ev((SZ_H + SZ_S1) > SZ_G ? (SZ_H + SZ_S1) : SZ_G);
   static constexpr int SZ_S2 = ev(3 * 4 * Q2 * S2S);
-  static constexpr int CS = 16;  // doubles per point: 1/W, W_0..2, J^-T[9], w detJ, sqrt(w detJ), pad
+  static constexpr int CS = 16;  // doubles per point: 1/W, v[3], M[3][3], w detJ, s = sqrt(w detJ), s/W (element_prepare)
   static constexpr int SZ_C = CS * NQ;
   static constexpr int KC = 16, LD = NBP + 4;
   static constexpr int SZ_SA = 2 * KC * LD;
@@ -56,8 +56,8 @@ struct FCfg {
 };
 
 // Steps (1)+(2) for one element, executed by the whole block (NT threads): tables + control points -> shared, geometry
-// of all quadrature points by sum factorisation, per-point constants sC[pt][16] = {1/W, dW/dxi_0..2, J^-T[3][3] row-major
-// [c][d], w detJ}.  Ends with a __syncthreads().
+// of all quadrature points by sum factorisation, per-point constants sC[pt][16] (layout below).  Ends with a
+// __syncthreads().
 template <int P, int Q, int NT>
 __device__ __forceinline__ void element_prepare(const PatchDev& Pd, long long e, const double* __restrict__ tab0,
                                                 const double* __restrict__ tab1, const double* __restrict__ tab2,
@@ -105,13 +105,21 @@ __device__ __forceinline__ void element_prepare(const PatchDev& Pd, long long e,
     w *= w1[q % Q];
     w *= w2[q / Q];
     double* o = sC + CS * pt;
-    o[0] = invW; o[1] = Wd[0]; o[2] = Wd[1]; o[3] = Wd[2];
-    // J^-T[c][d] = cof[d][c] / det
-    o[4] = c00 * id; o[5] = c10 * id; o[6] = c20 * id;
-    o[7] = c01 * id; o[8] = c11 * id; o[9] = c21 * id;
-    o[10] = c02 * id; o[11] = c12 * id; o[12] = c22 * id;
-    o[13] = w * fabs(det);
-    o[14] = sqrt(o[13]);  // rows of the gradient stack are pre-scaled by sqrt(w detJ): K = A^T A, no scaling in the MMA loop
+    // per point: physical gradient of R_i (pre-scaled by s = sqrt(w detJ), so that K = A^T A needs no scaling in the MMA
+    // loop) as G_c[i] = sum_d M[c][d] A_d[i] - v[c] Ahat[i] with Ahat = w_i Nhat_i, A_d = w_i d_d Nhat_i and
+    //   M[c][d] = s/W J^-T[c][d],  v[c] = (1/W) sum_d M[c][d] dW/dxi_d        (quotient rule folded into the constants)
+    const double wdet = w * fabs(det), sq = sqrt(wdet), f = sq * invW * id;
+    const double M[3][3] = {{c00 * f, c10 * f, c20 * f}, {c01 * f, c11 * f, c21 * f}, {c02 * f, c12 * f, c22 * f}};
+    o[0] = invW;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      o[1 + c] = (M[c][0] * Wd[0] + M[c][1] * Wd[1] + M[c][2] * Wd[2]) * invW;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) o[4 + 3 * c + d] = M[c][d];
+    }
+    o[13] = wdet;
+    o[14] = sq;
+    o[15] = sq * invW;
   }
   __syncthreads();
 
@@ -158,6 +166,7 @@ __global__ void __launch_bounds__(FCfg<P, Q>::NT, 2) gram_fused_kernel(
     // ---- (3) chunked Gram contraction
     auto build = [&](int ch) {
       double* A = sA + (ch & 1) * KC * LD;
+#pragma unroll 2
       for (int item = tid; item < pts * NBP; item += NT) {
         const int ql = item / NBP, i = item % NBP;
         const int pt = ch * pts + ql;
@@ -168,19 +177,18 @@ __global__ void __launch_bounds__(FCfg<P, Q>::NT, 2) gram_fused_kernel(
           const double2 a = lds2f(sT + (q0 * NB1 + i0) * 2), b = lds2f(sT + C::TAB + (q1 * NB1 + i1) * 2),
                         c = lds2f(sT + 2 * C::TAB + (q2 * NB1 + i2) * 2);
           const double* k = sC + CS * pt;
-          const double w = sW[i], invW = k[0];
+          const double w = sW[i];
           const double t00 = a.x * b.x, wn2 = w * c.x;
-          const double R = t00 * wn2 * invW;
-          const double sq = k[14];
+          const double Ah = t00 * wn2;
           if constexpr (NROW == 1) {
-            r0 = R * sq;
+            r0 = Ah * k[15];
           } else {
-            const double d0 = (a.y * b.x * wn2 - k[1] * R) * invW * sq;
-            const double d1 = (a.x * b.y * wn2 - k[2] * R) * invW * sq;
-            const double d2 = (t00 * (w * c.y) - k[3] * R) * invW * sq;
-            r0 = k[4] * d0 + k[5] * d1 + k[6] * d2;
-            r1 = k[7] * d0 + k[8] * d1 + k[9] * d2;
-            r2 = k[10] * d0 + k[11] * d1 + k[12] * d2;
+            const double2 k01 = lds2f(k), k23 = lds2f(k + 2), k45 = lds2f(k + 4), k67 = lds2f(k + 6),
+                          k89 = lds2f(k + 8), kab = lds2f(k + 10), kc = lds2f(k + 12);
+            const double A0 = (a.y * b.x) * wn2, A1 = (a.x * b.y) * wn2, A2 = t00 * (w * c.y);
+            r0 = k45.x * A0 + k45.y * A1 + k67.x * A2 - k01.y * Ah;
+            r1 = k67.y * A0 + k89.x * A1 + k89.y * A2 - k23.x * Ah;
+            r2 = kab.x * A0 + kab.y * A1 + kc.x * A2 - k23.y * Ah;
           }
         }
         if constexpr (NROW == 1) {
@@ -265,16 +273,24 @@ struct ElasCoef {
 template <int P, int Q>
 struct ECfg {
   using F = FCfg<P, Q>;
-  static constexpr int NT = 9 * 32;
-  static constexpr int KC = 16, LD = F::NBP + 4;
-  static constexpr int SZ_GS = 3 * KC * LD;
+  static constexpr int NT = 8 * 32;             // 2 x 4 warp grid over the 12 x 12 tiles of the nine blocks: 2 warps per SM sub-partition
+  static constexpr int KC = 16, LDC = 64 + 4;   // chunk rows: 32 columns of block bi, 32 of block bj, padding
+  static constexpr int SZ_GS = 3 * KC * LDC;    // one chunk buffer [3][KC][LDC]
   static constexpr int MS = 33;                 // row stride of a staged 32x32 block
   static constexpr int SZ_M = 9 * 32 * MS;
-  static constexpr int SZ_R2 = (F::SZ_A + F::SZ_S2 + SZ_GS) > SZ_M ? (F::SZ_A + F::SZ_S2 + SZ_GS) : SZ_M;
+  static constexpr int mx(int a, int b) { return a > b ? a : b; }
+  // the preparation scratch, the two chunk buffers and the staging of the nine blocks share one region
+  static constexpr int SZ_R2 = mx(mx(F::SZ_A + F::SZ_S2, 2 * SZ_GS), SZ_M);
   static constexpr int SZ_TOTAL = F::SZ_T + F::SZ_W + F::SZ_C + SZ_R2;
 };
 
-template <int P, int Q>
+// Cf[a][c][b][c'] of an orthotropic material aligned with the axes (isotropic included) is non-zero only for
+// (a==c, b==c') [normal-normal], (a==b, c==c') and (a==c', b==c) [shear-shear]: 21 of the 81 coefficients.
+__host__ __device__ constexpr bool ortho_pattern(int a, int c, int b, int cp) {
+  return (a == c && b == cp) || (a == b && c == cp) || (a == cp && b == c);
+}
+
+template <int P, int Q, bool ORTHO>
 __global__ void __launch_bounds__(ECfg<P, Q>::NT, 2) elasticity_fused_kernel(
     PatchDev Pd, long long elem_begin, long long nelem, const double* __restrict__ tab0,
     const double* __restrict__ tab1, const double* __restrict__ tab2, const double* __restrict__ w0,
@@ -282,8 +298,8 @@ __global__ void __launch_bounds__(ECfg<P, Q>::NT, 2) elasticity_fused_kernel(
     double* __restrict__ Ke, double* __restrict__ fe) {
   using C = FCfg<P, Q>;
   using E = ECfg<P, Q>;
-  constexpr int NB1 = C::NB1, NB = C::NB, NQ = C::NQ, Q2 = C::Q2, NBP = C::NBP, CS = C::CS;
-  constexpr int NT = E::NT, KC = E::KC, LD = E::LD, MS = E::MS, NBLK = C::NBLK;
+  constexpr int NB1 = C::NB1, NB = C::NB, NQ = C::NQ, Q2 = C::Q2, CS = C::CS;
+  constexpr int NT = E::NT, KC = E::KC, LDC = E::LDC, MS = E::MS, NBLK = C::NBLK;
   constexpr int nchunk = (NQ + KC - 1) / KC;
   constexpr int N3 = 3 * NB;
   extern __shared__ __align__(16) double esm[];
@@ -292,11 +308,24 @@ __global__ void __launch_bounds__(ECfg<P, Q>::NT, 2) elasticity_fused_kernel(
   double* const sC = sW + C::SZ_W;
   double* const rA = sC + C::SZ_C;
   double* const sS2 = rA + C::SZ_A;
-  double* const sGs = sS2 + C::SZ_S2;  // [3][KC][LD]
-  double* const sM = rA;               // [9][32][MS], after the contraction of a block pair
+  double* const sGs = rA;  // [2][3][KC][LDC], after element_prepare
+  double* const sM = rA;   // [9][32][MS], after the contraction of a block pair
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int wc = warp / 3, wcp = warp % 3;  // this warp's (c, c')
+  // The nine 32x32 blocks M^{cc'} of a block pair form a 96 x 96 matrix (rows (c, i), columns (c', j)) = 12 x 12 DMMA
+  // tiles; warp (wr, wq) of the 2 x 4 grid owns tile rows 6 wr .. 6 wr + 5 and tile columns 3 wq .. 3 wq + 2.
+  const int wr = warp >> 2, wq = warp & 3;
+  int aoff[6], boffs[3];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    const int tr = 6 * wr + a;
+    aoff[a] = (tr >> 2) * KC * LDC + (tr & 3) * 8 + g;
+  }
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    const int tc = 3 * wq + b;
+    boffs[b] = (tc >> 2) * KC * LDC + (tc & 3) * 8 + g;
+  }
   for (int idx = tid; idx < C::SZ_W; idx += NT) sW[idx] = 0.0;
 
   for (long long el = blockIdx.x; el < nelem; el += gridDim.x) {
@@ -305,18 +334,14 @@ __global__ void __launch_bounds__(ECfg<P, Q>::NT, 2) elasticity_fused_kernel(
     double* K = Ke + el * (long long)N3 * N3;
     for (int bi = 0; bi < NBLK; ++bi)
       for (int bj = bi; bj < NBLK; ++bj) {
-        double acc[4][4][2];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-        const int ncolblk = (bi == bj) ? 1 : 2;
-#pragma unroll 1
-        for (int ch = 0; ch < nchunk; ++ch) {
-          __syncthreads();  // previous chunk (or the previous block pair's staging) fully consumed
-          // gradients of 16 points for the columns of blocks bi and bj
-          for (int item = tid; item < KC * 32 * ncolblk; item += NT) {
-            const int ql = item / (32 * ncolblk), r = item % (32 * ncolblk);
+        const int ncol = (bi == bj) ? 32 : 64;
+        const int boff = (bi == bj) ? 0 : 32;
+        // physical gradients (pre-scaled by sqrt(w detJ)) of the 16 points of chunk ch for the columns of blocks bi, bj
+        auto build = [&](int ch) {
+          double* buf = sGs + (ch & 1) * E::SZ_GS;
+#pragma unroll 2
+          for (int item = tid; item < KC * ncol; item += NT) {
+            const int ql = item / ncol, r = item % ncol;
             const int i = (r < 32 ? bi * 32 : bj * 32 - 32) + r;
             const int pt = ch * KC + ql;
             double r0 = 0.0, r1 = 0.0, r2 = 0.0;
@@ -326,49 +351,56 @@ __global__ void __launch_bounds__(ECfg<P, Q>::NT, 2) elasticity_fused_kernel(
               const double2 a = lds2f(sT + (q0 * NB1 + i0) * 2), b = lds2f(sT + C::TAB + (q1 * NB1 + i1) * 2),
                             c = lds2f(sT + 2 * C::TAB + (q2 * NB1 + i2) * 2);
               const double* k = sC + CS * pt;
-              const double w = sW[i], invW = k[0];
+              const double2 k01 = lds2f(k), k23 = lds2f(k + 2), k45 = lds2f(k + 4), k67 = lds2f(k + 6),
+                            k89 = lds2f(k + 8), kab = lds2f(k + 10), kc = lds2f(k + 12);
+              const double w = sW[i];
               const double t00 = a.x * b.x, wn2 = w * c.x;
-              const double R = t00 * wn2 * invW;
-              const double sq = k[14];
-              const double d0 = (a.y * b.x * wn2 - k[1] * R) * invW * sq;
-              const double d1 = (a.x * b.y * wn2 - k[2] * R) * invW * sq;
-              const double d2 = (t00 * (w * c.y) - k[3] * R) * invW * sq;
-              r0 = k[4] * d0 + k[5] * d1 + k[6] * d2;
-              r1 = k[7] * d0 + k[8] * d1 + k[9] * d2;
-              r2 = k[10] * d0 + k[11] * d1 + k[12] * d2;
+              const double Ah = t00 * wn2;
+              const double A0 = (a.y * b.x) * wn2, A1 = (a.x * b.y) * wn2, A2 = t00 * (w * c.y);
+              r0 = k45.x * A0 + k45.y * A1 + k67.x * A2 - k01.y * Ah;
+              r1 = k67.y * A0 + k89.x * A1 + k89.y * A2 - k23.x * Ah;
+              r2 = kab.x * A0 + kab.y * A1 + kc.x * A2 - k23.y * Ah;
             }
-            sGs[(0 * KC + ql) * LD + i] = r0;
-            sGs[(1 * KC + ql) * LD + i] = r1;
-            sGs[(2 * KC + ql) * LD + i] = r2;
+            buf[(0 * KC + ql) * LDC + r] = r0;
+            buf[(1 * KC + ql) * LDC + r] = r1;
+            buf[(2 * KC + ql) * LDC + r] = r2;
           }
+        };
+        double acc[6][3][2];
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+          for (int b = 0; b < 3; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+        build(0);
+        __syncthreads();
+#pragma unroll 1
+        for (int ch = 0; ch < nchunk; ++ch) {
+          const double* Gk = sGs + (ch & 1) * E::SZ_GS + t * LDC;
+#pragma unroll
+          for (int ks = 0; ks < KC; ks += 4) {  // rows of points beyond the rule are zero
+            double af[6], bf[3];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) af[a] = Gk[ks * LDC + aoff[a]];
+#pragma unroll
+            for (int b = 0; b < 3; ++b) bf[b] = Gk[ks * LDC + boff + boffs[b]];
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+              for (int b = 0; b < 3; ++b) dmma8x8x4_f(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+          }
+          if (ch + 1 < nchunk) build(ch + 1);  // into the other buffer, overlapping the other warps' MMAs
           __syncthreads();
-          const double* Ga = sGs + wc * KC * LD;
-          const double* Gb = sGs + wcp * KC * LD;
+        }
+        // all warps are past the last chunk: the buffers are reused as staging, block (c, c') at sM[(3c + c') * 32 * MS]
 #pragma unroll
-          for (int ks = 0; ks < KC; ks += 4) {
-            const int k = ks + t;  // rows of points beyond the rule are zero
-            double af[4], bf[4];
+        for (int a = 0; a < 6; ++a)
 #pragma unroll
-            for (int a = 0; a < 4; ++a) af[a] = Ga[k * LD + bi * 32 + 8 * a + g];
-#pragma unroll
-            for (int b = 0; b < 4; ++b) bf[b] = Gb[k * LD + bj * 32 + 8 * b + g];
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-              for (int b = 0; b < 4; ++b) dmma8x8x4_f(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+          for (int b = 0; b < 3; ++b) {
+            const int tr = 6 * wr + a, tc = 3 * wq + b;
+            double* M = sM + (((tr >> 2) * 3 + (tc >> 2)) * 32 + (tr & 3) * 8 + g) * MS + (tc & 3) * 8 + 2 * t;
+            M[0] = acc[a][b][0];
+            M[1] = acc[a][b][1];
           }
-        }
-        __syncthreads();  // all warps done reading the chunk buffer; it is reused as staging
-        {
-          double* M = sM + warp * 32 * MS;  // block (c, c')
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              M[(8 * a + g) * MS + 8 * b + 2 * t] = acc[a][b][0];
-              M[(8 * a + g) * MS + 8 * b + 2 * t + 1] = acc[a][b][1];
-            }
-        }
         __syncthreads();
         // combine: direct block rows (i,a), columns (j,b); lanes over j -> contiguous 3-double groups per row
         for (int item = tid; item < 32 * 32; item += NT) {
@@ -386,7 +418,8 @@ __global__ void __launch_bounds__(ECfg<P, Q>::NT, 2) elasticity_fused_kernel(
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
 #pragma unroll
-                  for (int cp = 0; cp < 3; ++cp) v = fma(coef.cf[((a * 3 + c) * 3 + b) * 3 + cp], m[c * 3 + cp], v);
+                  for (int cp = 0; cp < 3; ++cp)
+                    if (!ORTHO || ortho_pattern(a, c, b, cp)) v = fma(coef.cf[((a * 3 + c) * 3 + b) * 3 + cp], m[c * 3 + cp], v);
                 K[(long long)(3 * i + a) * N3 + 3 * j + b] = v;
               }
           }
@@ -408,12 +441,14 @@ __global__ void __launch_bounds__(ECfg<P, Q>::NT, 2) elasticity_fused_kernel(
 #pragma unroll
                   for (int c = 0; c < 3; ++c)
 #pragma unroll
-                    for (int cp = 0; cp < 3; ++cp) v = fma(coef.cf[((b * 3 + cp) * 3 + a) * 3 + c], m[c * 3 + cp], v);
+                    for (int cp = 0; cp < 3; ++cp)
+                      if (!ORTHO || ortho_pattern(b, cp, a, c)) v = fma(coef.cf[((b * 3 + cp) * 3 + a) * 3 + c], m[c * 3 + cp], v);
                   K[(long long)(3 * j + b) * N3 + 3 * i + a] = v;
                 }
             }
           }
         }
+        __syncthreads();  // the staging area becomes chunk buffer 0 of the next block pair
       }
     if (fe) {
       for (int i = tid; i < NB; i += NT) {
@@ -442,21 +477,33 @@ igab_status launch_elas(const PatchDev& Pd, SfWorkspace& ws, const double* D_hos
   for (double& v : coef.cf) v = 0.0;
   for (auto& s1 : S)
     for (auto& s2 : S) coef.cf[((s1[1] * 3 + s1[2]) * 3 + s2[1]) * 3 + s2[2]] += D_host[s1[0] * 6 + s2[0]];
+  // orthotropic / isotropic D (the usual case): only 21 coefficients can be non-zero, the combination is specialised
+  bool ortho = true;
+  for (int a = 0; a < 3; ++a)
+    for (int c = 0; c < 3; ++c)
+      for (int b = 0; b < 3; ++b)
+        for (int cp = 0; cp < 3; ++cp)
+          if (!ortho_pattern(a, c, b, cp) && coef.cf[((a * 3 + c) * 3 + b) * 3 + cp] != 0.0) ortho = false;
   const size_t smem = (size_t)E::SZ_TOTAL * sizeof(double);
   static bool configured = false;
   static int sms = 148, bps = 1;
   if (!configured) {
-    IGAB_CUDA_TRY(cudaFuncSetAttribute(elasticity_fused_kernel<P, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IGAB_CUDA_TRY(cudaFuncSetAttribute(elasticity_fused_kernel<P, Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IGAB_CUDA_TRY(cudaFuncSetAttribute(elasticity_fused_kernel<P, Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0;
     IGAB_CUDA_TRY(cudaGetDevice(&dev));
     IGAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    IGAB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, elasticity_fused_kernel<P, Q>, E::NT, smem));
+    IGAB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, elasticity_fused_kernel<P, Q, false>, E::NT, smem));
     if (bps < 1) bps = 1;
     configured = true;
   }
   const unsigned grid = (unsigned)std::min<long long>(nel, (long long)bps * sms);
-  elasticity_fused_kernel<P, Q><<<grid, E::NT, smem, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],
-                                                               w_dev[1], w_dev[2], coef, fconst, Ke, fe);
+  if (ortho)
+    elasticity_fused_kernel<P, Q, true><<<grid, E::NT, smem, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],
+                                                                       w_dev[1], w_dev[2], coef, fconst, Ke, fe);
+  else
+    elasticity_fused_kernel<P, Q, false><<<grid, E::NT, smem, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],
+                                                                        w_dev[1], w_dev[2], coef, fconst, Ke, fe);
   count_launch();
   IGAB_CUDA_TRY(cudaGetLastError());
   return IGAB_OK;

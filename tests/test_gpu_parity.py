@@ -717,3 +717,31 @@ def test_field_norms_errors():
     with pytest.raises(capi.IgabError) as ei:
         Pt.norms(xi1d, w1d, np.zeros(n))
     assert ei.value.status == capi.UNSUPPORTED
+
+
+@pytest.mark.parametrize("name", ["cylinder_p3", "cylinder_p4"])
+@pytest.mark.parametrize("material", ["isotropic", "anisotropic", "nonsymmetric"])
+def test_elasticity_fused_kernel_materials(name, material):
+    """3-D elasticity element matrices of the fused nine-Gram-block kernel for the three coefficient cases: isotropic
+    (the specialised 21-coefficient combination), fully populated symmetric D (general 81-coefficient combination) and a
+    non-symmetric D (mirror block needs the transposed coefficients)."""
+    spec = PFT.small_patch(name)
+    Pp = port_for(spec)
+    P = gpu_patch(spec)
+    rule = [PD.gaussLegendre01(p + 1) for p in spec["degree"]]
+    xi1d, w1d = [r[0] for r in rule], [r[1] for r in rule]
+    rng = np.random.default_rng(31)
+    lam, mu = 0.3 / (1.3 * 0.4), 1 / 2.6
+    D = np.zeros((6, 6))
+    D[:3, :3] = lam
+    D[np.arange(3), np.arange(3)] = lam + 2 * mu
+    D[np.arange(3, 6), np.arange(3, 6)] = mu
+    if material != "isotropic":
+        A = rng.normal(size=(6, 6))
+        D = D + 0.1 * (A @ A.T if material == "anisotropic" else A)
+    ne = min(Pp.nelem, 6)
+    Kref, _ = Pp.assemble(capi.ASM_ELASTICITY, xi1d, w1d, D=D, elem_end=ne, want_fe=False)
+    K, _ = P.assemble(capi.ASM_ELASTICITY, xi1d, w1d, D=D, elem_end=ne, want_fe=False)
+    assert relerr(K.reshape(ne, -1), Kref.reshape(ne, -1)) <= TOL, relerr(K.reshape(ne, -1), Kref.reshape(ne, -1))
+    sym = np.abs(K - K.transpose(0, 2, 1)).max() / np.abs(K).max()
+    assert (sym > 1e-6) if material == "nonsymmetric" else (sym <= 1e-12)
