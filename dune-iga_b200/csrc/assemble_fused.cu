@@ -50,7 +50,7 @@ struct FCfg {
   static constexpr int SZ_S2 = ev(3 * 4 * Q2 * S2S);
   static constexpr int CS = 16;  // doubles per point: 1/W, v[3], M[3][3], w detJ, s = sqrt(w detJ), s/W (element_prepare)
   static constexpr int SZ_C = CS * NQ;
-  static constexpr int KC = 16, LD = NBP + 4;
+  static constexpr int KC = 24, LD = NBP + 4;  // k-rows per chunk: 8 points x 3 gradient components (24 points for mass)
   static constexpr int SZ_SA = 2 * KC * LD;
   static constexpr int SZ_TOTAL = SZ_T + SZ_W + SZ_A + SZ_S2 + SZ_C + SZ_SA;
 };
