@@ -461,6 +461,8 @@ bool eval_tensor_sf_supported(const PatchDev& P, const int* nq1, int order, cons
 void free_sf_workspace(SfWorkspace& ws) {
   for (int d = 0; d < kMaxDim; ++d)
     if (ws.tab[d]) cudaFree(ws.tab[d]);
+  for (int d = 0; d < kMaxDim; ++d)
+    if (ws.tabO2[d]) cudaFree(ws.tabO2[d]);
   if (ws.counter) cudaFree(ws.counter);
   ws = SfWorkspace();
 }

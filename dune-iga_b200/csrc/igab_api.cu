@@ -232,6 +232,8 @@ static igab_status run_eval_tensor_device(igab_patch* p, long long eb, long long
   if (t2) return launch_eval_tensor_2d(p->dev, p->sf, src, xi1d_host, nel, order, od, stream);
   if (p->kernel_mode != IGAB_KERNEL_GENERIC && !getenv("IGAB_NO_BLK") && eval_tensor_blk_supported(p->dev, nq1, order, od))
     return launch_eval_tensor_blk(p->dev, p->sf, src, xi1d_host, nel, order, od, stream);
+  if (p->kernel_mode != IGAB_KERNEL_GENERIC && eval_tensor_sf2_supported(p->dev, nq1, order, od))
+    return launch_eval_tensor_sf2(p->dev, p->sf, src, xi1d_host, nel, od, stream);
   if (p->kernel_mode == IGAB_KERNEL_TENSOR && !sf) {
     set_error("eval_tensor: no sum-factorised kernel compiled for this (dim, dimworld, degree, rule, outputs)");
     return IGAB_UNSUPPORTED;

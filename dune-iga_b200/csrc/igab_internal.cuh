@@ -54,6 +54,12 @@ struct SfWorkspace {
   unsigned int counterSlot = 0;
   bool valid = false;
   cudaStream_t stream = nullptr;    // stream the tables were built on (rebuilt when the caller switches streams)
+  // tables with second derivatives ([e][q][i][4]) of the order-2 tensor kernel, cached the same way
+  double* tabO2[kMaxDim] = {nullptr, nullptr, nullptr};
+  size_t tabO2Cap[kMaxDim] = {0, 0, 0};
+  std::vector<double> xiO2[kMaxDim];
+  bool validO2 = false;
+  cudaStream_t streamO2 = nullptr;
 };
 
 void set_error(const std::string& msg);
@@ -84,6 +90,11 @@ igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* 
                               long long eb, long long nel, const int* nq1, double* Ke, double* fe, cudaStream_t stream,
                               const double* D_host);
 bool eval_tensor_sf_supported(const PatchDev& P, const int* nq1, int order, const EvalOutDev& out);
+// 3-D with second derivatives (p = 2, 3)
+bool eval_tensor_sf2_supported(const PatchDev& P, const int* nq1, int order, const EvalOutDev& out);
+igab_status launch_eval_tensor_sf2(const PatchDev& P, SfWorkspace& ws, const PointSource& src,
+                                   const double* const* xi1d_host, long long nelem, const EvalOutDev& out,
+                                   cudaStream_t stream);
 // 3-D, large local bases (p = 4): one block per element
 bool eval_tensor_blk_supported(const PatchDev& P, const int* nq1, int order, const EvalOutDev& out);
 igab_status launch_eval_tensor_blk(const PatchDev& P, SfWorkspace& ws, const PointSource& src,

@@ -745,3 +745,32 @@ def test_elasticity_fused_kernel_materials(name, material):
     assert relerr(K.reshape(ne, -1), Kref.reshape(ne, -1)) <= TOL, relerr(K.reshape(ne, -1), Kref.reshape(ne, -1))
     sym = np.abs(K - K.transpose(0, 2, 1)).max() / np.abs(K).max()
     assert (sym > 1e-6) if material == "nonsymmetric" else (sym <= 1e-12)
+
+
+@pytest.mark.parametrize("p,extra", [(3, 0), (3, 1), (2, 0), (2, 1)])
+def test_3d_second_derivative_tensor_kernel(p, extra):
+    """eval_sf3d_o2_kernel (3-D tensor rules with second derivatives, p = 2, 3; Q = p+1, p+2) against the oracle: every
+    field, an element sub-range, and output subsets (the kernel skips phases whose outputs are absent)."""
+    pd = PD.thickCylinder(p, (1, 1, 2))
+    spec = dict(degree=pd.degree, knots=pd.knotSpans, cp=pd.cp, dimworld=3)
+    Pp = port_for(spec)
+    P = gpu_patch(spec)
+    xi1d = [PD.gaussLegendre01(p + 1 + extra)[0]] * 3
+    ref = Pp.eval_tensor(xi1d, order=2, want=EVAL_FIELDS + ("JinvT",))
+    got = P.evalTensor(xi1d, order=2, want=EVAL_FIELDS + ("JinvT",))
+    for f in EVAL_FIELDS + ("JinvT",):
+        assert relerr(got[f], ref[f]) <= TOL, (f, relerr(got[f], ref[f]))
+    P.setKernel(capi.KERNEL_GENERIC)
+    gen = P.evalTensor(xi1d, order=2, want=EVAL_FIELDS)
+    P.setKernel(capi.KERNEL_AUTO)
+    for f in EVAL_FIELDS:
+        assert relerr(got[f], gen[f]) <= TOL
+    eb, ee = 3, Pp.nelem - 2
+    nq = len(xi1d[0]) ** 3
+    sub = P.evalTensor(xi1d, order=2, elem_begin=eb, elem_end=ee, want=("d2N", "H"))
+    assert set(sub) == {"d2N", "H"}
+    assert np.array_equal(sub["d2N"], got["d2N"][eb * nq:ee * nq]) and np.array_equal(sub["H"], got["H"][eb * nq:ee * nq])
+    only = P.evalTensor(xi1d, order=2, want=("N", "d2N"))
+    assert np.array_equal(only["N"], got["N"]) and np.array_equal(only["d2N"], got["d2N"])
+    # second derivatives of a partition of unity vanish
+    assert np.abs(got["d2N"].sum(1)).max() < 1e-9 * max(1.0, np.abs(got["d2N"]).max())

@@ -77,7 +77,7 @@ def main():
     if "X" in which:  # beyond the five named configs
         eval_config("X1 3-D cylinder p=2 128^3 (16 k-layers), 3^3 Gauss, order 1", PD.thickCylinder(2, (7, 7, 7)), [3, 3, 3], 1,
                     ("N", "dN", "x", "Jt", "detJ"), el_chunk=128 * 128 * 16)
-        eval_config("X2 3-D cylinder p=3 64^3 (8 k-layers), 4^3 Gauss, order 2 (general kernel)", PD.thickCylinder(3, (6, 6, 6)), [4, 4, 4], 2,
+        eval_config("X2 3-D cylinder p=3 64^3 (8 k-layers), 4^3 Gauss, order 2", PD.thickCylinder(3, (6, 6, 6)), [4, 4, 4], 2,
                     ("N", "dN", "d2N", "x", "Jt", "H", "detJ"), el_chunk=64 * 64 * 8)
         eval_config("X3 3-D cylinder p=3 64^3 (8 k-layers), 5^3 Gauss, order 1 (general kernel: rule != p+1)", PD.thickCylinder(3, (6, 6, 6)),
                     [5, 5, 5], 1, ("N", "dN", "x", "Jt", "detJ"), el_chunk=64 * 64 * 8)
