@@ -96,6 +96,14 @@ out["geometry_surface"] = {
     # geometry.local(x) == u (trimmedgridtests.cpp:157-162)
     "local": [[[1.0, 1.0, 0.75], [0.5, 0.5]], [[2, 0, 2], [0, 1]]]}
 
+# --- element centres after one global refinement of the bilinear unit square element.ibra (trimmedgridtests.cpp:197-217;
+# fixture auxiliaryfiles/element.ibra: degree (1,1), knots {0,1}x{0,1}, poles (0,0),(0,1),(1,0),(1,1), unit weights).
+# The reference compares with operator== (exact).  Element index = position, first direction fastest.
+out["element_centres"] = {
+    "cite": "trimmedgridtests.cpp:197-217", "degree": [1, 1], "knots": [[0, 0, 1, 1], [0, 0, 1, 1]], "dimworld": 2,
+    "cp": [[0, 0, 1], [1, 0, 1], [0, 1, 1], [1, 1, 1]], "refine_level": 1,
+    "centres": [[0.25, 0.25], [0.75, 0.25], [0.25, 0.75], [0.75, 0.75]]}
+
 # --- degreeElevate by 2 of a p=2 rational curve (gridtests.cpp:1136-1166,1203-1221), tolerance 1e-10
 out["degree_elevate_curve"] = {
     "cite": "gridtests.cpp:1136-1166,1203-1221", "tol": 1e-10, "degree": [2], "knots": [[0, 0, 0, 0.5, 1, 1, 1]],

@@ -774,3 +774,16 @@ def test_3d_second_derivative_tensor_kernel(p, extra):
     assert np.array_equal(only["N"], got["N"]) and np.array_equal(only["d2N"], got["d2N"])
     # second derivatives of a partition of unity vanish
     assert np.abs(got["d2N"].sum(1)).max() < 1e-9 * max(1.0, np.abs(got["d2N"]).max())
+
+
+def test_element_centres_after_refinement_through_cuda():
+    """trimmedgridtests.cpp:197-217: geometry().center() of the four elements of the once-refined bilinear unit square,
+    compared with == as the reference does; the refinement itself runs on the device (igab_refine_apply)."""
+    c = G["element_centres"]
+    pd = PD.NurbsPatchData(c["knots"], c["cp"], c["degree"], c["dimworld"]).globalRefine(c["refine_level"])
+    P = capi.Patch.fromPatchData(pd)
+    assert P.nelem == 4
+    x = P.evalPoints(np.arange(4, dtype=np.int32), np.full((4, 2), 0.5), order=0, want=("x",))["x"]
+    assert np.array_equal(x, np.array(c["centres"]))
+    xt = P.evalTensor([np.array([0.5])] * 2, order=0, want=("x",))["x"]
+    assert np.array_equal(xt, np.array(c["centres"]))

@@ -332,3 +332,16 @@ def test_field_norms_port_properties():
     full = Pp.norms(xi1d, w1d, u2, ncomp=2)
     parts = Pp.norms(xi1d, w1d, u2, ncomp=2, elem_end=h) + Pp.norms(xi1d, w1d, u2, ncomp=2, elem_begin=h)
     assert np.abs(full - parts).max() < 1e-12 * full.max()
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_element_centres_after_refinement(impl):
+    """trimmedgridtests.cpp:197-217: centres of the four elements of the once-refined unit square, compared with ==."""
+    from dune_iga_b200 import patchdata as PD
+    c = G["element_centres"]
+    pd = PD.NurbsPatchData(c["knots"], c["cp"], c["degree"], c["dimworld"]).globalRefine(c["refine_level"])
+    P = make(impl, pd.degree, pd.knotSpans, pd.cp, 2)
+    spans = [(0.0, 0.5), (0.5, 1.0)]
+    for e, centre in enumerate(c["centres"]):
+        u = [0.5 * sum(spans[e % 2]), 0.5 * sum(spans[e // 2])]
+        assert np.array_equal(P.geo_global(u), np.array(centre)), (e, P.geo_global(u))
