@@ -24,7 +24,7 @@ EXPORTS = ("igab_last_error_string", "igab_version", "igab_launch_count", "igab_
            "igab_patch_create", "igab_patch_destroy", "igab_patch_sizes", "igab_patch_set_kernel",
            "igab_patch_update_control_points", "igab_patch_spans", "igab_patch_dofmap", "igab_eval_tensor",
            "igab_eval_points", "igab_partial", "igab_assemble", "igab_reduce_volume", "igab_csr_pattern",
-           "igab_csr_assemble", "igab_eval_faces", "igab_refine_apply", "igab_surface_forms", "igab_geometry_local", "igab_reduce_norms")
+           "igab_csr_assemble", "igab_eval_faces", "igab_refine_apply", "igab_surface_forms", "igab_geometry_local", "igab_reduce_norms", "igab_local_keys")
 
 
 class EvalOut(C.Structure):
@@ -76,6 +76,7 @@ def lib():
                                           C.c_void_p]
         L.igab_reduce_norms.argtypes = [C.c_void_p, C.c_int64, C.c_int64, ip, C.POINTER(dp), C.POINTER(dp), C.c_void_p,
                                         C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
+        L.igab_local_keys.argtypes = [C.c_int, ip, C.c_void_p, C.c_void_p, C.c_void_p]
         L.igab_refine_apply.argtypes = [C.c_int, C.c_int, ip, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, dp, dp,
                                         dp]
         L.igab_reduce_volume.argtypes = [C.c_void_p, C.c_int64, C.c_int64, ip, C.POINTER(dp), C.POINTER(dp),
@@ -400,6 +401,16 @@ class Patch:
         _check(lib().igab_reduce_norms(self.h, elem_begin, elem_end, nq1.ctypes.data_as(ip), xp, wp, ua, ncomp, us, r,
                                        nccl_comm, stream))
         return np.array([r[0], r[1]])
+
+
+def localKeys(degree):
+    """(subEntity, codim, index) uint32 arrays of the local shape functions: NurbsLocalCoefficients::init,
+    nurbsbasis.hh:220-271.  Host integers; works without a device."""
+    deg = _i32(degree)
+    nb = int(np.prod(deg + 1))
+    sub, cod, idx = (np.empty(nb, dtype=np.uint32) for _ in range(3))
+    _check(lib().igab_local_keys(len(deg), deg.ctypes.data_as(ip), sub.ctypes.data, cod.ctypes.data, idx.ctypes.data))
+    return sub, cod, idx
 
 
 def surfaceForms(Jt, H=None, want=("normal", "unitNormal", "metric", "secondFF", "gaussK"), stream=None):

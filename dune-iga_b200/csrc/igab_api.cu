@@ -929,6 +929,54 @@ igab_status igab_geometry_local(igab_patch* p, int64_t npts, const int32_t* elem
   return st;
 }
 
+// ---- local keys (host integers) ------------------------------------------------------------------------------------------
+igab_status igab_local_keys(int dim, const int* degree, uint32_t* sub_entity, uint32_t* codim, uint32_t* index) {
+  if (dim < 1 || dim > kMaxDim || !degree || !sub_entity || !codim || !index) {
+    set_error("local_keys: null argument or dim outside 1..3");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  unsigned sizes[kMaxDim] = {1, 1, 1};
+  unsigned nb = 1;
+  for (int d = 0; d < dim; ++d) {
+    if (degree[d] < 0 || degree[d] > kMaxDegree) {
+      set_error("local_keys: degree outside 0..8");
+      return IGAB_INVALID_ARGUMENT;
+    }
+    sizes[d] = (unsigned)degree[d] + 1;
+    nb *= sizes[d];
+  }
+  for (unsigned i = 0; i < nb; ++i) {
+    unsigned m[kMaxDim], r = i;
+    for (int d = 0; d < dim; ++d) {
+      m[d] = r % sizes[d];
+      r /= sizes[d];
+    }
+    unsigned cd = 0, ix = 0;
+    for (int d = 0; d < dim; ++d)
+      if (m[d] == 0 || m[d] == sizes[d] - 1) ++cd;
+    for (int d = dim - 1; d >= 0; --d)
+      if (m[d] > 0 && m[d] < sizes[d] - 1) ix = (sizes[d] - 1) * ix + (m[d] - 1);
+    codim[i] = cd;
+    index[i] = ix;
+    sub_entity[i] = 0;
+  }
+  if (dim == 1 && sizes[0] > 1) {
+    sub_entity[nb - 1] = 1;  // 0----0----1
+  } else if (dim == 2 && sizes[0] > 1 && sizes[1] > 1) {
+    // vertices 0 1 / 2 3, edges: left 0, right 1, lower 2, upper 3, face 0
+    for (unsigned j = 0; j < sizes[1]; ++j)
+      for (unsigned i = 0; i < sizes[0]; ++i) {
+        const bool lo0 = i == 0, hi0 = i == sizes[0] - 1, lo1 = j == 0, hi1 = j == sizes[1] - 1;
+        unsigned s = 0;
+        if (lo1) s = lo0 ? 0 : (hi0 ? 1 : 2);
+        else if (hi1) s = lo0 ? 2 : 3;  // corner 2, inner dofs of the upper edge 3, corner 3
+        else s = hi0 ? 1 : 0;           // left edge 0 / face 0 / right edge 1
+        sub_entity[j * sizes[0] + i] = s;
+      }
+  }
+  return IGAB_OK;
+}
+
 // ---- global CSR -----------------------------------------------------------------------------------------------------
 igab_status igab_csr_pattern(igab_patch* p, int ncomp, int64_t* nrows, int64_t* nnz, int64_t* rowptr, int32_t* colidx,
                              igab_memspace space, void* stream) {

@@ -11,6 +11,7 @@
 //   NurbsLocalBasis::order / size       dune/iga/nurbsbasis.hh:117-123     LocalBasis::order / size
 //   NurbsLocalFiniteElement::bind       dune/iga/nurbsbasis.hh:355-375     LocalView::bind(elementIndex)
 //   NurbsPreBasis::indices / size       dune/iga/nurbsbasis.hh:590-598,625 LocalView::index(i), PreBasis::size/dimension
+//   NurbsLocalCoefficients::localKey    dune/iga/nurbsbasis.hh:150-290     LocalView::localCoefficients().localKey(i)
 //   NURBSGeometry::global               dune/iga/nurbsgeometry.hh:133-138  Geometry::global
 //   NURBSGeometry::jacobianTransposed   dune/iga/nurbsgeometry.hh:182-196  Geometry::jacobianTransposed
 //   NURBSGeometry::integrationElement   dune/iga/nurbsgeometry.hh:200-203  Geometry::integrationElement
@@ -481,11 +482,38 @@ private:
   int64_t e_ = 0;
 };
 
+// ---- NurbsLocalCoefficients (nurbsbasis.hh:150-290): LocalKey (subEntity, codim, index) per local shape function ----
+struct LocalKey {
+  unsigned int subEntity_, codim_, index_;
+  unsigned int subEntity() const { return subEntity_; }
+  unsigned int codim() const { return codim_; }
+  unsigned int index() const { return index_; }
+};
+template <int dim>
+class LocalCoefficients {
+public:
+  LocalCoefficients() = default;
+  explicit LocalCoefficients(const std::array<int, dim>& degree) {
+    std::size_t nb = 1;
+    for (int d : degree) nb *= (std::size_t)d + 1;
+    std::vector<uint32_t> s(nb), c(nb), x(nb);
+    check(igab_local_keys(dim, degree.data(), s.data(), c.data(), x.data()));
+    li_.resize(nb);
+    for (std::size_t i = 0; i < nb; ++i) li_[i] = LocalKey{s[i], c[i], x[i]};
+  }
+  std::size_t size() const { return li_.size(); }
+  const LocalKey& localKey(std::size_t i) const { return li_[i]; }
+
+private:
+  std::vector<LocalKey> li_;
+};
+
 // ---- LocalView of a NurbsBasis: bind(element) / index(i) / tree().finiteElement().localBasis() --------------------
 template <int dim, int dimworld>
 class LocalView {
 public:
-  explicit LocalView(std::shared_ptr<const Patch<dim, dimworld>> p) : p_(std::move(p)) {}
+  explicit LocalView(std::shared_ptr<const Patch<dim, dimworld>> p)
+      : p_(std::move(p)), lc_(p_->patchData().degree) {}
   void bind(int64_t elementIndex) {
     if (elementIndex < 0 || elementIndex >= p_->size0()) throw Error(IGAB_INVALID_ARGUMENT, "bind: no such element");
     e_ = elementIndex;
@@ -503,10 +531,13 @@ public:
     if (!bound_) throw Error(IGAB_INVALID_ARGUMENT, "This element is not bound!");
     return lb_;
   }
+  // NurbsLocalFiniteElement::localCoefficients (nurbsbasis.hh:386-388)
+  const LocalCoefficients<dim>& localCoefficients() const { return lc_; }
   Geometry<dim, dimworld> geometry() const { return Geometry<dim, dimworld>(p_.get(), e_); }
 
 private:
   std::shared_ptr<const Patch<dim, dimworld>> p_;
+  LocalCoefficients<dim> lc_;
   LocalBasis<dim, dimworld> lb_;
   int64_t e_ = 0;
   bool bound_ = false;

@@ -114,6 +114,12 @@ igab_status igab_patch_spans(igab_patch* p, int32_t* span, igab_memspace space, 
  * dof [n_elem][nb]; entries of IGAB_TRIM_EMPTY elements whose DOF was dropped are -1; *ndof = size of the basis.   */
 igab_status igab_patch_dofmap(igab_patch* p, int32_t* dof, int64_t* ndof, igab_memspace space, void* stream);
 
+/* Replaces NurbsLocalCoefficients::init (nurbsbasis.hh:220-271): the LocalKey (subEntity, codim, index) of each of the
+ * nb = prod(degree_d + 1) local shape functions, identical for every element.  codim = number of directions in which the
+ * function sits on the element boundary; index = position among the functions of the same sub-entity; subEntity as
+ * setup1d / setup2d number it (:162-216) -- like the reference, 0 for dim 3.  Pure integer host code, no device needed. */
+igab_status igab_local_keys(int dim, const int* degree, uint32_t* sub_entity, uint32_t* codim, uint32_t* index);
+
 /* ---- batched evaluation -------------------------------------------------------------------------------------------
  * Replaces, for every point of every element in [elem_begin, elem_end) at the tensor rule xi1d[d][0..nq1[d]):
  * the user quadrature loop calling evaluateFunction / evaluateJacobian / partial (nurbsbasis.hh:77-108) and

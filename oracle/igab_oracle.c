@@ -927,6 +927,40 @@ int igo_norms(const igo_patch* P, long elem_begin, long elem_end, const int* nq1
   return 0;
 }
 
+/* ---- a9: NurbsLocalCoefficients::init (dune/iga/nurbsbasis.hh:220-271, setup1d :162-180, setup2d :182-216) ----------
+ * LocalKey (subEntity, codim, index) per local shape function; sizes_d = degree_d + 1; dim 3 leaves subEntity 0.     */
+void igo_local_keys(int dim, const int* degree, unsigned* sub, unsigned* codim, unsigned* index) {
+  unsigned sizes[MAXDIM] = {1, 1, 1}, nb = 1;
+  for (int d = 0; d < dim; ++d) { sizes[d] = degree[d] + 1; nb *= sizes[d]; }
+  for (unsigned i = 0; i < nb; ++i) {
+    unsigned m[MAXDIM], r = i;
+    for (int d = 0; d < dim; ++d) { m[d] = r % sizes[d]; r /= sizes[d]; }
+    codim[i] = 0; index[i] = 0; sub[i] = 0;
+    for (int j = 0; j < dim; ++j) if (m[j] == 0 || m[j] == sizes[j] - 1) codim[i]++;
+    for (int j = dim - 1; j >= 0; --j) if (m[j] > 0 && m[j] < sizes[j] - 1) index[i] = (sizes[j] - 1) * index[i] + (m[j] - 1);
+  }
+  if (dim == 1) {
+    if (sizes[0] == 1) return;
+    unsigned last = 0;
+    sub[last++] = 0;
+    for (unsigned i = 0; i + 2 < sizes[0]; ++i) sub[last++] = 0;
+    sub[last++] = 1;
+  } else if (dim == 2 && sizes[0] > 1 && sizes[1] > 1) {
+    unsigned last = 0;
+    sub[last++] = 0;                                                /* corner 0 */
+    for (unsigned i = 0; i + 2 < sizes[0]; ++i) sub[last++] = 2;   /* lower edge */
+    sub[last++] = 1;                                                /* corner 1 */
+    for (unsigned e = 0; e + 2 < sizes[1]; ++e) {
+      sub[last++] = 0;                                              /* left edge */
+      for (unsigned i = 0; i + 2 < sizes[0]; ++i) sub[last++] = 0; /* face */
+      sub[last++] = 1;                                              /* right edge */
+    }
+    sub[last++] = 2;                                                /* corner 2 */
+    for (unsigned i = 0; i + 2 < sizes[0]; ++i) sub[last++] = 3;   /* upper edge */
+    sub[last++] = 3;                                                /* corner 3 */
+  }
+}
+
 int igo_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -276,5 +276,15 @@ def surface_forms(Jt, H=None, want=("normal", "unitNormal", "metric", "secondFF"
     return {k: v for k, v in out.items() if v is not None}
 
 
+def local_keys(degree):
+    deg = _i32(degree)
+    nb = int(np.prod(deg + 1))
+    sub, cod, idx = (np.empty(nb, dtype=np.uint32) for _ in range(3))
+    up = C.POINTER(C.c_uint)
+    lib().igo_local_keys.argtypes = [C.c_int, ip, up, up, up]
+    lib().igo_local_keys(len(deg), _i(deg), sub.ctypes.data_as(up), cod.ctypes.data_as(up), idx.ctypes.data_as(up))
+    return sub, cod, idx
+
+
 def max_threads():
     return lib().igo_max_threads()

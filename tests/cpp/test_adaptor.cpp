@@ -159,6 +159,13 @@ int main() {
       }
     }
   CHECK(localView.localBasis().order() == 2 && localView.localBasis().size() == 9, "order/size");
+  {  // LocalKeys of the p = (2,2) element (nurbsbasis.hh:182-216): corners codim 2, edge midpoints codim 1, centre codim 0
+    const auto& lc = localView.localCoefficients();
+    const unsigned sub[9] = {0, 2, 1, 0, 0, 1, 2, 3, 3}, cod[9] = {2, 1, 2, 1, 0, 1, 2, 1, 2};
+    CHECK(lc.size() == 9, "local coefficients size");
+    for (int i = 0; i < 9; ++i)
+      CHECK(lc.localKey(i).subEntity() == sub[i] && lc.localKey(i).codim() == cod[i] && lc.localKey(i).index() == 0, "local key %d", i);
+  }
 
   // error behaviour: unbound view, bad element, bad knot vector
   igab::LocalView<dim, dw> v2(patch);

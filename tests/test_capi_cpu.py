@@ -62,3 +62,30 @@ def test_no_cpu_fallback_without_device():
     with pytest.raises(capi.IgabError) as ei:
         capi.Patch([1], [[0, 0, 1, 1]], [[0, 0, 1], [1, 0, 1]], 2)
     assert ei.value.status in (3, 2)
+
+
+def test_local_keys_match_oracle_and_reference_diagram():
+    """igab_local_keys (host integers, no device) == the oracle's restatement of NurbsLocalCoefficients::init
+    (nurbsbasis.hh:220-271) for every degree combination up to 4, and the p=(2,2) table read off the reference's edge /
+    vertex diagram (:182-216)."""
+    import itertools
+    import portbind as PT
+    for dim in (1, 2, 3):
+        for deg in itertools.product(range(0, 5), repeat=dim):
+            got = capi.localKeys(deg)
+            ref = PT.local_keys(deg)
+            for a, b in zip(got, ref):
+                assert np.array_equal(a, b), (deg, a, b)
+    sub, cod, idx = capi.localKeys([2, 2])
+    assert list(sub) == [0, 2, 1, 0, 0, 1, 2, 3, 3]
+    assert list(cod) == [2, 1, 2, 1, 0, 1, 2, 1, 2]
+    assert list(idx) == [0] * 9
+    sub, cod, idx = capi.localKeys([3, 2])  # two inner dofs on the horizontal edges
+    assert list(idx) == [0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1, 0]
+    assert list(capi.localKeys([3])[0]) == [0, 0, 0, 1]
+    # (subEntity, codim, index) identifies a shape function uniquely in 1-D and 2-D
+    for deg in ([4], [3, 4], [2, 2]):
+        keys = set(zip(*[k.tolist() for k in capi.localKeys(deg)]))
+        assert len(keys) == int(np.prod(np.array(deg) + 1))
+    with pytest.raises(capi.IgabError):
+        capi.localKeys([9])
