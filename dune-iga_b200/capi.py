@@ -24,7 +24,8 @@ EXPORTS = ("igab_last_error_string", "igab_version", "igab_launch_count", "igab_
            "igab_patch_create", "igab_patch_destroy", "igab_patch_sizes", "igab_patch_set_kernel",
            "igab_patch_update_control_points", "igab_patch_spans", "igab_patch_dofmap", "igab_eval_tensor",
            "igab_eval_points", "igab_partial", "igab_assemble", "igab_reduce_volume", "igab_csr_pattern",
-           "igab_csr_assemble", "igab_eval_faces", "igab_refine_apply", "igab_surface_forms", "igab_geometry_local", "igab_reduce_norms", "igab_local_keys")
+           "igab_csr_assemble", "igab_eval_faces", "igab_refine_apply", "igab_surface_forms", "igab_geometry_local", "igab_reduce_norms", "igab_local_keys", "igab_rhs_assemble",
+           "igab_csr_dirichlet")
 
 
 class EvalOut(C.Structure):
@@ -76,6 +77,10 @@ def lib():
                                           C.c_void_p]
         L.igab_reduce_norms.argtypes = [C.c_void_p, C.c_int64, C.c_int64, ip, C.POINTER(dp), C.POINTER(dp), C.c_void_p,
                                         C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
+        L.igab_rhs_assemble.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_void_p]
+        L.igab_csr_dirichlet.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_void_p]
         L.igab_local_keys.argtypes = [C.c_int, ip, C.c_void_p, C.c_void_p, C.c_void_p]
         L.igab_refine_apply.argtypes = [C.c_int, C.c_int, ip, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, dp, dp,
                                         dp]
@@ -331,6 +336,34 @@ class Patch:
         _check(lib().igab_eval_faces(self.h, len(elem), elem.ctypes.data, face.ctypes.data, nqf1.ctypes.data_as(ip),
                                      ptrs, x.ctypes.data, nrm.ctypes.data, dS.ctypes.data, HOST, None))
         return dict(x=x, normal=nrm, dS=dS)
+
+    def rhsAssemble(self, fe, ncomp=1, elem_begin=0, elem_end=None, b=None, accumulate=False, stream=None):
+        """b[nrows] (+)= gather of the element load vectors fe of elements [elem_begin, elem_end) (poisson.py:121)."""
+        if elem_end is None:
+            elem_end = self.nelem
+        fa, fs = _ptr(fe)
+        if b is None:
+            nrows = self.ndof_untrimmed * ncomp
+            if fs == HOST:
+                b = np.zeros(nrows)
+            else:
+                import torch
+                b = torch.zeros(nrows, dtype=torch.float64, device=fe.device)
+        ba, bs = _ptr(b)
+        assert bs == fs
+        _check(lib().igab_rhs_assemble(self.h, ncomp, elem_begin, elem_end, fa, ba, int(accumulate), fs, stream))
+        return b
+
+    def csrDirichlet(self, mask, values, b=None, g=None, ncomp=1, stream=None):
+        """Identity rows for the marked DOFs and b = g there, in place (poisson.py:91-93,117-119)."""
+        if isinstance(mask, np.ndarray):
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        ma, ms = _ptr(mask)
+        va, vs = _ptr(values)
+        assert ms == vs
+        _check(lib().igab_csr_dirichlet(self.h, ncomp, ma, _ptr(g)[0] if g is not None else None, va,
+                                        _ptr(b)[0] if b is not None else None, vs, stream))
+        return values, b
 
     # ---- inverse map
     def local(self, elem, xglobal):

@@ -116,6 +116,67 @@ __global__ void csr_gather_kernel(CsrGeom G, long long nrows, long long elem_beg
   }
 }
 
+// global load vector: b[g*ncomp + c] (+)= sum over the elements of [elem_begin, elem_end) that contain DOF g of
+// fe[e][i*ncomp + c] (dune/python/test/poisson.py:121, b[gi] += localb[i]); one thread per row, fixed element order
+__global__ void rhs_gather_kernel(CsrGeom G, long long nrows, long long elem_begin, long long elem_end,
+                                  const double* __restrict__ fe, double* __restrict__ b, int accumulate) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nrows) return;
+  int gd[kMaxDim], lo[kMaxDim], len[kMaxDim];
+  row_box(G, row / G.ncomp, gd, lo, len);
+  const int c = (int)(row % G.ncomp);
+  const long long n = (long long)G.nb * G.ncomp;
+  const int o0 = G.p[0] + 1, o1 = G.dim > 1 ? G.p[1] + 1 : 1;
+  int fa[kMaxDim], fb[kMaxDim];
+  for (int q = 0; q < kMaxDim; ++q) {
+    fa[q] = q < G.dim ? max(gd[q] - G.p[q], 0) : 0;
+    fb[q] = q < G.dim ? min(gd[q], G.n[q] - 1 - G.p[q]) : 0;
+  }
+  double acc = 0.0;
+  for (int f2 = fa[2]; f2 <= fb[2]; ++f2) {
+    const int e2 = G.dim > 2 ? G.elemOfFirst[2][f2] : 0;
+    if (e2 < 0) continue;
+    for (int f1 = fa[1]; f1 <= fb[1]; ++f1) {
+      const int e1 = G.dim > 1 ? G.elemOfFirst[1][f1] : 0;
+      if (e1 < 0) continue;
+      for (int f0 = fa[0]; f0 <= fb[0]; ++f0) {
+        const int e0 = G.elemOfFirst[0][f0];
+        if (e0 < 0) continue;
+        const long long e = e0 + (long long)G.nel[0] * (e1 + (long long)(G.dim > 1 ? G.nel[1] : 1) * e2);
+        if (e < elem_begin || e >= elem_end) continue;
+        const int i = (gd[0] - f0) + o0 * ((gd[1] - f1) + o1 * (gd[2] - f2));
+        acc += fe[(e - elem_begin) * n + i * G.ncomp + c];
+      }
+    }
+  }
+  b[row] = accumulate ? b[row] + acc : acc;
+}
+
+// Dirichlet rows as the reference's assembler sets them (poisson.py:117-119): row gi of a marked DOF becomes the identity
+// row (columns are left alone), b[gi] = g[gi].  One warp per row; the column of an entry is closed-form.
+__global__ void dirichlet_rows_kernel(CsrGeom G, long long nrows, const long long* __restrict__ rowptr,
+                                      const uint8_t* __restrict__ mask, const double* __restrict__ gval,
+                                      double* __restrict__ values, double* __restrict__ b) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= nrows || !mask[row]) return;
+  int gd[kMaxDim], lo[kMaxDim], len[kMaxDim];
+  row_box(G, row / G.ncomp, gd, lo, len);
+  const long long base = rowptr[row];
+  const int nn = len[0] * len[1] * len[2] * G.ncomp;
+  for (int k = lane; k < nn; k += 32) {
+    const int d = k % G.ncomp;
+    int kk = k / G.ncomp;
+    const int c0 = lo[0] + kk % len[0];
+    kk /= len[0];
+    const int c1 = lo[1] + kk % len[1];
+    const int c2 = lo[2] + kk / len[1];
+    const long long h = c0 + (long long)G.n[0] * (c1 + (long long)(G.dim > 1 ? G.n[1] : 1) * c2);
+    values[base + k] = (h * G.ncomp + d == row) ? 1.0 : 0.0;
+  }
+  if (lane == 0 && b) b[row] = gval ? gval[row] : 0.0;
+}
+
 igab_status make_geom(igab_patch* p, int ncomp, CsrGeom* G) {
   if (ncomp < 1 || ncomp > 3) {
     set_error("csr: ncomp must be 1..3");
@@ -239,6 +300,87 @@ igab_status csr_assemble(igab_patch* p, int ncomp, long long eb, long long ee, c
     cudaFree(dV);
   }
   if (e != cudaSuccess) return cuda_fail(e, "csr gather");
+  return IGAB_OK;
+}
+
+igab_status rhs_assemble(igab_patch* p, int ncomp, long long eb, long long ee, const double* fe, double* b, int accumulate,
+                         igab_memspace space, cudaStream_t stream) {
+  CsrGeom G;
+  igab_status st = make_geom(p, ncomp, &G);
+  if (st) return st;
+  const long long nrows = p->ndof_untrimmed * ncomp, n = (long long)p->dev.nb * ncomp, nel = ee - eb;
+  const double* dF = fe;
+  double* dB = b;
+  double* tmp = nullptr;
+  if (space == IGAB_HOST) {
+    IGAB_CUDA_TRY(cudaMalloc(&tmp, sizeof(double) * (std::max(1LL, nel * n) + nrows)));
+    dB = tmp + std::max(1LL, nel * n);
+    cudaError_t e = cudaMemcpyAsync(tmp, fe, sizeof(double) * nel * n, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess && accumulate) e = cudaMemcpyAsync(dB, b, sizeof(double) * nrows, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) {
+      cudaFree(tmp);
+      return cuda_fail(e, "rhs staging");
+    }
+    dF = tmp;
+  }
+  rhs_gather_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, stream>>>(G, nrows, eb, ee, dF, dB, accumulate);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (space == IGAB_HOST) {
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b, dB, sizeof(double) * nrows, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(tmp);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "rhs gather");
+  return IGAB_OK;
+}
+
+igab_status csr_dirichlet(igab_patch* p, int ncomp, const uint8_t* mask, const double* gval, double* values, double* b,
+                          igab_memspace space, cudaStream_t stream) {
+  CsrGeom G;
+  igab_status st = make_geom(p, ncomp, &G);
+  if (st) return st;
+  int64_t nrows = 0, nnz = 0;
+  if ((st = csr_pattern(p, ncomp, &nrows, &nnz, nullptr, nullptr, IGAB_HOST, stream))) return st;
+  const uint8_t* dM = mask;
+  const double* dG = gval;
+  double *dV = values, *dB = b;
+  uint8_t* tM = nullptr;
+  double* tmp = nullptr;
+  if (space == IGAB_HOST) {
+    IGAB_CUDA_TRY(cudaMalloc(&tM, (size_t)nrows));
+    cudaError_t e = cudaMalloc(&tmp, sizeof(double) * (nnz + 2 * nrows));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tM, mask, (size_t)nrows, cudaMemcpyHostToDevice, stream);
+    dV = tmp;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dV, values, sizeof(double) * nnz, cudaMemcpyHostToDevice, stream);
+    if (b) {
+      dB = tmp + nnz;
+      if (e == cudaSuccess) e = cudaMemcpyAsync(dB, b, sizeof(double) * nrows, cudaMemcpyHostToDevice, stream);
+    }
+    if (gval) {
+      double* t = tmp + nnz + nrows;
+      if (e == cudaSuccess) e = cudaMemcpyAsync(t, gval, sizeof(double) * nrows, cudaMemcpyHostToDevice, stream);
+      dG = t;
+    }
+    if (e != cudaSuccess) {
+      cudaFree(tM);
+      if (tmp) cudaFree(tmp);
+      return cuda_fail(e, "dirichlet staging");
+    }
+    dM = tM;
+  }
+  const long long threads = (long long)nrows * 32;
+  dirichlet_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(G, nrows, p->d_csr_rowptr, dM, dG, dV, dB);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (space == IGAB_HOST) {
+    if (e == cudaSuccess) e = cudaMemcpyAsync(values, dV, sizeof(double) * nnz, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && b) e = cudaMemcpyAsync(b, dB, sizeof(double) * nrows, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(tM);
+    cudaFree(tmp);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "dirichlet rows");
   return IGAB_OK;
 }
 

@@ -929,6 +929,27 @@ igab_status igab_geometry_local(igab_patch* p, int64_t npts, const int32_t* elem
   return st;
 }
 
+igab_status igab_rhs_assemble(igab_patch* p, int ncomp, int64_t elem_begin, int64_t elem_end, const double* fe, double* b,
+                              int accumulate, igab_memspace space, void* stream) {
+  if (!p || !fe || !b) {
+    set_error("rhs_assemble: null argument");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  if (elem_begin < 0 || elem_end < elem_begin || elem_end > p->dev.nelem) {
+    set_error("rhs_assemble: element range outside [0, n_elem]");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  return rhs_assemble(p, ncomp, elem_begin, elem_end, fe, b, accumulate, space, (cudaStream_t)stream);
+}
+igab_status igab_csr_dirichlet(igab_patch* p, int ncomp, const uint8_t* mask, const double* g, double* values, double* b,
+                               igab_memspace space, void* stream) {
+  if (!p || !mask || !values) {
+    set_error("csr_dirichlet: null argument");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  return csr_dirichlet(p, ncomp, mask, g, values, b, space, (cudaStream_t)stream);
+}
+
 // ---- local keys (host integers) ------------------------------------------------------------------------------------------
 igab_status igab_local_keys(int dim, const int* degree, uint32_t* sub_entity, uint32_t* codim, uint32_t* index) {
   if (dim < 1 || dim > kMaxDim || !degree || !sub_entity || !codim || !index) {

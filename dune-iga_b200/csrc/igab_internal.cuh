@@ -139,6 +139,11 @@ igab_status csr_pattern(igab_patch* p, int ncomp, int64_t* nrows, int64_t* nnz, 
 igab_status csr_assemble(igab_patch* p, int ncomp, long long eb, long long ee, const double* Ke, const int64_t* rowptr,
                          double* values, int accumulate, igab_memspace space, cudaStream_t stream);
 
+igab_status rhs_assemble(igab_patch* p, int ncomp, long long eb, long long ee, const double* fe, double* b, int accumulate,
+                         igab_memspace space, cudaStream_t stream);
+igab_status csr_dirichlet(igab_patch* p, int ncomp, const uint8_t* mask, const double* gval, double* values, double* b,
+                          igab_memspace space, cudaStream_t stream);
+
 }  // namespace igab
 
 // The host-side object behind the opaque handle.

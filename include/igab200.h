@@ -213,6 +213,16 @@ igab_status igab_csr_assemble(igab_patch* p, int ncomp, int64_t elem_begin, int6
                               const int64_t* rowptr, double* values, int accumulate, igab_memspace space,
                               void* stream);
 
+/* Global load vector, same gather: b[nrows] (+)= sum over the elements [elem_begin, elem_end) of fe[e - elem_begin][i]
+ * (poisson.py:121, b[gi] += localb[i]).                                                                            */
+igab_status igab_rhs_assemble(igab_patch* p, int ncomp, int64_t elem_begin, int64_t elem_end, const double* fe, double* b,
+                              int accumulate, igab_memspace space, void* stream);
+/* Dirichlet rows as the reference's assembler sets them (poisson.py:91-93,117-119): for every row with mask[row] != 0
+ * the row of `values` becomes the identity row (columns are left alone, as in the reference) and, when b is given,
+ * b[row] = g[row] (0 when g is NULL).  mask [nrows] bytes, g / b [nrows], values [nnz] -- all in `space`.          */
+igab_status igab_csr_dirichlet(igab_patch* p, int ncomp, const uint8_t* mask, const double* g, double* values, double* b,
+                               igab_memspace space, void* stream);
+
 /* ---- patch reductions ---------------------------------------------------------------------------------------------
  * Replaces the user loop summing NURBSGeometry::volume() over elements (nurbsgeometry.hh:96-113,
  * dune/iga/test/gridtests.cpp:338-341): result = sum_{e in range} sum_q detJ w.  Deterministic two-level tree sum.

@@ -787,3 +787,52 @@ def test_element_centres_after_refinement_through_cuda():
     assert np.array_equal(x, np.array(c["centres"]))
     xt = P.evalTensor([np.array([0.5])] * 2, order=0, want=("x",))["x"]
     assert np.array_equal(xt, np.array(c["centres"]))
+
+
+def test_poisson_global_assembler_on_the_device():
+    """The whole globalAssembler of dune/python/test/poisson.py:84-127 on the device: element matrices and load vectors,
+    CSR gather, load-vector gather, Dirichlet rows (first floor(sqrt(N)) DOFs, identity rows, columns untouched) -- against
+    the same loop written with the oracle's element matrices and a dense scatter; then both systems are solved."""
+    import math
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    spec = PFT.small_patch("plate_hole_p2")
+    Pp = port_for(spec)
+    P = gpu_patch(spec)
+    rule = [PD.gaussLegendre01(p + 1) for p in spec["degree"]]
+    xi1d, w1d = [r[0] for r in rule], [r[1] for r in rule]
+    Ke, fe = P.assemble(capi.ASM_POISSON, xi1d, w1d, fconst=1.0)
+    rowptr, colidx = P.csrPattern()
+    vals = P.csrAssemble(Ke)
+    b = P.rhsAssemble(fe)
+    N = len(rowptr) - 1
+    mask = np.zeros(N, dtype=np.uint8)
+    mask[:math.floor(math.sqrt(N))] = 1
+    vals, b = P.csrDirichlet(mask, vals, b=b)
+    A = sp.csr_matrix((vals, colidx, rowptr), shape=(N, N))
+    # the reference loop with the oracle's element matrices
+    Kref, fref = Pp.assemble(capi.ASM_POISSON, xi1d, w1d, fconst=1.0)
+    dof, _ = Pp.dofmap()
+    Ad, bd = np.zeros((N, N)), np.zeros(N)
+    for e in range(Pp.nelem):
+        for i in range(Pp.nb):
+            gi = dof[e, i]
+            if mask[gi]:
+                Ad[gi, gi] = 1.0
+                bd[gi] = 0.0
+            else:
+                bd[gi] += fref[e, i]
+                Ad[gi, dof[e]] += Kref[e, i]
+    assert np.abs(A.toarray() - Ad).max() <= 1e-12 * np.abs(Ad).max()
+    assert np.abs(b - bd).max() <= 1e-12 * np.abs(bd).max()
+    x = spla.spsolve(A.tocsc(), b)
+    xd = np.linalg.solve(Ad, bd)
+    assert np.abs(x - xd).max() <= 1e-9 * np.abs(xd).max()
+    assert np.abs(x[:math.floor(math.sqrt(N))]).max() == 0.0
+    # device-resident arrays, two element ranges accumulated: same bits as the single call
+    import torch
+    h = P.nelem // 2
+    fd = torch.from_numpy(fe).cuda()
+    b2 = P.rhsAssemble(fd[:h].contiguous(), elem_end=h)
+    b2 = P.rhsAssemble(fd[h:].contiguous(), elem_begin=h, b=b2, accumulate=True)
+    assert np.abs(b2.cpu().numpy() - P.rhsAssemble(fe)).max() <= 1e-14 * np.abs(bd).max()
