@@ -836,3 +836,54 @@ def test_poisson_global_assembler_on_the_device():
     b2 = P.rhsAssemble(fd[:h].contiguous(), elem_end=h)
     b2 = P.rhsAssemble(fd[h:].contiguous(), elem_begin=h, b=b2, accumulate=True)
     assert np.abs(b2.cpu().numpy() - P.rhsAssemble(fe)).max() <= 1e-14 * np.abs(bd).max()
+
+
+def _random_patch(rng, dim, dw, degree):
+    """Open knot vectors with random interior knots of random multiplicity (<= p: C^0 lines included), random positive
+    weights, control points = a perturbed lattice (so that detJ stays away from 0)."""
+    knots, ncp = [], []
+    for p in degree:
+        inner = []
+        for u in np.sort(rng.uniform(0.1, 0.9, rng.integers(1, 4))):
+            inner += [float(u)] * int(rng.integers(1, p + 1))
+        U = np.array([0.0] * (p + 1) + inner + [1.0] * (p + 1))
+        knots.append(U)
+        ncp.append(len(U) - p - 1)
+    grids = np.meshgrid(*[np.linspace(0, 1 + 0.3 * d, n) for d, n in enumerate(ncp)], indexing="ij")
+    pts = np.stack([g.transpose(*range(dim - 1, -1, -1)).reshape(-1) for g in grids], axis=1)  # first direction fastest
+    cp = np.zeros((pts.shape[0], dw + 1))
+    cp[:, :dim] = pts
+    cp[:, :dw] += rng.normal(0, 0.02, (pts.shape[0], dw))
+    if dw > dim:
+        cp[:, dim] += 0.3 * np.sin(2 * pts[:, 0]) * (pts[:, -1] + 0.5)
+    cp[:, dw] = rng.uniform(0.5, 2.0, pts.shape[0])
+    return dict(degree=list(degree), knots=knots, cp=cp, dimworld=dw)
+
+
+@pytest.mark.parametrize("case", [(1, 2, (3,)), (1, 3, (2,)), (2, 2, (2, 2)), (2, 2, (3, 3)), (2, 2, (1, 1)), (2, 2, (3, 2)),
+                                  (2, 3, (2, 2)), (2, 3, (3, 3)), (3, 3, (2, 2, 2)), (3, 3, (3, 3, 3)), (3, 3, (4, 4, 4)),
+                                  (3, 3, (1, 2, 3)), (3, 3, (1, 1, 1))],
+                         ids=lambda c: "d%dw%d_p%s" % (c[0], c[1], "".join(map(str, c[2]))))
+def test_random_patches_with_repeated_knots(case):
+    """Seeded random patches (repeated interior knots up to multiplicity p, random weights) through the tuned kernels
+    (auto) and the general kernel against the oracle, all fields up to second order; spans and DOF maps bit-exact."""
+    dim, dw, degree = case
+    rng = np.random.default_rng(1000 + 17 * dim + sum(degree) + 100 * dw)
+    spec = _random_patch(rng, dim, dw, degree)
+    O, kind = oracle_for(spec)
+    Pp = port_for(spec)
+    P = gpu_patch(spec)
+    assert np.array_equal(P.spans(), Pp.spans())
+    assert np.array_equal(P.dofmap()[0], Pp.dofmap()[0])
+    for extra in (0, 1):
+        xi1d = [PD.gaussLegendre01(p + 1 + extra)[0] for p in degree]
+        ref = O.eval_tensor(xi1d, order=2, want=EVAL_FIELDS)
+        assert ref["detJ"].min() > 1e-3
+        for mode in (capi.KERNEL_AUTO, capi.KERNEL_GENERIC):
+            P.setKernel(mode)
+            got = P.evalTensor(xi1d, order=2, want=EVAL_FIELDS)
+            for f in EVAL_FIELDS:
+                assert relerr(got[f], ref[f]) <= TOL, (f, mode, extra, relerr(got[f], ref[f]))
+            got1 = P.evalTensor(xi1d, order=1, want=("N", "dN", "x", "Jt", "detJ", "JinvT"))
+            for f in ("N", "dN", "x", "Jt", "detJ"):
+                assert relerr(got1[f], ref[f]) <= TOL, (f, mode, extra, "order1")
