@@ -425,6 +425,8 @@ igab_status assemble_dd(const PatchDev& P, SfWorkspace& ws, const double* const*
                         cudaStream_t stream) {
   if (!getenv("IGAB_NO_FUSED_ASSEMBLY") && gram_fused_supported(P, kind, nq1))
     return launch_gram_fused(P, ws, xi1d_host, xi, w, kind, fconst, eb, nel, nq1, Ke, fe, stream, D_host);
+  if (!getenv("IGAB_NO_FUSED_ASSEMBLY") && assemble2d_supported(P, kind, nq1))
+    return launch_assemble2d(P, ws, xi1d_host, kind, D_host, fconst, eb, nel, xi, w, Ke, fe, stream);
   long long nq = 1;
   for (int d = 0; d < DIM; ++d) nq *= nq1[d];
   const int nb = P.nb;
@@ -436,7 +438,8 @@ igab_status assemble_dd(const PatchDev& P, SfWorkspace& ws, const double* const*
   // fused Gram path: 3-D Poisson / mass with a local basis of 33..128 functions (p = 3, 4): no B-stack in HBM
   const bool gram = DIM == 3 && DW == 3 && kind != IGAB_ASM_ELASTICITY && nb > 32 && nb <= 128;
   const long long perEl = 8LL * ((gram ? 0LL : 2LL * kdim * n) + nq * (nb + nb * DIM + 1 + DIM * DW));
-  const long long chunk = std::max(1LL, std::min(nel, (4LL << 30) / perEl));
+  // the contraction kernels index elements with gridDim.z (<= 65535)
+  const long long chunk = std::max(1LL, std::min(std::min(nel, (4LL << 30) / perEl), gram ? nel : 65535LL));
   const int q0 = nq1[0], q1 = DIM > 1 ? nq1[1] : 1, q2 = DIM > 2 ? nq1[2] : 1;
   for (long long c0 = 0; c0 < nel; c0 += chunk) {
     const long long m = std::min(chunk, nel - c0);

@@ -1,0 +1,327 @@
+// assemble_2d.cu -- fused element matrices for 2-D patches (plane problems and surfaces in R^3), p = 1, 2, 3 with the
+// (p+1)^2 Gauss rule: evaluation and contraction in one kernel, only K_e / f_e leave the SM.  For these small local bases
+// (n = 4 .. 32) the contraction is FMA work, not tensor-core work (BASELINE north_star: DMMA only for p >= 3 in 3-D);
+// the general B-stack path (assemble.cu) makes an HBM round trip of ~8x the size of K_e, this kernel makes none.
+//
+// Functional spec: localAssembler of dune/python/test/poisson.py:37-81 generalised to B^T D B (same as assemble_fused.cu):
+//   Poisson     K[i][j] = sum_q w detJ grad R_i . grad R_j   (grad = J^T (J J^T)^-1 d/dxi: surfaces in R^3 included)
+//   mass        K[i][j] = sum_q w detJ R_i R_j
+//   elasticity  K[(i,a),(j,b)] = sum_{c,c'} Cf[a][c][b][c'] M^{cc'}[i][j],  M^{cc'} = sum_q w detJ G_c[i] G_c'[j],
+//               Cf = S^T D S for the plane Voigt operator (xx, yy, xy), DOFs i*2 + a
+//   f_e[i] = sum_q w detJ R_i fconst
+//
+// One warp owns EPW = 32 / Q^2 consecutive elements.
+//  (1) lanes <-> (element, quadrature point): univariate rows from the cached K1 tables (eval_tensor_2d.cu), homogeneous
+//      geometry sums, J, detJ = sqrtDetAAT, J^T (J J^T)^-1; the point's physical gradients of all (p+1)^2 functions,
+//      pre-scaled by sqrt(w detJ), go to shared memory  G[element][point][i][c];
+//  (2) lanes <-> upper-triangular entry pairs (i <= j) of the EPW elements: dot products over the points, mirrored into a
+//      shared-memory copy of the EPW element matrices;
+//  (3) the EPW matrices are one contiguous run in global memory: coalesced flush.
+#include <algorithm>
+
+#include "bspline_device.cuh"
+#include "igab_internal.cuh"
+
+namespace igab {
+
+namespace {
+
+struct Elas2Coef {
+  double cf[16];  // [a][c][b][c']
+};
+
+template <int DW, int P, int Q, int KIND>
+struct A2Cfg {
+  static constexpr int NB1 = P + 1, NB = NB1 * NB1, NQ = Q * Q;
+  static constexpr int EPW = 32 / NQ;                          // elements per warp
+  static constexpr int NR = KIND == IGAB_ASM_MASS ? 1 : DW;    // rows of the gradient stack per point
+  static constexpr int NRP = NR == 3 ? 4 : NR;                 // padded (16-byte rows)
+  static constexpr int NCOMP = KIND == IGAB_ASM_ELASTICITY ? 2 : 1;
+  static constexpr int N = NB * NCOMP;
+  static constexpr int NP = NB * (NB + 1) / 2;                 // pairs i <= j
+  static constexpr int PG = NB * NRP + 2;                      // stride of a point's gradient block (even: 16-byte loads;
+                                                               // not a multiple of 16 doubles: the 32 point-lanes spread over banks)
+  static constexpr int PR = NB | 1;                            // stride of a point's row of w detJ R_i (odd)
+  static constexpr int SZ_G = EPW * NQ * PG;
+  static constexpr int SZ_R = EPW * NQ * PR;                   // w detJ R_i (load vector)
+  static constexpr int SZ_K = EPW * N * N;
+  static constexpr int SZ_WARP = (SZ_G + SZ_R + SZ_K + 1) & ~1;
+  static constexpr int WARPS = 4;
+};
+
+__device__ __forceinline__ double2 lds2a(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+template <int DW, int P, int Q, int KIND>
+__global__ void __launch_bounds__(128) assemble2d_kernel(PatchDev Pd, long long elem_begin, long long nelem,
+                                                         const double* __restrict__ tab0, const double* __restrict__ tab1,
+                                                         const double* __restrict__ w0, const double* __restrict__ w1,
+                                                         Elas2Coef coef, double fconst, double* __restrict__ Ke,
+                                                         double* __restrict__ fe) {
+  using C = A2Cfg<DW, P, Q, KIND>;
+  constexpr int NB1 = C::NB1, NB = C::NB, NQ = C::NQ, EPW = C::EPW, NR = C::NR, NRP = C::NRP, N = C::N, NP = C::NP,
+                NCOMP = C::NCOMP, PG = C::PG, PR = C::PR;
+  extern __shared__ __align__(16) double a2smem[];
+  __shared__ unsigned char pairI[NP], pairJ[NP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* const sG = a2smem + (size_t)warp * C::SZ_WARP;
+  double* const sR = sG + C::SZ_G;
+  double* const sK = sR + C::SZ_R;
+  for (int s = threadIdx.x; s < NP; s += blockDim.x) {
+    // s -> (i, j), i <= j, row-major over the upper triangle
+    int i = 0, rem = s;
+    while (rem >= NB - i) { rem -= NB - i; ++i; }
+    pairI[s] = (unsigned char)i;
+    pairJ[s] = (unsigned char)(i + rem);
+  }
+  __syncthreads();
+  const long long ngroups = (nelem + EPW - 1) / EPW;
+  for (long long grp = (long long)blockIdx.x * C::WARPS + warp; grp < ngroups; grp += (long long)gridDim.x * C::WARPS) {
+    const long long el0 = grp * EPW;                         // first element of the group (relative)
+    const int nel = (int)min((long long)EPW, nelem - el0);   // elements in this group
+    // ---- (1) lanes <-> (element, point)
+    {
+      const int es = lane / NQ, q = lane % NQ;
+      const bool valid = es < nel;  // lanes >= EPW*NQ have es >= EPW >= nel
+      if (valid) {
+        const long long e = elem_begin + el0 + es;
+        const int e0 = (int)(e % Pd.nel[0]), e1 = (int)(e / Pd.nel[0]);
+        const int q0 = q % Q, q1 = q / Q;
+        const int s0 = Pd.spanTab[0][e0], s1 = Pd.spanTab[1][e1];
+        // univariate rows (value, d/dxi) of this point from the K1 tables [e_d][q][i][2]
+        double n0[2][NB1], n1[2][NB1];
+        {
+          const double2* t0 = reinterpret_cast<const double2*>(tab0) + ((size_t)e0 * Q + q0) * NB1;
+          const double2* t1 = reinterpret_cast<const double2*>(tab1) + ((size_t)e1 * Q + q1) * NB1;
+#pragma unroll
+          for (int i = 0; i < NB1; ++i) {
+            const double2 a = __ldg(t0 + i), b = __ldg(t1 + i);
+            n0[0][i] = a.x; n0[1][i] = a.y; n1[0][i] = b.x; n1[1][i] = b.y;
+          }
+        }
+        const long long cpBase = (s0 - P) + (long long)Pd.ncp[0] * (s1 - P);
+        const double* __restrict__ cp = Pd.cp;
+        double Wa[3] = {0.0, 0.0, 0.0}, Ca[3][DW], wv[NB];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int c = 0; c < DW; ++c) Ca[a][c] = 0.0;
+#pragma unroll
+        for (int i1 = 0; i1 < NB1; ++i1)
+#pragma unroll
+          for (int i0 = 0; i0 < NB1; ++i0) {
+            const double* pc = cp + (cpBase + i0 + (long long)Pd.ncp[0] * i1) * (DW + 1);
+            double Pc[DW + 1];
+#pragma unroll
+            for (int c = 0; c <= DW; ++c) Pc[c] = __ldg(pc + c);
+            const double w = Pc[DW];
+            wv[i0 + NB1 * i1] = w;
+            const double A[3] = {n0[0][i0] * n1[0][i1] * w, n0[1][i0] * n1[0][i1] * w, n0[0][i0] * n1[1][i1] * w};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+              Wa[a] += A[a];
+#pragma unroll
+              for (int c = 0; c < DW; ++c) Ca[a][c] = fma(A[a], Pc[c], Ca[a][c]);
+            }
+          }
+        const double invW = 1.0 / Wa[0];
+        double J[2][DW];
+#pragma unroll
+        for (int d = 0; d < 2; ++d)
+#pragma unroll
+          for (int c = 0; c < DW; ++c) J[d][c] = (Ca[1 + d][c] - Wa[1 + d] * (Ca[0][c] * invW)) * invW;
+        double g00 = 0.0, g01 = 0.0, g11 = 0.0;
+#pragma unroll
+        for (int c = 0; c < DW; ++c) {
+          g00 += J[0][c] * J[0][c];
+          g01 += J[0][c] * J[1][c];
+          g11 += J[1][c] * J[1][c];
+        }
+        double det;
+        if constexpr (DW == 2)
+          det = fabs(J[0][0] * J[1][1] - J[0][1] * J[1][0]);
+        else
+          det = sqrt(g00 * g11 - g01 * g01);
+        const double wdet = __ldg(w0 + q0) * __ldg(w1 + q1) * det, sq = sqrt(wdet);
+        double* G = sG + (size_t)(es * NQ + q) * PG;
+        if constexpr (KIND == IGAB_ASM_MASS) {
+          const double f = sq * invW;
+#pragma unroll
+          for (int i1 = 0; i1 < NB1; ++i1)
+#pragma unroll
+            for (int i0 = 0; i0 < NB1; ++i0) G[i0 + NB1 * i1] = n0[0][i0] * n1[0][i1] * wv[i0 + NB1 * i1] * f;
+        } else {
+          // G_c[i] = sum_d M[c][d] A_d[i] - v[c] Ahat[i],  M = s/W J^T (J J^T)^-1 [c][d],  v = (1/W) M dW/dxi
+          const double idet = 1.0 / (g00 * g11 - g01 * g01), f = sq * invW * idet;
+          double M[DW][2], v[DW];
+#pragma unroll
+          for (int c = 0; c < DW; ++c) {
+            M[c][0] = (J[0][c] * g11 - J[1][c] * g01) * f;
+            M[c][1] = (J[1][c] * g00 - J[0][c] * g01) * f;
+            v[c] = (M[c][0] * Wa[1] + M[c][1] * Wa[2]) * invW;
+          }
+#pragma unroll
+          for (int i1 = 0; i1 < NB1; ++i1)
+#pragma unroll
+            for (int i0 = 0; i0 < NB1; ++i0) {
+              const int i = i0 + NB1 * i1;
+              const double w = wv[i];
+              const double Ah = n0[0][i0] * n1[0][i1] * w, A0 = n0[1][i0] * n1[0][i1] * w, A1 = n0[0][i0] * n1[1][i1] * w;
+#pragma unroll
+              for (int c = 0; c < DW; ++c) G[i * NRP + c] = M[c][0] * A0 + M[c][1] * A1 - v[c] * Ah;
+              if constexpr (NRP > NR) G[i * NRP + NR] = 0.0;
+            }
+        }
+        if (fe) {
+          const double f = wdet * invW * fconst;
+          double* Rw = sR + (size_t)(es * NQ + q) * PR;
+#pragma unroll
+          for (int i1 = 0; i1 < NB1; ++i1)
+#pragma unroll
+            for (int i0 = 0; i0 < NB1; ++i0) Rw[i0 + NB1 * i1] = n0[0][i0] * n1[0][i1] * wv[i0 + NB1 * i1] * f;
+        }
+      }
+    }
+    __syncwarp();
+    // ---- (2) lanes <-> pairs (i <= j) of the group's elements
+    for (int s = lane; s < nel * NP; s += 32) {
+      const int es = s / NP, pr = s - es * NP;
+      const int i = pairI[pr], j = pairJ[pr];
+      const double* Gi = sG + (size_t)es * NQ * PG + i * NRP;
+      const double* Gj = sG + (size_t)es * NQ * PG + j * NRP;
+      double* K = sK + (size_t)es * N * N;
+      if constexpr (KIND == IGAB_ASM_ELASTICITY) {
+        double m00 = 0.0, m01 = 0.0, m10 = 0.0, m11 = 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const double2 a = lds2a(Gi + q * PG), b = lds2a(Gj + q * PG);
+          m00 = fma(a.x, b.x, m00); m01 = fma(a.x, b.y, m01); m10 = fma(a.y, b.x, m10); m11 = fma(a.y, b.y, m11);
+        }
+        const double m[4] = {m00, m01, m10, m11};  // [c][c']
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            double d = 0.0, t = 0.0;  // direct K[(i,a),(j,b)], mirror K[(j,b),(i,a)] (D need not be symmetric)
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+              for (int cp = 0; cp < 2; ++cp) {
+                d = fma(coef.cf[((a * 2 + c) * 2 + b) * 2 + cp], m[c * 2 + cp], d);
+                t = fma(coef.cf[((b * 2 + cp) * 2 + a) * 2 + c], m[c * 2 + cp], t);
+              }
+            if (i != j) K[(2 * j + b) * N + 2 * i + a] = t;
+            K[(2 * i + a) * N + 2 * j + b] = d;
+          }
+      } else {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          if constexpr (NR == 1) {
+            acc = fma(Gi[q * PG], Gj[q * PG], acc);
+          } else {
+            const double2 a = lds2a(Gi + q * PG), b = lds2a(Gj + q * PG);
+            acc = fma(a.x, b.x, acc);
+            acc = fma(a.y, b.y, acc);
+            if constexpr (NR == 3) acc = fma(Gi[q * PG + 2], Gj[q * PG + 2], acc);
+          }
+        }
+        K[i * N + j] = acc;
+        K[j * N + i] = acc;
+      }
+    }
+    __syncwarp();
+    // ---- (3) coalesced flush of the group's matrices (one contiguous run) and load vectors
+    {
+      double* g = Ke + el0 * (long long)(N * N);
+      const int tot = nel * N * N;
+      for (int k = lane; k < tot; k += 32) g[k] = sK[k];
+      if (fe) {
+        for (int s = lane; s < nel * NB; s += 32) {
+          const int es = s / NB, i = s - es * NB;
+          double acc = 0.0;
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) acc += sR[(size_t)(es * NQ + q) * PR + i];
+#pragma unroll
+          for (int a = 0; a < NCOMP; ++a) fe[(el0 + es) * N + i * NCOMP + a] = acc;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int DW, int P, int Q, int KIND>
+igab_status launch_a2(const PatchDev& Pd, const Elas2Coef& coef, double fconst, long long eb, long long nel,
+                      const double* const* tab, const double* const* w, double* Ke, double* fe, cudaStream_t stream) {
+  using C = A2Cfg<DW, P, Q, KIND>;
+  const size_t smem = (size_t)C::WARPS * C::SZ_WARP * sizeof(double);
+  static bool configured = false;
+  static int sms = 148, bps = 1;
+  if (!configured) {
+    IGAB_CUDA_TRY(cudaFuncSetAttribute(assemble2d_kernel<DW, P, Q, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0;
+    IGAB_CUDA_TRY(cudaGetDevice(&dev));
+    IGAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    IGAB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, assemble2d_kernel<DW, P, Q, KIND>, C::WARPS * 32, smem));
+    if (bps < 1) bps = 1;
+    configured = true;
+  }
+  const long long groups = (nel + C::EPW - 1) / C::EPW;
+  const long long need = (groups + C::WARPS - 1) / C::WARPS;
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(need, (long long)sms * bps * 4));
+  assemble2d_kernel<DW, P, Q, KIND><<<grid, C::WARPS * 32, smem, stream>>>(Pd, eb, nel, tab[0], tab[1], w[0], w[1], coef,
+                                                                           fconst, Ke, fe);
+  count_launch();
+  IGAB_CUDA_TRY(cudaGetLastError());
+  return IGAB_OK;
+}
+
+template <int DW, int KIND>
+igab_status dispatch_a2(int p, const PatchDev& Pd, const Elas2Coef& coef, double fconst, long long eb, long long nel,
+                        const double* const* xi, const double* const* w, double* Ke, double* fe, cudaStream_t stream) {
+  if (p == 1) return launch_a2<DW, 1, 2, KIND>(Pd, coef, fconst, eb, nel, xi, w, Ke, fe, stream);
+  if (p == 2) return launch_a2<DW, 2, 3, KIND>(Pd, coef, fconst, eb, nel, xi, w, Ke, fe, stream);
+  return launch_a2<DW, 3, 4, KIND>(Pd, coef, fconst, eb, nel, xi, w, Ke, fe, stream);
+}
+
+}  // namespace
+
+bool assemble2d_supported(const PatchDev& P, int kind, const int* nq1) {
+  if (P.dim != 2 || (P.dw != 2 && P.dw != 3)) return false;
+  if (P.degree[0] != P.degree[1] || P.degree[0] < 1 || P.degree[0] > 3) return false;
+  if (nq1[0] != P.degree[0] + 1 || nq1[1] != nq1[0]) return false;
+  if (kind == IGAB_ASM_ELASTICITY) return P.dw == 2;
+  return kind == IGAB_ASM_POISSON || kind == IGAB_ASM_MASS;
+}
+
+igab_status launch_assemble2d(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, int kind,
+                              const double* D_host, double fconst, long long eb, long long nel,
+                              const double* const* xi1d_dev_in, const double* const* w1d_dev, double* Ke, double* fe,
+                              cudaStream_t stream) {
+  if (nel == 0) return IGAB_OK;
+  igab_status tst = ensure_tables2d(P, ws, P.degree[0] + 1, 1, xi1d_dev_in, xi1d_host, stream);
+  if (tst) return tst;
+  const double* const xi1d_dev[2] = {ws.tab[0], ws.tab[1]};  // the kernels read the tables, not the abscissae
+  Elas2Coef coef;
+  for (double& v : coef.cf) v = 0.0;
+  const int p = P.degree[0];
+  if (kind == IGAB_ASM_ELASTICITY) {
+    if (!D_host) {
+      set_error("assemble: elasticity needs the 3x3 D matrix");
+      return IGAB_INVALID_ARGUMENT;
+    }
+    // Cf[a][c][b][c'] = sum_{r,t} S[r][a][c] D[r][t] S[t][b][c'], plane Voigt selector (xx, yy, xy; engineering shear)
+    static const int S[4][3] = {{0, 0, 0}, {1, 1, 1}, {2, 0, 1}, {2, 1, 0}};
+    for (auto& s1 : S)
+      for (auto& s2 : S) coef.cf[((s1[1] * 2 + s1[2]) * 2 + s2[1]) * 2 + s2[2]] += D_host[s1[0] * 3 + s2[0]];
+    return dispatch_a2<2, IGAB_ASM_ELASTICITY>(p, P, coef, fconst, eb, nel, xi1d_dev, w1d_dev, Ke, fe, stream);
+  }
+  if (kind == IGAB_ASM_MASS) {
+    if (P.dw == 2) return dispatch_a2<2, IGAB_ASM_MASS>(p, P, coef, fconst, eb, nel, xi1d_dev, w1d_dev, Ke, fe, stream);
+    return dispatch_a2<3, IGAB_ASM_MASS>(p, P, coef, fconst, eb, nel, xi1d_dev, w1d_dev, Ke, fe, stream);
+  }
+  if (P.dw == 2) return dispatch_a2<2, IGAB_ASM_POISSON>(p, P, coef, fconst, eb, nel, xi1d_dev, w1d_dev, Ke, fe, stream);
+  return dispatch_a2<3, IGAB_ASM_POISSON>(p, P, coef, fconst, eb, nel, xi1d_dev, w1d_dev, Ke, fe, stream);
+}
+
+}  // namespace igab

@@ -58,4 +58,69 @@ __device__ inline void ders1d_any(double u, const double* __restrict__ U, int p,
   }
 }
 
+// A2.3 (bsplinealgorithms.hh:148-222) with compile-time degree and order: fully unrolled, everything in registers.
+// out[k][i] = k-th derivative w.r.t. the ELEMENT-LOCAL coordinate (scaled by span length^k).
+template <int P, int K>
+__device__ __forceinline__ void ders1d_reg(double u, const double* __restrict__ U, int sp, double scale,
+                                           double (&out)[K + 1][P + 1]) {
+  double left[P + 1], right[P + 1], ndu[P + 1][P + 1];
+  ndu[0][0] = 1.0;
+#pragma unroll
+  for (int j = 1; j <= P; ++j) {
+    left[j] = u - U[sp + 1 - j];
+    right[j] = U[sp + j] - u;
+    double saved = 0.0;
+#pragma unroll
+    for (int r = 0; r < j; ++r) {
+      ndu[j][r] = right[r + 1] + left[j - r];
+      const double temp = ndu[r][j - 1] / ndu[j][r];
+      ndu[r][j] = saved + right[r + 1] * temp;
+      saved = left[j - r] * temp;
+    }
+    ndu[j][j] = saved;
+  }
+#pragma unroll
+  for (int j = 0; j <= P; ++j) out[0][j] = ndu[j][P];
+  if constexpr (K >= 1) {
+#pragma unroll
+    for (int r = 0; r <= P; ++r) {
+      double a[2][P + 1];
+      a[0][0] = 1.0;
+#pragma unroll
+      for (int k = 1; k <= K; ++k) {
+        const int s1 = (k - 1) & 1, s2 = k & 1;
+        double d = 0.0;
+        const int rk = r - k, pk = P - k;
+        if (k <= P) {
+          if (r >= k) {
+            a[s2][0] = a[s1][0] / ndu[pk + 1][rk];
+            d = a[s2][0] * ndu[rk][pk];
+          }
+          const int j1 = (rk >= -1) ? 1 : -rk;
+          const int j2 = (r - 1 <= pk) ? k - 1 : P - r;
+#pragma unroll
+          for (int j = 1; j <= K; ++j)
+            if (j >= j1 && j <= j2) {
+              a[s2][j] = (a[s1][j] - a[s1][j - 1]) / ndu[pk + 1][rk + j];
+              d += a[s2][j] * ndu[rk + j][pk];
+            }
+          if (r <= pk) {
+            a[s2][k] = -a[s1][k - 1] / ndu[pk + 1][r];
+            d += a[s2][k] * ndu[r][pk];
+          }
+        }
+        out[k][r] = d;
+      }
+    }
+    double fac = P, sc = scale;
+#pragma unroll
+    for (int k = 1; k <= K; ++k) {
+#pragma unroll
+      for (int j = 0; j <= P; ++j) out[k][j] *= fac * sc;
+      fac *= (P - k);
+      sc *= scale;
+    }
+  }
+}
+
 }  // namespace igab

@@ -43,70 +43,41 @@ __global__ void tables2d_kernel(PatchDev P, int d, int nq, int order, const doub
   }
 }
 
-// A2.3 (bsplinealgorithms.hh:148-222) with compile-time degree and order: fully unrolled, everything in registers.
-// out[k][i] = k-th derivative w.r.t. the ELEMENT-LOCAL coordinate (scaled by span length^k).
-template <int P, int K>
-__device__ __forceinline__ void ders1d_reg(double u, const double* __restrict__ U, int sp, double scale,
-                                           double (&out)[K + 1][P + 1]) {
-  double left[P + 1], right[P + 1], ndu[P + 1][P + 1];
-  ndu[0][0] = 1.0;
-#pragma unroll
-  for (int j = 1; j <= P; ++j) {
-    left[j] = u - U[sp + 1 - j];
-    right[j] = U[sp + j] - u;
-    double saved = 0.0;
-#pragma unroll
-    for (int r = 0; r < j; ++r) {
-      ndu[j][r] = right[r + 1] + left[j - r];
-      const double temp = ndu[r][j - 1] / ndu[j][r];
-      ndu[r][j] = saved + right[r + 1] * temp;
-      saved = left[j - r] * temp;
-    }
-    ndu[j][j] = saved;
+}  // namespace
+
+// K1 for 2-D patches: tab[d] = [e_d][q][i][a], a = 0..order, cached per handle (rebuilt when the rule, the derivative
+// order or the stream changes; the order is part of the key through nq1[2], the unused direction).  Shared by the
+// evaluation kernels and the fused 2-D assembly kernel.
+igab_status ensure_tables2d(const PatchDev& Pd, SfWorkspace& ws, int Q, int order, const double* const* xi1d_dev,
+                            const double* const* xi1d_host, cudaStream_t stream) {
+  bool same = ws.valid && ws.stream == stream && ws.nq1[2] == -(order + 1);
+  for (int d = 0; d < 2 && same; ++d) {
+    same = ws.nq1[d] == Q && (int)ws.xi[d].size() == Q;
+    for (int q = 0; q < Q && same; ++q) same = ws.xi[d][q] == xi1d_host[d][q];
   }
-#pragma unroll
-  for (int j = 0; j <= P; ++j) out[0][j] = ndu[j][P];
-  if constexpr (K >= 1) {
-#pragma unroll
-    for (int r = 0; r <= P; ++r) {
-      double a[2][P + 1];
-      a[0][0] = 1.0;
-#pragma unroll
-      for (int k = 1; k <= K; ++k) {
-        const int s1 = (k - 1) & 1, s2 = k & 1;
-        double d = 0.0;
-        const int rk = r - k, pk = P - k;
-        if (k <= P) {
-          if (r >= k) {
-            a[s2][0] = a[s1][0] / ndu[pk + 1][rk];
-            d = a[s2][0] * ndu[rk][pk];
-          }
-          const int j1 = (rk >= -1) ? 1 : -rk;
-          const int j2 = (r - 1 <= pk) ? k - 1 : P - r;
-#pragma unroll
-          for (int j = 1; j <= K; ++j)
-            if (j >= j1 && j <= j2) {
-              a[s2][j] = (a[s1][j] - a[s1][j - 1]) / ndu[pk + 1][rk + j];
-              d += a[s2][j] * ndu[rk + j][pk];
-            }
-          if (r <= pk) {
-            a[s2][k] = -a[s1][k - 1] / ndu[pk + 1][r];
-            d += a[s2][k] * ndu[r][pk];
-          }
-        }
-        out[k][r] = d;
-      }
+  if (same) return IGAB_OK;
+  for (int d = 0; d < 2; ++d) {
+    const size_t n = (size_t)Pd.nel[d] * Q * (Pd.degree[d] + 1) * (order + 1);
+    if (ws.tabCap[d] < n) {
+      if (ws.tab[d]) IGAB_CUDA_TRY(cudaFreeAsync(ws.tab[d], stream));
+      ws.tab[d] = nullptr;
+      ws.tabCap[d] = 0;
+      IGAB_CUDA_TRY(cudaMallocAsync(&ws.tab[d], n * sizeof(double), stream));
+      ws.tabCap[d] = n;
     }
-    double fac = P, sc = scale;
-#pragma unroll
-    for (int k = 1; k <= K; ++k) {
-#pragma unroll
-      for (int j = 0; j <= P; ++j) out[k][j] *= fac * sc;
-      fac *= (P - k);
-      sc *= scale;
-    }
+    const int threads = 128, total = Pd.nel[d] * Q;
+    tables2d_kernel<<<(total + threads - 1) / threads, threads, 0, stream>>>(Pd, d, Q, order, xi1d_dev[d], ws.tab[d]);
+    ws.nq1[d] = Q;
+    ws.xi[d].assign(xi1d_host[d], xi1d_host[d] + Q);
   }
+  count_launch(2);
+  ws.nq1[2] = -(order + 1);
+  ws.valid = true;
+  ws.stream = stream;
+  return IGAB_OK;
 }
+
+namespace {
 
 template <int DW, int P, int Q, int ORDER>
 struct Cfg2 {
@@ -325,32 +296,8 @@ template <int DW, int P, int Q, int ORDER>
 igab_status launch_2d(const PatchDev& Pd, SfWorkspace& ws, const PointSource& src, const double* const* xi1d_host,
                       long long nelem, const EvalOutDev& out, cudaStream_t stream) {
   using C = Cfg2<DW, P, Q, ORDER>;
-  // K1, cached per handle; the cache key includes the derivative order through nq1[2] (unused direction)
-  bool same = ws.valid && ws.stream == stream && ws.nq1[2] == -(ORDER + 1);
-  for (int d = 0; d < 2 && same; ++d) {
-    same = ws.nq1[d] == Q && (int)ws.xi[d].size() == Q;
-    for (int q = 0; q < Q && same; ++q) same = ws.xi[d][q] == xi1d_host[d][q];
-  }
-  if (!same) {
-    for (int d = 0; d < 2; ++d) {
-      const size_t n = (size_t)Pd.nel[d] * C::TAB;
-      if (ws.tabCap[d] < n) {
-        if (ws.tab[d]) IGAB_CUDA_TRY(cudaFreeAsync(ws.tab[d], stream));
-        ws.tab[d] = nullptr;
-        ws.tabCap[d] = 0;
-        IGAB_CUDA_TRY(cudaMallocAsync(&ws.tab[d], n * sizeof(double), stream));
-        ws.tabCap[d] = n;
-      }
-      const int threads = 128, total = Pd.nel[d] * Q;
-      tables2d_kernel<<<(total + threads - 1) / threads, threads, 0, stream>>>(Pd, d, Q, ORDER, src.xi1d[d], ws.tab[d]);
-      ws.nq1[d] = Q;
-      ws.xi[d].assign(xi1d_host[d], xi1d_host[d] + Q);
-    }
-    count_launch(2);
-    ws.nq1[2] = -(ORDER + 1);
-    ws.valid = true;
-    ws.stream = stream;
-  }
+  igab_status tst = ensure_tables2d(Pd, ws, Q, ORDER, src.xi1d, xi1d_host, stream);
+  if (tst) return tst;
   const long long npts = nelem * C::NQ;
   constexpr int WARPS = 4;
   const size_t smem = (size_t)WARPS * C::SLAB * sizeof(double);

@@ -89,6 +89,14 @@ igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* 
                               const double* const* xi1d_dev, const double* const* w1d_dev, int kind, double fconst,
                               long long eb, long long nel, const int* nq1, double* Ke, double* fe, cudaStream_t stream,
                               const double* D_host);
+// fused 2-D element matrices (p = 1..3, (p+1)^2 Gauss): no HBM round trip of the B-stacks
+bool assemble2d_supported(const PatchDev& P, int kind, const int* nq1);
+igab_status launch_assemble2d(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, int kind,
+                              const double* D_host, double fconst, long long eb, long long nel,
+                              const double* const* xi1d_dev, const double* const* w1d_dev, double* Ke, double* fe,
+                              cudaStream_t stream);
+igab_status ensure_tables2d(const PatchDev& Pd, SfWorkspace& ws, int Q, int order, const double* const* xi1d_dev,
+                            const double* const* xi1d_host, cudaStream_t stream);
 bool eval_tensor_sf_supported(const PatchDev& P, const int* nq1, int order, const EvalOutDev& out);
 // 3-D with second derivatives (p = 2, 3)
 bool eval_tensor_sf2_supported(const PatchDev& P, const int* nq1, int order, const EvalOutDev& out);

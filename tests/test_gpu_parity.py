@@ -887,3 +887,36 @@ def test_random_patches_with_repeated_knots(case):
             got1 = P.evalTensor(xi1d, order=1, want=("N", "dN", "x", "Jt", "detJ", "JinvT"))
             for f in ("N", "dN", "x", "Jt", "detJ"):
                 assert relerr(got1[f], ref[f]) <= TOL, (f, mode, extra, "order1")
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+@pytest.mark.parametrize("dw,kind", [(2, capi.ASM_POISSON), (2, capi.ASM_MASS), (2, capi.ASM_ELASTICITY),
+                                     (3, capi.ASM_POISSON), (3, capi.ASM_MASS)])
+def test_fused_2d_element_matrices(p, dw, kind):
+    """assemble2d_kernel (2-D patches, p = 1..3, fused evaluation + contraction) against the oracle and against the
+    general B-stack path, on a random patch with repeated knots; odd element ranges exercise the partial last group of
+    a warp; a non-symmetric D exercises the mirrored coefficients of the elasticity combination."""
+    rng = np.random.default_rng(50 + 7 * p + dw + 3 * kind)
+    spec = _random_patch(rng, 2, dw, (p, p))
+    Pp = port_for(spec)
+    P = gpu_patch(spec)
+    rule = [PD.gaussLegendre01(p + 1)] * 2
+    xi1d, w1d = [r[0] for r in rule], [r[1] for r in rule]
+    D = None
+    if kind == capi.ASM_ELASTICITY:
+        D = np.array([[1.35, 0.58, 0.02], [0.58, 1.35, -0.03], [0.05, 0.01, 0.385]])
+    for eb, ee in ((0, Pp.nelem), (1, Pp.nelem - 1), (2, 3), (3, 3)):
+        Kref, fref = Pp.assemble(kind, xi1d, w1d, D=D, fconst=0.7, elem_begin=eb, elem_end=ee)
+        K, f = P.assemble(kind, xi1d, w1d, D=D, fconst=0.7, elem_begin=eb, elem_end=ee)
+        assert K.shape == Kref.shape
+        if ee > eb:
+            assert relerr(K.reshape(ee - eb, -1), Kref.reshape(ee - eb, -1)) <= TOL
+            assert relerr(f, fref) <= TOL
+    os.environ["IGAB_NO_FUSED_ASSEMBLY"] = "1"
+    try:
+        Kg, fg = P.assemble(kind, xi1d, w1d, D=D, fconst=0.7)
+    finally:
+        del os.environ["IGAB_NO_FUSED_ASSEMBLY"]
+    K, f = P.assemble(kind, xi1d, w1d, D=D, fconst=0.7)
+    assert relerr(K.reshape(len(K), -1), Kg.reshape(len(K), -1)) <= TOL and relerr(f, fg) <= TOL
+    assert capi.launch_count() > 0
