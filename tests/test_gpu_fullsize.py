@@ -140,3 +140,24 @@ def test_c5_trimmed_batches():
     dof, nd = Pt.dofmap()
     dref, nref = Pp.dofmap(flags)
     assert nd == nref and np.array_equal(dof, dref)
+
+
+def test_general_assembly_path_beyond_65535_elements():
+    """Regression: the general B-stack contraction indexes elements with gridDim.z; 2-D patch with 512 x 256 = 131,072
+    elements and a rule that is not (p+1)^2 (so the fused 2-D kernel does not apply).  Properties: rows of the Poisson
+    matrices sum to zero (constants are in the kernel), sum of all mass-matrix entries = area; oracle on sampled elements."""
+    import portbind as PT
+    pd = PD.plateWithHole(8, 8)
+    P = capi.Patch.fromPatchData(pd)
+    nel = P.nelem
+    assert nel > 65535
+    x, w = PD.gaussLegendre01(4)
+    Ke, _ = P.assemble(capi.ASM_POISSON, [x, x], [w, w], want_fe=False)
+    assert Ke.shape == (nel, 9, 9)
+    assert np.abs(Ke.sum(2)).max() <= 1e-11 * np.abs(Ke).max()
+    Me, _ = P.assemble(capi.ASM_MASS, [x, x], [w, w], want_fe=False)
+    assert abs(Me.sum() - P.volume([x, x], [w, w])) <= 1e-11 * Me.sum()
+    Pp = PT.PortPatch(pd.degree, pd.knotSpans, pd.cp, pd.dimworld)
+    for e in (0, 65535, 65536, nel - 1):
+        Kref, _ = Pp.assemble(capi.ASM_POISSON, [x, x], [w, w], elem_begin=e, elem_end=e + 1, want_fe=False)
+        assert np.abs(Ke[e] - Kref[0]).max() <= 1e-12 * np.abs(Kref).max()
