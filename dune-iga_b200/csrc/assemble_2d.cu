@@ -14,8 +14,8 @@
 //  (1) lanes <-> (element, quadrature point): univariate rows from the cached K1 tables (eval_tensor_2d.cu), homogeneous
 //      geometry sums, J, detJ = sqrtDetAAT, J^T (J J^T)^-1; the point's physical gradients of all (p+1)^2 functions,
 //      pre-scaled by sqrt(w detJ), go to shared memory  G[element][point][i][c];
-//  (2) lanes <-> upper-triangular entry pairs (i <= j) of the EPW elements: dot products over the points, mirrored into a
-//      shared-memory copy of the EPW element matrices;
+//  (2) lanes <-> rows (element, i): each lane accumulates one row of K_e over the points in registers; the column
+//      operands are shared-memory broadcasts.  Rows are staged in shared memory;
 //  (3) the EPW matrices are one contiguous run in global memory: coalesced flush.
 #include <algorithm>
 
@@ -38,13 +38,14 @@ struct A2Cfg {
   static constexpr int NRP = NR == 3 ? 4 : NR;                 // padded (16-byte rows)
   static constexpr int NCOMP = KIND == IGAB_ASM_ELASTICITY ? 2 : 1;
   static constexpr int N = NB * NCOMP;
-  static constexpr int NP = NB * (NB + 1) / 2;                 // pairs i <= j
-  static constexpr int PG = NB * NRP + 2;                      // stride of a point's gradient block (even: 16-byte loads;
-                                                               // not a multiple of 16 doubles: the 32 point-lanes spread over banks)
+  // stride of a point's gradient block: odd for scalar rows, an odd number of 16-byte units otherwise, so that the
+  // point-lanes' vector stores of phase (1) spread over all banks
+  static constexpr int PG = NRP == 1 ? (NB | 1) : NB * NRP + (((NB * NRP / 2) % 2 == 0) ? 2 : 0);
   static constexpr int PR = NB | 1;                            // stride of a point's row of w detJ R_i (odd)
+  static constexpr int KS = N | 1;                             // row stride of the staged matrices (odd)
   static constexpr int SZ_G = EPW * NQ * PG;
   static constexpr int SZ_R = EPW * NQ * PR;                   // w detJ R_i (load vector)
-  static constexpr int SZ_K = EPW * N * N;
+  static constexpr int SZ_K = EPW * N * KS;
   static constexpr int SZ_WARP = (SZ_G + SZ_R + SZ_K + 1) & ~1;
   static constexpr int WARPS = 4;
 };
@@ -58,22 +59,13 @@ __global__ void __launch_bounds__(128) assemble2d_kernel(PatchDev Pd, long long 
                                                          Elas2Coef coef, double fconst, double* __restrict__ Ke,
                                                          double* __restrict__ fe) {
   using C = A2Cfg<DW, P, Q, KIND>;
-  constexpr int NB1 = C::NB1, NB = C::NB, NQ = C::NQ, EPW = C::EPW, NR = C::NR, NRP = C::NRP, N = C::N, NP = C::NP,
-                NCOMP = C::NCOMP, PG = C::PG, PR = C::PR;
+  constexpr int NB1 = C::NB1, NB = C::NB, NQ = C::NQ, EPW = C::EPW, NR = C::NR, NRP = C::NRP, N = C::N,
+                NCOMP = C::NCOMP, PG = C::PG, PR = C::PR, KS = C::KS;
   extern __shared__ __align__(16) double a2smem[];
-  __shared__ unsigned char pairI[NP], pairJ[NP];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* const sG = a2smem + (size_t)warp * C::SZ_WARP;
   double* const sR = sG + C::SZ_G;
   double* const sK = sR + C::SZ_R;
-  for (int s = threadIdx.x; s < NP; s += blockDim.x) {
-    // s -> (i, j), i <= j, row-major over the upper triangle
-    int i = 0, rem = s;
-    while (rem >= NB - i) { rem -= NB - i; ++i; }
-    pairI[s] = (unsigned char)i;
-    pairJ[s] = (unsigned char)(i + rem);
-  }
-  __syncthreads();
   const long long ngroups = (nelem + EPW - 1) / EPW;
   for (long long grp = (long long)blockIdx.x * C::WARPS + warp; grp < ngroups; grp += (long long)gridDim.x * C::WARPS) {
     const long long el0 = grp * EPW;                         // first element of the group (relative)
@@ -166,9 +158,11 @@ __global__ void __launch_bounds__(128) assemble2d_kernel(PatchDev Pd, long long 
               const int i = i0 + NB1 * i1;
               const double w = wv[i];
               const double Ah = n0[0][i0] * n1[0][i1] * w, A0 = n0[1][i0] * n1[0][i1] * w, A1 = n0[0][i0] * n1[1][i1] * w;
+              double gc[DW];
 #pragma unroll
-              for (int c = 0; c < DW; ++c) G[i * NRP + c] = M[c][0] * A0 + M[c][1] * A1 - v[c] * Ah;
-              if constexpr (NRP > NR) G[i * NRP + NR] = 0.0;
+              for (int c = 0; c < DW; ++c) gc[c] = M[c][0] * A0 + M[c][1] * A1 - v[c] * Ah;
+              *reinterpret_cast<double2*>(G + i * NRP) = make_double2(gc[0], gc[1]);
+              if constexpr (DW == 3) *reinterpret_cast<double2*>(G + i * NRP + 2) = make_double2(gc[2], 0.0);
             }
         }
         if (fe) {
@@ -182,51 +176,69 @@ __global__ void __launch_bounds__(128) assemble2d_kernel(PatchDev Pd, long long 
       }
     }
     __syncwarp();
-    // ---- (2) lanes <-> pairs (i <= j) of the group's elements
-    for (int s = lane; s < nel * NP; s += 32) {
-      const int es = s / NP, pr = s - es * NP;
-      const int i = pairI[pr], j = pairJ[pr];
-      const double* Gi = sG + (size_t)es * NQ * PG + i * NRP;
-      const double* Gj = sG + (size_t)es * NQ * PG + j * NRP;
-      double* K = sK + (size_t)es * N * N;
+    // ---- (2) lanes <-> rows (element, i): the lane keeps row i of K_e in registers; the columns' gradients G[.][j] are
+    //      the same address for all lanes of an element (shared-memory broadcast), the lane's own G[.][i] is read once
+    //      per point
+    if (lane < nel * NB) {
+      const int es = lane / NB, i = lane - es * NB;
+      const double* Ge = sG + (size_t)es * NQ * PG;
+      double* Krow = sK + (size_t)es * N * KS;
       if constexpr (KIND == IGAB_ASM_ELASTICITY) {
-        double m00 = 0.0, m01 = 0.0, m10 = 0.0, m11 = 0.0;
+        double m[NB][4];  // M^{cc'}[i][j], [c][c']
 #pragma unroll
+        for (int j = 0; j < NB; ++j) m[j][0] = m[j][1] = m[j][2] = m[j][3] = 0.0;
+#pragma unroll 1
         for (int q = 0; q < NQ; ++q) {
-          const double2 a = lds2a(Gi + q * PG), b = lds2a(Gj + q * PG);
-          m00 = fma(a.x, b.x, m00); m01 = fma(a.x, b.y, m01); m10 = fma(a.y, b.x, m10); m11 = fma(a.y, b.y, m11);
-        }
-        const double m[4] = {m00, m01, m10, m11};  // [c][c']
+          const double2 a = lds2a(Ge + q * PG + i * NRP);
 #pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            double d = 0.0, t = 0.0;  // direct K[(i,a),(j,b)], mirror K[(j,b),(i,a)] (D need not be symmetric)
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
-#pragma unroll
-              for (int cp = 0; cp < 2; ++cp) {
-                d = fma(coef.cf[((a * 2 + c) * 2 + b) * 2 + cp], m[c * 2 + cp], d);
-                t = fma(coef.cf[((b * 2 + cp) * 2 + a) * 2 + c], m[c * 2 + cp], t);
-              }
-            if (i != j) K[(2 * j + b) * N + 2 * i + a] = t;
-            K[(2 * i + a) * N + 2 * j + b] = d;
+          for (int j = 0; j < NB; ++j) {
+            const double2 b = lds2a(Ge + q * PG + j * NRP);
+            m[j][0] = fma(a.x, b.x, m[j][0]); m[j][1] = fma(a.x, b.y, m[j][1]);
+            m[j][2] = fma(a.y, b.x, m[j][2]); m[j][3] = fma(a.y, b.y, m[j][3]);
           }
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              double d = 0.0;
+#pragma unroll
+              for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int cp = 0; cp < 2; ++cp) d = fma(coef.cf[((a * 2 + c) * 2 + b) * 2 + cp], m[j][c * 2 + cp], d);
+              Krow[(2 * i + a) * KS + 2 * j + b] = d;
+            }
       } else {
-        double acc = 0.0;
+        double acc[NB];
 #pragma unroll
+        for (int j = 0; j < NB; ++j) acc[j] = 0.0;
+#pragma unroll 1
         for (int q = 0; q < NQ; ++q) {
+          const double* Gq = Ge + q * PG;
           if constexpr (NR == 1) {
-            acc = fma(Gi[q * PG], Gj[q * PG], acc);
+            const double a = Gq[i];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) acc[j] = fma(a, Gq[j], acc[j]);
+          } else if constexpr (NR == 2) {
+            const double2 a = lds2a(Gq + i * NRP);
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+              const double2 b = lds2a(Gq + j * NRP);
+              acc[j] = fma(a.y, b.y, fma(a.x, b.x, acc[j]));
+            }
           } else {
-            const double2 a = lds2a(Gi + q * PG), b = lds2a(Gj + q * PG);
-            acc = fma(a.x, b.x, acc);
-            acc = fma(a.y, b.y, acc);
-            if constexpr (NR == 3) acc = fma(Gi[q * PG + 2], Gj[q * PG + 2], acc);
+            const double2 a = lds2a(Gq + i * NRP), a2 = lds2a(Gq + i * NRP + 2);
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+              const double2 b = lds2a(Gq + j * NRP), b2 = lds2a(Gq + j * NRP + 2);
+              acc[j] = fma(a2.x, b2.x, fma(a.y, b.y, fma(a.x, b.x, acc[j])));
+            }
           }
         }
-        K[i * N + j] = acc;
-        K[j * N + i] = acc;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) Krow[i * KS + j] = acc[j];
       }
     }
     __syncwarp();
@@ -234,7 +246,10 @@ __global__ void __launch_bounds__(128) assemble2d_kernel(PatchDev Pd, long long 
     {
       double* g = Ke + el0 * (long long)(N * N);
       const int tot = nel * N * N;
-      for (int k = lane; k < tot; k += 32) g[k] = sK[k];
+      for (int k = lane; k < tot; k += 32) {
+        const int r = k / N, c = k - r * N;  // r = element-major row index
+        g[k] = sK[r * KS + c];
+      }
       if (fe) {
         for (int s = lane; s < nel * NB; s += 32) {
           const int es = s / NB, i = s - es * NB;
