@@ -920,3 +920,35 @@ def test_fused_2d_element_matrices(p, dw, kind):
     K, f = P.assemble(kind, xi1d, w1d, D=D, fconst=0.7)
     assert relerr(K.reshape(len(K), -1), Kg.reshape(len(K), -1)) <= TOL and relerr(f, fg) <= TOL
     assert capi.launch_count() > 0
+
+
+@pytest.mark.parametrize("kind", [capi.ASM_POISSON, capi.ASM_MASS, capi.ASM_ELASTICITY])
+def test_fused_3d_element_matrices_p2(kind):
+    """The fused tensor-core kernels at p = 2 (27 functions padded to one 32 x 32 block, 3^3 Gauss) against the oracle and
+    the general B-stack path, on a random patch with repeated knots and on the cylinder; non-symmetric D for elasticity."""
+    rng = np.random.default_rng(77 + kind)
+    pdc = PD.thickCylinder(2, (1, 1, 1))
+    specs = [_random_patch(rng, 3, 3, (2, 2, 2)), dict(degree=pdc.degree, knots=pdc.knotSpans, cp=pdc.cp, dimworld=3)]
+    x, w = PD.gaussLegendre01(3)
+    D = None
+    if kind == capi.ASM_ELASTICITY:
+        lam, mu = 0.3 / (1.3 * 0.4), 1 / 2.6
+        D = np.zeros((6, 6))
+        D[:3, :3] = lam
+        D[np.arange(3), np.arange(3)] = lam + 2 * mu
+        D[np.arange(3, 6), np.arange(3, 6)] = mu
+        D = D + 0.05 * rng.normal(size=(6, 6))
+    for spec in specs:
+        Pp = port_for(spec)
+        P = gpu_patch(spec)
+        ne = min(Pp.nelem, 7)
+        Kref, fref = Pp.assemble(kind, [x] * 3, [w] * 3, D=D, fconst=1.3, elem_begin=1, elem_end=ne)
+        K, f = P.assemble(kind, [x] * 3, [w] * 3, D=D, fconst=1.3, elem_begin=1, elem_end=ne)
+        assert relerr(K.reshape(ne - 1, -1), Kref.reshape(ne - 1, -1)) <= TOL, relerr(K.reshape(ne - 1, -1), Kref.reshape(ne - 1, -1))
+        assert relerr(f, fref) <= TOL
+        os.environ["IGAB_NO_FUSED_ASSEMBLY"] = "1"
+        try:
+            Kg, _ = P.assemble(kind, [x] * 3, [w] * 3, D=D, fconst=1.3, elem_begin=1, elem_end=ne)
+        finally:
+            del os.environ["IGAB_NO_FUSED_ASSEMBLY"]
+        assert relerr(K.reshape(ne - 1, -1), Kg.reshape(ne - 1, -1)) <= TOL
