@@ -1,4 +1,4 @@
-// assemble_fused.cu -- fully fused element-matrix kernel for 3-D Poisson / mass at p = 3, 4 (BASELINE config C3):
+// assemble_fused.cu -- fully fused element-matrix kernel for 3-D Poisson / mass at p = 2, 3, 4 (BASELINE config C3: p = 4):
 // evaluation AND contraction in one kernel, nothing but K_e (and f_e) leaves the SM.
 //
 // Functional spec: localAssembler of dune/python/test/poisson.py:37-81 (per point: evaluateJacobian, geometry

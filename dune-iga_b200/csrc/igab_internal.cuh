@@ -83,7 +83,7 @@ igab_status launch_eval_tensor_sf(const PatchDev& P, SfWorkspace& ws, const Poin
 void free_sf_workspace(SfWorkspace& ws);
 igab_status ensure_tables3d(const PatchDev& Pd, SfWorkspace& ws, int Q, const double* const* xi1d_dev,
                             const double* const* xi1d_host, cudaStream_t stream);
-// fully fused element matrices (3-D Poisson / mass, p = 3, 4)
+// fully fused element matrices (3-D Poisson / mass / elasticity, p = 2, 3, 4)
 bool gram_fused_supported(const PatchDev& P, int kind, const int* nq1);
 igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host,
                               const double* const* xi1d_dev, const double* const* w1d_dev, int kind, double fconst,
