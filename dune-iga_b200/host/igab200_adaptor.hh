@@ -11,6 +11,7 @@
 //   NurbsLocalBasis::order / size       dune/iga/nurbsbasis.hh:117-123     LocalBasis::order / size
 //   NurbsLocalFiniteElement::bind       dune/iga/nurbsbasis.hh:355-375     LocalView::bind(elementIndex)
 //   NurbsPreBasis::indices / size       dune/iga/nurbsbasis.hh:590-598,625 LocalView::index(i), PreBasis::size/dimension
+//   NurbsPreBasis::size / dimension / maxNodeSize / sizePerDirection   nurbsbasis.hh:545-633  PreBasis (same names)
 //   NurbsLocalCoefficients::localKey    dune/iga/nurbsbasis.hh:150-290     LocalView::localCoefficients().localKey(i)
 //   NURBSGeometry::global               dune/iga/nurbsgeometry.hh:133-138  Geometry::global
 //   NURBSGeometry::jacobianTransposed   dune/iga/nurbsgeometry.hh:182-196  Geometry::jacobianTransposed
@@ -541,6 +542,27 @@ private:
   LocalBasis<dim, dimworld> lb_;
   int64_t e_ = 0;
   bool bound_ = false;
+};
+
+// ---- NurbsPreBasis (nurbsbasis.hh:503-700): sizes of the global basis and the local view factory --------------------
+template <int dim, int dimworld>
+class PreBasis {
+public:
+  explicit PreBasis(std::shared_ptr<const Patch<dim, dimworld>> p) : p_(std::move(p)) {}
+  // number of basis functions of the (possibly trimmed) patch (nurbsbasis.hh:625-629)
+  std::size_t size() const { return (std::size_t)p_->numDofs(); }
+  std::size_t dimension() const { return size(); }
+  // prod (p_d + 1) (nurbsbasis.hh:545-550)
+  std::size_t maxNodeSize() const { return (std::size_t)p_->localSize(); }
+  // n_d = size(U_d) - p_d - 1 (nurbsbasis.hh:631-633)
+  unsigned int sizePerDirection(int d) const {
+    const auto& pd = p_->patchData();
+    return (unsigned int)(pd.knotSpans[d].size() - pd.degree[d] - 1);
+  }
+  LocalView<dim, dimworld> localView() const { return LocalView<dim, dimworld>(p_); }
+
+private:
+  std::shared_ptr<const Patch<dim, dimworld>> p_;
 };
 
 }  // namespace igab

@@ -159,6 +159,14 @@ int main() {
       }
     }
   CHECK(localView.localBasis().order() == 2 && localView.localBasis().size() == 9, "order/size");
+  {
+    igab::PreBasis<dim, dw> pre(patch);
+    CHECK(pre.size() == (std::size_t)patch->numDofs() && pre.dimension() == pre.size() && pre.maxNodeSize() == 9, "prebasis sizes");
+    CHECK(pre.sizePerDirection(0) * pre.sizePerDirection(1) == pre.size(), "sizePerDirection");
+    auto lv = pre.localView();
+    lv.bind(0);
+    CHECK(lv.size() == 9 && lv.index(3) == patch->dofsOf(0)[3], "localView from prebasis");
+  }
   {  // LocalKeys of the p = (2,2) element (nurbsbasis.hh:182-216): corners codim 2, edge midpoints codim 1, centre codim 0
     const auto& lc = localView.localCoefficients();
     const unsigned sub[9] = {0, 2, 1, 0, 0, 1, 2, 3, 3}, cod[9] = {2, 1, 2, 1, 0, 1, 2, 1, 2};
