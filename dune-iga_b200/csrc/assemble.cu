@@ -460,12 +460,9 @@ igab_status assemble_dd(const PatchDev& P, SfWorkspace& ws, const double* const*
     if (st) return st;
     double* K = Ke + (long long)c0 * n * n;
     if (gram) {
-      static int sms = 0;
-      if (!sms) {
-        int dev = 0;
-        IGAB_CUDA_TRY(cudaGetDevice(&dev));
-        IGAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      }
+      int sms = 148, dev = 0;
+      IGAB_CUDA_TRY(cudaGetDevice(&dev));
+      IGAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
       const bool mass = kind == IGAB_ASM_MASS;
       if (nb > 64) {
         const unsigned grid = (unsigned)std::min<long long>(m, 2LL * sms);

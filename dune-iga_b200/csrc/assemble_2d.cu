@@ -270,17 +270,9 @@ igab_status launch_a2(const PatchDev& Pd, const Elas2Coef& coef, double fconst, 
                       const double* const* tab, const double* const* w, double* Ke, double* fe, cudaStream_t stream) {
   using C = A2Cfg<DW, P, Q, KIND>;
   const size_t smem = (size_t)C::WARPS * C::SZ_WARP * sizeof(double);
-  static bool configured = false;
-  static int sms = 148, bps = 1;
-  if (!configured) {
-    IGAB_CUDA_TRY(cudaFuncSetAttribute(assemble2d_kernel<DW, P, Q, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0;
-    IGAB_CUDA_TRY(cudaGetDevice(&dev));
-    IGAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    IGAB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, assemble2d_kernel<DW, P, Q, KIND>, C::WARPS * 32, smem));
-    if (bps < 1) bps = 1;
-    configured = true;
-  }
+  KernelCfg kc;
+  if (igab_status cst = kernel_config((const void*)assemble2d_kernel<DW, P, Q, KIND>, C::WARPS * 32, smem, &kc)) return cst;
+  const int sms = kc.sms, bps = kc.blocksPerSm;
   const long long groups = (nel + C::EPW - 1) / C::EPW;
   const long long need = (groups + C::WARPS - 1) / C::WARPS;
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(need, (long long)sms * bps * 4));

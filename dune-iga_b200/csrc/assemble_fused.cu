@@ -485,18 +485,11 @@ igab_status launch_elas(const PatchDev& Pd, SfWorkspace& ws, const double* D_hos
         for (int cp = 0; cp < 3; ++cp)
           if (!ortho_pattern(a, c, b, cp) && coef.cf[((a * 3 + c) * 3 + b) * 3 + cp] != 0.0) ortho = false;
   const size_t smem = (size_t)E::SZ_TOTAL * sizeof(double);
-  static bool configured = false;
-  static int sms = 148, bps = 1;
-  if (!configured) {
-    IGAB_CUDA_TRY(cudaFuncSetAttribute(elasticity_fused_kernel<P, Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    IGAB_CUDA_TRY(cudaFuncSetAttribute(elasticity_fused_kernel<P, Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0;
-    IGAB_CUDA_TRY(cudaGetDevice(&dev));
-    IGAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    IGAB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, elasticity_fused_kernel<P, Q, false>, E::NT, smem));
-    if (bps < 1) bps = 1;
-    configured = true;
-  }
+  KernelCfg kc;
+  if (igab_status cst = kernel_config(ortho ? (const void*)elasticity_fused_kernel<P, Q, true>
+                                            : (const void*)elasticity_fused_kernel<P, Q, false>, E::NT, smem, &kc))
+    return cst;
+  const int sms = kc.sms, bps = kc.blocksPerSm;
   const unsigned grid = (unsigned)std::min<long long>(nel, (long long)bps * sms);
   if (ortho)
     elasticity_fused_kernel<P, Q, true><<<grid, E::NT, smem, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],
@@ -514,18 +507,11 @@ igab_status launch_pq(const PatchDev& Pd, SfWorkspace& ws, bool mass, double fco
                       const double* const* w_dev, double* Ke, double* fe, cudaStream_t stream) {
   using C = FCfg<P, Q>;
   const size_t smem = (size_t)C::SZ_TOTAL * sizeof(double);
-  static bool configured = false;
-  static int sms = 148, bps = 2;
-  if (!configured) {
-    IGAB_CUDA_TRY(cudaFuncSetAttribute(gram_fused_kernel<P, Q, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    IGAB_CUDA_TRY(cudaFuncSetAttribute(gram_fused_kernel<P, Q, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0;
-    IGAB_CUDA_TRY(cudaGetDevice(&dev));
-    IGAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    IGAB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, gram_fused_kernel<P, Q, 3>, C::NT, smem));
-    if (bps < 1) bps = 1;
-    configured = true;
-  }
+  KernelCfg kc;
+  if (igab_status cst = kernel_config(mass ? (const void*)gram_fused_kernel<P, Q, 1> : (const void*)gram_fused_kernel<P, Q, 3>,
+                                      C::NT, smem, &kc))
+    return cst;
+  const int sms = kc.sms, bps = kc.blocksPerSm;
   const unsigned grid = (unsigned)std::min<long long>(nel, (long long)bps * sms);  // persistent, grid-stride
   if (mass)
     gram_fused_kernel<P, Q, 1><<<grid, C::NT, smem, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],

@@ -301,11 +301,8 @@ igab_status launch_2d(const PatchDev& Pd, SfWorkspace& ws, const PointSource& sr
   const long long npts = nelem * C::NQ;
   constexpr int WARPS = 4;
   const size_t smem = (size_t)WARPS * C::SLAB * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
-    IGAB_CUDA_TRY(cudaFuncSetAttribute(eval_2d_kernel<DW, P, Q, ORDER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  KernelCfg kc;
+  if (igab_status cst = kernel_config((const void*)eval_2d_kernel<DW, P, Q, ORDER, false>, WARPS * 32, smem, &kc)) return cst;
   const long long blocks = (npts + WARPS * 32 - 1) / (WARPS * 32);
   if (blocks > 0x7fffffffLL) {
     set_error("eval_tensor: too many points for one launch");
@@ -335,11 +332,8 @@ igab_status launch_list(const PatchDev& Pd, const PointSource& src, long long np
   using C = Cfg2<DW, P, 0, ORDER>;
   constexpr int WARPS = 4;
   const size_t smem = (size_t)WARPS * C::SLAB * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
-    IGAB_CUDA_TRY(cudaFuncSetAttribute(eval_2d_kernel<DW, P, 0, ORDER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  KernelCfg kc;
+  if (igab_status cst = kernel_config((const void*)eval_2d_kernel<DW, P, 0, ORDER, true>, WARPS * 32, smem, &kc)) return cst;
   const long long blocks = (npts + WARPS * 32 - 1) / (WARPS * 32);
   if (blocks > 0x7fffffffLL) {
     set_error("eval_points: too many points for one launch");

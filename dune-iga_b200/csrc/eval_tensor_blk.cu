@@ -212,17 +212,9 @@ igab_status launch_blk(const PatchDev& Pd, SfWorkspace& ws, const PointSource& s
   igab_status st = ensure_tables3d(Pd, ws, Q, src.xi1d, xi1d_host, stream);
   if (st) return st;
   const size_t smem = (size_t)C::SZ_TOTAL * sizeof(double);
-  static bool configured = false;
-  static int bps = 1, sms = 148;
-  if (!configured) {
-    IGAB_CUDA_TRY(cudaFuncSetAttribute(eval_sf3d_blk_kernel<P, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0;
-    IGAB_CUDA_TRY(cudaGetDevice(&dev));
-    IGAB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    IGAB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, eval_sf3d_blk_kernel<P, Q>, C::NT, smem));
-    if (bps < 1) bps = 1;
-    configured = true;
-  }
+  KernelCfg kc;
+  if (igab_status cst = kernel_config((const void*)eval_sf3d_blk_kernel<P, Q>, C::NT, smem, &kc)) return cst;
+  const int bps = kc.blocksPerSm, sms = kc.sms;
   const long long blocks = std::min<long long>(nelem, (long long)bps * sms);
   unsigned int* ctr = ws.counter + (ws.counterSlot++ % 64);
   IGAB_CUDA_TRY(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), stream));

@@ -410,17 +410,9 @@ igab_status launch_cfg(const PatchDev& Pd, SfWorkspace& ws, const PointSource& s
   // K2: warps per block chosen so that at least three blocks fit the 227 KB of shared memory of an SM
   constexpr int WARPS = (C::SZ_WARP * 8 * 4 * 3 <= 225 * 1024) ? 4 : ((C::SZ_WARP * 8 * 2 * 3 <= 225 * 1024) ? 2 : 1);
   const size_t smem = (size_t)WARPS * C::SZ_WARP * sizeof(double);
-  static bool configured = false;
-  static int blocksPerSm = 1, numSms = 148;
-  if (!configured) {
-    IGAB_CUDA_TRY(cudaFuncSetAttribute(eval_sf3d_kernel<P, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0;
-    IGAB_CUDA_TRY(cudaGetDevice(&dev));
-    IGAB_CUDA_TRY(cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, dev));
-    IGAB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, eval_sf3d_kernel<P, Q>, WARPS * 32, smem));
-    if (blocksPerSm < 1) blocksPerSm = 1;
-    configured = true;
-  }
+  KernelCfg kc;
+  if (igab_status cst = kernel_config((const void*)eval_sf3d_kernel<P, Q>, WARPS * 32, smem, &kc)) return cst;
+  const int blocksPerSm = kc.blocksPerSm, numSms = kc.sms;
   int bps = blocksPerSm, tune = 0;
   if (const char* e = getenv("IGAB_SF_BLOCKS_PER_SM")) bps = std::max(1, std::min(blocksPerSm, atoi(e)));  // tuning knob
   if (const char* e = getenv("IGAB_SF_TUNE")) tune = atoi(e);

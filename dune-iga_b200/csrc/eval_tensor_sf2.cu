@@ -378,17 +378,9 @@ igab_status launch_o2(const PatchDev& Pd, SfWorkspace& ws, const PointSource& sr
   }
   constexpr int WARPS = (C::SZ_WARP * 8 * 4 * 2 <= 225 * 1024) ? 4 : 2;
   const size_t smem = (size_t)WARPS * C::SZ_WARP * sizeof(double);
-  static bool configured = false;
-  static int blocksPerSm = 1, numSms = 148;
-  if (!configured) {
-    IGAB_CUDA_TRY(cudaFuncSetAttribute(eval_sf3d_o2_kernel<P, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0;
-    IGAB_CUDA_TRY(cudaGetDevice(&dev));
-    IGAB_CUDA_TRY(cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, dev));
-    IGAB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, eval_sf3d_o2_kernel<P, Q>, WARPS * 32, smem));
-    if (blocksPerSm < 1) blocksPerSm = 1;
-    configured = true;
-  }
+  KernelCfg kc;
+  if (igab_status cst = kernel_config((const void*)eval_sf3d_o2_kernel<P, Q>, WARPS * 32, smem, &kc)) return cst;
+  const int blocksPerSm = kc.blocksPerSm, numSms = kc.sms;
   long long blocks = (long long)numSms * blocksPerSm;
   const long long need = (nelem + WARPS - 1) / WARPS;
   if (blocks > need) blocks = need;

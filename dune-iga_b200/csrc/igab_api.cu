@@ -7,6 +7,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 
 #include "igab_internal.cuh"
@@ -14,6 +16,25 @@
 namespace igab {
 
 static thread_local std::string g_last_error;
+
+igab_status kernel_config(const void* func, int threads, size_t smem, KernelCfg* out) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, KernelCfg> cache;
+  int dev = 0;
+  IGAB_CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find({func, dev});
+  if (it == cache.end()) {
+    KernelCfg c;
+    if (smem > 48 * 1024) IGAB_CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IGAB_CUDA_TRY(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
+    IGAB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.blocksPerSm, func, threads, smem));
+    if (c.blocksPerSm < 1) c.blocksPerSm = 1;
+    it = cache.emplace(std::make_pair(func, dev), c).first;
+  }
+  *out = it->second;
+  return IGAB_OK;
+}
 static std::atomic<long long> g_launches{0};
 
 void set_error(const std::string& msg) { g_last_error = msg; }

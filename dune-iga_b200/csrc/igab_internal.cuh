@@ -66,6 +66,14 @@ void set_error(const std::string& msg);
 igab_status cuda_fail(cudaError_t e, const char* what);
 void count_launch(int n = 1);
 
+// Per (kernel, device) launch configuration: raises the dynamic shared-memory limit once and caches the SM count and the
+// resident blocks per SM.  Thread-safe (handles may be driven from different host threads) and correct when a process
+// uses more than one device.
+struct KernelCfg {
+  int sms = 148, blocksPerSm = 1;
+};
+igab_status kernel_config(const void* func, int threads, size_t smem, KernelCfg* out);
+
 #define IGAB_CUDA_TRY(expr)                                           \
   do {                                                                \
     cudaError_t _e = (expr);                                          \
