@@ -1044,16 +1044,14 @@ typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cu
 static nccl_allreduce_fn resolve_nccl_allreduce() {
   // NCCL is resolved at run time from the process (torch ships libnccl.so.2) so that the library has no link-time
   // dependency on it; used only when the caller passes a communicator.
-  static nccl_allreduce_fn fn = nullptr;
-  static bool tried = false;
-  if (tried) return fn;
-  tried = true;
-  void* sym = dlsym(RTLD_DEFAULT, "ncclAllReduce");
-  if (!sym) {
-    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (h) sym = dlsym(h, "ncclAllReduce");
-  }
-  fn = (nccl_allreduce_fn)sym;
+  static const nccl_allreduce_fn fn = [] {  // initialised once, thread-safe (C++11 static)
+    void* sym = dlsym(RTLD_DEFAULT, "ncclAllReduce");
+    if (!sym) {
+      void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (h) sym = dlsym(h, "ncclAllReduce");
+    }
+    return (nccl_allreduce_fn)sym;
+  }();
   return fn;
 }
 
