@@ -232,7 +232,8 @@ bool eval_tensor_blk_supported(const PatchDev& P, const int* nq1, int order, con
   if (P.dim != 3 || P.dw != 3 || out.d2N || out.H) return false;
   if (P.degree[0] != P.degree[1] || P.degree[0] != P.degree[2]) return false;
   if (nq1[0] != nq1[1] || nq1[0] != nq1[2]) return false;
-  return P.degree[0] == 4 && (nq1[0] == 5 || nq1[0] == 6);
+  // 7 points per direction is the reference's default rule for p = 4 (order dim * p = 12, nurbsgridentity.hh:123-124)
+  return P.degree[0] == 4 && (nq1[0] == 5 || nq1[0] == 6 || nq1[0] == 7);
 }
 
 igab_status launch_eval_tensor_blk(const PatchDev& P, SfWorkspace& ws, const PointSource& src,
@@ -245,7 +246,8 @@ igab_status launch_eval_tensor_blk(const PatchDev& P, SfWorkspace& ws, const Poi
   EvalOutDev o = out;
   if (order < 1) o.dN = o.Jt = o.detJ = o.JinvT = nullptr;
   if (src.nq1[0] == 5) return launch_blk<4, 5>(P, ws, src, xi1d_host, nelem, o, stream);
-  return launch_blk<4, 6>(P, ws, src, xi1d_host, nelem, o, stream);
+  if (src.nq1[0] == 6) return launch_blk<4, 6>(P, ws, src, xi1d_host, nelem, o, stream);
+  return launch_blk<4, 7>(P, ws, src, xi1d_host, nelem, o, stream);
 }
 
 }  // namespace igab

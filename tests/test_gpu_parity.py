@@ -952,3 +952,21 @@ def test_fused_3d_element_matrices_p2(kind):
         finally:
             del os.environ["IGAB_NO_FUSED_ASSEMBLY"]
         assert relerr(K.reshape(ne - 1, -1), Kg.reshape(ne - 1, -1)) <= TOL
+
+
+@pytest.mark.parametrize("p,q", [(4, 7), (4, 6), (3, 5), (2, 4)])
+def test_reference_default_rules_in_3d_take_the_tuned_kernels(p, q):
+    """The reference's default rule has order dim * max(p) (nurbsgridentity.hh:123-124): q = floor(3p / 2) + 1 points per
+    direction in 3-D, i.e. 4 / 5 / 7 for p = 2 / 3 / 4.  Those rules must be served by the tuned kernels (KERNEL_TENSOR
+    refuses to fall back) and agree with the oracle."""
+    pd = PD.thickCylinder(p, (1, 1, 1))
+    spec = dict(degree=pd.degree, knots=pd.knotSpans, cp=pd.cp, dimworld=3)
+    Pp = port_for(spec)
+    P = gpu_patch(spec)
+    P.setKernel(capi.KERNEL_TENSOR)
+    xi1d = [PD.gaussLegendre01(q)[0]] * 3
+    want = ("N", "dN", "x", "Jt", "detJ", "JinvT")
+    ref = Pp.eval_tensor(xi1d, order=1, want=want)
+    got = P.evalTensor(xi1d, order=1, want=want)
+    for f in want:
+        assert relerr(got[f], ref[f]) <= TOL, (f, relerr(got[f], ref[f]))
