@@ -426,7 +426,7 @@ igab_status assemble_dd(const PatchDev& P, SfWorkspace& ws, const double* const*
   if (!getenv("IGAB_NO_FUSED_ASSEMBLY") && gram_fused_supported(P, kind, nq1))
     return launch_gram_fused(P, ws, xi1d_host, xi, w, kind, fconst, eb, nel, nq1, Ke, fe, stream, D_host);
   if (!getenv("IGAB_NO_FUSED_ASSEMBLY") && assemble2d_supported(P, kind, nq1))
-    return launch_assemble2d(P, ws, xi1d_host, kind, D_host, fconst, eb, nel, xi, w, Ke, fe, stream);
+    return launch_assemble2d(P, ws, xi1d_host, kind, D_host, fconst, eb, nel, nq1, xi, w, Ke, fe, stream);
   long long nq = 1;
   for (int d = 0; d < DIM; ++d) nq *= nq1[d];
   const int nb = P.nb;

@@ -1,5 +1,5 @@
-// assemble_2d.cu -- fused element matrices for 2-D patches (plane problems and surfaces in R^3), p = 1, 2, 3 with the
-// (p+1)^2 Gauss rule: evaluation and contraction in one kernel, only K_e / f_e leave the SM.  For these small local bases
+// assemble_2d.cu -- fused element matrices for 2-D patches (plane problems and surfaces in R^3), p = 1, 2, 3 with p, p+1
+// or p+2 Gauss points per direction: evaluation and contraction in one kernel, only K_e / f_e leave the SM.  For these small local bases
 // (n = 4 .. 32) the contraction is FMA work, not tensor-core work (BASELINE north_star: DMMA only for p >= 3 in 3-D);
 // the general B-stack path (assemble.cu) makes an HBM round trip of ~8x the size of K_e, this kernel makes none.
 //
@@ -179,8 +179,8 @@ __global__ void __launch_bounds__(128) assemble2d_kernel(PatchDev Pd, long long 
     // ---- (2) lanes <-> rows (element, i): the lane keeps row i of K_e in registers; the columns' gradients G[.][j] are
     //      the same address for all lanes of an element (shared-memory broadcast), the lane's own G[.][i] is read once
     //      per point
-    if (lane < nel * NB) {
-      const int es = lane / NB, i = lane - es * NB;
+    for (int row = lane; row < nel * NB; row += 32) {  // more than 32 rows only for reduced rules (EPW * NB > 32)
+      const int es = row / NB, i = row - es * NB;
       const double* Ge = sG + (size_t)es * NQ * PG;
       double* Krow = sK + (size_t)es * N * KS;
       if constexpr (KIND == IGAB_ASM_ELASTICITY) {
@@ -284,11 +284,16 @@ igab_status launch_a2(const PatchDev& Pd, const Elas2Coef& coef, double fconst, 
 }
 
 template <int DW, int KIND>
-igab_status dispatch_a2(int p, const PatchDev& Pd, const Elas2Coef& coef, double fconst, long long eb, long long nel,
+igab_status dispatch_a2(int p, int q, const PatchDev& Pd, const Elas2Coef& coef, double fconst, long long eb, long long nel,
                         const double* const* xi, const double* const* w, double* Ke, double* fe, cudaStream_t stream) {
-  if (p == 1) return launch_a2<DW, 1, 2, KIND>(Pd, coef, fconst, eb, nel, xi, w, Ke, fe, stream);
-  if (p == 2) return launch_a2<DW, 2, 3, KIND>(Pd, coef, fconst, eb, nel, xi, w, Ke, fe, stream);
-  return launch_a2<DW, 3, 4, KIND>(Pd, coef, fconst, eb, nel, xi, w, Ke, fe, stream);
+#define IGAB_A2_CASE(PP, QQ) \
+  if (p == PP && q == QQ) return launch_a2<DW, PP, QQ, KIND>(Pd, coef, fconst, eb, nel, xi, w, Ke, fe, stream);
+  IGAB_A2_CASE(1, 2) IGAB_A2_CASE(1, 3)
+  IGAB_A2_CASE(2, 2) IGAB_A2_CASE(2, 3) IGAB_A2_CASE(2, 4)
+  IGAB_A2_CASE(3, 3) IGAB_A2_CASE(3, 4) IGAB_A2_CASE(3, 5)
+#undef IGAB_A2_CASE
+  set_error("assemble: no fused 2-D kernel for this (degree, rule)");
+  return IGAB_UNSUPPORTED;
 }
 
 }  // namespace
@@ -296,17 +301,20 @@ igab_status dispatch_a2(int p, const PatchDev& Pd, const Elas2Coef& coef, double
 bool assemble2d_supported(const PatchDev& P, int kind, const int* nq1) {
   if (P.dim != 2 || (P.dw != 2 && P.dw != 3)) return false;
   if (P.degree[0] != P.degree[1] || P.degree[0] < 1 || P.degree[0] > 3) return false;
-  if (nq1[0] != P.degree[0] + 1 || nq1[1] != nq1[0]) return false;
+  // rules with p, p+1 or p+2 points per direction (p+1 = full Gauss; dune/python/test/poisson.py:44 uses order 3 = 2 points)
+  const int p = P.degree[0], q = nq1[0];
+  if (nq1[1] != q || q < p || q > p + 2 || q < 2) return false;
   if (kind == IGAB_ASM_ELASTICITY) return P.dw == 2;
   return kind == IGAB_ASM_POISSON || kind == IGAB_ASM_MASS;
 }
 
 igab_status launch_assemble2d(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, int kind,
                               const double* D_host, double fconst, long long eb, long long nel,
-                              const double* const* xi1d_dev_in, const double* const* w1d_dev, double* Ke, double* fe,
-                              cudaStream_t stream) {
+                              const int* nq1, const double* const* xi1d_dev_in, const double* const* w1d_dev, double* Ke,
+                              double* fe, cudaStream_t stream) {
+  const int nq = nq1[0];
   if (nel == 0) return IGAB_OK;
-  igab_status tst = ensure_tables2d(P, ws, P.degree[0] + 1, 1, xi1d_dev_in, xi1d_host, stream);
+  igab_status tst = ensure_tables2d(P, ws, nq, 1, xi1d_dev_in, xi1d_host, stream);
   if (tst) return tst;
   const double* const xi1d_dev[2] = {ws.tab[0], ws.tab[1]};  // the kernels read the tables, not the abscissae
   Elas2Coef coef;
@@ -321,14 +329,14 @@ igab_status launch_assemble2d(const PatchDev& P, SfWorkspace& ws, const double* 
     static const int S[4][3] = {{0, 0, 0}, {1, 1, 1}, {2, 0, 1}, {2, 1, 0}};
     for (auto& s1 : S)
       for (auto& s2 : S) coef.cf[((s1[1] * 2 + s1[2]) * 2 + s2[1]) * 2 + s2[2]] += D_host[s1[0] * 3 + s2[0]];
-    return dispatch_a2<2, IGAB_ASM_ELASTICITY>(p, P, coef, fconst, eb, nel, xi1d_dev, w1d_dev, Ke, fe, stream);
+    return dispatch_a2<2, IGAB_ASM_ELASTICITY>(p, nq, P, coef, fconst, eb, nel, xi1d_dev, w1d_dev, Ke, fe, stream);
   }
   if (kind == IGAB_ASM_MASS) {
-    if (P.dw == 2) return dispatch_a2<2, IGAB_ASM_MASS>(p, P, coef, fconst, eb, nel, xi1d_dev, w1d_dev, Ke, fe, stream);
-    return dispatch_a2<3, IGAB_ASM_MASS>(p, P, coef, fconst, eb, nel, xi1d_dev, w1d_dev, Ke, fe, stream);
+    if (P.dw == 2) return dispatch_a2<2, IGAB_ASM_MASS>(p, nq, P, coef, fconst, eb, nel, xi1d_dev, w1d_dev, Ke, fe, stream);
+    return dispatch_a2<3, IGAB_ASM_MASS>(p, nq, P, coef, fconst, eb, nel, xi1d_dev, w1d_dev, Ke, fe, stream);
   }
-  if (P.dw == 2) return dispatch_a2<2, IGAB_ASM_POISSON>(p, P, coef, fconst, eb, nel, xi1d_dev, w1d_dev, Ke, fe, stream);
-  return dispatch_a2<3, IGAB_ASM_POISSON>(p, P, coef, fconst, eb, nel, xi1d_dev, w1d_dev, Ke, fe, stream);
+  if (P.dw == 2) return dispatch_a2<2, IGAB_ASM_POISSON>(p, nq, P, coef, fconst, eb, nel, xi1d_dev, w1d_dev, Ke, fe, stream);
+  return dispatch_a2<3, IGAB_ASM_POISSON>(p, nq, P, coef, fconst, eb, nel, xi1d_dev, w1d_dev, Ke, fe, stream);
 }
 
 }  // namespace igab

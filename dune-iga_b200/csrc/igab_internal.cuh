@@ -100,7 +100,7 @@ igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* 
 // fused 2-D element matrices (p = 1..3, (p+1)^2 Gauss): no HBM round trip of the B-stacks
 bool assemble2d_supported(const PatchDev& P, int kind, const int* nq1);
 igab_status launch_assemble2d(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, int kind,
-                              const double* D_host, double fconst, long long eb, long long nel,
+                              const double* D_host, double fconst, long long eb, long long nel, const int* nq1,
                               const double* const* xi1d_dev, const double* const* w1d_dev, double* Ke, double* fe,
                               cudaStream_t stream);
 igab_status ensure_tables2d(const PatchDev& Pd, SfWorkspace& ws, int Q, int order, const double* const* xi1d_dev,

@@ -900,11 +900,18 @@ def test_fused_2d_element_matrices(p, dw, kind):
     spec = _random_patch(rng, 2, dw, (p, p))
     Pp = port_for(spec)
     P = gpu_patch(spec)
-    rule = [PD.gaussLegendre01(p + 1)] * 2
-    xi1d, w1d = [r[0] for r in rule], [r[1] for r in rule]
     D = None
     if kind == capi.ASM_ELASTICITY:
         D = np.array([[1.35, 0.58, 0.02], [0.58, 1.35, -0.03], [0.05, 0.01, 0.385]])
+    # reduced (p points) and over-integrated (p+2) rules are fused as well; poisson.py:44 itself uses 2 points
+    for q in (max(p, 2), p + 2):
+        xq, wq = PD.gaussLegendre01(q)
+        Kref, fref = Pp.assemble(kind, [xq] * 2, [wq] * 2, D=D, fconst=0.7)
+        K, f = P.assemble(kind, [xq] * 2, [wq] * 2, D=D, fconst=0.7)
+        assert relerr(K.reshape(len(K), -1), Kref.reshape(len(K), -1)) <= TOL, (q, relerr(K.reshape(len(K), -1), Kref.reshape(len(K), -1)))
+        assert relerr(f, fref) <= TOL
+    rule = [PD.gaussLegendre01(p + 1)] * 2
+    xi1d, w1d = [r[0] for r in rule], [r[1] for r in rule]
     for eb, ee in ((0, Pp.nelem), (1, Pp.nelem - 1), (2, 3), (3, 3)):
         Kref, fref = Pp.assemble(kind, xi1d, w1d, D=D, fconst=0.7, elem_begin=eb, elem_end=ee)
         K, f = P.assemble(kind, xi1d, w1d, D=D, fconst=0.7, elem_begin=eb, elem_end=ee)
