@@ -530,7 +530,9 @@ bool gram_fused_supported(const PatchDev& P, int kind, const int* nq1) {
   if (P.dim != 3 || P.dw != 3) return false;
   if (P.degree[0] != P.degree[1] || P.degree[0] != P.degree[2]) return false;
   if (nq1[0] != nq1[1] || nq1[0] != nq1[2]) return false;
-  return (P.degree[0] == 2 && nq1[0] == 3) || (P.degree[0] == 3 && nq1[0] == 4) || (P.degree[0] == 4 && nq1[0] == 5);
+  // full Gauss rule (p+1 points per direction) and the over-integrated p+2 rule
+  const int p = P.degree[0], q = nq1[0];
+  return p >= 2 && p <= 4 && (q == p + 1 || q == p + 2);
 }
 
 igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host,
@@ -548,14 +550,20 @@ igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* 
       set_error("assemble: elasticity needs the 6x6 D matrix");
       return IGAB_INVALID_ARGUMENT;
     }
-    if (P.degree[0] == 2) return launch_elas<2, 3>(P, ws, D_host, fconst, eb, nel, w1d_dev, Ke, fe, stream);
-    if (P.degree[0] == 3) return launch_elas<3, 4>(P, ws, D_host, fconst, eb, nel, w1d_dev, Ke, fe, stream);
-    return launch_elas<4, 5>(P, ws, D_host, fconst, eb, nel, w1d_dev, Ke, fe, stream);
+#define IGAB_ELAS_CASE(PP, QQ) \
+  if (P.degree[0] == PP && nq1[0] == QQ) return launch_elas<PP, QQ>(P, ws, D_host, fconst, eb, nel, w1d_dev, Ke, fe, stream);
+    IGAB_ELAS_CASE(2, 3) IGAB_ELAS_CASE(2, 4) IGAB_ELAS_CASE(3, 4) IGAB_ELAS_CASE(3, 5) IGAB_ELAS_CASE(4, 5) IGAB_ELAS_CASE(4, 6)
+#undef IGAB_ELAS_CASE
+    set_error("assemble: no fused kernel for this configuration");
+    return IGAB_UNSUPPORTED;
   }
   const bool mass = kind == IGAB_ASM_MASS;
-  if (P.degree[0] == 2) return launch_pq<2, 3>(P, ws, mass, fconst, eb, nel, w1d_dev, Ke, fe, stream);
-  if (P.degree[0] == 3) return launch_pq<3, 4>(P, ws, mass, fconst, eb, nel, w1d_dev, Ke, fe, stream);
-  return launch_pq<4, 5>(P, ws, mass, fconst, eb, nel, w1d_dev, Ke, fe, stream);
+#define IGAB_PQ_CASE(PP, QQ) \
+  if (P.degree[0] == PP && nq1[0] == QQ) return launch_pq<PP, QQ>(P, ws, mass, fconst, eb, nel, w1d_dev, Ke, fe, stream);
+  IGAB_PQ_CASE(2, 3) IGAB_PQ_CASE(2, 4) IGAB_PQ_CASE(3, 4) IGAB_PQ_CASE(3, 5) IGAB_PQ_CASE(4, 5) IGAB_PQ_CASE(4, 6)
+#undef IGAB_PQ_CASE
+  set_error("assemble: no fused kernel for this configuration");
+  return IGAB_UNSUPPORTED;
 }
 
 }  // namespace igab

@@ -977,3 +977,28 @@ def test_reference_default_rules_in_3d_take_the_tuned_kernels(p, q):
     got = P.evalTensor(xi1d, order=1, want=want)
     for f in want:
         assert relerr(got[f], ref[f]) <= TOL, (f, relerr(got[f], ref[f]))
+
+
+@pytest.mark.parametrize("p", [2, 3, 4])
+@pytest.mark.parametrize("kind", [capi.ASM_POISSON, capi.ASM_MASS, capi.ASM_ELASTICITY])
+def test_fused_3d_element_matrices_over_integrated(p, kind):
+    """Fused 3-D tensor-core assembly with the over-integrated rule (p+2 points per direction) against the oracle."""
+    pd = PD.thickCylinder(p, (1, 1, 0))
+    spec = dict(degree=pd.degree, knots=pd.knotSpans, cp=pd.cp, dimworld=3)
+    Pp = port_for(spec)
+    P = gpu_patch(spec)
+    x, w = PD.gaussLegendre01(p + 2)
+    D = None
+    if kind == capi.ASM_ELASTICITY:
+        lam, mu = 0.3 / (1.3 * 0.4), 1 / 2.6
+        D = np.zeros((6, 6))
+        D[:3, :3] = lam
+        D[np.arange(3), np.arange(3)] = lam + 2 * mu
+        D[np.arange(3, 6), np.arange(3, 6)] = mu
+    ne = min(Pp.nelem, 3)
+    Kref, fref = Pp.assemble(kind, [x] * 3, [w] * 3, D=D, fconst=0.9, elem_end=ne)
+    l0 = capi.launch_count()
+    K, f = P.assemble(kind, [x] * 3, [w] * 3, D=D, fconst=0.9, elem_end=ne)
+    assert capi.launch_count() - l0 <= 4  # tables + one fused kernel, not the evaluate / stack / contract sequence
+    assert relerr(K.reshape(ne, -1), Kref.reshape(ne, -1)) <= TOL, relerr(K.reshape(ne, -1), Kref.reshape(ne, -1))
+    assert relerr(f, fref) <= TOL
