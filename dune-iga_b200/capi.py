@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libigab200.so")
+SO_PATH = os.environ.get("IGAB200_SO") or os.path.join(_HERE, "libigab200.so")  # the override is for instrumented builds
 _lib = None
 
 dp = C.POINTER(C.c_double)

@@ -24,6 +24,22 @@ namespace igab {
 
 namespace {
 
+// Optional phase accounting (tools/phase_timing.py builds a separate library with -DIGAB_PHASE_TIMING): clock64 deltas of
+// lane 0 of every warp, summed per phase.  Compiled out of the product library.
+#ifdef IGAB_PHASE_TIMING
+__device__ unsigned long long g_phase_ticks[8];
+#define IGAB_PT_BEGIN long long pt_last = clock64();
+#define IGAB_PT(k)                                                                                   \
+  {                                                                                                  \
+    const long long pt_now = clock64();                                                              \
+    if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase_ticks[k], (unsigned long long)(pt_now - pt_last)); \
+    pt_last = pt_now;                                                                                \
+  }
+#else
+#define IGAB_PT_BEGIN
+#define IGAB_PT(k)
+#endif
+
 __device__ __forceinline__ void dmma8x8x4_f(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)
@@ -146,7 +162,10 @@ __global__ void __launch_bounds__(FCfg<P, Q>::NT, 2) gram_fused_kernel(
   using C = FCfg<P, Q>;
   constexpr int NB1 = C::NB1, NB = C::NB, NQ = C::NQ, Q2 = C::Q2, NBP = C::NBP, NT = C::NT, KC = C::KC, LD = C::LD;
   constexpr int CS = C::CS;
-  constexpr int pts = KC / NROW, nchunk = (NQ + pts - 1) / pts;
+  // k-rows per chunk and number of chunks: see the build below
+  constexpr int KCX = NROW == 3 ? (3 * Q + 3) / 4 * 4 : KC;
+  constexpr int pts = KC / NROW, nchunk = NROW == 3 ? Q * Q : (NQ + pts - 1) / pts;
+  static_assert(KCX <= KC, "chunk buffer too small");
   extern __shared__ __align__(16) double fsm[];
   double* const sT = fsm;
   double* const sW = sT + C::SZ_T;
@@ -161,42 +180,66 @@ __global__ void __launch_bounds__(FCfg<P, Q>::NT, 2) gram_fused_kernel(
 
   for (long long el = blockIdx.x; el < nelem; el += gridDim.x) {
     const long long e = elem_begin + el;
+    IGAB_PT_BEGIN
     element_prepare<P, Q, NT>(Pd, e, tab0, tab1, tab2, w0, w1, w2, sT, sW, rA, sS2, sC);
+    IGAB_PT(0)
 
     // ---- (3) chunked Gram contraction
+    // Poisson (NROW == 3): a chunk is one line (q1, q2) of the rule, its Q points x 3 gradient components are the k-rows
+    // (padded to a multiple of 4 with rows that stay zero).  Thread <-> (basis function i, half of the line): the
+    // function's indices, weight and direction-0 row live in registers for the whole element, the (q1, q2) factor is
+    // formed once per chunk, so that an item costs 4 multiplications + 12 FMAs and no index arithmetic.
+    // Mass (NROW == 1): 24 points per chunk, generic item mapping.
+    constexpr int QH = (Q + 1) / 2;
+    [[maybe_unused]] const int bi_ = tid % NBP, half_ = tid / NBP;
+    [[maybe_unused]] const bool bvalid = bi_ < NB;
+    [[maybe_unused]] const int bic = bvalid ? bi_ : 0;
+    [[maybe_unused]] const int bi1 = (bic / NB1) % NB1, bi2 = bic / (NB1 * NB1);
+    [[maybe_unused]] double2 areg[QH];
+    [[maybe_unused]] double bw = 0.0;
+    if constexpr (NROW == 3) {
+      bw = sW[bic];
+#pragma unroll
+      for (int u = 0; u < QH; ++u) {
+        const int q0 = min(half_ * QH + u, Q - 1);
+        areg[u] = lds2f(sT + (q0 * NB1 + bic % NB1) * 2);
+      }
+    }
     auto build = [&](int ch) {
       double* A = sA + (ch & 1) * KC * LD;
-#pragma unroll 2
-      for (int item = tid; item < pts * NBP; item += NT) {
-        const int ql = item / NBP, i = item % NBP;
-        const int pt = ch * pts + ql;
-        double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-        if (pt < NQ && i < NB) {
-          const int i0 = i % NB1, i1 = (i / NB1) % NB1, i2 = i / (NB1 * NB1);
-          const int q0 = pt % Q, q1 = (pt / Q) % Q, q2 = pt / Q2;
-          const double2 a = lds2f(sT + (q0 * NB1 + i0) * 2), b = lds2f(sT + C::TAB + (q1 * NB1 + i1) * 2),
-                        c = lds2f(sT + 2 * C::TAB + (q2 * NB1 + i2) * 2);
-          const double* k = sC + CS * pt;
-          const double w = sW[i];
-          const double t00 = a.x * b.x, wn2 = w * c.x;
-          const double Ah = t00 * wn2;
-          if constexpr (NROW == 1) {
-            r0 = Ah * k[15];
-          } else {
+      if constexpr (NROW == 3) {
+        if (!bvalid) return;  // padding columns stay zero
+        const int q1 = ch % Q, q2 = ch / Q;
+        const double2 b = lds2f(sT + C::TAB + (q1 * NB1 + bi1) * 2), c = lds2f(sT + 2 * C::TAB + (q2 * NB1 + bi2) * 2);
+        const double cw = c.x * bw;
+        const double BC0 = b.x * cw, BC1 = b.y * cw, BC2 = b.x * (c.y * bw);
+#pragma unroll
+        for (int u = 0; u < QH; ++u) {
+          const int q0 = half_ * QH + u;
+          if (q0 < Q) {
+            const double* k = sC + CS * (q0 + Q * ch);
             const double2 k01 = lds2f(k), k23 = lds2f(k + 2), k45 = lds2f(k + 4), k67 = lds2f(k + 6),
                           k89 = lds2f(k + 8), kab = lds2f(k + 10), kc = lds2f(k + 12);
-            const double A0 = (a.y * b.x) * wn2, A1 = (a.x * b.y) * wn2, A2 = t00 * (w * c.y);
-            r0 = k45.x * A0 + k45.y * A1 + k67.x * A2 - k01.y * Ah;
-            r1 = k67.y * A0 + k89.x * A1 + k89.y * A2 - k23.x * Ah;
-            r2 = kab.x * A0 + kab.y * A1 + kc.x * A2 - k23.y * Ah;
+            const double Ah = areg[u].x * BC0, A0 = areg[u].y * BC0, A1 = areg[u].x * BC1, A2 = areg[u].x * BC2;
+            A[(3 * q0 + 0) * LD + bi_] = k45.x * A0 + k45.y * A1 + k67.x * A2 - k01.y * Ah;
+            A[(3 * q0 + 1) * LD + bi_] = k67.y * A0 + k89.x * A1 + k89.y * A2 - k23.x * Ah;
+            A[(3 * q0 + 2) * LD + bi_] = kab.x * A0 + kab.y * A1 + kc.x * A2 - k23.y * Ah;
           }
         }
-        if constexpr (NROW == 1) {
+      } else {
+#pragma unroll 2
+        for (int item = tid; item < pts * NBP; item += NT) {
+          const int ql = item / NBP, i = item % NBP;
+          const int pt = ch * pts + ql;
+          double r0 = 0.0;
+          if (pt < NQ && i < NB) {
+            const int i0 = i % NB1, i1 = (i / NB1) % NB1, i2 = i / (NB1 * NB1);
+            const int q0 = pt % Q, q1 = (pt / Q) % Q, q2 = pt / Q2;
+            const double2 a = lds2f(sT + (q0 * NB1 + i0) * 2), b = lds2f(sT + C::TAB + (q1 * NB1 + i1) * 2),
+                          c = lds2f(sT + 2 * C::TAB + (q2 * NB1 + i2) * 2);
+            r0 = (a.x * b.x) * (sW[i] * c.x) * sC[CS * pt + 15];
+          }
           A[ql * LD + i] = r0;
-        } else {
-          A[(3 * ql + 0) * LD + i] = r0;
-          A[(3 * ql + 1) * LD + i] = r1;
-          A[(3 * ql + 2) * LD + i] = r2;
         }
       }
     };
@@ -210,19 +253,24 @@ __global__ void __launch_bounds__(FCfg<P, Q>::NT, 2) gram_fused_kernel(
       colOff[sl] = 8 * slot.col(sl);
     }
     build(0);
+    IGAB_PT(1)
     __syncthreads();
+    IGAB_PT(3)
 #pragma unroll 1
     for (int ch = 0; ch < nchunk; ++ch) {
       const double* A = sA + (ch & 1) * KC * LD;
 #pragma unroll
-      for (int ks = 0; ks < KC; ks += 4) {
+      for (int ks = 0; ks < KCX; ks += 4) {
         const double* Ak = A + (ks + t) * LD + g;  // rows beyond the chunk's points are zero
         const double aA = Ak[8 * slot.ra], aB = Ak[8 * slot.rb];
 #pragma unroll
         for (int sl = 0; sl < NS; ++sl) dmma8x8x4_f(acc[sl][0], acc[sl][1], sl < slot.na ? aA : aB, Ak[colOff[sl]]);
       }
+      IGAB_PT(2)
       if (ch + 1 < nchunk) build(ch + 1);
+      IGAB_PT(1)
       __syncthreads();
+      IGAB_PT(3)
     }
     double* K = Ke + el * (long long)NB * NB;
 #pragma unroll
@@ -253,6 +301,7 @@ __global__ void __launch_bounds__(FCfg<P, Q>::NT, 2) gram_fused_kernel(
         fe[el * NB + i] = s;
       }
     }
+    IGAB_PT(4)
   }
 }
 
@@ -330,7 +379,9 @@ __global__ void __launch_bounds__(ECfg<P, Q>::NT, 2) elasticity_fused_kernel(
 
   for (long long el = blockIdx.x; el < nelem; el += gridDim.x) {
     const long long e = elem_begin + el;
+    IGAB_PT_BEGIN
     element_prepare<P, Q, NT>(Pd, e, tab0, tab1, tab2, w0, w1, w2, sT, sW, rA, sS2, sC);
+    IGAB_PT(0)
     double* K = Ke + el * (long long)N3 * N3;
     for (int bi = 0; bi < NBLK; ++bi)
       for (int bj = bi; bj < NBLK; ++bj) {
@@ -372,7 +423,9 @@ __global__ void __launch_bounds__(ECfg<P, Q>::NT, 2) elasticity_fused_kernel(
 #pragma unroll
           for (int b = 0; b < 3; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
         build(0);
+        IGAB_PT(1)
         __syncthreads();
+        IGAB_PT(3)
 #pragma unroll 1
         for (int ch = 0; ch < nchunk; ++ch) {
           const double* Gk = sGs + (ch & 1) * E::SZ_GS + t * LDC;
@@ -388,8 +441,11 @@ __global__ void __launch_bounds__(ECfg<P, Q>::NT, 2) elasticity_fused_kernel(
 #pragma unroll
               for (int b = 0; b < 3; ++b) dmma8x8x4_f(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
           }
+          IGAB_PT(2)
           if (ch + 1 < nchunk) build(ch + 1);  // into the other buffer, overlapping the other warps' MMAs
+          IGAB_PT(1)
           __syncthreads();
+          IGAB_PT(3)
         }
         // all warps are past the last chunk: the buffers are reused as staging, block (c, c') at sM[(3c + c') * 32 * MS]
 #pragma unroll
@@ -449,6 +505,7 @@ __global__ void __launch_bounds__(ECfg<P, Q>::NT, 2) elasticity_fused_kernel(
           }
         }
         __syncthreads();  // the staging area becomes chunk buffer 0 of the next block pair
+        IGAB_PT(4)
       }
     if (fe) {
       for (int i = tid; i < NB; i += NT) {
@@ -567,3 +624,12 @@ igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* 
 }
 
 }  // namespace igab
+
+#ifdef IGAB_PHASE_TIMING
+extern "C" int igab_debug_phase_ticks(unsigned long long* out, int reset) {
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (out && cudaMemcpyFromSymbol(out, igab::g_phase_ticks, sizeof(z)) != cudaSuccess) return 1;
+  if (reset && cudaMemcpyToSymbol(igab::g_phase_ticks, z, sizeof(z)) != cudaSuccess) return 1;
+  return 0;
+}
+#endif
