@@ -35,6 +35,33 @@ __global__ void dfma_kernel(double* out, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Do DMMA and DFMA share one FP64 datapath?  Even warps run the DMMA loop, odd warps the DFMA loop, in the same block.
+// If the two pipes were independent the flops would add up (~70 TFLOP/s); if they are one datapath the mix stays at ~37.
+__global__ void mixed_kernel(double* out, int iters) {
+  const int warp = threadIdx.x >> 5;
+  double s = 0;
+  if (warp & 1) {
+    double c[8];
+    for (int i = 0; i < 8; ++i) c[i] = i;
+    const double a = 1.0 + threadIdx.x * 1e-9, b = threadIdx.x * 1e-6;
+    for (int it = 0; it < iters * 8; ++it) {  // 8 x 32 FMA per DMMA-equivalent of 256 FMA: same flops per iteration as below
+#pragma unroll
+      for (int i = 0; i < 8; ++i) c[i] = fma(c[i], a, b);
+    }
+    for (int i = 0; i < 8; ++i) s += c[i];
+  } else {
+    double c[8][2];
+    for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+    const double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-4;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dmma(c[i][0], c[i][1], a, b);
+    }
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <class F>
 float run(F f) {
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -64,6 +91,13 @@ int main() {
     float t = run([&] { dfma_kernel<8><<<blocks, threads>>>(out, iters); });
     double flops = (double)blocks * threads * iters * 8 * 2.0;
     printf("DFMA         %2d warps/SM ILP8: %.3f ms  %.2f TFLOP/s\n", warps, t, flops / t / 1e9);
+  }
+  {
+    // 16 warps / SM: 8 DMMA warps + 8 DFMA warps, each issuing iters * 8 * 512 flops
+    const int blocks = 148 * 2, threads = 8 * 32;
+    float t = run([&] { mixed_kernel<<<blocks, threads>>>(out, iters / 4); });
+    double flops = (double)blocks * (threads / 32) * (iters / 4) * 8 * 512.0;
+    printf("MIXED 8 DMMA + 8 DFMA warps/SM: %.3f ms  %.2f TFLOP/s (sum of both halves)\n", t, flops / t / 1e9);
   }
   return 0;
 }
