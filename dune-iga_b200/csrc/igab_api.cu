@@ -187,9 +187,21 @@ static igab_status stage_rule(igab_patch* p, const int* nq1, const double* const
     std::memcpy(host + d * kMaxRule, xi1d[d], sizeof(double) * nq1[d]);
     if (w1d && w1d[d]) std::memcpy(host + (kMaxDim + d) * kMaxRule, w1d[d], sizeof(double) * nq1[d]);
   }
-  // skip the copy when the same rule is already resident (one launch per call on the steady-state path)
-  const size_t nd = sizeof(host) / sizeof(double);
-  if (p->rule_host.size() != nd || p->rule_stream != stream || std::memcmp(p->rule_host.data(), host, sizeof(host)) != 0) {
+  // skip the copy when the same rule is already resident (one launch per call on the steady-state path).  A call without
+  // weights (evaluation) matches a resident rule with the same abscissae whatever weights it carries, so that alternating
+  // evaluation / assembly calls with one rule never restage.
+  const size_t nd = sizeof(host) / sizeof(double), nx = (size_t)kMaxDim * kMaxRule;
+  bool resident = p->rule_host.size() == nd && p->rule_stream == stream &&
+                  std::memcmp(p->rule_host.data(), host, nx * sizeof(double)) == 0;
+  if (resident && w1d) resident = std::memcmp(p->rule_host.data() + nx, host + nx, nx * sizeof(double)) == 0;
+  if (!resident) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (stream) cudaStreamIsCapturing(stream, &cap);
+    if (cap != cudaStreamCaptureStatusNone) {
+      // a copy node would read host memory at replay time: stage the rule once outside the capture instead
+      set_error("quadrature rule is not resident on this stream: call once with this rule before capturing a CUDA graph");
+      return IGAB_INVALID_ARGUMENT;
+    }
     // pageable source: the copy is staged by the runtime before the call returns, so `host` may go out of scope
     IGAB_CUDA_TRY(cudaMemcpyAsync(p->d_rule, host, sizeof(host), cudaMemcpyHostToDevice, stream));
     p->rule_host.assign(host, host + nd);

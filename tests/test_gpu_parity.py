@@ -1002,3 +1002,49 @@ def test_fused_3d_element_matrices_over_integrated(p, kind):
     assert capi.launch_count() - l0 <= 4  # tables + one fused kernel, not the evaluate / stack / contract sequence
     assert relerr(K.reshape(ne, -1), Kref.reshape(ne, -1)) <= TOL, relerr(K.reshape(ne, -1), Kref.reshape(ne, -1))
     assert relerr(f, fref) <= TOL
+
+
+def test_device_path_is_cuda_graph_capturable():
+    """The device-resident entry points enqueue on the caller's stream without host synchronisation (once the rule is
+    staged), so a quadrature loop can be captured in a CUDA graph and replayed -- here: evaluation + fused element
+    matrices of the C1-type patch, replayed after the control net changed."""
+    import torch
+    spec = PFT.small_patch("plate_hole_p2", level=3)
+    P = gpu_patch(spec)
+    x, w = PD.gaussLegendre01(3)
+    fields = ("N", "dN", "x", "Jt", "detJ")
+    sh = P.shapes(P.nelem * 9)
+    out = {f: torch.zeros(sh[f], dtype=torch.float64, device="cuda") for f in fields}
+    Ke = torch.zeros((P.nelem, 9, 9), dtype=torch.float64, device="cuda")
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        s = side.cuda_stream
+        P.assemble(capi.ASM_POISSON, [x, x], [w, w], Ke=Ke, fe=None, stream=s)  # warm-up: stages the rule (with weights) ...
+        P.evalTensor([x, x], order=1, want=fields, out=out, stream=s)           # ... and builds the tables
+    side.synchronize()
+    ref_x, ref_K = out["x"].clone(), Ke.clone()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        s = torch.cuda.current_stream().cuda_stream
+        P.evalTensor([x, x], order=1, want=fields, out=out, stream=s)
+        P.assemble(capi.ASM_POISSON, [x, x], [w, w], Ke=Ke, fe=None, stream=s)
+    out["x"].zero_()
+    Ke.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out["x"], ref_x) and torch.equal(Ke, ref_K)
+    # the graph holds pointers into the handle: new control points, same graph
+    cp2 = np.array(spec["cp"], float).copy()
+    cp2[:, :2] *= 2.0
+    P.updateControlPoints(cp2)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.allclose(out["x"], 2.0 * ref_x, rtol=1e-14, atol=0) and torch.allclose(Ke, ref_K, rtol=1e-12, atol=1e-15)
+    # a rule that is not resident cannot be staged from inside a capture (the copy node would read host memory at replay)
+    x4, w4 = PD.gaussLegendre01(4)
+    g2 = torch.cuda.CUDAGraph()
+    with pytest.raises(capi.IgabError) as ei:
+        with torch.cuda.graph(g2, stream=side):
+            P.evalTensor([x4, x4], order=1, want=fields, out=None if False else {f: torch.zeros(P.shapes(P.nelem * 16)[f], dtype=torch.float64, device="cuda") for f in fields},
+                         stream=torch.cuda.current_stream().cuda_stream)
+    assert ei.value.status == capi.INVALID_ARGUMENT
