@@ -343,7 +343,7 @@ template <int P, int Q, bool ORTHO>
 __global__ void __launch_bounds__(ECfg<P, Q>::NT, 2) elasticity_fused_kernel(
     PatchDev Pd, long long elem_begin, long long nelem, const double* __restrict__ tab0,
     const double* __restrict__ tab1, const double* __restrict__ tab2, const double* __restrict__ w0,
-    const double* __restrict__ w1, const double* __restrict__ w2, ElasCoef coef, double fconst,
+    const double* __restrict__ w1, const double* __restrict__ w2, ElasCoef coef, int symd, double fconst,
     double* __restrict__ Ke, double* __restrict__ fe) {
   using C = FCfg<P, Q>;
   using E = ECfg<P, Q>;
@@ -477,10 +477,25 @@ __global__ void __launch_bounds__(ECfg<P, Q>::NT, 2) elasticity_fused_kernel(
                   for (int cp = 0; cp < 3; ++cp)
                     if (!ORTHO || ortho_pattern(a, c, b, cp)) v = fma(coef.cf[((a * 3 + c) * 3 + b) * 3 + cp], m[c * 3 + cp], v);
                 K[(long long)(3 * i + a) * N3 + 3 * j + b] = v;
+                // symmetric D: the mirror block is the transpose of this one -- keep the value in the slot of M^{ab}
+                if (symd) sM[((a * 3 + b) * 32 + il) * MS + jl] = v;
               }
           }
         }
-        if (bi != bj) {
+        if (bi != bj && symd) {
+          __syncthreads();
+          // mirror block by transposition through shared memory (no arithmetic): lanes over i -> contiguous rows
+          for (int item = tid; item < 32 * 32; item += NT) {
+            const int jl = item / 32, il = item % 32;
+            const int i = bi * 32 + il, j = bj * 32 + jl;
+            if (i < NB && j < NB) {
+#pragma unroll
+              for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int a = 0; a < 3; ++a) K[(long long)(3 * j + b) * N3 + 3 * i + a] = sM[((a * 3 + b) * 32 + il) * MS + jl];
+            }
+          }
+        } else if (bi != bj) {
           // mirror block: K[(j,b),(i,a)] = sum Cf[b][c'][a][c] M^{cc'}[i][j]; lanes over i -> contiguous rows
           for (int item = tid; item < 32 * 32; item += NT) {
             const int jl = item / 32, il = item % 32;
@@ -548,12 +563,19 @@ igab_status launch_elas(const PatchDev& Pd, SfWorkspace& ws, const double* D_hos
     return cst;
   const int sms = kc.sms, bps = kc.blocksPerSm;
   const unsigned grid = (unsigned)std::min<long long>(nel, (long long)bps * sms);
+  // symmetric D (Cf[a][c][b][c'] == Cf[b][c'][a][c]): mirror blocks are written by transposition instead of recomputation
+  int symd = 1;
+  for (int a = 0; a < 3; ++a)
+    for (int c = 0; c < 3; ++c)
+      for (int b = 0; b < 3; ++b)
+        for (int cp = 0; cp < 3; ++cp)
+          if (coef.cf[((a * 3 + c) * 3 + b) * 3 + cp] != coef.cf[((b * 3 + cp) * 3 + a) * 3 + c]) symd = 0;
   if (ortho)
     elasticity_fused_kernel<P, Q, true><<<grid, E::NT, smem, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],
-                                                                       w_dev[1], w_dev[2], coef, fconst, Ke, fe);
+                                                                       w_dev[1], w_dev[2], coef, symd, fconst, Ke, fe);
   else
     elasticity_fused_kernel<P, Q, false><<<grid, E::NT, smem, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],
-                                                                        w_dev[1], w_dev[2], coef, fconst, Ke, fe);
+                                                                        w_dev[1], w_dev[2], coef, symd, fconst, Ke, fe);
   count_launch();
   IGAB_CUDA_TRY(cudaGetLastError());
   return IGAB_OK;
