@@ -25,7 +25,7 @@ EXPORTS = ("igab_last_error_string", "igab_version", "igab_launch_count", "igab_
            "igab_patch_update_control_points", "igab_patch_spans", "igab_patch_dofmap", "igab_eval_tensor",
            "igab_eval_points", "igab_partial", "igab_assemble", "igab_reduce_volume", "igab_csr_pattern",
            "igab_csr_assemble", "igab_eval_faces", "igab_refine_apply", "igab_surface_forms", "igab_geometry_local", "igab_reduce_norms", "igab_local_keys", "igab_rhs_assemble",
-           "igab_csr_dirichlet")
+           "igab_csr_dirichlet", "igab_assemble_points")
 
 
 class EvalOut(C.Structure):
@@ -81,6 +81,8 @@ def lib():
                                         C.c_void_p]
         L.igab_csr_dirichlet.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_void_p]
+        L.igab_assemble_points.argtypes = [C.c_void_p, C.c_int, dp, C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.igab_local_keys.argtypes = [C.c_int, ip, C.c_void_p, C.c_void_p, C.c_void_p]
         L.igab_refine_apply.argtypes = [C.c_int, C.c_int, ip, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, dp, dp,
                                         dp]
@@ -320,6 +322,21 @@ class Patch:
         Dm = _f64(D) if D is not None else None
         _check(lib().igab_assemble(self.h, kind, Dm.ctypes.data_as(dp) if Dm is not None else None, fconst,
                                    elem_begin, elem_end, nq1.ctypes.data_as(ip), xp, wp, ka, fa, ks, stream))
+        return Ke, fe
+
+    def assemblePoints(self, kind, elem, offset, xi, w, D=None, fconst=1.0, want_fe=True, stream=None):
+        """Element matrices of elements with their own quadrature (trimmed elements): list element k is patch element
+        elem[k] with points offset[k]:offset[k+1] of xi [npts][2], w [npts] (quadrature.trimmedBatch produces them)."""
+        elem = _i32(elem)
+        offset = np.ascontiguousarray(offset, dtype=np.int64)
+        xi, w = _f64(xi), _f64(w)
+        n = self.nb * (self.dim if kind == ASM_ELASTICITY else 1)
+        Ke = np.empty((len(elem), n, n))
+        fe = np.empty((len(elem), n)) if want_fe else None
+        Dm = _f64(D) if D is not None else None
+        _check(lib().igab_assemble_points(self.h, kind, Dm.ctypes.data_as(dp) if Dm is not None else None, fconst,
+                                          len(elem), elem.ctypes.data, offset.ctypes.data, xi.ctypes.data, w.ctypes.data,
+                                          Ke.ctypes.data, fe.ctypes.data if fe is not None else None, HOST, stream))
         return Ke, fe
 
     # ---- faces

@@ -983,6 +983,61 @@ igab_status igab_csr_dirichlet(igab_patch* p, int ncomp, const uint8_t* mask, co
   return csr_dirichlet(p, ncomp, mask, g, values, b, space, (cudaStream_t)stream);
 }
 
+igab_status igab_assemble_points(igab_patch* p, int kind, const double* D, double fconst, int64_t nlist,
+                                 const int32_t* elem, const int64_t* offset, const double* xi, const double* w,
+                                 double* Ke, double* fe, igab_memspace space, void* stream_) {
+  if (!p || nlist < 0 || !Ke || (nlist > 0 && (!elem || !offset))) {
+    set_error("assemble_points: null argument");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  if (kind != IGAB_ASM_POISSON && kind != IGAB_ASM_MASS && kind != IGAB_ASM_ELASTICITY) {
+    set_error("assemble_points: unknown kind");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (nlist == 0) return IGAB_OK;
+  static_assert(sizeof(long long) == sizeof(int64_t), "offset type");
+  if (space == IGAB_DEVICE)
+    return launch_assemble2d_points(p->dev, kind, D, fconst, nlist, elem, (const long long*)offset, xi, w, Ke, fe, stream);
+  const long long npts = offset[nlist];
+  for (long long k = 0; k < nlist; ++k)
+    if (elem[k] < 0 || elem[k] >= p->dev.nelem || offset[k + 1] < offset[k] || offset[0] != 0) {
+      set_error("assemble_points: element index out of range or offsets not ascending from 0");
+      return IGAB_INVALID_ARGUMENT;
+    }
+  if (npts > 0 && (!xi || !w)) {
+    set_error("assemble_points: null points / weights");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  const int ncomp = kind == IGAB_ASM_ELASTICITY ? p->dev.dim : 1;
+  const long long n = (long long)p->dev.nb * ncomp;
+  int* d_el = nullptr;
+  long long* d_off = nullptr;
+  double *d_xi = nullptr, *d_w = nullptr, *d_K = nullptr, *d_f = nullptr;
+  cudaError_t e = cudaMalloc(&d_el, sizeof(int) * nlist);
+  if (e == cudaSuccess) e = cudaMalloc(&d_off, sizeof(long long) * (nlist + 1));
+  if (e == cudaSuccess) e = cudaMalloc(&d_xi, sizeof(double) * std::max(1LL, npts * p->dev.dim));
+  if (e == cudaSuccess) e = cudaMalloc(&d_w, sizeof(double) * std::max(1LL, npts));
+  if (e == cudaSuccess) e = cudaMalloc(&d_K, sizeof(double) * nlist * n * n);
+  if (e == cudaSuccess && fe) e = cudaMalloc(&d_f, sizeof(double) * nlist * n);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_el, elem, sizeof(int) * nlist, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, offset, sizeof(long long) * (nlist + 1), cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess && npts) e = cudaMemcpyAsync(d_xi, xi, sizeof(double) * npts * p->dev.dim, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess && npts) e = cudaMemcpyAsync(d_w, w, sizeof(double) * npts, cudaMemcpyHostToDevice, stream);
+  igab_status st = e == cudaSuccess ? IGAB_OK : cuda_fail(e, "assemble_points staging");
+  if (!st) st = launch_assemble2d_points(p->dev, kind, D, fconst, nlist, d_el, d_off, d_xi, d_w, d_K, d_f, stream);
+  if (!st) {
+    e = cudaMemcpyAsync(Ke, d_K, sizeof(double) * nlist * n * n, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && fe) e = cudaMemcpyAsync(fe, d_f, sizeof(double) * nlist * n, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) st = cuda_fail(e, "assemble_points D2H");
+  }
+  cudaStreamSynchronize(stream);
+  cudaFree(d_el); cudaFree(d_off); cudaFree(d_xi); cudaFree(d_w); cudaFree(d_K);
+  if (d_f) cudaFree(d_f);
+  return st;
+}
+
 // ---- local keys (host integers) ------------------------------------------------------------------------------------------
 igab_status igab_local_keys(int dim, const int* degree, uint32_t* sub_entity, uint32_t* codim, uint32_t* index) {
   if (dim < 1 || dim > kMaxDim || !degree || !sub_entity || !codim || !index) {

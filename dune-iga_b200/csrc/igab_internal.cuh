@@ -103,6 +103,10 @@ igab_status launch_assemble2d(const PatchDev& P, SfWorkspace& ws, const double* 
                               const double* D_host, double fconst, long long eb, long long nel, const int* nq1,
                               const double* const* xi1d_dev, const double* const* w1d_dev, double* Ke, double* fe,
                               cudaStream_t stream);
+bool assemble2d_points_supported(const PatchDev& P, int kind);
+igab_status launch_assemble2d_points(const PatchDev& P, int kind, const double* D_host, double fconst, long long nlist,
+                                     const int* elem, const long long* offset, const double* xi, const double* w,
+                                     double* Ke, double* fe, cudaStream_t stream);
 igab_status ensure_tables2d(const PatchDev& Pd, SfWorkspace& ws, int Q, int order, const double* const* xi1d_dev,
                             const double* const* xi1d_host, cudaStream_t stream);
 bool eval_tensor_sf_supported(const PatchDev& P, const int* nq1, int order, const EvalOutDev& out);

@@ -152,6 +152,16 @@ igab_status igab_assemble(igab_patch* p, int kind, const double* D, double fcons
                           int64_t elem_end, const int* nq1, const double* const* xi1d, const double* const* w1d,
                           double* Ke, double* fe, igab_memspace out_space, void* stream);
 
+/* Element matrices of elements that carry their OWN quadrature: trimmed elements, whose rule is assembled from the
+ * sub-triangles of the trimmed domain (utils/fillquadraturerule.hh:8-19, NURBSGridEntity::getQuadratureRule
+ * nurbsgridentity.hh:120-141).  List element k is patch element elem[k] with the points offset[k] .. offset[k+1] of
+ * xi [npts][2] (element-local) and w [npts]; same integrands and layouts as igab_assemble; Ke [nlist][n][n],
+ * fe [nlist][n] or NULL.  2-D patches (trimming is 2-D in the reference) with equal degrees 1..3.  elem (int32),
+ * offset (int64, nlist + 1 entries), xi, w, Ke, fe live in `space`; D is HOST.                                     */
+igab_status igab_assemble_points(igab_patch* p, int kind, const double* D, double fconst, int64_t nlist,
+                                 const int32_t* elem, const int64_t* offset, const double* xi, const double* w,
+                                 double* Ke, double* fe, igab_memspace space, void* stream);
+
 /* ---- refinement of the control net -----------------------------------------------------------------------------------
  * Replaces the control-net part of knotRefinement / degreeElevate (dune/iga/nurbsalgorithms.hh:264-528) for one
  * direction: new net = T applied along `direction` in homogeneous coordinates.  T (n_new x ncp_old[direction]) is given

@@ -603,6 +603,55 @@ double igo_volume(const igo_patch* P, const int* nq1, const double* xi1d, const 
  *         PowerPreBasis<FlatInterleaved> (python/dune/iga/basis/__init__.py:53-67); strain Voigt order
  *         2-D (xx,yy,xy), 3-D (xx,yy,zz,yz,xz,xy) with engineering shear; D row-major ns x ns.
  * Ke[e][n][n] row-major, n = nb (kind 0,1) or nb*dim (kind 2); fe[e][n] (nullable).                              */
+/* one quadrature point's contribution to K_e / f_e (poisson.py:52-79 generalised to B^T D B); wd_ = w detJ */
+static void accum_point(int dim, int dw, int nb, int kind, const double* D, double fconst, double wd_, const double* Npt,
+                        const double* dNpt, const double* JinvTpt, double* grad, double* B, double* DB, double* K,
+                        double* fe_e) {
+  const int ncomp = (kind == 2) ? dim : 1, n = nb * ncomp;
+  const int ns = (dim == 2) ? 3 : (dim == 3 ? 6 : 1);
+  /* grad_i[c] = sum_d JinvT[c][d] dN_i[d]   (JinvT is dw x dim) */
+  for (int i = 0; i < nb; ++i)
+    for (int c = 0; c < dw; ++c) {
+      double s = 0;
+      for (int d = 0; d < dim; ++d) s += JinvTpt[c * dim + d] * dNpt[i * dim + d];
+      grad[i * dw + c] = s;
+    }
+  if (kind == 0) {
+    for (int i = 0; i < nb; ++i) {
+      for (int j = 0; j < nb; ++j) {
+        double s = 0;
+        for (int c = 0; c < dw; ++c) s += grad[i * dw + c] * grad[j * dw + c];
+        K[i * n + j] += wd_ * s;
+      }
+      if (fe_e) fe_e[i] += wd_ * Npt[i] * fconst;
+    }
+  } else if (kind == 1) {
+    for (int i = 0; i < nb; ++i) {
+      for (int j = 0; j < nb; ++j) K[i * n + j] += wd_ * Npt[i] * Npt[j];
+      if (fe_e) fe_e[i] += wd_ * Npt[i] * fconst;
+    }
+  } else {
+    for (int q2 = 0; q2 < ns * n; ++q2) B[q2] = 0;
+    for (int i = 0; i < nb; ++i) {
+      const double gx = grad[i * dw + 0], gy = grad[i * dw + 1], gz = dim == 3 ? grad[i * dw + 2] : 0;
+      if (dim == 2) {
+        B[0 * n + i * 2 + 0] = gx; B[1 * n + i * 2 + 1] = gy;
+        B[2 * n + i * 2 + 0] = gy; B[2 * n + i * 2 + 1] = gx;
+      } else {
+        B[0 * n + i * 3 + 0] = gx; B[1 * n + i * 3 + 1] = gy; B[2 * n + i * 3 + 2] = gz;
+        B[3 * n + i * 3 + 1] = gz; B[3 * n + i * 3 + 2] = gy;
+        B[4 * n + i * 3 + 0] = gz; B[4 * n + i * 3 + 2] = gx;
+        B[5 * n + i * 3 + 0] = gy; B[5 * n + i * 3 + 1] = gx;
+      }
+    }
+    for (int r = 0; r < ns; ++r)
+      for (int j = 0; j < n; ++j) { double s = 0; for (int t = 0; t < ns; ++t) s += D[r * ns + t] * B[t * n + j]; DB[r * n + j] = s; }
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) { double s = 0; for (int r = 0; r < ns; ++r) s += B[r * n + i] * DB[r * n + j]; K[i * n + j] += wd_ * s; }
+    if (fe_e) for (int i = 0; i < nb; ++i) for (int c = 0; c < ncomp; ++c) fe_e[i * ncomp + c] += wd_ * Npt[i] * fconst;
+  }
+}
+
 int igo_assemble(const igo_patch* P, int kind, const double* D, double fconst, long elem_begin, long elem_end,
                  const int* nq1, const double* xi1d, const double* w1d, double* Ke, double* fe, int nthreads) {
   const int dim = P->dim, dw = P->dimworld, nb = nb_of(P);
@@ -632,54 +681,45 @@ int igo_assemble(const igo_patch* P, int kind, const double* D, double fconst, l
         const long pt = e * nq + q;
         double w = 1; long hq = q;
         for (int d = 0; d < dim; ++d) { w *= wd[d][hq % nq1[d]]; hq /= nq1[d]; }
-        const double wd_ = w * detJ[pt];
-        /* grad_i[c] = sum_d JinvT[c][d] dN_i[d]   (JinvT is dw x dim) */
-        for (int i = 0; i < nb; ++i)
-          for (int c = 0; c < dw; ++c) {
-            double s = 0;
-            for (int d = 0; d < dim; ++d) s += JinvT[pt * dim * dw + c * dim + d] * dN[(pt * nb + i) * dim + d];
-            grad[i * dw + c] = s;
-          }
-        if (kind == 0) {
-          for (int i = 0; i < nb; ++i) {
-            for (int j = 0; j < nb; ++j) {
-              double s = 0;
-              for (int c = 0; c < dw; ++c) s += grad[i * dw + c] * grad[j * dw + c];
-              K[i * n + j] += wd_ * s;
-            }
-            if (fe) fe[e * n + i] += wd_ * N[pt * nb + i] * fconst;
-          }
-        } else if (kind == 1) {
-          for (int i = 0; i < nb; ++i) {
-            for (int j = 0; j < nb; ++j) K[i * n + j] += wd_ * N[pt * nb + i] * N[pt * nb + j];
-            if (fe) fe[e * n + i] += wd_ * N[pt * nb + i] * fconst;
-          }
-        } else {
-          for (int q2 = 0; q2 < ns * n; ++q2) B[q2] = 0;
-          for (int i = 0; i < nb; ++i) {
-            const double gx = grad[i * dw + 0], gy = grad[i * dw + 1], gz = dim == 3 ? grad[i * dw + 2] : 0;
-            if (dim == 2) {
-              B[0 * n + i * 2 + 0] = gx; B[1 * n + i * 2 + 1] = gy;
-              B[2 * n + i * 2 + 0] = gy; B[2 * n + i * 2 + 1] = gx;
-            } else {
-              B[0 * n + i * 3 + 0] = gx; B[1 * n + i * 3 + 1] = gy; B[2 * n + i * 3 + 2] = gz;
-              B[3 * n + i * 3 + 1] = gz; B[3 * n + i * 3 + 2] = gy;
-              B[4 * n + i * 3 + 0] = gz; B[4 * n + i * 3 + 2] = gx;
-              B[5 * n + i * 3 + 0] = gy; B[5 * n + i * 3 + 1] = gx;
-            }
-          }
-          for (int r = 0; r < ns; ++r)
-            for (int j = 0; j < n; ++j) { double s = 0; for (int t = 0; t < ns; ++t) s += D[r * ns + t] * B[t * n + j]; DB[r * n + j] = s; }
-          for (int i = 0; i < n; ++i)
-            for (int j = 0; j < n; ++j) { double s = 0; for (int r = 0; r < ns; ++r) s += B[r * n + i] * DB[r * n + j]; K[i * n + j] += wd_ * s; }
-          if (fe) for (int i = 0; i < nb; ++i) for (int c = 0; c < ncomp; ++c) fe[e * n + i * ncomp + c] += wd_ * N[pt * nb + i] * fconst;
-        }
+        accum_point(dim, dw, nb, kind, D, fconst, w * detJ[pt], N + pt * nb, dN + pt * nb * dim, JinvT + pt * dim * dw, grad, B, DB,
+                    K, fe ? fe + e * n : 0);
       }
     }
     free(grad); free(B); free(DB);
   }
   free(N); free(dN); free(detJ); free(JinvT);
   return used;
+}
+
+/* Element matrices of elements that carry their own quadrature (trimmed elements: the rule of
+ * utils/fillquadraturerule.hh:8-19): list element k is patch element elem[k] with the points offset[k] .. offset[k+1]
+ * of xi[npts][dim] (element-local) and w[npts].  Same per-point contribution as igo_assemble.                      */
+int igo_assemble_points(const igo_patch* P, int kind, const double* D, double fconst, long nlist, const int* elem,
+                        const long* offset, const double* xi, const double* w, double* Ke, double* fe) {
+  const int dim = P->dim, dw = P->dimworld, nb = nb_of(P);
+  const int ncomp = (kind == 2) ? dim : 1, n = nb * ncomp;
+  const int ns = (dim == 2) ? 3 : (dim == 3 ? 6 : 1);
+  const long npts = offset[nlist];
+  int* pe = (int*)malloc(sizeof(int) * (npts > 0 ? npts : 1));
+  for (long k = 0; k < nlist; ++k) for (long q = offset[k]; q < offset[k + 1]; ++q) pe[q] = elem[k];
+  double* N = (double*)malloc(sizeof(double) * (npts + 1) * nb);
+  double* dN = (double*)malloc(sizeof(double) * (npts + 1) * nb * dim);
+  double* detJ = (double*)malloc(sizeof(double) * (npts + 1));
+  double* JinvT = (double*)malloc(sizeof(double) * (npts + 1) * dim * dw);
+  igo_eval_points(P, npts, pe, xi, 1, N, dN, 0, 0, 0, 0, detJ, JinvT, 0);
+  double* grad = (double*)malloc(sizeof(double) * nb * dw);
+  double* B = (double*)malloc(sizeof(double) * ns * n);
+  double* DB = (double*)malloc(sizeof(double) * ns * n);
+  for (long k = 0; k < nlist; ++k) {
+    double* K = Ke + k * (long)n * n;
+    for (long q = 0; q < (long)n * n; ++q) K[q] = 0;
+    if (fe) for (int i = 0; i < n; ++i) fe[k * n + i] = 0;
+    for (long pt = offset[k]; pt < offset[k + 1]; ++pt)
+      accum_point(dim, dw, nb, kind, D, fconst, w[pt] * detJ[pt], N + pt * nb, dN + pt * nb * dim, JinvT + pt * dim * dw, grad, B,
+                  DB, K, fe ? fe + k * n : 0);
+  }
+  free(pe); free(N); free(dN); free(detJ); free(JinvT); free(grad); free(B); free(DB);
+  return 0;
 }
 
 /* ---- a19 (trimmed): utils/fillquadraturerule.hh:8-19 -- rule of a trimmed element from its sub-triangles -------

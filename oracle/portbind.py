@@ -60,6 +60,8 @@ def lib():
         L.igo_geometry_local.argtypes = [PP, C.c_long, ip, dp, dp, ip]
         L.igo_norms.restype = C.c_int
         L.igo_norms.argtypes = [PP, C.c_long, C.c_long, ip, dp, dp, dp, C.c_int, dp]
+        L.igo_assemble_points.restype = C.c_int
+        L.igo_assemble_points.argtypes = [PP, C.c_int, dp, C.c_double, C.c_long, ip, C.POINTER(C.c_long), dp, dp, dp, dp]
         L.igo_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -198,6 +200,17 @@ class PortPatch:
         lib().igo_norms(C.byref(self.c), elem_begin, elem_end, _i(nq1), _d(_f64(np.concatenate(xi1d))),
                         _d(_f64(np.concatenate(w1d))), _d(_f64(u)), ncomp, _d(out))
         return out
+
+    def assemble_points(self, kind, elem, offset, xi, w, D=None, fconst=1.0, want_fe=True):
+        elem = _i32(elem)
+        offset = np.ascontiguousarray(offset, dtype=np.int64)
+        n = self.nb * (self.dim if kind == 2 else 1)
+        Ke = np.empty((len(elem), n, n))
+        fe = np.empty((len(elem), n)) if want_fe else None
+        Dm = _f64(D) if D is not None else None
+        lib().igo_assemble_points(C.byref(self.c), kind, _d(Dm), fconst, len(elem), _i(elem),
+                                  offset.ctypes.data_as(C.POINTER(C.c_long)), _d(_f64(xi)), _d(_f64(w)), _d(Ke), _d(fe))
+        return Ke, fe
 
     def local(self, elem, xglobal):
         """NURBSGeometry::local per point (nurbsgeometry.hh:145-176): element-local xi and a flag per point."""

@@ -1048,3 +1048,43 @@ def test_device_path_is_cuda_graph_capturable():
             P.evalTensor([x4, x4], order=1, want=fields, out=None if False else {f: torch.zeros(P.shapes(P.nelem * 16)[f], dtype=torch.float64, device="cuda") for f in fields},
                          stream=torch.cuda.current_stream().cuda_stream)
     assert ei.value.status == capi.INVALID_ARGUMENT
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+@pytest.mark.parametrize("dw,kind", [(2, capi.ASM_POISSON), (2, capi.ASM_MASS), (2, capi.ASM_ELASTICITY),
+                                     (3, capi.ASM_POISSON), (3, capi.ASM_MASS)])
+def test_element_matrices_from_point_lists(p, dw, kind):
+    """igab_assemble_points: element matrices of elements with their own quadrature (trimmed-element batches: ragged
+    point counts per element from sub-triangle rules, an element without points, more than 32 points) against the
+    oracle; and the tensor rule written as a point list reproduces igab_assemble."""
+    from dune_iga_b200 import quadrature as QD
+    rng = np.random.default_rng(90 + 5 * p + dw + 2 * kind)
+    spec = _random_patch(rng, 2, dw, (p, p))
+    Pp = port_for(spec)
+    P = gpu_patch(spec)
+    D = np.array([[1.35, 0.58, 0.02], [0.58, 1.35, -0.03], [0.05, 0.01, 0.385]]) if kind == capi.ASM_ELASTICITY else None
+    # ragged batch: element -> 1..8 sub-triangles inside [0,1]^2, 6-point rule on each (6 .. 48 points per element)
+    chosen = sorted(rng.choice(Pp.nelem, size=min(5, Pp.nelem), replace=False).tolist())
+    batch = {e: np.stack([np.array([[0, 0], [1, 0], [0, 1.0]]) * rng.uniform(0.3, 1.0) for _ in range(int(rng.integers(1, 9)))])
+             for e in chosen}
+    batch[chosen[0]] = np.stack([np.array([[0, 0], [1, 0], [0, 1.0]]) * s for s in np.linspace(0.3, 1.0, 8)])  # > 32 points
+    elem_pt, xi, w, off = QD.trimmedBatch(batch, order=4)
+    elems = np.array(chosen, np.int32)
+    # add an element without points and one with the plain tensor rule
+    x1, w1 = PD.gaussLegendre01(p + 1)
+    Xt = np.array([[x1[q % (p + 1)], x1[q // (p + 1)]] for q in range((p + 1) ** 2)])
+    Wt = np.array([w1[q % (p + 1)] * w1[q // (p + 1)] for q in range((p + 1) ** 2)])
+    elems = np.concatenate([elems, [0, 1]]).astype(np.int32)
+    off = np.concatenate([off, [off[-1], off[-1] + len(Wt)]]).astype(np.int64)
+    xi = np.concatenate([xi, Xt])
+    w = np.concatenate([w, Wt])
+    assert np.diff(off).max() > 32 and np.diff(off).min() == 0
+    Kref, fref = Pp.assemble_points(kind, elems, off, xi, w, D=D, fconst=0.8)
+    K, f = P.assemblePoints(kind, elems, off, xi, w, D=D, fconst=0.8)
+    assert relerr(K.reshape(len(K), -1), Kref.reshape(len(K), -1)) <= TOL, relerr(K.reshape(len(K), -1), Kref.reshape(len(K), -1))
+    assert relerr(f, fref) <= TOL
+    assert np.abs(K[-2]).max() == 0.0 and np.abs(f[-2]).max() == 0.0          # the element without points
+    Kt, ft = P.assemble(kind, [x1, x1], [w1, w1], D=D, fconst=0.8, elem_begin=1, elem_end=2)
+    assert relerr(K[-1], Kt[0]) <= TOL and relerr(f[-1], ft[0]) <= TOL           # tensor rule as a list
+    with pytest.raises(capi.IgabError):
+        P.assemblePoints(kind, np.array([Pp.nelem], np.int32), np.array([0, 1], np.int64), xi[:1], w[:1], D=D)

@@ -345,3 +345,22 @@ def test_element_centres_after_refinement(impl):
     for e, centre in enumerate(c["centres"]):
         u = [0.5 * sum(spans[e % 2]), 0.5 * sum(spans[e // 2])]
         assert np.array_equal(P.geo_global(u), np.array(centre)), (e, P.geo_global(u))
+
+
+def test_assemble_points_port_equals_tensor_assembly():
+    """igo_assemble_points with the tensor rule written out as a point list reproduces igo_assemble (same per-point
+    contribution), element by element, for Poisson / mass / plane elasticity."""
+    spec = PFT.small_patch("plate_hole_p2")
+    Pp = PT.PortPatch(spec["degree"], spec["knots"], spec["cp"], 2)
+    x, w = PT.gauss01(3)
+    X = np.array([[x[q % 3], x[q // 3]] for q in range(9)])
+    W = np.array([w[q % 3] * w[q // 3] for q in range(9)])
+    elem = np.array([0, 3, Pp.nelem - 1], np.int32)
+    off = np.array([0, 9, 18, 27], np.int64)
+    D = np.array([[1.35, 0.58, 0], [0.58, 1.35, 0], [0, 0, 0.385]])
+    for kind in (0, 1, 2):
+        Kp, fp = Pp.assemble_points(kind, elem, off, np.tile(X, (3, 1)), np.tile(W, 3), D=D if kind == 2 else None, fconst=1.2)
+        for k, e in enumerate(elem):
+            Kt, ft = Pp.assemble(kind, [x, x], [w, w], D=D if kind == 2 else None, fconst=1.2, elem_begin=int(e), elem_end=int(e) + 1)
+            assert np.abs(Kp[k] - Kt[0]).max() <= 1e-14 * np.abs(Kt).max()
+            assert np.abs(fp[k] - ft[0]).max() <= 1e-14 * np.abs(ft).max()
