@@ -112,16 +112,19 @@ def run_reference(args, rank, world):
     else:
         O, kind = PT.PortPatch(pd.degree, pd.knotSpans, pd.cp, 3), "port"
     xi = [PD.gaussLegendre01(NQ1)[0]] * 3
-    layers = 1  # 16,384 elements = 1,048,576 points per step
+    layers = 2  # 32,768 elements = 2,097,152 points per step (4.5 GB of output, ~0.7 s on 16 cores)
     nel = 128 * 128 * layers
     ncpu = len(os.sched_getaffinity(0))  # torchrun exports OMP_NUM_THREADS=1: ask for every core explicitly
-    for _ in range(args.warmup):
-        O.eval_tensor(xi, order=1, elem_begin=0, elem_end=nel, want=FIELDS, nthreads=ncpu)
+    # the output buffers are allocated and touched once, outside the timed region (the reference arm is timed on its
+    # arithmetic, not on page faults of fresh numpy arrays)
+    out = None
+    for _ in range(max(1, args.warmup)):
+        out = O.eval_tensor(xi, order=1, elem_begin=0, elem_end=nel, want=FIELDS, nthreads=ncpu, out=out)
     t0 = time.perf_counter()
     threads = 1
     for s in range(args.steps):
-        eb = (s % 64) * nel
-        threads = O.eval_tensor(xi, order=1, elem_begin=eb, elem_end=eb + nel, want=FIELDS, nthreads=ncpu)["threads"]
+        eb = (s % 32) * nel
+        threads = O.eval_tensor(xi, order=1, elem_begin=eb, elem_end=eb + nel, want=FIELDS, nthreads=ncpu, out=out)["threads"]
     dt = time.perf_counter() - t0
     val = args.steps * nel * NQ / dt
     sample = "%d k-layer(s) of the C2 patch per step (%d elements, %d points), outputs %s" % (
@@ -411,9 +414,10 @@ def main():
         c_layers = 4
         c_el = 128 * 128 * c_layers
         ncpu = len(os.sched_getaffinity(0))
-        O.eval_tensor(xi, order=1, elem_begin=0, elem_end=128 * 16, want=FIELDS, nthreads=ncpu)  # warm
-        t0 = time.perf_counter()
+        # first call allocates and touches the 9 GB of output (untimed), the timed call reuses the buffers
         r = O.eval_tensor(xi, order=1, elem_begin=0, elem_end=c_el, want=FIELDS, nthreads=ncpu)
+        t0 = time.perf_counter()
+        r = O.eval_tensor(xi, order=1, elem_begin=c_el, elem_end=2 * c_el, want=FIELDS, nthreads=ncpu, out=r)
         dt = time.perf_counter() - t0
         cpu = {"value": c_el * NQ / dt, "unit": "points/s", "cores": r["threads"], "kind": kind,
                "sample": "%d k-layers of the same patch (%d elements, %d points), same outputs, %.1f s wall" % (

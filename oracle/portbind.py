@@ -161,12 +161,13 @@ class PortPatch:
         return out
 
     def eval_tensor(self, xi1d, order=1, elem_begin=0, elem_end=None,
-                    want=("N", "dN", "d2N", "x", "Jt", "H", "detJ", "JinvT"), nthreads=0):
+                    want=("N", "dN", "d2N", "x", "Jt", "H", "detJ", "JinvT"), nthreads=0, out=None):
         if elem_end is None:
             elem_end = self.nelem
         nq1 = _i32([len(x) for x in xi1d])
         npts = (elem_end - elem_begin) * int(np.prod(nq1))
-        out = self._alloc(npts, order, want)
+        if out is None:
+            out = self._alloc(npts, order, want)
         xcat = _f64(np.concatenate([_f64(x) for x in xi1d]))
         used = lib().igo_eval_tensor(C.byref(self.c), elem_begin, elem_end, order, _i(nq1), _d(xcat), _d(out["N"]),
                                      _d(out["dN"]), _d(out["d2N"]), _d(out["x"]), _d(out["Jt"]), _d(out["H"]),

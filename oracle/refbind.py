@@ -197,14 +197,15 @@ class RefPatch:
         return out
 
     def eval_tensor(self, xi1d, order=1, elem_begin=0, elem_end=None, want=("N", "dN", "d2N", "x", "Jt", "H", "detJ"),
-                    nthreads=0):
+                    nthreads=0, out=None):
         """Element-batched evaluation at the tensor rule xi1d (list of 1-D arrays in [0,1]); reference kernel path."""
         if elem_end is None:
             elem_end = self.nelem
         nq1 = _i32([len(x) for x in xi1d])
         nq = int(np.prod(nq1))
         npts = (elem_end - elem_begin) * nq
-        out = self._alloc(npts, order, want)
+        if out is None:  # a caller timing the evaluation passes its buffers in (no allocation / first touch per call)
+            out = self._alloc(npts, order, want)
         xcat = _f64(np.concatenate([_f64(x) for x in xi1d]))
         used = lib().oref_eval_tensor(self.h, elem_begin, elem_end, order, _i(nq1), _d(xcat), _d(out["N"]),
                                       _d(out["dN"]), _d(out["d2N"]), _d(out["x"]), _d(out["Jt"]), _d(out["H"]),
