@@ -1088,3 +1088,56 @@ def test_element_matrices_from_point_lists(p, dw, kind):
     assert relerr(K[-1], Kt[0]) <= TOL and relerr(f[-1], ft[0]) <= TOL           # tensor rule as a list
     with pytest.raises(capi.IgabError):
         P.assemblePoints(kind, np.array([Pp.nelem], np.int32), np.array([0, 1], np.int64), xi[:1], w[:1], D=D)
+
+
+def test_trimmed_patch_poisson_end_to_end():
+    """A trimmed patch end to end on the device path: trim flags (empty / trimmed / full elements) -> compacted DOF map
+    (prepareForTrim, nurbsbasis.hh:599-615), element matrices of the full elements from the tensor rule and of the trimmed
+    elements from their own sub-triangle rules (fillquadraturerule.hh:8-19), COO scatter through the compacted DOF map
+    (poisson.py:113-125) -- against the same loop with the oracle.  The area integrated by the load vector equals the
+    untrimmed area of the full elements plus the triangulated area of the trimmed ones."""
+    import scipy.sparse as sp
+    from dune_iga_b200 import quadrature as QD
+    rng = np.random.default_rng(123)
+    pd = PD.squarePlate(2, 2)                      # 4 x 4 elements, p = 2, unit weights, the unit square
+    spec = dict(degree=pd.degree, knots=pd.knotSpans, cp=pd.cp, dimworld=2)
+    nel = 16
+    flags = np.zeros(nel, np.uint8)
+    flags[[0, 1, 4]] = 1                           # empty corner
+    trimmed = [2, 5, 8]
+    flags[trimmed] = 2
+    P = gpu_patch(spec, trimflags=flags)
+    Pp = port_for(spec)
+    dof, ndof = P.dofmap()
+    dref, nref = Pp.dofmap(flags)
+    assert ndof == nref and np.array_equal(dof, dref) and ndof < 36
+    # each trimmed element keeps the upper-right triangle of its parameter square plus a small one
+    tris = {e: np.array([[[1, 0], [1, 1], [0, 1.0]], [[0.6, 0.1], [0.9, 0.1], [0.9, 0.4]]]) for e in trimmed}
+    elem_pt, xi, w, off = QD.trimmedBatch(tris, order=4)
+    x, wg = PD.gaussLegendre01(3)
+    Kfull, ffull = P.assemble(capi.ASM_POISSON, [x, x], [wg, wg], fconst=1.0)
+    Ktrim, ftrim = P.assemblePoints(capi.ASM_POISSON, np.array(trimmed, np.int32), off, xi, w, fconst=1.0)
+    Kref_full, fref_full = Pp.assemble(capi.ASM_POISSON, [x, x], [wg, wg], fconst=1.0)
+    Kref_trim, fref_trim = Pp.assemble_points(capi.ASM_POISSON, np.array(trimmed, np.int32), off, xi, w, fconst=1.0)
+
+    def scatter(Kf, ff, Kt, ft):
+        rows, cols, vals = [], [], []
+        b = np.zeros(ndof)
+        for e in range(nel):
+            if flags[e] == 1:
+                continue
+            Ke, fe = (Kt[trimmed.index(e)], ft[trimmed.index(e)]) if flags[e] == 2 else (Kf[e], ff[e])
+            rows.append(np.repeat(dof[e], 9)); cols.append(np.tile(dof[e], 9)); vals.append(Ke.reshape(-1))
+            np.add.at(b, dof[e], fe)
+        A = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(ndof, ndof)).tocsr()
+        return A, b
+
+    A, b = scatter(Kfull, ffull, Ktrim, ftrim)
+    Ar, br = scatter(Kref_full, fref_full, Kref_trim, fref_trim)
+    assert abs(A - Ar).max() <= 1e-12 * abs(Ar).max() and np.abs(b - br).max() <= 1e-12 * np.abs(br).max()
+    assert (dof[flags != 1] >= 0).all() and np.abs(A @ np.ones(ndof)).max() <= 1e-12 * abs(A).max()   # constants in the kernel
+    # sum_i f_i = integral of 1 over the kept domain = sum of w detJ over the full elements' rule and the trimmed rules
+    det = P.evalTensor([x, x], order=1, want=("detJ",))["detJ"].reshape(nel, 9)
+    area = (det[flags == 0] * np.outer(wg, wg).reshape(-1)).sum() + \
+        (P.evalPoints(elem_pt, xi, order=1, want=("detJ",))["detJ"] * w).sum()
+    assert abs(b.sum() - area) <= 1e-13
