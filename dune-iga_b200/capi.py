@@ -17,7 +17,7 @@ dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)
 HOST, DEVICE = 0, 1
 OK, INVALID_ARGUMENT, OUT_OF_MEMORY, CUDA_ERROR, NCCL_ERROR, UNSUPPORTED = range(6)
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TENSOR = 0, 1, 2
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TENSOR, KERNEL_WARP = 0, 1, 2, 3
 ASM_POISSON, ASM_MASS, ASM_ELASTICITY = 0, 1, 2
 FIELDS = ("N", "dN", "d2N", "x", "Jt", "H", "detJ", "JinvT")
 EXPORTS = ("igab_last_error_string", "igab_version", "igab_launch_count", "igab_host_alloc", "igab_host_free",

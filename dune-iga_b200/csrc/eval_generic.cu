@@ -13,6 +13,7 @@
 // HBM-bound on its stores (thread-per-point stores are sector-complete but not line-coalesced); the tuned tensor
 // kernel is the one measured against the roofline.
 #include "bspline_device.cuh"
+#include "geom_small.cuh"
 #include "igab_internal.cuh"
 
 namespace igab {
@@ -97,57 +98,6 @@ __device__ void ders1d(double u, const double* __restrict__ U, int p, int sp, do
     for (int j = 0; j <= p; ++j) dN[k][j] *= fac;
     fac *= (p - k);
   }
-}
-
-template <int DIM, int DW>
-__device__ __forceinline__ double sqrt_det_aat(const double (*J)[DW]) {
-  if constexpr (DIM == 1) {
-    double s = 0;
-    for (int c = 0; c < DW; ++c) s += J[0][c] * J[0][c];
-    return sqrt(s);
-  } else if constexpr (DIM == 2 && DW == 2) {
-    return fabs(J[0][0] * J[1][1] - J[0][1] * J[1][0]);
-  } else if constexpr (DIM == 2 && DW == 3) {
-    const double v0 = J[0][0] * J[1][1] - J[0][1] * J[1][0];
-    const double v1 = J[0][0] * J[1][2] - J[1][0] * J[0][2];
-    const double v2 = J[0][1] * J[1][2] - J[0][2] * J[1][1];
-    return sqrt(v0 * v0 + v1 * v1 + v2 * v2);
-  } else {
-    return fabs(J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
-                J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]));
-  }
-}
-
-// JinvT = J^T (J J^T)^-1, [DW][DIM]
-template <int DIM, int DW>
-__device__ __forceinline__ void right_inv(const double (*J)[DW], double* out) {
-  double G[DIM][DIM], Gi[DIM][DIM];
-  for (int i = 0; i < DIM; ++i)
-    for (int j = 0; j < DIM; ++j) {
-      double s = 0;
-      for (int c = 0; c < DW; ++c) s += J[i][c] * J[j][c];
-      G[i][j] = s;
-    }
-  if constexpr (DIM == 1) {
-    Gi[0][0] = 1.0 / G[0][0];
-  } else if constexpr (DIM == 2) {
-    const double det = G[0][0] * G[1][1] - G[0][1] * G[1][0];
-    Gi[0][0] = G[1][1] / det; Gi[0][1] = -G[0][1] / det; Gi[1][0] = -G[1][0] / det; Gi[1][1] = G[0][0] / det;
-  } else {
-    const double c00 = G[1][1] * G[2][2] - G[1][2] * G[2][1];
-    const double c01 = G[1][2] * G[2][0] - G[1][0] * G[2][2];
-    const double c02 = G[1][0] * G[2][1] - G[1][1] * G[2][0];
-    const double det = G[0][0] * c00 + G[0][1] * c01 + G[0][2] * c02;
-    Gi[0][0] = c00 / det; Gi[0][1] = (G[0][2] * G[2][1] - G[0][1] * G[2][2]) / det; Gi[0][2] = (G[0][1] * G[1][2] - G[0][2] * G[1][1]) / det;
-    Gi[1][0] = c01 / det; Gi[1][1] = (G[0][0] * G[2][2] - G[0][2] * G[2][0]) / det; Gi[1][2] = (G[0][2] * G[1][0] - G[0][0] * G[1][2]) / det;
-    Gi[2][0] = c02 / det; Gi[2][1] = (G[0][1] * G[2][0] - G[0][0] * G[2][1]) / det; Gi[2][2] = (G[0][0] * G[1][1] - G[0][1] * G[1][0]) / det;
-  }
-  for (int c = 0; c < DW; ++c)
-    for (int j = 0; j < DIM; ++j) {
-      double s = 0;
-      for (int k = 0; k < DIM; ++k) s += J[k][c] * Gi[k][j];
-      out[c * DIM + j] = s;
-    }
 }
 
 template <int DIM>

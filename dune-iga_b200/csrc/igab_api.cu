@@ -260,19 +260,32 @@ static igab_status run_eval_tensor_device(igab_patch* p, long long eb, long long
   const EvalOutDev od = to_dev(out);
   const long long nel = ee - eb;
   if (nel == 0) return IGAB_OK;
-  bool sf = p->kernel_mode != IGAB_KERNEL_GENERIC && eval_tensor_sf_supported(p->dev, nq1, order, od);
-  const bool t2 = p->kernel_mode != IGAB_KERNEL_GENERIC && eval_tensor_2d_supported(p->dev, nq1, order, od);
+  const bool tuned = p->kernel_mode == IGAB_KERNEL_AUTO || p->kernel_mode == IGAB_KERNEL_TENSOR;
+  bool sf = tuned && eval_tensor_sf_supported(p->dev, nq1, order, od);
+  const bool t2 = tuned && eval_tensor_2d_supported(p->dev, nq1, order, od);
   if (t2) return launch_eval_tensor_2d(p->dev, p->sf, src, xi1d_host, nel, order, od, stream);
-  if (p->kernel_mode != IGAB_KERNEL_GENERIC && !getenv("IGAB_NO_BLK") && eval_tensor_blk_supported(p->dev, nq1, order, od))
+  if (tuned && !getenv("IGAB_NO_BLK") && eval_tensor_blk_supported(p->dev, nq1, order, od))
     return launch_eval_tensor_blk(p->dev, p->sf, src, xi1d_host, nel, order, od, stream);
-  if (p->kernel_mode != IGAB_KERNEL_GENERIC && eval_tensor_sf2_supported(p->dev, nq1, order, od))
+  if (tuned && eval_tensor_sf2_supported(p->dev, nq1, order, od))
     return launch_eval_tensor_sf2(p->dev, p->sf, src, xi1d_host, nel, od, stream);
   if (p->kernel_mode == IGAB_KERNEL_TENSOR && !sf) {
     set_error("eval_tensor: no sum-factorised kernel compiled for this (dim, dimworld, degree, rule, outputs)");
     return IGAB_UNSUPPORTED;
   }
   if (sf) return launch_eval_tensor_sf(p->dev, p->sf, src, xi1d_host, nel, order, od, stream);
-  // general kernel: bounded launches
+  // no tuned instantiation: the general warp-per-element kernel (run-time degrees and rule) ...
+  if (p->kernel_mode != IGAB_KERNEL_GENERIC) {
+    EvalOutDev ow = od;
+    if (order < 2) ow.d2N = ow.H = nullptr;
+    if (order < 1) ow.dN = ow.Jt = ow.detJ = ow.JinvT = nullptr;
+    const igab_status st = launch_eval_warp(p->dev, src, nel, order, ow, stream);
+    if (st != IGAB_UNSUPPORTED) return st;
+    if (p->kernel_mode == IGAB_KERNEL_WARP) {
+      set_error("eval_tensor: the element's working set does not fit the warp-per-element kernel");
+      return IGAB_UNSUPPORTED;
+    }
+  }
+  // ... and, where even that does not fit (or on request), the thread-per-point kernel in bounded launches
   const long long maxPts = 1LL << 30;
   const long long elPer = std::max(1LL, maxPts / src.nq);
   for (long long b = 0; b < nel; b += elPer) {
@@ -445,7 +458,7 @@ igab_status igab_patch_sizes(const igab_patch* p, int64_t* n_elem, int32_t* n_el
 }
 
 igab_status igab_patch_set_kernel(igab_patch* p, int kernel) {
-  if (!p || kernel < 0 || kernel > 2) return IGAB_INVALID_ARGUMENT;
+  if (!p || kernel < 0 || kernel > 3) return IGAB_INVALID_ARGUMENT;
   p->kernel_mode = kernel;
   return IGAB_OK;
 }

@@ -83,6 +83,9 @@ igab_status kernel_config(const void* func, int threads, size_t smem, KernelCfg*
 // ---- kernels' host launchers (each returns after enqueueing on `stream`)
 igab_status launch_eval_generic(const PatchDev& P, const PointSource& src, long long npts, int order,
                                 const EvalOutDev& out, cudaStream_t stream);
+// general tensor-rule kernel, one warp per element (eval_warp.cu); IGAB_UNSUPPORTED when shared memory does not fit
+igab_status launch_eval_warp(const PatchDev& P, const PointSource& src, long long nelem, int order,
+                             const EvalOutDev& out, cudaStream_t stream);
 // returns IGAB_UNSUPPORTED when no sum-factorised instantiation matches
 // xi1d_host: the rule on the host (used to decide whether the cached tables are still valid)
 igab_status launch_eval_tensor_sf(const PatchDev& P, SfWorkspace& ws, const PointSource& src,

@@ -58,9 +58,11 @@ enum {
 
 typedef enum { IGAB_HOST = 0, IGAB_DEVICE = 1 } igab_memspace;
 
-/* igab_eval_* kernel choice (igab_patch_set_kernel): AUTO picks the sum-factorised tensor kernel when one is
- * compiled for the patch's (dim, dimworld, degree, rule) and the general per-point kernel otherwise. */
-enum { IGAB_KERNEL_AUTO = 0, IGAB_KERNEL_GENERIC = 1, IGAB_KERNEL_TENSOR = 2 };
+/* igab_eval_* kernel choice (igab_patch_set_kernel): AUTO picks a tuned tensor kernel when one is compiled for the
+ * patch's (dim, dimworld, degree, rule), else the general warp-per-element kernel (run-time degrees and rule), else the
+ * thread-per-point kernel.  GENERIC forces the thread-per-point kernel, WARP the warp-per-element kernel, TENSOR
+ * refuses anything but a tuned kernel (tests compare the paths with each other and with the oracle). */
+enum { IGAB_KERNEL_AUTO = 0, IGAB_KERNEL_GENERIC = 1, IGAB_KERNEL_TENSOR = 2, IGAB_KERNEL_WARP = 3 };
 
 /* element trim flags, values of Dune::IGA::ElementTrimFlag (dune/iga/nurbspatch.hh:633-647) */
 enum { IGAB_TRIM_FULL = 0, IGAB_TRIM_EMPTY = 1, IGAB_TRIM_TRIMMED = 2 };

@@ -33,7 +33,7 @@ def gauss(spec, extra=0):
 
 
 @pytest.mark.parametrize("name", NAMES)
-@pytest.mark.parametrize("kernel", [capi.KERNEL_GENERIC, capi.KERNEL_AUTO], ids=["generic", "auto"])
+@pytest.mark.parametrize("kernel", [capi.KERNEL_GENERIC, capi.KERNEL_AUTO, capi.KERNEL_WARP], ids=["generic", "auto", "warp"])
 def test_eval_tensor_matches_oracle(name, kernel):
     spec = PFT.small_patch(name)
     O, kind = oracle_for(spec)
@@ -866,7 +866,7 @@ def _random_patch(rng, dim, dw, degree):
                          ids=lambda c: "d%dw%d_p%s" % (c[0], c[1], "".join(map(str, c[2]))))
 def test_random_patches_with_repeated_knots(case):
     """Seeded random patches (repeated interior knots up to multiplicity p, random weights) through the tuned kernels
-    (auto) and the general kernel against the oracle, all fields up to second order; spans and DOF maps bit-exact."""
+    (auto), the thread-per-point kernel and the warp-per-element kernel against the oracle, all fields up to second order; spans and DOF maps bit-exact."""
     dim, dw, degree = case
     rng = np.random.default_rng(1000 + 17 * dim + sum(degree) + 100 * dw)
     spec = _random_patch(rng, dim, dw, degree)
@@ -879,7 +879,7 @@ def test_random_patches_with_repeated_knots(case):
         xi1d = [PD.gaussLegendre01(p + 1 + extra)[0] for p in degree]
         ref = O.eval_tensor(xi1d, order=2, want=EVAL_FIELDS)
         assert ref["detJ"].min() > 1e-3
-        for mode in (capi.KERNEL_AUTO, capi.KERNEL_GENERIC):
+        for mode in (capi.KERNEL_AUTO, capi.KERNEL_GENERIC, capi.KERNEL_WARP):
             P.setKernel(mode)
             got = P.evalTensor(xi1d, order=2, want=EVAL_FIELDS)
             for f in EVAL_FIELDS:
@@ -887,6 +887,54 @@ def test_random_patches_with_repeated_knots(case):
             got1 = P.evalTensor(xi1d, order=1, want=("N", "dN", "x", "Jt", "detJ", "JinvT"))
             for f in ("N", "dN", "x", "Jt", "detJ"):
                 assert relerr(got1[f], ref[f]) <= TOL, (f, mode, extra, "order1")
+
+
+@pytest.mark.parametrize("case", [(1, 1, (5,), (7,)), (1, 3, (8,), (33,)), (2, 2, (4, 2), (3, 6)), (2, 3, (5, 5), (7, 5)),
+                                  (3, 3, (2, 1, 1), (3, 2, 2)), (3, 3, (5, 2, 3), (2, 7, 3)), (3, 3, (4, 4, 4), (6, 6, 6)),
+                                  (3, 3, (6, 6, 6), (2, 2, 2)), (3, 3, (3, 3, 3), (1, 1, 1))],
+                         ids=lambda c: "d%dw%d_p%s_q%s" % (c[0], c[1], "".join(map(str, c[2])), "x".join(map(str, c[3]))))
+def test_warp_per_element_kernel_general_degrees_and_rules(case):
+    """The general warp-per-element kernel (eval_warp.cu) on what no tuned kernel covers: degrees up to 8, mixed degrees,
+    rules with a different number of points per direction (fewer and more than 32 points per element, chunk tails),
+    1-D / 2-D / 3-D, against the oracle and the thread-per-point kernel; then sub-ranges and output subsets.  AUTO must
+    route these configurations to it (same bits as WARP)."""
+    dim, dw, degree, nq1 = case
+    rng = np.random.default_rng(7000 + 31 * dim + sum(degree) + 100 * dw + sum(nq1))
+    spec = _random_patch(rng, dim, dw, degree)
+    Pp = port_for(spec)
+    P = gpu_patch(spec)
+    xi1d = [PD.gaussLegendre01(q)[0] for q in nq1]
+    fields1 = ("N", "dN", "x", "Jt", "detJ", "JinvT")
+    ref = Pp.eval_tensor(xi1d, order=2, want=EVAL_FIELDS)
+    P.setKernel(capi.KERNEL_WARP)
+    got = P.evalTensor(xi1d, order=2, want=EVAL_FIELDS)
+    for f in EVAL_FIELDS:
+        assert relerr(got[f], ref[f]) <= TOL, (f, relerr(got[f], ref[f]))
+    assert np.abs(got["N"].sum(1) - 1.0).max() < 1e-13
+    P.setKernel(capi.KERNEL_AUTO)
+    auto = P.evalTensor(xi1d, order=2, want=EVAL_FIELDS)
+    if not (dim == 3 and len(set(degree)) == 1 and len(set(nq1)) == 1 and degree[0] in (2, 3)):  # tuned order-2 kernel
+        for f in EVAL_FIELDS:
+            assert np.array_equal(auto[f], got[f]), f
+    # order 1 and 0, a sub-range that does not start at 0, JinvT
+    eb, ee = Pp.nelem // 3, Pp.nelem
+    P.setKernel(capi.KERNEL_WARP)
+    ref1 = Pp.eval_tensor(xi1d, order=1, elem_begin=eb, elem_end=ee)
+    got1 = P.evalTensor(xi1d, order=1, elem_begin=eb, elem_end=ee)
+    for f in fields1:
+        assert relerr(got1[f], ref1[f]) <= TOL, (f, "order1", relerr(got1[f], ref1[f]))
+    got0 = P.evalTensor(xi1d, order=0, elem_begin=eb, elem_end=ee)
+    assert set(got0) == {"N", "x"}
+    assert np.array_equal(got0["N"], got1["N"]) and np.array_equal(got0["x"], got1["x"])
+    # output subsets give the same bits as the full set
+    for want in (("dN",), ("detJ",), ("x", "JinvT"), ("N", "Jt")):
+        sub = P.evalTensor(xi1d, order=1, elem_begin=eb, elem_end=ee, want=want)
+        assert set(sub) == set(want)
+        for f in want:
+            assert np.array_equal(sub[f], got1[f]), (want, f)
+    sub2 = P.evalTensor(xi1d, order=2, want=("d2N", "H"))
+    assert np.array_equal(sub2["d2N"], got["d2N"]) and np.array_equal(sub2["H"], got["H"])
+    assert P.evalTensor(xi1d, order=1, elem_begin=1, elem_end=1)["N"].shape[0] == 0
 
 
 @pytest.mark.parametrize("p", [1, 2, 3])

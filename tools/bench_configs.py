@@ -82,6 +82,26 @@ def main():
         eval_config("X3 3-D cylinder p=3 64^3 (8 k-layers), 5^3 Gauss, order 1 (general kernel: rule != p+1)", PD.thickCylinder(3, (6, 6, 6)),
                     [5, 5, 5], 1, ("N", "dN", "x", "Jt", "detJ"), el_chunk=64 * 64 * 8)
         eval_config("X4 2-D plate p=2 1024^2, 3x3 Gauss, detJ only (volume path)", PD.plateWithHole(9, 10), [3, 3], 1, ("detJ",))
+    if "W" in which:  # the general kernels: thread per point (generic) against warp per element (warp)
+        F1 = ("N", "dN", "x", "Jt", "detJ")
+        F2 = ("N", "dN", "d2N", "x", "Jt", "H", "detJ")
+        cyl3, cyl4 = PD.thickCylinder(3, (6, 6, 6)), PD.thickCylinder(4, (5, 5, 5))
+        mixed = PD.thickCylinder(2).degreeElevate(0, 1)  # coarse solid at (3,2,2): mixed degrees
+        for d in range(3):
+            mixed = mixed.globalRefineInDirection(d, 6)
+        plate4 = PD.plateWithHole(0, 0).degreeElevate(0, 2).degreeElevate(1, 2)
+        plate4 = plate4.globalRefineInDirection(0, 8).globalRefineInDirection(1, 9)
+        for kn, km in (("generic", capi.KERNEL_GENERIC), ("warp", capi.KERNEL_WARP), ("auto", capi.KERNEL_AUTO)):
+            eval_config("W1[%s] 3-D p=3 64^3 (8 k-layers), 4^3 Gauss, order 1" % kn, cyl3, [4, 4, 4], 1, F1,
+                        el_chunk=64 * 64 * 8, kernel=km)
+            eval_config("W2[%s] 3-D p=3 64^3 (8 k-layers), 6^3 Gauss, order 1 (no tuned kernel)" % kn, cyl3, [6, 6, 6], 1,
+                        F1, el_chunk=64 * 64 * 8, kernel=km)
+            eval_config("W3[%s] 3-D p=(3,2,2), 4x3x3 Gauss, order 1 (mixed degrees)" % kn, mixed, [4, 3, 3], 1, F1,
+                        el_chunk=64 * 64 * 16, kernel=km)
+            eval_config("W4[%s] 3-D p=4 32^3 (8 k-layers), 5^3 Gauss, order 2 (no tuned kernel)" % kn, cyl4, [5, 5, 5], 2,
+                        F2, el_chunk=32 * 32 * 8, kernel=km)
+            eval_config("W5[%s] 2-D plate p=2 elevated to p=4 512^2, 5x5 Gauss, order 1" % kn,
+                        plate4, [5, 5], 1, F1, kernel=km)
     if "C4" in which:
         eval_config("C4 torus shell p=2 in R^3 1024x1024, 4x4 Gauss, order 2", PD.torusSurface(8), [4, 4], 2,
                     ("N", "dN", "d2N", "x", "Jt", "H", "detJ"))
