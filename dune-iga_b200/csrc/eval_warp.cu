@@ -4,17 +4,22 @@
 // eval_tensor_blk.cu) runs on; the thread-per-point kernel of eval_generic.cu remains for explicit point lists.
 //
 // Per element (element iteration of nurbsleafgridview.hh:147-155, batched):
-//   1. lanes <-> (direction, abscissa): univariate values and derivatives by A2.3
-//      (BsplineBasis1D::basisFunctionDerivatives, dune/iga/bsplinealgorithms.hh:148-222) at u = xi*scaling + offset
-//      (nurbsgeometry.hh:365-378), rows pre-multiplied by scaling^k (nurbsbasis.hh:93-95,105-107) -> shared memory;
+//   1. the element's slices of the univariate tables -> shared memory (tables_any_kernel builds them once per launch
+//      for every element of every direction: A2.3 values and derivatives, BsplineBasis1D::basisFunctionDerivatives,
+//      dune/iga/bsplinealgorithms.hh:148-222, at u = xi*scaling + offset, nurbsgeometry.hh:365-378, rows pre-multiplied
+//      by scaling^k, nurbsbasis.hh:93-95,105-107);
 //   2. lanes <-> local control points: netOfSpan (nurbsalgorithms.hh:80-89) -> shared memory, homogeneous (w x, w);
 //   3. 32 points at a time, lanes <-> points: homogeneous sums  G[alpha][c] = sum_i prod_d N_d^(alpha_d) (w P)_i[c]
 //      (control points are broadcast reads), then x, J^T, H, detJ, J^-T by the quotient rule
 //      (nurbsalgorithms.hh:226-248 applied to the geometry; nurbsgeometry.hh:133-138,182-210,257-292);
-//   4. one point at a time, lanes <-> basis functions: R^(alpha)_i by the same quotient rule with the point's W^(alpha)
-//      broadcast by shuffles; N rows leave as coalesced 256 B stores, the [i][d] derivative rows are transposed
-//      through a 32-function slab in shared memory so that they leave as contiguous runs too.
+//   4. lanes <-> basis functions (32 at a time), the chunk's points one after the other: R^(alpha)_i by the same
+//      quotient rule with the point's 1/W and W^(alpha) read back from shared memory (broadcast); the products over the
+//      directions >= 1 are refreshed only when the first direction's abscissa wraps; N rows leave as coalesced 256 B
+//      stores, the [i][d] derivative rows are transposed through a double-buffered 32-function slab in shared memory so
+//      that they leave as contiguous runs too.  One division per point (1/W), none per basis function.
 // HBM-bound on its stores once the local basis has >= 32 functions.
+#include <algorithm>
+
 #include "bspline_device.cuh"
 #include "geom_small.cuh"
 #include "igab_internal.cuh"
@@ -44,17 +49,43 @@ struct WarpLayout {
   int nq1[kMaxDim];
   int nqTot;             // sum nq1
   int packDoubles;       // block-level local-index table
-  int offC, offW, offS1, offS2, perWarp;
+  int offC, offW, offS1, offS2, offQ, perWarp;
+  long long tabGOff[kMaxDim];  // start of direction d's table in the global table buffer
+  long long tabGTotal;
 };
+
+// K1 for run-time degrees: one thread per (direction, element of that direction, abscissa): A2.3 values and derivatives
+// (BsplineBasis1D::basisFunctionDerivatives, dune/iga/bsplinealgorithms.hh:148-222) at u = xi*scaling + offset
+// (nurbsgeometry.hh:365-378), row k pre-multiplied by scaling^k (nurbsbasis.hh:93-95,105-107).
+// Layout per direction: [e_d][q][k][j], abscissa stride strideQ (odd), so an element's slice is one contiguous run.
+__global__ void tables_any_kernel(PatchDev P, PointSource src, WarpLayout L, int order, double* __restrict__ tabG) {
+  const int d = blockIdx.y;
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= P.nel[d] * L.nq1[d]) return;
+  const int e = item / L.nq1[d], q = item % L.nq1[d];
+  const double* U = P.knots[d];
+  const int p = P.degree[d], sp = P.spanTab[d][e];
+  const double lo = U[sp], scale = U[sp + 1] - lo;
+  const double u = src.xi1d[d][q] * scale + lo;
+  double loc[3 * kPM];
+  ders1d_any(u, U, p, sp, order, loc);
+  double* t = tabG + L.tabGOff[d] + (size_t)item * L.strideQ[d];
+  double sc = 1.0;
+  for (int k = 0; k <= order; ++k) {
+    for (int j = 0; j <= p; ++j) t[k * (p + 1) + j] = loc[k * kPM + j] * sc;
+    sc *= scale;
+  }
+  if ((((order + 1) * (p + 1)) & 1) == 0) t[(order + 1) * (p + 1)] = 0.0;  // the padding word is copied, keep it defined
+}
 
 template <int DIM, int DW, int ORDER>
 __global__ void __launch_bounds__(128)
-    eval_warp_kernel(PatchDev P, PointSource src, long long nelem, EvalOutDev out, WarpLayout L) {
+    eval_warp_kernel(PatchDev P, PointSource src, long long nelem, EvalOutDev out, WarpLayout L,
+                     const double* __restrict__ tabG) {
   extern __shared__ __align__(16) double smem[];
   constexpr int NH = Al<DIM>::NH;
   constexpr int NA = (ORDER == 0) ? 1 : (ORDER == 1 ? 1 + DIM : 1 + DIM + NH);
   constexpr int C1 = DW + 1;
-  constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int nb = P.nb;
   int n1[kMaxDim];
@@ -75,46 +106,33 @@ __global__ void __launch_bounds__(128)
   double* sW = sT + L.offW;
   double* sS1 = sT + L.offS1;  // two slabs [32][DIM]
   double* sS2 = sT + L.offS2;  // two slabs [32][NH]
+  double* sQ = sT + L.offQ;    // [32][NA]: 1/W, W^(alpha) of the chunk's points
   const long long nq = src.nq;
 
   for (long long we = (long long)blockIdx.x * nwarp + warp; we < nelem; we += (long long)gridDim.x * nwarp) {
     // ---- element -> span, offset, scaling (nurbspatch.hh:248-253, nurbsgeometry.hh:64-68)
-    int sp[DIM];
+    int sp[DIM], ed[DIM];
     long long cpStride[DIM], cpBase = 0;
     {
       long long h = src.elem_begin + we, stride = 1;
 #pragma unroll
       for (int d = 0; d < DIM; ++d) {
-        const int ed = (int)(h % P.nel[d]);
+        ed[d] = (int)(h % P.nel[d]);
         h /= P.nel[d];
-        sp[d] = P.spanTab[d][ed];
+        sp[d] = P.spanTab[d][ed[d]];
         cpStride[d] = stride;
         cpBase += (long long)(sp[d] - P.degree[d]) * stride;
         stride *= P.ncp[d];
       }
     }
     __syncwarp();  // the previous element's readers are done with sT / sC
-    // ---- 1. univariate tables
-    for (int item = lane; item < L.nqTot; item += 32) {
-      int d = 0, q = item;
+    // ---- 1. the element's slices of the univariate tables (built once per launch by tables_any_kernel)
 #pragma unroll
-      for (int dd = 0; dd < DIM - 1; ++dd)
-        if (d == dd && q >= L.nq1[dd]) {
-          q -= L.nq1[dd];
-          d = dd + 1;
-        }
-      const double* U = P.knots[d];
-      const int p = P.degree[d];
-      const double lo = U[sp[d]], scale = U[sp[d] + 1] - lo;
-      const double u = src.xi1d[d][q] * scale + lo;
-      double loc[(ORDER + 1) * kPM];
-      ders1d_any(u, U, p, sp[d], ORDER, loc);
-      double* t = sT + L.tabOff[d] + q * L.strideQ[d];
-      double sc = 1.0;
-      for (int k = 0; k <= ORDER; ++k) {
-        for (int j = 0; j <= p; ++j) t[k * (p + 1) + j] = loc[k * kPM + j] * sc;
-        sc *= scale;
-      }
+    for (int d = 0; d < DIM; ++d) {
+      const int len = L.nq1[d] * L.strideQ[d];
+      const double* g = tabG + L.tabGOff[d] + (size_t)ed[d] * len;
+      double* t = sT + L.tabOff[d];
+      for (int j = lane; j < len; j += 32) t[j] = __ldg(g + j);
     }
     // ---- 2. control points of the span, homogeneous
     for (int i = lane; i < nb; i += 32) {
@@ -132,20 +150,21 @@ __global__ void __launch_bounds__(128)
     __syncwarp();
 
     const long long pt0 = we * nq;
-    for (long long qb = 0; qb < nq; qb += 32) {
-      const int cnt = (int)((nq - qb < 32) ? (nq - qb) : 32);
+    const int nqi = (int)nq;
+    for (int qb = 0; qb < nqi; qb += 32) {
+      const int cnt = (nqi - qb < 32) ? (nqi - qb) : 32;
       // ---- 3. geometry of 32 points, lane <-> point
-      double G[NA][C1];
-#pragma unroll
-      for (int a = 0; a < NA; ++a)
-#pragma unroll
-        for (int c = 0; c < C1; ++c) G[a][c] = 0.0;
       if (lane < cnt) {
-        long long q = qb + lane;
+        double G[NA][C1];
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+#pragma unroll
+          for (int c = 0; c < C1; ++c) G[a][c] = 0.0;
+        int q = qb + lane;
         const double* t[kMaxDim];
 #pragma unroll
         for (int d = 0; d < DIM; ++d) {
-          t[d] = sT + L.tabOff[d] + (int)(q % L.nq1[d]) * L.strideQ[d];
+          t[d] = sT + L.tabOff[d] + (q % L.nq1[d]) * L.strideQ[d];
           q /= L.nq1[d];
         }
         int i = 0;
@@ -175,11 +194,15 @@ __global__ void __launch_bounds__(128)
             }
           }
         }
-        const double W0 = G[0][DW];
+        // quotient rule on the geometry; the point's 1/W and W^(alpha) go to shared memory for phase 4
+        const double inv = 1.0 / G[0][DW];
+        sQ[lane * NA] = inv;
+#pragma unroll
+        for (int a = 1; a < NA; ++a) sQ[lane * NA + a] = G[a][DW];
         const long long pt = pt0 + qb + lane;
         double X[DW];
 #pragma unroll
-        for (int c = 0; c < DW; ++c) X[c] = G[0][c] / W0;
+        for (int c = 0; c < DW; ++c) X[c] = G[0][c] * inv;
         if (out.x)
 #pragma unroll
           for (int c = 0; c < DW; ++c) out.x[pt * DW + c] = X[c];
@@ -188,7 +211,7 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
           for (int d = 0; d < DIM; ++d)
 #pragma unroll
-            for (int c = 0; c < DW; ++c) J[d][c] = (G[1 + d][c] - G[1 + d][DW] * X[c]) / W0;
+            for (int c = 0; c < DW; ++c) J[d][c] = (G[1 + d][c] - G[1 + d][DW] * X[c]) * inv;
           if (out.Jt)
 #pragma unroll
             for (int d = 0; d < DIM; ++d)
@@ -203,7 +226,7 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
                 for (int c = 0; c < DW; ++c)
                   out.H[pt * NH * DW + d * DW + c] =
-                      (G[1 + DIM + d][c] - 2.0 * G[1 + d][DW] * J[d][c] - G[1 + DIM + d][DW] * X[c]) / W0;
+                      (G[1 + DIM + d][c] - 2.0 * G[1 + d][DW] * J[d][c] - G[1 + DIM + d][DW] * X[c]) * inv;
               int m = 0;
 #pragma unroll
               for (int c0 = 0; c0 < DIM; ++c0)
@@ -213,7 +236,7 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
                   for (int c = 0; c < DW; ++c)
                     out.H[pt * NH * DW + (DIM + m) * DW + c] =
-                        (G[a][c] - G[1 + c0][DW] * J[c1][c] - G[1 + c1][DW] * J[c0][c] - G[a][DW] * X[c]) / W0;
+                        (G[a][c] - G[1 + c0][DW] * J[c1][c] - G[1 + c1][DW] * J[c0][c] - G[a][DW] * X[c]) * inv;
                   ++m;
                 }
             }
@@ -221,63 +244,74 @@ __global__ void __launch_bounds__(128)
         }
       }
       if (!(out.N || out.dN || out.d2N)) continue;
-      // ---- 4. basis rows, one point at a time, lane <-> basis function
+      __syncwarp();  // sQ visible
+      // ---- 4. basis rows: lane <-> basis function (32 at a time), then the chunk's points one after the other.  The
+      //         points run first-direction-fastest, so the products over the directions >= 1 change only when q0 wraps.
+      const bool wd = (ORDER >= 1) && out.dN != nullptr;
+      const bool wh = (ORDER >= 2) && out.d2N != nullptr;
       int buf = 0;
-      for (int tp = 0; tp < cnt; ++tp) {
-        double Wt[NA];
-#pragma unroll
-        for (int a = 0; a < NA; ++a) Wt[a] = __shfl_sync(FULL, G[a][DW], tp);
-        long long q = qb + tp;
-        const double* t[kMaxDim];
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) {
-          t[d] = sT + L.tabOff[d] + (int)(q % L.nq1[d]) * L.strideQ[d];
-          q /= L.nq1[d];
+      for (int ib = 0; ib < nb; ib += 32) {
+        const int i = ib + lane;
+        const bool act = i < nb;
+        const int rows = (nb - ib < 32) ? (nb - ib) : 32;
+        const unsigned pk = pack[act ? i : 0];
+        const double w = sW[act ? i : 0];
+        const double* b0 = sT + L.tabOff[0] + (int)(pk & 255u);
+        const double* b1 = sT + L.tabOff[1] + (int)((pk >> 8) & 255u);
+        const double* b2 = sT + L.tabOff[2] + (int)(pk >> 16);
+        int q0 = qb % L.nq1[0], q1 = 0, q2 = 0;
+        if constexpr (DIM >= 2) {
+          const int r = qb / L.nq1[0];
+          q1 = r % L.nq1[1];
+          q2 = r / L.nq1[1];
         }
-        const long long pt = pt0 + qb + tp;
-        for (int ib = 0; ib < nb; ib += 32, buf ^= 1) {
-          const int i = ib + lane;
-          double R[NA];
-          if (i < nb) {
-            const unsigned pk = pack[i];
-            const int l0 = pk & 255u, l1 = (pk >> 8) & 255u, l2 = pk >> 16;
-            const double w = sW[i];
+        bool fresh = true;
+        double g12[NA];
+        for (int tp = 0; tp < cnt; ++tp, buf ^= 1) {
+          if (fresh) {
+            fresh = false;
 #pragma unroll
             for (int a = 0; a < NA; ++a) {
-              double f = t[0][Al<DIM>::comp(a, 0) * n1[0] + l0];
-              if constexpr (DIM >= 2) f *= t[1][Al<DIM>::comp(a, 1) * n1[1] + l1];
-              if constexpr (DIM >= 3) f *= t[2][Al<DIM>::comp(a, 2) * n1[2] + l2];
-              R[a] = f * w;
+              double f = w;
+              if constexpr (DIM >= 2) f *= b1[q1 * L.strideQ[1] + Al<DIM>::comp(a, 1) * n1[1]];
+              if constexpr (DIM >= 3) f *= b2[q2 * L.strideQ[2] + Al<DIM>::comp(a, 2) * n1[2]];
+              g12[a] = f;
             }
-            // quotient rule, nurbsalgorithms.hh:226-248
-            R[0] = R[0] / Wt[0];
-            if constexpr (ORDER >= 1) {
-#pragma unroll
-              for (int d = 0; d < DIM; ++d) R[1 + d] = (R[1 + d] - Wt[1 + d] * R[0]) / Wt[0];
-            }
-            if constexpr (ORDER >= 2) {
-#pragma unroll
-              for (int d = 0; d < DIM; ++d)
-                R[1 + DIM + d] = (R[1 + DIM + d] - 2.0 * Wt[1 + d] * R[1 + d] - Wt[1 + DIM + d] * R[0]) / Wt[0];
-              int m = 0;
-#pragma unroll
-              for (int c0 = 0; c0 < DIM; ++c0)
-#pragma unroll
-                for (int c1 = c0 + 1; c1 < DIM; ++c1) {
-                  const int a = 1 + 2 * DIM + m;
-                  R[a] = (R[a] - Wt[1 + c0] * R[1 + c1] - Wt[1 + c1] * R[1 + c0] - Wt[a] * R[0]) / Wt[0];
-                  ++m;
-                }
-            }
-            if (out.N) out.N[pt * nb + i] = R[0];
           }
+          double t0[ORDER + 1];
+#pragma unroll
+          for (int k = 0; k <= ORDER; ++k) t0[k] = b0[q0 * L.strideQ[0] + k * n1[0]];
+          const double* wq = sQ + tp * NA;  // broadcast reads
+          const double inv = wq[0];
+          double R[NA];
+#pragma unroll
+          for (int a = 0; a < NA; ++a) R[a] = t0[Al<DIM>::comp(a, 0)] * g12[a];
+          // quotient rule, nurbsalgorithms.hh:226-248
+          R[0] *= inv;
           if constexpr (ORDER >= 1) {
-            const int rows = (nb - ib < 32) ? (nb - ib) : 32;
-            const bool wd = out.dN != nullptr;
-            const bool wh = (ORDER >= 2) && out.d2N != nullptr;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) R[1 + d] = (R[1 + d] - wq[1 + d] * R[0]) * inv;
+          }
+          if constexpr (ORDER >= 2) {
+#pragma unroll
+            for (int d = 0; d < DIM; ++d)
+              R[1 + DIM + d] = (R[1 + DIM + d] - 2.0 * wq[1 + d] * R[1 + d] - wq[1 + DIM + d] * R[0]) * inv;
+            int m = 0;
+#pragma unroll
+            for (int c0 = 0; c0 < DIM; ++c0)
+#pragma unroll
+              for (int c1 = c0 + 1; c1 < DIM; ++c1) {
+                const int a = 1 + 2 * DIM + m;
+                R[a] = (R[a] - wq[1 + c0] * R[1 + c1] - wq[1 + c1] * R[1 + c0] - wq[a] * R[0]) * inv;
+                ++m;
+              }
+          }
+          const long long pt = pt0 + qb + tp;
+          if (act && out.N) out.N[pt * nb + i] = R[0];
+          if constexpr (ORDER >= 1) {
             double* s1 = sS1 + buf * 32 * DIM;
             double* s2 = sS2 + buf * 32 * NH;
-            if (i < nb) {
+            if (act) {
               if (wd)
 #pragma unroll
                 for (int d = 0; d < DIM; ++d) s1[lane * DIM + d] = R[1 + d];
@@ -307,9 +341,17 @@ __global__ void __launch_bounds__(128)
               }
             }
           }
+          if (++q0 == L.nq1[0]) {
+            q0 = 0;
+            fresh = true;
+            if (++q1 == L.nq1[1]) {
+              q1 = 0;
+              ++q2;
+            }
+          }
         }
       }
-      __syncwarp();  // slabs are reused by the next chunk from buffer 0
+      __syncwarp();  // sQ and the slabs are rewritten by the next chunk
     }
   }
 }
@@ -338,6 +380,8 @@ igab_status launch_o(const PatchDev& P, const PointSource& src, long long nelem,
   off += 2 * 32 * DIM;
   L.offS2 = off;
   off += 2 * 32 * NH;
+  L.offQ = off;
+  off += 32 * (1 + DIM + NH);
   L.perWarp = ev(off);
   L.packDoubles = ev((P.nb + 1) / 2);
   auto kern = eval_warp_kernel<DIM, DW, ORDER>;
@@ -354,9 +398,22 @@ igab_status launch_o(const PatchDev& P, const PointSource& src, long long nelem,
   long long blocks = (long long)kc.sms * bps;
   const long long need = (nelem + warps - 1) / warps;
   if (blocks > need) blocks = need;
-  kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(P, src, nelem, out, L);
-  count_launch();
+  // univariate tables of this rule for all elements of every direction: a few hundred KB, stream-ordered scratch
+  long long tot = 0;
+  int maxItems = 0;
+  for (int d = 0; d < DIM; ++d) {
+    L.tabGOff[d] = tot;
+    tot += (long long)P.nel[d] * src.nq1[d] * L.strideQ[d];
+    maxItems = std::max(maxItems, P.nel[d] * src.nq1[d]);
+  }
+  L.tabGTotal = tot;
+  double* tabG = nullptr;
+  IGAB_CUDA_TRY(cudaMallocAsync(&tabG, sizeof(double) * tot, stream));
+  tables_any_kernel<<<dim3((maxItems + 127) / 128, DIM), 128, 0, stream>>>(P, src, L, ORDER, tabG);
+  kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(P, src, nelem, out, L, tabG);
+  count_launch(2);
   IGAB_CUDA_TRY(cudaGetLastError());
+  IGAB_CUDA_TRY(cudaFreeAsync(tabG, stream));
   return IGAB_OK;
 }
 
