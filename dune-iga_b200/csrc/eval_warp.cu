@@ -180,8 +180,17 @@ __global__ void __launch_bounds__(128)
             }
             for (int l0 = 0; l0 < n1[0]; ++l0, ++i) {
               double hc[C1];
+              if constexpr (C1 % 2 == 0) {  // 16-byte aligned rows: broadcast LDS.128
 #pragma unroll
-              for (int c = 0; c < C1; ++c) hc[c] = sC[i * C1 + c];
+                for (int c = 0; c < C1; c += 2) {
+                  const double2 v = *reinterpret_cast<const double2*>(sC + i * C1 + c);
+                  hc[c] = v.x;
+                  hc[c + 1] = v.y;
+                }
+              } else {
+#pragma unroll
+                for (int c = 0; c < C1; ++c) hc[c] = sC[i * C1 + c];
+              }
               double t0[ORDER + 1];
 #pragma unroll
               for (int k = 0; k <= ORDER; ++k) t0[k] = t[0][k * n1[0] + l0];
@@ -247,9 +256,13 @@ __global__ void __launch_bounds__(128)
       __syncwarp();  // sQ visible
       // ---- 4. basis rows: lane <-> basis function (32 at a time), then the chunk's points one after the other.  The
       //         points run first-direction-fastest, so the products over the directions >= 1 change only when q0 wraps.
+      const bool wn = out.N != nullptr;
       const bool wd = (ORDER >= 1) && out.dN != nullptr;
       const bool wh = (ORDER >= 2) && out.d2N != nullptr;
-      int buf = 0;
+      const int s0 = L.strideQ[0], s1q = L.strideQ[1], s2q = L.strideQ[2];
+      const int nq0 = L.nq1[0], nq1b = L.nq1[1];
+      int bo = 0;  // slab buffer toggle (0 / 1)
+      const long long ptb = pt0 + qb;
       for (int ib = 0; ib < nb; ib += 32) {
         const int i = ib + lane;
         const bool act = i < nb;
@@ -259,30 +272,43 @@ __global__ void __launch_bounds__(128)
         const double* b0 = sT + L.tabOff[0] + (int)(pk & 255u);
         const double* b1 = sT + L.tabOff[1] + (int)((pk >> 8) & 255u);
         const double* b2 = sT + L.tabOff[2] + (int)(pk >> 16);
-        int q0 = qb % L.nq1[0], q1 = 0, q2 = 0;
+        int q0 = qb % nq0, q1 = 0, q2 = 0;
         if constexpr (DIM >= 2) {
-          const int r = qb / L.nq1[0];
-          q1 = r % L.nq1[1];
-          q2 = r / L.nq1[1];
+          const int r = qb / nq0;
+          q1 = r % nq1b;
+          q2 = r / nq1b;
         }
+        const double* p0 = b0 + q0 * s0;
+        const double* p1 = b1 + q1 * s1q;
+        const double* p2 = b2 + q2 * s2q;
+        const double* wq = sQ;
+        double* pN = out.N + ptb * nb + i;
+        double* pD = nullptr;
+        double* pH = nullptr;
+        if constexpr (ORDER >= 1) pD = out.dN + (ptb * nb + ib) * DIM + lane;
+        if constexpr (ORDER >= 2) pH = out.d2N + (ptb * nb + ib) * NH + lane;
+        bool okD[DIM > 0 ? DIM : 1], okH[NH];
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) okD[k] = wd && (k * 32 + lane < rows * DIM);
+#pragma unroll
+        for (int k = 0; k < NH; ++k) okH[k] = wh && (k * 32 + lane < rows * NH);
         bool fresh = true;
         double g12[NA];
-        for (int tp = 0; tp < cnt; ++tp, buf ^= 1) {
+        for (int tp = 0; tp < cnt; ++tp) {
           if (fresh) {
             fresh = false;
 #pragma unroll
             for (int a = 0; a < NA; ++a) {
               double f = w;
-              if constexpr (DIM >= 2) f *= b1[q1 * L.strideQ[1] + Al<DIM>::comp(a, 1) * n1[1]];
-              if constexpr (DIM >= 3) f *= b2[q2 * L.strideQ[2] + Al<DIM>::comp(a, 2) * n1[2]];
+              if constexpr (DIM >= 2) f *= p1[Al<DIM>::comp(a, 1) * n1[1]];
+              if constexpr (DIM >= 3) f *= p2[Al<DIM>::comp(a, 2) * n1[2]];
               g12[a] = f;
             }
           }
           double t0[ORDER + 1];
 #pragma unroll
-          for (int k = 0; k <= ORDER; ++k) t0[k] = b0[q0 * L.strideQ[0] + k * n1[0]];
-          const double* wq = sQ + tp * NA;  // broadcast reads
-          const double inv = wq[0];
+          for (int k = 0; k <= ORDER; ++k) t0[k] = p0[k * n1[0]];
+          const double inv = wq[0];  // broadcast reads
           double R[NA];
 #pragma unroll
           for (int a = 0; a < NA; ++a) R[a] = t0[Al<DIM>::comp(a, 0)] * g12[a];
@@ -306,11 +332,10 @@ __global__ void __launch_bounds__(128)
                 ++m;
               }
           }
-          const long long pt = pt0 + qb + tp;
-          if (act && out.N) out.N[pt * nb + i] = R[0];
+          if (act && wn) *pN = R[0];
           if constexpr (ORDER >= 1) {
-            double* s1 = sS1 + buf * 32 * DIM;
-            double* s2 = sS2 + buf * 32 * NH;
+            double* s1 = sS1 + bo * (32 * DIM);
+            double* s2 = sS2 + bo * (32 * NH);
             if (act) {
               if (wd)
 #pragma unroll
@@ -322,31 +347,30 @@ __global__ void __launch_bounds__(128)
               }
             }
             if (wd || wh) __syncwarp();
-            if (wd) {
-              double* o = out.dN + (pt * nb + ib) * DIM;
 #pragma unroll
-              for (int k = 0; k < DIM; ++k) {
-                const int j = k * 32 + lane;
-                if (j < rows * DIM) o[j] = s1[j];
-              }
-            }
+            for (int k = 0; k < DIM; ++k)
+              if (okD[k]) pD[k * 32] = s1[k * 32 + lane];
             if constexpr (ORDER >= 2) {
-              if (wh) {
-                double* o = out.d2N + (pt * nb + ib) * NH;
 #pragma unroll
-                for (int k = 0; k < NH; ++k) {
-                  const int j = k * 32 + lane;
-                  if (j < rows * NH) o[j] = s2[j];
-                }
-              }
+              for (int k = 0; k < NH; ++k)
+                if (okH[k]) pH[k * 32] = s2[k * 32 + lane];
             }
+            bo ^= 1;
+            pD += (size_t)nb * DIM;
+            if constexpr (ORDER >= 2) pH += (size_t)nb * NH;
           }
-          if (++q0 == L.nq1[0]) {
+          pN += nb;
+          wq += NA;
+          p0 += s0;
+          if (++q0 == nq0) {
             q0 = 0;
+            p0 = b0;
             fresh = true;
-            if (++q1 == L.nq1[1]) {
+            p1 += s1q;
+            if (++q1 == nq1b) {
               q1 = 0;
-              ++q2;
+              p1 = b1;
+              p2 += s2q;
             }
           }
         }
