@@ -423,6 +423,22 @@ def main():
                "sample": "%d k-layers of the same patch (%d elements, %d points), same outputs, %.1f s wall" % (
                    c_layers, c_el, c_el * NQ, dt)}
         del r
+        # the path AS SHIPPED: per-point calls that copy the whole patch's weights / coordinates
+        # (nurbsbasis.hh:637-663, nurbspatchgeometry.hh:76-82,163-185), on a 16^3 patch only, labelled as such
+        if kind == "reference":
+            small = PD.thickCylinder(3, (4, 4, 4))
+            Os = RF.RefPatch.create(small.degree, small.knotSpans, small.cp, 3)
+            rng = np.random.default_rng(0)
+            u = rng.random((1 << 15, 3))
+            Os.as_shipped_points(u[:256], nthreads=ncpu)
+            t0 = time.perf_counter()
+            used, _ = Os.as_shipped_points(u, nthreads=ncpu)
+            dt = time.perf_counter() - t0
+            cpu["as_shipped"] = {"value": len(u) / dt, "unit": "points/s", "cores": used,
+                                 "sample": "16^3-element p=3 patch (19^3 control points), %d random points, per point "
+                                           "evaluateFunction + evaluateJacobian + global + jacobianTransposed + "
+                                           "integrationElement exactly as the shipped classes call them (whole-patch "
+                                           "weight / coordinate copies per call); %.2f s wall" % (len(u), dt)}
 
     # ---- second half of BASELINE.json's metric: element matrices/sec (config C3: p=4 Poisson stiffness, 5^3 Gauss,
     # FP64 tensor-core contraction), each rank assembling its own slab of a 64 x 64 x 64N patch

@@ -565,6 +565,50 @@ void oref_partial(void* h, long npts, const int* elem, const double* xi, const i
   });
 }
 
+// The per-point path AS SHIPPED: what a dune-functions / dune-grid client pays per quadrature point when
+// it calls localBasis.evaluateFunction + evaluateJacobian (nurbsbasis.hh:637-663: extractWeights of the WHOLE patch per
+// call) and the patch geometry's global + jacobianTransposed + integrationElement (nurbspatchgeometry.hh:76-82,163-185:
+// extractControlCoordinates of the whole patch per call).  O(N_cp) copies per point; OpenMP over points.
+// u: [npts][dim] patch coordinates.  acc: a checksum so that nothing is optimised away.  Returns threads used.
+int oref_as_shipped_points(void* h, long npts, const double* u, double* acc, int nthreads) {
+  int used = 1;
+  dispatch(static_cast<PatchBase*>(h), [&](auto* P) {
+    constexpr int dim = std::remove_pointer_t<decltype(P)>::Data::patchDim;
+    constexpr int dw  = std::remove_pointer_t<decltype(P)>::Data::dimworld;
+    const auto& D     = *P->data;
+    double total      = 0.0;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel reduction(+ : total)
+#endif
+    {
+#ifdef _OPENMP
+#pragma omp single
+      used = omp_get_num_threads();
+#pragma omp for schedule(static)
+#endif
+      for (long k = 0; k < npts; ++k) {
+        FieldVector<double, dim> uu;
+        for (int d = 0; d < dim; ++d) uu[d] = u[k * dim + d];
+        const auto span = findSpanCorrected(D.degree, uu, D.knotSpans);
+        const auto N    = Nurbs<dim>::basisFunctions(uu, D.knotSpans, D.degree, extractWeights(D.controlPoints), span);
+        const auto dN   = Nurbs<dim>::basisFunctionDerivatives(uu, D.knotSpans, D.degree,
+                                                               extractWeights(D.controlPoints), 1, false, span);
+        NURBSPatchGeometry<dim, dw> geo(P->data);
+        const auto x  = geo.global(uu);
+        const auto J  = geo.jacobianTransposed(uu);
+        const double dj = geo.integrationElement(uu);
+        std::array<int, dim> e0{};
+        e0[0] = 1;
+        total += N.directGet(0) + dN.get(e0).directGet(0) + x[0] + J[0][0] + dj;
+      }
+    }
+    if (acc) *acc = total;
+    return 0;
+  });
+  return used;
+}
+
 int oref_max_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

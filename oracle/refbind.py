@@ -62,6 +62,9 @@ def lib():
         L.oref_eval_points.argtypes = [C.c_void_p, C.c_long, ip, dp, C.c_int] + [dp] * 7 + [C.c_int]
         L.oref_partial.argtypes = [C.c_void_p, C.c_long, ip, dp, ip, dp]
         L.oref_max_threads.restype = C.c_int
+        if hasattr(L, "oref_as_shipped_points"):
+            L.oref_as_shipped_points.restype = C.c_int
+            L.oref_as_shipped_points.argtypes = [C.c_void_p, C.c_long, dp, dp, C.c_int]
         _lib = L
     return _lib
 
@@ -212,6 +215,15 @@ class RefPatch:
                                       _d(out["detJ"]), nthreads)
         out["threads"] = used
         return out
+
+    def as_shipped_points(self, u, nthreads=0):
+        """The per-point path as shipped (whole-patch extractWeights / extractControlCoordinates per call):
+        evaluateFunction + evaluateJacobian + patch geometry global / jacobianTransposed / integrationElement at the
+        patch coordinates u [npts][dim].  Returns (threads used, checksum).  Timing baseline only."""
+        u = _f64(u).reshape(-1, self.dim)
+        acc = np.zeros(1)
+        used = lib().oref_as_shipped_points(self.h, len(u), _d(u), _d(acc), nthreads)
+        return used, float(acc[0])
 
     def eval_points(self, elem, xi, order=1, want=("N", "dN", "d2N", "x", "Jt", "H", "detJ"), nthreads=0):
         elem = _i32(elem)
