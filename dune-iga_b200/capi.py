@@ -360,7 +360,9 @@ class Patch:
             elem_end = self.nelem
         fa, fs = _ptr(fe)
         if b is None:
-            nrows = self.ndof_untrimmed * ncomp
+            nr = C.c_int64()  # rows of the global system: compacted DOFs on a trimmed patch
+            _check(lib().igab_csr_pattern(self.h, ncomp, C.byref(nr), None, None, None, HOST, None))
+            nrows = nr.value
             if fs == HOST:
                 b = np.zeros(nrows)
             else:

@@ -6,6 +6,11 @@
 // [max(0, g_d - p_d), min(n_d - 1, g_d + p_d)]: row length and the position of a column inside the row are closed-form.
 // One warp per row, lanes over the row's non-zeros; every non-zero gathers the contributions Ke[e][i][j] of the (at
 // most prod (p_d + 1)) elements whose local bases contain both DOFs, in a fixed order -- no atomics.
+//
+// Trimmed patches (NurbsPreBasis::prepareForTrim, nurbsbasis.hh:599-615): rows and columns are the compacted DOFs (those
+// touched by a non-empty element, renumbered ascending); a row keeps exactly the columns that share a non-empty element
+// with it, which is the pattern the scatter loop of poisson.py would produce.  Row pointer and column indices are built
+// once per handle (thread per row) and cached on the device; gather, load vector and Dirichlet rows read them.
 #include "igab_internal.cuh"
 
 namespace igab {
@@ -17,9 +22,41 @@ struct CsrGeom {
   int p[kMaxDim], n[kMaxDim], nel[kMaxDim];
   const int* elemOfFirst[kMaxDim];  // first-DOF index f_d -> element e_d (or -1): inverse of span - degree
   int nb;
+  // trimmed patches only (nullptr otherwise)
+  const uint8_t* trim;    // element flags
+  const int32_t* map;     // original scalar DOF -> compacted (or -1)
+  const int32_t* inv;     // compacted scalar DOF -> original
+  const int32_t* colidx;  // cached column indices of the compacted pattern
 };
 
-__device__ __forceinline__ void row_box(const CsrGeom& G, long long g, int* gd, int* lo, int* len) {
+__device__ __forceinline__ void dof_box(const CsrGeom& G, long long g, int* gd, int* lo, int* len);
+
+// element (e0, e1, e2) of the first-DOF triple, -1 if there is none or (trimmed patches) it is empty
+__device__ __forceinline__ long long live_element(const CsrGeom& G, int f0, int f1, int f2) {
+  const int e0 = G.elemOfFirst[0][f0];
+  const int e1 = G.dim > 1 ? G.elemOfFirst[1][f1] : 0;
+  const int e2 = G.dim > 2 ? G.elemOfFirst[2][f2] : 0;
+  if (e0 < 0 || e1 < 0 || e2 < 0) return -1;
+  const long long e = e0 + (long long)G.nel[0] * (e1 + (long long)(G.dim > 1 ? G.nel[1] : 1) * e2);
+  if (G.trim && G.trim[e] == IGAB_TRIM_EMPTY) return -1;
+  return e;
+}
+
+// do the DOFs g and h share a live element?
+__device__ __forceinline__ bool coupled(const CsrGeom& G, const int* gd, const int* hd) {
+  int fa[kMaxDim], fb[kMaxDim];
+  for (int q = 0; q < kMaxDim; ++q) {
+    fa[q] = q < G.dim ? max(max(gd[q], hd[q]) - G.p[q], 0) : 0;
+    fb[q] = q < G.dim ? min(min(gd[q], hd[q]), G.n[q] - 1 - G.p[q]) : 0;
+  }
+  for (int f2 = fa[2]; f2 <= fb[2]; ++f2)
+    for (int f1 = fa[1]; f1 <= fb[1]; ++f1)
+      for (int f0 = fa[0]; f0 <= fb[0]; ++f0)
+        if (live_element(G, f0, f1, f2) >= 0) return true;
+  return false;
+}
+
+__device__ __forceinline__ void dof_box(const CsrGeom& G, long long g, int* gd, int* lo, int* len) {
   for (int d = 0; d < G.dim; ++d) {
     gd[d] = (int)(g % G.n[d]);
     g /= G.n[d];
@@ -28,6 +65,50 @@ __device__ __forceinline__ void row_box(const CsrGeom& G, long long g, int* gd, 
     len[d] = hi - lo[d] + 1;
   }
   for (int d = G.dim; d < kMaxDim; ++d) { gd[d] = 0; lo[d] = 0; len[d] = 1; }
+}
+
+// scalar DOF index in the matrix numbering (compacted for trimmed patches) -> box of the original DOF
+__device__ __forceinline__ void row_box(const CsrGeom& G, long long r, int* gd, int* lo, int* len) {
+  dof_box(G, G.inv ? (long long)G.inv[r] : r, gd, lo, len);
+}
+
+// trimmed patches: row lengths and column indices of the compacted pattern, one thread per compacted scalar DOF
+__global__ void csr_rowlen_trim_kernel(CsrGeom G, long long ndofc, long long* __restrict__ rowlen) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= ndofc) return;
+  int gd[kMaxDim], lo[kMaxDim], len[kMaxDim], hd[kMaxDim];
+  row_box(G, r, gd, lo, len);
+  long long cnt = 0;
+  for (int k2 = 0; k2 < len[2]; ++k2)
+    for (int k1 = 0; k1 < len[1]; ++k1)
+      for (int k0 = 0; k0 < len[0]; ++k0) {
+        hd[0] = lo[0] + k0; hd[1] = lo[1] + k1; hd[2] = lo[2] + k2;
+        cnt += coupled(G, gd, hd) ? 1 : 0;
+      }
+  for (int c = 0; c < G.ncomp; ++c) rowlen[r * G.ncomp + c] = cnt * G.ncomp;
+}
+__global__ void csr_colidx_trim_kernel(CsrGeom G, long long ndofc, const long long* __restrict__ rowptr,
+                                       int32_t* __restrict__ colidx) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= ndofc) return;
+  int gd[kMaxDim], lo[kMaxDim], len[kMaxDim], hd[kMaxDim];
+  row_box(G, r, gd, lo, len);
+  long long cnt = 0;
+  for (int k2 = 0; k2 < len[2]; ++k2)
+    for (int k1 = 0; k1 < len[1]; ++k1)
+      for (int k0 = 0; k0 < len[0]; ++k0) {
+        hd[0] = lo[0] + k0; hd[1] = lo[1] + k1; hd[2] = lo[2] + k2;
+        if (!coupled(G, gd, hd)) continue;
+        const long long h = hd[0] + (long long)G.n[0] * (hd[1] + (long long)(G.dim > 1 ? G.n[1] : 1) * hd[2]);
+        const long long hc = G.map[h];  // >= 0: h shares a live element with g
+        for (int c = 0; c < G.ncomp; ++c)
+          for (int d = 0; d < G.ncomp; ++d) colidx[rowptr[r * G.ncomp + c] + cnt * G.ncomp + d] = (int32_t)(hc * G.ncomp + d);
+        ++cnt;
+      }
+}
+__global__ void dof_inverse_kernel(long long n, const int32_t* __restrict__ map, int32_t* __restrict__ inv) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n && map[g] >= 0) inv[map[g]] = (int32_t)g;
 }
 
 // row lengths (one thread per scalar DOF); the host turns them into rowptr with a prefix sum
@@ -71,17 +152,27 @@ __global__ void csr_gather_kernel(CsrGeom G, long long nrows, long long elem_beg
   row_box(G, row / G.ncomp, gd, lo, len);
   const int c = (int)(row % G.ncomp);
   const long long base = rowptr[row];
-  const int nn = len[0] * len[1] * len[2] * G.ncomp;
+  const int nn = (int)(rowptr[row + 1] - base);
   const long long n = (long long)G.nb * G.ncomp;
   const int o0 = G.p[0] + 1, o1 = G.dim > 1 ? G.p[1] + 1 : 1;
   for (int k = lane; k < nn; k += 32) {
-    const int d = k % G.ncomp;
-    int kk = k / G.ncomp;
-    int hd[kMaxDim];
-    hd[0] = lo[0] + kk % len[0];
-    kk /= len[0];
-    hd[1] = lo[1] + kk % len[1];
-    hd[2] = lo[2] + kk / len[1];
+    int d, hd[kMaxDim];
+    if (G.colidx) {  // trimmed: the cached compacted column -> original DOF
+      const int col = G.colidx[base + k];
+      d = col % G.ncomp;
+      long long h = G.inv[col / G.ncomp];
+      hd[0] = (int)(h % G.n[0]);
+      h /= G.n[0];
+      hd[1] = G.dim > 1 ? (int)(h % G.n[1]) : 0;
+      hd[2] = G.dim > 1 ? (int)(h / G.n[1]) : 0;
+    } else {
+      d = k % G.ncomp;
+      int kk = k / G.ncomp;
+      hd[0] = lo[0] + kk % len[0];
+      kk /= len[0];
+      hd[1] = lo[1] + kk % len[1];
+      hd[2] = lo[2] + kk / len[1];
+    }
     int fa[kMaxDim], fb[kMaxDim];  // range of first-DOF indices of the elements that contain both g and h
     for (int q = 0; q < kMaxDim; ++q) {
       if (q < G.dim) {
@@ -92,23 +183,15 @@ __global__ void csr_gather_kernel(CsrGeom G, long long nrows, long long elem_beg
       }
     }
     double acc = 0.0;
-    for (int f2 = fa[2]; f2 <= fb[2]; ++f2) {
-      const int e2 = G.dim > 2 ? G.elemOfFirst[2][f2] : 0;
-      if (e2 < 0) continue;
-      for (int f1 = fa[1]; f1 <= fb[1]; ++f1) {
-        const int e1 = G.dim > 1 ? G.elemOfFirst[1][f1] : 0;
-        if (e1 < 0) continue;
+    for (int f2 = fa[2]; f2 <= fb[2]; ++f2)
+      for (int f1 = fa[1]; f1 <= fb[1]; ++f1)
         for (int f0 = fa[0]; f0 <= fb[0]; ++f0) {
-          const int e0 = G.elemOfFirst[0][f0];
-          if (e0 < 0) continue;
-          const long long e = e0 + (long long)G.nel[0] * (e1 + (long long)(G.dim > 1 ? G.nel[1] : 1) * e2);
+          const long long e = live_element(G, f0, f1, f2);
           if (e < elem_begin || e >= elem_end) continue;
           const int i = (gd[0] - f0) + o0 * ((gd[1] - f1) + o1 * (gd[2] - f2));
           const int j = (hd[0] - f0) + o0 * ((hd[1] - f1) + o1 * (hd[2] - f2));
           acc += Ke[(e - elem_begin) * n * n + (long long)(i * G.ncomp + c) * n + (j * G.ncomp + d)];
         }
-      }
-    }
     if (accumulate)
       values[base + k] += acc;
     else
@@ -133,22 +216,14 @@ __global__ void rhs_gather_kernel(CsrGeom G, long long nrows, long long elem_beg
     fb[q] = q < G.dim ? min(gd[q], G.n[q] - 1 - G.p[q]) : 0;
   }
   double acc = 0.0;
-  for (int f2 = fa[2]; f2 <= fb[2]; ++f2) {
-    const int e2 = G.dim > 2 ? G.elemOfFirst[2][f2] : 0;
-    if (e2 < 0) continue;
-    for (int f1 = fa[1]; f1 <= fb[1]; ++f1) {
-      const int e1 = G.dim > 1 ? G.elemOfFirst[1][f1] : 0;
-      if (e1 < 0) continue;
+  for (int f2 = fa[2]; f2 <= fb[2]; ++f2)
+    for (int f1 = fa[1]; f1 <= fb[1]; ++f1)
       for (int f0 = fa[0]; f0 <= fb[0]; ++f0) {
-        const int e0 = G.elemOfFirst[0][f0];
-        if (e0 < 0) continue;
-        const long long e = e0 + (long long)G.nel[0] * (e1 + (long long)(G.dim > 1 ? G.nel[1] : 1) * e2);
+        const long long e = live_element(G, f0, f1, f2);
         if (e < elem_begin || e >= elem_end) continue;
         const int i = (gd[0] - f0) + o0 * ((gd[1] - f1) + o1 * (gd[2] - f2));
         acc += fe[(e - elem_begin) * n + i * G.ncomp + c];
       }
-    }
-  }
   b[row] = accumulate ? b[row] + acc : acc;
 }
 
@@ -163,16 +238,21 @@ __global__ void dirichlet_rows_kernel(CsrGeom G, long long nrows, const long lon
   int gd[kMaxDim], lo[kMaxDim], len[kMaxDim];
   row_box(G, row / G.ncomp, gd, lo, len);
   const long long base = rowptr[row];
-  const int nn = len[0] * len[1] * len[2] * G.ncomp;
+  const int nn = (int)(rowptr[row + 1] - base);
   for (int k = lane; k < nn; k += 32) {
-    const int d = k % G.ncomp;
-    int kk = k / G.ncomp;
-    const int c0 = lo[0] + kk % len[0];
-    kk /= len[0];
-    const int c1 = lo[1] + kk % len[1];
-    const int c2 = lo[2] + kk / len[1];
-    const long long h = c0 + (long long)G.n[0] * (c1 + (long long)(G.dim > 1 ? G.n[1] : 1) * c2);
-    values[base + k] = (h * G.ncomp + d == row) ? 1.0 : 0.0;
+    long long col;
+    if (G.colidx) {
+      col = G.colidx[base + k];
+    } else {
+      const int d = k % G.ncomp;
+      int kk = k / G.ncomp;
+      const int c0 = lo[0] + kk % len[0];
+      kk /= len[0];
+      const int c1 = lo[1] + kk % len[1];
+      const int c2 = lo[2] + kk / len[1];
+      col = (c0 + (long long)G.n[0] * (c1 + (long long)(G.dim > 1 ? G.n[1] : 1) * c2)) * G.ncomp + d;
+    }
+    values[base + k] = (col == row) ? 1.0 : 0.0;
   }
   if (lane == 0 && b) b[row] = gval ? gval[row] : 0.0;
 }
@@ -182,11 +262,42 @@ igab_status make_geom(igab_patch* p, int ncomp, CsrGeom* G) {
     set_error("csr: ncomp must be 1..3");
     return IGAB_INVALID_ARGUMENT;
   }
-  if (p->d_trim) {
-    set_error("csr: trimmed patches (compacted DOF numbering) are not supported yet");
-    return IGAB_UNSUPPORTED;
-  }
   const PatchDev& D = p->dev;
+  if (p->d_trim && !p->d_dofc_map) {
+    // compacted numbering (prepareForTrim): the same mark / scan kernels as igab_patch_dofmap, kept in the handle
+    const long long n = D.nelem * D.nb, nd = p->ndof_untrimmed;
+    int32_t *dof = nullptr, *used = nullptr, *map = nullptr, *inv = nullptr;
+    long long* total_dev = nullptr;
+    long long total = 0;
+    cudaError_t e = cudaMalloc(&dof, sizeof(int32_t) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&used, sizeof(int32_t) * nd);
+    if (e == cudaSuccess) e = cudaMalloc(&map, sizeof(int32_t) * nd);
+    if (e == cudaSuccess) e = cudaMalloc(&total_dev, sizeof(long long));
+    igab_status st = e == cudaSuccess ? IGAB_OK : cuda_fail(e, "csr: compacted DOF scratch");
+    if (!st) st = launch_dofmap(D, dof, nullptr);
+    if (!st) st = launch_dof_compact(D, p->d_trim, dof, used, map, nd, total_dev, nullptr);
+    if (!st) {
+      e = cudaMemcpy(&total, total_dev, sizeof(long long), cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMalloc(&inv, sizeof(int32_t) * std::max(1LL, total));
+      if (e == cudaSuccess) {
+        dof_inverse_kernel<<<(unsigned)((nd + 255) / 256), 256>>>(nd, map, inv);
+        count_launch();
+        e = cudaDeviceSynchronize();
+      }
+      if (e != cudaSuccess) st = cuda_fail(e, "csr: compacted DOF numbering");
+    }
+    if (dof) cudaFree(dof);
+    if (used) cudaFree(used);
+    if (total_dev) cudaFree(total_dev);
+    if (st) {
+      if (map) cudaFree(map);
+      if (inv) cudaFree(inv);
+      return st;
+    }
+    p->d_dofc_map = map;
+    p->d_dofc_inv = inv;
+    p->ndof_compact = total;
+  }
   for (int d = 0; d < D.dim; ++d) {
     if (!p->d_elem_of_first[d]) {
       const int nf = D.ncp[d] - D.degree[d];  // possible first-DOF indices 0 .. n_d - p_d - 1
@@ -205,6 +316,10 @@ igab_status make_geom(igab_patch* p, int ncomp, CsrGeom* G) {
     G->nel[d] = d < D.dim ? D.nel[d] : 1;
     G->elemOfFirst[d] = d < D.dim ? p->d_elem_of_first[d] : nullptr;
   }
+  G->trim = p->d_trim;
+  G->map = p->d_dofc_map;
+  G->inv = p->d_dofc_inv;
+  G->colidx = p->d_csr_colidx;
   return IGAB_OK;
 }
 
@@ -215,12 +330,15 @@ igab_status csr_pattern(igab_patch* p, int ncomp, int64_t* nrows_out, int64_t* n
   CsrGeom G;
   igab_status st = make_geom(p, ncomp, &G);
   if (st) return st;
-  const long long ndof = p->ndof_untrimmed, nrows = ndof * ncomp;
-  // row pointer: closed-form row lengths, host prefix sum (cached in the handle)
+  const long long ndof = p->d_trim ? p->ndof_compact : p->ndof_untrimmed, nrows = ndof * ncomp;
+  // row pointer: row lengths (closed form, or counted per row on trimmed patches), host prefix sum (cached in the handle)
   if ((long long)p->csr_rowptr_host.size() != nrows + 1 || p->csr_ncomp != ncomp) {
     long long* d_len = nullptr;
-    IGAB_CUDA_TRY(cudaMalloc(&d_len, sizeof(long long) * nrows));
-    csr_rowlen_kernel<<<(unsigned)((ndof + 255) / 256), 256, 0, stream>>>(G, ndof, d_len);
+    IGAB_CUDA_TRY(cudaMalloc(&d_len, sizeof(long long) * std::max(1LL, nrows)));
+    if (p->d_trim)
+      csr_rowlen_trim_kernel<<<(unsigned)((ndof + 127) / 128), 128, 0, stream>>>(G, ndof, d_len);
+    else
+      csr_rowlen_kernel<<<(unsigned)((ndof + 255) / 256), 256, 0, stream>>>(G, ndof, d_len);
     count_launch();
     std::vector<long long> len(nrows);
     cudaError_t e = cudaMemcpyAsync(len.data(), d_len, sizeof(long long) * nrows, cudaMemcpyDeviceToHost, stream);
@@ -232,8 +350,18 @@ igab_status csr_pattern(igab_patch* p, int ncomp, int64_t* nrows_out, int64_t* n
     p->csr_ncomp = ncomp;
     if (p->d_csr_rowptr) cudaFree(p->d_csr_rowptr);
     p->d_csr_rowptr = nullptr;
+    if (p->d_csr_colidx) cudaFree(p->d_csr_colidx);
+    p->d_csr_colidx = nullptr;
+    G.colidx = nullptr;
     IGAB_CUDA_TRY(cudaMalloc(&p->d_csr_rowptr, sizeof(long long) * (nrows + 1)));
     IGAB_CUDA_TRY(cudaMemcpy(p->d_csr_rowptr, p->csr_rowptr_host.data(), sizeof(long long) * (nrows + 1), cudaMemcpyHostToDevice));
+    if (p->d_trim) {  // the compacted pattern has no closed form: build its column indices once and keep them
+      const long long nz = p->csr_rowptr_host[nrows];
+      IGAB_CUDA_TRY(cudaMalloc(&p->d_csr_colidx, sizeof(int32_t) * std::max(1LL, nz)));
+      csr_colidx_trim_kernel<<<(unsigned)((ndof + 127) / 128), 128, 0, stream>>>(G, ndof, p->d_csr_rowptr, p->d_csr_colidx);
+      count_launch();
+      IGAB_CUDA_TRY(cudaGetLastError());
+    }
   }
   const long long nnz = p->csr_rowptr_host[nrows];
   if (nrows_out) *nrows_out = nrows;
@@ -251,10 +379,15 @@ igab_status csr_pattern(igab_patch* p, int ncomp, int64_t* nrows_out, int64_t* n
   if (colidx) {
     int32_t* d_col = colidx;
     if (space == IGAB_HOST) IGAB_CUDA_TRY(cudaMalloc(&d_col, sizeof(int32_t) * nnz));
-    const long long threads = nrows * 32;
-    csr_colidx_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(G, nrows, p->d_csr_rowptr, d_col);
-    count_launch();
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = cudaSuccess;
+    if (p->d_trim) {
+      e = cudaMemcpyAsync(d_col, p->d_csr_colidx, sizeof(int32_t) * nnz, cudaMemcpyDeviceToDevice, stream);
+    } else {
+      const long long threads = nrows * 32;
+      csr_colidx_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(G, nrows, p->d_csr_rowptr, d_col);
+      count_launch();
+      e = cudaGetLastError();
+    }
     if (e == cudaSuccess && space == IGAB_HOST) {
       e = cudaMemcpyAsync(colidx, d_col, sizeof(int32_t) * nnz, cudaMemcpyDeviceToHost, stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
@@ -272,6 +405,7 @@ igab_status csr_assemble(igab_patch* p, int ncomp, long long eb, long long ee, c
   if (st) return st;
   int64_t nrows = 0, nnz = 0;
   if ((st = csr_pattern(p, ncomp, &nrows, &nnz, nullptr, nullptr, IGAB_HOST, stream))) return st;
+  G.colidx = p->d_csr_colidx;
   (void)rowptr;  // the handle's own copy is used; the argument documents which pattern `values` belongs to
   const long long n = (long long)p->dev.nb * ncomp, nel = ee - eb;
   const double* dK = Ke;
@@ -308,7 +442,8 @@ igab_status rhs_assemble(igab_patch* p, int ncomp, long long eb, long long ee, c
   CsrGeom G;
   igab_status st = make_geom(p, ncomp, &G);
   if (st) return st;
-  const long long nrows = p->ndof_untrimmed * ncomp, n = (long long)p->dev.nb * ncomp, nel = ee - eb;
+  const long long nrows = (p->d_trim ? p->ndof_compact : p->ndof_untrimmed) * ncomp, n = (long long)p->dev.nb * ncomp,
+                  nel = ee - eb;
   const double* dF = fe;
   double* dB = b;
   double* tmp = nullptr;
@@ -342,6 +477,7 @@ igab_status csr_dirichlet(igab_patch* p, int ncomp, const uint8_t* mask, const d
   if (st) return st;
   int64_t nrows = 0, nnz = 0;
   if ((st = csr_pattern(p, ncomp, &nrows, &nnz, nullptr, nullptr, IGAB_HOST, stream))) return st;
+  G.colidx = p->d_csr_colidx;
   const uint8_t* dM = mask;
   const double* dG = gval;
   double *dV = values, *dB = b;

@@ -442,6 +442,9 @@ void igab_patch_destroy(igab_patch* p) {
   for (int d = 0; d < kMaxDim; ++d)
     if (p->d_elem_of_first[d]) cudaFree(p->d_elem_of_first[d]);
   if (p->d_csr_rowptr) cudaFree(p->d_csr_rowptr);
+  if (p->d_csr_colidx) cudaFree(p->d_csr_colidx);
+  if (p->d_dofc_map) cudaFree(p->d_dofc_map);
+  if (p->d_dofc_inv) cudaFree(p->d_dofc_inv);
   free_sf_workspace(p->sf);
   delete p;
 }

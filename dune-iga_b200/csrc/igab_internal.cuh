@@ -199,6 +199,11 @@ struct igab_patch {
   std::vector<long long> csr_rowptr_host;
   long long* d_csr_rowptr = nullptr;
   int csr_ncomp = 0;
+  // trimmed patches: compacted DOF numbering (prepareForTrim) and the cached column indices of its pattern
+  int32_t* d_dofc_map = nullptr;   // original scalar DOF -> compacted (-1: untouched)
+  int32_t* d_dofc_inv = nullptr;   // compacted -> original
+  long long ndof_compact = 0;
+  int32_t* d_csr_colidx = nullptr;
   // reduction scratch
   double* d_red = nullptr;
   int red_cap = 0;

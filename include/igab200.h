@@ -211,8 +211,11 @@ igab_status igab_geometry_local(igab_patch* p, int64_t npts, const int32_t* elem
  * Replaces the scatter loop of globalAssembler, dune/python/test/poisson.py:113-125 (A[gi,gj] += localA[i,j] through
  * localView.index), for the tensor-product DOF numbering of NurbsPreBasis (nurbsbasis.hh:572-584): row g couples
  * with the DOFs within +-degree in every direction.  ncomp > 1: vector-valued basis, flat-interleaved numbering
- * g*ncomp + c (dune-functions PowerPreBasis, python/dune/iga/basis/__init__.py:53-67).  Untrimmed patches only
- * (IGAB_UNSUPPORTED when trim flags were given).
+ * g*ncomp + c (dune-functions PowerPreBasis, python/dune/iga/basis/__init__.py:53-67).  Patches created with trim
+ * flags use the compacted numbering of prepareForTrim (nurbsbasis.hh:599-615, the one igab_patch_dofmap returns):
+ * rows / columns are the DOFs touched by a non-empty element, a row keeps exactly the columns that share a non-empty
+ * element with it (the pattern the scatter loop produces), IGAB_TRIM_EMPTY elements of Ke / fe are never read, and
+ * the caller puts the matrices of IGAB_TRIM_TRIMMED elements (igab_assemble_points) into their slots of Ke.
  *   igab_csr_pattern : *nrows = ndof*ncomp, *nnz; rowptr[nrows+1] (int64) and colidx[nnz] (int32) may be NULL to
  *                      query the sizes first.  Columns ascending within a row.
  *   igab_csr_assemble: values[nnz] (+)= sum over the elements [elem_begin, elem_end) of Ke[e - elem_begin][i][j];

@@ -1189,3 +1189,67 @@ def test_trimmed_patch_poisson_end_to_end():
     area = (det[flags == 0] * np.outer(wg, wg).reshape(-1)).sum() + \
         (P.evalPoints(elem_pt, xi, order=1, want=("detJ",))["detJ"] * w).sum()
     assert abs(b.sum() - area) <= 1e-13
+    # the same system through the device-side global assembler (compacted CSR pattern, gather, load vector, Dirichlet
+    # rows): element matrices of the trimmed elements replace the tensor-rule ones, empty elements are never read
+    Kall, fall = Kfull.copy(), ffull.copy()
+    Kall[trimmed], fall[trimmed] = Ktrim, ftrim
+    Kall[flags == 1], fall[flags == 1] = np.nan, np.nan
+    rowptr, colidx = P.csrPattern()
+    A.sort_indices()
+    assert len(rowptr) == ndof + 1 and rowptr[-1] == A.nnz == len(colidx)
+    assert np.array_equal(rowptr, A.indptr) and np.array_equal(colidx, A.indices)        # exactly the scatter's pattern
+    vals = P.csrAssemble(Kall)
+    Ad = sp.csr_matrix((vals, colidx, rowptr), shape=(ndof, ndof))
+    assert abs(Ad - Ar).max() <= 1e-12 * abs(Ar).max()
+    bd = P.rhsAssemble(fall)
+    assert bd.shape == (ndof,) and np.abs(bd - br).max() <= 1e-12 * np.abs(br).max()
+    # two element ranges accumulated give the same matrix
+    v2 = P.csrAssemble(Kall[:7], elem_end=7)
+    v2 = P.csrAssemble(Kall[7:], elem_begin=7, values=v2, accumulate=True)
+    assert np.abs(v2 - vals).max() <= 1e-14 * np.abs(vals).max()
+    # Dirichlet rows on the compacted numbering
+    mask = np.zeros(ndof, np.uint8)
+    mask[[0, ndof - 1]] = 1
+    gD = np.full(ndof, 2.5)
+    vD, bD = P.csrDirichlet(mask, vals.copy(), b=bd.copy(), g=gD)
+    AD = sp.csr_matrix((vD, colidx, rowptr), shape=(ndof, ndof)).toarray()
+    for r in (0, ndof - 1):
+        e = np.zeros(ndof); e[r] = 1.0
+        assert np.array_equal(AD[r], e) and bD[r] == 2.5
+    keep = np.setdiff1d(np.arange(ndof), [0, ndof - 1])
+    assert np.array_equal(AD[keep], Ad.toarray()[keep]) and np.array_equal(bD[keep], bd[keep])
+
+
+def test_trimmed_csr_pattern_random_flags_3d_and_vector_valued():
+    """Compacted CSR of patches with random empty elements (2-D with two components, 3-D scalar; repeated knots):
+    pattern and values equal the COO scatter through the compacted DOF map, bit for bit in the pattern."""
+    import scipy.sparse as sp
+    for dim, dw, degree, ncomp, seed in ((2, 2, (2, 3), 2, 5), (3, 3, (2, 1, 2), 1, 6)):
+        rng = np.random.default_rng(seed)
+        spec = _random_patch(rng, dim, dw, degree)
+        Pp = port_for(spec)
+        nel = Pp.nelem
+        flags = rng.choice([0, 1, 2], nel, p=[0.5, 0.35, 0.15]).astype(np.uint8)
+        P = gpu_patch(spec, trimflags=flags)
+        dof, ndof = P.dofmap()
+        n = P.nb * ncomp
+        Ke = rng.normal(size=(nel, n, n))
+        fe = rng.normal(size=(nel, n))
+        rows, cols, vals = [], [], []
+        b = np.zeros(ndof * ncomp)
+        for e in range(nel):
+            if flags[e] == 1:
+                continue
+            gd = (dof[e][:, None] * ncomp + np.arange(ncomp)[None, :]).reshape(-1)   # flat-interleaved power basis
+            rows.append(np.repeat(gd, n)); cols.append(np.tile(gd, n)); vals.append(Ke[e].reshape(-1))
+            np.add.at(b, gd, fe[e])
+        A = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
+                          shape=(ndof * ncomp,) * 2).tocsr()
+        A.sort_indices()
+        Ke[flags == 1] = np.nan
+        fe[flags == 1] = np.nan
+        rowptr, colidx = P.csrPattern(ncomp)
+        assert np.array_equal(rowptr, A.indptr) and np.array_equal(colidx, A.indices)
+        v = P.csrAssemble(Ke, ncomp)
+        assert np.abs(v - A.data).max() <= 1e-13 * np.abs(A.data).max()
+        assert np.abs(P.rhsAssemble(fe, ncomp) - b).max() <= 1e-13 * np.abs(b).max()
