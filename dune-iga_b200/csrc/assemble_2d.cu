@@ -330,8 +330,9 @@ __global__ void __launch_bounds__(128) assemble2d_points_kernel(PatchDev Pd, lon
       if (lane < np) {
         const long long pt = c0 + lane;
         double n0[2][NB1], n1[2][NB1];
-        ders1d_reg<P, 1>(xi[pt * 2] * sc0 + lo0, U0, s0, sc0, n0);
-        ders1d_reg<P, 1>(xi[pt * 2 + 1] * sc1 + lo1, U1, s1, sc1, n1);
+        constexpr int TRI = P * (P + 1) / 2;
+        ders1d_reg_rd<P, 1>(xi[pt * 2] * sc0 + lo0, U0, s0, sc0, Pd.rden[0] + (size_t)e0 * TRI, n0);
+        ders1d_reg_rd<P, 1>(xi[pt * 2 + 1] * sc1 + lo1, U1, s1, sc1, Pd.rden[1] + (size_t)e1 * TRI, n1);
         a2_point<DW, P, KIND>(Pd, cpBase, n0, n1, wq[pt], fconst, sG + (size_t)lane * PG, fe ? sR + (size_t)lane * PR : nullptr);
       }
       __syncwarp();

@@ -123,4 +123,74 @@ __device__ __forceinline__ void ders1d_reg(double u, const double* __restrict__ 
   }
 }
 
+// The same A2.3 with the divisions replaced by multiplications: every denominator ndu[j][r] (r < j) is the knot
+// difference U[sp+r+1] - U[sp+1-j+r] of the span, independent of u, so its reciprocal rd[j*(j-1)/2 + r] is tabulated per
+// element of the direction at patch creation (PatchDev::rden).  Differs from the dividing form by <= 1 ulp per quotient.
+template <int P, int K>
+__device__ __forceinline__ void ders1d_reg_rd(double u, const double* __restrict__ U, int sp, double scale,
+                                              const double* __restrict__ rdp, double (&out)[K + 1][P + 1]) {
+  double left[P + 1], right[P + 1], nd[P + 1][P + 1];  // nd[r][j], r <= j: the upper triangle (basis values)
+  constexpr int TRI = P * (P + 1) / 2;
+  double rd[TRI > 0 ? TRI : 1];
+#pragma unroll
+  for (int t = 0; t < TRI; ++t) rd[t] = __ldg(rdp + t);
+  nd[0][0] = 1.0;
+#pragma unroll
+  for (int j = 1; j <= P; ++j) {
+    left[j] = u - U[sp + 1 - j];
+    right[j] = U[sp + j] - u;
+    double saved = 0.0;
+#pragma unroll
+    for (int r = 0; r < j; ++r) {
+      const double temp = nd[r][j - 1] * rd[j * (j - 1) / 2 + r];
+      nd[r][j] = saved + right[r + 1] * temp;
+      saved = left[j - r] * temp;
+    }
+    nd[j][j] = saved;
+  }
+#pragma unroll
+  for (int j = 0; j <= P; ++j) out[0][j] = nd[j][P];
+  if constexpr (K >= 1) {
+#pragma unroll
+    for (int r = 0; r <= P; ++r) {
+      double a[2][P + 1];
+      a[0][0] = 1.0;
+#pragma unroll
+      for (int k = 1; k <= K; ++k) {
+        const int s1 = (k - 1) & 1, s2 = k & 1;
+        double d = 0.0;
+        const int rk = r - k, pk = P - k;
+        if (k <= P) {
+          // 1 / ndu[pk+1][c] = rd[(pk+1) pk / 2 + c]
+          if (r >= k) {
+            a[s2][0] = a[s1][0] * rd[(pk + 1) * pk / 2 + rk];
+            d = a[s2][0] * nd[rk][pk];
+          }
+          const int j1 = (rk >= -1) ? 1 : -rk;
+          const int j2 = (r - 1 <= pk) ? k - 1 : P - r;
+#pragma unroll
+          for (int j = 1; j <= K; ++j)
+            if (j >= j1 && j <= j2) {
+              a[s2][j] = (a[s1][j] - a[s1][j - 1]) * rd[(pk + 1) * pk / 2 + rk + j];
+              d += a[s2][j] * nd[rk + j][pk];
+            }
+          if (r <= pk) {
+            a[s2][k] = -a[s1][k - 1] * rd[(pk + 1) * pk / 2 + r];
+            d += a[s2][k] * nd[r][pk];
+          }
+        }
+        out[k][r] = d;
+      }
+    }
+    double fac = P, sc = scale;
+#pragma unroll
+    for (int k = 1; k <= K; ++k) {
+#pragma unroll
+      for (int j = 0; j <= P; ++j) out[k][j] *= fac * sc;
+      fac *= (P - k);
+      sc *= scale;
+    }
+  }
+}
+
 }  // namespace igab

@@ -110,7 +110,7 @@ __device__ __forceinline__ void flush_field(double* __restrict__ slab, const dou
 }
 
 // LIST = false: tensor rule, univariate rows from the K1 tables.  LIST = true: arbitrary element-local points (trimmed
-// batches, utils/fillquadraturerule.hh:8-19): rows computed per point with ders1d_reg.
+// batches, utils/fillquadraturerule.hh:8-19): rows computed per point with ders1d_reg_rd (A2.3 in registers, tabulated reciprocals).
 template <int DW, int P, int Q, int ORDER, bool LIST>
 __global__ void __launch_bounds__(128, (ORDER >= 2 ? 3 : 4)) eval_2d_kernel(PatchDev Pd, long long elem_begin, long long npts,
                                                       const double* __restrict__ tab0, const double* __restrict__ tab1,
@@ -137,8 +137,9 @@ __global__ void __launch_bounds__(128, (ORDER >= 2 ? 3 : 4)) eval_2d_kernel(Patc
     const double* U0 = Pd.knots[0];
     const double* U1 = Pd.knots[1];
     const double lo0 = U0[s0], sc0 = U0[s0 + 1] - lo0, lo1 = U1[s1], sc1 = U1[s1 + 1] - lo1;
-    ders1d_reg<P, ORDER>(xiList[ptc * 2] * sc0 + lo0, U0, s0, sc0, n0);
-    ders1d_reg<P, ORDER>(xiList[ptc * 2 + 1] * sc1 + lo1, U1, s1, sc1, n1);
+    constexpr int TRI = P * (P + 1) / 2 > 0 ? P * (P + 1) / 2 : 1;
+    ders1d_reg_rd<P, ORDER>(xiList[ptc * 2] * sc0 + lo0, U0, s0, sc0, Pd.rden[0] + (size_t)e0 * TRI, n0);
+    ders1d_reg_rd<P, ORDER>(xiList[ptc * 2 + 1] * sc1 + lo1, U1, s1, sc1, Pd.rden[1] + (size_t)e1 * TRI, n1);
   } else {
     const int q = (int)(ptc % (NQ > 0 ? NQ : 1)), q0 = q % (Q > 0 ? Q : 1), q1 = q / (Q > 0 ? Q : 1);
     const double* t0 = tab0 + ((size_t)e0 * Q + q0) * NB1 * A1;

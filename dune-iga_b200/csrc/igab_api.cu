@@ -408,6 +408,20 @@ igab_status igab_patch_create(int dim, int dimworld, const int* degree, const in
       return fail(e, "copy spans");
     D.knots[d] = p->d_knots[d];
     D.spanTab[d] = p->d_span[d];
+    // every division of A2.3 (bsplinealgorithms.hh:161-213) is by a knot difference U[sp+r+1] - U[sp+1-j+r] of the
+    // point's span: their reciprocals, per element of the direction, row j*(j-1)/2 + r  (j = 1..p, r < j)
+    const int pd = D.degree[d], tri = std::max(1, pd * (pd + 1) / 2);
+    std::vector<double> rd((size_t)D.nel[d] * tri, 0.0);
+    for (int el = 0; el < D.nel[d]; ++el) {
+      const int sp = p->hspan[d][el];
+      for (int j = 1; j <= pd; ++j)
+        for (int r = 0; r < j; ++r)
+          rd[(size_t)el * tri + j * (j - 1) / 2 + r] = 1.0 / (p->hknots[d][sp + r + 1] - p->hknots[d][sp + 1 - j + r]);
+    }
+    if ((e = cudaMalloc(&p->d_rden[d], sizeof(double) * rd.size())) != cudaSuccess) return fail(e, "cudaMalloc rden");
+    if ((e = cudaMemcpy(p->d_rden[d], rd.data(), sizeof(double) * rd.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+      return fail(e, "copy rden");
+    D.rden[d] = p->d_rden[d];
   }
   const size_t cpBytes = sizeof(double) * p->ncp_total * (dimworld + 1);
   if ((e = cudaMalloc(&p->d_cp, cpBytes)) != cudaSuccess) return fail(e, "cudaMalloc control net");
@@ -427,6 +441,7 @@ void igab_patch_destroy(igab_patch* p) {
   for (int d = 0; d < kMaxDim; ++d) {
     if (p->d_knots[d]) cudaFree(p->d_knots[d]);
     if (p->d_span[d]) cudaFree(p->d_span[d]);
+    if (p->d_rden[d]) cudaFree(p->d_rden[d]);
   }
   if (p->d_cp) cudaFree(p->d_cp);
   if (p->d_trim) cudaFree(p->d_trim);

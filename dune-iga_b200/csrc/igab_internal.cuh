@@ -23,6 +23,7 @@ struct PatchDev {
   int nel[kMaxDim];               // elements (non-empty spans) per direction
   const double* knots[kMaxDim];   // device
   const int* spanTab[kMaxDim];    // device: span index of element e_d, bit-exact with findSpanCorrected(p,uq[e],U,e)
+  const double* rden[kMaxDim];    // device [nel_d][p(p+1)/2]: reciprocals of the knot differences A2.3 divides by (per span)
   const double* cp;               // device [prod ncp][dw+1]  (x.., w)
   int nb;                         // prod (degree+1)
   long long nelem;
@@ -179,6 +180,7 @@ struct igab_patch {
   std::vector<uint8_t> htrim;
   double* d_knots[igab::kMaxDim] = {nullptr, nullptr, nullptr};
   int* d_span[igab::kMaxDim] = {nullptr, nullptr, nullptr};
+  double* d_rden[igab::kMaxDim] = {nullptr, nullptr, nullptr};
   double* d_cp = nullptr;
   uint8_t* d_trim = nullptr;
   long long ncp_total = 0;
