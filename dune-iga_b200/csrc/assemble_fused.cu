@@ -15,6 +15,7 @@
 //       accumulators.  K_e is symmetric: only the upper 32x32 blocks are contracted (one warp each) and mirrored
 //       on the way out.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "igab_internal.cuh"
@@ -581,10 +582,279 @@ igab_status launch_elas(const PatchDev& Pd, SfWorkspace& ws, const double* D_hos
   return IGAB_OK;
 }
 
+// =====================================================================================================================
+// Sum-factorised Gram kernel (3-D Poisson / mass).  The physical gradient of a rational basis function is LINEAR in the
+// four tensor-product B-spline quantities Phi_i^(beta), beta = 0 (value), 1..3 (d/dxi_0..2):
+//     grad_c R_i (x sqrt(w detJ)) = w_i sum_beta C[c][beta] Phi_i^(beta),   C[c][0] = -v[c],  C[c][1+d] = M[c][d]
+// (element_prepare's per-point constants), so
+//     K_ij = w_i w_j sum_q sum_{beta,gamma} Phi_i^(beta)(q) M4_{beta gamma}(q) Phi_j^(gamma)(q),   M4 = C^T C (4x4, per point)
+// and every Phi is a product of univariate table entries: the sum over q factorises direction by direction over PAIRS
+// (i_d, j_d).  Per element 0.6 M multiply-adds instead of 3.5 M (upper tiles of the dense B^T B).  For each i2:
+//   stage 1 (FMA)   T1[(j2,q0)][(beta gamma, q1)] = sum_q2 Phi2[q2][i2] Phi2[q2][j2] M4[q0,q1,q2]
+//   stage 2 (DMMA)  T2[(j1,j2,i1)][(g,q0)]        = sum_{(beta gamma) in g, q1} T1 . Phi1[q1][i1] Phi1[q1][j1]
+//                   g = (is beta the d/dxi_0 index, is gamma) -- the only thing stage 3 needs to know about (beta, gamma)
+//   stage 3 (DMMA)  K[(j1,j2,i1)][(j0,i0)]        = sum_{g,q0} T2 . Phi0[q0][i0] Phi0[q0][j0]
+// and the 8x8 accumulator tiles go straight to global memory: rows of a tile step j by NB1, columns by 1, so a warp's
+// stores form contiguous runs of the 25 complete K_e rows that belong to this i2.
+template <int P, int Q, bool MASS>
+struct SCfg {
+  using F = FCfg<P, Q>;
+  static constexpr int NB1 = P + 1, NP = NB1 * NB1, NB = F::NB, NQ = F::NQ, NT = 256, NWARP = NT / 32;
+  static constexpr int r4(int x) { return (x + 3) & ~3; }
+  static constexpr int r8(int x) { return (x + 7) & ~7; }
+  static constexpr int NG = MASS ? 1 : 4;
+  static constexpr int NCOMBO = MASS ? 1 : 16;
+  static constexpr int NU = MASS ? 1 : 10;  // distinct entries of the symmetric M4
+  static constexpr int ncombo(int g) { return MASS ? 1 : (g == 0 ? 9 : (g == 3 ? 1 : 3)); }
+  static constexpr int goff(int g) {
+    int o = 0;
+    for (int h = 0; h < g; ++h) o += r4(ncombo(h) * Q);
+    return o;
+  }
+  static constexpr int KTOT = goff(NG);
+  static constexpr int M2 = NB1 * Q, M2P = r8(M2);      // stage-2 rows (j2, q0)
+  static constexpr int NPP = r8(NP);                    // pair index, padded
+  static constexpr int MT2 = M2P / 8, NT2 = NPP / 8;
+  static constexpr int TPW = (MT2 * NT2 + NWARP - 1) / NWARP;  // stage-2 tiles per warp (same tile row)
+  static constexpr int K3 = r4(NG * Q);
+  static constexpr int M3 = NB1 * NP, M3P = r8(M3);     // stage-3 rows (j1, j2, i1)
+  static constexpr int MT3 = M3P / 8, NT3 = NPP / 8;
+  // leading dimensions: A operands = 4 mod 8 doubles, B operand = 8 mod 16 (conflict-free fragment loads)
+  static constexpr int LDA2 = (KTOT + 3) / 8 * 8 + 4;
+  static constexpr int LDB2 = (NPP + 7) / 16 * 16 + 8;
+  static constexpr int LDA3 = (K3 + 3) / 8 * 8 + 4;
+  static constexpr int SZ_T1 = M2P * LDA2;
+  static constexpr int SZ_X = F::ev((F::SZ_A + F::SZ_S2) > SZ_T1 ? (F::SZ_A + F::SZ_S2) : SZ_T1);
+  static constexpr int SZ_M = F::ev(NU * NQ);
+  static constexpr int SZ_T2 = M3P * LDA3;
+  static constexpr int SZ_B2 = KTOT * LDB2;
+  static constexpr int SZ_TOTAL = F::SZ_T + F::SZ_W + F::SZ_C + SZ_X + SZ_M + SZ_T2 + SZ_B2;
+  static_assert(TPW * NWARP >= MT2 * NT2 && (TPW == 1 || NT2 % TPW == 0), "stage-2 tile distribution");
+  // combo index (group order) -> (beta, gamma)
+  __host__ __device__ static constexpr int set0(int k) { return k == 0 ? 0 : k + 1; }  // {0, 2, 3}
+  __host__ __device__ static constexpr int beta_of(int g, int c) { return MASS ? 0 : (g == 0 ? set0(c / 3) : (g == 2 ? set0(c) : 1)); }
+  __host__ __device__ static constexpr int gamma_of(int g, int c) { return MASS ? 0 : (g == 0 ? set0(c % 3) : (g == 1 ? set0(c) : 1)); }
+  __host__ __device__ static constexpr int usym(int b, int c) {
+    const int lo = b < c ? b : c, hi = b < c ? c : b;
+    return lo * 4 - lo * (lo - 1) / 2 + (hi - lo);
+  }
+};
+
+template <int P, int Q, bool MASS>
+__global__ void __launch_bounds__(256, 2) gram_sf_kernel(
+    PatchDev Pd, long long elem_begin, long long nelem, const double* __restrict__ tab0,
+    const double* __restrict__ tab1, const double* __restrict__ tab2, const double* __restrict__ w0,
+    const double* __restrict__ w1, const double* __restrict__ w2, double fconst, double* __restrict__ Ke,
+    double* __restrict__ fe) {
+  using C = FCfg<P, Q>;
+  using S = SCfg<P, Q, MASS>;
+  constexpr int NB1 = S::NB1, NP = S::NP, NB = S::NB, NQ = S::NQ, NT = S::NT, CS = C::CS, TAB = C::TAB;
+  constexpr int LDA2 = S::LDA2, LDB2 = S::LDB2, LDA3 = S::LDA3;
+  extern __shared__ __align__(16) double ssm[];
+  double* const sT = ssm;
+  double* const sW = sT + C::SZ_T;
+  double* const sC = sW + C::SZ_W;
+  double* const rX = sC + C::SZ_C;        // element_prepare's scratch (rA | sS2), then T1
+  double* const sT1 = rX;
+  double* const sM = rX + S::SZ_X;
+  double* const sT2 = sM + S::SZ_M;
+  double* const sB2 = sT2 + S::SZ_T2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lr = lane >> 2, lc = lane & 3;
+  for (int idx = tid; idx < C::SZ_W; idx += NT) sW[idx] = 0.0;
+  for (int idx = tid; idx < S::SZ_T2; idx += NT) sT2[idx] = 0.0;  // padding rows / columns stay zero
+  for (int idx = tid; idx < S::SZ_B2; idx += NT) sB2[idx] = 0.0;
+
+  for (long long el = blockIdx.x; el < nelem; el += gridDim.x) {
+    const long long e = elem_begin + el;
+    element_prepare<P, Q, NT>(Pd, e, tab0, tab1, tab2, w0, w1, w2, sT, sW, rX, rX + C::SZ_A, sC);
+    // ---- per point: M4 = C^T C (symmetric 4x4; mass: (sqrt(w detJ)/W)^2)
+    for (int pt = tid; pt < NQ; pt += NT) {
+      const double* o = sC + CS * pt;
+      if constexpr (MASS) {
+        sM[pt] = o[15] * o[15];
+      } else {
+        double Cm[3][4];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          Cm[c][0] = -o[1 + c];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) Cm[c][1 + d] = o[4 + 3 * c + d];
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+          for (int g = b; g < 4; ++g)
+            sM[S::usym(b, g) * NQ + pt] = Cm[0][b] * Cm[0][g] + Cm[1][b] * Cm[1][g] + Cm[2][b] * Cm[2][g];
+      }
+    }
+    // ---- T1 zeroed (its padding columns must stay zero; the scratch it aliases is free after element_prepare)
+    for (int idx = tid; idx < S::SZ_T1; idx += NT) sT1[idx] = 0.0;
+    // ---- B2[(g, c, q1)][pi1 = j1 + NB1 i1] = Phi1[q1][i1][b1(beta)] Phi1[q1][j1][b1(gamma)],  b1(beta) = (beta == 2)
+#pragma unroll
+    for (int g = 0; g < S::NG; ++g) {
+      for (int idx = tid; idx < S::ncombo(g) * Q * NP; idx += NT) {
+        const int n = idx % NP, r = idx / NP, q1 = r % Q, c = r / Q;
+        const int j1 = n % NB1, i1 = n / NB1;
+        const int bb = S::beta_of(g, c) == 2, bg = S::gamma_of(g, c) == 2;
+        sB2[(S::goff(g) + c * Q + q1) * LDB2 + n] =
+            sT[TAB + (q1 * NB1 + i1) * 2 + bb] * sT[TAB + (q1 * NB1 + j1) * 2 + bg];
+      }
+    }
+    // ---- B3 fragments (registers): B3[(g, q0)][pi0 = j0 + NB1 i0] = Phi0[q0][i0][b0(beta)] Phi0[q0][j0][b0(gamma)],
+    //      group g = (b0(beta), b0(gamma)): 0 (0,0), 1 (1,0), 2 (0,1), 3 (1,1)
+    double b3[S::K3 / 4][S::NT3];
+#pragma unroll
+    for (int ks = 0; ks < S::K3 / 4; ++ks)
+#pragma unroll
+      for (int nt = 0; nt < S::NT3; ++nt) {
+        const int k = 4 * ks + lc, n = 8 * nt + lr;
+        double v = 0.0;
+        if (k < S::NG * Q && n < NP) {
+          const int g = k / Q, q0 = k % Q, j0 = n % NB1, i0 = n / NB1;
+          const int bb = (g == 1 || g == 3) ? 1 : 0, bg = (g >= 2) ? 1 : 0;
+          v = sT[(q0 * NB1 + i0) * 2 + bb] * sT[(q0 * NB1 + j0) * 2 + bg];
+        }
+        b3[ks][nt] = v;
+      }
+    __syncthreads();
+
+    double* const K = Ke + el * (long long)NB * NB;
+    for (int i2 = 0; i2 < NB1; ++i2) {
+      // ---- stage 1: thread <-> (combo, q0, q1), all j2
+      for (int item = tid; item < S::NCOMBO * Q * Q; item += NT) {
+        const int q0 = item % Q, r = item / Q, q1 = r % Q, cc = r / Q;
+        int g = 0, c = cc;
+        if constexpr (!MASS) {
+          if (cc >= 15) { g = 3; c = 0; }
+          else if (cc >= 12) { g = 2; c = cc - 12; }
+          else if (cc >= 9) { g = 1; c = cc - 9; }
+        }
+        const int be = S::beta_of(g, c), ga = S::gamma_of(g, c);
+        const int bb = be == 3, bg = ga == 3;
+        const double* mrow = sM + S::usym(be, ga) * NQ + q0 + Q * q1;
+        double am[Q];
+#pragma unroll
+        for (int q2 = 0; q2 < Q; ++q2) am[q2] = sT[2 * TAB + (q2 * NB1 + i2) * 2 + bb] * mrow[Q * Q * q2];
+        const int col = S::goff(g) + c * Q + q1;
+#pragma unroll
+        for (int j2 = 0; j2 < NB1; ++j2) {
+          double sum = 0.0;
+#pragma unroll
+          for (int q2 = 0; q2 < Q; ++q2) sum = fma(am[q2], sT[2 * TAB + (q2 * NB1 + j2) * 2 + bg], sum);
+          sT1[(j2 * Q + q0) * LDA2 + col] = sum;
+        }
+      }
+      __syncthreads();
+      // ---- stage 2: C_g[(j2,q0)][pi1] = sum_{k in g} T1[.][k] B2[k][.]  ->  T2[j1 + NB1 j2 + NP i1][g Q + q0]
+      {
+        const int tile0 = warp * S::TPW;
+        if (tile0 < S::MT2 * S::NT2) {
+          const int mt = tile0 / S::NT2, nt0 = tile0 % S::NT2;
+          const double* arow = sT1 + (8 * mt + lr) * LDA2 + lc;
+#pragma unroll
+          for (int g = 0; g < S::NG; ++g) {
+            double acc[S::TPW][2];
+#pragma unroll
+            for (int s = 0; s < S::TPW; ++s) acc[s][0] = acc[s][1] = 0.0;
+            constexpr int k0 = S::goff(0);  // (silence unused warnings for NG == 1)
+            (void)k0;
+            const int kb = S::goff(g), nks = S::r4(S::ncombo(g) * Q) / 4;
+#pragma unroll 4
+            for (int ks = 0; ks < nks; ++ks) {
+              const double a = arow[kb + 4 * ks];
+#pragma unroll
+              for (int s = 0; s < S::TPW; ++s) {
+                const double b = sB2[(kb + 4 * ks + lc) * LDB2 + 8 * (nt0 + s) + lr];
+                dmma8x8x4_f(acc[s][0], acc[s][1], a, b);
+              }
+            }
+            const int m = 8 * mt + lr;
+            if (m < S::M2) {
+              const int j2 = m / Q, q0 = m % Q;
+#pragma unroll
+              for (int s = 0; s < S::TPW; ++s)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const int n = 8 * (nt0 + s) + 2 * lc + h;
+                  if (n < NP) sT2[((n % NB1) + NB1 * j2 + NP * (n / NB1)) * LDA3 + g * Q + q0] = acc[s][h];
+                }
+            }
+          }
+        }
+      }
+      __syncthreads();
+      // ---- stage 3: K[(j1,j2,i1)][pi0] = sum_{(g,q0)} T2 B3, straight to global memory with the weights w_i w_j
+      for (int mt = warp; mt < S::MT3; mt += S::NWARP) {
+        double acc[S::NT3][2];
+#pragma unroll
+        for (int nt = 0; nt < S::NT3; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+        const double* arow = sT2 + (8 * mt + lr) * LDA3 + lc;
+#pragma unroll
+        for (int ks = 0; ks < S::K3 / 4; ++ks) {
+          const double a = arow[4 * ks];
+#pragma unroll
+          for (int nt = 0; nt < S::NT3; ++nt) dmma8x8x4_f(acc[nt][0], acc[nt][1], a, b3[ks][nt]);
+        }
+        const int mp = 8 * mt + lr;
+        if (mp < S::M3) {
+          const int j1 = mp % NB1, j2 = (mp / NB1) % NB1, i1 = mp / NP;
+          const int ib = NB1 * i1 + NP * i2, jb = NB1 * j1 + NP * j2;
+#pragma unroll
+          for (int nt = 0; nt < S::NT3; ++nt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int n = 8 * nt + 2 * lc + h;
+              if (n < NP) {
+                const int i = ib + n / NB1, j = jb + n % NB1;
+                K[(long long)i * NB + j] = acc[nt][h] * (sW[i] * sW[j]);
+              }
+            }
+        }
+      }
+      // no barrier here: the next pass writes T1 (stage 2 is done with it) and T2 only after its own first barrier
+    }
+    // ---- load vector f_e[i] = sum_q w detJ R_i fconst  (poisson.py:79)
+    if (fe) {
+      for (int i = tid; i < NB; i += NT) {
+        const int i0 = i % NB1, i1 = (i / NB1) % NB1, i2 = i / (NB1 * NB1);
+        const double w = sW[i];
+        double s = 0.0;
+        for (int pt = 0; pt < NQ; ++pt) {
+          const int q0 = pt % Q, q1 = (pt / Q) % Q, q2 = pt / (Q * Q);
+          const double R = sT[(q0 * NB1 + i0) * 2] * sT[TAB + (q1 * NB1 + i1) * 2] *
+                           (w * sT[2 * TAB + (q2 * NB1 + i2) * 2]) * sC[CS * pt];
+          s += sC[CS * pt + 13] * R * fconst;
+        }
+        fe[el * NB + i] = s;
+      }
+    }
+  }
+}
+
 template <int P, int Q>
 igab_status launch_pq(const PatchDev& Pd, SfWorkspace& ws, bool mass, double fconst, long long eb, long long nel,
                       const double* const* w_dev, double* Ke, double* fe, cudaStream_t stream) {
   using C = FCfg<P, Q>;
+  {
+    const char* env = getenv("IGAB_GRAM_SF");
+    if (!(env && env[0] == '0')) {
+      const void* fn = mass ? (const void*)gram_sf_kernel<P, Q, true> : (const void*)gram_sf_kernel<P, Q, false>;
+      const size_t sm = (size_t)(mass ? SCfg<P, Q, true>::SZ_TOTAL : SCfg<P, Q, false>::SZ_TOTAL) * sizeof(double);
+      KernelCfg kc;
+      if (igab_status cst = kernel_config(fn, 256, sm, &kc)) return cst;
+      const unsigned grid = (unsigned)std::min<long long>(nel, (long long)kc.blocksPerSm * kc.sms);
+      if (mass)
+        gram_sf_kernel<P, Q, true><<<grid, 256, sm, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],
+                                                             w_dev[1], w_dev[2], fconst, Ke, fe);
+      else
+        gram_sf_kernel<P, Q, false><<<grid, 256, sm, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],
+                                                              w_dev[1], w_dev[2], fconst, Ke, fe);
+      count_launch();
+      IGAB_CUDA_TRY(cudaGetLastError());
+      return IGAB_OK;
+    }
+  }
   const size_t smem = (size_t)C::SZ_TOTAL * sizeof(double);
   KernelCfg kc;
   if (igab_status cst = kernel_config(mass ? (const void*)gram_fused_kernel<P, Q, 1> : (const void*)gram_fused_kernel<P, Q, 3>,
