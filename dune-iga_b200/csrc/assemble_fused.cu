@@ -662,8 +662,33 @@ __global__ void __launch_bounds__(256, 2) gram_sf_kernel(
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lr = lane >> 2, lc = lane & 3;
   for (int idx = tid; idx < C::SZ_W; idx += NT) sW[idx] = 0.0;
-  for (int idx = tid; idx < S::SZ_T2; idx += NT) sT2[idx] = 0.0;  // padding rows / columns stay zero
-  for (int idx = tid; idx < S::SZ_B2; idx += NT) sB2[idx] = 0.0;
+  for (int idx = tid; idx < S::SZ_B2; idx += NT) sB2[idx] = 0.0;  // padding rows stay zero
+
+  // ---- per-thread constants of the fragment <-> index maps (the same for every element)
+  // stage 2: this warp's tiles (tile row mt2, tiles nt2 .. nt2 + TPW - 1); where C[lr][2 lc + h] of tile s goes in T2
+  const int tile0 = warp * S::TPW;
+  const bool has2 = tile0 < S::MT2 * S::NT2;
+  const int mt2 = has2 ? tile0 / S::NT2 : 0, nt2 = has2 ? tile0 % S::NT2 : 0;
+  int t2off[S::TPW][2];
+  {
+    const int m = 8 * mt2 + lr;
+#pragma unroll
+    for (int s = 0; s < S::TPW; ++s)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int n = 8 * (nt2 + s) + 2 * lc + h;
+        t2off[s][h] = (has2 && m < S::M2 && n < NP) ? ((n % NB1) + NB1 * (m / Q) + NP * (n / NB1)) * LDA3 + (m % Q) : -1;
+      }
+  }
+  // stage 3: column n = 8 nt + 2 lc + h of a tile is (j0, i0) = (n % NB1, n / NB1): offset i0 NB + j0 | i0 << 16 | j0 << 20
+  int c3[S::NT3][2];
+#pragma unroll
+  for (int nt = 0; nt < S::NT3; ++nt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n = 8 * nt + 2 * lc + h;
+      c3[nt][h] = n < NP ? ((n / NB1) * NB + (n % NB1)) | ((n / NB1) << 16) | ((n % NB1) << 20) : -1;
+    }
 
   for (long long el = blockIdx.x; el < nelem; el += gridDim.x) {
     const long long e = elem_begin + el;
@@ -701,29 +726,33 @@ __global__ void __launch_bounds__(256, 2) gram_sf_kernel(
             sT[TAB + (q1 * NB1 + i1) * 2 + bb] * sT[TAB + (q1 * NB1 + j1) * 2 + bg];
       }
     }
-    // ---- B3 fragments (registers): B3[(g, q0)][pi0 = j0 + NB1 i0] = Phi0[q0][i0][b0(beta)] Phi0[q0][j0][b0(gamma)],
-    //      group g = (b0(beta), b0(gamma)): 0 (0,0), 1 (1,0), 2 (0,1), 3 (1,1)
+    // ---- B3[(g, q0)][pi0 = j0 + NB1 i0] = Phi0[q0][i0][b0(beta)] Phi0[q0][j0][b0(gamma)], group g = (b0(beta), b0(gamma)):
+    //      0 (0,0), 1 (1,0), 2 (0,1), 3 (1,1).  Built once in the (still unused) T2 region, then held as fragments.
+    for (int idx = tid; idx < S::K3 * S::NPP; idx += NT) {
+      const int n = idx % S::NPP, k = idx / S::NPP;
+      double v = 0.0;
+      if (k < S::NG * Q && n < NP) {
+        const int g = k / Q, q0 = k % Q, j0 = n % NB1, i0 = n / NB1;
+        const int bb = (g == 1 || g == 3) ? 1 : 0, bg = (g >= 2) ? 1 : 0;
+        v = sT[(q0 * NB1 + i0) * 2 + bb] * sT[(q0 * NB1 + j0) * 2 + bg];
+      }
+      sT2[k * LDB2 + n] = v;
+    }
+    __syncthreads();
     double b3[S::K3 / 4][S::NT3];
 #pragma unroll
     for (int ks = 0; ks < S::K3 / 4; ++ks)
 #pragma unroll
-      for (int nt = 0; nt < S::NT3; ++nt) {
-        const int k = 4 * ks + lc, n = 8 * nt + lr;
-        double v = 0.0;
-        if (k < S::NG * Q && n < NP) {
-          const int g = k / Q, q0 = k % Q, j0 = n % NB1, i0 = n / NB1;
-          const int bb = (g == 1 || g == 3) ? 1 : 0, bg = (g >= 2) ? 1 : 0;
-          v = sT[(q0 * NB1 + i0) * 2 + bb] * sT[(q0 * NB1 + j0) * 2 + bg];
-        }
-        b3[ks][nt] = v;
-      }
+      for (int nt = 0; nt < S::NT3; ++nt) b3[ks][nt] = sT2[(4 * ks + lc) * LDB2 + 8 * nt + lr];
     __syncthreads();
+    for (int idx = tid; idx < S::SZ_T2; idx += NT) sT2[idx] = 0.0;  // padding rows / columns of T2 must be zero
 
     double* const K = Ke + el * (long long)NB * NB;
     for (int i2 = 0; i2 < NB1; ++i2) {
-      // ---- stage 1: thread <-> (combo, q0, q1), all j2
-      for (int item = tid; item < S::NCOMBO * Q * Q; item += NT) {
-        const int q0 = item % Q, r = item / Q, q1 = r % Q, cc = r / Q;
+      // ---- stage 1: thread <-> (combo, q1, half of the q0 range), all j2: the M4 line and the i2 factor in registers
+      constexpr int QH = (Q + 1) / 2;
+      for (int item = tid; item < S::NCOMBO * Q * 2; item += NT) {
+        const int half = item & 1, r = item >> 1, q1 = r % Q, cc = r / Q;
         int g = 0, c = cc;
         if constexpr (!MASS) {
           if (cc >= 15) { g = 3; c = 0; }
@@ -732,55 +761,52 @@ __global__ void __launch_bounds__(256, 2) gram_sf_kernel(
         }
         const int be = S::beta_of(g, c), ga = S::gamma_of(g, c);
         const int bb = be == 3, bg = ga == 3;
-        const double* mrow = sM + S::usym(be, ga) * NQ + q0 + Q * q1;
-        double am[Q];
+        const int qa = half * QH;                       // q0 in [qa, qa + QH) (clipped to Q)
+        const double* mrow = sM + S::usym(be, ga) * NQ + Q * q1;
+        double am[QH][Q];
 #pragma unroll
-        for (int q2 = 0; q2 < Q; ++q2) am[q2] = sT[2 * TAB + (q2 * NB1 + i2) * 2 + bb] * mrow[Q * Q * q2];
-        const int col = S::goff(g) + c * Q + q1;
+        for (int q2 = 0; q2 < Q; ++q2) {
+          const double a2 = sT[2 * TAB + (q2 * NB1 + i2) * 2 + bb];
+#pragma unroll
+          for (int u = 0; u < QH; ++u) am[u][q2] = a2 * mrow[min(qa + u, Q - 1) + Q * Q * q2];
+        }
+        double* trow = sT1 + S::goff(g) + c * Q + q1;
 #pragma unroll
         for (int j2 = 0; j2 < NB1; ++j2) {
-          double sum = 0.0;
+          double f[Q];
 #pragma unroll
-          for (int q2 = 0; q2 < Q; ++q2) sum = fma(am[q2], sT[2 * TAB + (q2 * NB1 + j2) * 2 + bg], sum);
-          sT1[(j2 * Q + q0) * LDA2 + col] = sum;
+          for (int q2 = 0; q2 < Q; ++q2) f[q2] = sT[2 * TAB + (q2 * NB1 + j2) * 2 + bg];
+#pragma unroll
+          for (int u = 0; u < QH; ++u) {
+            double sum = 0.0;
+#pragma unroll
+            for (int q2 = 0; q2 < Q; ++q2) sum = fma(am[u][q2], f[q2], sum);
+            if (qa + u < Q) trow[(j2 * Q + qa + u) * LDA2] = sum;
+          }
         }
       }
       __syncthreads();
       // ---- stage 2: C_g[(j2,q0)][pi1] = sum_{k in g} T1[.][k] B2[k][.]  ->  T2[j1 + NB1 j2 + NP i1][g Q + q0]
-      {
-        const int tile0 = warp * S::TPW;
-        if (tile0 < S::MT2 * S::NT2) {
-          const int mt = tile0 / S::NT2, nt0 = tile0 % S::NT2;
-          const double* arow = sT1 + (8 * mt + lr) * LDA2 + lc;
+      if (has2) {
+        const double* arow = sT1 + (8 * mt2 + lr) * LDA2 + lc;
+        const double* brow = sB2 + lc * LDB2 + 8 * nt2 + lr;
 #pragma unroll
-          for (int g = 0; g < S::NG; ++g) {
-            double acc[S::TPW][2];
+        for (int g = 0; g < S::NG; ++g) {
+          double acc[S::TPW][2];
 #pragma unroll
-            for (int s = 0; s < S::TPW; ++s) acc[s][0] = acc[s][1] = 0.0;
-            constexpr int k0 = S::goff(0);  // (silence unused warnings for NG == 1)
-            (void)k0;
-            const int kb = S::goff(g), nks = S::r4(S::ncombo(g) * Q) / 4;
+          for (int s = 0; s < S::TPW; ++s) acc[s][0] = acc[s][1] = 0.0;
+          const int kb = S::goff(g), nks = S::r4(S::ncombo(g) * Q) / 4;  // constants after unrolling over g
 #pragma unroll 4
-            for (int ks = 0; ks < nks; ++ks) {
-              const double a = arow[kb + 4 * ks];
+          for (int ks = 0; ks < nks; ++ks) {
+            const double a = arow[kb + 4 * ks];
 #pragma unroll
-              for (int s = 0; s < S::TPW; ++s) {
-                const double b = sB2[(kb + 4 * ks + lc) * LDB2 + 8 * (nt0 + s) + lr];
-                dmma8x8x4_f(acc[s][0], acc[s][1], a, b);
-              }
-            }
-            const int m = 8 * mt + lr;
-            if (m < S::M2) {
-              const int j2 = m / Q, q0 = m % Q;
-#pragma unroll
-              for (int s = 0; s < S::TPW; ++s)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  const int n = 8 * (nt0 + s) + 2 * lc + h;
-                  if (n < NP) sT2[((n % NB1) + NB1 * j2 + NP * (n / NB1)) * LDA3 + g * Q + q0] = acc[s][h];
-                }
-            }
+            for (int s = 0; s < S::TPW; ++s) dmma8x8x4_f(acc[s][0], acc[s][1], a, brow[(kb + 4 * ks) * LDB2 + 8 * s]);
           }
+#pragma unroll
+          for (int s = 0; s < S::TPW; ++s)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              if (t2off[s][h] >= 0) sT2[t2off[s][h] + g * Q] = acc[s][h];
         }
       }
       __syncthreads();
@@ -800,15 +826,15 @@ __global__ void __launch_bounds__(256, 2) gram_sf_kernel(
         if (mp < S::M3) {
           const int j1 = mp % NB1, j2 = (mp / NB1) % NB1, i1 = mp / NP;
           const int ib = NB1 * i1 + NP * i2, jb = NB1 * j1 + NP * j2;
+          double* const Kb = K + (long long)ib * NB + jb;
+          const double* const wI = sW + ib;
+          const double* const wJ = sW + jb;
 #pragma unroll
           for (int nt = 0; nt < S::NT3; ++nt)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const int n = 8 * nt + 2 * lc + h;
-              if (n < NP) {
-                const int i = ib + n / NB1, j = jb + n % NB1;
-                K[(long long)i * NB + j] = acc[nt][h] * (sW[i] * sW[j]);
-              }
+              const int pk = c3[nt][h];
+              if (pk >= 0) Kb[pk & 0xffff] = acc[nt][h] * (wI[(pk >> 16) & 15] * wJ[pk >> 20]);
             }
         }
       }
