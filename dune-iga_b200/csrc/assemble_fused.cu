@@ -690,6 +690,15 @@ __global__ void __launch_bounds__(256, 2) gram_sf_kernel(
       c3[nt][h] = n < NP ? ((n / NB1) * NB + (n % NB1)) | ((n / NB1) << 16) | ((n % NB1) << 20) : -1;
     }
 
+  // stage 3: row lr of this warp's u-th tile (tile row warp + 8 u) is (j1, j2, i1): NB1 i1 | (NB1 j1 + NP j2) << 8, or -1
+  constexpr int NMT = (S::MT3 + S::NWARP - 1) / S::NWARP;
+  int r3[NMT];
+#pragma unroll
+  for (int u = 0; u < NMT; ++u) {
+    const int mp = 8 * (warp + S::NWARP * u) + lr;
+    r3[u] = mp < S::M3 ? (NB1 * (mp / NP)) | ((NB1 * (mp % NB1) + NP * ((mp / NB1) % NB1)) << 8) : -1;
+  }
+
   for (long long el = blockIdx.x; el < nelem; el += gridDim.x) {
     const long long e = elem_begin + el;
     element_prepare<P, Q, NT>(Pd, e, tab0, tab1, tab2, w0, w1, w2, sT, sW, rX, rX + C::SZ_A, sC);
@@ -811,7 +820,10 @@ __global__ void __launch_bounds__(256, 2) gram_sf_kernel(
       }
       __syncthreads();
       // ---- stage 3: K[(j1,j2,i1)][pi0] = sum_{(g,q0)} T2 B3, straight to global memory with the weights w_i w_j
-      for (int mt = warp; mt < S::MT3; mt += S::NWARP) {
+#pragma unroll
+      for (int u = 0; u < NMT; ++u) {
+        const int mt = warp + S::NWARP * u;
+        if (mt >= S::MT3) break;
         double acc[S::NT3][2];
 #pragma unroll
         for (int nt = 0; nt < S::NT3; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
@@ -822,11 +834,9 @@ __global__ void __launch_bounds__(256, 2) gram_sf_kernel(
 #pragma unroll
           for (int nt = 0; nt < S::NT3; ++nt) dmma8x8x4_f(acc[nt][0], acc[nt][1], a, b3[ks][nt]);
         }
-        const int mp = 8 * mt + lr;
-        if (mp < S::M3) {
-          const int j1 = mp % NB1, j2 = (mp / NB1) % NB1, i1 = mp / NP;
-          const int ib = NB1 * i1 + NP * i2, jb = NB1 * j1 + NP * j2;
-          double* const Kb = K + (long long)ib * NB + jb;
+        if (r3[u] >= 0) {
+          const int ib = (r3[u] & 255) + NP * i2, jb = r3[u] >> 8;
+          double* const Kb = K + ib * NB + jb;
           const double* const wI = sW + ib;
           const double* const wJ = sW + jb;
 #pragma unroll
