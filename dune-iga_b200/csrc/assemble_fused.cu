@@ -596,15 +596,17 @@ igab_status launch_elas(const PatchDev& Pd, SfWorkspace& ws, const double* D_hos
 //   stage 3 (DMMA)  K[(j1,j2,i1)][(j0,i0)]        = sum_{g,q0} T2 . Phi0[q0][i0] Phi0[q0][j0]
 // and the 8x8 accumulator tiles go straight to global memory: rows of a tile step j by NB1, columns by 1, so a warp's
 // stores form contiguous runs of the 25 complete K_e rows that belong to this i2.
-template <int P, int Q, bool MASS>
+// KIND: 0 Poisson, 1 mass, 2 elasticity (nine (a, b) blocks, each a Poisson-like contraction with its own 4x4 M4)
+template <int P, int Q, int KIND>
 struct SCfg {
+  static constexpr bool MASS = KIND == 1, ELAS = KIND == 2;
   using F = FCfg<P, Q>;
   static constexpr int NB1 = P + 1, NP = NB1 * NB1, NB = F::NB, NQ = F::NQ, NT = 256, NWARP = NT / 32;
   static constexpr int r4(int x) { return (x + 3) & ~3; }
   static constexpr int r8(int x) { return (x + 7) & ~7; }
   static constexpr int NG = MASS ? 1 : 4;
   static constexpr int NCOMBO = MASS ? 1 : 16;
-  static constexpr int NU = MASS ? 1 : 10;  // distinct entries of the symmetric M4
+  static constexpr int NU = MASS ? 1 : (ELAS ? 16 : 10);  // stored entries of M4 (symmetric for Poisson)
   static constexpr int ncombo(int g) { return MASS ? 1 : (g == 0 ? 9 : (g == 3 ? 1 : 3)); }
   static constexpr int goff(int g) {
     int o = 0;
@@ -635,19 +637,22 @@ struct SCfg {
   __host__ __device__ static constexpr int beta_of(int g, int c) { return MASS ? 0 : (g == 0 ? set0(c / 3) : (g == 2 ? set0(c) : 1)); }
   __host__ __device__ static constexpr int gamma_of(int g, int c) { return MASS ? 0 : (g == 0 ? set0(c % 3) : (g == 1 ? set0(c) : 1)); }
   __host__ __device__ static constexpr int usym(int b, int c) {
+    if (ELAS) return b * 4 + c;
     const int lo = b < c ? b : c, hi = b < c ? c : b;
     return lo * 4 - lo * (lo - 1) / 2 + (hi - lo);
   }
 };
 
-template <int P, int Q, bool MASS>
+template <int P, int Q, int KIND>
 __global__ void __launch_bounds__(256, 2) gram_sf_kernel(
     PatchDev Pd, long long elem_begin, long long nelem, const double* __restrict__ tab0,
     const double* __restrict__ tab1, const double* __restrict__ tab2, const double* __restrict__ w0,
-    const double* __restrict__ w1, const double* __restrict__ w2, double fconst, double* __restrict__ Ke,
-    double* __restrict__ fe) {
+    const double* __restrict__ w1, const double* __restrict__ w2, ElasCoef coef, double fconst,
+    double* __restrict__ Ke, double* __restrict__ fe) {
   using C = FCfg<P, Q>;
-  using S = SCfg<P, Q, MASS>;
+  using S = SCfg<P, Q, KIND>;
+  constexpr bool MASS = S::MASS, ELAS = S::ELAS;
+  constexpr int NCP = ELAS ? 3 : 1, NROWK = NCP * S::NB;  // components per basis function, rows of K_e
   constexpr int NB1 = S::NB1, NP = S::NP, NB = S::NB, NQ = S::NQ, NT = S::NT, CS = C::CS, TAB = C::TAB;
   constexpr int LDA2 = S::LDA2, LDB2 = S::LDB2, LDA3 = S::LDA3;
   extern __shared__ __align__(16) double ssm[];
@@ -702,26 +707,6 @@ __global__ void __launch_bounds__(256, 2) gram_sf_kernel(
   for (long long el = blockIdx.x; el < nelem; el += gridDim.x) {
     const long long e = elem_begin + el;
     element_prepare<P, Q, NT>(Pd, e, tab0, tab1, tab2, w0, w1, w2, sT, sW, rX, rX + C::SZ_A, sC);
-    // ---- per point: M4 = C^T C (symmetric 4x4; mass: (sqrt(w detJ)/W)^2)
-    for (int pt = tid; pt < NQ; pt += NT) {
-      const double* o = sC + CS * pt;
-      if constexpr (MASS) {
-        sM[pt] = o[15] * o[15];
-      } else {
-        double Cm[3][4];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          Cm[c][0] = -o[1 + c];
-#pragma unroll
-          for (int d = 0; d < 3; ++d) Cm[c][1 + d] = o[4 + 3 * c + d];
-        }
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-#pragma unroll
-          for (int g = b; g < 4; ++g)
-            sM[S::usym(b, g) * NQ + pt] = Cm[0][b] * Cm[0][g] + Cm[1][b] * Cm[1][g] + Cm[2][b] * Cm[2][g];
-      }
-    }
     // ---- T1 zeroed (its padding columns must stay zero; the scratch it aliases is free after element_prepare)
     for (int idx = tid; idx < S::SZ_T1; idx += NT) sT1[idx] = 0.0;
     // ---- B2[(g, c, q1)][pi1 = j1 + NB1 i1] = Phi1[q1][i1][b1(beta)] Phi1[q1][j1][b1(gamma)],  b1(beta) = (beta == 2)
@@ -756,7 +741,48 @@ __global__ void __launch_bounds__(256, 2) gram_sf_kernel(
     __syncthreads();
     for (int idx = tid; idx < S::SZ_T2; idx += NT) sT2[idx] = 0.0;  // padding rows / columns of T2 must be zero
 
-    double* const K = Ke + el * (long long)NB * NB;
+    double* const K = Ke + el * (long long)NROWK * NROWK;
+    for (int ab = 0; ab < NCP * NCP; ++ab) {
+    const int ca = ab / NCP, cb = ab % NCP;  // elasticity: the (a, b) component block
+    // ---- per point: M4 = C^T C (symmetric 4x4; mass: (sqrt(w detJ)/W)^2; elasticity: C^T Cf[a][.][b][.] C)
+    for (int pt = tid; pt < NQ; pt += NT) {
+      const double* o = sC + CS * pt;
+      if constexpr (MASS) {
+        sM[pt] = o[15] * o[15];
+      } else {
+        double Cm[3][4];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          Cm[c][0] = -o[1 + c];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) Cm[c][1 + d] = o[4 + 3 * c + d];
+        }
+        if constexpr (ELAS) {
+          double Tm[3][4];
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              double t = 0.0;
+#pragma unroll
+              for (int cp = 0; cp < 3; ++cp) t = fma(coef.cf[((ca * 3 + c) * 3 + cb) * 3 + cp], Cm[cp][g], t);
+              Tm[c][g] = t;
+            }
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              sM[(b * 4 + g) * NQ + pt] = Cm[0][b] * Tm[0][g] + Cm[1][b] * Tm[1][g] + Cm[2][b] * Tm[2][g];
+        } else {
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int g = b; g < 4; ++g)
+              sM[S::usym(b, g) * NQ + pt] = Cm[0][b] * Cm[0][g] + Cm[1][b] * Cm[1][g] + Cm[2][b] * Cm[2][g];
+        }
+      }
+    }
+    __syncthreads();
     for (int i2 = 0; i2 < NB1; ++i2) {
       // ---- stage 1: thread <-> (combo, q1, half of the q0 range), all j2: the M4 line and the i2 factor in registers
       constexpr int QH = (Q + 1) / 2;
@@ -836,20 +862,35 @@ __global__ void __launch_bounds__(256, 2) gram_sf_kernel(
         }
         if (r3[u] >= 0) {
           const int ib = (r3[u] & 255) + NP * i2, jb = r3[u] >> 8;
-          double* const Kb = K + ib * NB + jb;
           const double* const wI = sW + ib;
           const double* const wJ = sW + jb;
+          if constexpr (ELAS) {
+            double* const Kb = K + (long long)(ib * 3 + ca) * NROWK + jb * 3 + cb;
 #pragma unroll
-          for (int nt = 0; nt < S::NT3; ++nt)
+            for (int nt = 0; nt < S::NT3; ++nt)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int pk = c3[nt][h];
-              if (pk >= 0) Kb[pk & 0xffff] = acc[nt][h] * (wI[(pk >> 16) & 15] * wJ[pk >> 20]);
-            }
+              for (int h = 0; h < 2; ++h) {
+                const int pk = c3[nt][h];
+                if (pk >= 0) {
+                  const int i0 = (pk >> 16) & 15, j0 = pk >> 20;
+                  Kb[i0 * 3 * NROWK + j0 * 3] = acc[nt][h] * (wI[i0] * wJ[j0]);
+                }
+              }
+          } else {
+            double* const Kb = K + ib * NB + jb;
+#pragma unroll
+            for (int nt = 0; nt < S::NT3; ++nt)
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int pk = c3[nt][h];
+                if (pk >= 0) Kb[pk & 0xffff] = acc[nt][h] * (wI[(pk >> 16) & 15] * wJ[pk >> 20]);
+              }
+          }
         }
       }
       // no barrier here: the next pass writes T1 (stage 2 is done with it) and T2 only after its own first barrier
     }
+    }  // (a, b) blocks: the next block rewrites sM, last read two barriers ago
     // ---- load vector f_e[i] = sum_q w detJ R_i fconst  (poisson.py:79)
     if (fe) {
       for (int i = tid; i < NB; i += NT) {
@@ -862,10 +903,33 @@ __global__ void __launch_bounds__(256, 2) gram_sf_kernel(
                            (w * sT[2 * TAB + (q2 * NB1 + i2) * 2]) * sC[CS * pt];
           s += sC[CS * pt + 13] * R * fconst;
         }
-        fe[el * NB + i] = s;
+        if constexpr (ELAS)
+          fe[el * NROWK + 3 * i] = fe[el * NROWK + 3 * i + 1] = fe[el * NROWK + 3 * i + 2] = s;
+        else
+          fe[el * NB + i] = s;
       }
     }
   }
+}
+
+template <int P, int Q>
+igab_status launch_elas_sf(const PatchDev& Pd, SfWorkspace& ws, const double* D_host, double fconst, long long eb,
+                           long long nel, const double* const* w_dev, double* Ke, double* fe, cudaStream_t stream) {
+  // Cf[a][c][b][c'] = sum_{r,t} S[r][a][c] D[r][t] S[t][b][c'], S = Voigt selector (xx,yy,zz,yz,xz,xy; engineering shear)
+  static const int S[9][3] = {{0, 0, 0}, {1, 1, 1}, {2, 2, 2}, {3, 1, 2}, {3, 2, 1}, {4, 0, 2}, {4, 2, 0}, {5, 0, 1}, {5, 1, 0}};
+  ElasCoef coef;
+  for (double& v : coef.cf) v = 0.0;
+  for (auto& s1 : S)
+    for (auto& s2 : S) coef.cf[((s1[1] * 3 + s1[2]) * 3 + s2[1]) * 3 + s2[2]] += D_host[s1[0] * 6 + s2[0]];
+  const size_t sm = (size_t)SCfg<P, Q, 2>::SZ_TOTAL * sizeof(double);
+  KernelCfg kc;
+  if (igab_status cst = kernel_config((const void*)gram_sf_kernel<P, Q, 2>, 256, sm, &kc)) return cst;
+  const unsigned grid = (unsigned)std::min<long long>(nel, (long long)kc.blocksPerSm * kc.sms);
+  gram_sf_kernel<P, Q, 2><<<grid, 256, sm, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0], w_dev[1],
+                                                    w_dev[2], coef, fconst, Ke, fe);
+  count_launch();
+  IGAB_CUDA_TRY(cudaGetLastError());
+  return IGAB_OK;
 }
 
 template <int P, int Q>
@@ -875,17 +939,18 @@ igab_status launch_pq(const PatchDev& Pd, SfWorkspace& ws, bool mass, double fco
   {
     const char* env = getenv("IGAB_GRAM_SF");
     if (!(env && env[0] == '0')) {
-      const void* fn = mass ? (const void*)gram_sf_kernel<P, Q, true> : (const void*)gram_sf_kernel<P, Q, false>;
-      const size_t sm = (size_t)(mass ? SCfg<P, Q, true>::SZ_TOTAL : SCfg<P, Q, false>::SZ_TOTAL) * sizeof(double);
+      const void* fn = mass ? (const void*)gram_sf_kernel<P, Q, 1> : (const void*)gram_sf_kernel<P, Q, 0>;
+      const size_t sm = (size_t)(mass ? SCfg<P, Q, 1>::SZ_TOTAL : SCfg<P, Q, 0>::SZ_TOTAL) * sizeof(double);
+      const ElasCoef nocoef{};
       KernelCfg kc;
       if (igab_status cst = kernel_config(fn, 256, sm, &kc)) return cst;
       const unsigned grid = (unsigned)std::min<long long>(nel, (long long)kc.blocksPerSm * kc.sms);
       if (mass)
-        gram_sf_kernel<P, Q, true><<<grid, 256, sm, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],
-                                                             w_dev[1], w_dev[2], fconst, Ke, fe);
+        gram_sf_kernel<P, Q, 1><<<grid, 256, sm, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],
+                                                          w_dev[1], w_dev[2], nocoef, fconst, Ke, fe);
       else
-        gram_sf_kernel<P, Q, false><<<grid, 256, sm, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],
-                                                              w_dev[1], w_dev[2], fconst, Ke, fe);
+        gram_sf_kernel<P, Q, 0><<<grid, 256, sm, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],
+                                                          w_dev[1], w_dev[2], nocoef, fconst, Ke, fe);
       count_launch();
       IGAB_CUDA_TRY(cudaGetLastError());
       return IGAB_OK;
@@ -935,8 +1000,12 @@ igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* 
       set_error("assemble: elasticity needs the 6x6 D matrix");
       return IGAB_INVALID_ARGUMENT;
     }
-#define IGAB_ELAS_CASE(PP, QQ) \
-  if (P.degree[0] == PP && nq1[0] == QQ) return launch_elas<PP, QQ>(P, ws, D_host, fconst, eb, nel, w1d_dev, Ke, fe, stream);
+    const char* esf = getenv("IGAB_ELAS_SF");
+    const bool use_sf = !(esf && esf[0] == '0');
+#define IGAB_ELAS_CASE(PP, QQ)                                                                                   \
+  if (P.degree[0] == PP && nq1[0] == QQ)                                                                         \
+    return use_sf ? launch_elas_sf<PP, QQ>(P, ws, D_host, fconst, eb, nel, w1d_dev, Ke, fe, stream)              \
+                  : launch_elas<PP, QQ>(P, ws, D_host, fconst, eb, nel, w1d_dev, Ke, fe, stream);
     IGAB_ELAS_CASE(2, 3) IGAB_ELAS_CASE(2, 4) IGAB_ELAS_CASE(3, 4) IGAB_ELAS_CASE(3, 5) IGAB_ELAS_CASE(4, 5) IGAB_ELAS_CASE(4, 6)
 #undef IGAB_ELAS_CASE
     set_error("assemble: no fused kernel for this configuration");
