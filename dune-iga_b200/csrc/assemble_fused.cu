@@ -937,8 +937,10 @@ igab_status launch_pq(const PatchDev& Pd, SfWorkspace& ws, bool mass, double fco
                       const double* const* w_dev, double* Ke, double* fe, cudaStream_t stream) {
   using C = FCfg<P, Q>;
   {
+    // the sum-factorised contraction wins from p = 3 on (measured: p = 3 1.5x, p = 4 2.4-3.8x; p = 2 0.5-0.7x);
+    // IGAB_GRAM_SF=0 / 1 forces the dense-Gram / the sum-factorised kernel
     const char* env = getenv("IGAB_GRAM_SF");
-    if (!(env && env[0] == '0')) {
+    if (env ? env[0] != '0' : P >= 3) {
       const void* fn = mass ? (const void*)gram_sf_kernel<P, Q, 1> : (const void*)gram_sf_kernel<P, Q, 0>;
       const size_t sm = (size_t)(mass ? SCfg<P, Q, 1>::SZ_TOTAL : SCfg<P, Q, 0>::SZ_TOTAL) * sizeof(double);
       const ElasCoef nocoef{};
@@ -1000,8 +1002,10 @@ igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* 
       set_error("assemble: elasticity needs the 6x6 D matrix");
       return IGAB_INVALID_ARGUMENT;
     }
+    // elasticity: the sum-factorised kernel pays off at p = 4 (1.09x; its interleaved (j, b) stores cost a quarter of its
+    // time), the nine-Gram-block kernel stays ahead below; IGAB_ELAS_SF=0 / 1 forces one of them
     const char* esf = getenv("IGAB_ELAS_SF");
-    const bool use_sf = !(esf && esf[0] == '0');
+    const bool use_sf = esf ? esf[0] != '0' : P.degree[0] >= 4;
 #define IGAB_ELAS_CASE(PP, QQ)                                                                                   \
   if (P.degree[0] == PP && nq1[0] == QQ)                                                                         \
     return use_sf ? launch_elas_sf<PP, QQ>(P, ws, D_host, fconst, eb, nel, w1d_dev, Ke, fe, stream)              \

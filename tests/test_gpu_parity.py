@@ -1052,6 +1052,31 @@ def test_fused_3d_element_matrices_over_integrated(p, kind):
     assert relerr(f, fref) <= TOL
 
 
+@pytest.mark.parametrize("p,extra", [(2, 0), (3, 0), (3, 1), (4, 0), (4, 1)])
+@pytest.mark.parametrize("kind", [capi.ASM_POISSON, capi.ASM_MASS, capi.ASM_ELASTICITY])
+@pytest.mark.parametrize("sf", ["0", "1"], ids=["dense", "sumfact"])
+def test_fused_3d_element_matrices_both_contractions(p, extra, kind, sf, monkeypatch):
+    """Both fused 3-D assembly kernels -- the dense Gram contraction and the sum-factorised one (pairs (i_d, j_d)
+    contracted direction by direction) -- forced through IGAB_GRAM_SF / IGAB_ELAS_SF at every degree, with a random
+    NON-symmetric material for elasticity and a patch whose weights vary in every direction, against the oracle."""
+    monkeypatch.setenv("IGAB_GRAM_SF", sf)
+    monkeypatch.setenv("IGAB_ELAS_SF", sf)
+    rng = np.random.default_rng(40 + p)
+    pd = PD.thickCylinder(p, (1, 1, 1))
+    cp = pd.cp.copy()
+    cp[:, 3] *= rng.uniform(0.7, 1.3, cp.shape[0])          # weights without tensor-product structure
+    spec = dict(degree=pd.degree, knots=pd.knotSpans, cp=cp, dimworld=3)
+    Pp = port_for(spec)
+    P = gpu_patch(spec)
+    x, w = PD.gaussLegendre01(p + 1 + extra)
+    D = rng.normal(size=(6, 6)) + 4 * np.eye(6) if kind == capi.ASM_ELASTICITY else None
+    eb, ee = 3, 8
+    Kref, fref = Pp.assemble(kind, [x] * 3, [w] * 3, D=D, fconst=1.3, elem_begin=eb, elem_end=ee)
+    K, f = P.assemble(kind, [x] * 3, [w] * 3, D=D, fconst=1.3, elem_begin=eb, elem_end=ee)
+    assert relerr(K.reshape(ee - eb, -1), Kref.reshape(ee - eb, -1)) <= TOL, relerr(K.reshape(ee - eb, -1), Kref.reshape(ee - eb, -1))
+    assert relerr(f, fref) <= TOL
+
+
 def test_device_path_is_cuda_graph_capturable():
     """The device-resident entry points enqueue on the caller's stream without host synchronisation (once the rule is
     staged), so a quadrature loop can be captured in a CUDA graph and replayed -- here: evaluation + fused element
