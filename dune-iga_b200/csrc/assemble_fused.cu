@@ -742,9 +742,13 @@ __global__ void __launch_bounds__(256, 2) gram_sf_kernel(
     for (int idx = tid; idx < S::SZ_T2; idx += NT) sT2[idx] = 0.0;  // padding rows / columns of T2 must be zero
 
     double* const K = Ke + el * (long long)NROWK * NROWK;
-    for (int ab = 0; ab < NCP * NCP; ++ab) {
-    const int ca = ab / NCP, cb = ab % NCP;  // elasticity: the (a, b) component block
+    // elasticity: the (a, b) component blocks, b innermost INSIDE a pass, so that the three stores that complete a
+    // 32-byte sector of the interleaved (j, b) columns reach L2 close together (b outermost: 4x the DRAM traffic)
+    for (int ca = 0; ca < NCP; ++ca)
+    for (int i2 = 0; i2 < NB1; ++i2)
+    for (int cb = 0; cb < NCP; ++cb) {
     // ---- per point: M4 = C^T C (symmetric 4x4; mass: (sqrt(w detJ)/W)^2; elasticity: C^T Cf[a][.][b][.] C)
+    if (ELAS || i2 == 0) {
     for (int pt = tid; pt < NQ; pt += NT) {
       const double* o = sC + CS * pt;
       if constexpr (MASS) {
@@ -783,7 +787,8 @@ __global__ void __launch_bounds__(256, 2) gram_sf_kernel(
       }
     }
     __syncthreads();
-    for (int i2 = 0; i2 < NB1; ++i2) {
+    }
+    {
       // ---- stage 1: thread <-> (combo, q1, half of the q0 range), all j2: the M4 line and the i2 factor in registers
       constexpr int QH = (Q + 1) / 2;
       for (int item = tid; item < S::NCOMBO * Q * 2; item += NT) {
@@ -890,7 +895,7 @@ __global__ void __launch_bounds__(256, 2) gram_sf_kernel(
       }
       // no barrier here: the next pass writes T1 (stage 2 is done with it) and T2 only after its own first barrier
     }
-    }  // (a, b) blocks: the next block rewrites sM, last read two barriers ago
+    }  // (a, i2, b): the next block rewrites sM, last read two barriers ago
     // ---- load vector f_e[i] = sum_q w detJ R_i fconst  (poisson.py:79)
     if (fe) {
       for (int i = tid; i < NB; i += NT) {
