@@ -25,7 +25,7 @@ EXPORTS = ("igab_last_error_string", "igab_version", "igab_launch_count", "igab_
            "igab_patch_update_control_points", "igab_patch_spans", "igab_patch_dofmap", "igab_eval_tensor",
            "igab_eval_points", "igab_partial", "igab_assemble", "igab_reduce_volume", "igab_csr_pattern",
            "igab_csr_assemble", "igab_eval_faces", "igab_refine_apply", "igab_surface_forms", "igab_geometry_local", "igab_reduce_norms", "igab_local_keys", "igab_rhs_assemble",
-           "igab_csr_dirichlet", "igab_assemble_points")
+           "igab_csr_dirichlet", "igab_assemble_points", "igab_global_assemble")
 
 
 class EvalOut(C.Structure):
@@ -68,6 +68,9 @@ def lib():
                                     C.POINTER(dp), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.igab_csr_pattern.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p,
                                        C.c_void_p, C.c_int, C.c_void_p]
+        L.igab_global_assemble.argtypes = [C.c_void_p, C.c_int, dp, C.c_double, ip, C.POINTER(dp), C.POINTER(dp),
+                                           C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_int, C.c_void_p]
         L.igab_csr_assemble.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_int, C.c_int, C.c_void_p]
         L.igab_eval_faces.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, ip, C.POINTER(dp), C.c_void_p,
@@ -426,6 +429,35 @@ class Patch:
         _check(lib().igab_csr_assemble(self.h, ncomp, elem_begin, elem_end, ka, None, va, 1 if accumulate else 0, ks,
                                        stream))
         return values
+
+    def globalAssemble(self, kind, xi1d, w1d, D=None, fconst=1.0, trimmed=None, want_b=True, device=False, stream=None):
+        """globalAssembler of poisson.py:84-127 in one call: (values [nnz] of csrPattern(ncomp), b [nrows]).  The element
+        matrices stay on the device.  trimmed = (elem, offset, xi, w) of the trimmed elements' own rules
+        (quadrature.trimmedBatch; elem ascending) or None.  device=True returns CUDA tensors."""
+        xa, xp = _rule_arrays(xi1d)
+        wa, wp = _rule_arrays(w1d)
+        nq1 = _i32([len(a) for a in xa])
+        ncomp = self.dim if kind == ASM_ELASTICITY else 1
+        nr, nnz = C.c_int64(), C.c_int64()
+        _check(lib().igab_csr_pattern(self.h, ncomp, C.byref(nr), C.byref(nnz), None, None, HOST, None))
+        if device:
+            import torch
+            values = torch.empty(nnz.value, dtype=torch.float64, device="cuda")
+            b = torch.empty(nr.value, dtype=torch.float64, device="cuda") if want_b else None
+        else:
+            values = np.empty(nnz.value)
+            b = np.empty(nr.value) if want_b else None
+        Dm = _f64(D) if D is not None else None
+        nl, ea, oa, xia, wqa = 0, None, None, None, None
+        if trimmed is not None and len(trimmed[0]):
+            te, to = _i32(trimmed[0]), np.ascontiguousarray(trimmed[1], dtype=np.int64)
+            tx, tw = _f64(trimmed[2]), _f64(trimmed[3])
+            nl, ea, oa, xia, wqa = len(te), te.ctypes.data, to.ctypes.data, tx.ctypes.data, tw.ctypes.data
+        va, vs = _ptr(values)
+        _check(lib().igab_global_assemble(self.h, kind, Dm.ctypes.data_as(dp) if Dm is not None else None, fconst,
+                                          nq1.ctypes.data_as(ip), xp, wp, nl, ea, oa, xia, wqa, va,
+                                          _ptr(b)[0] if b is not None else None, vs, stream))
+        return values, b
 
     def volume(self, xi1d, w1d, elem_begin=0, elem_end=None, nccl_comm=None, stream=None):
         if elem_end is None:

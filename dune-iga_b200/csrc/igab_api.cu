@@ -1137,6 +1137,125 @@ igab_status igab_csr_assemble(igab_patch* p, int ncomp, int64_t elem_begin, int6
   return csr_assemble(p, ncomp, elem_begin, elem_end, Ke, rowptr, values, accumulate, space, (cudaStream_t)stream);
 }
 
+// ---- the whole globalAssembler in one call --------------------------------------------------------------------------
+namespace {
+// element matrices of trimmed elements (their own rules) replace the tensor-rule ones in a chunk's Ke / fe
+__global__ void put_trimmed_kernel(long long n2, long long m, const int32_t* __restrict__ elem, long long eb,
+                                   const double* __restrict__ src, double* __restrict__ dst) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n2 * m) return;
+  const long long k = idx / n2, r = idx - k * n2;
+  dst[(elem[k] - eb) * n2 + r] = src[idx];
+}
+}  // namespace
+
+igab_status igab_global_assemble(igab_patch* p, int kind, const double* D, double fconst, const int* nq1,
+                                 const double* const* xi1d, const double* const* w1d, int64_t nlist,
+                                 const int32_t* elem, const int64_t* offset, const double* xi, const double* w,
+                                 double* values, double* b, igab_memspace space, void* stream_) {
+  if (!p || !nq1 || !xi1d || !w1d || !values || nlist < 0 || (nlist > 0 && (!elem || !offset || !xi || !w))) {
+    set_error("global_assemble: null argument");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  if (kind < 0 || kind > 2) {
+    set_error("global_assemble: unknown kind");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  for (int64_t k = 0; k < nlist; ++k)
+    if (elem[k] < 0 || elem[k] >= p->dev.nelem || (k > 0 && elem[k] <= elem[k - 1]) || offset[k + 1] < offset[k]) {
+      set_error("global_assemble: trimmed-element list must be strictly ascending with valid offsets");
+      return IGAB_INVALID_ARGUMENT;
+    }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int ncomp = kind == IGAB_ASM_ELASTICITY ? p->dev.dim : 1;
+  const long long n = (long long)p->dev.nb * ncomp, n2 = n * n, nelem = p->dev.nelem;
+  int64_t nrows = 0, nnz = 0;
+  igab_status st = csr_pattern(p, ncomp, &nrows, &nnz, nullptr, nullptr, IGAB_HOST, stream);
+  if (st) return st;
+  const long long chunk = std::max(1LL, std::min(nelem, (256LL << 20) / (8 * n2)));
+  double *dK = nullptr, *dF = nullptr, *dV = values, *dB = b, *dKt = nullptr, *dFt = nullptr, *dXi = nullptr, *dW = nullptr;
+  int32_t* dElem = nullptr;
+  int64_t* dOff = nullptr;
+  long long ktCap = 0;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(stream);
+    if (dK) cudaFree(dK);
+    if (dF) cudaFree(dF);
+    if (dKt) cudaFree(dKt);
+    if (dFt) cudaFree(dFt);
+    if (dXi) cudaFree(dXi);
+    if (dW) cudaFree(dW);
+    if (dElem) cudaFree(dElem);
+    if (dOff) cudaFree(dOff);
+    if (space == IGAB_HOST) {
+      if (dV) cudaFree(dV);
+      if (dB) cudaFree(dB);
+    }
+  };
+  cudaError_t e = cudaMalloc(&dK, sizeof(double) * chunk * n2);
+  if (e == cudaSuccess && b) e = cudaMalloc(&dF, sizeof(double) * chunk * n);
+  if (space == IGAB_HOST) {
+    dV = dB = nullptr;
+    if (e == cudaSuccess) e = cudaMalloc(&dV, sizeof(double) * std::max<long long>(1, nnz));
+    if (e == cudaSuccess && b) e = cudaMalloc(&dB, sizeof(double) * std::max<long long>(1, nrows));
+  }
+  if (e == cudaSuccess && nlist > 0) {
+    const long long np = offset[nlist];
+    e = cudaMalloc(&dElem, sizeof(int32_t) * nlist);
+    if (e == cudaSuccess) e = cudaMalloc(&dOff, sizeof(int64_t) * (nlist + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&dXi, sizeof(double) * std::max(1LL, np) * p->dev.dim);
+    if (e == cudaSuccess) e = cudaMalloc(&dW, sizeof(double) * std::max(1LL, np));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dElem, elem, sizeof(int32_t) * nlist, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dOff, offset, sizeof(int64_t) * (nlist + 1), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dXi, xi, sizeof(double) * np * p->dev.dim, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dW, w, sizeof(double) * np, cudaMemcpyHostToDevice, stream);
+  }
+  if (e != cudaSuccess) {
+    st = cuda_fail(e, "global_assemble: device buffers");
+    cleanup();
+    return st;
+  }
+  long long k0 = 0;  // first trimmed list entry not yet consumed
+  for (long long eb = 0; eb < nelem && !st; eb += chunk) {
+    const long long ee = std::min(nelem, eb + chunk);
+    st = igab_assemble(p, kind, D, fconst, eb, ee, nq1, xi1d, w1d, dK, dF, IGAB_DEVICE, stream);
+    long long k1 = k0;
+    while (k1 < nlist && elem[k1] < ee) ++k1;
+    if (!st && k1 > k0) {
+      const long long m = k1 - k0;
+      if (m > ktCap) {
+        cudaStreamSynchronize(stream);
+        if (dKt) cudaFree(dKt);
+        if (dFt) cudaFree(dFt);
+        dKt = dFt = nullptr;
+        e = cudaMalloc(&dKt, sizeof(double) * m * n2);
+        if (e == cudaSuccess && b) e = cudaMalloc(&dFt, sizeof(double) * m * n);
+        if (e != cudaSuccess) st = cuda_fail(e, "global_assemble: trimmed staging");
+        ktCap = m;
+      }
+      // offsets are absolute indices into xi / w, so a sub-list is the same arrays with shifted elem / offset pointers
+      if (!st) st = igab_assemble_points(p, kind, D, fconst, m, dElem + k0, dOff + k0, dXi, dW, dKt, dFt, IGAB_DEVICE, stream);
+      if (!st) {
+        put_trimmed_kernel<<<(unsigned)((m * n2 + 255) / 256), 256, 0, stream>>>(n2, m, dElem + k0, eb, dKt, dK);
+        if (b) put_trimmed_kernel<<<(unsigned)((m * n + 255) / 256), 256, 0, stream>>>(n, m, dElem + k0, eb, dFt, dF);
+        count_launch(b ? 2 : 1);
+        if ((e = cudaGetLastError()) != cudaSuccess) st = cuda_fail(e, "global_assemble: put_trimmed");
+      }
+    }
+    k0 = k1;
+    if (!st) st = csr_assemble(p, ncomp, eb, ee, dK, nullptr, dV, eb > 0, IGAB_DEVICE, stream);
+    if (!st && b) st = rhs_assemble(p, ncomp, eb, ee, dF, dB, eb > 0, IGAB_DEVICE, stream);
+  }
+  if (!st && space == IGAB_HOST) {
+    e = cudaMemcpyAsync(values, dV, sizeof(double) * nnz, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && b) e = cudaMemcpyAsync(b, dB, sizeof(double) * nrows, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) st = cuda_fail(e, "global_assemble: D2H");
+  }
+  cleanup();
+  return st;
+}
+
 // ---- reductions -----------------------------------------------------------------------------------------------------
 typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 static nccl_allreduce_fn resolve_nccl_allreduce() {

@@ -565,4 +565,67 @@ private:
   std::shared_ptr<const Patch<dim, dimworld>> p_;
 };
 
+// ---- globalAssembler (dune/python/test/poisson.py:84-127), vectorised: the whole loop over elements, quadrature points
+//      and local DOF pairs is one device pass; what comes back is the CSR matrix and the load vector -----------------------
+struct CsrMatrix {
+  int64_t rows = 0;
+  std::vector<int64_t> rowptr;
+  std::vector<int32_t> colidx;
+  std::vector<double> values;
+};
+
+// own quadrature of the trimmed elements (NURBSGridEntity::getQuadratureRule, fillquadraturerule.hh:8-19):
+// element elem[k] carries the points offset[k] .. offset[k+1] of xi [npts][2] (element-local) with weights w
+struct TrimmedRules {
+  std::vector<int32_t> elem;     // strictly ascending
+  std::vector<int64_t> offset;   // elem.size() + 1 entries
+  std::vector<double> xi, w;
+};
+
+template <int dim, int dimworld>
+class GlobalAssembler {
+public:
+  // kind: IGAB_ASM_POISSON / IGAB_ASM_MASS (scalar basis) or IGAB_ASM_ELASTICITY (power basis, flat-interleaved)
+  GlobalAssembler(std::shared_ptr<const Patch<dim, dimworld>> p, int kind)
+      : p_(std::move(p)), kind_(kind), ncomp_(kind == IGAB_ASM_ELASTICITY ? dim : 1) {
+    int64_t nnz = 0;
+    check(igab_csr_pattern(p_->handle(), ncomp_, &A_.rows, &nnz, nullptr, nullptr, IGAB_HOST, nullptr));
+    A_.rowptr.resize((size_t)A_.rows + 1);
+    A_.colidx.resize((size_t)nnz);
+    A_.values.assign((size_t)nnz, 0.0);
+    check(igab_csr_pattern(p_->handle(), ncomp_, &A_.rows, &nnz, A_.rowptr.data(), A_.colidx.data(), IGAB_HOST, nullptr));
+  }
+  // A and b from the rule (xi, w per direction); D: the material matrix of elasticity (3x3 / 6x6, Voigt) or nullptr;
+  // f: the constant source of poisson.py:79
+  void assemble(const std::array<std::vector<double>, dim>& xi, const std::array<std::vector<double>, dim>& w,
+                const double* D = nullptr, double f = 1.0, const TrimmedRules* trimmed = nullptr) {
+    std::array<int, dim> nq1;
+    std::array<const double*, dim> xp, wp;
+    for (int i = 0; i < dim; ++i) {
+      nq1[i] = (int)xi[i].size();
+      xp[i] = xi[i].data();
+      wp[i] = w[i].data();
+    }
+    b_.assign((size_t)A_.rows, 0.0);
+    const int64_t nl = trimmed ? (int64_t)trimmed->elem.size() : 0;
+    check(igab_global_assemble(p_->handle(), kind_, D, f, nq1.data(), xp.data(), wp.data(), nl,
+                               nl ? trimmed->elem.data() : nullptr, nl ? trimmed->offset.data() : nullptr,
+                               nl ? trimmed->xi.data() : nullptr, nl ? trimmed->w.data() : nullptr, A_.values.data(),
+                               b_.data(), IGAB_HOST, nullptr));
+  }
+  // rows of the marked DOFs become identity rows, b = g there (poisson.py:91-93,117-119)
+  void applyDirichlet(const std::vector<uint8_t>& mask, const std::vector<double>* g = nullptr) {
+    check(igab_csr_dirichlet(p_->handle(), ncomp_, mask.data(), g ? g->data() : nullptr, A_.values.data(), b_.data(),
+                             IGAB_HOST, nullptr));
+  }
+  const CsrMatrix& matrix() const { return A_; }
+  const std::vector<double>& rhs() const { return b_; }
+
+private:
+  std::shared_ptr<const Patch<dim, dimworld>> p_;
+  int kind_, ncomp_;
+  CsrMatrix A_;
+  std::vector<double> b_;
+};
+
 }  // namespace igab

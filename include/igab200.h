@@ -238,6 +238,17 @@ igab_status igab_rhs_assemble(igab_patch* p, int ncomp, int64_t elem_begin, int6
 igab_status igab_csr_dirichlet(igab_patch* p, int ncomp, const uint8_t* mask, const double* g, double* values, double* b,
                                igab_memspace space, void* stream);
 
+/* The whole globalAssembler of dune/python/test/poisson.py:84-127 in ONE call: element matrices (igab_assemble) in
+ * device-resident chunks, the trimmed elements' matrices from their own rules (igab_assemble_points; nlist may be 0)
+ * put into their slots, CSR gather and load-vector gather per chunk -- the element matrices never leave the device.
+ * values [nnz] (pattern of igab_csr_pattern with ncomp = 1, or dim for IGAB_ASM_ELASTICITY) and b [nrows] (or NULL)
+ * live in `space`; the rule, D and the trimmed lists (elem strictly ascending, offset absolute into xi / w) are HOST.
+ * Dirichlet rows are applied afterwards with igab_csr_dirichlet, as the reference does inside its loop.            */
+igab_status igab_global_assemble(igab_patch* p, int kind, const double* D, double fconst, const int* nq1,
+                                 const double* const* xi1d, const double* const* w1d, int64_t nlist,
+                                 const int32_t* elem, const int64_t* offset, const double* xi, const double* w,
+                                 double* values, double* b, igab_memspace space, void* stream);
+
 /* ---- patch reductions ---------------------------------------------------------------------------------------------
  * Replaces the user loop summing NURBSGeometry::volume() over elements (nurbsgeometry.hh:96-113,
  * dune/iga/test/gridtests.cpp:338-341): result = sum_{e in range} sum_q detJ w.  Deterministic two-level tree sum.

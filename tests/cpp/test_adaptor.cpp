@@ -88,6 +88,8 @@ int main() {
   // the loop of poisson.py:37-127, written against the adaptor
   igab::LocalView<dim, dw> localView(patch);
   double area = 0;
+  const std::size_t nd = (std::size_t)patch->numDofs();
+  std::vector<double> Aglob(nd * nd, 0.0), bglob(nd, 0.0);  // the scatter of poisson.py:113-125, dense for the check
   for (int64_t e = 0; e < patch->size0(); ++e) {
     localView.bind(e);
     const auto& localBasis = localView.localBasis();
@@ -136,7 +138,37 @@ int main() {
       CHECK(close(localB[i], ofe[e * nb + i], 1.0), "fe");
       for (std::size_t j = 0; j < n; ++j) CHECK(close(localA[i * n + j], oKe[(e * nb + i) * nb + j], 10.0), "Ke");
     }
+    for (std::size_t i = 0; i < n; ++i) {
+      bglob[(std::size_t)localView.index(i)] += localB[i];
+      for (std::size_t j = 0; j < n; ++j)
+        Aglob[(std::size_t)localView.index(i) * nd + (std::size_t)localView.index(j)] += localA[i * n + j];
+    }
     area += geo.volume();
+  }
+  {  // the same system from the vectorised globalAssembler: one device pass, CSR back
+    igab::GlobalAssembler<dim, dw> assembler(patch, IGAB_ASM_POISSON);
+    assembler.assemble(xi, w, nullptr, 1.0);
+    const igab::CsrMatrix& A = assembler.matrix();
+    CHECK(A.rows == (int64_t)nd, "global rows %ld", (long)A.rows);
+    std::vector<double> dense(nd * nd, 0.0);
+    for (int64_t r = 0; r < A.rows; ++r)
+      for (int64_t k = A.rowptr[r]; k < A.rowptr[r + 1]; ++k) dense[(std::size_t)r * nd + A.colidx[k]] += A.values[k];
+    double amax = 0;
+    for (double v : Aglob) amax = std::fmax(amax, std::fabs(v));
+    for (std::size_t k = 0; k < nd * nd; ++k) CHECK(close(dense[k], Aglob[k], amax), "global A entry %zu: %g vs %g", k, dense[k], Aglob[k]);
+    for (std::size_t k = 0; k < nd; ++k) CHECK(close(assembler.rhs()[k], bglob[k], 1.0), "global b entry %zu", k);
+    // Dirichlet rows as poisson.py:117-119: identity row, b = g
+    std::vector<uint8_t> mask(nd, 0);
+    std::vector<double> g(nd, 7.0);
+    mask[0] = mask[nd - 1] = 1;
+    assembler.applyDirichlet(mask, &g);
+    const igab::CsrMatrix& AD = assembler.matrix();
+    for (int64_t r : {(int64_t)0, (int64_t)nd - 1}) {
+      for (int64_t k = AD.rowptr[r]; k < AD.rowptr[r + 1]; ++k)
+        CHECK(AD.values[k] == (AD.colidx[k] == r ? 1.0 : 0.0), "dirichlet row %ld", (long)r);
+      CHECK(assembler.rhs()[(std::size_t)r] == 7.0, "dirichlet rhs");
+    }
+    CHECK(close(assembler.rhs()[1], bglob[1], 1.0), "untouched rhs");
   }
   CHECK(std::fabs(area - patch->volume()) < 1e-13, "volume sum %g vs reduction %g", area, patch->volume());
   CHECK(std::fabs(area - (16.0 - M_PI / 4.0)) < 2e-2, "area %g", area);  // coarse 2-element patch, 3x3 Gauss

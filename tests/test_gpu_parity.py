@@ -1228,6 +1228,12 @@ def test_trimmed_patch_poisson_end_to_end():
     assert abs(Ad - Ar).max() <= 1e-12 * abs(Ar).max()
     bd = P.rhsAssemble(fall)
     assert bd.shape == (ndof,) and np.abs(bd - br).max() <= 1e-12 * np.abs(br).max()
+    # ... and the whole thing in ONE call, trimmed rules included
+    vg, bg = P.globalAssemble(capi.ASM_POISSON, [x, x], [wg, wg], fconst=1.0,
+                              trimmed=(np.array(trimmed, np.int32), off, xi, w))
+    assert np.abs(vg - vals).max() <= 1e-14 * np.abs(vals).max() and np.abs(bg - bd).max() <= 1e-14 * np.abs(bd).max()
+    with pytest.raises(capi.IgabError):  # the trimmed list must be ascending
+        P.globalAssemble(capi.ASM_POISSON, [x, x], [wg, wg], trimmed=(np.array(trimmed[::-1], np.int32), off, xi, w))
     # two element ranges accumulated give the same matrix
     v2 = P.csrAssemble(Kall[:7], elem_end=7)
     v2 = P.csrAssemble(Kall[7:], elem_begin=7, values=v2, accumulate=True)
@@ -1243,6 +1249,30 @@ def test_trimmed_patch_poisson_end_to_end():
         assert np.array_equal(AD[r], e) and bD[r] == 2.5
     keep = np.setdiff1d(np.arange(ndof), [0, ndof - 1])
     assert np.array_equal(AD[keep], Ad.toarray()[keep]) and np.array_equal(bD[keep], bd[keep])
+
+
+@pytest.mark.parametrize("name,kind", [("plate_hole_p2", capi.ASM_POISSON), ("cylinder_p3", capi.ASM_MASS),
+                                       ("plate_hole_p2", capi.ASM_ELASTICITY), ("cylinder_p4", capi.ASM_POISSON)])
+def test_global_assemble_one_call_matches_the_stepwise_path(name, kind):
+    """igab_global_assemble (the whole globalAssembler in one call, element matrices kept on the device in chunks)
+    against element matrices -> csrAssemble -> rhsAssemble, host and device outputs."""
+    spec = PFT.small_patch(name)
+    P = gpu_patch(spec)
+    dim = len(spec["degree"])
+    rule = [PD.gaussLegendre01(p + 1) for p in spec["degree"]]
+    xi, w = [r[0] for r in rule], [r[1] for r in rule]
+    ncomp = dim if kind == capi.ASM_ELASTICITY else 1
+    ns = 3 if dim == 2 else 6
+    D = np.eye(ns) + 0.1 if kind == capi.ASM_ELASTICITY else None
+    Ke, fe = P.assemble(kind, xi, w, D=D, fconst=0.7)
+    vref = P.csrAssemble(Ke, ncomp)
+    bref = P.rhsAssemble(fe, ncomp)
+    v, b = P.globalAssemble(kind, xi, w, D=D, fconst=0.7)
+    assert np.abs(v - vref).max() <= 1e-14 * np.abs(vref).max() and np.abs(b - bref).max() <= 1e-14 * np.abs(bref).max()
+    vd, bd = P.globalAssemble(kind, xi, w, D=D, fconst=0.7, device=True)
+    assert np.array_equal(vd.cpu().numpy(), v) and np.array_equal(bd.cpu().numpy(), b)
+    v2, b2 = P.globalAssemble(kind, xi, w, D=D, fconst=0.7, want_b=False)
+    assert b2 is None and np.array_equal(v2, v)
 
 
 def test_trimmed_csr_pattern_random_flags_3d_and_vector_valued():
