@@ -199,16 +199,59 @@ def bench_assembly(args, rank, world, local, barrier, dist):
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    launches = int(capi.launch_count() - l0)
     nel = 64 ** 3 * world * npass
     flops_el = 125 * (2 * 3 * n * n + 2 * 9 * n)  # nq (2 s n^2 + 2 s^2 n)
     exec_el = 3360 * 512 + 5 * 400 * 55  # DMMA instructions x 512 flop + stage-1 FMAs of gram_sf_kernel<4,5>
     dmma, dfma, src = measured_fp64_peak() if rank == 0 else (37.0, 34.0, "")
     achieved = flops_el * nel / world / (ms * 1e-3) / 1e12  # per GPU
     del ring
+    # end to end through the reference-facing call: host patch (handle creation = control-net H2D), igab_global_assemble
+    # (element matrices in device chunks, CSR gather), CSR values + load vector back to host memory
+    asm_e2e = None
+    if not args.no_e2e:
+        k_layers = 16  # 64 x 64 x 16 elements per e2e step
+        sub = PD.thickCylinder(p, (lev, lev, 4))
+        Ps = capi.Patch.fromPatchData(sub)
+        rp, _ = Ps.csrPattern()
+        v, bb = capi.pinned_empty(int(rp[-1])), capi.pinned_empty(len(rp) - 1)  # page-locked host outputs
+        Ps.globalAssemble(capi.ASM_POISSON, xi, ww, out=(v, bb))  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            Ps.updateControlPoints(sub.cp)
+            Ps.globalAssemble(capi.ASM_POISSON, xi, ww, out=(v, bb))
+        dt = (time.perf_counter() - t0) / reps
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        asm_e2e = {"value": Ps.nelem * world / dt, "unit": "elements/s", "h2d_bytes_per_step": int(sub.cp.nbytes),
+                   "d2h_bytes_per_step": int(v.nbytes + bb.nbytes),
+                   "sample": "%d elements per rank per step (64 x 64 x %d), control net H2D, igab_global_assemble, CSR "
+                             "values (%d non-zeros) + load vector D2H" % (Ps.nelem, k_layers, v.size)}
+        capi.pinned_free(v)
+        capi.pinned_free(bb)
+        del Ps
+    # CPU beside it (rank 0, N=1): the oracle's plain-loop element matrices (transliteration of poisson.py:37-81), all cores
+    asm_cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import portbind as PT
+        small = PD.thickCylinder(p, (3, 3, 3))
+        Op = PT.PortPatch(small.degree, small.knotSpans, small.cp, 3)
+        ncpu = len(os.sched_getaffinity(0))
+        Op.assemble(0, xi, ww, elem_end=16, nthreads=ncpu)
+        t0 = time.perf_counter()
+        Op.assemble(0, xi, ww, nthreads=ncpu)
+        dt = time.perf_counter() - t0
+        asm_cpu = {"value": Op.nelem / dt, "unit": "elements/s", "cores": ncpu, "kind": "port",
+                   "sample": "8^3-element p=4 patch (512 element matrices, evaluation + plain-loop B^T B), %.1f s wall" % dt}
     return {"metric": "element matrices/sec", "value": nel / (ms * 1e-3), "unit": "elements/s",
             "config": {"workload": "C3: 3-D Poisson stiffness p=4 (n=125), 5^3 Gauss, 64x64x%d elements (64^3 per GPU)"
                                    % (64 * world)},
-            "ms_per_pass": ms / npass, "gpu_launches": int(capi.launch_count() - l0),
+            "ms_per_pass": ms / npass, "gpu_launches": launches, "e2e": asm_e2e, "cpu_baseline": asm_cpu,
             "roofline": {"bound": "tensor", "kernel": "gram_sf_kernel<4,5> (evaluation + sum-factorised Gram contraction, "
                                                       "stages 2 and 3 on the FP64 tensor cores, one kernel)",
                          "achieved": achieved, "peak": dmma, "unit": "TFLOP/s", "frac": achieved / dmma,

@@ -430,7 +430,8 @@ class Patch:
                                        stream))
         return values
 
-    def globalAssemble(self, kind, xi1d, w1d, D=None, fconst=1.0, trimmed=None, want_b=True, device=False, stream=None):
+    def globalAssemble(self, kind, xi1d, w1d, D=None, fconst=1.0, trimmed=None, want_b=True, device=False, stream=None,
+                       out=None):
         """globalAssembler of poisson.py:84-127 in one call: (values [nnz] of csrPattern(ncomp), b [nrows]).  The element
         matrices stay on the device.  trimmed = (elem, offset, xi, w) of the trimmed elements' own rules
         (quadrature.trimmedBatch; elem ascending) or None.  device=True returns CUDA tensors."""
@@ -440,7 +441,9 @@ class Patch:
         ncomp = self.dim if kind == ASM_ELASTICITY else 1
         nr, nnz = C.c_int64(), C.c_int64()
         _check(lib().igab_csr_pattern(self.h, ncomp, C.byref(nr), C.byref(nnz), None, None, HOST, None))
-        if device:
+        if out is not None:  # caller's buffers (e.g. pinned_empty arrays): (values [nnz], b [nrows] or None)
+            values, b = out
+        elif device:
             import torch
             values = torch.empty(nnz.value, dtype=torch.float64, device="cuda")
             b = torch.empty(nr.value, dtype=torch.float64, device="cuda") if want_b else None

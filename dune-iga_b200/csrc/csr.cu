@@ -142,10 +142,10 @@ __global__ void csr_colidx_kernel(CsrGeom G, long long nrows, const long long* _
   }
 }
 
-__global__ void csr_gather_kernel(CsrGeom G, long long nrows, long long elem_begin, long long elem_end,
-                                  const double* __restrict__ Ke, const long long* __restrict__ rowptr,
-                                  double* __restrict__ values, int accumulate) {
-  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+__global__ void csr_gather_kernel(CsrGeom G, long long row_begin, long long nrows, long long elem_begin,
+                                  long long elem_end, const double* __restrict__ Ke,
+                                  const long long* __restrict__ rowptr, double* __restrict__ values, int accumulate) {
+  const long long row = row_begin + (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= nrows) return;
   int gd[kMaxDim], lo[kMaxDim], len[kMaxDim];
@@ -183,15 +183,28 @@ __global__ void csr_gather_kernel(CsrGeom G, long long nrows, long long elem_beg
       }
     }
     double acc = 0.0;
-    for (int f2 = fa[2]; f2 <= fb[2]; ++f2)
-      for (int f1 = fa[1]; f1 <= fb[1]; ++f1)
+    const int nel1 = G.dim > 1 ? G.nel[1] : 1;
+    const double* __restrict__ Kc = Ke + (long long)c * n + d;  // component (c, d) of every (i, j) block
+    for (int f2 = fa[2]; f2 <= fb[2]; ++f2) {
+      const int e2 = G.dim > 2 ? G.elemOfFirst[2][f2] : 0;
+      if (e2 < 0) continue;
+      for (int f1 = fa[1]; f1 <= fb[1]; ++f1) {
+        const int e1 = G.dim > 1 ? G.elemOfFirst[1][f1] : 0;
+        if (e1 < 0) continue;
+        const long long erow = (long long)G.nel[0] * (e1 + (long long)nel1 * e2);
+        // local indices of g and h in an element whose first DOF is (f0, f1, f2): i = i12 + (gd0 - f0), same for j
+        const int i12 = o0 * ((gd[1] - f1) + o1 * (gd[2] - f2)) + gd[0];
+        const int j12 = o0 * ((hd[1] - f1) + o1 * (hd[2] - f2)) + hd[0];
         for (int f0 = fa[0]; f0 <= fb[0]; ++f0) {
-          const long long e = live_element(G, f0, f1, f2);
+          const int e0 = G.elemOfFirst[0][f0];
+          if (e0 < 0) continue;
+          const long long e = erow + e0;
           if (e < elem_begin || e >= elem_end) continue;
-          const int i = (gd[0] - f0) + o0 * ((gd[1] - f1) + o1 * (gd[2] - f2));
-          const int j = (hd[0] - f0) + o0 * ((hd[1] - f1) + o1 * (hd[2] - f2));
-          acc += Ke[(e - elem_begin) * n * n + (long long)(i * G.ncomp + c) * n + (j * G.ncomp + d)];
+          if (G.trim && G.trim[e] == IGAB_TRIM_EMPTY) continue;
+          acc += Kc[(e - elem_begin) * n * n + ((long long)(i12 - f0) * n + (j12 - f0)) * G.ncomp];
         }
+      }
+    }
     if (accumulate)
       values[base + k] += acc;
     else
@@ -423,10 +436,34 @@ igab_status csr_assemble(igab_patch* p, int ncomp, long long eb, long long ee, c
     }
     dK = tK;
   }
-  const long long threads = nrows * 32;
-  csr_gather_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(G, nrows, eb, ee, dK, p->d_csr_rowptr, dV, accumulate);
-  count_launch();
-  cudaError_t e = cudaGetLastError();
+  // only the rows that elements [eb, ee) can touch: the DOF layers g_last in [span(e_min) - p, span(e_max)] of the
+  // slowest direction are one contiguous row range (untrimmed numbering); the other rows are zeroed when not accumulating
+  long long rowBegin = 0, rowEnd = nrows;
+  cudaError_t e = cudaSuccess;
+  if (!p->d_trim && nel > 0) {
+    const PatchDev& D = p->dev;
+    const int dl = D.dim - 1;
+    long long perLayer = 1, dofStride = 1;
+    for (int d = 0; d < dl; ++d) {
+      perLayer *= D.nel[d];
+      dofStride *= D.ncp[d];
+    }
+    const int eLo = (int)(eb / perLayer), eHi = (int)((ee - 1) / perLayer);
+    rowBegin = (long long)(p->hspan[dl][eLo] - D.degree[dl]) * dofStride * ncomp;
+    rowEnd = (long long)(p->hspan[dl][eHi] + 1) * dofStride * ncomp;
+    if (!accumulate && (rowBegin > 0 || rowEnd < nrows)) {
+      const long long zb = p->csr_rowptr_host[rowBegin], ze = p->csr_rowptr_host[rowEnd];
+      if (zb > 0) e = cudaMemsetAsync(dV, 0, sizeof(double) * zb, stream);
+      if (e == cudaSuccess && ze < nnz) e = cudaMemsetAsync(dV + ze, 0, sizeof(double) * (nnz - ze), stream);
+    }
+  }
+  if (e == cudaSuccess && rowEnd > rowBegin) {
+    const long long threads = (rowEnd - rowBegin) * 32;
+    csr_gather_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(G, rowBegin, rowEnd, eb, ee, dK, p->d_csr_rowptr,
+                                                                            dV, accumulate);
+    count_launch();
+    e = cudaGetLastError();
+  }
   if (space == IGAB_HOST) {
     if (e == cudaSuccess) e = cudaMemcpyAsync(values, dV, sizeof(double) * nnz, cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);

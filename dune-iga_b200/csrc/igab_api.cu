@@ -1172,7 +1172,7 @@ igab_status igab_global_assemble(igab_patch* p, int kind, const double* D, doubl
   int64_t nrows = 0, nnz = 0;
   igab_status st = csr_pattern(p, ncomp, &nrows, &nnz, nullptr, nullptr, IGAB_HOST, stream);
   if (st) return st;
-  const long long chunk = std::max(1LL, std::min(nelem, (256LL << 20) / (8 * n2)));
+  const long long chunk = std::max(1LL, std::min(nelem, (1024LL << 20) / (8 * n2)));  // <= 1 GB of element matrices
   double *dK = nullptr, *dF = nullptr, *dV = values, *dB = b, *dKt = nullptr, *dFt = nullptr, *dXi = nullptr, *dW = nullptr;
   int32_t* dElem = nullptr;
   int64_t* dOff = nullptr;
