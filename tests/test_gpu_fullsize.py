@@ -161,3 +161,78 @@ def test_general_assembly_path_beyond_65535_elements():
     for e in (0, 65535, 65536, nel - 1):
         Kref, _ = Pp.assemble(capi.ASM_POISSON, [x, x], [w, w], elem_begin=e, elem_end=e + 1, want_fe=False)
         assert np.abs(Ke[e] - Kref[0]).max() <= 1e-12 * np.abs(Kref).max()
+
+
+def test_c3_full_size_element_matrices(monkeypatch):
+    """Config C3 at full size (p = 4, 64^3 elements, 5^3 Gauss): element matrices of whole k-slabs checked on the device
+    through properties that do not need the oracle -- symmetry, constants in the kernel of the stiffness matrix (row sums
+    0), positive diagonal, sum of all mass-matrix entries == patch volume in closed form, rigid translations in the
+    kernel of the elasticity matrix, bitwise reproducibility -- then the sum-factorised contraction against the dense
+    Gram kernel on a whole chunk, and a random sample of elements against the oracle."""
+    import torch
+    p, lev = 4, 6
+    pd = PD.thickCylinder(p, (lev, lev, lev))
+    P = capi.Patch.fromPatchData(pd)
+    assert P.nelem == 64 ** 3 and P.nb == 125
+    x1, w1 = Q.gaussLegendre01(5)
+    xi, w = [x1] * 3, [w1] * 3
+    nel = 64 * 64 * 2  # two k-layers per call: 1.02 GB of element matrices
+    K = torch.empty((nel, 125, 125), dtype=torch.float64, device="cuda")
+    F = torch.empty((nel, 125), dtype=torch.float64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    Pp = PT.PortPatch(pd.degree, pd.knotSpans, pd.cp, 3)
+    rng = np.random.default_rng(3)
+    vol = 0.0
+    for k0 in range(0, 64, 2):
+        eb = 64 * 64 * k0
+        P.assemble(capi.ASM_MASS, xi, w, elem_begin=eb, elem_end=eb + nel, Ke=K, fe=None, stream=s)
+        vol += float(K.sum())
+        if k0 in (0, 30, 62):
+            assert float((K - K.transpose(1, 2)).abs().max()) <= 1e-13 * float(K.abs().max())
+            assert float(K.min()) > 0                     # products of positive rational functions
+    assert abs(vol - np.pi / 4 * (2.0 ** 2 - 1.0 ** 2) * 3.0) <= 1e-11 * vol   # sum_ij M_ij = int 1 = volume of the solid
+    for k0 in (0, 30, 62):
+        eb = 64 * 64 * k0
+        P.assemble(capi.ASM_POISSON, xi, w, fconst=1.0, elem_begin=eb, elem_end=eb + nel, Ke=K, fe=F, stream=s)
+        torch.cuda.synchronize()
+        amax = float(K.abs().max())
+        assert float((K - K.transpose(1, 2)).abs().max()) <= 1e-12 * amax
+        assert float(K.sum(2).abs().max()) <= 1e-11 * amax          # grad of the constant function is 0
+        assert float(torch.diagonal(K, dim1=1, dim2=2).min()) > 0
+        ref = K.clone()
+        P.assemble(capi.ASM_POISSON, xi, w, fconst=1.0, elem_begin=eb, elem_end=eb + nel, Ke=K, fe=F, stream=s)
+        torch.cuda.synchronize()
+        assert torch.equal(ref, K)                                   # bitwise reproducible
+        # the dense-Gram kernel on the same chunk (a different algorithm, same numbers)
+        monkeypatch.setenv("IGAB_GRAM_SF", "0")
+        P.assemble(capi.ASM_POISSON, xi, w, fconst=1.0, elem_begin=eb, elem_end=eb + nel, Ke=K, fe=None, stream=s)
+        monkeypatch.delenv("IGAB_GRAM_SF")
+        torch.cuda.synchronize()
+        assert float((K - ref).abs().max()) <= 1e-12 * amax
+        for e in rng.integers(eb, eb + nel, 3):
+            Ko, fo = Pp.assemble(capi.ASM_POISSON, xi, w, fconst=1.0, elem_begin=int(e), elem_end=int(e) + 1)
+            assert relerr(ref[int(e) - eb].cpu().numpy(), Ko[0]) <= TOL
+            assert relerr(F[int(e) - eb].cpu().numpy(), fo[0]) <= TOL
+    # elasticity (n = 375): a chunk of one quarter k-layer, symmetric material
+    lam, mu = 0.3 / (1.3 * 0.4), 1 / 2.6
+    D = np.zeros((6, 6))
+    D[:3, :3] = lam
+    D[np.arange(3), np.arange(3)] = lam + 2 * mu
+    D[np.arange(3, 6), np.arange(3, 6)] = mu
+    ne = 1024
+    KE = torch.empty((ne, 375, 375), dtype=torch.float64, device="cuda")
+    eb = 64 * 64 * 31 + 517
+    P.assemble(capi.ASM_ELASTICITY, xi, w, D=D, elem_begin=eb, elem_end=eb + ne, Ke=KE, fe=None, stream=s)
+    torch.cuda.synchronize()
+    amax = float(KE.abs().max())
+    assert float((KE - KE.transpose(1, 2)).abs().max()) <= 1e-12 * amax
+    for c in range(3):                                               # rigid translations produce no strain
+        t = torch.zeros(375, dtype=torch.float64, device="cuda")
+        t[c::3] = 1.0
+        assert float((KE @ t).abs().max()) <= 1e-11 * amax
+    ref = KE.clone()
+    monkeypatch.setenv("IGAB_ELAS_SF", "0")
+    P.assemble(capi.ASM_ELASTICITY, xi, w, D=D, elem_begin=eb, elem_end=eb + ne, Ke=KE, fe=None, stream=s)
+    monkeypatch.delenv("IGAB_ELAS_SF")
+    torch.cuda.synchronize()
+    assert float((KE - ref).abs().max()) <= 1e-12 * amax
