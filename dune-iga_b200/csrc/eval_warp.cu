@@ -134,7 +134,12 @@ __global__ void __launch_bounds__(128)
       double* t = sT + L.tabOff[d];
       for (int j = lane; j < len; j += 32) t[j] = __ldg(g + j);
     }
-    // ---- 2. control points of the span, homogeneous
+    // ---- 2. control points of the span, homogeneous and RELATIVE to the span's first control point: the sums of
+    //         step 3 then carry magnitudes of the element's size instead of the patch's, which keeps the cancellation
+    //         in the quotient rule (S_a - W_a x) harmless on strongly refined patches; x gets the offset back
+    double pref[DW];
+#pragma unroll
+    for (int k = 0; k < DW; ++k) pref[k] = __ldg(P.cp + cpBase * C1 + k);
     for (int i = lane; i < nb; i += 32) {
       const unsigned pk = pack[i];
       long long g = cpBase + (long long)(pk & 255u) * cpStride[0];
@@ -143,7 +148,7 @@ __global__ void __launch_bounds__(128)
       const double* c = P.cp + g * C1;
       const double w = c[DW];
 #pragma unroll
-      for (int k = 0; k < DW; ++k) sC[i * C1 + k] = c[k] * w;
+      for (int k = 0; k < DW; ++k) sC[i * C1 + k] = (c[k] - pref[k]) * w;
       sC[i * C1 + DW] = w;
       sW[i] = w;
     }
@@ -211,10 +216,10 @@ __global__ void __launch_bounds__(128)
         const long long pt = pt0 + qb + lane;
         double X[DW];
 #pragma unroll
-        for (int c = 0; c < DW; ++c) X[c] = G[0][c] * inv;
+        for (int c = 0; c < DW; ++c) X[c] = __dmul_rn(G[0][c], inv);  // no FMA contraction: same bits for every order
         if (out.x)
 #pragma unroll
-          for (int c = 0; c < DW; ++c) out.x[pt * DW + c] = X[c];
+          for (int c = 0; c < DW; ++c) out.x[pt * DW + c] = __dadd_rn(X[c], pref[c]);  // X stays relative below
         if constexpr (ORDER >= 1) {
           double J[DIM][DW];
 #pragma unroll

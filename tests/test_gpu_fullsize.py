@@ -236,3 +236,54 @@ def test_c3_full_size_element_matrices(monkeypatch):
     monkeypatch.delenv("IGAB_ELAS_SF")
     torch.cuda.synchronize()
     assert float((KE - ref).abs().max()) <= 1e-12 * amax
+
+
+@pytest.mark.parametrize("case", [(2, 2, (4, 5), (6, 5), (7, 6)), (3, 3, (3, 2, 4), (4, 3, 5), (5, 4, 3)),
+                                  (2, 3, (5, 4), (7, 7), (7, 7))],
+                         ids=lambda c: "d%dw%d_p%s" % (c[0], c[1], "".join(map(str, c[2]))))
+def test_warp_per_element_kernel_many_elements(case):
+    """The general warp-per-element kernel with far more elements than resident warps (grid-stride loop, chunk tails,
+    mixed degrees, second derivatives): every field against the thread-per-point kernel on the device, a random sample
+    of elements against the oracle."""
+    import torch
+    dim, dw, degree, nq1, lev = case
+    if dim == 2 and dw == 2:
+        pd = PD.plateWithHole(0, 0)
+        for d, p in enumerate(degree):
+            pd = pd.degreeElevate(d, p - 2)
+    elif dim == 2:
+        pd = PD.torusSurface(0)
+        for d, p in enumerate(degree):
+            pd = pd.degreeElevate(d, p - 2)
+    else:
+        pd = PD.thickCylinder(2)
+        for d, p in enumerate(degree):
+            pd = pd.degreeElevate(d, p - 2)
+    for d in range(dim):
+        pd = pd.globalRefineInDirection(d, lev[d])
+    P = capi.Patch.fromPatchData(pd)
+    assert P.nelem > 148 * 5 * 4
+    xi = [Q.gaussLegendre01(q)[0] for q in nq1]
+    fields = ("N", "dN", "d2N", "x", "Jt", "H", "detJ")
+    npts = P.nelem * int(np.prod(nq1))
+    s = torch.cuda.current_stream().cuda_stream
+    outs = {}
+    for mode in (capi.KERNEL_WARP, capi.KERNEL_GENERIC):
+        P.setKernel(mode)
+        outs[mode] = dev_out(P, npts, fields)
+        P.evalTensor(xi, order=2, want=fields, out=outs[mode], stream=s)
+    torch.cuda.synchronize()
+    for f in fields:
+        a, b = outs[capi.KERNEL_WARP][f], outs[capi.KERNEL_GENERIC][f]
+        assert float((a - b).abs().max()) <= 1e-12 * max(1.0, float(b.abs().max())), f
+    assert float((outs[capi.KERNEL_WARP]["N"].sum(1) - 1).abs().max()) < 1e-13
+    Pp = PT.PortPatch(pd.degree, pd.knotSpans, pd.cp, dw)
+    nq = int(np.prod(nq1))
+    for e in np.random.default_rng(5).integers(0, P.nelem, 5):
+        o = Pp.eval_tensor(xi, order=2, elem_begin=int(e), elem_end=int(e) + 1, want=fields)
+        for f in fields:
+            # second derivatives of a degree-5 basis on 2^-7 spans are second differences over tiny knot intervals: two
+            # correct FP64 algorithms (the oracle's sums of R'' P and the kernel's homogeneous quotient rule) agree to
+            # ~ eps (p / h)^2 h^2 / |H|, a few 1e-12 here -- 1e-11 for the order-2 fields, 1e-12 for everything else
+            tol = 1e-11 if f in ("d2N", "H") else TOL
+            assert relerr(outs[capi.KERNEL_WARP][f][int(e) * nq:(int(e) + 1) * nq].cpu().numpy(), o[f]) <= tol, (f, int(e))
