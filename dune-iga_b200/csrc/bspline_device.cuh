@@ -8,6 +8,32 @@ namespace igab {
 
 constexpr int kPM = kMaxOrder1D;  // 9: row length of every univariate work array
 
+__device__ __forceinline__ bool feq8(double a, double b) {
+  // Dune::FloatCmp::eq default (relativeWeak, 8 eps) -- bsplinealgorithms.hh:104-108
+  const double eps = 8.0 * 2.220446049250313e-16;
+  return fabs(a - b) <= eps * fmax(fabs(a), fabs(b));
+}
+
+// A2.2 with the reference's clamp and end-point early exits
+__device__ inline void basis1d(double u, const double* __restrict__ U, int n, int p, int sp, double* N) {
+  for (int i = 0; i <= p; ++i) N[i] = 0.0;
+  u = fmin(fmax(u, U[0]), U[n - 1]);
+  if (feq8(u, U[n - 1])) { N[p] = 1.0; return; }
+  if (feq8(u, U[0])) { N[0] = 1.0; return; }
+  N[0] = 1.0;
+  for (int j = 0; j < p; ++j) {
+    double saved = 0.0;
+    for (int r = 0; r <= j; ++r) {
+      const double rD = U[sp + 1 + r] - u;
+      const double lD = u - U[sp - (j - r)];
+      const double tmp = N[r] / (rD + lD);
+      N[r] = saved + rD * tmp;
+      saved = lD * tmp;
+    }
+    N[j + 1] = saved;
+  }
+}
+
 // values + derivatives 0..K of the p+1 non-zero B-splines of span sp at u.  dN[k*kPM + j].  K may exceed p (rows = 0).
 __device__ inline void ders1d_any(double u, const double* __restrict__ U, int p, int sp, int K, double* dN) {
   double left[kPM], right[kPM], ndu[kPM][kPM], a[2][kPM];

@@ -22,32 +22,6 @@ namespace {
 
 constexpr int PM = kPM;  // 9
 
-__device__ __forceinline__ bool feq8(double a, double b) {
-  // Dune::FloatCmp::eq default (relativeWeak, 8 eps) -- bsplinealgorithms.hh:104-108
-  const double eps = 8.0 * 2.220446049250313e-16;
-  return fabs(a - b) <= eps * fmax(fabs(a), fabs(b));
-}
-
-// A2.2 with the reference's clamp and end-point early exits
-__device__ void basis1d(double u, const double* __restrict__ U, int n, int p, int sp, double* N) {
-  for (int i = 0; i <= p; ++i) N[i] = 0.0;
-  u = fmin(fmax(u, U[0]), U[n - 1]);
-  if (feq8(u, U[n - 1])) { N[p] = 1.0; return; }
-  if (feq8(u, U[0])) { N[0] = 1.0; return; }
-  N[0] = 1.0;
-  for (int j = 0; j < p; ++j) {
-    double saved = 0.0;
-    for (int r = 0; r <= j; ++r) {
-      const double rD = U[sp + 1 + r] - u;
-      const double lD = u - U[sp - (j - r)];
-      const double tmp = N[r] / (rD + lD);
-      N[r] = saved + rD * tmp;
-      saved = lD * tmp;
-    }
-    N[j + 1] = saved;
-  }
-}
-
 // A2.3, rows 0..K (K <= 2 here), dN[k][PM]
 template <int K>
 __device__ void ders1d(double u, const double* __restrict__ U, int p, int sp, double (*dN)[PM]) {

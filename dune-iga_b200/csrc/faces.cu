@@ -113,7 +113,10 @@ igab_status eval_faces_device(igab_patch* p, long long nfaces, const int* elem, 
   if (p->kernel_mode != IGAB_KERNEL_GENERIC && eval_points_2d_supported(D))
     st = launch_eval_points_2d(D, src, npts, 1, o, stream);
   else
-    st = launch_eval_generic(D, src, npts, 1, o, stream);
+  {
+    st = launch_eval_warp(D, src, npts, 1, o, stream);  // warp per 32 face points
+    if (st == IGAB_UNSUPPORTED) st = launch_eval_generic(D, src, npts, 1, o, stream);
+  }
   if (!st && (normal || dS)) {
     if (D.dim == 2 && D.dw == 2)
       face_normals_kernel<2, 2><<<blocks, th, 0, stream>>>(npts, nqf, face, d_Jt, normal, dS);

@@ -303,6 +303,18 @@ static igab_status run_eval_tensor_device(igab_patch* p, long long eb, long long
   return IGAB_OK;
 }
 
+// point lists: tuned 2-D list kernel (p <= 3), else the warp-per-32-points kernel, else thread per point
+static igab_status run_eval_points_device(igab_patch* p, const PointSource& src, long long npts, int order,
+                                          const EvalOutDev& out, cudaStream_t stream) {
+  const bool tuned = p->kernel_mode == IGAB_KERNEL_AUTO || p->kernel_mode == IGAB_KERNEL_TENSOR;
+  if (tuned && eval_points_2d_supported(p->dev)) return launch_eval_points_2d(p->dev, src, npts, order, out, stream);
+  if (p->kernel_mode != IGAB_KERNEL_GENERIC) {
+    const igab_status st = launch_eval_warp(p->dev, src, npts, order, out, stream);
+    if (st != IGAB_UNSUPPORTED) return st;
+  }
+  return launch_eval_generic(p->dev, src, npts, order, out, stream);
+}
+
 }  // namespace igab
 
 using namespace igab;
@@ -644,9 +656,7 @@ igab_status igab_eval_points(igab_patch* p, int64_t npts, const int32_t* elem, c
   if (space == IGAB_DEVICE) {
     src.elem = elem;
     src.xi = xi;
-    if (p->kernel_mode != IGAB_KERNEL_GENERIC && eval_points_2d_supported(p->dev))
-      return launch_eval_points_2d(p->dev, src, npts, deriv_order, to_dev(eff), stream);
-    return launch_eval_generic(p->dev, src, npts, deriv_order, to_dev(eff), stream);
+    return run_eval_points_device(p, src, npts, deriv_order, to_dev(eff), stream);
   }
   for (long long k = 0; k < npts; ++k)
     if (elem[k] < 0 || elem[k] >= p->dev.nelem) {
@@ -670,10 +680,7 @@ igab_status igab_eval_points(igab_patch* p, int64_t npts, const int32_t* elem, c
     src.xi = d_xi;
     igab_eval_out dv{};
     for (int k = 0; k < 8; ++k) *out_field(&dv, k) = dbuf[k];
-    if (p->kernel_mode != IGAB_KERNEL_GENERIC && eval_points_2d_supported(p->dev))
-      st = launch_eval_points_2d(p->dev, src, npts, deriv_order, to_dev(dv), stream);
-    else
-      st = launch_eval_generic(p->dev, src, npts, deriv_order, to_dev(dv), stream);
+    st = run_eval_points_device(p, src, npts, deriv_order, to_dev(dv), stream);
   }
   for (int k = 0; k < 8 && !st; ++k)
     if (dbuf[k]) {

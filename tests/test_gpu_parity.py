@@ -126,6 +126,38 @@ def test_eval_points_corners_and_random(name):
     assert np.all(np.isfinite(got["d2N"])) and np.all(np.isfinite(got["H"]))  # gridtests.cpp:1085-1124
 
 
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("mode", [capi.KERNEL_GENERIC, capi.KERNEL_WARP], ids=["generic", "warp"])
+def test_eval_points_kernels_incl_points_outside_the_patch(name, mode):
+    """Point lists through the thread-per-point kernel and the warp-per-32-points kernel: several chunks with a tail,
+    points grouped by element and scattered, element corners, and points slightly OUTSIDE the patch, where the
+    reference's value path clamps (bsplinealgorithms.hh:103) and its derivative path does not -- both kernels must
+    reproduce that.  Orders 0, 1, 2, output subsets."""
+    spec = PFT.small_patch(name)
+    O, kind = oracle_for(spec)
+    P = gpu_patch(spec)
+    P.setKernel(mode)
+    rng = np.random.default_rng(7)
+    n = 32 * 3 + 11
+    elem = np.sort(rng.integers(0, P.nelem, n)).astype(np.int32)
+    elem[-8:] = rng.integers(0, P.nelem, 8)
+    xi = rng.random((n, P.dim))
+    elem[:6] = [0, 0, 0, P.nelem - 1, P.nelem - 1, P.nelem - 1]
+    xi[0], xi[1], xi[2] = 0.0, -0.02, -1e-9
+    xi[3], xi[4], xi[5] = 1.0, 1.03, 1 + 1e-9
+    ref = O.eval_points(elem, xi, order=2, want=EVAL_FIELDS)
+    got = P.evalPoints(elem, xi, order=2, want=EVAL_FIELDS)
+    for f in EVAL_FIELDS:
+        assert relerr(got[f], ref[f]) <= TOL, (f, kind, relerr(got[f], ref[f]))
+    got1 = P.evalPoints(elem, xi, order=1, want=("N", "dN", "x", "Jt", "detJ", "JinvT"))
+    for f in ("N", "dN", "x", "Jt", "detJ"):
+        assert relerr(got1[f], ref[f]) <= TOL, (f, "order 1")
+    got0 = P.evalPoints(elem, xi, order=0)
+    assert set(got0) == {"N", "x"} and relerr(got0["N"], ref["N"]) <= TOL and relerr(got0["x"], ref["x"]) <= TOL
+    sub = P.evalPoints(elem, xi, order=2, want=("d2N", "detJ"))
+    assert np.array_equal(sub["d2N"], got["d2N"]) and np.array_equal(sub["detJ"], got["detJ"])
+
+
 def test_reference_literals_through_cuda():
     """The reference's known-answer vectors (Appendix B) replayed through the CUDA kernels."""
     n = G["nurbs2d"]

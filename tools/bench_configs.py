@@ -102,6 +102,26 @@ def main():
                         F2, el_chunk=32 * 32 * 8, kernel=km)
             eval_config("W5[%s] 2-D plate p=2 elevated to p=4 512^2, 5x5 Gauss, order 1" % kn,
                         plate4, [5, 5], 1, F1, kernel=km)
+    if "L" in which:  # explicit point lists in 3-D: thread per point against warp per 32 points
+        pd = PD.thickCylinder(3, (5, 5, 5))
+        rng = np.random.default_rng(1)
+        for label, grouped in (("grouped by element (40 points each)", True), ("scattered", False)):
+            P = capi.Patch.fromPatchData(pd)
+            npts = 1 << 20
+            elem = (np.repeat(rng.choice(P.nelem, npts // 40 + 1, replace=False), 40)[:npts] if grouped
+                    else rng.integers(0, P.nelem, npts)).astype(np.int32)
+            d_elem, d_xi = torch.from_numpy(elem).cuda(), torch.from_numpy(rng.random((npts, 3))).cuda()
+            fields = ("N", "dN", "x", "Jt", "detJ")
+            sh = P.shapes(npts)
+            out = {f: torch.empty(sh[f], dtype=torch.float64, device="cuda") for f in fields}
+            s = torch.cuda.current_stream().cuda_stream
+            for kn, km in (("generic", capi.KERNEL_GENERIC), ("warp", capi.KERNEL_WARP)):
+                P.setKernel(km)
+                ms = timed(lambda: P.evalPoints(d_elem, d_xi, order=1, want=fields, out=out, stream=s))
+                bpp = 8 * (64 * 4 + 3 + 9 + 1) + 8 * 4
+                print(json.dumps({"config": "L[%s] 3-D p=3 point list, %s" % (kn, label), "points": npts, "ms": ms,
+                                  "points_per_s": npts / ms * 1e3, "GBs": bpp * npts / ms / 1e6,
+                                  "frac_of_copy_peak": bpp * npts / ms / 1e6 / PEAK}), flush=True)
     if "C4" in which:
         eval_config("C4 torus shell p=2 in R^3 1024x1024, 4x4 Gauss, order 2", PD.torusSurface(8), [4, 4], 2,
                     ("N", "dN", "d2N", "x", "Jt", "H", "detJ"))
