@@ -416,6 +416,10 @@ igab_status eval_for(const PatchDev& P, SfWorkspace& ws, const double* const* xi
   if (eval_tensor_blk_supported(P, nq1, 1, out)) return launch_eval_tensor_blk(P, ws, src, xi1d_host, nel, 1, out, stream);
   if (eval_tensor_sf_supported(P, nq1, 1, out)) return launch_eval_tensor_sf(P, ws, src, xi1d_host, nel, 1, out, stream);
   if (eval_tensor_2d_supported(P, nq1, 1, out)) return launch_eval_tensor_2d(P, ws, src, xi1d_host, nel, 1, out, stream);
+  {
+    const igab_status st = launch_eval_warp(P, src, nel, 1, out, stream);  // general warp-per-element kernel
+    if (st != IGAB_UNSUPPORTED) return st;
+  }
   return launch_eval_generic(P, src, nel * src.nq, 1, out, stream);
 }
 
