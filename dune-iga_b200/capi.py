@@ -25,7 +25,7 @@ EXPORTS = ("igab_last_error_string", "igab_version", "igab_launch_count", "igab_
            "igab_patch_update_control_points", "igab_patch_spans", "igab_patch_dofmap", "igab_eval_tensor",
            "igab_eval_points", "igab_partial", "igab_assemble", "igab_reduce_volume", "igab_csr_pattern",
            "igab_csr_assemble", "igab_eval_faces", "igab_refine_apply", "igab_surface_forms", "igab_geometry_local", "igab_reduce_norms", "igab_local_keys", "igab_rhs_assemble",
-           "igab_csr_dirichlet", "igab_assemble_points", "igab_global_assemble")
+           "igab_csr_dirichlet", "igab_assemble_points", "igab_global_assemble", "igab_reduce_volume_trimmed")
 
 
 class EvalOut(C.Structure):
@@ -68,6 +68,9 @@ def lib():
                                     C.POINTER(dp), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.igab_csr_pattern.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p,
                                        C.c_void_p, C.c_int, C.c_void_p]
+        L.igab_reduce_volume_trimmed.argtypes = [C.c_void_p, C.c_int64, C.c_int64, ip, C.POINTER(dp), C.POINTER(dp),
+                                                 C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
         L.igab_global_assemble.argtypes = [C.c_void_p, C.c_int, dp, C.c_double, ip, C.POINTER(dp), C.POINTER(dp),
                                            C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_int, C.c_void_p]
@@ -462,13 +465,21 @@ class Patch:
                                           _ptr(b)[0] if b is not None else None, vs, stream))
         return values, b
 
-    def volume(self, xi1d, w1d, elem_begin=0, elem_end=None, nccl_comm=None, stream=None):
+    def volume(self, xi1d, w1d, elem_begin=0, elem_end=None, nccl_comm=None, stream=None, trimmed=None):
+        """sum of detJ w over the tensor rule of the (full) elements [elem_begin, elem_end); trimmed = (elem [npts],
+        xi [npts][dim], w [npts]) adds the trimmed elements' own points (quadrature.trimmedBatch)."""
         if elem_end is None:
             elem_end = self.nelem
         xa, xp = _rule_arrays(xi1d)
         wa, wp = _rule_arrays(w1d)
         nq1 = _i32([len(a) for a in xa])
         r = C.c_double()
+        if trimmed is not None:
+            te, tx, tw = _i32(trimmed[0]), _f64(trimmed[1]), _f64(trimmed[2])
+            _check(lib().igab_reduce_volume_trimmed(self.h, elem_begin, elem_end, nq1.ctypes.data_as(ip), xp, wp, len(te),
+                                                    te.ctypes.data, tx.ctypes.data, tw.ctypes.data, C.byref(r), nccl_comm,
+                                                    stream))
+            return r.value
         _check(lib().igab_reduce_volume(self.h, elem_begin, elem_end, nq1.ctypes.data_as(ip), xp, wp, C.byref(r),
                                         nccl_comm, stream))
         return r.value

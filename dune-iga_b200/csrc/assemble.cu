@@ -370,12 +370,15 @@ template <int DIM>
 __global__ void __launch_bounds__(256) volume_partial_kernel(long long npts, long long nq, int nq0, int nq1_, int nq2,
                                                              const double* __restrict__ w0, const double* __restrict__ w1,
                                                              const double* __restrict__ w2,
-                                                             const double* __restrict__ detJ, double* __restrict__ partial) {
+                                                             const double* __restrict__ detJ, double* __restrict__ partial,
+                                                             const uint8_t* __restrict__ trim, long long elem_begin) {
   __shared__ double sh[256];
   const long long per = (npts + gridDim.x - 1) / gridDim.x;
   const long long b0 = (long long)blockIdx.x * per, b1 = min(npts, b0 + per);
   double acc = 0.0;
   for (long long pt = b0 + threadIdx.x; pt < b1; pt += 256) {
+    // trimmed patches: only full elements carry the tensor rule (trimmed ones bring their own points, empty ones nothing)
+    if (trim && trim[elem_begin + pt / nq] != IGAB_TRIM_FULL) continue;
     long long q = pt % nq;
     double w = w0[q % nq0];
     q /= nq0;
@@ -530,7 +533,7 @@ igab_status launch_assemble(const PatchDev& P, SfWorkspace& ws, const double* co
 
 igab_status launch_volume(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, long long elem_begin, long long nelem, const int* nq1,
                           const double* const* xi1d_dev, const double* const* w1d_dev, double* partial_dev,
-                          int npartial, double* result_dev, cudaStream_t stream) {
+                          int npartial, double* result_dev, cudaStream_t stream, const uint8_t* trim_dev) {
   long long nq = 1;
   for (int d = 0; d < P.dim; ++d) nq *= nq1[d];
   const long long npts = nelem * nq;
@@ -550,11 +553,11 @@ igab_status launch_volume(const PatchDev& P, SfWorkspace& ws, const double* cons
   const double* w1 = w1d_dev[P.dim > 1 ? 1 : 0];
   const double* w2 = w1d_dev[P.dim > 2 ? 2 : 0];
   if (P.dim == 1)
-    volume_partial_kernel<1><<<nblk, 256, 0, stream>>>(npts, nq, q0, q1, q2, w0, w1, w2, ddet, partial_dev);
+    volume_partial_kernel<1><<<nblk, 256, 0, stream>>>(npts, nq, q0, q1, q2, w0, w1, w2, ddet, partial_dev, trim_dev, elem_begin);
   else if (P.dim == 2)
-    volume_partial_kernel<2><<<nblk, 256, 0, stream>>>(npts, nq, q0, q1, q2, w0, w1, w2, ddet, partial_dev);
+    volume_partial_kernel<2><<<nblk, 256, 0, stream>>>(npts, nq, q0, q1, q2, w0, w1, w2, ddet, partial_dev, trim_dev, elem_begin);
   else
-    volume_partial_kernel<3><<<nblk, 256, 0, stream>>>(npts, nq, q0, q1, q2, w0, w1, w2, ddet, partial_dev);
+    volume_partial_kernel<3><<<nblk, 256, 0, stream>>>(npts, nq, q0, q1, q2, w0, w1, w2, ddet, partial_dev, trim_dev, elem_begin);
   volume_final_kernel<<<1, 1024, 0, stream>>>(nblk, partial_dev, result_dev);
   count_launch(2);
   IGAB_CUDA_TRY(cudaGetLastError());

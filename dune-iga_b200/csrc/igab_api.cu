@@ -1279,13 +1279,58 @@ static nccl_allreduce_fn resolve_nccl_allreduce() {
   return fn;
 }
 
+namespace {
+// sum_k detJ[k] w[k] over a point list, same fixed two-level tree as the tensor part
+__global__ void __launch_bounds__(256) volume_points_partial_kernel(long long npts, const double* __restrict__ detJ,
+                                                                    const double* __restrict__ w,
+                                                                    double* __restrict__ partial) {
+  __shared__ double sh[256];
+  const long long per = (npts + gridDim.x - 1) / gridDim.x;
+  const long long b0 = (long long)blockIdx.x * per, b1 = min(npts, b0 + per);
+  double acc = 0.0;
+  for (long long k = b0 + threadIdx.x; k < b1; k += 256) acc += detJ[k] * w[k];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+// *result += fixed-order sum of the partials
+__global__ void __launch_bounds__(1024) volume_points_final_kernel(int n, const double* __restrict__ partial,
+                                                                   double* __restrict__ result) {
+  __shared__ double sh[1024];
+  sh[threadIdx.x] = threadIdx.x < n ? partial[threadIdx.x] : 0.0;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *result += sh[0];
+}
+}  // namespace
+
 igab_status igab_reduce_volume(igab_patch* p, int64_t elem_begin, int64_t elem_end, const int* nq1,
                                const double* const* xi1d, const double* const* w1d, double* result, void* nccl_comm,
                                void* stream_) {
-  if (!p || !nq1 || !xi1d || !w1d || !result) {
+  return igab_reduce_volume_trimmed(p, elem_begin, elem_end, nq1, xi1d, w1d, 0, nullptr, nullptr, nullptr, result,
+                                    nccl_comm, stream_);
+}
+
+igab_status igab_reduce_volume_trimmed(igab_patch* p, int64_t elem_begin, int64_t elem_end, const int* nq1,
+                                       const double* const* xi1d, const double* const* w1d, int64_t npts_list,
+                                       const int32_t* elem, const double* xi, const double* w, double* result,
+                                       void* nccl_comm, void* stream_) {
+  if (!p || !nq1 || !xi1d || !w1d || !result || npts_list < 0 || (npts_list > 0 && (!elem || !xi || !w))) {
     set_error("reduce_volume: null argument");
     return IGAB_INVALID_ARGUMENT;
   }
+  for (int64_t k = 0; k < npts_list; ++k)
+    if (elem[k] < 0 || elem[k] >= p->dev.nelem) {
+      set_error("reduce_volume: element index of a list point out of range");
+      return IGAB_INVALID_ARGUMENT;
+    }
   if (elem_begin < 0 || elem_end < elem_begin || elem_end > p->dev.nelem) {
     set_error("reduce_volume: element range outside [0, n_elem]");
     return IGAB_INVALID_ARGUMENT;
@@ -1300,8 +1345,46 @@ igab_status igab_reduce_volume(igab_patch* p, int64_t elem_begin, int64_t elem_e
     p->red_cap = npartial;
   }
   double* res_dev = p->d_red + npartial;
-  st = launch_volume(p->dev, p->sf, xi1d, elem_begin, elem_end - elem_begin, nq1, rule.xi, rule.w, p->d_red, npartial, res_dev, stream);
+  st = launch_volume(p->dev, p->sf, xi1d, elem_begin, elem_end - elem_begin, nq1, rule.xi, rule.w, p->d_red, npartial, res_dev,
+                     stream, p->d_trim);
   if (st) return st;
+  if (npts_list > 0) {
+    // the trimmed elements' own rules (fillquadraturerule.hh:8-19): detJ at the list points, sum_k detJ w added on
+    int* d_elem = nullptr;
+    double *d_xi = nullptr, *d_w = nullptr, *d_det = nullptr;
+    const int dim = p->dev.dim;
+    cudaError_t e = cudaMallocAsync(&d_elem, sizeof(int) * npts_list, stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_xi, sizeof(double) * npts_list * dim, stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_w, sizeof(double) * npts_list, stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_det, sizeof(double) * npts_list, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_elem, elem, sizeof(int) * npts_list, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_xi, xi, sizeof(double) * npts_list * dim, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_w, w, sizeof(double) * npts_list, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) st = cuda_fail(e, "reduce_volume: list staging");
+    if (!st) {
+      PointSource src{};
+      src.tensor = 0;
+      src.elem = d_elem;
+      src.xi = d_xi;
+      EvalOutDev o{};
+      o.detJ = d_det;
+      st = run_eval_points_device(p, src, npts_list, 1, o, stream);
+    }
+    if (!st) {
+      const int nblk = (int)std::min<long long>(npartial, (npts_list + 255) / 256);
+      volume_points_partial_kernel<<<nblk, 256, 0, stream>>>(npts_list, d_det, d_w, p->d_red);
+      volume_points_final_kernel<<<1, 1024, 0, stream>>>(nblk, p->d_red, res_dev);
+      count_launch(2);
+      if ((e = cudaGetLastError()) != cudaSuccess) st = cuda_fail(e, "reduce_volume: list reduction");
+    }
+    // host list arrays must stay valid until the copies have run
+    cudaStreamSynchronize(stream);
+    if (d_elem) cudaFreeAsync(d_elem, stream);
+    if (d_xi) cudaFreeAsync(d_xi, stream);
+    if (d_w) cudaFreeAsync(d_w, stream);
+    if (d_det) cudaFreeAsync(d_det, stream);
+    if (st) return st;
+  }
   if (nccl_comm) {
     nccl_allreduce_fn ar = resolve_nccl_allreduce();
     if (!ar) {

@@ -144,7 +144,7 @@ igab_status launch_assemble(const PatchDev& P, SfWorkspace& ws, const double* co
                             const double* const* w1d_dev, double* Ke, double* fe, cudaStream_t stream);
 igab_status launch_volume(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, long long elem_begin, long long nelem, const int* nq1,
                           const double* const* xi1d_dev, const double* const* w1d_dev, double* partial_dev,
-                          int npartial, double* result_dev, cudaStream_t stream);
+                          int npartial, double* result_dev, cudaStream_t stream, const uint8_t* trim_dev = nullptr);
 
 igab_status refine_apply(int dim, int dw, const int* ncp_old, int direction, int n_new, int maxlen, const int* first,
                          const int* len, const double* coef, const double* cp_in, double* cp_out, cudaStream_t stream);

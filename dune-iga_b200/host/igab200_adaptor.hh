@@ -199,6 +199,21 @@ public:
     check(igab_reduce_volume(h_, 0, nElements_, nq1.data(), xp.data(), wp.data(), &r, nullptr, nullptr));
     return r;
   }
+  // the same on a trimmed patch: full elements with the tensor rule, trimmed elements with their own points
+  // (elem [npts], xi [npts][dim] element-local, w [npts]; NURBSGridEntity::getQuadratureRule, fillquadraturerule.hh:8-19)
+  double volume(const std::vector<int32_t>& elem, const std::vector<double>& xi, const std::vector<double>& w) const {
+    std::array<int, dim> nq1;
+    std::array<const double*, dim> xp, wp;
+    for (int i = 0; i < dim; ++i) {
+      nq1[i] = (int)xi_[i].size();
+      xp[i] = xi_[i].data();
+      wp[i] = w_[i].data();
+    }
+    double r = 0;
+    check(igab_reduce_volume_trimmed(h_, 0, nElements_, nq1.data(), xp.data(), wp.data(), (int64_t)elem.size(), elem.data(),
+                                     xi.data(), w.data(), &r, nullptr, nullptr));
+    return r;
+  }
 
 private:
   PatchData<dim, dimworld> data_;

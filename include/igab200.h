@@ -258,6 +258,16 @@ igab_status igab_reduce_volume(igab_patch* p, int64_t elem_begin, int64_t elem_e
                                const double* const* xi1d, const double* const* w1d, double* result, void* nccl_comm,
                                void* stream);
 
+/* The same sum on a TRIMMED patch (NURBSGeometry::volume of a trimmed element integrates its sub-triangle rule,
+ * nurbsgeometry.hh:96-113 with fillquadraturerule.hh:8-19): the tensor rule over the IGAB_TRIM_FULL elements of
+ * [elem_begin, elem_end) (trimmed and empty elements are skipped whenever the patch has trim flags -- also by
+ * igab_reduce_volume) plus sum_k detJ(elem[k], xi[k]) w[k] over the trimmed elements' own points: elem [npts_list]
+ * (int32), xi [npts_list][dim] element-local, w [npts_list], HOST arrays (quadrature.trimmedBatch).                */
+igab_status igab_reduce_volume_trimmed(igab_patch* p, int64_t elem_begin, int64_t elem_end, const int* nq1,
+                                       const double* const* xi1d, const double* const* w1d, int64_t npts_list,
+                                       const int32_t* elem, const double* xi, const double* w, double* result,
+                                       void* nccl_comm, void* stream);
+
 /* L2 norm and energy (H1 seminorm) of a discrete field u_h = sum_i R_i u_i, fused evaluation + reduction:
  *   result[0] = sum_q w detJ |u_h|^2 (= u^T M u),  result[1] = sum_q w detJ |grad u_h|^2 (= u^T K u of the Poisson
  * operator), with R_i / dR_i as evaluateFunction / evaluateJacobian (nurbsbasis.hh:77-96), detJ = integrationElement and

@@ -1246,6 +1246,9 @@ def test_trimmed_patch_poisson_end_to_end():
     area = (det[flags == 0] * np.outer(wg, wg).reshape(-1)).sum() + \
         (P.evalPoints(elem_pt, xi, order=1, want=("detJ",))["detJ"] * w).sum()
     assert abs(b.sum() - area) <= 1e-13
+    # NURBSGeometry::volume summed over the trimmed grid (full elements: tensor rule, trimmed: their sub-triangle rules)
+    assert abs(P.volume([x, x], [wg, wg], trimmed=(elem_pt, xi, w)) - area) <= 1e-14
+    assert abs(P.volume([x, x], [wg, wg]) - (det[flags == 0] * np.outer(wg, wg).reshape(-1)).sum()) <= 1e-14
     # the same system through the device-side global assembler (compacted CSR pattern, gather, load vector, Dirichlet
     # rows): element matrices of the trimmed elements replace the tensor-rule ones, empty elements are never read
     Kall, fall = Kfull.copy(), ffull.copy()
