@@ -836,7 +836,7 @@ __global__ void __launch_bounds__(256, 2) gram_sf_kernel(
 #pragma unroll
           for (int s = 0; s < S::TPW; ++s) acc[s][0] = acc[s][1] = 0.0;
           const int kb = S::goff(g), nks = S::r4(S::ncombo(g) * Q) / 4;  // constants after unrolling over g
-#pragma unroll 4
+#pragma unroll
           for (int ks = 0; ks < nks; ++ks) {
             const double a = arow[kb + 4 * ks];
 #pragma unroll
