@@ -71,7 +71,7 @@ def lib():
         L.igab_reduce_volume_trimmed.argtypes = [C.c_void_p, C.c_int64, C.c_int64, ip, C.POINTER(dp), C.POINTER(dp),
                                                  C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                                  C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
-        L.igab_global_assemble.argtypes = [C.c_void_p, C.c_int, dp, C.c_double, ip, C.POINTER(dp), C.POINTER(dp),
+        L.igab_global_assemble.argtypes = [C.c_void_p, C.c_int, dp, C.c_double, C.c_int64, C.c_int64, ip, C.POINTER(dp), C.POINTER(dp),
                                            C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_int, C.c_void_p]
         L.igab_csr_assemble.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -434,10 +434,12 @@ class Patch:
         return values
 
     def globalAssemble(self, kind, xi1d, w1d, D=None, fconst=1.0, trimmed=None, want_b=True, device=False, stream=None,
-                       out=None):
+                       out=None, elem_begin=0, elem_end=None):
         """globalAssembler of poisson.py:84-127 in one call: (values [nnz] of csrPattern(ncomp), b [nrows]).  The element
         matrices stay on the device.  trimmed = (elem, offset, xi, w) of the trimmed elements' own rules
         (quadrature.trimmedBatch; elem ascending) or None.  device=True returns CUDA tensors."""
+        if elem_end is None:
+            elem_end = self.nelem
         xa, xp = _rule_arrays(xi1d)
         wa, wp = _rule_arrays(w1d)
         nq1 = _i32([len(a) for a in xa])
@@ -461,7 +463,7 @@ class Patch:
             nl, ea, oa, xia, wqa = len(te), te.ctypes.data, to.ctypes.data, tx.ctypes.data, tw.ctypes.data
         va, vs = _ptr(values)
         _check(lib().igab_global_assemble(self.h, kind, Dm.ctypes.data_as(dp) if Dm is not None else None, fconst,
-                                          nq1.ctypes.data_as(ip), xp, wp, nl, ea, oa, xia, wqa, va,
+                                          elem_begin, elem_end, nq1.ctypes.data_as(ip), xp, wp, nl, ea, oa, xia, wqa, va,
                                           _ptr(b)[0] if b is not None else None, vs, stream))
         return values, b
 

@@ -1156,8 +1156,9 @@ __global__ void put_trimmed_kernel(long long n2, long long m, const int32_t* __r
 }
 }  // namespace
 
-igab_status igab_global_assemble(igab_patch* p, int kind, const double* D, double fconst, const int* nq1,
-                                 const double* const* xi1d, const double* const* w1d, int64_t nlist,
+igab_status igab_global_assemble(igab_patch* p, int kind, const double* D, double fconst, int64_t elem_begin,
+                                 int64_t elem_end, const int* nq1, const double* const* xi1d,
+                                 const double* const* w1d, int64_t nlist,
                                  const int32_t* elem, const int64_t* offset, const double* xi, const double* w,
                                  double* values, double* b, igab_memspace space, void* stream_) {
   if (!p || !nq1 || !xi1d || !w1d || !values || nlist < 0 || (nlist > 0 && (!elem || !offset || !xi || !w))) {
@@ -1168,6 +1169,10 @@ igab_status igab_global_assemble(igab_patch* p, int kind, const double* D, doubl
     set_error("global_assemble: unknown kind");
     return IGAB_INVALID_ARGUMENT;
   }
+  if (elem_begin < 0 || elem_end < elem_begin || elem_end > p->dev.nelem) {
+    set_error("global_assemble: element range outside [0, n_elem]");
+    return IGAB_INVALID_ARGUMENT;
+  }
   for (int64_t k = 0; k < nlist; ++k)
     if (elem[k] < 0 || elem[k] >= p->dev.nelem || (k > 0 && elem[k] <= elem[k - 1]) || offset[k + 1] < offset[k]) {
       set_error("global_assemble: trimmed-element list must be strictly ascending with valid offsets");
@@ -1175,11 +1180,11 @@ igab_status igab_global_assemble(igab_patch* p, int kind, const double* D, doubl
     }
   cudaStream_t stream = (cudaStream_t)stream_;
   const int ncomp = kind == IGAB_ASM_ELASTICITY ? p->dev.dim : 1;
-  const long long n = (long long)p->dev.nb * ncomp, n2 = n * n, nelem = p->dev.nelem;
+  const long long n = (long long)p->dev.nb * ncomp, n2 = n * n, nrange = elem_end - elem_begin;
   int64_t nrows = 0, nnz = 0;
   igab_status st = csr_pattern(p, ncomp, &nrows, &nnz, nullptr, nullptr, IGAB_HOST, stream);
   if (st) return st;
-  const long long chunk = std::max(1LL, std::min(nelem, (1024LL << 20) / (8 * n2)));  // <= 1 GB of element matrices
+  const long long chunk = std::max(1LL, std::min(std::max(1LL, nrange), (1024LL << 20) / (8 * n2)));  // <= 1 GB of element matrices
   double *dK = nullptr, *dF = nullptr, *dV = values, *dB = b, *dKt = nullptr, *dFt = nullptr, *dXi = nullptr, *dW = nullptr;
   int32_t* dElem = nullptr;
   int64_t* dOff = nullptr;
@@ -1223,8 +1228,14 @@ igab_status igab_global_assemble(igab_patch* p, int kind, const double* D, doubl
     return st;
   }
   long long k0 = 0;  // first trimmed list entry not yet consumed
-  for (long long eb = 0; eb < nelem && !st; eb += chunk) {
-    const long long ee = std::min(nelem, eb + chunk);
+  while (k0 < nlist && elem[k0] < elem_begin) ++k0;
+  if (nrange == 0) {  // nothing to add: the caller still gets a defined (zero) result
+    e = cudaMemsetAsync(dV, 0, sizeof(double) * nnz, stream);
+    if (e == cudaSuccess && b) e = cudaMemsetAsync(dB, 0, sizeof(double) * nrows, stream);
+    if (e != cudaSuccess) st = cuda_fail(e, "global_assemble: memset");
+  }
+  for (long long eb = elem_begin; eb < elem_end && !st; eb += chunk) {
+    const long long ee = std::min((long long)elem_end, eb + chunk);
     st = igab_assemble(p, kind, D, fconst, eb, ee, nq1, xi1d, w1d, dK, dF, IGAB_DEVICE, stream);
     long long k1 = k0;
     while (k1 < nlist && elem[k1] < ee) ++k1;
@@ -1250,8 +1261,8 @@ igab_status igab_global_assemble(igab_patch* p, int kind, const double* D, doubl
       }
     }
     k0 = k1;
-    if (!st) st = csr_assemble(p, ncomp, eb, ee, dK, nullptr, dV, eb > 0, IGAB_DEVICE, stream);
-    if (!st && b) st = rhs_assemble(p, ncomp, eb, ee, dF, dB, eb > 0, IGAB_DEVICE, stream);
+    if (!st) st = csr_assemble(p, ncomp, eb, ee, dK, nullptr, dV, eb > elem_begin, IGAB_DEVICE, stream);
+    if (!st && b) st = rhs_assemble(p, ncomp, eb, ee, dF, dB, eb > elem_begin, IGAB_DEVICE, stream);
   }
   if (!st && space == IGAB_HOST) {
     e = cudaMemcpyAsync(values, dV, sizeof(double) * nnz, cudaMemcpyDeviceToHost, stream);

@@ -623,7 +623,7 @@ public:
     }
     b_.assign((size_t)A_.rows, 0.0);
     const int64_t nl = trimmed ? (int64_t)trimmed->elem.size() : 0;
-    check(igab_global_assemble(p_->handle(), kind_, D, f, nq1.data(), xp.data(), wp.data(), nl,
+    check(igab_global_assemble(p_->handle(), kind_, D, f, 0, p_->size0(), nq1.data(), xp.data(), wp.data(), nl,
                                nl ? trimmed->elem.data() : nullptr, nl ? trimmed->offset.data() : nullptr,
                                nl ? trimmed->xi.data() : nullptr, nl ? trimmed->w.data() : nullptr, A_.values.data(),
                                b_.data(), IGAB_HOST, nullptr));

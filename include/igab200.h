@@ -243,9 +243,13 @@ igab_status igab_csr_dirichlet(igab_patch* p, int ncomp, const uint8_t* mask, co
  * put into their slots, CSR gather and load-vector gather per chunk -- the element matrices never leave the device.
  * values [nnz] (pattern of igab_csr_pattern with ncomp = 1, or dim for IGAB_ASM_ELASTICITY) and b [nrows] (or NULL)
  * live in `space`; the rule, D and the trimmed lists (elem strictly ascending, offset absolute into xi / w) are HOST.
- * Dirichlet rows are applied afterwards with igab_csr_dirichlet, as the reference does inside its loop.            */
-igab_status igab_global_assemble(igab_patch* p, int kind, const double* D, double fconst, const int* nq1,
-                                 const double* const* xi1d, const double* const* w1d, int64_t nlist,
+ * Only the elements [elem_begin, elem_end) contribute (list entries outside are ignored): a rank owning a knot-span
+ * slab assembles its share of the one shared pattern, rows of DOFs on a cut are completed by the interface-row exchange
+ * (dune-iga_b200/partition.py).  Dirichlet rows are applied afterwards with igab_csr_dirichlet, as the reference does
+ * inside its loop.                                                                                                  */
+igab_status igab_global_assemble(igab_patch* p, int kind, const double* D, double fconst, int64_t elem_begin,
+                                 int64_t elem_end, const int* nq1, const double* const* xi1d,
+                                 const double* const* w1d, int64_t nlist,
                                  const int32_t* elem, const int64_t* offset, const double* xi, const double* w,
                                  double* values, double* b, igab_memspace space, void* stream);
 

@@ -1308,6 +1308,13 @@ def test_global_assemble_one_call_matches_the_stepwise_path(name, kind):
     assert np.array_equal(vd.cpu().numpy(), v) and np.array_equal(bd.cpu().numpy(), b)
     v2, b2 = P.globalAssemble(kind, xi, w, D=D, fconst=0.7, want_b=False)
     assert b2 is None and np.array_equal(v2, v)
+    # element ranges (a rank's slab): the shares add up to the whole system; an empty range gives zeros
+    h = P.nelem // 3
+    va, ba = P.globalAssemble(kind, xi, w, D=D, fconst=0.7, elem_end=h)
+    vb, bb = P.globalAssemble(kind, xi, w, D=D, fconst=0.7, elem_begin=h)
+    assert np.abs(va + vb - v).max() <= 1e-14 * np.abs(v).max() and np.abs(ba + bb - b).max() <= 1e-14 * np.abs(b).max()
+    vz, bz = P.globalAssemble(kind, xi, w, D=D, fconst=0.7, elem_begin=h, elem_end=h)
+    assert not vz.any() and not bz.any()
 
 
 def test_trimmed_csr_pattern_random_flags_3d_and_vector_valued():
