@@ -30,6 +30,10 @@ def main():
     vals = P.csrAssemble(Ke, 1, eb, ee)
     cuts = partition.interface_row_ranges(pd, world)
     partition.exchange_interface_rows(vals, rowptr, cuts, rank, world, dist)
+    # the same share from the one-call global assembler restricted to this rank's slab (identical bits), then exchanged
+    vals1, _ = P.globalAssemble(capi.ASM_POISSON, xi, ww, want_b=False, device=True, elem_begin=eb, elem_end=ee)
+    partition.exchange_interface_rows(vals1, rowptr, cuts, rank, world, dist)
+    assert torch.equal(vals1, vals), "igab_global_assemble over a slab differs from assemble + csr_assemble"
     # single-GPU reference of the whole matrix
     Kall = torch.empty((P.nelem, n, n), dtype=torch.float64, device="cuda")
     P.assemble(capi.ASM_POISSON, xi, ww, Ke=Kall, fe=None)
