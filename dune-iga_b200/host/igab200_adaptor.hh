@@ -37,6 +37,7 @@
 #include <array>
 #include <cstdint>
 #include <memory>
+#include <cmath>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -579,6 +580,71 @@ public:
 private:
   std::shared_ptr<const Patch<dim, dimworld>> p_;
 };
+
+// ---- quadrature rules handed to the batched entry points (host-side; the C-ABI takes rules as input) -----------------
+// Mirrors NURBSGridEntity<0>::fillQuadratureRule / getQuadratureRule (dune/iga/nurbsgridentity.hh:120-141) and
+// fillQuadratureRuleImpl for trimmed elements (dune/iga/utils/fillquadraturerule.hh:8-19).  dune-geometry's tabulated
+// Gauss rules are not vendored with the reference: Gauss-Legendre nodes are computed here (Newton on P_n).
+
+// n-point Gauss-Legendre rule on [0,1], abscissae ascending
+inline void gaussLegendre01(int n, std::vector<double>& x, std::vector<double>& w) {
+  x.assign((size_t)n, 0.0);
+  w.assign((size_t)n, 0.0);
+  const double pi = 3.14159265358979323846;
+  for (int i = 0; i < (n + 1) / 2; ++i) {
+    double z = std::cos(pi * (i + 0.75) / (n + 0.5)), pp = 1.0;
+    for (int it = 0; it < 100; ++it) {
+      double p1 = 1.0, p2 = 0.0;
+      for (int j = 1; j <= n; ++j) {
+        const double p3 = p2;
+        p2 = p1;
+        p1 = ((2.0 * j - 1.0) * z * p2 - (j - 1.0) * p3) / j;
+      }
+      pp = n * (z * p1 - p2) / (z * z - 1.0);
+      const double dz = p1 / pp;
+      z -= dz;
+      if (std::fabs(dz) < 1e-16) break;
+    }
+    x[(size_t)i] = 0.5 * (1.0 - z);
+    x[(size_t)(n - 1 - i)] = 0.5 * (1.0 + z);
+    w[(size_t)i] = w[(size_t)(n - 1 - i)] = 1.0 / ((1.0 - z * z) * pp * pp);
+  }
+}
+
+// Gauss points per direction for polynomial order `order` (dune-geometry: floor(order / 2) + 1)
+inline int pointsForOrder(int order) { return order / 2 + 1; }
+
+// the rule of an UNTRIMMED element: QuadratureRules<double,dim>::rule(cube, order), order defaulting to dim * max(p)
+// (nurbsgridentity.hh:123-124,131-132)
+template <int dim>
+void getQuadratureRule(const std::array<int, dim>& degree, std::array<std::vector<double>, dim>& xi,
+                       std::array<std::vector<double>, dim>& w, int order = -1) {
+  int pmax = 0;
+  for (int d = 0; d < dim; ++d) pmax = degree[d] > pmax ? degree[d] : pmax;
+  const int n = pointsForOrder(order >= 0 ? order : dim * pmax);
+  for (int d = 0; d < dim; ++d) gaussLegendre01(n, xi[d], w[d]);
+}
+
+// the rule of a TRIMMED element from its sub-triangles in element-local coordinates (fillquadraturerule.hh:13-19):
+// position = triangle.global(ip), weight = ip.weight * triangle.integrationElement; 6-point rule of degree 4.
+// triangles: [ntri][3][2]; appends to xi [npts][2], w [npts].
+inline void fillQuadratureRule(const std::vector<double>& triangles, std::vector<double>& xi, std::vector<double>& w) {
+  static const double rp[6][2] = {{0.445948490915965, 0.445948490915965}, {0.445948490915965, 0.108103018168070},
+                                  {0.108103018168070, 0.445948490915965}, {0.091576213509771, 0.091576213509771},
+                                  {0.091576213509771, 0.816847572980459}, {0.816847572980459, 0.091576213509771}};
+  static const double rw[6] = {0.223381589678011 * 0.5, 0.223381589678011 * 0.5, 0.223381589678011 * 0.5,
+                               0.109951743655322 * 0.5, 0.109951743655322 * 0.5, 0.109951743655322 * 0.5};
+  for (size_t t = 0; t + 6 <= triangles.size(); t += 6) {
+    const double* T = triangles.data() + t;
+    const double ax = T[2] - T[0], ay = T[3] - T[1], bx = T[4] - T[0], by = T[5] - T[1];
+    const double ie = std::fabs(ax * by - ay * bx);
+    for (int k = 0; k < 6; ++k) {
+      xi.push_back(T[0] + rp[k][0] * ax + rp[k][1] * bx);
+      xi.push_back(T[1] + rp[k][0] * ay + rp[k][1] * by);
+      w.push_back(rw[k] * ie);
+    }
+  }
+}
 
 // ---- globalAssembler (dune/python/test/poisson.py:84-127), vectorised: the whole loop over elements, quadrature points
 //      and local DOF pairs is one device pass; what comes back is the CSR matrix and the load vector -----------------------

@@ -59,6 +59,22 @@ int main() {
     w[d].resize(3);
     igo_gauss01(3, xi[d].data(), w[d].data());
   }
+  {  // the adaptor's own rules: Gauss-Legendre on [0,1] against the oracle's, the default order dim * max(p), a triangle
+    std::array<std::vector<double>, dim> gx, gw;
+    igab::getQuadratureRule<dim>(pd.degree, gx, gw);  // order 4 -> 3 points per direction
+    CHECK(gx[0].size() == 3 && gx[1].size() == 3, "default rule size %zu", gx[0].size());
+    for (int k = 0; k < 3; ++k)
+      CHECK(std::fabs(gx[0][k] - xi[0][k]) < 1e-15 && std::fabs(gw[1][k] - w[1][k]) < 1e-15, "Gauss point %d", k);
+    std::vector<double> g7x, g7w, o7x(7), o7w(7);
+    igab::gaussLegendre01(7, g7x, g7w);
+    igo_gauss01(7, o7x.data(), o7w.data());
+    for (int k = 0; k < 7; ++k) CHECK(std::fabs(g7x[k] - o7x[k]) < 1e-15 && std::fabs(g7w[k] - o7w[k]) < 1e-15, "7-point rule %d", k);
+    std::vector<double> tx, tw;
+    igab::fillQuadratureRule({0.0, 0.0, 1.0, 0.0, 0.0, 1.0, 1.0, 0.0, 1.0, 1.0, 0.0, 1.0}, tx, tw);  // the unit square in 2 triangles
+    double area = 0, mx = 0;
+    for (std::size_t k = 0; k < tw.size(); ++k) { area += tw[k]; mx += tw[k] * tx[2 * k] * tx[2 * k] * tx[2 * k + 1]; }
+    CHECK(tw.size() == 12 && std::fabs(area - 1.0) < 1e-14 && std::fabs(mx - 1.0 / 6.0) < 1e-13, "triangle rule: area %g, int x^2 y %g", area, mx);
+  }
   patch->setQuadratureRule(xi, w, 1);
 
   // oracle
