@@ -79,7 +79,7 @@ __global__ void tables_any_kernel(PatchDev P, PointSource src, WarpLayout L, int
 }
 
 template <int DIM, int DW, int ORDER>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (ORDER <= 1 ? 5 : 2))
     eval_warp_kernel(PatchDev P, PointSource src, long long nelem, EvalOutDev out, WarpLayout L,
                      const double* __restrict__ tabG) {
   extern __shared__ __align__(16) double smem[];
