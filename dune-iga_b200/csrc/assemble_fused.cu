@@ -631,7 +631,10 @@ struct SCfg {
   static constexpr int SZ_T2 = M3P * LDA3;
   static constexpr int SZ_B2 = KTOT * LDB2;
   static constexpr int SZ_TOTAL = F::SZ_T + F::SZ_W + F::SZ_C + SZ_X + SZ_M + SZ_T2 + SZ_B2;
-  static_assert(TPW * NWARP >= MT2 * NT2 && (TPW == 1 || NT2 % TPW == 0), "stage-2 tile distribution");
+  // tiles of a warp share a tile row (one A fragment for TPW tiles) when that divides evenly; otherwise (GEN2) every
+  // warp walks single tiles round-robin
+  static constexpr bool GEN2 = !(TPW == 1 || NT2 % TPW == 0);
+  static_assert(TPW * NWARP >= MT2 * NT2, "stage-2 tile distribution");
   // combo index (group order) -> (beta, gamma)
   __host__ __device__ static constexpr int set0(int k) { return k == 0 ? 0 : k + 1; }  // {0, 2, 3}
   __host__ __device__ static constexpr int beta_of(int g, int c) { return MASS ? 0 : (g == 0 ? set0(c / 3) : (g == 2 ? set0(c) : 1)); }
@@ -644,7 +647,7 @@ struct SCfg {
 };
 
 template <int P, int Q, int KIND>
-__global__ void __launch_bounds__(256, 2) gram_sf_kernel(
+__global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1024 ? 1 : 2)) gram_sf_kernel(
     PatchDev Pd, long long elem_begin, long long nelem, const double* __restrict__ tab0,
     const double* __restrict__ tab1, const double* __restrict__ tab2, const double* __restrict__ w0,
     const double* __restrict__ w1, const double* __restrict__ w2, ElasCoef coef, double fconst,
@@ -827,7 +830,29 @@ __global__ void __launch_bounds__(256, 2) gram_sf_kernel(
       }
       __syncthreads();
       // ---- stage 2: C_g[(j2,q0)][pi1] = sum_{k in g} T1[.][k] B2[k][.]  ->  T2[j1 + NB1 j2 + NP i1][g Q + q0]
-      if (has2) {
+      if constexpr (S::GEN2) {
+        for (int tile = warp; tile < S::MT2 * S::NT2; tile += S::NWARP) {
+          const int mt = tile / S::NT2, nt = tile % S::NT2;
+          const double* arow = sT1 + (8 * mt + lr) * LDA2 + lc;
+          const double* brow = sB2 + lc * LDB2 + 8 * nt + lr;
+          const int m = 8 * mt + lr;
+          int off[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int n = 8 * nt + 2 * lc + h;
+            off[h] = (m < S::M2 && n < NP) ? ((n % NB1) + NB1 * (m / Q) + NP * (n / NB1)) * LDA3 + (m % Q) : -1;
+          }
+#pragma unroll
+          for (int g = 0; g < S::NG; ++g) {
+            double a0 = 0.0, a1 = 0.0;
+            const int kb = S::goff(g), nks = S::r4(S::ncombo(g) * Q) / 4;
+#pragma unroll 4
+            for (int ks = 0; ks < nks; ++ks) dmma8x8x4_f(a0, a1, arow[kb + 4 * ks], brow[(kb + 4 * ks) * LDB2]);
+            if (off[0] >= 0) sT2[off[0] + g * Q] = a0;
+            if (off[1] >= 0) sT2[off[1] + g * Q] = a1;
+          }
+        }
+      } else if (has2) {
         const double* arow = sT1 + (8 * mt2 + lr) * LDA2 + lc;
         const double* brow = sB2 + lc * LDB2 + 8 * nt2 + lr;
 #pragma unroll
@@ -987,9 +1012,10 @@ bool gram_fused_supported(const PatchDev& P, int kind, const int* nq1) {
   if (P.dim != 3 || P.dw != 3) return false;
   if (P.degree[0] != P.degree[1] || P.degree[0] != P.degree[2]) return false;
   if (nq1[0] != nq1[1] || nq1[0] != nq1[2]) return false;
-  // full Gauss rule (p+1 points per direction) and the over-integrated p+2 rule
+  // full Gauss rule (p+1 points per direction), the over-integrated p+2 rule, and at p = 4 the reference's default rule
+  // (order dim * max(p) = 12 -> 7 points per direction, nurbsgridentity.hh:123-124)
   const int p = P.degree[0], q = nq1[0];
-  return p >= 2 && p <= 4 && (q == p + 1 || q == p + 2);
+  return p >= 2 && p <= 4 && (q == p + 1 || q == p + 2 || (p == 4 && q == 7));
 }
 
 igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host,
@@ -1016,6 +1042,7 @@ igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* 
     return use_sf ? launch_elas_sf<PP, QQ>(P, ws, D_host, fconst, eb, nel, w1d_dev, Ke, fe, stream)              \
                   : launch_elas<PP, QQ>(P, ws, D_host, fconst, eb, nel, w1d_dev, Ke, fe, stream);
     IGAB_ELAS_CASE(2, 3) IGAB_ELAS_CASE(2, 4) IGAB_ELAS_CASE(3, 4) IGAB_ELAS_CASE(3, 5) IGAB_ELAS_CASE(4, 5) IGAB_ELAS_CASE(4, 6)
+    IGAB_ELAS_CASE(4, 7)
 #undef IGAB_ELAS_CASE
     set_error("assemble: no fused kernel for this configuration");
     return IGAB_UNSUPPORTED;
@@ -1024,6 +1051,7 @@ igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* 
 #define IGAB_PQ_CASE(PP, QQ) \
   if (P.degree[0] == PP && nq1[0] == QQ) return launch_pq<PP, QQ>(P, ws, mass, fconst, eb, nel, w1d_dev, Ke, fe, stream);
   IGAB_PQ_CASE(2, 3) IGAB_PQ_CASE(2, 4) IGAB_PQ_CASE(3, 4) IGAB_PQ_CASE(3, 5) IGAB_PQ_CASE(4, 5) IGAB_PQ_CASE(4, 6)
+  IGAB_PQ_CASE(4, 7)
 #undef IGAB_PQ_CASE
   set_error("assemble: no fused kernel for this configuration");
   return IGAB_UNSUPPORTED;

@@ -1084,7 +1084,7 @@ def test_fused_3d_element_matrices_over_integrated(p, kind):
     assert relerr(f, fref) <= TOL
 
 
-@pytest.mark.parametrize("p,extra", [(2, 0), (3, 0), (3, 1), (4, 0), (4, 1)])
+@pytest.mark.parametrize("p,extra", [(2, 0), (3, 0), (3, 1), (4, 0), (4, 1), (4, 2)])
 @pytest.mark.parametrize("kind", [capi.ASM_POISSON, capi.ASM_MASS, capi.ASM_ELASTICITY])
 @pytest.mark.parametrize("sf", ["0", "1"], ids=["dense", "sumfact"])
 def test_fused_3d_element_matrices_both_contractions(p, extra, kind, sf, monkeypatch):
@@ -1104,7 +1104,9 @@ def test_fused_3d_element_matrices_both_contractions(p, extra, kind, sf, monkeyp
     D = rng.normal(size=(6, 6)) + 4 * np.eye(6) if kind == capi.ASM_ELASTICITY else None
     eb, ee = 3, 8
     Kref, fref = Pp.assemble(kind, [x] * 3, [w] * 3, D=D, fconst=1.3, elem_begin=eb, elem_end=ee)
+    l0 = capi.launch_count()
     K, f = P.assemble(kind, [x] * 3, [w] * 3, D=D, fconst=1.3, elem_begin=eb, elem_end=ee)
+    assert capi.launch_count() - l0 <= 4   # tables + ONE fused kernel (p = 4 with 7 points = the reference's default rule)
     assert relerr(K.reshape(ee - eb, -1), Kref.reshape(ee - eb, -1)) <= TOL, relerr(K.reshape(ee - eb, -1), Kref.reshape(ee - eb, -1))
     assert relerr(f, fref) <= TOL
 
