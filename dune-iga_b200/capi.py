@@ -25,7 +25,7 @@ EXPORTS = ("igab_last_error_string", "igab_version", "igab_launch_count", "igab_
            "igab_patch_update_control_points", "igab_patch_spans", "igab_patch_dofmap", "igab_eval_tensor",
            "igab_eval_points", "igab_partial", "igab_assemble", "igab_reduce_volume", "igab_csr_pattern",
            "igab_csr_assemble", "igab_eval_faces", "igab_refine_apply", "igab_surface_forms", "igab_geometry_local", "igab_reduce_norms", "igab_local_keys", "igab_rhs_assemble",
-           "igab_csr_dirichlet", "igab_assemble_points", "igab_global_assemble", "igab_reduce_volume_trimmed")
+           "igab_csr_dirichlet", "igab_assemble_points", "igab_global_assemble", "igab_reduce_volume_trimmed", "igab_reduce_norms_trimmed")
 
 
 class EvalOut(C.Structure):
@@ -68,6 +68,9 @@ def lib():
                                     C.POINTER(dp), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.igab_csr_pattern.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p,
                                        C.c_void_p, C.c_int, C.c_void_p]
+        L.igab_reduce_norms_trimmed.argtypes = [C.c_void_p, C.c_int64, C.c_int64, ip, C.POINTER(dp), C.POINTER(dp),
+                                                C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
         L.igab_reduce_volume_trimmed.argtypes = [C.c_void_p, C.c_int64, C.c_int64, ip, C.POINTER(dp), C.POINTER(dp),
                                                  C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                                  C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
@@ -486,7 +489,7 @@ class Patch:
                                         nccl_comm, stream))
         return r.value
 
-    def norms(self, xi1d, w1d, u, ncomp=1, elem_begin=0, elem_end=None, nccl_comm=None, stream=None):
+    def norms(self, xi1d, w1d, u, ncomp=1, elem_begin=0, elem_end=None, nccl_comm=None, stream=None, trimmed=None):
         """(sum w detJ |u_h|^2, sum w detJ |grad u_h|^2) of the discrete field with coefficients u [ndof*ncomp] (numpy
         or CUDA tensor) over the elements [elem_begin, elem_end): squared L2 norm and energy, one fused pass."""
         if elem_end is None:
@@ -498,6 +501,12 @@ class Patch:
         wa, wp = _rule_arrays(w1d)
         nq1 = _i32([len(a) for a in xa])
         r = (C.c_double * 2)()
+        if trimmed is not None:  # (elem [npts], xi [npts][dim], w [npts]): the trimmed elements' own points
+            te, tx, tw = _i32(trimmed[0]), _f64(trimmed[1]), _f64(trimmed[2])
+            _check(lib().igab_reduce_norms_trimmed(self.h, elem_begin, elem_end, nq1.ctypes.data_as(ip), xp, wp, ua, ncomp,
+                                                   us, len(te), te.ctypes.data, tx.ctypes.data, tw.ctypes.data, r,
+                                                   nccl_comm, stream))
+            return np.array([r[0], r[1]])
         _check(lib().igab_reduce_norms(self.h, elem_begin, elem_end, nq1.ctypes.data_as(ip), xp, wp, ua, ncomp, us, r,
                                        nccl_comm, stream))
         return np.array([r[0], r[1]])

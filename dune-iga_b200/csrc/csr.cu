@@ -276,6 +276,36 @@ igab_status make_geom(igab_patch* p, int ncomp, CsrGeom* G) {
     return IGAB_INVALID_ARGUMENT;
   }
   const PatchDev& D = p->dev;
+  if (igab_status cst = ensure_dof_compaction(p)) return cst;
+  for (int d = 0; d < D.dim; ++d) {
+    if (!p->d_elem_of_first[d]) {
+      const int nf = D.ncp[d] - D.degree[d];  // possible first-DOF indices 0 .. n_d - p_d - 1
+      std::vector<int> tab(nf, -1);
+      for (int e = 0; e < D.nel[d]; ++e) tab[p->hspan[d][e] - D.degree[d]] = e;
+      IGAB_CUDA_TRY(cudaMalloc(&p->d_elem_of_first[d], sizeof(int) * nf));
+      IGAB_CUDA_TRY(cudaMemcpy(p->d_elem_of_first[d], tab.data(), sizeof(int) * nf, cudaMemcpyHostToDevice));
+    }
+  }
+  G->dim = D.dim;
+  G->ncomp = ncomp;
+  G->nb = D.nb;
+  for (int d = 0; d < kMaxDim; ++d) {
+    G->p[d] = d < D.dim ? D.degree[d] : 0;
+    G->n[d] = d < D.dim ? D.ncp[d] : 1;
+    G->nel[d] = d < D.dim ? D.nel[d] : 1;
+    G->elemOfFirst[d] = d < D.dim ? p->d_elem_of_first[d] : nullptr;
+  }
+  G->trim = p->d_trim;
+  G->map = p->d_dofc_map;
+  G->inv = p->d_dofc_inv;
+  G->colidx = p->d_csr_colidx;
+  return IGAB_OK;
+}
+
+}  // namespace
+
+igab_status ensure_dof_compaction(igab_patch* p) {
+  const PatchDev& D = p->dev;
   if (p->d_trim && !p->d_dofc_map) {
     // compacted numbering (prepareForTrim): the same mark / scan kernels as igab_patch_dofmap, kept in the handle
     const long long n = D.nelem * D.nb, nd = p->ndof_untrimmed;
@@ -311,32 +341,8 @@ igab_status make_geom(igab_patch* p, int ncomp, CsrGeom* G) {
     p->d_dofc_inv = inv;
     p->ndof_compact = total;
   }
-  for (int d = 0; d < D.dim; ++d) {
-    if (!p->d_elem_of_first[d]) {
-      const int nf = D.ncp[d] - D.degree[d];  // possible first-DOF indices 0 .. n_d - p_d - 1
-      std::vector<int> tab(nf, -1);
-      for (int e = 0; e < D.nel[d]; ++e) tab[p->hspan[d][e] - D.degree[d]] = e;
-      IGAB_CUDA_TRY(cudaMalloc(&p->d_elem_of_first[d], sizeof(int) * nf));
-      IGAB_CUDA_TRY(cudaMemcpy(p->d_elem_of_first[d], tab.data(), sizeof(int) * nf, cudaMemcpyHostToDevice));
-    }
-  }
-  G->dim = D.dim;
-  G->ncomp = ncomp;
-  G->nb = D.nb;
-  for (int d = 0; d < kMaxDim; ++d) {
-    G->p[d] = d < D.dim ? D.degree[d] : 0;
-    G->n[d] = d < D.dim ? D.ncp[d] : 1;
-    G->nel[d] = d < D.dim ? D.nel[d] : 1;
-    G->elemOfFirst[d] = d < D.dim ? p->d_elem_of_first[d] : nullptr;
-  }
-  G->trim = p->d_trim;
-  G->map = p->d_dofc_map;
-  G->inv = p->d_dofc_inv;
-  G->colidx = p->d_csr_colidx;
   return IGAB_OK;
 }
-
-}  // namespace
 
 igab_status csr_pattern(igab_patch* p, int ncomp, int64_t* nrows_out, int64_t* nnz_out, int64_t* rowptr, int32_t* colidx,
                         igab_memspace space, cudaStream_t stream) {

@@ -1417,35 +1417,66 @@ igab_status igab_reduce_volume_trimmed(igab_patch* p, int64_t elem_begin, int64_
 igab_status igab_reduce_norms(igab_patch* p, int64_t elem_begin, int64_t elem_end, const int* nq1,
                               const double* const* xi1d, const double* const* w1d, const double* u, int ncomp,
                               igab_memspace u_space, double* result, void* nccl_comm, void* stream_) {
-  if (!p || !nq1 || !xi1d || !w1d || !u || !result) {
+  return igab_reduce_norms_trimmed(p, elem_begin, elem_end, nq1, xi1d, w1d, u, ncomp, u_space, 0, nullptr, nullptr, nullptr,
+                                   result, nccl_comm, stream_);
+}
+
+igab_status igab_reduce_norms_trimmed(igab_patch* p, int64_t elem_begin, int64_t elem_end, const int* nq1,
+                                      const double* const* xi1d, const double* const* w1d, const double* u, int ncomp,
+                                      igab_memspace u_space, int64_t npts_list, const int32_t* elem, const double* xi,
+                                      const double* w, double* result, void* nccl_comm, void* stream_) {
+  if (!p || !nq1 || !xi1d || !w1d || !u || !result || npts_list < 0 || (npts_list > 0 && (!elem || !xi || !w))) {
     set_error("reduce_norms: null argument");
     return IGAB_INVALID_ARGUMENT;
   }
+  for (int64_t k = 0; k < npts_list; ++k)
+    if (elem[k] < 0 || elem[k] >= p->dev.nelem) {
+      set_error("reduce_norms: element index of a list point out of range");
+      return IGAB_INVALID_ARGUMENT;
+    }
   if (elem_begin < 0 || elem_end < elem_begin || elem_end > p->dev.nelem) {
     set_error("reduce_norms: element range outside [0, n_elem]");
     return IGAB_INVALID_ARGUMENT;
-  }
-  if (!p->htrim.empty()) {
-    set_error("reduce_norms: trimmed patches are not supported (compacted DOF numbering)");
-    return IGAB_UNSUPPORTED;
   }
   cudaStream_t stream = (cudaStream_t)stream_;
   RuleDev rule;
   igab_status st = stage_rule(p, nq1, xi1d, w1d, &rule, stream);
   if (st) return st;
+  long long ndof = p->ndof_untrimmed;
+  if (p->d_trim) {  // u is numbered like the trimmed basis (prepareForTrim, nurbsbasis.hh:599-615)
+    if ((st = ensure_dof_compaction(p))) return st;
+    ndof = p->ndof_compact;
+  }
   const int npartial = 1024;
   if (!p->d_norm) IGAB_CUDA_TRY(cudaMalloc(&p->d_norm, sizeof(double) * (2 * npartial + 2)));
   double* res_dev = p->d_norm + 2 * npartial;
   const double* u_dev = u;
   double* u_tmp = nullptr;
   if (u_space == IGAB_HOST) {
-    const size_t bytes = sizeof(double) * (size_t)p->ndof_untrimmed * ncomp;
+    const size_t bytes = sizeof(double) * (size_t)ndof * ncomp;
     IGAB_CUDA_TRY(cudaMallocAsync(&u_tmp, bytes, stream));
     IGAB_CUDA_TRY(cudaMemcpyAsync(u_tmp, u, bytes, cudaMemcpyHostToDevice, stream));
     u_dev = u_tmp;
   }
-  st = launch_norms(p->dev, elem_begin, elem_end - elem_begin, nq1, rule.xi, rule.w, u_dev, ncomp, p->d_norm, npartial,
-                    res_dev, stream);
+  int* d_le = nullptr;
+  double *d_lx = nullptr, *d_lw = nullptr;
+  if (npts_list > 0) {  // the trimmed elements' own points (HOST arrays)
+    const int dim = p->dev.dim;
+    cudaError_t e = cudaMallocAsync(&d_le, sizeof(int) * npts_list, stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_lx, sizeof(double) * npts_list * dim, stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_lw, sizeof(double) * npts_list, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_le, elem, sizeof(int) * npts_list, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_lx, xi, sizeof(double) * npts_list * dim, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_lw, w, sizeof(double) * npts_list, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) st = cuda_fail(e, "reduce_norms: list staging");
+  }
+  if (!st)
+    st = launch_norms(p->dev, elem_begin, elem_end - elem_begin, nq1, rule.xi, rule.w, u_dev, ncomp, p->d_norm, npartial,
+                      res_dev, stream, p->d_trim, p->d_dofc_map, npts_list, d_le, d_lx, d_lw);
+  if (npts_list > 0) cudaStreamSynchronize(stream);  // the host list arrays may go away after the call
+  if (d_le) cudaFreeAsync(d_le, stream);
+  if (d_lx) cudaFreeAsync(d_lx, stream);
+  if (d_lw) cudaFreeAsync(d_lw, stream);
   if (u_tmp) cudaFreeAsync(u_tmp, stream);
   if (st) return st;
   if (nccl_comm) {

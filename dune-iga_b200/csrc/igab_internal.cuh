@@ -152,7 +152,12 @@ igab_status eval_faces_device(igab_patch* p, long long nfaces, const int* elem, 
                               const double* const* xi_dev, double* x, double* normal, double* dS, cudaStream_t stream);
 igab_status launch_norms(const PatchDev& P, long long elem_begin, long long nelem, const int* nq1,
                          const double* const* xi1d_dev, const double* const* w1d_dev, const double* u_dev, int ncomp,
-                         double* partial_dev, int npartial, double* result_dev, cudaStream_t stream);
+                         double* partial_dev, int npartial, double* result_dev, cudaStream_t stream,
+                         const uint8_t* trim_dev = nullptr, const int32_t* map_dev = nullptr, long long npts_list = 0,
+                         const int32_t* lelem_dev = nullptr, const double* lxi_dev = nullptr,
+                         const double* lw_dev = nullptr);
+// trimmed patches: builds (once) the compacted DOF numbering of prepareForTrim in the handle (d_dofc_map / d_dofc_inv)
+igab_status ensure_dof_compaction(igab_patch* p);
 igab_status geometry_local_device(const PatchDev& P, long long npts, const int* elem, const double* xg, double* xi,
                                   int* flag, cudaStream_t stream);
 igab_status surface_forms_device(int dim, int dw, long long npts, const double* Jt, const double* H, double* normal,

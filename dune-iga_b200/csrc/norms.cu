@@ -22,8 +22,17 @@ namespace {
 
 constexpr int kMaxComp = 3;
 
-template <int DIM, int DW>
-__global__ void __launch_bounds__(128) norms_partial_kernel(PatchDev P, long long elem_begin, long long npts, long long nq,
+// where the points come from besides the tensor rule, and the numbering of u on trimmed patches
+struct NormSrc {
+  const uint8_t* trim;    // element flags (tensor mode: only IGAB_TRIM_FULL elements contribute) or nullptr
+  const int32_t* map;     // original scalar DOF -> compacted (prepareForTrim) or nullptr
+  const int32_t* lelem;   // list mode: element of point k
+  const double* lxi;      //            element-local coordinates [npts][dim]
+  const double* lw;       //            weights
+};
+
+template <int DIM, int DW, bool LIST>
+__global__ void __launch_bounds__(128) norms_partial_kernel(PatchDev P, NormSrc S, long long elem_begin, long long npts, long long nq,
                                                             int nq0, int nq1_, int nq2, const double* __restrict__ x0,
                                                             const double* __restrict__ x1, const double* __restrict__ x2,
                                                             const double* __restrict__ w0, const double* __restrict__ w1,
@@ -35,10 +44,15 @@ __global__ void __launch_bounds__(128) norms_partial_kernel(PatchDev P, long lon
   constexpr int NK = DW + 1 + kMaxComp;
   double accL2 = 0.0, accEn = 0.0;
   for (long long pt = b0 + threadIdx.x; pt < b1; pt += 128) {
-    const long long e = elem_begin + pt / nq;
-    long long q = pt % nq;
+    const long long e = LIST ? (long long)S.lelem[pt] : elem_begin + pt / nq;
+    if (!LIST && S.trim && S.trim[e] != IGAB_TRIM_FULL) continue;  // trimmed elements bring their own points
+    long long q = LIST ? 0 : pt % nq;
     double xi[DIM], wq;
-    {
+    if constexpr (LIST) {
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) xi[d] = S.lxi[pt * DIM + d];
+      wq = S.lw[pt];
+    } else {
       const int a = (int)(q % nq0);
       xi[0] = x0[a];
       wq = w0[a];
@@ -90,7 +104,9 @@ __global__ void __launch_bounds__(128) norms_partial_kernel(PatchDev P, long lon
       V[DW] = 1.0;
       const double w = P.cp[g * (DW + 1) + DW];
 #pragma unroll
-      for (int c = 0; c < kMaxComp; ++c) V[DW + 1 + c] = c < ncomp ? u[g * ncomp + c] : 0.0;
+      const long long gu = S.map ? (long long)S.map[g] : g;  // compacted numbering on trimmed patches
+#pragma unroll
+      for (int c = 0; c < kMaxComp; ++c) V[DW + 1 + c] = (c < ncomp && gu >= 0) ? u[gu * ncomp + c] : 0.0;
 #pragma unroll
       for (int a = 0; a <= DIM; ++a) {
         double f = w;
@@ -171,7 +187,7 @@ __global__ void __launch_bounds__(128) norms_partial_kernel(PatchDev P, long lon
 
 // result[k] = fixed-order tree sum of partial[k*npartial .. +n)
 __global__ void __launch_bounds__(1024) norms_final_kernel(int n, int npartial, const double* __restrict__ partial,
-                                                           double* __restrict__ result) {
+                                                           double* __restrict__ result, int accumulate) {
   __shared__ double sh[1024];
   for (int k = 0; k < 2; ++k) {
     sh[threadIdx.x] = threadIdx.x < n ? partial[k * npartial + threadIdx.x] : 0.0;
@@ -180,25 +196,55 @@ __global__ void __launch_bounds__(1024) norms_final_kernel(int n, int npartial, 
       if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
       __syncthreads();
     }
-    if (threadIdx.x == 0) result[k] = sh[0];
+    if (threadIdx.x == 0) result[k] = accumulate ? result[k] + sh[0] : sh[0];
     __syncthreads();
   }
 }
 
 template <int DIM, int DW>
-void launch(const PatchDev& P, long long eb, long long npts, long long nq, const int* nq1, const double* const* xi,
-            const double* const* w, const double* u, int ncomp, double* partial, int npartial, int nblk,
-            cudaStream_t stream) {
+void launch(const PatchDev& P, const NormSrc& S, bool list, long long eb, long long npts, long long nq, const int* nq1,
+            const double* const* xi, const double* const* w, const double* u, int ncomp, double* partial, int npartial,
+            int nblk, cudaStream_t stream) {
   const int d1 = DIM > 1 ? 1 : 0, d2 = DIM > 2 ? 2 : 0;
-  norms_partial_kernel<DIM, DW><<<nblk, 128, 0, stream>>>(P, eb, npts, nq, nq1[0], nq1[d1], nq1[d2], xi[0], xi[d1], xi[d2],
-                                                          w[0], w[d1], w[d2], u, ncomp, partial, npartial);
+  if (list)
+    norms_partial_kernel<DIM, DW, true><<<nblk, 128, 0, stream>>>(P, S, eb, npts, 1, 1, 1, 1, nullptr, nullptr, nullptr,
+                                                                  nullptr, nullptr, nullptr, u, ncomp, partial, npartial);
+  else
+    norms_partial_kernel<DIM, DW, false><<<nblk, 128, 0, stream>>>(P, S, eb, npts, nq, nq1[0], nq1[d1], nq1[d2], xi[0],
+                                                                   xi[d1], xi[d2], w[0], w[d1], w[d2], u, ncomp, partial,
+                                                                   npartial);
+}
+
+igab_status run(const PatchDev& P, const NormSrc& S, bool list, long long eb, long long npts, long long nq, const int* nq1,
+                const double* const* xi, const double* const* w, const double* u, int ncomp, double* partial, int npartial,
+                double* result_dev, int accumulate, cudaStream_t stream) {
+  const int nblk = (int)std::min<long long>(npartial, (npts + 127) / 128);
+  switch (P.dim * 10 + P.dw) {
+    case 11: launch<1, 1>(P, S, list, eb, npts, nq, nq1, xi, w, u, ncomp, partial, npartial, nblk, stream); break;
+    case 12: launch<1, 2>(P, S, list, eb, npts, nq, nq1, xi, w, u, ncomp, partial, npartial, nblk, stream); break;
+    case 13: launch<1, 3>(P, S, list, eb, npts, nq, nq1, xi, w, u, ncomp, partial, npartial, nblk, stream); break;
+    case 22: launch<2, 2>(P, S, list, eb, npts, nq, nq1, xi, w, u, ncomp, partial, npartial, nblk, stream); break;
+    case 23: launch<2, 3>(P, S, list, eb, npts, nq, nq1, xi, w, u, ncomp, partial, npartial, nblk, stream); break;
+    case 33: launch<3, 3>(P, S, list, eb, npts, nq, nq1, xi, w, u, ncomp, partial, npartial, nblk, stream); break;
+    default:
+      set_error("reduce_norms: unsupported (dim, dimworld)");
+      return IGAB_UNSUPPORTED;
+  }
+  norms_final_kernel<<<1, 1024, 0, stream>>>(nblk, npartial, partial, result_dev, accumulate);
+  count_launch(2);
+  IGAB_CUDA_TRY(cudaGetLastError());
+  return IGAB_OK;
 }
 
 }  // namespace
 
+// Tensor rule over the (full) elements [elem_begin, elem_begin + nelem), then -- npts_list > 0 -- the trimmed elements' own
+// points (device arrays) added on.  trim_dev / map_dev: nullptr on untrimmed patches.
 igab_status launch_norms(const PatchDev& P, long long elem_begin, long long nelem, const int* nq1,
                          const double* const* xi1d_dev, const double* const* w1d_dev, const double* u_dev, int ncomp,
-                         double* partial_dev, int npartial, double* result_dev, cudaStream_t stream) {
+                         double* partial_dev, int npartial, double* result_dev, cudaStream_t stream,
+                         const uint8_t* trim_dev, const int32_t* map_dev, long long npts_list, const int32_t* lelem_dev,
+                         const double* lxi_dev, const double* lw_dev) {
   if (ncomp < 1 || ncomp > kMaxComp) {
     set_error("reduce_norms: ncomp must be 1, 2 or 3");
     return IGAB_INVALID_ARGUMENT;
@@ -206,26 +252,15 @@ igab_status launch_norms(const PatchDev& P, long long elem_begin, long long nele
   long long nq = 1;
   for (int d = 0; d < P.dim; ++d) nq *= nq1[d];
   const long long npts = nelem * nq;
-  if (npts == 0) {
-    IGAB_CUDA_TRY(cudaMemsetAsync(result_dev, 0, 2 * sizeof(double), stream));
-    return IGAB_OK;
+  NormSrc S{trim_dev, map_dev, lelem_dev, lxi_dev, lw_dev};
+  IGAB_CUDA_TRY(cudaMemsetAsync(result_dev, 0, 2 * sizeof(double), stream));
+  if (npts > 0) {
+    const igab_status st = run(P, S, false, elem_begin, npts, nq, nq1, xi1d_dev, w1d_dev, u_dev, ncomp, partial_dev, npartial,
+                               result_dev, 0, stream);
+    if (st) return st;
   }
-  const int nblk = (int)std::min<long long>(npartial, (npts + 127) / 128);
-  const int key = P.dim * 10 + P.dw;
-  switch (key) {
-    case 11: launch<1, 1>(P, elem_begin, npts, nq, nq1, xi1d_dev, w1d_dev, u_dev, ncomp, partial_dev, npartial, nblk, stream); break;
-    case 12: launch<1, 2>(P, elem_begin, npts, nq, nq1, xi1d_dev, w1d_dev, u_dev, ncomp, partial_dev, npartial, nblk, stream); break;
-    case 13: launch<1, 3>(P, elem_begin, npts, nq, nq1, xi1d_dev, w1d_dev, u_dev, ncomp, partial_dev, npartial, nblk, stream); break;
-    case 22: launch<2, 2>(P, elem_begin, npts, nq, nq1, xi1d_dev, w1d_dev, u_dev, ncomp, partial_dev, npartial, nblk, stream); break;
-    case 23: launch<2, 3>(P, elem_begin, npts, nq, nq1, xi1d_dev, w1d_dev, u_dev, ncomp, partial_dev, npartial, nblk, stream); break;
-    case 33: launch<3, 3>(P, elem_begin, npts, nq, nq1, xi1d_dev, w1d_dev, u_dev, ncomp, partial_dev, npartial, nblk, stream); break;
-    default:
-      set_error("reduce_norms: unsupported (dim, dimworld)");
-      return IGAB_UNSUPPORTED;
-  }
-  norms_final_kernel<<<1, 1024, 0, stream>>>(nblk, npartial, partial_dev, result_dev);
-  count_launch(2);
-  IGAB_CUDA_TRY(cudaGetLastError());
+  if (npts_list > 0)
+    return run(P, S, true, 0, npts_list, 1, nq1, xi1d_dev, w1d_dev, u_dev, ncomp, partial_dev, npartial, result_dev, 1, stream);
   return IGAB_OK;
 }
 

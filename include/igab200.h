@@ -277,11 +277,20 @@ igab_status igab_reduce_volume_trimmed(igab_patch* p, int64_t elem_begin, int64_
  * operator), with R_i / dR_i as evaluateFunction / evaluateJacobian (nurbsbasis.hh:77-96), detJ = integrationElement and
  * grad = jacobianInverseTransposed * d/dxi (nurbsgeometry.hh:200-210) -- the per-point quantities of the loop
  * dune/python/test/poisson.py:47-79.  u [ndof*ncomp] in `u_space`, indexed g*ncomp + c with the DOF numbering of
- * igab_patch_dofmap (untrimmed patches; IGAB_UNSUPPORTED with trim flags), ncomp <= 3.  result[2] is HOST memory.
+ * igab_patch_dofmap, ncomp <= 3.  result[2] is HOST memory.
  * Deterministic (fixed two-level tree); nccl_comm as in igab_reduce_volume (both sums all-reduced).                   */
 igab_status igab_reduce_norms(igab_patch* p, int64_t elem_begin, int64_t elem_end, const int* nq1,
                               const double* const* xi1d, const double* const* w1d, const double* u, int ncomp,
                               igab_memspace u_space, double* result, void* nccl_comm, void* stream);
+
+/* The same on a TRIMMED patch: u [ndof*ncomp] is numbered like the trimmed basis (the compacted DOF map of
+ * igab_patch_dofmap); the tensor rule runs over the IGAB_TRIM_FULL elements of the range (also in igab_reduce_norms when
+ * the patch has trim flags) and the trimmed elements' own points are added: elem [npts_list], xi [npts_list][dim]
+ * element-local, w [npts_list], HOST arrays (quadrature.trimmedBatch).                                             */
+igab_status igab_reduce_norms_trimmed(igab_patch* p, int64_t elem_begin, int64_t elem_end, const int* nq1,
+                                      const double* const* xi1d, const double* const* w1d, const double* u, int ncomp,
+                                      igab_memspace u_space, int64_t npts_list, const int32_t* elem, const double* xi,
+                                      const double* w, double* result, void* nccl_comm, void* stream);
 
 #ifdef __cplusplus
 }

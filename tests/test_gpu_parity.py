@@ -743,12 +743,16 @@ def test_field_norms_errors():
     with pytest.raises(capi.IgabError) as ei:
         P.norms(xi1d, w1d, np.zeros(n), elem_begin=0, elem_end=P.nelem + 1)
     assert ei.value.status == capi.INVALID_ARGUMENT
+    # a patch with trim flags takes u in the trimmed basis' numbering: the empty element is skipped, the norm of the
+    # constant field 1 is the area of the remaining elements
     flags = np.zeros(P.nelem, np.uint8)
     flags[0] = 1
     Pt = gpu_patch(spec, trimflags=flags)
-    with pytest.raises(capi.IgabError) as ei:
-        Pt.norms(xi1d, w1d, np.zeros(n))
-    assert ei.value.status == capi.UNSUPPORTED
+    nt = Pt.dofmap()[1]
+    det = Pt.evalTensor(xi1d, order=1, want=("detJ",))["detJ"].reshape(P.nelem, -1)
+    area = (det[1:] * np.outer(w1d[1], w1d[0]).reshape(-1)).sum()
+    r = Pt.norms(xi1d, w1d, np.ones(nt))
+    assert abs(r[0] - area) <= 1e-12 * area and abs(r[1]) <= 1e-20 + 1e-12 * area
 
 
 @pytest.mark.parametrize("name", ["cylinder_p3", "cylinder_p4"])
@@ -1271,6 +1275,17 @@ def test_trimmed_patch_poisson_end_to_end():
     assert np.abs(vg - vals).max() <= 1e-14 * np.abs(vals).max() and np.abs(bg - bd).max() <= 1e-14 * np.abs(bd).max()
     with pytest.raises(capi.IgabError):  # the trimmed list must be ascending
         P.globalAssemble(capi.ASM_POISSON, [x, x], [wg, wg], trimmed=(np.array(trimmed[::-1], np.int32), off, xi, w))
+    # L2 norm and energy of a field on the trimmed patch (u numbered like the trimmed basis) = the quadratic forms of
+    # the trimmed mass / stiffness matrices assembled above by a different kernel chain
+    uf = rng.normal(size=ndof)
+    vm, _ = P.globalAssemble(capi.ASM_MASS, [x, x], [wg, wg], trimmed=(np.array(trimmed, np.int32), off, xi, w), want_b=False)
+    Md = sp.csr_matrix((vm, colidx, rowptr), shape=(ndof, ndof))
+    nrm = P.norms([x, x], [wg, wg], uf, trimmed=(elem_pt, xi, w))
+    assert abs(nrm[0] - uf @ (Md @ uf)) <= 1e-12 * abs(nrm[0]) and abs(nrm[1] - uf @ (Ad @ uf)) <= 1e-12 * abs(nrm[1])
+    # without the lists only the full elements count
+    nfull = P.norms([x, x], [wg, wg], uf)
+    vmf, _ = P.globalAssemble(capi.ASM_MASS, [x, x], [wg, wg], want_b=False)   # trimmed elements with the tensor rule ...
+    assert nfull[0] < nrm[0] and nfull[1] < nrm[1] + 1e-12
     # two element ranges accumulated give the same matrix
     v2 = P.csrAssemble(Kall[:7], elem_end=7)
     v2 = P.csrAssemble(Kall[7:], elem_begin=7, values=v2, accumulate=True)
