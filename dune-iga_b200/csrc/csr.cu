@@ -11,6 +11,9 @@
 // touched by a non-empty element, renumbered ascending); a row keeps exactly the columns that share a non-empty element
 // with it, which is the pattern the scatter loop of poisson.py would produce.  Row pointer and column indices are built
 // once per handle (thread per row) and cached on the device; gather, load vector and Dirichlet rows read them.
+#include <algorithm>
+#include <cstdlib>
+
 #include "igab_internal.cuh"
 
 namespace igab {
@@ -209,6 +212,68 @@ __global__ void csr_gather_kernel(CsrGeom G, long long row_begin, long long nrow
       values[base + k] += acc;
     else
       values[base + k] = acc;
+  }
+}
+
+// The same gather organised by ROWS OF THE ELEMENT MATRICES (untrimmed numbering): one warp per matrix row (g, c).  For every
+// element that contains g (fixed order) the warp reads the element matrix row of g -- n contiguous doubles, coalesced --
+// and adds entry (j, d) to the row's accumulator in shared memory at the closed-form position of column h = f + j inside
+// the row's box.  Every K_e entry is read once, in 1000-byte runs (the per-non-zero gather above reads it as scattered
+// 8-byte words); one lane owns one column per element, so the sums have a fixed order: bitwise reproducible.
+__global__ void __launch_bounds__(128) csr_gather_rows_kernel(CsrGeom G, long long row_begin, long long nrows,
+                                                              long long elem_begin, long long elem_end,
+                                                              const double* __restrict__ Ke,
+                                                              const long long* __restrict__ rowptr,
+                                                              double* __restrict__ values, int accumulate, int accStride) {
+  extern __shared__ double sacc[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long row = row_begin + (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= nrows) return;
+  double* acc = sacc + (size_t)warp * accStride;
+  int gd[kMaxDim], lo[kMaxDim], len[kMaxDim];
+  dof_box(G, row / G.ncomp, gd, lo, len);
+  const int c = (int)(row % G.ncomp);
+  const long long base = rowptr[row];
+  const int nn = (int)(rowptr[row + 1] - base);
+  for (int k = lane; k < nn; k += 32) acc[k] = 0.0;
+  const int n = G.nb * G.ncomp;
+  const int o0 = G.p[0] + 1, o1 = G.dim > 1 ? G.p[1] + 1 : 1;
+  const int nel1 = G.dim > 1 ? G.nel[1] : 1;
+  int fa[kMaxDim], fb[kMaxDim];
+  for (int q = 0; q < kMaxDim; ++q) {
+    fa[q] = q < G.dim ? max(gd[q] - G.p[q], 0) : 0;
+    fb[q] = q < G.dim ? min(gd[q], G.n[q] - 1 - G.p[q]) : 0;
+  }
+  __syncwarp();
+  for (int f2 = fa[2]; f2 <= fb[2]; ++f2) {
+    const int e2 = G.dim > 2 ? G.elemOfFirst[2][f2] : 0;
+    if (e2 < 0) continue;
+    for (int f1 = fa[1]; f1 <= fb[1]; ++f1) {
+      const int e1 = G.dim > 1 ? G.elemOfFirst[1][f1] : 0;
+      if (e1 < 0) continue;
+      for (int f0 = fa[0]; f0 <= fb[0]; ++f0) {
+        const int e0 = G.elemOfFirst[0][f0];
+        if (e0 < 0) continue;
+        const long long e = e0 + (long long)G.nel[0] * (e1 + (long long)nel1 * e2);
+        if (e < elem_begin || e >= elem_end) continue;
+        const int i = (gd[0] - f0) + o0 * ((gd[1] - f1) + o1 * (gd[2] - f2));
+        const double* __restrict__ src = Ke + (e - elem_begin) * (long long)n * n + (long long)(i * G.ncomp + c) * n;
+        // column h = f + j sits at ((h2 - lo2) len1 + (h1 - lo1)) len0 + (h0 - lo0) of the row's box
+        const int kb = ((f2 - lo[2]) * len[1] + (f1 - lo[1])) * len[0] + (f0 - lo[0]);
+        for (int jj = lane; jj < n; jj += 32) {
+          const int j = jj / G.ncomp, d = jj - j * G.ncomp;
+          const int j0 = j % o0, r = j / o0, j1 = r % o1, j2 = r / o1;
+          acc[(kb + (j2 * len[1] + j1) * len[0] + j0) * G.ncomp + d] += src[jj];
+        }
+      }
+    }
+  }
+  __syncwarp();
+  for (int k = lane; k < nn; k += 32) {
+    if (accumulate)
+      values[base + k] += acc[k];
+    else
+      values[base + k] = acc[k];
   }
 }
 
@@ -464,11 +529,30 @@ igab_status csr_assemble(igab_patch* p, int ncomp, long long eb, long long ee, c
     }
   }
   if (e == cudaSuccess && rowEnd > rowBegin) {
-    const long long threads = (rowEnd - rowBegin) * 32;
-    csr_gather_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(G, rowBegin, rowEnd, eb, ee, dK, p->d_csr_rowptr,
-                                                                            dV, accumulate);
+    // untrimmed numbering: gather by rows of the element matrices (coalesced reads); trimmed: per non-zero
+    long long maxRow = ncomp;
+    for (int d = 0; d < p->dev.dim; ++d) maxRow *= std::min(2 * p->dev.degree[d] + 1, p->dev.ncp[d]);
+    const int accStride = (int)((maxRow + 1) & ~1LL);
+    const size_t smem = sizeof(double) * 4 * accStride;
+    const char* env = getenv("IGAB_CSR_GATHER");
+    if (!p->d_trim && smem <= 200 * 1024 && !(env && env[0] == '0')) {
+      static bool raised = false;  // one attribute call per process is enough (the limit only grows)
+      if (smem > 48 * 1024 && !raised) {
+        e = cudaFuncSetAttribute(csr_gather_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        raised = e == cudaSuccess;
+      }
+      if (e == cudaSuccess) {
+        const long long blocks = (rowEnd - rowBegin + 3) / 4;
+        csr_gather_rows_kernel<<<(unsigned)blocks, 128, smem, stream>>>(G, rowBegin, rowEnd, eb, ee, dK, p->d_csr_rowptr, dV,
+                                                                       accumulate, accStride);
+      }
+    } else {
+      const long long threads = (rowEnd - rowBegin) * 32;
+      csr_gather_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(G, rowBegin, rowEnd, eb, ee, dK,
+                                                                              p->d_csr_rowptr, dV, accumulate);
+    }
     count_launch();
-    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
   }
   if (space == IGAB_HOST) {
     if (e == cudaSuccess) e = cudaMemcpyAsync(values, dV, sizeof(double) * nnz, cudaMemcpyDeviceToHost, stream);

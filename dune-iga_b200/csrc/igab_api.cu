@@ -470,6 +470,7 @@ void igab_patch_destroy(igab_patch* p) {
     if (p->d_elem_of_first[d]) cudaFree(p->d_elem_of_first[d]);
   if (p->d_csr_rowptr) cudaFree(p->d_csr_rowptr);
   if (p->d_csr_colidx) cudaFree(p->d_csr_colidx);
+  if (p->ga_scratch) cudaFree(p->ga_scratch);
   if (p->d_dofc_map) cudaFree(p->d_dofc_map);
   if (p->d_dofc_inv) cudaFree(p->d_dofc_inv);
   free_sf_workspace(p->sf);
@@ -1191,25 +1192,34 @@ igab_status igab_global_assemble(igab_patch* p, int kind, const double* D, doubl
   long long ktCap = 0;
   auto cleanup = [&]() {
     cudaStreamSynchronize(stream);
-    if (dK) cudaFree(dK);
-    if (dF) cudaFree(dF);
     if (dKt) cudaFree(dKt);
     if (dFt) cudaFree(dFt);
     if (dXi) cudaFree(dXi);
     if (dW) cudaFree(dW);
     if (dElem) cudaFree(dElem);
     if (dOff) cudaFree(dOff);
-    if (space == IGAB_HOST) {
-      if (dV) cudaFree(dV);
-      if (dB) cudaFree(dB);
-    }
   };
-  cudaError_t e = cudaMalloc(&dK, sizeof(double) * chunk * n2);
-  if (e == cudaSuccess && b) e = cudaMalloc(&dF, sizeof(double) * chunk * n);
-  if (space == IGAB_HOST) {
-    dV = dB = nullptr;
-    if (e == cudaSuccess) e = cudaMalloc(&dV, sizeof(double) * std::max<long long>(1, nnz));
-    if (e == cudaSuccess && b) e = cudaMalloc(&dB, sizeof(double) * std::max<long long>(1, nrows));
+  // one scratch block per handle, grown on demand and kept: [element matrices | element vectors | values | load vector]
+  const size_t nK = (size_t)chunk * n2, nF = b ? (size_t)chunk * n : 0;
+  const size_t nV = space == IGAB_HOST ? (size_t)std::max<long long>(1, nnz) : 0;
+  const size_t nB = (space == IGAB_HOST && b) ? (size_t)std::max<long long>(1, nrows) : 0;
+  const size_t need = nK + nF + nV + nB + 8;
+  cudaError_t e = cudaSuccess;
+  if (p->ga_cap < need) {
+    cudaStreamSynchronize(stream);
+    if (p->ga_scratch) cudaFree(p->ga_scratch);
+    p->ga_scratch = nullptr;
+    p->ga_cap = 0;
+    e = cudaMalloc(&p->ga_scratch, sizeof(double) * need);
+    if (e == cudaSuccess) p->ga_cap = need;
+  }
+  if (e == cudaSuccess) {
+    dK = p->ga_scratch;
+    dF = b ? dK + nK : nullptr;
+    if (space == IGAB_HOST) {
+      dV = dK + nK + nF;
+      dB = b ? dV + nV : nullptr;
+    }
   }
   if (e == cudaSuccess && nlist > 0) {
     const long long np = offset[nlist];

@@ -211,6 +211,9 @@ struct igab_patch {
   int32_t* d_dofc_inv = nullptr;   // compacted -> original
   long long ndof_compact = 0;
   int32_t* d_csr_colidx = nullptr;
+  // igab_global_assemble: element-matrix chunk and (host-space calls) value / load-vector staging, kept between calls
+  double* ga_scratch = nullptr;
+  size_t ga_cap = 0;  // doubles
   // reduction scratch
   double* d_red = nullptr;
   int red_cap = 0;

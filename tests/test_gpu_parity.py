@@ -1305,7 +1305,7 @@ def test_trimmed_patch_poisson_end_to_end():
 
 @pytest.mark.parametrize("name,kind", [("plate_hole_p2", capi.ASM_POISSON), ("cylinder_p3", capi.ASM_MASS),
                                        ("plate_hole_p2", capi.ASM_ELASTICITY), ("cylinder_p4", capi.ASM_POISSON)])
-def test_global_assemble_one_call_matches_the_stepwise_path(name, kind):
+def test_global_assemble_one_call_matches_the_stepwise_path(name, kind, monkeypatch):
     """igab_global_assemble (the whole globalAssembler in one call, element matrices kept on the device in chunks)
     against element matrices -> csrAssemble -> rhsAssemble, host and device outputs."""
     spec = PFT.small_patch(name)
@@ -1325,6 +1325,10 @@ def test_global_assemble_one_call_matches_the_stepwise_path(name, kind):
     assert np.array_equal(vd.cpu().numpy(), v) and np.array_equal(bd.cpu().numpy(), b)
     v2, b2 = P.globalAssemble(kind, xi, w, D=D, fconst=0.7, want_b=False)
     assert b2 is None and np.array_equal(v2, v)
+    # the two gather kernels (by rows of the element matrices / per non-zero) add in the same order: identical bits
+    monkeypatch.setenv("IGAB_CSR_GATHER", "0")
+    assert np.array_equal(P.csrAssemble(Ke, ncomp), vref)
+    monkeypatch.delenv("IGAB_CSR_GATHER")
     # element ranges (a rank's slab): the shares add up to the whole system; an empty range gives zeros
     h = P.nelem // 3
     va, ba = P.globalAssemble(kind, xi, w, D=D, fconst=0.7, elem_end=h)
