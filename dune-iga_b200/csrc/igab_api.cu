@@ -1185,7 +1185,9 @@ igab_status igab_global_assemble(igab_patch* p, int kind, const double* D, doubl
   int64_t nrows = 0, nnz = 0;
   igab_status st = csr_pattern(p, ncomp, &nrows, &nnz, nullptr, nullptr, IGAB_HOST, stream);
   if (st) return st;
-  const long long chunk = std::max(1LL, std::min(std::max(1LL, nrange), (1024LL << 20) / (8 * n2)));  // <= 1 GB of element matrices
+  long long chunk = std::max(1LL, (1024LL << 20) / (8 * n2));  // <= 1 GB of element matrices per chunk
+  if (const char* env = getenv("IGAB_GA_CHUNK_ELEMS")) chunk = std::max(1L, atol(env));  // test knob
+  chunk = std::min(chunk, std::max(1LL, nrange));
   double *dK = nullptr, *dF = nullptr, *dV = values, *dB = b, *dKt = nullptr, *dFt = nullptr, *dXi = nullptr, *dW = nullptr;
   int32_t* dElem = nullptr;
   int64_t* dOff = nullptr;
@@ -1237,6 +1239,25 @@ igab_status igab_global_assemble(igab_patch* p, int kind, const double* D, doubl
     cleanup();
     return st;
   }
+  // overlap of the value D2H with the assembly of later chunks (host outputs, untrimmed numbering, non-empty range)
+  bool overlap = space == IGAB_HOST && !p->d_trim && nrange > 0;
+  cudaEvent_t evt = nullptr;
+  const int dl = p->dev.dim - 1;
+  long long perLayer = 1, dofStride = 1, rowsOut = 0;
+  for (int d = 0; d < dl; ++d) {
+    perLayer *= p->dev.nel[d];
+    dofStride *= p->dev.ncp[d];
+  }
+  if (overlap) {
+    if (!p->stage_stream) e = cudaStreamCreateWithFlags(&p->stage_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&evt, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+      overlap = false;
+      evt = nullptr;
+      e = cudaSuccess;
+      cudaGetLastError();
+    }
+  }
   long long k0 = 0;  // first trimmed list entry not yet consumed
   while (k0 < nlist && elem[k0] < elem_begin) ++k0;
   if (nrange == 0) {  // nothing to add: the caller still gets a defined (zero) result
@@ -1273,12 +1294,35 @@ igab_status igab_global_assemble(igab_patch* p, int kind, const double* D, doubl
     k0 = k1;
     if (!st) st = csr_assemble(p, ncomp, eb, ee, dK, nullptr, dV, eb > elem_begin, IGAB_DEVICE, stream);
     if (!st && b) st = rhs_assemble(p, ncomp, eb, ee, dF, dB, eb > elem_begin, IGAB_DEVICE, stream);
+    // host outputs: the rows below the next chunk's first row are final -- their values leave on the copy stream while
+    // the next chunk is assembled (untrimmed numbering: rows of a k-slab of elements are one contiguous range)
+    if (!st && overlap) {
+      long long done = nrows;
+      if (ee < elem_end) done = (long long)(p->hspan[dl][(int)(ee / perLayer)] - p->dev.degree[dl]) * dofStride * ncomp;
+      if (done > rowsOut) {
+        const long long z0 = p->csr_rowptr_host[rowsOut], z1 = p->csr_rowptr_host[done];
+        e = cudaEventRecord(evt, stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(p->stage_stream, evt, 0);
+        if (e == cudaSuccess && z1 > z0)
+          e = cudaMemcpyAsync(values + z0, dV + z0, sizeof(double) * (z1 - z0), cudaMemcpyDeviceToHost, p->stage_stream);
+        if (e != cudaSuccess) st = cuda_fail(e, "global_assemble: overlapped D2H");
+        rowsOut = done;
+      }
+    }
   }
   if (!st && space == IGAB_HOST) {
-    e = cudaMemcpyAsync(values, dV, sizeof(double) * nnz, cudaMemcpyDeviceToHost, stream);
+    if (overlap) {
+      e = cudaStreamSynchronize(p->stage_stream);
+    } else {
+      e = cudaMemcpyAsync(values, dV, sizeof(double) * nnz, cudaMemcpyDeviceToHost, stream);
+    }
     if (e == cudaSuccess && b) e = cudaMemcpyAsync(b, dB, sizeof(double) * nrows, cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) st = cuda_fail(e, "global_assemble: D2H");
+  }
+  if (evt) {
+    cudaStreamSynchronize(p->stage_stream);
+    cudaEventDestroy(evt);
   }
   cleanup();
   return st;

@@ -1325,6 +1325,13 @@ def test_global_assemble_one_call_matches_the_stepwise_path(name, kind, monkeypa
     assert np.array_equal(vd.cpu().numpy(), v) and np.array_equal(bd.cpu().numpy(), b)
     v2, b2 = P.globalAssemble(kind, xi, w, D=D, fconst=0.7, want_b=False)
     assert b2 is None and np.array_equal(v2, v)
+    # many small chunks (the value D2H of finished rows overlaps the assembly of later chunks): same bits
+    monkeypatch.setenv("IGAB_GA_CHUNK_ELEMS", "3")
+    vc, bc = P.globalAssemble(kind, xi, w, D=D, fconst=0.7)
+    vcd, bcd = P.globalAssemble(kind, xi, w, D=D, fconst=0.7, device=True)
+    monkeypatch.delenv("IGAB_GA_CHUNK_ELEMS")
+    assert np.array_equal(vc, vcd.cpu().numpy()) and np.array_equal(bc, bcd.cpu().numpy())
+    assert np.abs(vc - v).max() <= 1e-14 * np.abs(v).max() and np.abs(bc - b).max() <= 1e-14 * np.abs(b).max()
     # the two gather kernels (by rows of the element matrices / per non-zero) add in the same order: identical bits
     monkeypatch.setenv("IGAB_CSR_GATHER", "0")
     assert np.array_equal(P.csrAssemble(Ke, ncomp), vref)
