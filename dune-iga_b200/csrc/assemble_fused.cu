@@ -962,6 +962,27 @@ igab_status launch_elas_sf(const PatchDev& Pd, SfWorkspace& ws, const double* D_
   return IGAB_OK;
 }
 
+// degrees the dense-Gram kernels were never built for (p = 5): sum-factorised contraction only
+template <int P, int Q>
+igab_status launch_sf_only(const PatchDev& Pd, SfWorkspace& ws, bool mass, double fconst, long long eb, long long nel,
+                           const double* const* w_dev, double* Ke, double* fe, cudaStream_t stream) {
+  const void* fn = mass ? (const void*)gram_sf_kernel<P, Q, 1> : (const void*)gram_sf_kernel<P, Q, 0>;
+  const size_t sm = (size_t)(mass ? SCfg<P, Q, 1>::SZ_TOTAL : SCfg<P, Q, 0>::SZ_TOTAL) * sizeof(double);
+  const ElasCoef nocoef{};
+  KernelCfg kc;
+  if (igab_status cst = kernel_config(fn, 256, sm, &kc)) return cst;
+  const unsigned grid = (unsigned)std::min<long long>(nel, (long long)kc.blocksPerSm * kc.sms);
+  if (mass)
+    gram_sf_kernel<P, Q, 1><<<grid, 256, sm, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0], w_dev[1],
+                                                      w_dev[2], nocoef, fconst, Ke, fe);
+  else
+    gram_sf_kernel<P, Q, 0><<<grid, 256, sm, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0], w_dev[1],
+                                                      w_dev[2], nocoef, fconst, Ke, fe);
+  count_launch();
+  IGAB_CUDA_TRY(cudaGetLastError());
+  return IGAB_OK;
+}
+
 template <int P, int Q>
 igab_status launch_pq(const PatchDev& Pd, SfWorkspace& ws, bool mass, double fconst, long long eb, long long nel,
                       const double* const* w_dev, double* Ke, double* fe, cudaStream_t stream) {
@@ -1015,6 +1036,8 @@ bool gram_fused_supported(const PatchDev& P, int kind, const int* nq1) {
   // full Gauss rule (p+1 points per direction), the over-integrated p+2 rule, and at p = 4 the reference's default rule
   // (order dim * max(p) = 12 -> 7 points per direction, nurbsgridentity.hh:123-124)
   const int p = P.degree[0], q = nq1[0];
+  // p = 5: sum-factorised kernel only; 7 points fit the 227 KB of shared memory for the mass matrix only (Poisson: 233 KB)
+  if (p == 5) return (kind == IGAB_ASM_POISSON && q == 6) || (kind == IGAB_ASM_MASS && (q == 6 || q == 7));
   return p >= 2 && p <= 4 && (q == p + 1 || q == p + 2 || (p == 4 && q == 7));
 }
 
@@ -1048,6 +1071,8 @@ igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* 
     return IGAB_UNSUPPORTED;
   }
   const bool mass = kind == IGAB_ASM_MASS;
+  if (P.degree[0] == 5 && nq1[0] == 6) return launch_sf_only<5, 6>(P, ws, mass, fconst, eb, nel, w1d_dev, Ke, fe, stream);
+  if (P.degree[0] == 5 && nq1[0] == 7) return launch_sf_only<5, 7>(P, ws, mass, fconst, eb, nel, w1d_dev, Ke, fe, stream);
 #define IGAB_PQ_CASE(PP, QQ) \
   if (P.degree[0] == PP && nq1[0] == QQ) return launch_pq<PP, QQ>(P, ws, mass, fconst, eb, nel, w1d_dev, Ke, fe, stream);
   IGAB_PQ_CASE(2, 3) IGAB_PQ_CASE(2, 4) IGAB_PQ_CASE(3, 4) IGAB_PQ_CASE(3, 5) IGAB_PQ_CASE(4, 5) IGAB_PQ_CASE(4, 6)

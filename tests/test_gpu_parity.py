@@ -1115,6 +1115,26 @@ def test_fused_3d_element_matrices_both_contractions(p, extra, kind, sf, monkeyp
     assert relerr(f, fref) <= TOL
 
 
+@pytest.mark.parametrize("kind,q", [(capi.ASM_POISSON, 6), (capi.ASM_MASS, 6), (capi.ASM_MASS, 7)])
+def test_fused_3d_element_matrices_p5(kind, q):
+    """p = 5 (216 functions): the sum-factorised kernel alone (one block per SM, general stage-2 tile loop) against the
+    oracle, one fused launch."""
+    rng = np.random.default_rng(55)
+    pd = PD.thickCylinder(5, (1, 1, 0))
+    cp = pd.cp.copy()
+    cp[:, 3] *= rng.uniform(0.8, 1.2, cp.shape[0])
+    spec = dict(degree=pd.degree, knots=pd.knotSpans, cp=cp, dimworld=3)
+    Pp = port_for(spec)
+    P = gpu_patch(spec)
+    x, w = PD.gaussLegendre01(q)
+    Kref, fref = Pp.assemble(kind, [x] * 3, [w] * 3, fconst=0.4, elem_begin=1, elem_end=4)
+    l0 = capi.launch_count()
+    K, f = P.assemble(kind, [x] * 3, [w] * 3, fconst=0.4, elem_begin=1, elem_end=4)
+    assert capi.launch_count() - l0 <= 4
+    assert relerr(K.reshape(3, -1), Kref.reshape(3, -1)) <= TOL, relerr(K.reshape(3, -1), Kref.reshape(3, -1))
+    assert relerr(f, fref) <= TOL
+
+
 def test_device_path_is_cuda_graph_capturable():
     """The device-resident entry points enqueue on the caller's stream without host synchronisation (once the rule is
     staged), so a quadrature loop can be captured in a CUDA graph and replayed -- here: evaluation + fused element
