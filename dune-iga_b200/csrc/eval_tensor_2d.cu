@@ -112,7 +112,7 @@ __device__ __forceinline__ void flush_field(double* __restrict__ slab, const dou
 // LIST = false: tensor rule, univariate rows from the K1 tables.  LIST = true: arbitrary element-local points (trimmed
 // batches, utils/fillquadraturerule.hh:8-19): rows computed per point with ders1d_reg_rd (A2.3 in registers, tabulated reciprocals).
 template <int DW, int P, int Q, int ORDER, bool LIST>
-__global__ void __launch_bounds__(128, (ORDER >= 2 ? 3 : 4)) eval_2d_kernel(PatchDev Pd, long long elem_begin, long long npts,
+__global__ void __launch_bounds__(128, (ORDER >= 2 ? 3 : (P <= 2 ? 5 : 4))) eval_2d_kernel(PatchDev Pd, long long elem_begin, long long npts,
                                                       const double* __restrict__ tab0, const double* __restrict__ tab1,
                                                       const int* __restrict__ elemList, const double* __restrict__ xiList,
                                                       EvalOutDev out) {
