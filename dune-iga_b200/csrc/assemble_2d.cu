@@ -467,6 +467,9 @@ igab_status dispatch_a2(int p, int q, const PatchDev& Pd, const Elas2Coef& coef,
   IGAB_A2_CASE(1, 2) IGAB_A2_CASE(1, 3)
   IGAB_A2_CASE(2, 2) IGAB_A2_CASE(2, 3) IGAB_A2_CASE(2, 4)
   IGAB_A2_CASE(3, 3) IGAB_A2_CASE(3, 4) IGAB_A2_CASE(3, 5)
+  if constexpr (KIND != IGAB_ASM_ELASTICITY) {  // p = 4: 25 functions, one element per warp; scalar problems only
+    IGAB_A2_CASE(4, 4) IGAB_A2_CASE(4, 5)
+  }
 #undef IGAB_A2_CASE
   set_error("assemble: no fused 2-D kernel for this (degree, rule)");
   return IGAB_UNSUPPORTED;
@@ -476,10 +479,11 @@ igab_status dispatch_a2(int p, int q, const PatchDev& Pd, const Elas2Coef& coef,
 
 bool assemble2d_supported(const PatchDev& P, int kind, const int* nq1) {
   if (P.dim != 2 || (P.dw != 2 && P.dw != 3)) return false;
-  if (P.degree[0] != P.degree[1] || P.degree[0] < 1 || P.degree[0] > 3) return false;
+  if (P.degree[0] != P.degree[1] || P.degree[0] < 1 || P.degree[0] > 4) return false;
   // rules with p, p+1 or p+2 points per direction (p+1 = full Gauss; dune/python/test/poisson.py:44 uses order 3 = 2 points)
   const int p = P.degree[0], q = nq1[0];
   if (nq1[1] != q || q < p || q > p + 2 || q < 2) return false;
+  if (p == 4 && (q > 5 || kind == IGAB_ASM_ELASTICITY)) return false;  // q^2 <= 32 lanes; scalar problems
   if (kind == IGAB_ASM_ELASTICITY) return P.dw == 2;
   return kind == IGAB_ASM_POISSON || kind == IGAB_ASM_MASS;
 }

@@ -973,11 +973,11 @@ def test_warp_per_element_kernel_general_degrees_and_rules(case):
     assert P.evalTensor(xi1d, order=1, elem_begin=1, elem_end=1)["N"].shape[0] == 0
 
 
-@pytest.mark.parametrize("p", [1, 2, 3])
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
 @pytest.mark.parametrize("dw,kind", [(2, capi.ASM_POISSON), (2, capi.ASM_MASS), (2, capi.ASM_ELASTICITY),
                                      (3, capi.ASM_POISSON), (3, capi.ASM_MASS)])
 def test_fused_2d_element_matrices(p, dw, kind):
-    """assemble2d_kernel (2-D patches, p = 1..3, fused evaluation + contraction) against the oracle and against the
+    """assemble2d_kernel (2-D patches, p = 1..3 and p = 4 for the scalar problems, fused evaluation + contraction) against the oracle and against the
     general B-stack path, on a random patch with repeated knots; odd element ranges exercise the partial last group of
     a warp; a non-symmetric D exercises the mirrored coefficients of the elasticity combination."""
     rng = np.random.default_rng(50 + 7 * p + dw + 3 * kind)
