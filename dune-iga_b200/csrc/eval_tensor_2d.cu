@@ -112,7 +112,7 @@ __device__ __forceinline__ void flush_field(double* __restrict__ slab, const dou
 // LIST = false: tensor rule, univariate rows from the K1 tables.  LIST = true: arbitrary element-local points (trimmed
 // batches, utils/fillquadraturerule.hh:8-19): rows computed per point with ders1d_reg_rd (A2.3 in registers, tabulated reciprocals).
 template <int DW, int P, int Q, int ORDER, bool LIST>
-__global__ void __launch_bounds__(128, (ORDER >= 2 ? 3 : (P <= 2 ? 5 : 4))) eval_2d_kernel(PatchDev Pd, long long elem_begin, long long npts,
+__global__ void __launch_bounds__(128, (ORDER >= 2 ? 3 : (P <= 2 ? 5 : (P >= 4 ? 2 : 4)))) eval_2d_kernel(PatchDev Pd, long long elem_begin, long long npts,
                                                       const double* __restrict__ tab0, const double* __restrict__ tab1,
                                                       const int* __restrict__ elemList, const double* __restrict__ xiList,
                                                       EvalOutDev out) {
@@ -323,6 +323,10 @@ igab_status dispatch_pq(int p, int q, const PatchDev& Pd, SfWorkspace& ws, const
   if (p == 2 && q == 3) return launch_2d<DW, 2, 3, ORDER>(Pd, ws, src, xi, nelem, out, stream);
   if (p == 2 && q == 4) return launch_2d<DW, 2, 4, ORDER>(Pd, ws, src, xi, nelem, out, stream);
   if (p == 3 && q == 4) return launch_2d<DW, 3, 4, ORDER>(Pd, ws, src, xi, nelem, out, stream);
+  if (p == 3 && q == 5) return launch_2d<DW, 3, 5, ORDER>(Pd, ws, src, xi, nelem, out, stream);
+  if constexpr (ORDER <= 1) {
+    if (p == 4 && q == 5) return launch_2d<DW, 4, 5, ORDER>(Pd, ws, src, xi, nelem, out, stream);
+  }
   set_error("eval_tensor: no 2-D kernel for this (degree, rule)");
   return IGAB_UNSUPPORTED;
 }
@@ -392,7 +396,8 @@ bool eval_tensor_2d_supported(const PatchDev& P, const int* nq1, int order, cons
   if (P.degree[0] != P.degree[1] || nq1[0] != nq1[1]) return false;
   if (order < 0 || order > 2) return false;
   const int p = P.degree[0], q = nq1[0];
-  return (p == 1 && q == 2) || (p == 2 && q == 3) || (p == 2 && q == 4) || (p == 3 && q == 4);
+  return (p == 1 && q == 2) || (p == 2 && q == 3) || (p == 2 && q == 4) || (p == 3 && q == 4) || (p == 3 && q == 5) ||
+         (p == 4 && q == 5 && order <= 1 && !out.d2N && !out.H);
 }
 
 igab_status launch_eval_tensor_2d(const PatchDev& P, SfWorkspace& ws, const PointSource& src,
