@@ -25,7 +25,9 @@ EXPORTS = ("igab_last_error_string", "igab_version", "igab_launch_count", "igab_
            "igab_patch_update_control_points", "igab_patch_spans", "igab_patch_dofmap", "igab_eval_tensor",
            "igab_eval_points", "igab_partial", "igab_assemble", "igab_reduce_volume", "igab_csr_pattern",
            "igab_csr_assemble", "igab_eval_faces", "igab_refine_apply", "igab_surface_forms", "igab_geometry_local", "igab_reduce_norms", "igab_local_keys", "igab_rhs_assemble",
-           "igab_csr_dirichlet", "igab_assemble_points", "igab_global_assemble", "igab_reduce_volume_trimmed", "igab_reduce_norms_trimmed")
+           "igab_csr_dirichlet", "igab_assemble_points", "igab_global_assemble", "igab_reduce_volume_trimmed", "igab_reduce_norms_trimmed",
+           "igab_partition_slab", "igab_interface_row_ranges", "igab_comm_unique_id", "igab_comm_create",
+           "igab_comm_destroy", "igab_comm_info", "igab_exchange_interface_rows")
 
 
 class EvalOut(C.Structure):
@@ -97,6 +99,15 @@ def lib():
                                         dp]
         L.igab_reduce_volume.argtypes = [C.c_void_p, C.c_int64, C.c_int64, ip, C.POINTER(dp), C.POINTER(dp),
                                          C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
+        L.igab_partition_slab.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.igab_interface_row_ranges.argtypes = [C.c_int, ip, ip, C.POINTER(dp), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                C.c_void_p]
+        L.igab_comm_unique_id.argtypes = [C.c_void_p]
+        L.igab_comm_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.igab_comm_destroy.argtypes = [C.c_void_p]
+        L.igab_comm_info.argtypes = [C.c_void_p, ip, ip]
+        L.igab_exchange_interface_rows.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                   C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -129,6 +140,10 @@ def _ptr(a):
         assert a.is_contiguous()
         return a.data_ptr(), (DEVICE if a.is_cuda else HOST)
     raise TypeError("expected numpy array or CUDA tensor")
+
+
+def _comm(c):
+    return c.comm if isinstance(c, Communicator) else c
 
 
 def _rule_arrays(rule1d):
@@ -173,7 +188,8 @@ def refineApply(pd, direction, T, newKnots, newDegree=None):
 
 
 def pinned_empty(shape, dtype=np.float64):
-    """numpy array over page-locked memory from igab_host_alloc (freed when the array is collected)."""
+    """numpy array over page-locked memory from igab_host_alloc; release it with pinned_free(arr) (views of the array
+    must not outlive that call -- nothing is freed behind the caller's back)."""
     n = int(np.prod(shape)) * np.dtype(dtype).itemsize
     p = C.c_void_p()
     _check(lib().igab_host_alloc(C.byref(p), max(n, 1)))
@@ -470,6 +486,20 @@ class Patch:
                                           _ptr(b)[0] if b is not None else None, vs, stream))
         return values, b
 
+    def exchangeInterfaceRows(self, comm, values=None, b=None, ncomp=1, elem_bounds=None, stream=None):
+        """In place: complete the rows of the sharded global matrix / load vector that several ranks touch
+        (igab_exchange_interface_rows; comm = Communicator or a raw ncclComm_t)."""
+        va, vs = _ptr(values)
+        ba, bs = _ptr(b)
+        space = vs if vs is not None else bs
+        if vs is not None and bs is not None and vs != bs:
+            raise ValueError("values and b must live in the same memory space")
+        eb = np.ascontiguousarray(elem_bounds, dtype=np.int64) if elem_bounds is not None else None
+        c = comm.comm if isinstance(comm, Communicator) else comm
+        _check(lib().igab_exchange_interface_rows(self.h, ncomp, eb.ctypes.data if eb is not None else None, va, ba, space,
+                                                  c, stream))
+        return values, b
+
     def volume(self, xi1d, w1d, elem_begin=0, elem_end=None, nccl_comm=None, stream=None, trimmed=None):
         """sum of detJ w over the tensor rule of the (full) elements [elem_begin, elem_end); trimmed = (elem [npts],
         xi [npts][dim], w [npts]) adds the trimmed elements' own points (quadrature.trimmedBatch)."""
@@ -479,6 +509,7 @@ class Patch:
         wa, wp = _rule_arrays(w1d)
         nq1 = _i32([len(a) for a in xa])
         r = C.c_double()
+        nccl_comm = _comm(nccl_comm)
         if trimmed is not None:
             te, tx, tw = _i32(trimmed[0]), _f64(trimmed[1]), _f64(trimmed[2])
             _check(lib().igab_reduce_volume_trimmed(self.h, elem_begin, elem_end, nq1.ctypes.data_as(ip), xp, wp, len(te),
@@ -501,6 +532,7 @@ class Patch:
         wa, wp = _rule_arrays(w1d)
         nq1 = _i32([len(a) for a in xa])
         r = (C.c_double * 2)()
+        nccl_comm = _comm(nccl_comm)
         if trimmed is not None:  # (elem [npts], xi [npts][dim], w [npts]): the trimmed elements' own points
             te, tx, tw = _i32(trimmed[0]), _f64(trimmed[1]), _f64(trimmed[2])
             _check(lib().igab_reduce_norms_trimmed(self.h, elem_begin, elem_end, nq1.ctypes.data_as(ip), xp, wp, ua, ncomp,
@@ -510,6 +542,67 @@ class Patch:
         _check(lib().igab_reduce_norms(self.h, elem_begin, elem_end, nq1.ctypes.data_as(ip), xp, wp, ua, ncomp, us, r,
                                        nccl_comm, stream))
         return np.array([r[0], r[1]])
+
+
+class Communicator:
+    """ncclComm_t created through the C-ABI (igab_comm_unique_id / igab_comm_create).  `bcast(bytes_or_None) -> bytes`
+    distributes rank 0's 128-byte id with whatever the host program has (MPI in a DUNE program); fromTorch uses an
+    initialised torch.distributed process group for that and nothing else."""
+
+    def __init__(self, rank, world, bcast):
+        uid = (C.c_char * 128)()
+        if rank == 0:
+            _check(lib().igab_comm_unique_id(uid))
+        raw = bcast(bytes(uid.raw) if rank == 0 else None)
+        uid = (C.c_char * 128).from_buffer_copy(raw)
+        self.comm = C.c_void_p()
+        _check(lib().igab_comm_create(rank, world, uid, C.byref(self.comm)))
+        self.rank, self.world = rank, world
+
+    @classmethod
+    def fromTorch(cls, dist, device=None):
+        import torch
+
+        def bcast(raw):
+            t = torch.zeros(128, dtype=torch.uint8, device=device)
+            if raw is not None:
+                t = torch.tensor(list(raw), dtype=torch.uint8, device=device)
+            if dist.is_initialized() and dist.get_world_size() > 1:
+                dist.broadcast(t, 0)
+            return bytes(t.cpu().tolist())
+        multi = dist.is_initialized()
+        return cls(dist.get_rank() if multi else 0, dist.get_world_size() if multi else 1, bcast)
+
+    def info(self):
+        r, w = C.c_int(), C.c_int()
+        _check(lib().igab_comm_info(self.comm, C.byref(r), C.byref(w)))
+        return r.value, w.value
+
+    def close(self):
+        if getattr(self, "comm", None):
+            lib().igab_comm_destroy(self.comm)
+            self.comm = None
+
+
+def partitionSlab(nel_dir, world, rank):
+    """[elem_begin, elem_end) of `rank` (igab_partition_slab): whole layers of the slowest direction."""
+    n = _i32(nel_dir)
+    eb, ee = C.c_int64(), C.c_int64()
+    _check(lib().igab_partition_slab(len(n), n.ctypes.data, world, rank, C.byref(eb), C.byref(ee)))
+    return eb.value, ee.value
+
+
+def interfaceRowRanges(degree, knotSpans, world, ncomp=1, elem_bounds=None):
+    """(row_begin, row_end) int64 [world]: the rows every rank's slab touches (igab_interface_row_ranges; host only)."""
+    deg = _i32(degree)
+    kn = [_f64(k) for k in knotSpans]
+    kptr = (dp * len(kn))(*[k.ctypes.data_as(dp) for k in kn])
+    nk = _i32([len(k) for k in kn])
+    rb, re = np.zeros(world, dtype=np.int64), np.zeros(world, dtype=np.int64)
+    eb = np.ascontiguousarray(elem_bounds, dtype=np.int64) if elem_bounds is not None else None
+    _check(lib().igab_interface_row_ranges(len(deg), deg.ctypes.data_as(ip), nk.ctypes.data_as(ip), kptr, ncomp, world,
+                                           eb.ctypes.data if eb is not None else None, rb.ctypes.data, re.ctypes.data))
+    return rb, re
 
 
 def localKeys(degree):

@@ -471,6 +471,7 @@ void igab_patch_destroy(igab_patch* p) {
   if (p->d_csr_rowptr) cudaFree(p->d_csr_rowptr);
   if (p->d_csr_colidx) cudaFree(p->d_csr_colidx);
   if (p->ga_scratch) cudaFree(p->ga_scratch);
+  if (p->xch_buf) cudaFree(p->xch_buf);
   if (p->d_dofc_map) cudaFree(p->d_dofc_map);
   if (p->d_dofc_inv) cudaFree(p->d_dofc_inv);
   free_sf_workspace(p->sf);

@@ -214,6 +214,10 @@ struct igab_patch {
   // igab_global_assemble: element-matrix chunk and (host-space calls) value / load-vector staging, kept between calls
   double* ga_scratch = nullptr;
   size_t ga_cap = 0;  // doubles
+  // igab_exchange_interface_rows: receive buffers / staged pieces, host copy of the compaction map (trimmed patches)
+  double* xch_buf = nullptr;
+  size_t xch_cap = 0;  // doubles
+  std::vector<int32_t> dofc_map_host;
   // reduction scratch
   double* d_red = nullptr;
   int red_cap = 0;

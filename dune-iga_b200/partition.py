@@ -4,32 +4,40 @@ Elements are independent on the hot path (no state between elements in dune/iga/
 each rank owns a contiguous range of the x-fastest element index (dune/iga/utils/mdnet.hh:245-257): whole layers of the
 slowest direction.  Knots and control net are replicated; evaluation and element matrices need no collective.  Only
 patch-level scalars (volume, norms) are all-reduced, and rows of the assembled global matrix that belong to DOFs touched
-from both sides of a cut (p layers of n_0 x n_1 basis functions, from g_d = s_d - p_d + l_d, nurbsbasis.hh:576) are
-exchanged with the neighbour.
+by elements of several ranks (from g_d = s_d - p_d + l_d, nurbsbasis.hh:576) are exchanged.
+
+The partition, the row ranges and the exchange itself live behind the C-ABI (igab_partition_slab,
+igab_interface_row_ranges, igab_exchange_interface_rows in csrc/comm.cu: ncclSend / ncclRecv + an ordered add kernel);
+this module is the thin Python face of those calls plus the point-count balancing of trimmed patches.
 """
 import numpy as np
+
+from . import capi
 
 
 def slab_range(nel_dir, world, rank):
     """[elem_begin, elem_end) of `rank`: ceil/floor split of the layers of the slowest direction."""
-    nel_dir = [int(n) for n in nel_dir]
-    layers = nel_dir[-1]
-    per_layer = int(np.prod(nel_dir[:-1])) if len(nel_dir) > 1 else 1
-    base, rem = divmod(layers, world)
-    lo = rank * base + min(rank, rem)
-    hi = lo + base + (1 if rank < rem else 0)
-    return lo * per_layer, hi * per_layer
+    return capi.partitionSlab(nel_dir, world, rank)
 
 
-def weighted_ranges(counts, world):
+def slab_bounds(nel_dir, world):
+    """world + 1 element bounds of the slab partition."""
+    return [slab_range(nel_dir, world, r)[0] for r in range(world)] + [int(np.prod([int(n) for n in nel_dir]))]
+
+
+def weighted_ranges(counts, world, per_layer=None):
     """Trimmed patches: contiguous element ranges with (nearly) equal cumulative point counts.
-    counts[e] = quadrature points of element e (0 for empty elements).  Returns world+1 boundaries."""
+    counts[e] = quadrature points of element e (0 for empty elements).  Returns world+1 boundaries; with per_layer the
+    boundaries are rounded to whole layers of the slowest direction (what the interface-row exchange needs)."""
     counts = np.asarray(counts, dtype=np.int64)
     cum = np.concatenate([[0], np.cumsum(counts)])
     total = cum[-1]
     bounds = [0]
     for r in range(1, world):
-        bounds.append(int(np.searchsorted(cum, total * r / world, side="left")))
+        b = int(np.searchsorted(cum, total * r / world, side="left"))
+        if per_layer:
+            b = int(round(b / per_layer)) * per_layer
+        bounds.append(b)
     bounds.append(len(counts))
     return [min(max(b, bounds[i - 1] if i else 0), len(counts)) for i, b in enumerate(bounds)]
 
@@ -45,56 +53,19 @@ def interface_dofs(dofmap, ranges):
     return out
 
 
-# ---- interface rows of the assembled global matrix (north star: "NCCL ... for the interface rows") ---------------------
-def element_first_dofs(U, p):
-    """First global DOF index (per direction) of every element: span - p with span = findSpanCorrected(p, uq[e], U, e)
-    (dune/iga/nurbsbasis.hh:355-360,576)."""
-    from .patchdata import uniqueKnots
-    U = np.asarray(U, float)
-    uq = uniqueKnots(U)
-    spans = np.searchsorted(U, uq[:-1], side="right") - 1
-    return spans - p
+def touched_row_ranges(pd, world, ncomp=1, elem_bounds=None):
+    """(row_begin, row_end) [world]: the contiguous range of global rows (untrimmed numbering g*ncomp + c) that the
+    elements of every rank's slab touch; two ranks share the intersection of their ranges."""
+    return capi.interfaceRowRanges(pd.degree, pd.knotSpans, world, ncomp, elem_bounds)
 
 
 def interface_row_ranges(pd, world, ncomp=1):
-    """For the slab partition of `pd` over `world` ranks: per cut c (between rank c and c+1) the contiguous global row
-    range [row_begin, row_end) of the DOF layers that elements on BOTH sides touch (p layers of n_0 x n_1 functions
-    for simple knots).  Rows are numbered g*ncomp + comp with g first-direction-fastest."""
-    nel = pd.elementsPerDirection
-    last = pd.patchDim - 1
-    first = element_first_dofs(pd.knotSpans[last], pd.degree[last])
-    per_layer = int(np.prod(pd.ncp[:last])) if last > 0 else 1
-    cuts = []
-    for r in range(world - 1):
-        eb, ee = slab_range(nel, world, r)
-        per_el_layer = int(np.prod(nel[:last])) if last > 0 else 1
-        l_end = ee // per_el_layer  # first element layer of rank r+1
-        if l_end <= 0 or l_end >= nel[last]:
-            cuts.append((0, 0))
-            continue
-        lo = int(first[l_end])                           # lowest DOF layer the right side touches
-        hi = int(first[l_end - 1]) + pd.degree[last]     # highest DOF layer the left side touches
-        cuts.append((lo * per_layer * ncomp, (hi + 1) * per_layer * ncomp))
-    return cuts
+    """Per cut c (between rank c and c+1): the rows [row_begin, row_end) both sides touch -- the intersection of the two
+    neighbours' ranges (p layers of n_0 x n_1 functions for simple knots)."""
+    rb, re = touched_row_ranges(pd, world, ncomp)
+    return [(int(max(rb[c], rb[c + 1])), int(max(min(re[c], re[c + 1]), max(rb[c], rb[c + 1])))) for c in range(world - 1)]
 
 
-def exchange_interface_rows(values, rowptr, cuts, rank, world, dist):
-    """In place: add the neighbour's partial sums on the interface rows (both sides end up with the complete rows).
-    `values` is a torch tensor (CUDA with the nccl backend, CPU with gloo); one send/recv pair per cut."""
-    import torch
-    ops, bufs = [], []
-    for c, (r0, r1) in enumerate(cuts):
-        if r1 <= r0 or rank not in (c, c + 1):
-            continue
-        peer = c + 1 if rank == c else c
-        a, b = int(rowptr[r0]), int(rowptr[r1])
-        recv = torch.empty(b - a, dtype=values.dtype, device=values.device)
-        send = values[a:b].clone()
-        ops += [dist.P2POp(dist.isend, send, peer), dist.P2POp(dist.irecv, recv, peer)]
-        bufs.append((a, b, recv, send))
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
-    for a, b, recv, _ in bufs:
-        values[a:b] += recv
-    return values
+def exchange_interface_rows(P, comm, values=None, b=None, ncomp=1, elem_bounds=None, stream=None):
+    """In place on every rank: add the other ranks' partial sums on the shared rows (igab_exchange_interface_rows)."""
+    return P.exchangeInterfaceRows(comm, values=values, b=b, ncomp=ncomp, elem_bounds=elem_bounds, stream=stream)

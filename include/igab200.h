@@ -292,6 +292,48 @@ igab_status igab_reduce_norms_trimmed(igab_patch* p, int64_t elem_begin, int64_t
                                       igab_memspace u_space, int64_t npts_list, const int32_t* elem, const double* xi,
                                       const double* w, double* result, void* nccl_comm, void* stream);
 
+/* ---- multi-GPU: element slabs, communicator, interface rows ------------------------------------------------------------
+ * One process per GPU; every rank holds the whole patch handle (knots and control net replicated) and owns a contiguous
+ * slab of elements: whole layers of the slowest direction, so that its elements (first direction fastest,
+ * dune/iga/utils/mdnet.hh:245-257), its outputs and the rows it touches are each ONE contiguous range.  Evaluation and
+ * element matrices need no collective; the reductions above take the communicator; the sharded global matrix needs the
+ * exchange below.  The reference is sequential -- the place a DUNE caller hooks this in is the grid view's
+ * communicate() (dune/iga/nurbsleafgridview.hh:163-165).
+ *
+ * igab_partition_slab: [elem_begin, elem_end) of `rank`: ceil / floor split of the n_elem_dir[dim-1] layers.  Host only. */
+igab_status igab_partition_slab(int dim, const int32_t* n_elem_dir, int world, int rank, int64_t* elem_begin,
+                                int64_t* elem_end);
+
+/* Rows of the global system (untrimmed numbering g*ncomp + c) that the elements of every rank touch: the DOF layers
+ * span(l) - p .. span(l') of the slab's first / last element layer (g_d = s_d - p_d + l_d, dune/iga/nurbsbasis.hh:576).
+ * elem_bounds: NULL (igab_partition_slab) or world + 1 ascending multiples of the layer size.  Rows shared by ranks r
+ * and s are the intersection of their ranges; with slabs thinner than the degree that includes ranks that are not
+ * neighbours.  row_begin / row_end [world].  Pure host integer code: needs no device.                                */
+igab_status igab_interface_row_ranges(int dim, const int* degree, const int* nknots, const double* const* knots,
+                                      int ncomp, int world, const int64_t* elem_bounds, int64_t* row_begin,
+                                      int64_t* row_end);
+
+/* NCCL communicator without the caller touching NCCL (resolved from the process with dlsym; libnccl.so.2 otherwise):
+ * rank 0 fills a 128-byte id and distributes it by whatever the host code has (MPI_Bcast in a DUNE program, a file, a
+ * torch.distributed broadcast); every rank then calls igab_comm_create with the CUDA device it drives current.  The
+ * result is an ncclComm_t and may equally be one the caller created itself.                                         */
+igab_status igab_comm_unique_id(void* id128);
+igab_status igab_comm_create(int rank, int world, const void* id128, void** comm);
+igab_status igab_comm_destroy(void* comm);
+igab_status igab_comm_info(void* comm, int* rank, int* world);
+
+/* Completes the rows of the sharded global matrix and load vector: every rank has gathered the element matrices of ITS
+ * slab into the one shared pattern (igab_global_assemble / igab_csr_assemble / igab_rhs_assemble with its element
+ * range), so rows of DOFs that elements of several ranks contain hold partial sums (poisson.py:113-125 split over
+ * ranks).  For every pair of ranks with intersecting row ranges the contiguous value range of the shared rows is sent
+ * both ways (ncclSend / ncclRecv in one group on `stream`), then one kernel adds the contributions in ASCENDING RANK
+ * ORDER: afterwards every rank holds the complete rows it touches, bit-identical on all ranks that hold them.  values
+ * [nnz] of igab_csr_pattern(ncomp) and / or b [nrows], in `space` (host arrays are staged piecewise through the
+ * device); rank and size are the communicator's.  Trimmed patches use the compacted numbering.  elem_bounds as above
+ * and the same on every rank.  Asynchronous on `stream` for device arrays.                                           */
+igab_status igab_exchange_interface_rows(igab_patch* p, int ncomp, const int64_t* elem_bounds, double* values, double* b,
+                                         igab_memspace space, void* nccl_comm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

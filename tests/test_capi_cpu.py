@@ -89,3 +89,46 @@ def test_local_keys_match_oracle_and_reference_diagram():
         assert len(keys) == int(np.prod(np.array(deg) + 1))
     with pytest.raises(capi.IgabError):
         capi.localKeys([9])
+
+
+def test_slab_partition_and_interface_row_planner_host_only():
+    """igab_partition_slab / igab_interface_row_ranges are pure host integer code (no device): the planner's row range of
+    a slab is exactly the set of rows the slab's elements touch through the oracle's DOF map (nurbsbasis.hh:576), also
+    with repeated interior knots, vector-valued numbering, custom layer bounds, thin slabs and empty ranks."""
+    import portbind as PT
+    from dune_iga_b200 import patchdata as PD
+    rng = np.random.default_rng(3)
+    cases = [([2, 3], [[0, 0, 0, .2, .2, .5, .7, 1, 1, 1], [0, 0, 0, 0, .25, .5, .5, .75, 1, 1, 1, 1]]),
+             ([3, 2, 3], [[0, 0, 0, 0, .5, 1, 1, 1, 1], [0, 0, 0, .3, 1, 1, 1],
+                          [0, 0, 0, 0, .1, .2, .3, .3, .6, .8, .9, 1, 1, 1, 1]])]
+    for deg, kn in cases:
+        dim = len(deg)
+        ncp = [len(kn[d]) - deg[d] - 1 for d in range(dim)]
+        cp = np.concatenate([rng.random((int(np.prod(ncp)), dim)), np.ones((int(np.prod(ncp)), 1))], axis=1)
+        O = PT.PortPatch(deg, kn, cp, dim)
+        dof, ndof = O.dofmap()
+        nel = [len(np.unique(k)) - 1 for k in kn]
+        per_layer = int(np.prod(nel[:-1]))
+        for world in (1, 2, 3, nel[-1], nel[-1] + 2):
+            bounds = [capi.partitionSlab(nel, world, r) for r in range(world)]
+            assert bounds[0][0] == 0 and bounds[-1][1] == O.nelem
+            assert all(bounds[i][1] == bounds[i + 1][0] for i in range(world - 1))
+            for ncomp in (1, 3):
+                rb, re = capi.interfaceRowRanges(deg, kn, world, ncomp)
+                for r, (eb, ee) in enumerate(bounds):
+                    if ee == eb:
+                        assert rb[r] == re[r]
+                        continue
+                    t = np.unique(dof[eb:ee])
+                    assert rb[r] == t.min() * ncomp and re[r] == (t.max() + 1) * ncomp
+                    assert len(t) * ncomp == re[r] - rb[r]  # contiguous: whole DOF layers
+        # custom bounds on layer boundaries; anything else is refused
+        eb = [0, per_layer, per_layer, O.nelem]
+        rb, re = capi.interfaceRowRanges(deg, kn, 3, 1, eb)
+        assert rb[1] == re[1] and rb[0] == 0 and re[2] == ndof
+        with pytest.raises(capi.IgabError):
+            capi.interfaceRowRanges(deg, kn, 2, 1, [0, 1, O.nelem])
+    # thin slabs: 4 element layers of degree 3 over 4 ranks -> ranks 0 and 3 share DOF layers without being neighbours
+    pd = PD.thickCylinder(3, (1, 1, 2))
+    rb, re = capi.interfaceRowRanges(pd.degree, pd.knotSpans, 4)
+    assert min(re[0], re[3]) > max(rb[0], rb[3])

@@ -27,6 +27,31 @@ def _torchrun(script, port):
     return subprocess.run(cmd, capture_output=True, text=True, timeout=600)
 
 
+def test_single_rank_communicator_through_the_c_abi():
+    """The product's own communicator path on a one-GPU box: igab_comm_unique_id / igab_comm_create with one rank, the
+    reductions all-reduce through it (ncclAllReduce on the call's stream) and the interface-row exchange finds no peer."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import igab200  # noqa: F401
+    from dune_iga_b200 import capi, patchdata as PD
+    comm = capi.Communicator(0, 1, lambda raw: raw)
+    assert comm.info() == (0, 1)
+    pd = PD.thickCylinder(3, (3, 3, 3))
+    P = capi.Patch.fromPatchData(pd)
+    x, w = PD.gaussLegendre01(4)
+    v0 = P.volume([x] * 3, [w] * 3)
+    v1 = P.volume([x] * 3, [w] * 3, nccl_comm=comm)
+    assert v0 == v1 and abs(v0 - np.pi / 4 * 3.0 * 3.0) < 1e-9
+    u = np.random.default_rng(1).normal(size=P.dofmap()[1])
+    assert np.array_equal(P.norms([x] * 3, [w] * 3, u), P.norms([x] * 3, [w] * 3, u, nccl_comm=comm))
+    vals, b = P.globalAssemble(capi.ASM_POISSON, [x] * 3, [w] * 3)
+    keep = vals.copy()
+    P.exchangeInterfaceRows(comm, values=vals, b=b)
+    assert np.array_equal(keep, vals)
+    comm.close()
+
+
 @needs2
 def test_reductions_all_reduce_over_nccl():
     r = _torchrun("nccl_volume_check.py", 29611)

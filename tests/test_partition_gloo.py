@@ -76,7 +76,39 @@ def test_partition_helpers():
     assert max(loads) - min(loads) <= 2 * 120
 
 
-def _csr_worker(rank, world, port, q):
+def _gloo_exchange(vals, rowptr, rb, re, rank, world):
+    """The algorithm of igab_exchange_interface_rows (csrc/comm.cu) with gloo standing in for ncclSend / ncclRecv: every
+    pair of ranks with intersecting row ranges swaps the value range of the shared rows, contributions are added in
+    ascending rank order."""
+    peers = []
+    for s in range(world):
+        r0, r1 = max(rb[s], rb[rank]), min(re[s], re[rank])
+        if s != rank and r1 > r0:
+            peers.append((s, int(rowptr[r0]), int(rowptr[r1])))
+    own = vals.clone()
+    ops, recv = [], {}
+    for s, a, z in peers:
+        recv[s] = torch.empty(z - a, dtype=vals.dtype)
+        ops += [dist.P2POp(dist.isend, own[a:z].clone(), s), dist.P2POp(dist.irecv, recv[s], s)]
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    acc = torch.zeros_like(vals)
+    seen = torch.zeros(len(vals), dtype=torch.bool)
+    for s in sorted([q[0] for q in peers] + [rank]):
+        if s == rank:
+            a, z = int(rowptr[rb[rank]]), int(rowptr[re[rank]])
+            acc[a:z] = torch.where(seen[a:z], acc[a:z] + own[a:z], own[a:z])
+        else:
+            a, z = next((q[1], q[2]) for q in peers if q[0] == s)
+            acc[a:z] = torch.where(seen[a:z], acc[a:z] + recv[s], recv[s])
+        seen[a:z] = True
+    a, z = int(rowptr[rb[rank]]), int(rowptr[re[rank]])
+    vals[a:z] = acc[a:z]
+    return vals
+
+
+def _csr_worker(rank, world, port, q, name="plate_hole_p2", level=2):
     for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -86,11 +118,11 @@ def _csr_worker(rank, world, port, q):
     import patches_for_tests as PFT
     import portbind as PT
     from dune_iga_b200 import partition, patchdata as PD
-    spec = PFT.small_patch("plate_hole_p2", level=2)
+    spec = PFT.small_patch(name, level=level)
     pd = spec["patch"]
-    P = PT.PortPatch(pd.degree, pd.knotSpans, pd.cp, 2)
-    x, w = PD.gaussLegendre01(3)
-    Ke, _ = P.assemble(0, [x, x], [w, w])
+    P = PT.PortPatch(pd.degree, pd.knotSpans, pd.cp, spec["dimworld"])
+    x, w = PD.gaussLegendre01(max(pd.degree) + 1)
+    Ke, _ = P.assemble(0, [x] * pd.patchDim, [w] * pd.patchDim)
     dof, n = P.dofmap()
     # dense stand-in for the device CSR gather on this GPU-less box: full band pattern, row-major
     rowptr = np.arange(n + 1) * n
@@ -102,13 +134,23 @@ def _csr_worker(rank, world, port, q):
     for e in range(P.nelem):
         np.add.at(full, (dof[e][:, None], dof[e][None, :]), Ke[e])
     cuts = partition.interface_row_ranges(pd, world)
+    rb, re = partition.touched_row_ranges(pd, world)
     vals = torch.from_numpy(mine.reshape(-1).copy())
-    partition.exchange_interface_rows(vals, rowptr, cuts, rank, world, dist)
+    _gloo_exchange(vals, rowptr, rb, re, rank, world)
     got = vals.numpy().reshape(n, n)
     # rows of the DOF layers this rank touches are now complete
     touched = np.unique(dof[eb:ee])
+    assert touched.min() == rb[rank] and touched.max() == re[rank] - 1  # the planner's range is exactly what is touched
     err = np.abs(got[touched] - full[touched]).max() / np.abs(full).max()
-    q.put((rank, cuts, float(err), pd.ncp, pd.degree))
+    # every rank holding a shared row holds the same bits (ascending-rank summation)
+    allv = [None] * world
+    dist.all_gather_object(allv, got)
+    same = True
+    for s in range(world):
+        r0, r1 = max(rb[s], rb[rank]), min(re[s], re[rank])
+        if r1 > r0:
+            same = same and np.array_equal(allv[s][r0:r1], got[r0:r1])
+    q.put((rank, cuts, float(err), pd.ncp, pd.degree, bool(same), [int(v) for v in rb], [int(v) for v in re]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -125,7 +167,28 @@ def test_interface_rows_exchange_two_ranks():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, cuts, err, ncp, deg in res:
-        assert err < 1e-14
+    for rank, cuts, err, ncp, deg, same, rb, re in res:
+        assert err < 1e-14 and same
         (r0, r1), = cuts
         assert (r1 - r0) == deg[1] * ncp[0]  # p layers of n_0 basis functions
+
+
+def test_interface_rows_exchange_thin_slabs_three_and_four_ranks():
+    """Slabs thinner than the degree: a DOF layer is shared by more than two ranks and the outer ranks must receive each
+    other's partial sums too (4 element layers, p = 3 in the slowest direction, 3 and 4 ranks)."""
+    for world in (3, 4):
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        port = 33500 + (os.getpid() % 2000) + world
+        procs = [ctx.Process(target=_csr_worker, args=(r, world, port, q, "cylinder_p3", 2)) for r in range(world)]
+        for p in procs:
+            p.start()
+        res = sorted(q.get(timeout=300) for _ in range(world))
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+        for rank, cuts, err, ncp, deg, same, rb, re in res:
+            assert err < 1e-14 and same, (world, rank, err, same)
+        # rank 0 and rank 2 are not neighbours but share DOF layers
+        rb, re = res[0][6], res[0][7]
+        assert min(re[0], re[2]) > max(rb[0], rb[2])

@@ -1,8 +1,7 @@
 """Multi-GPU check of the patch reduction fused with its NCCL all-reduce (run under torchrun on >= 2 GPUs):
 each rank reduces the volume of its element slab on its own GPU, igab_reduce_volume all-reduces the scalar through the
-process group's NCCL communicator... torch does not expose its ncclComm_t, so this script creates one with the
-NCCL C API (ncclGetUniqueId broadcast through torch.distributed)."""
-import ctypes as C
+communicator the C-ABI created (igab_comm_unique_id on rank 0, the 128-byte id broadcast through torch.distributed,
+igab_comm_create on every rank)."""
 import os
 import sys
 
@@ -17,32 +16,12 @@ import igab200  # noqa: E402,F401
 from dune_iga_b200 import capi, partition, patchdata as PD  # noqa: E402
 
 
-def nccl_lib():
-    import glob
-    import torch as _t
-    cands = glob.glob(os.path.join(os.path.dirname(_t.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so.2"))
-    return C.CDLL(cands[0] if cands else "libnccl.so.2", mode=C.RTLD_GLOBAL)
-
-
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    nccl = nccl_lib()
-    uid = (C.c_char * 128)()
-    if rank == 0:
-        assert nccl.ncclGetUniqueId(C.byref(uid)) == 0
-    t = torch.tensor(list(uid.raw), dtype=torch.uint8, device="cuda")
-    dist.broadcast(t, 0)
-    uid = (C.c_char * 128).from_buffer_copy(bytes(t.cpu().tolist()))
-    comm = C.c_void_p()
-
-    class UID(C.Structure):
-        _fields_ = [("internal", C.c_char * 128)]
-    u = UID()
-    C.memmove(C.byref(u), uid, 128)
-    nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UID, C.c_int]
-    assert nccl.ncclCommInitRank(C.byref(comm), world, u, rank) == 0
+    comm = capi.Communicator.fromTorch(dist, device="cuda")  # igab_comm_unique_id / igab_comm_create
+    assert comm.info() == (rank, world)
 
     pd = PD.thickCylinder(3, (4, 4, 5))
     P = capi.Patch.fromPatchData(pd)
@@ -74,8 +53,7 @@ def main():
         assert len({tuple(v[1]) for v in alln}) == 1
         assert np.abs(sum(np.array(v[0]) for v in alln) - whole_n).max() <= 1e-12 * whole_n.max()
         print("nccl norms check ok")
-    nccl.ncclCommDestroy.argtypes = [C.c_void_p]
-    nccl.ncclCommDestroy(comm)
+    comm.close()
     dist.destroy_process_group()
 
 
