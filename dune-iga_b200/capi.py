@@ -27,7 +27,8 @@ EXPORTS = ("igab_last_error_string", "igab_version", "igab_launch_count", "igab_
            "igab_csr_assemble", "igab_eval_faces", "igab_refine_apply", "igab_surface_forms", "igab_geometry_local", "igab_reduce_norms", "igab_local_keys", "igab_rhs_assemble",
            "igab_csr_dirichlet", "igab_assemble_points", "igab_global_assemble", "igab_reduce_volume_trimmed", "igab_reduce_norms_trimmed",
            "igab_partition_slab", "igab_interface_row_ranges", "igab_comm_unique_id", "igab_comm_create",
-           "igab_comm_destroy", "igab_comm_info", "igab_exchange_interface_rows")
+           "igab_comm_destroy", "igab_comm_info", "igab_exchange_interface_rows", "igab_patch_real_index_maps",
+           "igab_load_vector", "igab_load_vector_points", "igab_global_load_vector")
 
 
 class EvalOut(C.Structure):
@@ -108,6 +109,15 @@ def lib():
         L.igab_comm_info.argtypes = [C.c_void_p, ip, ip]
         L.igab_exchange_interface_rows.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                                    C.c_void_p, C.c_void_p]
+        L.igab_patch_real_index_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int,
+                                                 C.c_void_p]
+        L.igab_load_vector.argtypes = [C.c_void_p, C.c_int64, C.c_int64, ip, C.POINTER(dp), C.POINTER(dp), C.c_void_p,
+                                       C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.igab_load_vector_points.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.igab_global_load_vector.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, ip, C.POINTER(dp), C.POINTER(dp),
+                                              C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -272,6 +282,15 @@ class Patch:
         _check(lib().igab_patch_dofmap(self.h, out.ctypes.data, C.byref(n), HOST, None))
         return out, n.value
 
+    def realIndexMaps(self):
+        """(direct_of_real [n_real], real_of_direct [n_elem], -1 for empty elements): getDirectIndex<0> / getRealIndex<0>
+        of the reference's trimmed patch (nurbspatch.hh:599-631)."""
+        dor = np.empty(self.nelem, dtype=np.int32)
+        rod = np.empty(self.nelem, dtype=np.int32)
+        n = C.c_int64()
+        _check(lib().igab_patch_real_index_maps(self.h, dor.ctypes.data, rod.ctypes.data, C.byref(n), HOST, None))
+        return dor[:n.value].copy(), rod
+
     # ---- evaluation
     def shapes(self, npts):
         return dict(N=(npts, self.nb), dN=(npts, self.nb, self.dim), d2N=(npts, self.nb, self.nh),
@@ -363,6 +382,69 @@ class Patch:
                                           len(elem), elem.ctypes.data, offset.ctypes.data, xi.ctypes.data, w.ctypes.data,
                                           Ke.ctypes.data, fe.ctypes.data if fe is not None else None, HOST, stream))
         return Ke, fe
+
+    def loadVector(self, xi1d, w1d, f, ncomp=1, elem_begin=0, elem_end=None, fe=None, stream=None):
+        """Element load vectors with the source given per quadrature point: f [(elem_end-elem_begin)*nq][ncomp]
+        (poisson.py:79 with f(posGlobal) evaluated by the caller)."""
+        if elem_end is None:
+            elem_end = self.nelem
+        if isinstance(f, np.ndarray):
+            f = _f64(f)
+        fa, fs = _ptr(f)
+        if fe is None:
+            shape = (elem_end - elem_begin, self.nb * ncomp)
+            if fs == HOST:
+                fe = np.empty(shape)
+            else:
+                import torch
+                fe = torch.empty(shape, dtype=torch.float64, device=f.device)
+        xa, xp = _rule_arrays(xi1d)
+        wa, wp = _rule_arrays(w1d)
+        nq1 = _i32([len(a) for a in xa])
+        _check(lib().igab_load_vector(self.h, elem_begin, elem_end, nq1.ctypes.data_as(ip), xp, wp, fa, ncomp,
+                                      _ptr(fe)[0], fs, stream))
+        return fe
+
+    def loadVectorPoints(self, elem, offset, xi, w, f, ncomp=1):
+        """Element load vectors of elements with their own rules (trimmed elements): lists as in assemblePoints,
+        f [npts][ncomp] indexed like xi / w."""
+        elem = _i32(elem)
+        offset = np.ascontiguousarray(offset, dtype=np.int64)
+        xi, w, f = _f64(xi), _f64(w), _f64(f)
+        fe = np.empty((len(elem), self.nb * ncomp))
+        _check(lib().igab_load_vector_points(self.h, len(elem), elem.ctypes.data, offset.ctypes.data, xi.ctypes.data,
+                                             w.ctypes.data, f.ctypes.data, ncomp, fe.ctypes.data, HOST, None))
+        return fe
+
+    def globalLoadVector(self, xi1d, w1d, f, ncomp=1, trimmed=None, f_list=None, elem_begin=0, elem_end=None, stream=None):
+        """b [nrows] of the global system from a per-point source (numpy in / out, or CUDA tensors in place of f, f_list
+        and the trimmed xi / w): the load-vector half of globalAssembler, element vectors stay on the device."""
+        if elem_end is None:
+            elem_end = self.nelem
+        if isinstance(f, np.ndarray):
+            f = _f64(f)
+        fa, fs = _ptr(f)
+        nr = C.c_int64()
+        _check(lib().igab_csr_pattern(self.h, ncomp, C.byref(nr), None, None, None, HOST, None))
+        if fs == HOST:
+            b = np.empty(nr.value)
+        else:
+            import torch
+            b = torch.empty(nr.value, dtype=torch.float64, device=f.device)
+        xa, xp = _rule_arrays(xi1d)
+        wa, wp = _rule_arrays(w1d)
+        nq1 = _i32([len(a) for a in xa])
+        nl, ea, oa, xia, wqa, fla = 0, None, None, None, None, None
+        if trimmed is not None and len(trimmed[0]):
+            te, to = _i32(trimmed[0]), np.ascontiguousarray(trimmed[1], dtype=np.int64)
+            tx, tw = trimmed[2], trimmed[3]
+            if fs == HOST:
+                tx, tw, f_list = _f64(tx), _f64(tw), _f64(f_list)
+            nl, ea, oa = len(te), te.ctypes.data, to.ctypes.data
+            xia, wqa, fla = _ptr(tx)[0], _ptr(tw)[0], _ptr(f_list)[0]
+        _check(lib().igab_global_load_vector(self.h, ncomp, elem_begin, elem_end, nq1.ctypes.data_as(ip), xp, wp, fa, nl,
+                                             ea, oa, xia, wqa, fla, _ptr(b)[0], fs, stream))
+        return b
 
     # ---- faces
     def evalFaces(self, elem, face, xi1d):

@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(128) csr_gather_rows_kernel(CsrGeom G, long lo
           const int j0 = j % o0, r = j / o0, j1 = r % o1, j2 = r / o1;
           acc[(kb + (j2 * len[1] + j1) * len[0] + j0) * G.ncomp + d] += src[jj];
         }
+        __syncwarp();  // the next element's columns map to other lanes: order the read-modify-writes of acc
       }
     }
   }
@@ -536,11 +537,9 @@ igab_status csr_assemble(igab_patch* p, int ncomp, long long eb, long long ee, c
     const size_t smem = sizeof(double) * 4 * accStride;
     const char* env = getenv("IGAB_CSR_GATHER");
     if (!p->d_trim && smem <= 200 * 1024 && !(env && env[0] == '0')) {
-      static bool raised = false;  // one attribute call per process is enough (the limit only grows)
-      if (smem > 48 * 1024 && !raised) {
-        e = cudaFuncSetAttribute(csr_gather_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        raised = e == cudaSuccess;
-      }
+      // per (kernel, device): raises the dynamic shared-memory limit once on every device a process drives
+      KernelCfg kc;
+      if (igab_status kst = kernel_config((const void*)csr_gather_rows_kernel, 128, 200 * 1024, &kc)) return kst;
       if (e == cudaSuccess) {
         const long long blocks = (rowEnd - rowBegin + 3) / 4;
         csr_gather_rows_kernel<<<(unsigned)blocks, 128, smem, stream>>>(G, rowBegin, rowEnd, eb, ee, dK, p->d_csr_rowptr, dV,

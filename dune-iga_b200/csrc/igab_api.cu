@@ -83,44 +83,130 @@ __global__ void dof_mark_kernel(PatchDev P, const uint8_t* __restrict__ trim, co
   if (t >= P.nelem * P.nb) return;
   if (trim[t / P.nb] != IGAB_TRIM_EMPTY) used[dof[t]] = 1;
 }
-// single-block ordered scan (the DOF count of one patch is small next to the evaluation; kept simple and exact)
-__global__ void dof_scan_kernel(const int32_t* __restrict__ used, int32_t* __restrict__ map, long long n,
-                                long long* __restrict__ total) {
+// Ordered exclusive scan of a 0/1 predicate over n entries in three phases (tile sums, scan of the tile sums by one
+// block, tile-local scan + write): exact integers, any n, every SM busy.  The predicate is used[i] != 0 (DOF marks) or
+// trim[i] != IGAB_TRIM_EMPTY (element flags).  map[i] = exclusive rank of a kept entry, -1 otherwise; inv (nullable):
+// inv[rank] = i -- the list of kept entries in ascending order.
+constexpr int kScanThreads = 256, kScanPer = 16, kScanTile = kScanThreads * kScanPer;
+__device__ __forceinline__ int scan_pred(const int32_t* __restrict__ used, const uint8_t* __restrict__ trim, long long i) {
+  return used ? (used[i] != 0) : (trim[i] != IGAB_TRIM_EMPTY);
+}
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const int32_t* __restrict__ used,
+                                                                      const uint8_t* __restrict__ trim, long long n,
+                                                                      long long* __restrict__ tileSum) {
+  __shared__ int wsum[kScanThreads / 32];
+  const long long base = (long long)blockIdx.x * kScanTile;
+  int c = 0;
+  for (int k = 0; k < kScanPer; ++k) {
+    const long long i = base + (long long)k * kScanThreads + threadIdx.x;
+    if (i < n) c += scan_pred(used, trim, i);
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long t = 0;
+    for (int w = 0; w < kScanThreads / 32; ++w) t += wsum[w];
+    tileSum[blockIdx.x] = t;
+  }
+}
+// exclusive scan of the tile sums in place; tileSum[ntiles] = total
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(long long* __restrict__ tileSum, long long ntiles) {
   __shared__ long long carry;
-  __shared__ int wsum[32];
+  __shared__ long long wsum[32];
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (long long base = 0; base < n; base += blockDim.x) {
+  for (long long base = 0; base < ntiles; base += blockDim.x) {
     const long long i = base + threadIdx.x;
-    const int v = (i < n) ? used[i] : 0;
-    int s = v;
+    const long long v = i < ntiles ? tileSum[i] : 0;
+    long long s = v;
     for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, s, o);
+      const long long t = __shfl_up_sync(0xffffffffu, s, o);
       if (lane >= o) s += t;
     }
     if (lane == 31) wsum[warp] = s;
     __syncthreads();
     if (warp == 0) {
-      int w = (lane < (int)(blockDim.x >> 5)) ? wsum[lane] : 0;
+      long long w = wsum[lane];
       for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        const long long t = __shfl_up_sync(0xffffffffu, w, o);
         if (lane >= o) w += t;
       }
       wsum[lane] = w;
     }
     __syncthreads();
-    const long long excl = carry + (warp ? wsum[warp - 1] : 0) + s - v;
-    if (i < n) map[i] = v ? (int32_t)excl : -1;
+    if (i < ntiles) tileSum[i] = carry + (warp ? wsum[warp - 1] : 0) + s - v;
     __syncthreads();
-    if (threadIdx.x == 0) carry += wsum[(blockDim.x >> 5) - 1];
+    if (threadIdx.x == 0) carry += wsum[31];
     __syncthreads();
   }
-  if (threadIdx.x == 0) *total = carry;
+  if (threadIdx.x == 0) tileSum[ntiles] = carry;
+}
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const int32_t* __restrict__ used,
+                                                                  const uint8_t* __restrict__ trim, long long n,
+                                                                  const long long* __restrict__ tileSum,
+                                                                  int32_t* __restrict__ map, int32_t* __restrict__ inv,
+                                                                  long long* __restrict__ total) {
+  __shared__ int wsum[kScanThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // thread t owns the kScanPer consecutive entries base + t*kScanPer .. so that ranks follow the index order
+  const long long first = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanPer;
+  int v[kScanPer], c = 0;
+#pragma unroll
+  for (int k = 0; k < kScanPer; ++k) {
+    v[k] = (first + k < n) ? scan_pred(used, trim, first + k) : 0;
+    c += v[k];
+  }
+  int s = c;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, s, o);
+    if (lane >= o) s += t;
+  }
+  if (lane == 31) wsum[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < kScanThreads / 32 ? wsum[lane] : 0;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    if (lane < kScanThreads / 32) wsum[lane] = w;
+  }
+  __syncthreads();
+  long long r = tileSum[blockIdx.x] + (warp ? wsum[warp - 1] : 0) + s - c;
+#pragma unroll
+  for (int k = 0; k < kScanPer; ++k) {
+    const long long i = first + k;
+    if (i >= n) break;
+    if (map) map[i] = v[k] ? (int32_t)r : -1;
+    if (v[k] && inv) inv[r] = (int32_t)i;
+    r += v[k];
+  }
+  if (total && blockIdx.x == 0 && threadIdx.x == 0) *total = tileSum[gridDim.x];
 }
 __global__ void dof_remap_kernel(long long n, const int32_t* __restrict__ map, int32_t* __restrict__ dof) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) dof[t] = map[dof[t]];
+}
+
+igab_status launch_flag_scan(const int32_t* used, const uint8_t* trim, long long n, int32_t* map, int32_t* inv,
+                             long long* total_dev, cudaStream_t stream) {
+  if (n <= 0) {
+    if (total_dev) IGAB_CUDA_TRY(cudaMemsetAsync(total_dev, 0, sizeof(long long), stream));
+    return IGAB_OK;
+  }
+  const long long ntiles = (n + kScanTile - 1) / kScanTile;
+  long long* tileSum = nullptr;
+  IGAB_CUDA_TRY(cudaMallocAsync(&tileSum, sizeof(long long) * (ntiles + 1), stream));
+  scan_tile_sums_kernel<<<(unsigned)ntiles, kScanThreads, 0, stream>>>(used, trim, n, tileSum);
+  scan_tiles_kernel<<<1, 1024, 0, stream>>>(tileSum, ntiles);
+  scan_apply_kernel<<<(unsigned)ntiles, kScanThreads, 0, stream>>>(used, trim, n, tileSum, map, inv, total_dev);
+  count_launch(3);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(tileSum, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "flag scan");
+  return IGAB_OK;
 }
 
 igab_status launch_spans(const PatchDev& P, int32_t* span, cudaStream_t stream) {
@@ -144,9 +230,10 @@ igab_status launch_dof_compact(const PatchDev& P, const uint8_t* trim_dev, int32
   const long long n = P.nelem * P.nb;
   IGAB_CUDA_TRY(cudaMemsetAsync(used, 0, sizeof(int32_t) * ndof, stream));
   dof_mark_kernel<<<(unsigned)((n + th - 1) / th), th, 0, stream>>>(P, trim_dev, dof, used);
-  dof_scan_kernel<<<1, 1024, 0, stream>>>(used, map, ndof, total_dev);
+  igab_status st = launch_flag_scan(used, nullptr, ndof, map, nullptr, total_dev, stream);
+  if (st) return st;
   dof_remap_kernel<<<(unsigned)((n + th - 1) / th), th, 0, stream>>>(n, map, dof);
-  count_launch(3);
+  count_launch(2);
   IGAB_CUDA_TRY(cudaGetLastError());
   return IGAB_OK;
 }
@@ -165,6 +252,34 @@ static int find_span_corrected(int p, double u, const std::vector<double>& U, in
 }
 
 constexpr int kMaxRule = 64;  // points per direction of a tensor rule
+
+// Handle-owned device scratch (staged rule, univariate tables, scheduler counters, reduction buffers, the control net
+// on update) is shared by all calls on a handle.  When the caller moves to ANOTHER stream, the work it queued on the
+// previous one may still be reading that scratch: order the new stream behind it with an event recorded on the old
+// stream at the moment of the switch (no per-call cost on the steady path: one pointer compare).
+igab_status enter_stream(igab_patch* p, cudaStream_t stream) {
+  if (!p) {
+    set_error("null patch handle");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  if (p->have_last_stream && p->last_stream != stream) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (p->last_stream) cudaStreamIsCapturing(p->last_stream, &cap);
+    if (cap != cudaStreamCaptureStatusNone) {
+      set_error("this handle is inside a CUDA graph capture on another stream: end the capture before switching streams");
+      return IGAB_INVALID_ARGUMENT;
+    }
+    if (!p->stream_switch_ev) IGAB_CUDA_TRY(cudaEventCreateWithFlags(&p->stream_switch_ev, cudaEventDisableTiming));
+    if (cudaEventRecord(p->stream_switch_ev, p->last_stream) == cudaSuccess) {
+      IGAB_CUDA_TRY(cudaStreamWaitEvent(stream, p->stream_switch_ev, 0));
+    } else {
+      cudaGetLastError();  // the caller destroyed the old stream: its work has been released with it
+    }
+  }
+  p->last_stream = stream;
+  p->have_last_stream = true;
+  return IGAB_OK;
+}
 
 struct RuleDev {
   const double* xi[kMaxDim];
@@ -472,6 +587,10 @@ void igab_patch_destroy(igab_patch* p) {
   if (p->d_csr_colidx) cudaFree(p->d_csr_colidx);
   if (p->ga_scratch) cudaFree(p->ga_scratch);
   if (p->xch_buf) cudaFree(p->xch_buf);
+  if (p->stream_switch_ev) cudaEventDestroy(p->stream_switch_ev);
+  if (p->d_D) cudaFree(p->d_D);
+  for (int b = 0; b < 2; ++b)
+    if (p->asm_buf[b]) cudaFree(p->asm_buf[b]);
   if (p->d_dofc_map) cudaFree(p->d_dofc_map);
   if (p->d_dofc_inv) cudaFree(p->d_dofc_inv);
   free_sf_workspace(p->sf);
@@ -497,6 +616,8 @@ igab_status igab_patch_set_kernel(igab_patch* p, int kernel) {
 
 igab_status igab_patch_update_control_points(igab_patch* p, const double* cp) {
   if (!p || !cp) return IGAB_INVALID_ARGUMENT;
+  // kernels still in flight on the stream of the last call (possibly a non-blocking one) read the control net
+  if (p->have_last_stream && cudaStreamSynchronize(p->last_stream) != cudaSuccess) cudaGetLastError();
   IGAB_CUDA_TRY(cudaMemcpy(p->d_cp, cp, sizeof(double) * p->ncp_total * (p->dev.dw + 1), cudaMemcpyHostToDevice));
   return IGAB_OK;
 }
@@ -504,6 +625,7 @@ igab_status igab_patch_update_control_points(igab_patch* p, const double* cp) {
 igab_status igab_patch_spans(igab_patch* p, int32_t* span, igab_memspace space, void* stream_) {
   if (!p || !span) return IGAB_INVALID_ARGUMENT;
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (igab_status est = enter_stream(p, stream)) return est;
   if (space == IGAB_DEVICE) return launch_spans(p->dev, span, stream);
   int32_t* d = nullptr;
   const size_t bytes = sizeof(int32_t) * p->dev.nelem * p->dev.dim;
@@ -521,6 +643,7 @@ igab_status igab_patch_spans(igab_patch* p, int32_t* span, igab_memspace space, 
 igab_status igab_patch_dofmap(igab_patch* p, int32_t* dof, int64_t* ndof, igab_memspace space, void* stream_) {
   if (!p || !dof) return IGAB_INVALID_ARGUMENT;
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (igab_status est = enter_stream(p, stream)) return est;
   const long long n = p->dev.nelem * p->dev.nb;
   if (n > 0x7fffffffLL * 256LL) {
     set_error("dofmap: too many entries");
@@ -557,6 +680,55 @@ igab_status igab_patch_dofmap(igab_patch* p, int32_t* dof, int64_t* ndof, igab_m
   return st;
 }
 
+igab_status igab_patch_real_index_maps(igab_patch* p, int32_t* direct_of_real, int32_t* real_of_direct, int64_t* n_real,
+                                       igab_memspace space, void* stream_) {
+  if (!p) return IGAB_INVALID_ARGUMENT;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (igab_status est = enter_stream(p, stream)) return est;
+  const long long n = p->dev.nelem;
+  if (!p->d_trim) {  // untrimmed patch: identity (nurbspatch.hh:599-606)
+    if (n_real) *n_real = n;
+    if (space == IGAB_HOST) {
+      for (long long e = 0; e < n; ++e) {
+        if (direct_of_real) direct_of_real[e] = (int32_t)e;
+        if (real_of_direct) real_of_direct[e] = (int32_t)e;
+      }
+      return IGAB_OK;
+    }
+    std::vector<int32_t> id(n);
+    for (long long e = 0; e < n; ++e) id[e] = (int32_t)e;
+    if (direct_of_real) IGAB_CUDA_TRY(cudaMemcpyAsync(direct_of_real, id.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, stream));
+    if (real_of_direct) IGAB_CUDA_TRY(cudaMemcpyAsync(real_of_direct, id.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, stream));
+    IGAB_CUDA_TRY(cudaStreamSynchronize(stream));
+    return IGAB_OK;
+  }
+  int32_t *dMap = real_of_direct, *dInv = direct_of_real;
+  long long* dTotal = nullptr;
+  int32_t* tmp = nullptr;
+  if (space == IGAB_HOST) {
+    IGAB_CUDA_TRY(cudaMalloc(&tmp, sizeof(int32_t) * 2 * std::max(1LL, n)));
+    dMap = tmp;
+    dInv = tmp + n;
+  }
+  cudaError_t e = cudaMalloc(&dTotal, sizeof(long long));
+  igab_status st = e == cudaSuccess ? IGAB_OK : cuda_fail(e, "real_index_maps scratch");
+  if (!st) st = launch_flag_scan(nullptr, p->d_trim, n, dMap, dInv, dTotal, stream);
+  long long total = 0;
+  if (!st) {
+    e = cudaMemcpyAsync(&total, dTotal, sizeof(long long), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess && space == IGAB_HOST) {
+      if (real_of_direct) e = cudaMemcpy(real_of_direct, dMap, sizeof(int32_t) * n, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess && direct_of_real) e = cudaMemcpy(direct_of_real, dInv, sizeof(int32_t) * total, cudaMemcpyDeviceToHost);
+    }
+    if (e != cudaSuccess) st = cuda_fail(e, "real_index_maps D2H");
+  }
+  if (dTotal) cudaFree(dTotal);
+  if (tmp) cudaFree(tmp);
+  if (!st && n_real) *n_real = total;
+  return st;
+}
+
 // ---- evaluation -----------------------------------------------------------------------------------------------------
 igab_status igab_eval_tensor(igab_patch* p, int64_t elem_begin, int64_t elem_end, int deriv_order, const int* nq1,
                              const double* const* xi1d, const igab_eval_out* out, igab_memspace out_space,
@@ -573,6 +745,7 @@ igab_status igab_eval_tensor(igab_patch* p, int64_t elem_begin, int64_t elem_end
   igab_status st = check_out(out, deriv_order, &eff);
   if (st) return st;
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (igab_status est = enter_stream(p, stream)) return est;
   RuleDev rule;
   if ((st = stage_rule(p, nq1, xi1d, nullptr, &rule, stream))) return st;
   if (out_space == IGAB_DEVICE) return run_eval_tensor_device(p, elem_begin, elem_end, deriv_order, nq1, xi1d, rule, eff, stream);
@@ -653,6 +826,7 @@ igab_status igab_eval_points(igab_patch* p, int64_t npts, const int32_t* elem, c
   if (st) return st;
   if (npts == 0) return IGAB_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (igab_status est = enter_stream(p, stream)) return est;
   PointSource src{};
   src.tensor = 0;
   if (space == IGAB_DEVICE) {
@@ -711,6 +885,7 @@ igab_status igab_partial(igab_patch* p, int64_t npts, const int32_t* elem, const
     }
   if (npts == 0) return IGAB_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (igab_status est = enter_stream(p, stream)) return est;
   if (space == IGAB_DEVICE) return launch_partial(p->dev, npts, elem, xi, alpha, out, stream);
   for (long long k = 0; k < npts; ++k)
     if (elem[k] < 0 || elem[k] >= p->dev.nelem) {
@@ -763,6 +938,7 @@ igab_status igab_assemble(igab_patch* p, int kind, const double* D, double fcons
     return IGAB_UNSUPPORTED;
   }
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (igab_status est = enter_stream(p, stream)) return est;
   RuleDev rule;
   igab_status st = stage_rule(p, nq1, xi1d, w1d, &rule, stream);
   if (st) return st;
@@ -773,40 +949,77 @@ igab_status igab_assemble(igab_patch* p, int kind, const double* D, double fcons
   double* d_D = nullptr;
   cudaError_t e;
   if (kind == IGAB_ASM_ELASTICITY) {
-    if ((e = cudaMalloc(&d_D, sizeof(double) * ns * ns)) != cudaSuccess) return cuda_fail(e, "assemble D");
-    if ((e = cudaMemcpyAsync(d_D, D, sizeof(double) * ns * ns, cudaMemcpyHostToDevice, stream)) != cudaSuccess) {
-      cudaFree(d_D);
-      return cuda_fail(e, "assemble D copy");
+    // D lives in the handle and is restaged only when it (or the stream) changes: no allocation, no synchronisation,
+    // capturable in a CUDA graph once resident -- the same contract as the quadrature rule
+    if (!p->d_D) IGAB_CUDA_TRY(cudaMalloc(&p->d_D, sizeof(double) * 36));
+    const bool resident = p->D_host.size() == (size_t)(ns * ns) && p->D_stream == stream &&
+                          std::memcmp(p->D_host.data(), D, sizeof(double) * ns * ns) == 0;
+    if (!resident) {
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      if (stream) cudaStreamIsCapturing(stream, &cap);
+      if (cap != cudaStreamCaptureStatusNone) {
+        set_error("material matrix D is not resident on this stream: call once with this D before capturing a CUDA graph");
+        return IGAB_INVALID_ARGUMENT;
+      }
+      p->D_host.assign(D, D + ns * ns);
+      // pageable source: staged by the runtime before the call returns
+      IGAB_CUDA_TRY(cudaMemcpyAsync(p->d_D, p->D_host.data(), sizeof(double) * ns * ns, cudaMemcpyHostToDevice, stream));
+      p->D_stream = stream;
+    }
+    d_D = p->d_D;
+  }
+  if (out_space == IGAB_DEVICE)
+    return launch_assemble(p->dev, p->sf, xi1d, kind, D, d_D, fconst, elem_begin, nel, nq1, rule.xi, rule.w, Ke, fe, stream);
+  // HOST outputs: element chunks through two device buffers kept in the handle; the D2H copy of chunk k (copy stream)
+  // overlaps the kernel of chunk k+1.  Full PCIe rate needs pinned destination memory (igab_host_alloc).
+  const long long keD = (long long)n * n, feD = fe ? n : 0;
+  long long elChunk = std::max(1LL, std::min(nel, (512LL << 20) / (8 * (keD + feD))));
+  if (const char* env = getenv("IGAB_ASM_CHUNK_ELEMS")) elChunk = std::max(1L, atol(env));  // test knob
+  const size_t need = (size_t)((keD + feD) * elChunk);
+  e = cudaSuccess;
+  if (!p->stage_stream) {
+    e = cudaStreamCreateWithFlags(&p->stage_stream, cudaStreamNonBlocking);
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+      e = cudaEventCreateWithFlags(&p->stage_done[b], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->stage_copied[b], cudaEventDisableTiming);
+    }
+  } else if (!p->stage_done[0]) {
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+      e = cudaEventCreateWithFlags(&p->stage_done[b], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->stage_copied[b], cudaEventDisableTiming);
     }
   }
-  if (out_space == IGAB_DEVICE) {
-    st = launch_assemble(p->dev, p->sf, xi1d, kind, D, d_D, fconst, elem_begin, nel, nq1, rule.xi, rule.w, Ke, fe, stream);
-    if (d_D) {
-      cudaStreamSynchronize(stream);
-      cudaFree(d_D);
+  if (e == cudaSuccess && p->asm_cap < need) {
+    cudaStreamSynchronize(stream);
+    for (int b = 0; b < 2; ++b) {
+      if (p->asm_buf[b]) cudaFree(p->asm_buf[b]);
+      p->asm_buf[b] = nullptr;
     }
-    return st;
+    p->asm_cap = 0;
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaMalloc(&p->asm_buf[b], sizeof(double) * need);
+    if (e == cudaSuccess) p->asm_cap = need;
   }
-  // HOST outputs: chunked through one device buffer
-  const long long keBytes = 8LL * n * n, chunkBytes = 512LL << 20;
-  const long long elChunk = std::max(1LL, std::min(nel, chunkBytes / keBytes));
-  double *dK = nullptr, *dF = nullptr;
-  e = cudaMalloc(&dK, keBytes * elChunk);
-  if (e == cudaSuccess && fe) e = cudaMalloc(&dF, 8LL * n * elChunk);
-  if (e != cudaSuccess) st = cuda_fail(e, "assemble staging");
-  for (long long c0 = 0; c0 < nel && !st; c0 += elChunk) {
+  if (e != cudaSuccess) return cuda_fail(e, "assemble host staging allocation");
+  cudaStream_t cstream = p->stage_stream;
+  int b = 0;
+  for (long long c0 = 0; c0 < nel && !st; c0 += elChunk, b ^= 1) {
     const long long m = std::min(elChunk, nel - c0);
+    double* dK = p->asm_buf[b];
+    double* dF = fe ? dK + keD * elChunk : nullptr;
+    if ((e = cudaStreamWaitEvent(stream, p->stage_copied[b], 0)) != cudaSuccess) { st = cuda_fail(e, "assemble: wait copied"); break; }
     st = launch_assemble(p->dev, p->sf, xi1d, kind, D, d_D, fconst, elem_begin + c0, m, nq1, rule.xi, rule.w, dK, dF, stream);
     if (st) break;
-    e = cudaMemcpyAsync(Ke + (long long)n * n * c0, dK, keBytes * m, cudaMemcpyDeviceToHost, stream);
-    if (e == cudaSuccess && fe) e = cudaMemcpyAsync(fe + (long long)n * c0, dF, 8LL * n * m, cudaMemcpyDeviceToHost, stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if ((e = cudaEventRecord(p->stage_done[b], stream)) != cudaSuccess) { st = cuda_fail(e, "assemble: record done"); break; }
+    if ((e = cudaStreamWaitEvent(cstream, p->stage_done[b], 0)) != cudaSuccess) { st = cuda_fail(e, "assemble: wait done"); break; }
+    e = cudaMemcpyAsync(Ke + keD * c0, dK, sizeof(double) * keD * m, cudaMemcpyDeviceToHost, cstream);
+    if (e == cudaSuccess && fe) e = cudaMemcpyAsync(fe + (long long)n * c0, dF, sizeof(double) * n * m, cudaMemcpyDeviceToHost, cstream);
+    if (e == cudaSuccess) e = cudaEventRecord(p->stage_copied[b], cstream);
     if (e != cudaSuccess) st = cuda_fail(e, "assemble D2H");
   }
-  cudaStreamSynchronize(stream);
-  if (dK) cudaFree(dK);
-  if (dF) cudaFree(dF);
-  if (d_D) cudaFree(d_D);
+  e = cudaStreamSynchronize(cstream);
+  if (e != cudaSuccess && !st) st = cuda_fail(e, "assemble: sync copy stream");
+  e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess && !st) st = cuda_fail(e, "assemble: sync stream");
   return st;
 }
 
@@ -865,6 +1078,7 @@ igab_status igab_eval_faces(igab_patch* p, int64_t nfaces, const int32_t* elem, 
     return IGAB_INVALID_ARGUMENT;
   }
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (igab_status est = enter_stream(p, stream)) return est;
   const int dim = p->dev.dim, dw = p->dev.dw;
   if (dim < 2) {
     set_error("eval_faces: needs a 2-D or 3-D patch");
@@ -966,6 +1180,7 @@ igab_status igab_geometry_local(igab_patch* p, int64_t npts, const int32_t* elem
     return IGAB_INVALID_ARGUMENT;
   }
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (igab_status est = enter_stream(p, stream)) return est;
   const int dim = p->dev.dim, dw = p->dev.dw;
   if (dim != dw && dim > 2) {
     set_error("geometry_local: closest-point projection exists for curves and surfaces only");
@@ -1012,6 +1227,7 @@ igab_status igab_rhs_assemble(igab_patch* p, int ncomp, int64_t elem_begin, int6
     set_error("rhs_assemble: element range outside [0, n_elem]");
     return IGAB_INVALID_ARGUMENT;
   }
+  if (igab_status est = enter_stream(p, (cudaStream_t)stream)) return est;
   return rhs_assemble(p, ncomp, elem_begin, elem_end, fe, b, accumulate, space, (cudaStream_t)stream);
 }
 igab_status igab_csr_dirichlet(igab_patch* p, int ncomp, const uint8_t* mask, const double* g, double* values, double* b,
@@ -1020,6 +1236,7 @@ igab_status igab_csr_dirichlet(igab_patch* p, int ncomp, const uint8_t* mask, co
     set_error("csr_dirichlet: null argument");
     return IGAB_INVALID_ARGUMENT;
   }
+  if (igab_status est = enter_stream(p, (cudaStream_t)stream)) return est;
   return csr_dirichlet(p, ncomp, mask, g, values, b, space, (cudaStream_t)stream);
 }
 
@@ -1035,6 +1252,7 @@ igab_status igab_assemble_points(igab_patch* p, int kind, const double* D, doubl
     return IGAB_INVALID_ARGUMENT;
   }
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (igab_status est = enter_stream(p, stream)) return est;
   if (nlist == 0) return IGAB_OK;
   static_assert(sizeof(long long) == sizeof(int64_t), "offset type");
   if (space == IGAB_DEVICE)
@@ -1130,6 +1348,7 @@ igab_status igab_local_keys(int dim, const int* degree, uint32_t* sub_entity, ui
 igab_status igab_csr_pattern(igab_patch* p, int ncomp, int64_t* nrows, int64_t* nnz, int64_t* rowptr, int32_t* colidx,
                              igab_memspace space, void* stream) {
   if (!p) return IGAB_INVALID_ARGUMENT;
+  if (igab_status est = enter_stream(p, (cudaStream_t)stream)) return est;
   return csr_pattern(p, ncomp, nrows, nnz, rowptr, colidx, space, (cudaStream_t)stream);
 }
 igab_status igab_csr_assemble(igab_patch* p, int ncomp, int64_t elem_begin, int64_t elem_end, const double* Ke,
@@ -1143,6 +1362,7 @@ igab_status igab_csr_assemble(igab_patch* p, int ncomp, int64_t elem_begin, int6
     set_error("csr_assemble: element range outside [0, n_elem]");
     return IGAB_INVALID_ARGUMENT;
   }
+  if (igab_status est = enter_stream(p, (cudaStream_t)stream)) return est;
   return csr_assemble(p, ncomp, elem_begin, elem_end, Ke, rowptr, values, accumulate, space, (cudaStream_t)stream);
 }
 
@@ -1181,6 +1401,7 @@ igab_status igab_global_assemble(igab_patch* p, int kind, const double* D, doubl
       return IGAB_INVALID_ARGUMENT;
     }
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (igab_status est = enter_stream(p, stream)) return est;
   const int ncomp = kind == IGAB_ASM_ELASTICITY ? p->dev.dim : 1;
   const long long n = (long long)p->dev.nb * ncomp, n2 = n * n, nrange = elem_end - elem_begin;
   int64_t nrows = 0, nnz = 0;
@@ -1329,6 +1550,328 @@ igab_status igab_global_assemble(igab_patch* p, int kind, const double* D, doubl
   return st;
 }
 
+// ---- load vectors with a per-point source ----------------------------------------------------------------------------
+namespace {
+// fe[k][i*ncomp + c] = sum_q w_q detJ_q R_i(q) f_q[c]  (poisson.py:79, localB[i] += weight * integrationElement * phi[i] *
+// f(posGlobal), with f already evaluated at the points).  One warp per element, lanes over the local functions, points in
+// their rule order (the reference's summation order).  Tensor rules: the nq points of element k are k*nq .. with
+// w = prod w1d; lists: off[k] - off[0] .. with their own weights.
+struct LoadVecArgs {
+  int nb, ncomp, tensor;
+  long long nq;
+  int nq1[kMaxDim];
+  const double* w1d[kMaxDim];
+  const long long* off;  // list mode: absolute offsets, off[0] is the first point of the chunk
+  const double* wlist;   // list mode: weights of the chunk's points
+  const double *N, *detJ, *f;
+  double* fe;
+};
+__global__ void __launch_bounds__(128) loadvec_kernel(LoadVecArgs A, long long nel) {
+  const long long k = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (k >= nel) return;
+  long long p0, p1;
+  if (A.tensor) {
+    p0 = k * A.nq;
+    p1 = p0 + A.nq;
+  } else {
+    p0 = A.off[k] - A.off[0];
+    p1 = A.off[k + 1] - A.off[0];
+  }
+  for (int i = lane; i < A.nb; i += 32) {
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (long long pt = p0; pt < p1; ++pt) {
+      double wq;
+      if (A.tensor) {
+        long long q = pt - p0;
+        wq = A.w1d[0][q % A.nq1[0]];
+        q /= A.nq1[0];
+        if (A.w1d[1]) wq *= A.w1d[1][q % A.nq1[1]];
+        q /= A.nq1[1];
+        if (A.w1d[2]) wq *= A.w1d[2][q];
+      } else {
+        wq = A.wlist[pt];
+      }
+      const double s = wq * A.detJ[pt] * A.N[pt * A.nb + i];
+      for (int c = 0; c < A.ncomp; ++c) acc[c] += s * A.f[pt * A.ncomp + c];
+    }
+    for (int c = 0; c < A.ncomp; ++c) A.fe[(k * A.nb + i) * A.ncomp + c] = acc[c];
+  }
+}
+}  // namespace
+
+igab_status igab_load_vector(igab_patch* p, int64_t elem_begin, int64_t elem_end, const int* nq1,
+                             const double* const* xi1d, const double* const* w1d, const double* f, int ncomp, double* fe,
+                             igab_memspace space, void* stream_) {
+  if (!p || !nq1 || !xi1d || !w1d || !f || !fe || ncomp < 1 || ncomp > 3) {
+    set_error("load_vector: null argument or ncomp outside 1..3");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  if (elem_begin < 0 || elem_end < elem_begin || elem_end > p->dev.nelem) {
+    set_error("load_vector: element range outside [0, n_elem]");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (igab_status est = enter_stream(p, stream)) return est;
+  RuleDev rule;
+  igab_status st = stage_rule(p, nq1, xi1d, w1d, &rule, stream);
+  if (st) return st;
+  const long long nel = elem_end - elem_begin;
+  if (nel == 0) return IGAB_OK;
+  const int nb = p->dev.nb, dim = p->dev.dim;
+  long long nq = 1;
+  for (int d = 0; d < dim; ++d) nq *= nq1[d];
+  const long long elChunk = std::max(1LL, std::min(nel, (256LL << 20) / (8 * nq * nb)));
+  // scratch: N, detJ of a chunk (+ staged f / fe for host arrays)
+  const size_t nN = (size_t)elChunk * nq * nb, nJ = (size_t)elChunk * nq, nF = (size_t)elChunk * nq * ncomp,
+               nE = (size_t)elChunk * nb * ncomp;
+  double* scratch = nullptr;
+  IGAB_CUDA_TRY(cudaMallocAsync(&scratch, sizeof(double) * (nN + nJ + (space == IGAB_HOST ? nF + nE : 0)), stream));
+  double *dN = scratch, *dJ = dN + nN, *dF = dJ + nJ, *dE = dF + nF;
+  cudaError_t e = cudaSuccess;
+  for (long long c0 = 0; c0 < nel && !st; c0 += elChunk) {
+    const long long m = std::min(elChunk, nel - c0);
+    igab_eval_out o{};
+    o.N = dN;
+    o.detJ = dJ;
+    st = run_eval_tensor_device(p, elem_begin + c0, elem_begin + c0 + m, 1, nq1, xi1d, rule, o, stream);
+    if (st) break;
+    LoadVecArgs A{};
+    A.nb = nb;
+    A.ncomp = ncomp;
+    A.tensor = 1;
+    A.nq = nq;
+    for (int d = 0; d < kMaxDim; ++d) {
+      A.nq1[d] = d < dim ? nq1[d] : 1;
+      A.w1d[d] = d < dim ? rule.w[d] : nullptr;
+    }
+    A.N = dN;
+    A.detJ = dJ;
+    if (space == IGAB_HOST) {
+      e = cudaMemcpyAsync(dF, f + c0 * nq * ncomp, sizeof(double) * m * nq * ncomp, cudaMemcpyHostToDevice, stream);
+      if (e != cudaSuccess) { st = cuda_fail(e, "load_vector f H2D"); break; }
+      A.f = dF;
+      A.fe = dE;
+    } else {
+      A.f = f + c0 * nq * ncomp;
+      A.fe = fe + c0 * nb * ncomp;
+    }
+    loadvec_kernel<<<(unsigned)((m + 3) / 4), 128, 0, stream>>>(A, m);
+    count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) { st = cuda_fail(e, "load_vector kernel"); break; }
+    if (space == IGAB_HOST) {
+      e = cudaMemcpyAsync(fe + c0 * nb * ncomp, dE, sizeof(double) * m * nb * ncomp, cudaMemcpyDeviceToHost, stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // dF / dE are reused by the next chunk
+      if (e != cudaSuccess) st = cuda_fail(e, "load_vector D2H");
+    }
+  }
+  cudaFreeAsync(scratch, stream);
+  return st;
+}
+
+igab_status igab_load_vector_points(igab_patch* p, int64_t nlist, const int32_t* elem, const int64_t* offset,
+                                    const double* xi, const double* w, const double* f, int ncomp, double* fe,
+                                    igab_memspace space, void* stream_) {
+  if (!p || nlist < 0 || ncomp < 1 || ncomp > 3 || (nlist > 0 && (!elem || !offset || !fe))) {
+    set_error("load_vector_points: null argument or ncomp outside 1..3");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  if (nlist == 0) return IGAB_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (igab_status est = enter_stream(p, stream)) return est;
+  const int nb = p->dev.nb, dim = p->dev.dim;
+  int32_t* dEl = nullptr;   // element index of every POINT (what the point-list evaluation takes)
+  long long* dOff = nullptr;
+  double* scratch = nullptr;
+  igab_status st = IGAB_OK;
+  cudaError_t e = cudaSuccess;
+  // the list's offsets are needed on the host to expand elem per point and to size the scratch
+  std::vector<long long> hoff(nlist + 1);
+  std::vector<int32_t> hel(nlist);
+  if (space == IGAB_HOST) {
+    std::copy(offset, offset + nlist + 1, hoff.begin());
+    std::copy(elem, elem + nlist, hel.begin());
+  } else {
+    e = cudaMemcpyAsync(hoff.data(), offset, sizeof(long long) * (nlist + 1), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hel.data(), elem, sizeof(int32_t) * nlist, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return cuda_fail(e, "load_vector_points: list D2H");
+  }
+  const long long p0 = hoff[0], np = hoff[nlist] - p0;
+  for (long long k = 0; k < nlist; ++k)
+    if (hel[k] < 0 || hel[k] >= p->dev.nelem || hoff[k + 1] < hoff[k]) {
+      set_error("load_vector_points: element index out of range or offsets not ascending");
+      return IGAB_INVALID_ARGUMENT;
+    }
+  if (np > 0 && (!xi || !w || !f)) {
+    set_error("load_vector_points: null points / weights / source");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  std::vector<int32_t> pel((size_t)std::max(1LL, np));
+  for (long long k = 0; k < nlist; ++k)
+    for (long long q = hoff[k]; q < hoff[k + 1]; ++q) pel[q - p0] = hel[k];
+  const size_t nN = (size_t)np * nb, nJ = (size_t)np;
+  const size_t nIn = space == IGAB_HOST ? (size_t)np * (dim + 1 + ncomp) + (size_t)nlist * nb * ncomp : 0;
+  e = cudaMallocAsync(&scratch, sizeof(double) * std::max<size_t>(1, nN + nJ + nIn), stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&dEl, sizeof(int32_t) * std::max(1LL, np), stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&dOff, sizeof(long long) * (nlist + 1), stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dEl, pel.data(), sizeof(int32_t) * np, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dOff, hoff.data(), sizeof(long long) * (nlist + 1), cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) st = cuda_fail(e, "load_vector_points staging");
+  double *dN = scratch, *dJ = dN + nN, *dXi = dJ + nJ, *dW = dXi + (size_t)np * dim, *dF = dW + np,
+         *dE = dF + (size_t)np * ncomp;
+  const double *xiD = xi ? xi + p0 * dim : nullptr, *wD = w ? w + p0 : nullptr, *fD = f ? f + p0 * ncomp : nullptr;
+  if (!st && space == IGAB_HOST && np > 0) {
+    e = cudaMemcpyAsync(dXi, xiD, sizeof(double) * np * dim, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dW, wD, sizeof(double) * np, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dF, fD, sizeof(double) * np * ncomp, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) st = cuda_fail(e, "load_vector_points H2D");
+    xiD = dXi;
+    wD = dW;
+    fD = dF;
+  }
+  if (!st && np > 0) {
+    PointSource src{};
+    src.tensor = 0;
+    src.elem = dEl;
+    src.xi = xiD;
+    EvalOutDev o{};
+    o.N = dN;
+    o.detJ = dJ;
+    st = run_eval_points_device(p, src, np, 1, o, stream);
+  }
+  if (!st) {
+    LoadVecArgs A{};
+    A.nb = nb;
+    A.ncomp = ncomp;
+    A.tensor = 0;
+    A.off = dOff;
+    A.wlist = wD;
+    A.N = dN;
+    A.detJ = dJ;
+    A.f = fD;
+    A.fe = space == IGAB_HOST ? dE : fe;
+    loadvec_kernel<<<(unsigned)((nlist + 3) / 4), 128, 0, stream>>>(A, nlist);
+    count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) st = cuda_fail(e, "load_vector_points kernel");
+  }
+  if (!st && space == IGAB_HOST) {
+    e = cudaMemcpyAsync(fe, dE, sizeof(double) * nlist * nb * ncomp, cudaMemcpyDeviceToHost, stream);
+    if (e != cudaSuccess) st = cuda_fail(e, "load_vector_points D2H");
+  }
+  // pel / hoff are pageable host arrays read by the async copies above: drain before they go out of scope
+  e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess && !st) st = cuda_fail(e, "load_vector_points sync");
+  if (scratch) cudaFreeAsync(scratch, stream);
+  if (dEl) cudaFreeAsync(dEl, stream);
+  if (dOff) cudaFreeAsync(dOff, stream);
+  return st;
+}
+
+igab_status igab_global_load_vector(igab_patch* p, int ncomp, int64_t elem_begin, int64_t elem_end, const int* nq1,
+                                    const double* const* xi1d, const double* const* w1d, const double* f, int64_t nlist,
+                                    const int32_t* elem, const int64_t* offset, const double* xi, const double* w,
+                                    const double* f_list, double* b, igab_memspace space, void* stream_) {
+  if (!p || !nq1 || !xi1d || !w1d || !f || !b || nlist < 0 || (nlist > 0 && (!elem || !offset || !xi || !w || !f_list))) {
+    set_error("global_load_vector: null argument");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  if (elem_begin < 0 || elem_end < elem_begin || elem_end > p->dev.nelem) {
+    set_error("global_load_vector: element range outside [0, n_elem]");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  for (int64_t k = 0; k < nlist; ++k)
+    if (elem[k] < 0 || elem[k] >= p->dev.nelem || (k > 0 && elem[k] <= elem[k - 1]) || offset[k + 1] < offset[k]) {
+      set_error("global_load_vector: trimmed-element list must be strictly ascending with valid offsets");
+      return IGAB_INVALID_ARGUMENT;
+    }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (igab_status est = enter_stream(p, stream)) return est;
+  const int nb = p->dev.nb;
+  long long nq = 1;
+  for (int d = 0; d < p->dev.dim; ++d) nq *= nq1[d];
+  int64_t nrows = 0, nnz = 0;
+  igab_status st = csr_pattern(p, ncomp, &nrows, &nnz, nullptr, nullptr, IGAB_HOST, stream);
+  if (st) return st;
+  const long long nrange = elem_end - elem_begin, n = (long long)nb * ncomp;
+  const long long chunk = std::max(1LL, std::min(std::max(1LL, nrange), (64LL << 20) / (8 * n)));
+  long long k0 = 0;
+  while (k0 < nlist && elem[k0] < elem_begin) ++k0;
+  const long long kFirst = k0;  // dFt / dElem hold the list entries kFirst .. kEnd of the range
+  long long kEnd = k0;
+  while (kEnd < nlist && elem[kEnd] < elem_end) ++kEnd;
+  double *dFe = nullptr, *dB = b, *dFt = nullptr, *dFsrc = nullptr;
+  int32_t* dElem = nullptr;
+  cudaError_t e = cudaMallocAsync(&dFe, sizeof(double) * chunk * n, stream);
+  if (e == cudaSuccess && space == IGAB_HOST) e = cudaMallocAsync(&dB, sizeof(double) * std::max<int64_t>(1, nrows), stream);
+  if (e == cudaSuccess && space == IGAB_HOST) e = cudaMallocAsync(&dFsrc, sizeof(double) * chunk * nq * ncomp, stream);
+  if (e == cudaSuccess && kEnd > k0) {
+    // element vectors of all trimmed elements of the range from their own rules, once
+    e = cudaMallocAsync(&dFt, sizeof(double) * (kEnd - k0) * n, stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&dElem, sizeof(int32_t) * (kEnd - k0), stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dElem, elem + k0, sizeof(int32_t) * (kEnd - k0), cudaMemcpyHostToDevice, stream);
+  }
+  if (e != cudaSuccess) st = cuda_fail(e, "global_load_vector: device buffers");
+  if (!st && kEnd > k0) {
+    if (space == IGAB_HOST) {
+      std::vector<double> host((size_t)(kEnd - k0) * n);  // host lists in, device element vectors out: stage the result
+      st = igab_load_vector_points(p, kEnd - k0, elem + k0, offset + k0, xi, w, f_list, ncomp, host.data(), IGAB_HOST, stream);
+      if (!st) {
+        e = cudaMemcpyAsync(dFt, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) st = cuda_fail(e, "global_load_vector: trimmed vectors H2D");
+      }
+    } else {
+      // device space: elem / offset are HOST arrays by contract (as in igab_global_assemble), xi / w / f_list device
+      long long* dOff = nullptr;
+      e = cudaMallocAsync(&dOff, sizeof(long long) * (kEnd - k0 + 1), stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(dOff, offset + k0, sizeof(long long) * (kEnd - k0 + 1), cudaMemcpyHostToDevice, stream);
+      if (e != cudaSuccess) st = cuda_fail(e, "global_load_vector: offsets");
+      if (!st) st = igab_load_vector_points(p, kEnd - k0, dElem, (const int64_t*)dOff, xi, w, f_list, ncomp, dFt, IGAB_DEVICE, stream);
+      if (dOff) cudaFreeAsync(dOff, stream);
+    }
+  }
+  if (!st && nrange == 0) {
+    e = cudaMemsetAsync(dB, 0, sizeof(double) * nrows, stream);
+    if (e != cudaSuccess) st = cuda_fail(e, "global_load_vector: memset");
+  }
+  for (long long eb = elem_begin; eb < elem_end && !st; eb += chunk) {
+    const long long ee = std::min((long long)elem_end, eb + chunk);
+    const double* fsrc = f + (eb - elem_begin) * nq * ncomp;
+    if (space == IGAB_HOST) {
+      e = cudaMemcpyAsync(dFsrc, fsrc, sizeof(double) * (ee - eb) * nq * ncomp, cudaMemcpyHostToDevice, stream);
+      if (e != cudaSuccess) { st = cuda_fail(e, "global_load_vector: f H2D"); break; }
+      fsrc = dFsrc;
+    }
+    st = igab_load_vector(p, eb, ee, nq1, xi1d, w1d, fsrc, ncomp, dFe, IGAB_DEVICE, stream);
+    long long k1 = k0;
+    while (k1 < kEnd && elem[k1] < ee) ++k1;
+    if (!st && k1 > k0) {
+      const long long m = k1 - k0, first = k0 - kFirst;
+      put_trimmed_kernel<<<(unsigned)((m * n + 255) / 256), 256, 0, stream>>>(n, m, dElem + first, eb, dFt + first * n, dFe);
+      count_launch();
+      if ((e = cudaGetLastError()) != cudaSuccess) st = cuda_fail(e, "global_load_vector: put_trimmed");
+    }
+    k0 = k1;
+    if (!st) st = rhs_assemble(p, ncomp, eb, ee, dFe, dB, eb > elem_begin, IGAB_DEVICE, stream);
+    if (!st && space == IGAB_HOST) {
+      e = cudaStreamSynchronize(stream);  // dFsrc is reused by the next chunk
+      if (e != cudaSuccess) st = cuda_fail(e, "global_load_vector: sync");
+    }
+  }
+  if (!st && space == IGAB_HOST) {
+    e = cudaMemcpyAsync(b, dB, sizeof(double) * nrows, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) st = cuda_fail(e, "global_load_vector: D2H");
+  }
+  if (dFe) cudaFreeAsync(dFe, stream);
+  if (space == IGAB_HOST && dB) cudaFreeAsync(dB, stream);
+  if (dFsrc) cudaFreeAsync(dFsrc, stream);
+  if (dFt) cudaFreeAsync(dFt, stream);
+  if (dElem) cudaFreeAsync(dElem, stream);
+  return st;
+}
+
 // ---- reductions -----------------------------------------------------------------------------------------------------
 typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 static nccl_allreduce_fn resolve_nccl_allreduce() {
@@ -1402,6 +1945,7 @@ igab_status igab_reduce_volume_trimmed(igab_patch* p, int64_t elem_begin, int64_
     return IGAB_INVALID_ARGUMENT;
   }
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (igab_status est = enter_stream(p, stream)) return est;
   RuleDev rule;
   igab_status st = stage_rule(p, nq1, xi1d, w1d, &rule, stream);
   if (st) return st;
@@ -1494,6 +2038,7 @@ igab_status igab_reduce_norms_trimmed(igab_patch* p, int64_t elem_begin, int64_t
     return IGAB_INVALID_ARGUMENT;
   }
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (igab_status est = enter_stream(p, stream)) return est;
   RuleDev rule;
   igab_status st = stage_rule(p, nq1, xi1d, w1d, &rule, stream);
   if (st) return st;

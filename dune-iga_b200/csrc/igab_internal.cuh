@@ -63,6 +63,8 @@ struct SfWorkspace {
   cudaStream_t streamO2 = nullptr;
 };
 
+// orders `stream` behind the handle's previous stream when the caller switches streams (handle scratch is shared)
+igab_status enter_stream(igab_patch* p, cudaStream_t stream);
 void set_error(const std::string& msg);
 igab_status cuda_fail(cudaError_t e, const char* what);
 void count_launch(int n = 1);
@@ -139,6 +141,10 @@ igab_status launch_spans(const PatchDev& P, int32_t* span, cudaStream_t stream);
 igab_status launch_dofmap(const PatchDev& P, int32_t* dof, cudaStream_t stream);
 igab_status launch_dof_compact(const PatchDev& P, const uint8_t* trim_dev, int32_t* dof, int32_t* scratch_used,
                                int32_t* scratch_map, long long ndof, long long* ndof_out_host, cudaStream_t stream);
+// ordered exclusive scan of a 0/1 predicate (used[i] != 0, or trim[i] != EMPTY when used is null): map[i] = rank or -1,
+// inv[rank] = i, *total_dev = number kept; multi-block, exact
+igab_status launch_flag_scan(const int32_t* used, const uint8_t* trim, long long n, int32_t* map, int32_t* inv,
+                             long long* total_dev, cudaStream_t stream);
 igab_status launch_assemble(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, int kind, const double* D_host, const double* D_dev, double fconst, long long elem_begin,
                             long long nelem, const int* nq1, const double* const* xi1d_dev,
                             const double* const* w1d_dev, double* Ke, double* fe, cudaStream_t stream);
@@ -218,6 +224,17 @@ struct igab_patch {
   double* xch_buf = nullptr;
   size_t xch_cap = 0;  // doubles
   std::vector<int32_t> dofc_map_host;
+  // stream discipline: the stream of the last call, and the event that orders a new stream behind it
+  cudaStream_t last_stream = nullptr;
+  bool have_last_stream = false;
+  cudaEvent_t stream_switch_ev = nullptr;
+  // elasticity matrix D of igab_assemble, kept on the device (restaged only when it changes)
+  double* d_D = nullptr;
+  std::vector<double> D_host;
+  cudaStream_t D_stream = nullptr;
+  // igab_assemble(IGAB_HOST): two element-matrix chunks (+ element vectors) so that D2H overlaps the next chunk's kernel
+  double* asm_buf[2] = {nullptr, nullptr};
+  size_t asm_cap = 0;  // doubles per buffer
   // reduction scratch
   double* d_red = nullptr;
   int red_cap = 0;

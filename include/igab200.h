@@ -116,6 +116,15 @@ igab_status igab_patch_spans(igab_patch* p, int32_t* span, igab_memspace space, 
  * dof [n_elem][nb]; entries of IGAB_TRIM_EMPTY elements whose DOF was dropped are -1; *ndof = size of the basis.   */
 igab_status igab_patch_dofmap(igab_patch* p, int32_t* dof, int64_t* ndof, igab_memspace space, void* stream);
 
+/* Replaces NURBSPatch::getDirectIndex<0> / getRealIndex<0> (dune/iga/nurbspatch.hh:599-631): the reference numbers the
+ * elements of a trimmed patch by their REAL index -- position among the non-empty (full or trimmed) elements in
+ * ascending direct index (elementIndexMap, nurbspatch.hh:696-716) -- and this library by the DIRECT index (flat index of
+ * the knot span).  direct_of_real [*n_real] = getDirectIndex<0>(r); real_of_direct [n_elem] = getRealIndex<0>(e), -1
+ * where the reference throws ("No corresponding realIndex": IGAB_TRIM_EMPTY elements).  Identity without trim flags.
+ * An ordered prefix sum over the flags on the device; either array may be NULL; int32, bit-exact.                    */
+igab_status igab_patch_real_index_maps(igab_patch* p, int32_t* direct_of_real, int32_t* real_of_direct, int64_t* n_real,
+                                       igab_memspace space, void* stream);
+
 /* Replaces NurbsLocalCoefficients::init (nurbsbasis.hh:220-271): the LocalKey (subEntity, codim, index) of each of the
  * nb = prod(degree_d + 1) local shape functions, identical for every element.  codim = number of directions in which the
  * function sits on the element boundary; index = position among the functions of the same sub-entity; subEntity as
@@ -163,6 +172,20 @@ igab_status igab_assemble(igab_patch* p, int kind, const double* D, double fcons
 igab_status igab_assemble_points(igab_patch* p, int kind, const double* D, double fconst, int64_t nlist,
                                  const int32_t* elem, const int64_t* offset, const double* xi, const double* w,
                                  double* Ke, double* fe, igab_memspace space, void* stream);
+
+/* Element load vectors with a source given PER QUADRATURE POINT: fe[k][i*ncomp + c] = sum_q w_q detJ_q R_i(xi_q) f[pt][c]
+ * -- localB[i] += pt.weight * integrationElement * phi[i] * f(posGlobal), dune/python/test/poisson.py:79, with the
+ * caller's f already evaluated at the points (x from igab_eval_tensor / igab_eval_points; a C-ABI cannot take the
+ * Python callable).  igab_load_vector: tensor rule over [elem_begin, elem_end), f [(elem_end - elem_begin) * nq][ncomp],
+ * fe [n_el][nb * ncomp].  igab_load_vector_points: elements with their own rules (trimmed elements), same list format
+ * as igab_assemble_points with f [npts][ncomp] indexed like xi / w; any dim.  f and fe (and the lists) live in `space`;
+ * points are summed in rule order.  ncomp 1..3.                                                                     */
+igab_status igab_load_vector(igab_patch* p, int64_t elem_begin, int64_t elem_end, const int* nq1,
+                             const double* const* xi1d, const double* const* w1d, const double* f, int ncomp, double* fe,
+                             igab_memspace space, void* stream);
+igab_status igab_load_vector_points(igab_patch* p, int64_t nlist, const int32_t* elem, const int64_t* offset,
+                                    const double* xi, const double* w, const double* f, int ncomp, double* fe,
+                                    igab_memspace space, void* stream);
 
 /* ---- refinement of the control net -----------------------------------------------------------------------------------
  * Replaces the control-net part of knotRefinement / degreeElevate (dune/iga/nurbsalgorithms.hh:264-528) for one
@@ -252,6 +275,16 @@ igab_status igab_global_assemble(igab_patch* p, int kind, const double* D, doubl
                                  const double* const* w1d, int64_t nlist,
                                  const int32_t* elem, const int64_t* offset, const double* xi, const double* w,
                                  double* values, double* b, igab_memspace space, void* stream);
+
+/* The load-vector half of globalAssembler (poisson.py:79,121) with a per-point source, in one call: element vectors of
+ * [elem_begin, elem_end) from the tensor rule (f [(elem_end - elem_begin) * nq][ncomp]) in device-resident chunks, those
+ * of the listed trimmed elements from their own rules (f_list [npts][ncomp]; elem / offset HOST arrays as in
+ * igab_global_assemble), gathered into b [nrows] of igab_csr_pattern(ncomp).  f, f_list, xi, w and b live in `space`.
+ * Dirichlet values g go in afterwards through igab_csr_dirichlet (poisson.py:91-93,117-119).                         */
+igab_status igab_global_load_vector(igab_patch* p, int ncomp, int64_t elem_begin, int64_t elem_end, const int* nq1,
+                                    const double* const* xi1d, const double* const* w1d, const double* f, int64_t nlist,
+                                    const int32_t* elem, const int64_t* offset, const double* xi, const double* w,
+                                    const double* f_list, double* b, igab_memspace space, void* stream);
 
 /* ---- patch reductions ---------------------------------------------------------------------------------------------
  * Replaces the user loop summing NURBSGeometry::volume() over elements (nurbsgeometry.hh:96-113,

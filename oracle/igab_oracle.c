@@ -722,6 +722,95 @@ int igo_assemble_points(const igo_patch* P, int kind, const double* D, double fc
   return 0;
 }
 
+/* ---- a21 with a non-constant source: dune/python/test/poisson.py:79  localB[i] += weight * integrationElement *
+ * phi[i] * f(posGlobal), the caller's f given per quadrature point (f[pt][ncomp]; vector-valued: flat-interleaved
+ * i*ncomp + c).  Tensor rule over [elem_begin, elem_end) (f indexed (e - elem_begin)*nq + q) ...                   */
+int igo_load_vector(const igo_patch* P, long elem_begin, long elem_end, const int* nq1, const double* xi1d,
+                    const double* w1d, const double* f, int ncomp, double* fe) {
+  const int dim = P->dim, nb = nb_of(P);
+  long nq = 1; for (int d = 0; d < dim; ++d) nq *= nq1[d];
+  const long ne = elem_end - elem_begin;
+  double* N = (double*)malloc(sizeof(double) * (ne * nq + 1) * nb);
+  double* detJ = (double*)malloc(sizeof(double) * (ne * nq + 1));
+  igo_eval_tensor(P, elem_begin, elem_end, 1, nq1, xi1d, N, 0, 0, 0, 0, 0, detJ, 0, 0);
+  const double* wd[MAXDIM]; { long off = 0; for (int d = 0; d < dim; ++d) { wd[d] = w1d + off; off += nq1[d]; } }
+  for (long e = 0; e < ne; ++e) {
+    for (int i = 0; i < nb * ncomp; ++i) fe[e * nb * ncomp + i] = 0;
+    for (long q = 0; q < nq; ++q) {
+      const long pt = e * nq + q;
+      double w = 1; long hq = q;
+      for (int d = 0; d < dim; ++d) { w *= wd[d][hq % nq1[d]]; hq /= nq1[d]; }
+      for (int i = 0; i < nb; ++i)
+        for (int c = 0; c < ncomp; ++c) fe[(e * nb + i) * ncomp + c] += w * detJ[pt] * N[pt * nb + i] * f[pt * ncomp + c];
+    }
+  }
+  free(N); free(detJ);
+  return 0;
+}
+/* ... and over elements with their own rules (trimmed elements, fillquadraturerule.hh:8-19), lists as igo_assemble_points */
+int igo_load_vector_points(const igo_patch* P, long nlist, const int* elem, const long* offset, const double* xi,
+                           const double* w, const double* f, int ncomp, double* fe) {
+  const int nb = nb_of(P);
+  const long npts = offset[nlist];
+  int* pe = (int*)malloc(sizeof(int) * (npts > 0 ? npts : 1));
+  for (long k = 0; k < nlist; ++k) for (long q = offset[k]; q < offset[k + 1]; ++q) pe[q] = elem[k];
+  double* N = (double*)malloc(sizeof(double) * (npts + 1) * nb);
+  double* detJ = (double*)malloc(sizeof(double) * (npts + 1));
+  igo_eval_points(P, npts, pe, xi, 1, N, 0, 0, 0, 0, 0, detJ, 0, 0);
+  for (long k = 0; k < nlist; ++k) {
+    for (int i = 0; i < nb * ncomp; ++i) fe[k * nb * ncomp + i] = 0;
+    for (long pt = offset[k]; pt < offset[k + 1]; ++pt)
+      for (int i = 0; i < nb; ++i)
+        for (int c = 0; c < ncomp; ++c) fe[(k * nb + i) * ncomp + c] += w[pt] * detJ[pt] * N[pt * nb + i] * f[pt * ncomp + c];
+  }
+  free(pe); free(N); free(detJ);
+  return 0;
+}
+
+/* ---- a11: dune/iga/nurbspatch.hh:599-631 getDirectIndex<0> / getRealIndex<0> with the element map filled at
+ * :696-716 (direct indices of the trimmed and full elements in ascending order).  real_of_direct[e] = -1 where the
+ * reference throws "No corresponding realIndex" (empty elements).  trimflag NULL: identity (:599-606).  Returns n_real.
+ * Pinned by dune/iga/test/trimmedgridtests.cpp:335-373 (tests/test_oracle.py).                                     */
+long igo_real_index_maps(long nelem, const unsigned char* trimflag, int* direct_of_real, int* real_of_direct) {
+  long r = 0;
+  for (long e = 0; e < nelem; ++e) {
+    const int keep = !trimflag || trimflag[e] != 1; /* ElementTrimFlag::empty == 1 in this library's encoding */
+    if (keep) {
+      if (direct_of_real) direct_of_real[r] = (int)e;
+      if (real_of_direct) real_of_direct[e] = (int)r;
+      ++r;
+    } else if (real_of_direct) {
+      real_of_direct[e] = -1;
+    }
+  }
+  return r;
+}
+
+/* ---- a19, Gauss-Lobatto branch of fillQuadratureRuleImpl (utils/fillquadraturerule.hh:21-44): points that several
+ * sub-triangles share are merged -- exact coordinate equality, weights added in the order of appearance -- and the rule
+ * comes out sorted lexicographically (x, then y): the std::map with the Comparator of :23-33.  In place on xi[n][2],
+ * w[n]; returns the number of unique points.                                                                       */
+long igo_merge_duplicate_points(long n, double* xi, double* w) {
+  long m = 0; /* insertion into a sorted prefix = what std::map::try_emplace does, O(n^2) is fine for a checker */
+  double* ox = (double*)malloc(sizeof(double) * 2 * (n > 0 ? n : 1));
+  double* ow = (double*)malloc(sizeof(double) * (n > 0 ? n : 1));
+  for (long k = 0; k < n; ++k) {
+    const double x = xi[2 * k], y = xi[2 * k + 1];
+    long pos = 0;
+    while (pos < m && (ox[2 * pos] < x || (!(ox[2 * pos] > x) && ox[2 * pos + 1] < y))) ++pos;
+    if (pos < m && !(x < ox[2 * pos]) && !(ox[2 * pos] < x) && !(y < ox[2 * pos + 1])) { /* equivalent key */
+      ow[pos] += w[k];
+      continue;
+    }
+    for (long j = m; j > pos; --j) { ox[2 * j] = ox[2 * j - 2]; ox[2 * j + 1] = ox[2 * j - 1]; ow[j] = ow[j - 1]; }
+    ox[2 * pos] = x; ox[2 * pos + 1] = y; ow[pos] = w[k];
+    ++m;
+  }
+  for (long k = 0; k < m; ++k) { xi[2 * k] = ox[2 * k]; xi[2 * k + 1] = ox[2 * k + 1]; w[k] = ow[k]; }
+  free(ox); free(ow);
+  return m;
+}
+
 /* ---- a19 (trimmed): utils/fillquadraturerule.hh:8-19 -- rule of a trimmed element from its sub-triangles -------
  * tri[ntri][3][2] in element-local [0,1]^2; simplex rule (ref_pts[nrp][2], ref_w[nrp]) on the reference triangle;
  * position = triangle.global(ip) (affine), weight = ip.w * triangle.integrationElement (= |det| = 2*area).       */

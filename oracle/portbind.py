@@ -63,6 +63,12 @@ def lib():
         L.igo_assemble_points.restype = C.c_int
         L.igo_assemble_points.argtypes = [PP, C.c_int, dp, C.c_double, C.c_long, ip, C.POINTER(C.c_long), dp, dp, dp, dp]
         L.igo_max_threads.restype = C.c_int
+        L.igo_load_vector.argtypes = [PP, C.c_long, C.c_long, ip, dp, dp, dp, C.c_int, dp]
+        L.igo_load_vector_points.argtypes = [PP, C.c_long, ip, C.POINTER(C.c_long), dp, dp, dp, C.c_int, dp]
+        L.igo_real_index_maps.restype = C.c_long
+        L.igo_real_index_maps.argtypes = [C.c_long, C.POINTER(C.c_ubyte), ip, ip]
+        L.igo_merge_duplicate_points.restype = C.c_long
+        L.igo_merge_duplicate_points.argtypes = [C.c_long, dp, dp]
         _lib = L
     return _lib
 
@@ -213,6 +219,24 @@ class PortPatch:
                                   offset.ctypes.data_as(C.POINTER(C.c_long)), _d(_f64(xi)), _d(_f64(w)), _d(Ke), _d(fe))
         return Ke, fe
 
+    def load_vector(self, xi1d, w1d, f, ncomp=1, elem_begin=0, elem_end=None):
+        """Element load vectors with a per-point source f [(ee-eb)*nq][ncomp] (poisson.py:79)."""
+        if elem_end is None:
+            elem_end = self.nelem
+        fe = np.empty((elem_end - elem_begin, self.nb * ncomp))
+        nq1 = _i32([len(x) for x in xi1d])
+        lib().igo_load_vector(C.byref(self.c), elem_begin, elem_end, _i(nq1), _d(_f64(np.concatenate(xi1d))),
+                              _d(_f64(np.concatenate(w1d))), _d(_f64(f)), ncomp, _d(fe))
+        return fe
+
+    def load_vector_points(self, elem, offset, xi, w, f, ncomp=1):
+        elem = _i32(elem)
+        offset = np.ascontiguousarray(offset, dtype=np.int64)
+        fe = np.empty((len(elem), self.nb * ncomp))
+        lib().igo_load_vector_points(C.byref(self.c), len(elem), _i(elem), offset.ctypes.data_as(C.POINTER(C.c_long)),
+                                     _d(_f64(xi)), _d(_f64(w)), _d(_f64(f)), ncomp, _d(fe))
+        return fe
+
     def local(self, elem, xglobal):
         """NURBSGeometry::local per point (nurbsgeometry.hh:145-176): element-local xi and a flag per point."""
         elem = _i32(elem)
@@ -288,6 +312,24 @@ def surface_forms(Jt, H=None, want=("normal", "unitNormal", "metric", "secondFF"
     lib().igo_surface_forms(dim, dw, npts, _d(Jt), _d(H), _d(out["normal"]), _d(out["unitNormal"]), _d(out["metric"]),
                             _d(out["secondFF"]), _d(out["gaussK"]))
     return {k: v for k, v in out.items() if v is not None}
+
+
+def real_index_maps(nelem, trimflag=None):
+    """(direct_of_real, real_of_direct) of NURBSPatch::getDirectIndex<0> / getRealIndex<0> (nurbspatch.hh:599-631)."""
+    dor = np.empty(nelem, dtype=np.int32)
+    rod = np.empty(nelem, dtype=np.int32)
+    tf = np.ascontiguousarray(trimflag, dtype=np.uint8) if trimflag is not None else None
+    n = lib().igo_real_index_maps(nelem, tf.ctypes.data_as(C.POINTER(C.c_ubyte)) if tf is not None else None, _i(dor),
+                                  _i(rod))
+    return dor[:n].copy(), rod
+
+
+def merge_duplicate_points(xi, w):
+    """Gauss-Lobatto branch of fillQuadratureRuleImpl (fillquadraturerule.hh:21-44)."""
+    xi = _f64(xi).reshape(-1, 2).copy()
+    w = _f64(w).copy()
+    m = lib().igo_merge_duplicate_points(len(w), _d(xi), _d(w))
+    return xi[:m].copy(), w[:m].copy()
 
 
 def local_keys(degree):

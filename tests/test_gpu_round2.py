@@ -1,0 +1,200 @@
+"""GPU parity tests (-m gpu) of the entry points added in round 2: real <-> direct element index maps, the multi-block
+ordered scan behind them and behind the trim compaction of the DOF map, load vectors with a per-point source, and the
+handle's stream discipline.  Everything goes through the C-ABI and is compared with the oracle."""
+import numpy as np
+import pytest
+
+import igab200  # noqa: F401
+import patches_for_tests as PFT
+import portbind as PT
+from dune_iga_b200 import capi
+from dune_iga_b200 import patchdata as PD
+from dune_iga_b200 import quadrature as QD
+from parity_util import TOL, port_for, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_patch(spec, **kw):
+    return capi.Patch(spec["degree"], spec["knots"], spec["cp"], spec["dimworld"], **kw)
+
+
+def test_real_index_maps_reference_golden_and_random_flags():
+    """igab_patch_real_index_maps == getDirectIndex<0> / getRealIndex<0> (nurbspatch.hh:599-631): the patterns of the
+    reference's own test (trimmedgridtests.cpp:335-373), random flags over more elements than one scan tile (4,096), and
+    the identity on an untrimmed patch -- int32, bit-exact against the oracle."""
+    pd = PD.squarePlate(2, 1)  # 2 x 2 elements
+    spec = dict(degree=pd.degree, knots=pd.knotSpans, cp=pd.cp, dimworld=2)
+    EMPTY, TRIMMED, FULL = 1, 2, 0
+    for flags, real, direct in (([FULL, TRIMMED, TRIMMED, TRIMMED], [0, 1, 2, 3], [0, 1, 2, 3]),
+                                ([EMPTY, TRIMMED, TRIMMED, TRIMMED], [-1, 0, 1, 2], [1, 2, 3])):
+        P = gpu_patch(spec, trimflags=np.array(flags, np.uint8))
+        dor, rod = P.realIndexMaps()
+        assert rod.tolist() == real and dor.tolist() == direct
+    P = gpu_patch(spec)
+    dor, rod = P.realIndexMaps()
+    assert dor.tolist() == [0, 1, 2, 3] == rod.tolist()
+    rng = np.random.default_rng(17)
+    pd = PD.squarePlate(2, 7)  # 128 x 128 = 16,384 elements: several scan tiles
+    spec = dict(degree=pd.degree, knots=pd.knotSpans, cp=pd.cp, dimworld=2)
+    for probs in ([0.5, 0.3, 0.2], [0.0, 1.0, 0.0], [0.02, 0.97, 0.01]):
+        flags = rng.choice([0, 1, 2], size=128 * 128, p=probs).astype(np.uint8)
+        P = gpu_patch(spec, trimflags=flags)
+        dor, rod = P.realIndexMaps()
+        odor, orod = PT.real_index_maps(len(flags), flags)
+        assert dor.dtype == np.int32 and np.array_equal(dor, odor) and np.array_equal(rod, orod)
+        # the DOF compaction runs through the same scan (18,496 DOFs: several tiles)
+        dof, n = P.dofmap()
+        dref, nref = port_for(spec).dofmap(flags)
+        assert n == nref and np.array_equal(dof, dref)
+
+
+@pytest.mark.parametrize("name,ncomp", [("plate_hole_p2", 1), ("cylinder_p3", 3), ("torus_p2", 2), ("curve_p3", 1),
+                                        ("mixed_deg_3d", 1)])
+def test_load_vector_with_per_point_source_matches_oracle(name, ncomp):
+    """fe[i] = sum_q w detJ R_i f(x_q) (poisson.py:79) with f given per point: tensor rule, sub-ranges, device arrays."""
+    import torch
+    spec = PFT.small_patch(name)
+    P, O = gpu_patch(spec), port_for(spec)
+    dim = len(spec["degree"])
+    rule = [PD.gaussLegendre01(p + 1) for p in spec["degree"]]
+    xi, w = [r[0] for r in rule], [r[1] for r in rule]
+    nq = int(np.prod([len(a) for a in xi]))
+    x = P.evalTensor(xi, order=0, want=("x",))["x"]
+    # a smooth source evaluated by the caller at the quadrature points, as f(posGlobal) in the reference's loop
+    f = np.stack([np.sin(1.0 + c + x @ np.arange(1, x.shape[1] + 1)) for c in range(ncomp)], axis=1)
+    fe = P.loadVector(xi, w, f, ncomp)
+    ref = O.load_vector(xi, w, f, ncomp)
+    assert relerr(fe, ref) <= TOL
+    eb, ee = P.nelem // 3, P.nelem - 1
+    sub = P.loadVector(xi, w, f[eb * nq:ee * nq], ncomp, elem_begin=eb, elem_end=ee)
+    assert np.array_equal(sub, fe[eb:ee])
+    fd = P.loadVector(xi, w, torch.from_numpy(f).cuda(), ncomp)
+    assert np.array_equal(fd.cpu().numpy(), fe)
+    # a constant source reproduces igab_assemble's load vector (Poisson kind; scalar)
+    if ncomp == 1 and dim == spec["dimworld"]:
+        _, f0 = P.assemble(capi.ASM_POISSON, xi, w, fconst=1.75)
+        f1 = P.loadVector(xi, w, np.full((P.nelem * nq, 1), 1.75))
+        assert relerr(f1, f0) <= TOL
+    # global load vector = scatter of the element vectors through the DOF map (poisson.py:121)
+    dof, ndof = P.dofmap()
+    b = P.globalLoadVector(xi, w, f, ncomp)
+    bref = np.zeros(ndof * ncomp)
+    for c in range(ncomp):
+        np.add.at(bref, dof.reshape(-1) * ncomp + c, ref[:, c::ncomp].reshape(-1))
+    assert np.abs(b - bref).max() <= TOL * np.abs(bref).max()
+    assert np.array_equal(P.globalLoadVector(xi, w, torch.from_numpy(f).cuda(), ncomp).cpu().numpy(), b)
+
+
+def test_load_vector_on_a_trimmed_patch_with_own_rules():
+    """Trimmed elements integrate the source with their own sub-triangle rules (fillquadraturerule.hh:8-19), empty
+    elements contribute nothing, numbering compacted (prepareForTrim)."""
+    pd = PD.squarePlate(2, 2)
+    spec = dict(degree=pd.degree, knots=pd.knotSpans, cp=pd.cp, dimworld=2)
+    flags = np.zeros(16, np.uint8)
+    flags[[0, 1, 4]] = 1
+    trimmed = [2, 5, 8]
+    flags[trimmed] = 2
+    P, O = gpu_patch(spec, trimflags=flags), port_for(spec)
+    tris = {e: np.array([[[1, 0], [1, 1], [0, 1.0]], [[0.6, 0.1], [0.9, 0.1], [0.9, 0.4]]]) for e in trimmed}
+    for qt in ("GaussLegendre", "GaussLobatto"):
+        elem_pt, xl, wl, off = QD.trimmedBatch(tris, order=3 if qt == "GaussLobatto" else 4, qt=qt)
+        x, wg = PD.gaussLegendre01(3)
+        xq = P.evalTensor([x, x], order=0, want=("x",))["x"]
+        xlq = P.evalPoints(elem_pt, xl, order=0, want=("x",))["x"]
+        src = lambda X: (1.0 + X[:, 0] + 2.0 * X[:, 1] ** 2)[:, None]  # noqa: E731
+        f, fl = src(xq), src(xlq)
+        fel = P.loadVectorPoints(np.array(trimmed, np.int32), off, xl, wl, fl)
+        assert relerr(fel, O.load_vector_points(np.array(trimmed, np.int32), off, xl, wl, fl)) <= TOL
+        b = P.globalLoadVector([x, x], [wg, wg], f, trimmed=(np.array(trimmed, np.int32), off, xl, wl), f_list=fl)
+        dof, ndof = P.dofmap()
+        fe = O.load_vector([x, x], [wg, wg], f)
+        fe[trimmed] = O.load_vector_points(np.array(trimmed, np.int32), off, xl, wl, fl)
+        bref = np.zeros(ndof)
+        for e in range(16):
+            if flags[e] != 1:
+                np.add.at(bref, dof[e], fe[e])
+        assert b.shape == (ndof,) and np.abs(b - bref).max() <= TOL * np.abs(bref).max()
+        # integral of the source over the kept domain = sum of the load vector (partition of unity)
+        det = P.evalTensor([x, x], order=1, want=("detJ",))["detJ"].reshape(16, 9)
+        detl = P.evalPoints(elem_pt, xl, order=1, want=("detJ",))["detJ"]
+        tot = (det * np.outer(wg, wg).reshape(-1) * f.reshape(16, 9))[flags == 0].sum() + (detl * wl * fl[:, 0]).sum()
+        assert abs(b.sum() - tot) <= 1e-13 * abs(tot)
+
+
+def test_elasticity_device_path_does_not_synchronise():
+    """igab_assemble(ELASTICITY, IGAB_DEVICE) keeps D in the handle: no allocation, no stream synchronisation -- the call
+    can be captured in a CUDA graph and replayed (streams and graphs)."""
+    import torch
+    spec = PFT.small_patch("cylinder_p3")
+    P, O = gpu_patch(spec), port_for(spec)
+    x, w = PD.gaussLegendre01(4)
+    E, nu = 1.0, 0.3
+    lam, mu = E * nu / ((1 + nu) * (1 - 2 * nu)), E / (2 * (1 + nu))
+    D = np.zeros((6, 6))
+    D[:3, :3] = lam
+    D[np.arange(3), np.arange(3)] += 2 * mu
+    D[np.arange(3, 6), np.arange(3, 6)] = mu
+    n = P.nb * 3
+    Ke = torch.empty((P.nelem, n, n), dtype=torch.float64, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        P.assemble(capi.ASM_ELASTICITY, [x] * 3, [w] * 3, D=D, Ke=Ke, fe=None, stream=s.cuda_stream)  # stages rule + D
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        Ke.zero_()
+        with torch.cuda.graph(g, stream=s):
+            P.assemble(capi.ASM_ELASTICITY, [x] * 3, [w] * 3, D=D, Ke=Ke, fe=None, stream=s.cuda_stream)
+        g.replay()
+        s.synchronize()
+    ref, _ = O.assemble(capi.ASM_ELASTICITY, [x] * 3, [w] * 3, D=D, want_fe=False)
+    assert relerr(Ke.cpu().numpy().reshape(P.nelem, -1), ref.reshape(P.nelem, -1)) <= TOL
+    # a different material is picked up (restaged) by the next plain call
+    Ke2 = torch.empty_like(Ke)
+    P.assemble(capi.ASM_ELASTICITY, [x] * 3, [w] * 3, D=2.0 * D, Ke=Ke2, fe=None)
+    torch.cuda.synchronize()
+    assert relerr(Ke2.cpu().numpy().reshape(P.nelem, -1), 2.0 * ref.reshape(P.nelem, -1)) <= TOL
+
+
+def test_assemble_host_outputs_in_chunks_match_device_outputs(monkeypatch):
+    """igab_assemble(IGAB_HOST) streams chunks through two device buffers with the D2H copy of chunk k overlapping the
+    kernel of chunk k+1: identical bits to the device-resident result, also with a ragged last chunk."""
+    import torch
+    spec = PFT.small_patch("cylinder_p3", level=2)
+    P = gpu_patch(spec)
+    x, w = PD.gaussLegendre01(4)
+    Kd = torch.empty((P.nelem, 64, 64), dtype=torch.float64, device="cuda")
+    fd = torch.empty((P.nelem, 64), dtype=torch.float64, device="cuda")
+    P.assemble(capi.ASM_POISSON, [x] * 3, [w] * 3, Ke=Kd, fe=fd)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("IGAB_ASM_CHUNK_ELEMS", "7")
+    Kh, fh = P.assemble(capi.ASM_POISSON, [x] * 3, [w] * 3)
+    assert np.array_equal(Kh, Kd.cpu().numpy()) and np.array_equal(fh, fd.cpu().numpy())
+    Kp = capi.pinned_empty((P.nelem, 64, 64))
+    P.assemble(capi.ASM_POISSON, [x] * 3, [w] * 3, Ke=Kp, fe=None)
+    assert np.array_equal(Kp, Kh)
+    capi.pinned_free(Kp)
+
+
+def test_switching_streams_on_one_handle_is_ordered():
+    """ADVICE (round 1): handle-owned scratch (staged rule, univariate tables, counters) is re-staged when the caller
+    switches streams; the library orders the new stream behind the work still in flight on the old one, so alternating
+    rules and streams without host synchronisation gives the same results as a serial run."""
+    import torch
+    spec = PFT.small_patch("cylinder_p3", level=3)
+    P = gpu_patch(spec)
+    rules = [PD.gaussLegendre01(4)[0], PD.gaussLegendre01(5)[0]]
+    serial = [P.evalTensor([r] * 3, order=1, want=("N", "dN", "detJ")) for r in rules]
+    s = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = []
+    for it in range(6):
+        k = it & 1
+        npts = P.nelem * len(rules[k]) ** 3
+        sh = P.shapes(npts)
+        o = {f: torch.empty(sh[f], dtype=torch.float64, device="cuda") for f in ("N", "dN", "detJ")}
+        P.evalTensor([rules[k]] * 3, order=1, want=("N", "dN", "detJ"), out=o, stream=s[k].cuda_stream)
+        outs.append((k, o))
+    torch.cuda.synchronize()
+    for k, o in outs:
+        for f in ("N", "dN", "detJ"):
+            assert np.array_equal(o[f].cpu().numpy(), serial[k][f]), (k, f)

@@ -364,3 +364,57 @@ def test_assemble_points_port_equals_tensor_assembly():
             Kt, ft = Pp.assemble(kind, [x, x], [w, w], D=D if kind == 2 else None, fconst=1.2, elem_begin=int(e), elem_end=int(e) + 1)
             assert np.abs(Kp[k] - Kt[0]).max() <= 1e-14 * np.abs(Kt).max()
             assert np.abs(fp[k] - ft[0]).max() <= 1e-14 * np.abs(ft).max()
+
+
+def test_real_index_maps_port_against_the_reference_tests():
+    """getDirectIndex<0> / getRealIndex<0> (nurbspatch.hh:599-631).  The flag patterns are the ones the reference's own
+    test produces (trimmedgridtests.cpp:335-373): one trimmed element; after one refinement 1 full + 3 trimmed (1:1
+    maps); element_trim_xb after one refinement: element 0 empty, 1..3 trimmed -> real(i) = i - 1, direct(i - 1) = i."""
+    EMPTY, TRIMMED, FULL = 1, 2, 0
+    dor, rod = PT.real_index_maps(1, [TRIMMED])
+    assert dor.tolist() == [0] and rod.tolist() == [0]
+    dor, rod = PT.real_index_maps(4, [FULL, TRIMMED, TRIMMED, TRIMMED])
+    assert dor.tolist() == [0, 1, 2, 3] and rod.tolist() == [0, 1, 2, 3]
+    dor, rod = PT.real_index_maps(4, [EMPTY, TRIMMED, TRIMMED, TRIMMED])
+    assert [rod[i] for i in range(1, 4)] == [0, 1, 2] and [dor[i - 1] for i in range(1, 4)] == [1, 2, 3]
+    assert rod[0] == -1  # the reference throws "No corresponding realIndex" (:616-622)
+    dor, rod = PT.real_index_maps(7)  # no trimming: identity (:599-606)
+    assert dor.tolist() == list(range(7)) == rod.tolist()
+    rng = np.random.default_rng(0)
+    fl = rng.choice([0, 1, 2], size=1000).astype(np.uint8)
+    dor, rod = PT.real_index_maps(1000, fl)
+    keep = np.flatnonzero(fl != EMPTY)
+    assert np.array_equal(dor, keep) and np.array_equal(rod[keep], np.arange(len(keep))) and (rod[fl == EMPTY] == -1).all()
+
+
+def test_load_vector_port_properties():
+    """Per-point source (poisson.py:79): a constant source reproduces the load vector of igo_assemble; the tensor-rule
+    and the point-list variants agree when the list holds the tensor points; the vector-valued numbering is
+    flat-interleaved."""
+    from dune_iga_b200 import patchdata as PD
+    import patches_for_tests as PFT
+    for name in ("plate_hole_p2", "cylinder_p3"):
+        spec = PFT.small_patch(name)
+        O = PT.PortPatch(spec["degree"], spec["knots"], spec["cp"], spec["dimworld"])
+        dim = len(spec["degree"])
+        x, w = PD.gaussLegendre01(max(spec["degree"]) + 1)
+        nq = len(x) ** dim
+        _, fe0 = O.assemble(0, [x] * dim, [w] * dim, fconst=2.5)
+        fe1 = O.load_vector([x] * dim, [w] * dim, np.full((O.nelem * nq, 1), 2.5))
+        assert np.abs(fe0 - fe1).max() <= 1e-15 * np.abs(fe0).max()
+        rng = np.random.default_rng(5)
+        f = rng.normal(size=(O.nelem * nq, 3))
+        fe3 = O.load_vector([x] * dim, [w] * dim, f, ncomp=3)
+        for c in range(3):
+            assert np.array_equal(fe3[:, c::3], O.load_vector([x] * dim, [w] * dim, f[:, c:c + 1].copy()))
+        # the same points as explicit lists
+        grids = np.meshgrid(*([x] * dim), indexing="ij")
+        xi = np.stack([g.T.reshape(-1) for g in grids], axis=1) if dim > 1 else x[:, None]
+        ww = np.ones(nq)
+        for d in range(dim):
+            ww = ww * np.tile(np.repeat(w, len(x) ** d), len(x) ** (dim - 1 - d))
+        xi = np.stack([np.tile(np.repeat(x, len(x) ** d), len(x) ** (dim - 1 - d)) for d in range(dim)], axis=1)
+        elem = np.arange(O.nelem, dtype=np.int32)
+        off = np.arange(O.nelem + 1) * nq
+        fel = O.load_vector_points(elem, off, np.tile(xi, (O.nelem, 1)), np.tile(ww, O.nelem), f, ncomp=3)
+        assert np.abs(fel - fe3).max() <= 1e-14 * np.abs(fe3).max()
