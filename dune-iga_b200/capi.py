@@ -28,7 +28,7 @@ EXPORTS = ("igab_last_error_string", "igab_version", "igab_launch_count", "igab_
            "igab_csr_dirichlet", "igab_assemble_points", "igab_global_assemble", "igab_reduce_volume_trimmed", "igab_reduce_norms_trimmed",
            "igab_partition_slab", "igab_interface_row_ranges", "igab_comm_unique_id", "igab_comm_create",
            "igab_comm_destroy", "igab_comm_info", "igab_exchange_interface_rows", "igab_patch_real_index_maps",
-           "igab_load_vector", "igab_load_vector_points", "igab_global_load_vector")
+           "igab_load_vector", "igab_load_vector_points", "igab_global_load_vector", "igab_device_numa_node")
 
 
 class EvalOut(C.Structure):

@@ -1,8 +1,11 @@
 // igab_api.cu -- the C-ABI of include/igab200.h: handle management, integer kernels (spans, DOF map), dispatch of the
 // evaluation / assembly / reduction kernels, and host<->device staging for IGAB_HOST buffers.
 #include <dlfcn.h>
+#include <sched.h>
 
 #include <algorithm>
+#include <cctype>
+#include <cstdio>
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
@@ -441,10 +444,66 @@ const char* igab_last_error_string(void) { return g_last_error.c_str(); }
 const char* igab_version(void) { return "igab200 0.1 (sm_100a)"; }
 int64_t igab_launch_count(void) { return g_launches.load(); }
 
+namespace {
+// CPUs of the NUMA node the current CUDA device hangs off (sysfs), empty when unknown / single-node
+bool device_numa_cpus(cpu_set_t* set, int* node_out) {
+  int dev = 0;
+  char bus[32] = {0};
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, sizeof(bus), dev) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+  char path[128];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE* f = fopen(path, "r");
+  if (!f) return false;
+  int node = -1;
+  const int got = fscanf(f, "%d", &node);
+  fclose(f);
+  if (got != 1 || node < 0) return false;
+  snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+  f = fopen(path, "r");
+  if (!f) return false;
+  char list[4096] = {0};
+  const bool ok = fgets(list, sizeof(list), f) != nullptr;
+  fclose(f);
+  if (!ok) return false;
+  CPU_ZERO(set);
+  int n = 0;
+  for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+    int a = 0, b = 0;
+    const int k = sscanf(tok, "%d-%d", &a, &b);
+    if (k == 1) b = a;
+    if (k < 1) continue;
+    for (int c = a; c <= b && c < CPU_SETSIZE; ++c) {
+      CPU_SET(c, set);
+      ++n;
+    }
+  }
+  if (node_out) *node_out = node;
+  return n > 0;
+}
+}  // namespace
+
 igab_status igab_host_alloc(void** ptr, uint64_t bytes) {
   if (!ptr) return IGAB_INVALID_ARGUMENT;
-  IGAB_CUDA_TRY(cudaMallocHost(ptr, bytes));
+  // Page-locked memory is populated at allocation time on the NUMA node of the CALLING thread.  With one process per GPU
+  // on a two-socket box that is whatever node the launcher left the process on (usually node 0 for every rank), and the
+  // D2H streams of the GPUs on the other socket then cross the inter-socket link.  Allocate from a CPU of the node the
+  // current device hangs off, then restore the caller's affinity.
+  cpu_set_t want, old;
+  const bool rebind = !getenv("IGAB_NO_NUMA_BIND") && device_numa_cpus(&want, nullptr) &&
+                      sched_getaffinity(0, sizeof(old), &old) == 0 && sched_setaffinity(0, sizeof(want), &want) == 0;
+  const cudaError_t e = cudaMallocHost(ptr, bytes);
+  if (rebind) sched_setaffinity(0, sizeof(old), &old);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
   return IGAB_OK;
+}
+int igab_device_numa_node(void) {
+  cpu_set_t s;
+  int node = -1;
+  return device_numa_cpus(&s, &node) ? node : -1;
 }
 igab_status igab_host_free(void* ptr) {
   IGAB_CUDA_TRY(cudaFreeHost(ptr));

@@ -87,9 +87,12 @@ const char* igab_last_error_string(void);
 const char* igab_version(void);
 /* number of CUDA kernels this library has launched in this process (for benchmarks' gpu_launches) */
 int64_t igab_launch_count(void);
-/* pinned host memory for IGAB_HOST buffers that should transfer at full PCIe rate */
+/* pinned host memory for IGAB_HOST buffers that should transfer at full PCIe rate; placed on the NUMA node of the
+ * CURRENT CUDA device (one process per GPU on a multi-socket box: every rank's buffers next to its own GPU) */
 igab_status igab_host_alloc(void** ptr, uint64_t bytes);
 igab_status igab_host_free(void* ptr);
+/* NUMA node the current CUDA device hangs off (sysfs), -1 when unknown */
+int igab_device_numa_node(void);
 
 /* ---- patch handle -------------------------------------------------------------------------------------------------
  * Replaces: NURBSPatchData (dune/iga/nurbspatchdata.hh:17-36) + the per-element state NURBSPatch / NURBSGeometry /
