@@ -28,7 +28,7 @@ namespace {
 // Optional phase accounting (tools/phase_timing.py builds a separate library with -DIGAB_PHASE_TIMING): clock64 deltas of
 // lane 0 of every warp, summed per phase.  Compiled out of the product library.
 #ifdef IGAB_PHASE_TIMING
-__device__ unsigned long long g_phase_ticks[8];
+__device__ unsigned long long g_phase_ticks[16];
 #define IGAB_PT_BEGIN long long pt_last = clock64();
 #define IGAB_PT(k)                                                                                   \
   {                                                                                                  \
@@ -36,9 +36,18 @@ __device__ unsigned long long g_phase_ticks[8];
     if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase_ticks[k], (unsigned long long)(pt_now - pt_last)); \
     pt_last = pt_now;                                                                                \
   }
+#define IGAB_WPT_BEGIN long long wpt_last = clock64();
+#define IGAB_WPT(k)                                                                                    \
+  {                                                                                                    \
+    const long long wpt_now = clock64();                                                               \
+    if ((threadIdx.x & 127) == 0) atomicAdd(&g_phase_ticks[k], (unsigned long long)(wpt_now - wpt_last)); \
+    wpt_last = wpt_now;                                                                                \
+  }
 #else
 #define IGAB_PT_BEGIN
 #define IGAB_PT(k)
+#define IGAB_WPT_BEGIN
+#define IGAB_WPT(k)
 #endif
 
 __device__ __forceinline__ void dmma8x8x4_f(double& c0, double& c1, double a, double b) {
@@ -75,14 +84,14 @@ struct FCfg {
 // Steps (1)+(2) for one element, executed by the whole block (NT threads): tables + control points -> shared, geometry
 // of all quadrature points by sum factorisation, per-point constants sC[pt][16] (layout below).  Ends with a
 // __syncthreads().
-template <int P, int Q, int NT>
+template <int P, int Q, int NT, int CS = FCfg<P, Q>::CS>
 __device__ __forceinline__ void element_prepare(const PatchDev& Pd, long long e, const double* __restrict__ tab0,
                                                 const double* __restrict__ tab1, const double* __restrict__ tab2,
                                                 const double* __restrict__ w0, const double* __restrict__ w1,
                                                 const double* __restrict__ w2, double* sT, double* sW, double* rA,
                                                 double* sS2, double* sC) {
   using C = FCfg<P, Q>;
-  constexpr int NB1 = C::NB1, NB = C::NB, NQ = C::NQ, Q2 = C::Q2, CS = C::CS;
+  constexpr int NB1 = C::NB1, NB = C::NB, NQ = C::NQ, Q2 = C::Q2;
   double* const sH = rA;
   double* const sS1 = rA + C::SZ_H;
   double* const sG = rA;
@@ -597,11 +606,11 @@ igab_status launch_elas(const PatchDev& Pd, SfWorkspace& ws, const double* D_hos
 // and the 8x8 accumulator tiles go straight to global memory: rows of a tile step j by NB1, columns by 1, so a warp's
 // stores form contiguous runs of the 25 complete K_e rows that belong to this i2.
 // KIND: 0 Poisson, 1 mass, 2 elasticity (nine (a, b) blocks, each a Poisson-like contraction with its own 4x4 M4)
-template <int P, int Q, int KIND>
+template <int P, int Q, int KIND, int NW = 8>
 struct SCfg {
   static constexpr bool MASS = KIND == 1, ELAS = KIND == 2;
   using F = FCfg<P, Q>;
-  static constexpr int NB1 = P + 1, NP = NB1 * NB1, NB = F::NB, NQ = F::NQ, NT = 256, NWARP = NT / 32;
+  static constexpr int NB1 = P + 1, NP = NB1 * NB1, NB = F::NB, NQ = F::NQ, NWARP = NW, NT = 32 * NW;
   static constexpr int r4(int x) { return (x + 3) & ~3; }
   static constexpr int r8(int x) { return (x + 7) & ~7; }
   static constexpr int NG = MASS ? 1 : 4;
@@ -623,14 +632,20 @@ struct SCfg {
   static constexpr int MT3 = M3P / 8, NT3 = NPP / 8;
   // leading dimensions: A operands = 4 mod 8 doubles, B operand = 8 mod 16 (conflict-free fragment loads)
   static constexpr int LDA2 = (KTOT + 3) / 8 * 8 + 4;
-  static constexpr int LDB2 = (NPP + 7) / 16 * 16 + 8;
+  // B operand: lane (lr, lc) reads [4 ks + lc][8 nt + lr]; a 64-bit shared load is served per half-warp (lr 0..3, lc 0..3), so
+  // the four rows must start 8 banks apart: LDB2 = 4 mod 16 doubles (8 mod 16 put rows lc and lc + 2 on the same banks: half
+  // of the stage-2 B loads were bank conflicts, profiles/README.md)
+  static constexpr int LDB2 = (NPP + 11) / 16 * 16 + 4;
+  // per-point constants of element_prepare with an ODD stride: a thread per point reads them (M4, load vector), and the
+  // even stride 16 put every lane of a half-warp on the same banks
+  static constexpr int CSS = 17, SZ_CS = F::ev(CSS * NQ);
   static constexpr int LDA3 = (K3 + 3) / 8 * 8 + 4;
   static constexpr int SZ_T1 = M2P * LDA2;
   static constexpr int SZ_X = F::ev((F::SZ_A + F::SZ_S2) > SZ_T1 ? (F::SZ_A + F::SZ_S2) : SZ_T1);
   static constexpr int SZ_M = F::ev(NU * NQ);
   static constexpr int SZ_T2 = M3P * LDA3;
   static constexpr int SZ_B2 = KTOT * LDB2;
-  static constexpr int SZ_TOTAL = F::SZ_T + F::SZ_W + F::SZ_C + SZ_X + SZ_M + SZ_T2 + SZ_B2;
+  static constexpr int SZ_TOTAL = F::SZ_T + F::SZ_W + SZ_CS + SZ_X + SZ_M + SZ_T2 + SZ_B2;
   // tiles of a warp share a tile row (one A fragment for TPW tiles) when that divides evenly; otherwise (GEN2) every
   // warp walks single tiles round-robin
   static constexpr bool GEN2 = !(TPW == 1 || NT2 % TPW == 0);
@@ -656,13 +671,13 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
   using S = SCfg<P, Q, KIND>;
   constexpr bool MASS = S::MASS, ELAS = S::ELAS;
   constexpr int NCP = ELAS ? 3 : 1, NROWK = NCP * S::NB;  // components per basis function, rows of K_e
-  constexpr int NB1 = S::NB1, NP = S::NP, NB = S::NB, NQ = S::NQ, NT = S::NT, CS = C::CS, TAB = C::TAB;
+  constexpr int NB1 = S::NB1, NP = S::NP, NB = S::NB, NQ = S::NQ, NT = S::NT, CS = S::CSS, TAB = C::TAB;
   constexpr int LDA2 = S::LDA2, LDB2 = S::LDB2, LDA3 = S::LDA3;
   extern __shared__ __align__(16) double ssm[];
   double* const sT = ssm;
   double* const sW = sT + C::SZ_T;
   double* const sC = sW + C::SZ_W;
-  double* const rX = sC + C::SZ_C;        // element_prepare's scratch (rA | sS2), then T1
+  double* const rX = sC + S::SZ_CS;       // element_prepare's scratch (rA | sS2), then T1
   double* const sT1 = rX;
   double* const sM = rX + S::SZ_X;
   double* const sT2 = sM + S::SZ_M;
@@ -709,7 +724,7 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
 
   for (long long el = blockIdx.x; el < nelem; el += gridDim.x) {
     const long long e = elem_begin + el;
-    element_prepare<P, Q, NT>(Pd, e, tab0, tab1, tab2, w0, w1, w2, sT, sW, rX, rX + C::SZ_A, sC);
+    element_prepare<P, Q, NT, CS>(Pd, e, tab0, tab1, tab2, w0, w1, w2, sT, sW, rX, rX + C::SZ_A, sC);
     // ---- T1 zeroed (its padding columns must stay zero; the scratch it aliases is free after element_prepare)
     for (int idx = tid; idx < S::SZ_T1; idx += NT) sT1[idx] = 0.0;
     // ---- B2[(g, c, q1)][pi1 = j1 + NB1 i1] = Phi1[q1][i1][b1(beta)] Phi1[q1][j1][b1(gamma)],  b1(beta) = (beta == 2)
@@ -942,6 +957,402 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
   }
 }
 
+// =====================================================================================================================
+// Warp-specialised version of the sum-factorised kernel: ONE 512-thread block per SM, the same three stages per pass
+// (a, i2, b), but run as a pipeline between two kinds of warps instead of barrier-separated phases of one block:
+//   * 4 DMMA warps (one per SM sub-partition): stage 2 and stage 3 of pass k, nothing else -- their instruction stream is
+//     fragment loads, DMMAs and the unscaled 8x8 accumulator tiles written to a shared-memory tile buffer;
+//   * 12 helper warps: stage 1 (FMA) of pass k+1 while the DMMA warps are in stage 3 of pass k, and the epilogue of pass
+//     k -- scaling by the rational weights w_i w_j and the stores to global memory -- while they are in stage 2 of pass
+//     k+1.  A pass's 25 rows of K_e are ONE contiguous run, so the epilogue is a flat, fully coalesced scaled copy; for
+//     elasticity the three b-blocks of a row meet in the tile buffer and leave together as complete rows of 3 n_b doubles
+//     (the interleaved (j, b) stores of gram_sf_kernel cost it 2.2x the algorithmic DRAM traffic).
+// Hand-offs are named barriers (bar.arrive on the producing side, bar.sync on the consuming side): T1 full / free, tile
+// buffer full / free, plus one barrier inside each group.  The element preparation (tables, control points, geometry,
+// stage operands) is done by all 16 warps together between two elements.
+__device__ __forceinline__ void nb_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nb_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <int P, int Q, int KIND>
+struct WCfg {
+  static constexpr int NWM = 8, NWH = 8, NT = 32 * (NWM + NWH), NTH = 32 * NWH, NTM = 32 * NWM;
+  using S = SCfg<P, Q, KIND, NWM>;
+  using F = FCfg<P, Q>;
+  static constexpr int NCP = S::ELAS ? 3 : 1;
+  static constexpr int SZ_B3 = S::K3 * S::LDB2;
+  static constexpr int SZ_K = F::ev(S::NP * S::NB * NCP);  // the rows (i0, i1) of one i2 (x the three b-blocks)
+  static constexpr int SZ_TOTAL = F::SZ_T + F::SZ_W + S::SZ_CS + S::SZ_X + S::SZ_M + 2 * S::SZ_T2 + S::SZ_B2 + SZ_B3 + SZ_K;
+  static constexpr bool FITS = SZ_TOTAL * 8 <= 227 * 1024;
+};
+
+template <int P, int Q, int KIND>
+__global__ void __launch_bounds__(512, 1) gram_ws_kernel(
+    PatchDev Pd, long long elem_begin, long long nelem, const double* __restrict__ tab0,
+    const double* __restrict__ tab1, const double* __restrict__ tab2, const double* __restrict__ w0,
+    const double* __restrict__ w1, const double* __restrict__ w2, ElasCoef coef, double fconst,
+    double* __restrict__ Ke, double* __restrict__ fe) {
+  using C = FCfg<P, Q>;
+  using WC = WCfg<P, Q, KIND>;
+  using S = typename WC::S;
+  constexpr bool MASS = S::MASS, ELAS = S::ELAS;
+  constexpr int NCP = WC::NCP, NROWK = NCP * S::NB;
+  constexpr int NB1 = S::NB1, NP = S::NP, NB = S::NB, NQ = S::NQ, CS = S::CSS, TAB = C::TAB;
+  constexpr int NT = WC::NT, NTH = WC::NTH, NTM = WC::NTM;
+  constexpr int LDA2 = S::LDA2, LDB2 = S::LDB2, LDA3 = S::LDA3;
+  constexpr int NPASS = NCP * NB1 * NCP;
+  enum { BAR_T1_FULL = 1, BAR_T1_FREE = 2, BAR_K_FULL = 3, BAR_K_FREE = 4, BAR_MMA = 5, BAR_HLP = 6 };
+  extern __shared__ __align__(16) double ssm[];
+  double* const sT = ssm;
+  double* const sW = sT + C::SZ_T;
+  double* const sC = sW + C::SZ_W;
+  double* const rX = sC + S::SZ_CS;  // element_prepare's scratch (rA | sS2), then T1
+  double* const sT1 = rX;
+  double* const sM = rX + S::SZ_X;
+  double* const sT2 = sM + S::SZ_M;  // two buffers
+  double* const sB2 = sT2 + 2 * S::SZ_T2;
+  double* const sB3 = sB2 + S::SZ_B2;
+  double* const sK = sB3 + WC::SZ_B3;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool is_mma = warp < WC::NWM;
+  const int htid = tid - NTM;  // helper thread index (negative for the DMMA warps)
+  const int lr = lane >> 2, lc = lane & 3;
+  for (int idx = tid; idx < C::SZ_W; idx += NT) sW[idx] = 0.0;
+  for (int idx = tid; idx < S::SZ_B2; idx += NT) sB2[idx] = 0.0;      // padding rows stay zero
+  for (int idx = tid; idx < 2 * S::SZ_T2; idx += NT) sT2[idx] = 0.0;  // padding rows / columns of T2 stay zero
+
+  // ---- DMMA warps: fragment <-> index maps, the same for every element (see gram_sf_kernel)
+  const int tile0 = warp * S::TPW;
+  const bool has2 = is_mma && tile0 < S::MT2 * S::NT2;
+  const int mt2 = has2 ? tile0 / S::NT2 : 0, nt2 = has2 ? tile0 % S::NT2 : 0;
+  int t2off[S::TPW][2];
+  {
+    const int m = 8 * mt2 + lr;
+#pragma unroll
+    for (int s = 0; s < S::TPW; ++s)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int n = 8 * (nt2 + s) + 2 * lc + h;
+        t2off[s][h] = (has2 && m < S::M2 && n < NP) ? ((n % NB1) + NB1 * (m / Q) + NP * (n / NB1)) * LDA3 + (m % Q) : -1;
+      }
+  }
+  // stage 3: column n of a tile is (j0, i0) = (n % NB1, n / NB1): offset into the tile buffer i0 * (NB * NCP) + j0 * NCP
+  int c3[S::NT3][2];
+#pragma unroll
+  for (int nt = 0; nt < S::NT3; ++nt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n = 8 * nt + 2 * lc + h;
+      c3[nt][h] = n < NP ? (n / NB1) * (NB * NCP) + (n % NB1) * NCP : -1;
+    }
+  // stage 3: row lr of this warp's u-th tile row is (j1, j2, i1): offset NB1 i1 * (NB * NCP) + (NB1 j1 + NP j2) * NCP
+  constexpr int NMT = (S::MT3 + WC::NWM - 1) / WC::NWM;
+  int r3[NMT];
+#pragma unroll
+  for (int u = 0; u < NMT; ++u) {
+    const int mp = 8 * (warp + WC::NWM * u) + lr;
+    r3[u] = (is_mma && mp < S::M3) ? (NB1 * (mp / NP)) * (NB * NCP) + (NB1 * (mp % NB1) + NP * ((mp / NB1) % NB1)) * NCP : -1;
+  }
+
+  IGAB_WPT_BEGIN
+  for (long long el = blockIdx.x; el < nelem; el += gridDim.x) {
+    const long long e = elem_begin + el;
+    element_prepare<P, Q, NT, CS>(Pd, e, tab0, tab1, tab2, w0, w1, w2, sT, sW, rX, rX + C::SZ_A, sC);
+    IGAB_WPT(is_mma ? 8 : 9)
+    // ---- between two elements, all 16 warps: T1 zeroed, the B operands of stages 2 / 3, the point matrices M4
+    for (int idx = tid; idx < S::SZ_T1; idx += NT) sT1[idx] = 0.0;
+#pragma unroll
+    for (int g = 0; g < S::NG; ++g) {
+      for (int idx = tid; idx < S::ncombo(g) * Q * NP; idx += NT) {
+        const int n = idx % NP, r = idx / NP, q1 = r % Q, c = r / Q;
+        const int j1 = n % NB1, i1 = n / NB1;
+        const int bb = S::beta_of(g, c) == 2, bg = S::gamma_of(g, c) == 2;
+        sB2[(S::goff(g) + c * Q + q1) * LDB2 + n] =
+            sT[TAB + (q1 * NB1 + i1) * 2 + bb] * sT[TAB + (q1 * NB1 + j1) * 2 + bg];
+      }
+    }
+    for (int idx = tid; idx < S::K3 * S::NPP; idx += NT) {
+      const int n = idx % S::NPP, k = idx / S::NPP;
+      double v = 0.0;
+      if (k < S::NG * Q && n < NP) {
+        const int g = k / Q, q0 = k % Q, j0 = n % NB1, i0 = n / NB1;
+        const int bb = (g == 1 || g == 3) ? 1 : 0, bg = (g >= 2) ? 1 : 0;
+        v = sT[(q0 * NB1 + i0) * 2 + bb] * sT[(q0 * NB1 + j0) * 2 + bg];
+      }
+      sB3[k * LDB2 + n] = v;
+    }
+    if constexpr (!ELAS) {
+      for (int pt = tid; pt < NQ; pt += NT) {
+        const double* o = sC + CS * pt;
+        if constexpr (MASS) {
+          sM[pt] = o[15] * o[15];
+        } else {
+          double Cm[3][4];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            Cm[c][0] = -o[1 + c];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) Cm[c][1 + d] = o[4 + 3 * c + d];
+          }
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int g = b; g < 4; ++g)
+              sM[S::usym(b, g) * NQ + pt] = Cm[0][b] * Cm[0][g] + Cm[1][b] * Cm[1][g] + Cm[2][b] * Cm[2][g];
+        }
+      }
+    }
+    __syncthreads();
+    IGAB_WPT(is_mma ? 10 : 11)
+    double* const K = Ke + el * (long long)NROWK * NROWK;
+
+    if (is_mma) {
+      // ================================ DMMA warps: stage 2, stage 3 ================================================
+      double b3[S::K3 / 4][S::NT3];
+#pragma unroll
+      for (int ks = 0; ks < S::K3 / 4; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < S::NT3; ++nt) b3[ks][nt] = sB3[(4 * ks + lc) * LDB2 + 8 * nt + lr];
+      for (int k = 0; k < NPASS; ++k) {
+        const int cb = k % NCP;
+        double* const T2 = sT2 + (k & 1) * S::SZ_T2;
+        nb_sync(BAR_T1_FULL, NT);
+        IGAB_WPT(0)
+        // ---- stage 2: C_g[(j2,q0)][pi1] = sum_{k in g} T1[.][k] B2[k][.]  ->  T2[j1 + NB1 j2 + NP i1][g Q + q0]
+        if constexpr (S::GEN2) {
+          for (int tile = warp; tile < S::MT2 * S::NT2; tile += WC::NWM) {
+            const int mt = tile / S::NT2, nt = tile % S::NT2;
+            const double* arow = sT1 + (8 * mt + lr) * LDA2 + lc;
+            const double* brow = sB2 + lc * LDB2 + 8 * nt + lr;
+            const int m = 8 * mt + lr;
+            int off[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int n = 8 * nt + 2 * lc + h;
+              off[h] = (m < S::M2 && n < NP) ? ((n % NB1) + NB1 * (m / Q) + NP * (n / NB1)) * LDA3 + (m % Q) : -1;
+            }
+#pragma unroll
+            for (int g = 0; g < S::NG; ++g) {
+              double a0 = 0.0, a1 = 0.0;
+              const int kb = S::goff(g), nks = S::r4(S::ncombo(g) * Q) / 4;
+#pragma unroll 4
+              for (int ks = 0; ks < nks; ++ks) dmma8x8x4_f(a0, a1, arow[kb + 4 * ks], brow[(kb + 4 * ks) * LDB2]);
+              if (off[0] >= 0) T2[off[0] + g * Q] = a0;
+              if (off[1] >= 0) T2[off[1] + g * Q] = a1;
+            }
+          }
+        } else if (has2) {
+          const double* arow = sT1 + (8 * mt2 + lr) * LDA2 + lc;
+          const double* brow = sB2 + lc * LDB2 + 8 * nt2 + lr;
+#pragma unroll
+          for (int g = 0; g < S::NG; ++g) {
+            double acc[S::TPW][2];
+#pragma unroll
+            for (int s = 0; s < S::TPW; ++s) acc[s][0] = acc[s][1] = 0.0;
+            const int kb = S::goff(g), nks = S::r4(S::ncombo(g) * Q) / 4;
+#pragma unroll
+            for (int ks = 0; ks < nks; ++ks) {
+              const double a = arow[kb + 4 * ks];
+#pragma unroll
+              for (int s = 0; s < S::TPW; ++s) dmma8x8x4_f(acc[s][0], acc[s][1], a, brow[(kb + 4 * ks) * LDB2 + 8 * s]);
+            }
+#pragma unroll
+            for (int s = 0; s < S::TPW; ++s)
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+                if (t2off[s][h] >= 0) T2[t2off[s][h] + g * Q] = acc[s][h];
+          }
+        }
+        IGAB_WPT(1)
+        if (k + 1 < NPASS) nb_arrive(BAR_T1_FREE, NT);  // T1 consumed: the helpers may write pass k+1 into it
+        nb_sync(BAR_MMA, NTM);                           // T2 of this pass complete
+        if (cb == 0 && k > 0) nb_sync(BAR_K_FREE, NT);   // the epilogue of the previous rows has left the tile buffer
+        IGAB_WPT(2)
+        // ---- stage 3: G[(j1,j2,i1)][pi0] = sum_{(g,q0)} T2 B3, unscaled, into the tile buffer
+#pragma unroll
+        for (int u = 0; u < NMT; ++u) {
+          const int mt = warp + WC::NWM * u;
+          if (mt >= S::MT3) break;
+          double acc[S::NT3][2];
+#pragma unroll
+          for (int nt = 0; nt < S::NT3; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+          const double* arow = T2 + (8 * mt + lr) * LDA3 + lc;
+#pragma unroll
+          for (int ks = 0; ks < S::K3 / 4; ++ks) {
+            const double a = arow[4 * ks];
+#pragma unroll
+            for (int nt = 0; nt < S::NT3; ++nt) dmma8x8x4_f(acc[nt][0], acc[nt][1], a, b3[ks][nt]);
+          }
+          if (r3[u] >= 0) {
+            double* const kb = sK + r3[u] + cb;
+#pragma unroll
+            for (int nt = 0; nt < S::NT3; ++nt)
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+                if (c3[nt][h] >= 0) kb[c3[nt][h]] = acc[nt][h];
+          }
+        }
+        IGAB_WPT(3)
+        if (cb == NCP - 1) {
+          __threadfence_block();
+          nb_arrive(BAR_K_FULL, NT);
+        }
+      }
+    } else {
+      // ================================ helper warps: stage 1, epilogue ============================================
+      auto point_matrices = [&](int ca, int cb) {  // elasticity: M4 = C^T Cf[a][.][b][.] C per point
+        if constexpr (ELAS) {
+          for (int pt = htid; pt < NQ; pt += NTH) {
+            const double* o = sC + CS * pt;
+            double Cm[3][4], Tm[3][4];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              Cm[c][0] = -o[1 + c];
+#pragma unroll
+              for (int d = 0; d < 3; ++d) Cm[c][1 + d] = o[4 + 3 * c + d];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                double t = 0.0;
+#pragma unroll
+                for (int cp = 0; cp < 3; ++cp) t = fma(coef.cf[((ca * 3 + c) * 3 + cb) * 3 + cp], Cm[cp][g], t);
+                Tm[c][g] = t;
+              }
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                sM[(b * 4 + g) * NQ + pt] = Cm[0][b] * Tm[0][g] + Cm[1][b] * Tm[1][g] + Cm[2][b] * Tm[2][g];
+          }
+          nb_sync(BAR_HLP, NTH);
+        }
+      };
+      auto stage1 = [&](int i2) {
+        // thread <-> (combo, q1, pair of q0), all j2: the M4 line and the i2 factor in registers
+        constexpr int QH = 2, NSPL = (Q + QH - 1) / QH;
+        for (int item = htid; item < S::NCOMBO * Q * NSPL; item += NTH) {
+          const int part = item % NSPL, r = item / NSPL, q1 = r % Q, cc = r / Q;
+          int g = 0, c = cc;
+          if constexpr (!MASS) {
+            if (cc >= 15) { g = 3; c = 0; }
+            else if (cc >= 12) { g = 2; c = cc - 12; }
+            else if (cc >= 9) { g = 1; c = cc - 9; }
+          }
+          const int be = S::beta_of(g, c), ga = S::gamma_of(g, c);
+          const int bb = be == 3, bg = ga == 3;
+          const int qa = part * QH;
+          const double* mrow = sM + S::usym(be, ga) * NQ + Q * q1;
+          double am[QH][Q];
+#pragma unroll
+          for (int q2 = 0; q2 < Q; ++q2) {
+            const double a2 = sT[2 * TAB + (q2 * NB1 + i2) * 2 + bb];
+#pragma unroll
+            for (int u = 0; u < QH; ++u) am[u][q2] = a2 * mrow[min(qa + u, Q - 1) + Q * Q * q2];
+          }
+          double* trow = sT1 + S::goff(g) + c * Q + q1;
+#pragma unroll
+          for (int j2 = 0; j2 < NB1; ++j2) {
+            double f[Q];
+#pragma unroll
+            for (int q2 = 0; q2 < Q; ++q2) f[q2] = sT[2 * TAB + (q2 * NB1 + j2) * 2 + bg];
+#pragma unroll
+            for (int u = 0; u < QH; ++u) {
+              double sum = 0.0;
+#pragma unroll
+              for (int q2 = 0; q2 < Q; ++q2) sum = fma(am[u][q2], f[q2], sum);
+              if (qa + u < Q) trow[(j2 * Q + qa + u) * LDA2] = sum;
+            }
+          }
+        }
+        __threadfence_block();
+        nb_arrive(BAR_T1_FULL, NT);
+      };
+      point_matrices(0, 0);
+      stage1(0);
+      IGAB_WPT(5)
+      for (int k = 0; k < NPASS; ++k) {
+        const int cb = k % NCP, i2 = (k / NCP) % NB1, ca = k / (NCP * NB1);
+        if (k + 1 < NPASS) {
+          const int k1 = k + 1;
+          nb_sync(BAR_T1_FREE, NT);
+          IGAB_WPT(4)
+          point_matrices(k1 / (NCP * NB1), k1 % NCP);
+          stage1((k1 / NCP) % NB1);
+          IGAB_WPT(5)
+        }
+        if (cb == NCP - 1) {
+          nb_sync(BAR_K_FULL, NT);
+          IGAB_WPT(6)
+          // ---- epilogue: the NP rows (i0, i1) of this i2 (x component a), scaled by w_i w_j, as complete rows: a warp
+          //      takes whole rows, its lanes consecutive columns (coalesced 256-byte stores)
+          {
+            const int hw = warp - WC::NWM;
+            for (int row = hw; row < NP; row += WC::NWH) {
+              const int i = row + NP * i2;
+              const double wi = sW[i];
+              const double* src = sK + row * NROWK;
+              double* dst = ELAS ? K + (long long)(i * 3 + ca) * NROWK : K + (long long)i * NB;
+#pragma unroll 4
+              for (int c = lane; c < NROWK; c += 32) dst[c] = src[c] * (wi * sW[ELAS ? c / 3 : c]);
+            }
+          }
+          IGAB_WPT(7)
+          if (k + 1 < NPASS) nb_arrive(BAR_K_FREE, NT);
+        }
+      }
+      IGAB_WPT(12)
+      // ---- load vector f_e[i] = sum_q w detJ R_i fconst  (poisson.py:79)
+      if (fe) {
+        for (int i = htid; i < NB; i += NTH) {
+          const int i0 = i % NB1, i1 = (i / NB1) % NB1, i2 = i / (NB1 * NB1);
+          const double w = sW[i];
+          double s = 0.0;
+          for (int pt = 0; pt < NQ; ++pt) {
+            const int q0 = pt % Q, q1 = (pt / Q) % Q, q2 = pt / (Q * Q);
+            const double R = sT[(q0 * NB1 + i0) * 2] * sT[TAB + (q1 * NB1 + i1) * 2] *
+                             (w * sT[2 * TAB + (q2 * NB1 + i2) * 2]) * sC[CS * pt];
+            s += sC[CS * pt + 13] * R * fconst;
+          }
+          if constexpr (ELAS)
+            fe[el * NROWK + 3 * i] = fe[el * NROWK + 3 * i + 1] = fe[el * NROWK + 3 * i + 2] = s;
+          else
+            fe[el * NB + i] = s;
+        }
+      }
+    }
+  }
+}
+
+template <int P, int Q, int KIND>
+igab_status launch_ws(const PatchDev& Pd, SfWorkspace& ws, const ElasCoef& coef, double fconst, long long eb,
+                      long long nel, const double* const* w_dev, double* Ke, double* fe, cudaStream_t stream) {
+  using WC = WCfg<P, Q, KIND>;
+  const size_t sm = (size_t)WC::SZ_TOTAL * sizeof(double);
+  KernelCfg kc;
+  if (igab_status cst = kernel_config((const void*)gram_ws_kernel<P, Q, KIND>, WC::NT, sm, &kc)) return cst;
+  const unsigned grid = (unsigned)std::min<long long>(nel, (long long)kc.blocksPerSm * kc.sms);
+  gram_ws_kernel<P, Q, KIND><<<grid, WC::NT, sm, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],
+                                                          w_dev[1], w_dev[2], coef, fconst, Ke, fe);
+  count_launch();
+  IGAB_CUDA_TRY(cudaGetLastError());
+  return IGAB_OK;
+}
+// Which configurations take the warp-specialised kernel.  Measured on B200 (tools/ws_bench.py, profiles/README.md): for
+// elasticity at p = 4 it runs at the speed of gram_sf_kernel and writes K_e with 0.98x the algorithmic DRAM traffic
+// instead of 2.2x (complete rows leave the tile buffer) -> default there.  For Poisson / mass it is 0.7-0.9x: with one
+// block per SM the element preparation is exposed (a quarter of the element's time) and the shared-memory pipe, not the
+// DMMA pipe, is the busiest unit -> compiled, tested, selectable with IGAB_GRAM_WS=1, not the default.
+template <int P, int Q, int KIND>
+constexpr bool ws_compiled() {
+  return (P == 4 && Q == 5) || (P == 3 && Q == 4);
+}
+template <int P, int Q, int KIND>
+inline bool ws_wanted() {
+  const char* env = getenv("IGAB_GRAM_WS");
+  return env ? env[0] != '0' : (KIND == 2 && P == 4);
+}
+
 template <int P, int Q>
 igab_status launch_elas_sf(const PatchDev& Pd, SfWorkspace& ws, const double* D_host, double fconst, long long eb,
                            long long nel, const double* const* w_dev, double* Ke, double* fe, cudaStream_t stream) {
@@ -951,6 +1362,9 @@ igab_status launch_elas_sf(const PatchDev& Pd, SfWorkspace& ws, const double* D_
   for (double& v : coef.cf) v = 0.0;
   for (auto& s1 : S)
     for (auto& s2 : S) coef.cf[((s1[1] * 3 + s1[2]) * 3 + s2[1]) * 3 + s2[2]] += D_host[s1[0] * 6 + s2[0]];
+  if constexpr (ws_compiled<P, Q, 2>()) {
+    if (ws_wanted<P, Q, 2>()) return launch_ws<P, Q, 2>(Pd, ws, coef, fconst, eb, nel, w_dev, Ke, fe, stream);
+  }
   const size_t sm = (size_t)SCfg<P, Q, 2>::SZ_TOTAL * sizeof(double);
   KernelCfg kc;
   if (igab_status cst = kernel_config((const void*)gram_sf_kernel<P, Q, 2>, 256, sm, &kc)) return cst;
@@ -992,6 +1406,13 @@ igab_status launch_pq(const PatchDev& Pd, SfWorkspace& ws, bool mass, double fco
     // IGAB_GRAM_SF=0 / 1 forces the dense-Gram / the sum-factorised kernel
     const char* env = getenv("IGAB_GRAM_SF");
     if (env ? env[0] != '0' : P >= 3) {
+      if constexpr (ws_compiled<P, Q, 0>()) {
+        if (ws_wanted<P, Q, 0>()) {
+          const ElasCoef nc{};
+          return mass ? launch_ws<P, Q, 1>(Pd, ws, nc, fconst, eb, nel, w_dev, Ke, fe, stream)
+                      : launch_ws<P, Q, 0>(Pd, ws, nc, fconst, eb, nel, w_dev, Ke, fe, stream);
+        }
+      }
       const void* fn = mass ? (const void*)gram_sf_kernel<P, Q, 1> : (const void*)gram_sf_kernel<P, Q, 0>;
       const size_t sm = (size_t)(mass ? SCfg<P, Q, 1>::SZ_TOTAL : SCfg<P, Q, 0>::SZ_TOTAL) * sizeof(double);
       const ElasCoef nocoef{};
@@ -1086,7 +1507,7 @@ igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* 
 
 #ifdef IGAB_PHASE_TIMING
 extern "C" int igab_debug_phase_ticks(unsigned long long* out, int reset) {
-  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long z[16] = {0};
   if (out && cudaMemcpyFromSymbol(out, igab::g_phase_ticks, sizeof(z)) != cudaSuccess) return 1;
   if (reset && cudaMemcpyToSymbol(igab::g_phase_ticks, z, sizeof(z)) != cudaSuccess) return 1;
   return 0;

@@ -198,3 +198,36 @@ def test_switching_streams_on_one_handle_is_ordered():
     for k, o in outs:
         for f in ("N", "dN", "detJ"):
             assert np.array_equal(o[f].cpu().numpy(), serial[k][f]), (k, f)
+
+
+@pytest.mark.parametrize("p", [3, 4])
+@pytest.mark.parametrize("kind", [capi.ASM_POISSON, capi.ASM_MASS, capi.ASM_ELASTICITY])
+def test_warp_specialised_assembly_kernel_matches_oracle_and_the_barrier_separated_kernel(p, kind, monkeypatch):
+    """gram_ws_kernel (DMMA warps + helper warps, named barriers, tile buffer) against the oracle and, bit for bit, against
+    gram_sf_kernel: more elements than resident blocks (grid-stride + pipeline drain between elements), non-symmetric
+    material, load vector."""
+    import torch
+    pd = PD.thickCylinder(p, (3, 3, 2))  # 8 x 8 x 4 = 256 elements > 148 resident blocks
+    spec = dict(degree=pd.degree, knots=pd.knotSpans, cp=PD.perturbed(pd, seed=3, amp=0.05).cp, dimworld=3)
+    P, O = gpu_patch(spec), port_for(spec)
+    x, w = PD.gaussLegendre01(p + 1)
+    rng = np.random.default_rng(9)
+    D = rng.normal(size=(6, 6)) + 4 * np.eye(6) if kind == capi.ASM_ELASTICITY else None
+    n = P.nb * (3 if kind == capi.ASM_ELASTICITY else 1)
+    out = {}
+    monkeypatch.setenv("IGAB_ELAS_SF", "1")
+    for mode in ("0", "1"):
+        monkeypatch.setenv("IGAB_GRAM_WS", mode)
+        Ke = torch.zeros((P.nelem, n, n), dtype=torch.float64, device="cuda")
+        fe = torch.zeros((P.nelem, n), dtype=torch.float64, device="cuda")
+        l0 = capi.launch_count()
+        P.assemble(kind, [x] * 3, [w] * 3, D=D, fconst=0.7, Ke=Ke, fe=fe)
+        torch.cuda.synchronize()
+        assert capi.launch_count() > l0
+        out[mode] = (Ke.cpu().numpy(), fe.cpu().numpy())
+    assert np.array_equal(out["0"][0], out["1"][0]) and np.array_equal(out["0"][1], out["1"][1])
+    sample = np.array([0, 1, 147, 148, 149, 200, 255])
+    for e in sample:
+        Kr, fr = O.assemble(kind, [x] * 3, [w] * 3, D=D, fconst=0.7, elem_begin=int(e), elem_end=int(e) + 1)
+        assert relerr(out["1"][0][e].reshape(1, -1), Kr.reshape(1, -1)) <= TOL
+        assert relerr(out["1"][1][e].reshape(1, -1), fr.reshape(1, -1)) <= TOL
