@@ -28,7 +28,7 @@ EXPORTS = ("igab_last_error_string", "igab_version", "igab_launch_count", "igab_
            "igab_csr_dirichlet", "igab_assemble_points", "igab_global_assemble", "igab_reduce_volume_trimmed", "igab_reduce_norms_trimmed",
            "igab_partition_slab", "igab_interface_row_ranges", "igab_comm_unique_id", "igab_comm_create",
            "igab_comm_destroy", "igab_comm_info", "igab_exchange_interface_rows", "igab_patch_real_index_maps",
-           "igab_load_vector", "igab_load_vector_points", "igab_global_load_vector", "igab_device_numa_node")
+           "igab_load_vector", "igab_load_vector_points", "igab_global_load_vector", "igab_device_numa_node", "igab_eval_tensor_begin", "igab_patch_wait")
 
 
 class EvalOut(C.Structure):
@@ -64,6 +64,9 @@ def lib():
         L.igab_patch_dofmap.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.c_void_p]
         L.igab_eval_tensor.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, ip, C.POINTER(dp),
                                        C.POINTER(EvalOut), C.c_int, C.c_void_p]
+        L.igab_eval_tensor_begin.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, ip, C.POINTER(dp),
+                                             C.POINTER(EvalOut), C.c_void_p]
+        L.igab_patch_wait.argtypes = [C.c_void_p]
         L.igab_eval_points.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(EvalOut),
                                        C.c_int, C.c_void_p]
         L.igab_partial.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, ip, C.c_void_p, C.c_int, C.c_void_p]
@@ -325,6 +328,23 @@ class Patch:
         _check(lib().igab_eval_tensor(self.h, elem_begin, elem_end, order, nq1.ctypes.data_as(ip), ptrs,
                                       C.byref(eo), space, stream))
         return res
+
+    def evalTensorBegin(self, xi1d, out, order=1, elem_begin=0, elem_end=None, want=FIELDS, stream=None):
+        """igab_eval_tensor_begin: queue the evaluation of [elem_begin, elem_end) into the HOST arrays `out` (pinned_empty)
+        and return at once; wait() before reading them."""
+        if elem_end is None:
+            elem_end = self.nelem
+        arrs, ptrs = _rule_arrays(xi1d)
+        nq1 = _i32([len(a) for a in arrs])
+        npts = (elem_end - elem_begin) * int(np.prod(nq1))
+        res, eo, space = self._outset(npts, order, want, out)
+        assert space == HOST
+        _check(lib().igab_eval_tensor_begin(self.h, elem_begin, elem_end, order, nq1.ctypes.data_as(ip), ptrs,
+                                            C.byref(eo), stream))
+        return res
+
+    def wait(self):
+        _check(lib().igab_patch_wait(self.h))
 
     def evalPoints(self, elem, xi, order=1, want=FIELDS, out=None, stream=None):
         ea, es = _ptr(elem if not isinstance(elem, (list, tuple)) else _i32(elem))

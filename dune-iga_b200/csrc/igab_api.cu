@@ -265,6 +265,9 @@ igab_status enter_stream(igab_patch* p, cudaStream_t stream) {
     set_error("null patch handle");
     return IGAB_INVALID_ARGUMENT;
   }
+  if (p->pending_host) {  // an igab_eval_tensor_begin is in flight: its staging buffers are handle scratch
+    if (igab_status wst = igab_patch_wait(p)) return wst;
+  }
   if (p->have_last_stream && p->last_stream != stream) {
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (p->last_stream) cudaStreamIsCapturing(p->last_stream, &cap);
@@ -789,9 +792,9 @@ igab_status igab_patch_real_index_maps(igab_patch* p, int32_t* direct_of_real, i
 }
 
 // ---- evaluation -----------------------------------------------------------------------------------------------------
-igab_status igab_eval_tensor(igab_patch* p, int64_t elem_begin, int64_t elem_end, int deriv_order, const int* nq1,
-                             const double* const* xi1d, const igab_eval_out* out, igab_memspace out_space,
-                             void* stream_) {
+static igab_status eval_tensor_impl(igab_patch* p, int64_t elem_begin, int64_t elem_end, int deriv_order, const int* nq1,
+                                    const double* const* xi1d, const igab_eval_out* out, igab_memspace out_space,
+                                    void* stream_, bool async_host) {
   if (!p || !nq1 || !xi1d) {
     set_error("eval_tensor: null argument");
     return IGAB_INVALID_ARGUMENT;
@@ -867,11 +870,43 @@ igab_status igab_eval_tensor(igab_patch* p, int64_t elem_begin, int64_t elem_end
     if (st) break;
     if ((e = cudaEventRecord(p->stage_copied[b], cstream)) != cudaSuccess) { st = cuda_fail(e, "record copied"); break; }
   }
+  if (async_host && !st) {  // igab_eval_tensor_begin: the caller collects the result with igab_patch_wait
+    p->pending_host_stream = stream;
+    p->pending_host = true;
+    return IGAB_OK;
+  }
   e = cudaStreamSynchronize(cstream);
   if (e != cudaSuccess && !st) st = cuda_fail(e, "sync copy stream");
   e = cudaStreamSynchronize(stream);
   if (e != cudaSuccess && !st) st = cuda_fail(e, "sync stream");
   return st;
+}
+
+igab_status igab_eval_tensor(igab_patch* p, int64_t elem_begin, int64_t elem_end, int deriv_order, const int* nq1,
+                             const double* const* xi1d, const igab_eval_out* out, igab_memspace out_space,
+                             void* stream_) {
+  if (p && p->pending_host) {
+    if (igab_status st = igab_patch_wait(p)) return st;
+  }
+  return eval_tensor_impl(p, elem_begin, elem_end, deriv_order, nq1, xi1d, out, out_space, stream_, false);
+}
+
+igab_status igab_eval_tensor_begin(igab_patch* p, int64_t elem_begin, int64_t elem_end, int deriv_order, const int* nq1,
+                                   const double* const* xi1d, const igab_eval_out* out, void* stream_) {
+  if (p && p->pending_host) {
+    if (igab_status st = igab_patch_wait(p)) return st;
+  }
+  return eval_tensor_impl(p, elem_begin, elem_end, deriv_order, nq1, xi1d, out, IGAB_HOST, stream_, true);
+}
+
+igab_status igab_patch_wait(igab_patch* p) {
+  if (!p) return IGAB_INVALID_ARGUMENT;
+  if (!p->pending_host) return IGAB_OK;
+  p->pending_host = false;
+  cudaError_t e = p->stage_stream ? cudaStreamSynchronize(p->stage_stream) : cudaSuccess;
+  if (e == cudaSuccess) e = cudaStreamSynchronize(p->pending_host_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "patch_wait");
+  return IGAB_OK;
 }
 
 igab_status igab_eval_points(igab_patch* p, int64_t npts, const int32_t* elem, const double* xi, int deriv_order,

@@ -224,6 +224,9 @@ struct igab_patch {
   double* xch_buf = nullptr;
   size_t xch_cap = 0;  // doubles
   std::vector<int32_t> dofc_map_host;
+  // igab_eval_tensor_begin in flight (host outputs still landing): collected by igab_patch_wait / the next call
+  bool pending_host = false;
+  cudaStream_t pending_host_stream = nullptr;
   // stream discipline: the stream of the last call, and the event that orders a new stream behind it
   cudaStream_t last_stream = nullptr;
   bool have_last_stream = false;

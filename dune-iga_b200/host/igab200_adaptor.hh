@@ -23,17 +23,20 @@
 //   NURBSGeometry::normal/unitNormal/metric/secondFundamentalForm/gaussianCurvature  :216-255  same names
 //   NURBSGridEntity::getQuadratureRule  dune/iga/nurbsgridentity.hh:120-141 Patch::setQuadratureRule (rule is an input)
 //
-// How it works: Patch::setQuadratureRule(rule) evaluates EVERY point of EVERY element once on the GPU
-// (igab_eval_tensor) and keeps the result in host vectors.  bind(e) + evaluate*(xi) then return the cached row when xi
-// is a point of the rule (exact coordinate match -- the quadrature loop of dune/python/test/poisson.py:47-79 or
-// dune/iga/test/gridtests.cpp:338-360), and fall back to a single-point GPU call (igab_eval_points) otherwise.  There is
-// no CPU evaluation path.
+// How it works: Patch::setQuadratureRule(rule) fixes the rule and a WINDOW of element blocks in page-locked host memory
+// (512 MB by default, whatever the patch size).  bind(e) + evaluate*(xi) return the cached row when xi is a point of the
+// rule (exact coordinate match -- the quadrature loop of dune/python/test/poisson.py:47-79 or
+// dune/iga/test/gridtests.cpp:338-360); the block of elements that holds e is evaluated on the GPU (igab_eval_tensor) the
+// first time one of its elements is touched, and the block after it is kept in flight (igab_eval_tensor_begin) while the
+// caller works on this one.  Arguments off the rule fall back to a single-point GPU call (igab_eval_points); corners and
+// centres are evaluated for a whole block at once.  There is no CPU evaluation path.
 //
 // Generic over the vector types: anything with operator[] works (Dune::FieldVector / FieldMatrix when DUNE is there,
 // std::array in the tests), because DUNE itself is not available in this build environment.
 // Error behaviour: the reference asserts / throws (DUNE_THROW, std::logic_error); the adaptor throws igab::Error
 // carrying the igab_status and igab_last_error_string().
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <memory>
@@ -85,7 +88,10 @@ public:
   }
   Patch(const Patch&) = delete;
   Patch& operator=(const Patch&) = delete;
-  ~Patch() { igab_patch_destroy(h_); }
+  ~Patch() {
+    releaseWindow();
+    igab_patch_destroy(h_);
+  }
 
   igab_patch* handle() const { return h_; }
   int64_t size0() const { return nElements_; }  // number of elements (codim 0)
@@ -96,44 +102,60 @@ public:
 
   // The rule every untrimmed element uses (nurbsgridentity.hh:120-133): abscissae / weights per direction on [0,1].
   // derivOrder 1: N, dN, x, Jt, detJ, JinvT are cached; 2 adds d2N, H.
+  //
+  // The results are NOT held for the whole patch (config C2 would need 289 GB): the cache is a WINDOW of `slots` blocks
+  // of consecutive elements in page-locked host memory, windowBytes in total.  Touching an element of a block that is
+  // not resident evaluates that block on the GPU (igab_eval_tensor) into the least recently used slot; walking the
+  // elements in index order -- the element iteration of the reference, nurbsleafgridview.hh:147-155 -- additionally
+  // keeps the NEXT block in flight (igab_eval_tensor_begin), so the caller's per-element work on block b overlaps the
+  // kernel and the transfer of block b + 1.  Host memory is bounded by windowBytes whatever the patch size.
   void setQuadratureRule(const std::array<std::vector<double>, dim>& xi, const std::array<std::vector<double>, dim>& w,
-                         int derivOrder = 1) {
+                         int derivOrder = 1, size_t windowBytes = size_t(512) << 20, int slots = 3) {
+    releaseWindow();
     xi_ = xi;
     w_ = w;
     order_ = derivOrder;
     nq_ = 1;
-    std::array<int, dim> nq1;
-    std::array<const double*, dim> xp;
     for (int i = 0; i < dim; ++i) {
-      nq1[i] = (int)xi[i].size();
-      xp[i] = xi[i].data();
-      nq_ *= nq1[i];
+      nq1_[i] = (int)xi[i].size();
+      xp_[i] = xi_[i].data();
+      nq_ *= nq1_[i];
     }
-    const size_t npts = (size_t)nElements_ * nq_;
-    N_.resize(npts * nb_);
-    dN_.resize(npts * nb_ * dim);
-    x_.resize(npts * dimworld);
-    Jt_.resize(npts * dim * dimworld);
-    detJ_.resize(npts);
-    JinvT_.resize(npts * dim * dimworld);
-    igab_eval_out out{};
-    out.N = N_.data();
-    out.dN = dN_.data();
-    out.x = x_.data();
-    out.Jt = Jt_.data();
-    out.detJ = detJ_.data();
-    out.JinvT = JinvT_.data();
-    if (derivOrder >= 2) {
-      d2N_.resize(npts * nb_ * nh);
-      H_.resize(npts * nh * dimworld);
-      out.d2N = d2N_.data();
-      out.H = H_.data();
+    // doubles per point of every cached field, in slot order: N dN x Jt detJ JinvT [d2N H]
+    const size_t per[8] = {(size_t)nb_, (size_t)nb_ * dim, (size_t)dimworld, (size_t)dim * dimworld, 1,
+                           (size_t)dim * dimworld, derivOrder >= 2 ? (size_t)nb_ * nh : 0,
+                           derivOrder >= 2 ? (size_t)nh * dimworld : 0};
+    size_t perPoint = 0;
+    for (size_t v : per) perPoint += v;
+    const size_t perElem = perPoint * (size_t)nq_ * sizeof(double);
+    if (slots < 2) slots = 2;
+    blockElems_ = (int64_t)(windowBytes / (size_t)slots / perElem);
+    if (blockElems_ < 1) blockElems_ = 1;
+    if (blockElems_ > nElements_) blockElems_ = nElements_;
+    numBlocks_ = (nElements_ + blockElems_ - 1) / blockElems_;
+    if ((int64_t)slots > numBlocks_) slots = (int)numBlocks_;
+    const size_t npts = (size_t)blockElems_ * nq_;
+    slotDoubles_ = 0;
+    for (int f = 0; f < 8; ++f) {
+      fieldOff_[f] = slotDoubles_;
+      slotDoubles_ += per[f] * npts;
     }
-    check(igab_eval_tensor(h_, 0, nElements_, derivOrder, nq1.data(), xp.data(), &out, IGAB_HOST, nullptr));
+    slots_.assign((size_t)slots, Slot{});
+    for (auto& sl : slots_) {
+      void* mem = nullptr;
+      check(igab_host_alloc(&mem, slotDoubles_ * sizeof(double)));
+      sl.mem = static_cast<double*>(mem);
+    }
     haveRule_ = true;
+    clock_ = 0;
+    blockEvaluations_ = 0;
   }
   bool hasRule() const { return haveRule_; }
   int64_t pointsPerElement() const { return nq_; }
+  // what the window holds: host bytes pinned, elements per block, blocks evaluated so far (re-evaluations included)
+  size_t windowBytes() const { return slots_.size() * slotDoubles_ * sizeof(double); }
+  int64_t blockElements() const { return blockElems_; }
+  int64_t blockEvaluations() const { return blockEvaluations_; }
   // weight of rule point q (product of the 1-D weights, first direction fastest)
   double weight(int64_t q) const {
     double r = 1;
@@ -167,16 +189,39 @@ public:
     return q;
   }
 
-  // cached rows
-  const double* N(int64_t e, int64_t q) const { return N_.data() + ((size_t)e * nq_ + q) * nb_; }
-  const double* dN(int64_t e, int64_t q) const { return dN_.data() + ((size_t)e * nq_ + q) * nb_ * dim; }
-  const double* d2N(int64_t e, int64_t q) const { return d2N_.data() + ((size_t)e * nq_ + q) * nb_ * nh; }
-  const double* x(int64_t e, int64_t q) const { return x_.data() + ((size_t)e * nq_ + q) * dimworld; }
-  const double* Jt(int64_t e, int64_t q) const { return Jt_.data() + ((size_t)e * nq_ + q) * dim * dimworld; }
-  const double* H(int64_t e, int64_t q) const { return H_.data() + ((size_t)e * nq_ + q) * nh * dimworld; }
-  double detJ(int64_t e, int64_t q) const { return detJ_[(size_t)e * nq_ + q]; }
-  const double* JinvT(int64_t e, int64_t q) const { return JinvT_.data() + ((size_t)e * nq_ + q) * dim * dimworld; }
+  // cached rows of element e (the block that holds e is made resident first)
+  const double* N(int64_t e, int64_t q) const { return field(0, e, q, (size_t)nb_); }
+  const double* dN(int64_t e, int64_t q) const { return field(1, e, q, (size_t)nb_ * dim); }
+  const double* x(int64_t e, int64_t q) const { return field(2, e, q, (size_t)dimworld); }
+  const double* Jt(int64_t e, int64_t q) const { return field(3, e, q, (size_t)dim * dimworld); }
+  double detJ(int64_t e, int64_t q) const { return *field(4, e, q, 1); }
+  const double* JinvT(int64_t e, int64_t q) const { return field(5, e, q, (size_t)dim * dimworld); }
+  const double* d2N(int64_t e, int64_t q) const { return field(6, e, q, (size_t)nb_ * nh); }
+  const double* H(int64_t e, int64_t q) const { return field(7, e, q, (size_t)nh * dimworld); }
   int derivOrder() const { return order_; }
+
+  // corners (k < 2^dim) and centre (k == 2^dim) of element e: evaluated for the WHOLE block of e in one batched call the
+  // first time any of them is asked for (the reference evaluates them per call, nurbsgeometry.hh:115-131)
+  const double* cornerOrCenter(int64_t e, int k) const {
+    if (!haveRule_) return nullptr;
+    Slot& sl = slotOf(e);
+    constexpr int nc = (1 << dim) + 1;
+    if (sl.corners.empty()) {
+      const int64_t e0 = sl.block * blockElems_, n = std::min(blockElems_, nElements_ - e0);
+      std::vector<int32_t> el((size_t)n * nc);
+      std::vector<double> xi((size_t)n * nc * dim);
+      for (int64_t a = 0; a < n; ++a)
+        for (int c = 0; c < nc; ++c) {
+          el[(size_t)a * nc + c] = (int32_t)(e0 + a);
+          for (int d = 0; d < dim; ++d) xi[((size_t)a * nc + c) * dim + d] = c == nc - 1 ? 0.5 : ((c >> d) & 1 ? 1.0 : 0.0);
+        }
+      sl.corners.resize((size_t)n * nc * dimworld);
+      igab_eval_out o{};
+      o.x = sl.corners.data();
+      check(igab_eval_points(h_, n * nc, el.data(), xi.data(), 0, &o, IGAB_HOST, nullptr));
+    }
+    return sl.corners.data() + ((size_t)(e - sl.block * blockElems_) * nc + k) * dimworld;
+  }
 
   // single point on the GPU (off-rule arguments)
   template <class Local>
@@ -217,6 +262,92 @@ public:
   }
 
 private:
+  struct Slot {
+    double* mem = nullptr;        // pinned host memory, all fields of one block back to back
+    int64_t block = -1;           // which block it holds (or is being filled with)
+    bool inFlight = false;        // igab_eval_tensor_begin queued, not yet waited for
+    uint64_t stamp = 0;           // last use (LRU)
+    std::vector<double> corners;  // [n][2^dim + 1][dimworld], filled on demand
+  };
+  igab_eval_out outOf(const Slot& sl) const {
+    igab_eval_out o{};
+    o.N = sl.mem + fieldOff_[0];
+    o.dN = sl.mem + fieldOff_[1];
+    o.x = sl.mem + fieldOff_[2];
+    o.Jt = sl.mem + fieldOff_[3];
+    o.detJ = sl.mem + fieldOff_[4];
+    o.JinvT = sl.mem + fieldOff_[5];
+    if (order_ >= 2) {
+      o.d2N = sl.mem + fieldOff_[6];
+      o.H = sl.mem + fieldOff_[7];
+    }
+    return o;
+  }
+  Slot* findSlot(int64_t block) const {
+    for (auto& sl : slots_)
+      if (sl.block == block) return &sl;
+    return nullptr;
+  }
+  Slot& victim(int64_t keep) const {
+    Slot* v = nullptr;
+    for (auto& sl : slots_)
+      if ((keep < 0 || sl.block != keep) && (!v || sl.stamp < v->stamp)) v = &sl;
+    return *v;
+  }
+  void launch(Slot& sl, int64_t block, bool async) const {
+    if (sl.inFlight) check(igab_patch_wait(h_));
+    sl.block = block;
+    sl.corners.clear();
+    sl.inFlight = false;
+    const int64_t e0 = block * blockElems_, e1 = std::min(nElements_, e0 + blockElems_);
+    const igab_eval_out o = outOf(sl);
+    if (async) {
+      check(igab_eval_tensor_begin(h_, e0, e1, order_, nq1_.data(), xp_.data(), &o, nullptr));
+      sl.inFlight = true;
+    } else {
+      check(igab_eval_tensor(h_, e0, e1, order_, nq1_.data(), xp_.data(), &o, IGAB_HOST, nullptr));
+    }
+    ++blockEvaluations_;
+  }
+  // the slot that holds element e, resident and complete; prefetches the following block
+  Slot& slotOf(int64_t e) const {
+    if (!haveRule_) throw Error(IGAB_INVALID_ARGUMENT, "setQuadratureRule first");
+    const int64_t block = e / blockElems_;
+    if (last_ && last_->block == block && !last_->inFlight) return *last_;
+    Slot* sl = findSlot(block);
+    if (!sl) {
+      sl = &victim(-1);
+      launch(*sl, block, false);
+    } else if (sl->inFlight) {
+      check(igab_patch_wait(h_));
+      sl->inFlight = false;
+    }
+    sl->stamp = ++clock_;
+    if (block + 1 < numBlocks_ && !findSlot(block + 1) && slots_.size() >= 2) {
+      bool busy = false;
+      for (auto& o : slots_) busy = busy || o.inFlight;
+      if (!busy) {
+        Slot& nx = victim(block);
+        launch(nx, block + 1, true);
+        nx.stamp = clock_;  // as recent as the block in use: the next miss evicts an older one
+      }
+    }
+    last_ = sl;
+    return *sl;
+  }
+  const double* field(int f, int64_t e, int64_t q, size_t width) const {
+    const Slot& sl = slotOf(e);
+    return sl.mem + fieldOff_[f] + ((size_t)(e - sl.block * blockElems_) * nq_ + q) * width;
+  }
+  void releaseWindow() {
+    if (h_) igab_patch_wait(h_);
+    for (auto& sl : slots_)
+      if (sl.mem) igab_host_free(sl.mem);
+    slots_.clear();
+    last_ = nullptr;
+    haveRule_ = false;
+  }
+
   PatchData<dim, dimworld> data_;
   igab_patch* h_ = nullptr;
   int64_t nElements_ = 0, nDofs_ = 0, nq_ = 0;
@@ -224,8 +355,16 @@ private:
   int nb_ = 0, order_ = 1;
   bool haveRule_ = false;
   std::array<std::vector<double>, dim> xi_, w_;
+  std::array<int, dim> nq1_{};
+  std::array<const double*, dim> xp_{};
   std::vector<int32_t> dof_;
-  std::vector<double> N_, dN_, d2N_, x_, Jt_, H_, detJ_, JinvT_;
+  // element-block window
+  int64_t blockElems_ = 0, numBlocks_ = 0;
+  size_t slotDoubles_ = 0, fieldOff_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  mutable std::vector<Slot> slots_;
+  mutable Slot* last_ = nullptr;
+  mutable uint64_t clock_ = 0;
+  mutable int64_t blockEvaluations_ = 0;
 };
 
 // ---- NurbsLocalBasis -------------------------------------------------------------------------------------------------
@@ -475,11 +614,21 @@ public:
 
   int corners() const { return 1 << dim; }
   GlobalCoordinate corner(int k) const {
+    GlobalCoordinate r;
+    if (const double* c = p_->cornerOrCenter(e_, k)) {
+      for (int i = 0; i < dimworld; ++i) r[i] = c[i];
+      return r;
+    }
     std::array<double, dim> l;
     for (int i = 0; i < dim; ++i) l[i] = (k & (1 << i)) ? 1 : 0;
     return global(l);
   }
   GlobalCoordinate center() const {
+    GlobalCoordinate r;
+    if (const double* c = p_->cornerOrCenter(e_, 1 << dim)) {
+      for (int i = 0; i < dimworld; ++i) r[i] = c[i];
+      return r;
+    }
     std::array<double, dim> l;
     l.fill(0.5);
     return global(l);

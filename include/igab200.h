@@ -145,6 +145,15 @@ igab_status igab_eval_tensor(igab_patch* p, int64_t elem_begin, int64_t elem_end
                              const double* const* xi1d, const igab_eval_out* out, igab_memspace out_space,
                              void* stream);
 
+/* The same with HOST outputs, without waiting: returns once the kernels and the device-to-host copies are queued, so the
+ * caller's loop over the elements it already holds (the per-element calls of the reference, nurbsbasis.hh:77-108,
+ * nurbsgeometry.hh:133-203) overlaps the evaluation and the transfer of the NEXT block of elements.  The output
+ * arrays (pinned memory from igab_host_alloc for a truly asynchronous copy) may be read after igab_patch_wait; any
+ * other call on the handle waits for a pending begin first.                                                         */
+igab_status igab_eval_tensor_begin(igab_patch* p, int64_t elem_begin, int64_t elem_end, int deriv_order, const int* nq1,
+                                   const double* const* xi1d, const igab_eval_out* out, void* stream);
+igab_status igab_patch_wait(igab_patch* p);
+
 /* Same at arbitrary element-local points (trimmed-element rules, utils/fillquadraturerule.hh:8-19; probes):
  * elem[npts] element direct index, xi[npts][dim]; inputs and outputs all in `space`.                             */
 igab_status igab_eval_points(igab_patch* p, int64_t npts, const int32_t* elem, const double* xi, int deriv_order,

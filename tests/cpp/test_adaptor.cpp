@@ -286,6 +286,109 @@ int main() {
     CHECK(std::fabs(x0[2] - 0.75) < 1e-15 && J0[0][1] == Jt[0][1] && H0[0][0] == H[0][0], "zeroFirstAndSecondDerivativeOfPosition");
   }
 
+  // ---- a patch whose results do not fit the window: the element loop of gridtests.cpp:338-341 over 48^3 (p = 1) and
+  //      32^3 (p = 2, checked against the oracle on a sample) elements with a small window of element blocks in pinned
+  //      host memory.  Host memory stays at the window size, every block is evaluated exactly once when the elements are
+  //      walked in index order, the next block is in flight while the current one is consumed.
+  {
+    const char* big = std::getenv("IGAB_TEST_FULL");  // IGAB_TEST_FULL=1: the same walk over 128^3 elements (minutes)
+    for (int pdeg = 1; pdeg <= 2; ++pdeg) {
+      const int n = big ? 128 : (pdeg == 1 ? 48 : 32);
+      igab::PatchData<3, 3> bd;
+      bd.degree = {pdeg, pdeg, pdeg};
+      for (int d = 0; d < 3; ++d) {
+        for (int k = 0; k <= pdeg; ++k) bd.knotSpans[d].push_back(0.0);
+        for (int k = 1; k < n; ++k) bd.knotSpans[d].push_back((double)k / n);
+        for (int k = 0; k <= pdeg; ++k) bd.knotSpans[d].push_back(1.0);
+      }
+      const int ncp = n + pdeg;
+      // a smoothly distorted brick [0,2] x [0,1] x [0,3] with non-uniform weights (Greville abscissae as parameters)
+      auto grev = [&](int i) {
+        double sum = 0;
+        for (int k = 1; k <= pdeg; ++k) sum += bd.knotSpans[0][(size_t)(i + k)];
+        return sum / pdeg;
+      };
+      for (int k = 0; k < ncp; ++k)
+        for (int j = 0; j < ncp; ++j)
+          for (int i = 0; i < ncp; ++i) {
+            const double u = grev(i), v = grev(j), t = grev(k);
+            bd.controlPoints.push_back(2.0 * u + 0.05 * std::sin(3.0 * v));
+            bd.controlPoints.push_back(v + 0.04 * u * t);
+            bd.controlPoints.push_back(3.0 * t + 0.03 * std::cos(2.0 * u));
+            bd.controlPoints.push_back(1.0 + 0.2 * u * v);
+          }
+      auto bp = std::make_shared<igab::Patch<3, 3>>(bd);
+      std::array<std::vector<double>, 3> bx, bw;
+      igab::getQuadratureRule<3>(bd.degree, bx, bw, 2 * pdeg);  // p + 1 points per direction
+      const size_t window = size_t(48) << 20;
+      bp->setQuadratureRule(bx, bw, 1, window, 3);
+      const int64_t nq = bp->pointsPerElement();
+      CHECK(bp->windowBytes() <= window, "window %zu bytes", bp->windowBytes());
+      const double full = (double)bp->size0() * nq * (bp->localSize() * 4 + 3 + 9 + 1 + 9) * 8.0;
+      CHECK(full > 4.0 * window, "the test patch must not fit the window (%g bytes)", full);
+      double vol = 0, pu = 0, worst = 0;
+      igab::LocalView<3, 3> lv(bp);
+      for (int64_t e = 0; e < bp->size0(); ++e) {
+        lv.bind(e);
+        const auto geo = lv.geometry();
+        vol += geo.volume();
+        if (e % 97 == 0) {  // partition of unity and sum of gradients at a rule point of a sample of elements
+          std::array<double, 3> q;
+          bp->position(nq / 2, q);
+          std::vector<double> ph;
+          std::vector<std::array<std::array<double, 3>, 1>> gr;
+          lv.localBasis().evaluateFunction(q, ph);
+          lv.localBasis().evaluateJacobian(q, gr);
+          double s0 = 0, s1 = 0;
+          for (size_t i = 0; i < ph.size(); ++i) { s0 += ph[i]; s1 += gr[i][0][0] + gr[i][0][1] + gr[i][0][2]; }
+          pu = std::fmax(pu, std::fabs(s0 - 1.0));
+          worst = std::fmax(worst, std::fabs(s1));
+        }
+      }
+      const int64_t blocks = (bp->size0() + bp->blockElements() - 1) / bp->blockElements();
+      CHECK(bp->blockEvaluations() == blocks, "blocks evaluated %ld of %ld", (long)bp->blockEvaluations(), (long)blocks);
+      CHECK(pu < 1e-13 && worst < 1e-10, "partition of unity %g, gradient sum %g", pu, worst);
+      const double dev = bp->volume();  // the device reduction over the same rule
+      CHECK(std::fabs(vol - dev) <= 1e-12 * dev, "windowed element loop volume %.15g, device reduction %.15g", vol, dev);
+      // random access far apart evicts and re-evaluates, values stay those of the oracle
+      igo_patch bo{};
+      bo.dim = 3; bo.dimworld = 3;
+      for (int d = 0; d < 3; ++d) {
+        bo.degree[d] = pdeg;
+        bo.nknots[d] = (int)bd.knotSpans[d].size();
+        bo.knots[d] = bd.knotSpans[d].data();
+        bo.ncp[d] = ncp;
+      }
+      bo.cp = bd.controlPoints.data();
+      const int bnq1[3] = {pdeg + 1, pdeg + 1, pdeg + 1};
+      std::vector<double> bxc;
+      for (int d = 0; d < 3; ++d) bxc.insert(bxc.end(), bx[d].begin(), bx[d].end());
+      const int nb3 = bp->localSize();
+      std::vector<double> rN((size_t)nq * nb3), rdN((size_t)nq * nb3 * 3), rx((size_t)nq * 3), rJ((size_t)nq * 9), rd((size_t)nq),
+          rJi((size_t)nq * 9);
+      const int64_t probe[5] = {bp->size0() - 1, 0, bp->size0() / 2, 3, bp->size0() - 2};
+      for (int64_t e : probe) {
+        igo_eval_tensor(&bo, (long)e, (long)e + 1, 1, bnq1, bxc.data(), rN.data(), rdN.data(), nullptr, rx.data(), rJ.data(),
+                        nullptr, rd.data(), rJi.data(), 1);
+        for (int64_t q = 0; q < nq; q += 3) {
+          for (int i = 0; i < nb3; ++i) CHECK(close(bp->N(e, q)[i], rN[(size_t)q * nb3 + i], 1.0), "window N e=%ld", (long)e);
+          for (int i = 0; i < nb3 * 3; ++i) CHECK(close(bp->dN(e, q)[i], rdN[(size_t)q * nb3 * 3 + i], 8.0), "window dN e=%ld", (long)e);
+          CHECK(close(bp->detJ(e, q), rd[(size_t)q], rd[(size_t)q]), "window detJ e=%ld", (long)e);
+        }
+        // corners and centre of the element: one batched call per block, equal to global() at those points
+        igab::Geometry<3, 3> g3(bp.get(), e);
+        const auto c5 = g3.corner(5), ce = g3.center();
+        const auto d5 = g3.global(std::array<double, 3>{1.0, 0.0, 1.0}), de = g3.global(std::array<double, 3>{0.5, 0.5, 0.5});
+        for (int c = 0; c < 3; ++c)
+          CHECK(close(c5[c], d5[c], 3.0) && close(ce[c], de[c], 3.0), "corner / centre e=%ld: %.17g %.17g | %.17g %.17g", (long)e,
+                c5[c], d5[c], ce[c], de[c]);
+      }
+      CHECK(bp->blockEvaluations() > blocks && bp->windowBytes() <= window, "eviction");
+      std::printf("windowed walk p=%d: %ld elements, %ld blocks of %ld, window %.1f MB of %.1f MB, volume %.12f\n", pdeg,
+                  (long)bp->size0(), (long)blocks, (long)bp->blockElements(), bp->windowBytes() / 1048576.0, full / 1048576.0, vol);
+    }
+  }
+
   std::printf(failures ? "adaptor test: %d FAILURES\n" : "adaptor test: ok\n", failures);
   return failures ? 1 : 0;
 }
