@@ -28,7 +28,8 @@ EXPORTS = ("igab_last_error_string", "igab_version", "igab_launch_count", "igab_
            "igab_csr_dirichlet", "igab_assemble_points", "igab_global_assemble", "igab_reduce_volume_trimmed", "igab_reduce_norms_trimmed",
            "igab_partition_slab", "igab_interface_row_ranges", "igab_comm_unique_id", "igab_comm_create",
            "igab_comm_destroy", "igab_comm_info", "igab_exchange_interface_rows", "igab_patch_real_index_maps",
-           "igab_load_vector", "igab_load_vector_points", "igab_global_load_vector", "igab_device_numa_node", "igab_eval_tensor_begin", "igab_patch_wait")
+           "igab_load_vector", "igab_load_vector_points", "igab_global_load_vector", "igab_device_numa_node", "igab_eval_tensor_begin", "igab_patch_wait", "igab_refine_knots",
+           "igab_patch_create_from_device")
 
 
 class EvalOut(C.Structure):
@@ -54,6 +55,10 @@ def lib():
         L.igab_host_free.argtypes = [C.c_void_p]
         L.igab_patch_create.argtypes = [C.c_int, C.c_int, ip, ip, C.POINTER(dp), dp, C.POINTER(C.c_ubyte),
                                         C.POINTER(C.c_void_p)]
+        L.igab_patch_create_from_device.argtypes = [C.c_int, C.c_int, ip, ip, C.POINTER(dp), C.c_void_p,
+                                                    C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]
+        L.igab_refine_knots.argtypes = [C.c_int, C.c_int, ip, ip, C.POINTER(dp), ip, C.POINTER(dp), C.c_void_p, C.c_int,
+                                        C.c_void_p, C.c_int, C.c_void_p]
         L.igab_patch_destroy.argtypes = [C.c_void_p]
         L.igab_patch_destroy.restype = None
         L.igab_patch_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
@@ -200,6 +205,32 @@ def refineApply(pd, direction, T, newKnots, newDegree=None):
     return NurbsPatchData(knots, cp_out, deg, pd.dimworld)
 
 
+def refineKnots(pd, newKnotVectors, cp_dev=None, device_out=False, stream=None):
+    """Knot refinement of all directions on the device (igab_refine_knots): pd = coarse NurbsPatchData, newKnotVectors =
+    the refined knot vector per direction (each containing the old one).  cp_dev: the coarse net as a CUDA tensor (else
+    pd.cp is copied in).  Returns the refined net [prod n_new][dimworld+1] as numpy array, or as CUDA tensor with
+    device_out=True (feed it to Patch.fromDeviceNet: the refined net never leaves HBM)."""
+    dim = pd.patchDim
+    deg = _i32(pd.degree)
+    ko = [_f64(k) for k in pd.knotSpans]
+    kn = [_f64(k) for k in newKnotVectors]
+    kop = (dp * dim)(*[k.ctypes.data_as(dp) for k in ko])
+    knp = (dp * dim)(*[k.ctypes.data_as(dp) for k in kn])
+    nko, nkn = _i32([len(k) for k in ko]), _i32([len(k) for k in kn])
+    nout = int(np.prod([len(kn[d]) - pd.degree[d] - 1 for d in range(dim)]))
+    src = cp_dev if cp_dev is not None else _f64(pd.cp)
+    sa, ss = _ptr(src)
+    if device_out:
+        import torch
+        out = torch.empty((nout, pd.dimworld + 1), dtype=torch.float64, device="cuda")
+    else:
+        out = np.empty((nout, pd.dimworld + 1))
+    oa, os_ = _ptr(out)
+    _check(lib().igab_refine_knots(dim, pd.dimworld, deg.ctypes.data_as(ip), nko.ctypes.data_as(ip), kop,
+                                   nkn.ctypes.data_as(ip), knp, sa, ss, oa, os_, stream))
+    return out
+
+
 def pinned_empty(shape, dtype=np.float64):
     """numpy array over page-locked memory from igab_host_alloc; release it with pinned_free(arr) (views of the array
     must not outlive that call -- nothing is freed behind the caller's back)."""
@@ -226,23 +257,34 @@ class Patch:
     (dune/iga/nurbspatch.hh:53-69, nurbsgeometry.hh:58-85, nurbsbasis.hh:503-518)."""
 
     def __init__(self, degree, knotSpans, cp, dimworld, trimflags=None):
+        self._init(degree, knotSpans, cp, dimworld, trimflags)
+
+    def _init(self, degree, knotSpans, cp, dimworld, trimflags=None):
         self.dim = len(degree)
         self.dimworld = int(dimworld)
         self.degree = [int(p) for p in degree]
         kn = [_f64(k) for k in knotSpans]
-        cp = _f64(cp).reshape(-1, self.dimworld + 1)
+        on_device = hasattr(cp, "data_ptr")
+        if not on_device:
+            cp = _f64(cp).reshape(-1, self.dimworld + 1)
         ncp = [len(kn[d]) - self.degree[d] - 1 for d in range(self.dim)]
-        if cp.shape[0] != int(np.prod(ncp)):
+        if int(cp.shape[0]) != int(np.prod(ncp)):
             raise ValueError("control net has %d points, knots/degree imply %s" % (cp.shape[0], ncp))
         kptr = (dp * self.dim)(*[k.ctypes.data_as(dp) for k in kn])
         tf = None
         if trimflags is not None:
             tf = np.ascontiguousarray(trimflags, dtype=np.uint8)
         h = C.c_void_p()
-        _check(lib().igab_patch_create(self.dim, self.dimworld, _i32(self.degree).ctypes.data_as(ip),
-                                       _i32([len(k) for k in kn]).ctypes.data_as(ip), kptr, cp.ctypes.data_as(dp),
-                                       tf.ctypes.data_as(C.POINTER(C.c_ubyte)) if tf is not None else None,
-                                       C.byref(h)))
+        tfp = tf.ctypes.data_as(C.POINTER(C.c_ubyte)) if tf is not None else None
+        if on_device:
+            assert cp.is_cuda and cp.is_contiguous()
+            _check(lib().igab_patch_create_from_device(self.dim, self.dimworld, _i32(self.degree).ctypes.data_as(ip),
+                                                       _i32([len(k) for k in kn]).ctypes.data_as(ip), kptr,
+                                                       cp.data_ptr(), tfp, C.byref(h)))
+        else:
+            _check(lib().igab_patch_create(self.dim, self.dimworld, _i32(self.degree).ctypes.data_as(ip),
+                                           _i32([len(k) for k in kn]).ctypes.data_as(ip), kptr, cp.ctypes.data_as(dp),
+                                           tfp, C.byref(h)))
         self.h = h
         ne, nb, nd = C.c_int64(), C.c_int32(), C.c_int64()
         ned = (C.c_int32 * 3)()
@@ -254,6 +296,14 @@ class Patch:
     @classmethod
     def fromPatchData(cls, pd, trimflags=None):
         return cls(pd.degree, pd.knotSpans, pd.cp, pd.dimworld, trimflags)
+
+    @classmethod
+    def fromDeviceNet(cls, degree, knotSpans, cp_dev, dimworld, trimflags=None):
+        """Handle from a control net that already lives on the device (CUDA tensor [n][dimworld+1]), e.g. the output of
+        refineKnots(..., device_out=True): igab_patch_create_from_device."""
+        self = cls.__new__(cls)
+        self._init(degree, knotSpans, cp_dev, dimworld, trimflags)
+        return self
 
     def close(self):
         if getattr(self, "h", None):

@@ -513,8 +513,21 @@ igab_status igab_host_free(void* ptr) {
   return IGAB_OK;
 }
 
+static igab_status patch_create_impl(int dim, int dimworld, const int* degree, const int* nknots,
+                                     const double* const* knots, const double* cp, igab_memspace cp_space,
+                                     const uint8_t* trimflags, igab_patch** out);
 igab_status igab_patch_create(int dim, int dimworld, const int* degree, const int* nknots, const double* const* knots,
                               const double* cp, const uint8_t* trimflags, igab_patch** out) {
+  return patch_create_impl(dim, dimworld, degree, nknots, knots, cp, IGAB_HOST, trimflags, out);
+}
+igab_status igab_patch_create_from_device(int dim, int dimworld, const int* degree, const int* nknots,
+                                          const double* const* knots, const double* cp_dev, const uint8_t* trimflags,
+                                          igab_patch** out) {
+  return patch_create_impl(dim, dimworld, degree, nknots, knots, cp_dev, IGAB_DEVICE, trimflags, out);
+}
+static igab_status patch_create_impl(int dim, int dimworld, const int* degree, const int* nknots,
+                                     const double* const* knots, const double* cp, igab_memspace cp_space,
+                                     const uint8_t* trimflags, igab_patch** out) {
   if (!out) return IGAB_INVALID_ARGUMENT;
   *out = nullptr;
   if (dim < 1 || dim > kMaxDim || dimworld < dim || dimworld > 3 || !degree || !nknots || !knots || !cp) {
@@ -614,7 +627,9 @@ igab_status igab_patch_create(int dim, int dimworld, const int* degree, const in
   }
   const size_t cpBytes = sizeof(double) * p->ncp_total * (dimworld + 1);
   if ((e = cudaMalloc(&p->d_cp, cpBytes)) != cudaSuccess) return fail(e, "cudaMalloc control net");
-  if ((e = cudaMemcpy(p->d_cp, cp, cpBytes, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e, "copy control net");
+  if ((e = cudaMemcpy(p->d_cp, cp, cpBytes, cp_space == IGAB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice)) !=
+      cudaSuccess)
+    return fail(e, "copy control net");
   D.cp = p->d_cp;
   if (trimflags) {
     if ((e = cudaMalloc(&p->d_trim, D.nelem)) != cudaSuccess) return fail(e, "cudaMalloc trim flags");
@@ -1160,6 +1175,65 @@ igab_status igab_refine_apply(int dim, int dimworld, const int* ncp_old, int dir
   if (d_coef) cudaFree(d_coef);
   if (d_in) cudaFree(d_in);
   if (d_out) cudaFree(d_out);
+  return st;
+}
+
+igab_status igab_refine_knots(int dim, int dimworld, const int* degree, const int* nknots_old,
+                              const double* const* knots_old, const int* nknots_new, const double* const* knots_new,
+                              const double* cp_in, igab_memspace in_space, double* cp_out, igab_memspace out_space,
+                              void* stream_) {
+  if (dim < 1 || dim > kMaxDim || dimworld < 1 || dimworld > 3 || !degree || !nknots_old || !knots_old || !nknots_new ||
+      !knots_new || !cp_in || !cp_out) {
+    set_error("refine_knots: invalid argument");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  long long nin = 1, nout = 1;
+  for (int d = 0; d < dim; ++d) {
+    const int p = degree[d];
+    if (p < 1 || p > kMaxDegree || nknots_old[d] < 2 * (p + 1) || nknots_new[d] < nknots_old[d] || !knots_old[d] || !knots_new[d]) {
+      set_error("refine_knots: degree 1..8, open knot vectors, and the new knot vector must contain the old one");
+      return IGAB_INVALID_ARGUMENT;
+    }
+    // the new knot vector must be a refinement: every old knot appears (with at least its multiplicity), sorted
+    int j = 0;
+    for (int i = 0; i < nknots_new[d]; ++i) {
+      if (i > 0 && knots_new[d][i] < knots_new[d][i - 1]) {
+        set_error("refine_knots: You passed a non-sorted vector of new knots.");  // the reference's assert, :444-445
+        return IGAB_INVALID_ARGUMENT;
+      }
+      if (j < nknots_old[d] && knots_new[d][i] == knots_old[d][j]) ++j;
+    }
+    if (j != nknots_old[d]) {
+      set_error("refine_knots: the new knot vector does not contain the old one");
+      return IGAB_INVALID_ARGUMENT;
+    }
+    nin *= nknots_old[d] - p - 1;
+    nout *= nknots_new[d] - p - 1;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const size_t row = sizeof(double) * (dimworld + 1);
+  double *dIn = nullptr, *dOut = nullptr, *dScr = nullptr;
+  cudaError_t e = cudaSuccess;
+  if (in_space == IGAB_HOST) {
+    e = cudaMallocAsync(&dIn, row * nin, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dIn, cp_in, row * nin, cudaMemcpyHostToDevice, stream);
+  }
+  if (e == cudaSuccess && out_space == IGAB_HOST) e = cudaMallocAsync(&dOut, row * nout, stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&dScr, row * nout, stream);
+  igab_status st = e == cudaSuccess ? IGAB_OK : cuda_fail(e, "refine_knots: buffers");
+  if (!st)
+    st = refine_knots_device(dim, dimworld, degree, nknots_old, knots_old, nknots_new, knots_new, dIn ? dIn : cp_in,
+                             dOut ? dOut : cp_out, dScr, stream);
+  if (!st && out_space == IGAB_HOST) {
+    e = cudaMemcpyAsync(cp_out, dOut, row * nout, cudaMemcpyDeviceToHost, stream);
+    if (e != cudaSuccess) st = cuda_fail(e, "refine_knots: D2H");
+  }
+  // the knot vectors are pageable host arrays read by the asynchronous copies above
+  e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess && !st) st = cuda_fail(e, "refine_knots: sync");
+  if (dIn) cudaFreeAsync(dIn, stream);
+  if (dOut) cudaFreeAsync(dOut, stream);
+  if (dScr) cudaFreeAsync(dScr, stream);
   return st;
 }
 

@@ -154,6 +154,11 @@ igab_status launch_volume(const PatchDev& P, SfWorkspace& ws, const double* cons
 
 igab_status refine_apply(int dim, int dw, const int* ncp_old, int direction, int n_new, int maxlen, const int* first,
                          const int* len, const double* coef, const double* cp_in, double* cp_out, cudaStream_t stream);
+// knot refinement of all directions in HBM: Oslo operators built on the device, banded apply per direction; knots are HOST
+// arrays, the nets device arrays (cp_out_dev and scratch_dev hold the refined net's size)
+igab_status refine_knots_device(int dim, int dw, const int* degree, const int* nknots_old,
+                                const double* const* knots_old, const int* nknots_new, const double* const* knots_new,
+                                const double* cp_in_dev, double* cp_out_dev, double* scratch_dev, cudaStream_t stream);
 igab_status eval_faces_device(igab_patch* p, long long nfaces, const int* elem, const int* face, const int* nqf1,
                               const double* const* xi_dev, double* x, double* normal, double* dS, cudaStream_t stream);
 igab_status launch_norms(const PatchDev& P, long long elem_begin, long long nelem, const int* nq1,

@@ -208,6 +208,21 @@ igab_status igab_refine_apply(int dim, int dimworld, const int* ncp_old, int dir
                               const int32_t* first, const int32_t* len, const double* coef, const double* cp_in,
                               double* cp_out);
 
+/* Knot refinement of ALL directions without leaving HBM (the chain NURBSGrid::globalRefine -> knotRefinement per direction,
+ * dune/iga/nurbsgrid.hh:130-165 -> dune/iga/nurbsalgorithms.hh:441-528): for every direction whose knot vector grows, the
+ * knot-insertion operator is built on the device (Oslo recursion, one thread per new control-point row) and applied to
+ * the net in homogeneous coordinates; intermediate nets stay on the device.  knots_* are HOST arrays (knots_new[d] must
+ * contain knots_old[d]); cp_in [prod n_old][dimworld+1] in `in_space`, cp_out [prod n_new][dimworld+1] in `out_space` --
+ * with IGAB_DEVICE on both sides and igab_patch_create_from_device the refined net never crosses PCIe.               */
+igab_status igab_refine_knots(int dim, int dimworld, const int* degree, const int* nknots_old,
+                              const double* const* knots_old, const int* nknots_new, const double* const* knots_new,
+                              const double* cp_in, igab_memspace in_space, double* cp_out, igab_memspace out_space,
+                              void* stream);
+/* igab_patch_create with the control net already on the current device (copied device to device) */
+igab_status igab_patch_create_from_device(int dim, int dimworld, const int* degree, const int* nknots,
+                                          const double* const* knots, const double* cp_dev, const uint8_t* trimflags,
+                                          igab_patch** out);
+
 /* ---- element faces (boundary / intersection integrals) -----------------------------------------------------------------
  * Replaces, for nfaces faces x the tensor rule of dimension dim-1: NURBSintersection::geometry().global /
  * integrationElement and outerNormal / unitOuterNormal / integrationOuterNormal (dune/iga/nurbsintersection.hh:86-160;

@@ -231,3 +231,62 @@ def test_warp_specialised_assembly_kernel_matches_oracle_and_the_barrier_separat
         Kr, fr = O.assemble(kind, [x] * 3, [w] * 3, D=D, fconst=0.7, elem_begin=int(e), elem_end=int(e) + 1)
         assert relerr(out["1"][0][e].reshape(1, -1), Kr.reshape(1, -1)) <= TOL
         assert relerr(out["1"][1][e].reshape(1, -1), fr.reshape(1, -1)) <= TOL
+
+
+def test_device_resident_refinement_chain_matches_host_and_reference():
+    """igab_refine_knots: operators built on the device (Oslo), all directions applied in HBM, the handle created from the
+    device net (igab_patch_create_from_device) -- against the host operators (patchdata.knotRefinement) and the
+    reference's own knotRefinement (nurbsalgorithms.hh:441-528 through oracle/_ref) on 2-D / 3-D patches with repeated
+    interior knots, non-uniform weights and uneven refinement per direction; then the whole chain at 128^3 elements."""
+    import torch
+    import refbind as RF
+    cases = [PFT.small_patch("torus_p2", level=0)["patch"], PFT.small_patch("mixed_deg_3d", level=0)["patch"],
+             PD.perturbed(PD.thickCylinder(3, (1, 0, 2)), seed=2), PFT.small_patch("curve_p3", level=0)["patch"]]
+    for pd in cases:
+        levels = [2, 1, 3][:pd.patchDim]
+        fine = pd
+        for d, lev in enumerate(levels):
+            fine = fine.globalRefineInDirection(d, lev)
+        got = capi.refineKnots(pd, fine.knotSpans)
+        assert got.shape == fine.cp.shape
+        scale = np.abs(fine.cp).max()
+        assert np.abs(got - fine.cp).max() <= 1e-13 * scale
+        if RF.available():
+            R = RF.RefPatch.create(pd.degree, pd.knotSpans, pd.cp, pd.dimworld)
+            for d, lev in enumerate(levels):
+                R = R.refine_uniform(d, lev)
+            assert np.abs(got - np.asarray(R.cp).reshape(got.shape)).max() <= 1e-13 * scale
+        # device in / device out, then a handle straight from the device net: evaluation equals the host-built handle
+        gdev = capi.refineKnots(pd, fine.knotSpans, cp_dev=torch.from_numpy(np.ascontiguousarray(pd.cp)).cuda(), device_out=True)
+        assert np.array_equal(gdev.cpu().numpy(), got)
+        Pd_ = capi.Patch.fromDeviceNet(fine.degree, fine.knotSpans, gdev, fine.dimworld)
+        Ph = capi.Patch(fine.degree, fine.knotSpans, got, fine.dimworld)
+        xi = [PD.gaussLegendre01(p + 1)[0] for p in fine.degree]
+        a, b = Pd_.evalTensor(xi, order=1), Ph.evalTensor(xi, order=1)
+        assert all(np.array_equal(a[f], b[f]) for f in a)
+    # errors: not a refinement / unsorted
+    pd = cases[0]
+    bad = [k.copy() for k in pd.knotSpans]
+    bad[0] = np.concatenate([bad[0][:3], [0.3, 0.2], bad[0][3:]])
+    with pytest.raises(capi.IgabError):
+        capi.refineKnots(pd, bad)
+    # the C2 chain: coarse solid (elevated to p=3) -> 128^3 elements, entirely on the device; the map is unchanged
+    coarse = PD.thickCylinder(3, (0, 0, 0))
+    knots = []
+    for d in range(3):
+        knots.append(np.sort(np.concatenate([coarse.knotSpans[d], PD.generateRefinedKnots(coarse.knotSpans, d, 7)])))
+    net = capi.refineKnots(coarse, knots, device_out=True)
+    assert net.shape == (131 ** 3, 4)
+    P = capi.Patch.fromDeviceNet(coarse.degree, knots, net, 3)
+    assert P.nelem == 128 ** 3
+    x, w = PD.gaussLegendre01(4)
+    vol = P.volume([x] * 3, [w] * 3)
+    assert abs(vol - np.pi / 4 * 3.0 * 3.0) <= 1e-12 * vol
+    if RF.available():  # the reference's own chain to 32^3 on the CPU, the device chain to the same level: same net
+        R = RF.RefPatch.create(coarse.degree, coarse.knotSpans, coarse.cp, 3)
+        k5 = []
+        for d in range(3):
+            R = R.refine_uniform(d, 5)
+            k5.append(np.sort(np.concatenate([coarse.knotSpans[d], PD.generateRefinedKnots(coarse.knotSpans, d, 5)])))
+        n5 = capi.refineKnots(coarse, k5)
+        assert np.abs(n5 - np.asarray(R.cp).reshape(n5.shape)).max() <= 1e-13 * np.abs(n5).max()
