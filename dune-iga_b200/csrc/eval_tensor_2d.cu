@@ -121,8 +121,10 @@ __global__ void __launch_bounds__(128, (ORDER >= 2 ? 3 : (P <= 2 ? 5 : (P >= 4 ?
   extern __shared__ double smem2[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* slab = smem2 + (size_t)warp * C::SLAB;
-  const long long pt0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * 32;  // first point of this warp
-  if (pt0 >= npts) return;
+  // persistent warps: the grid is a fixed number of resident blocks per SM (no partial last wave: at config C1 the
+  // one-block-per-128-points grid ran 6.2 waves), every warp walks chunks of 32 points with the grid's stride
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5) * 32;
+  for (long long pt0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * 32; pt0 < npts; pt0 += wstride) {
   const long long pt = pt0 + lane;
   const bool valid = pt < npts;
   const int nvalid = (int)min(32LL, npts - pt0);
@@ -291,6 +293,7 @@ __global__ void __launch_bounds__(128, (ORDER >= 2 ? 3 : (P <= 2 ? 5 : (P >= 4 ?
       flush_field<NH * DW, C::STRIDE>(slab, row, out.H + pt0 * NH * DW, lane, nvalid);
     }
   }
+  }  // chunk loop
 }
 
 template <int DW, int P, int Q, int ORDER>
@@ -304,7 +307,8 @@ igab_status launch_2d(const PatchDev& Pd, SfWorkspace& ws, const PointSource& sr
   const size_t smem = (size_t)WARPS * C::SLAB * sizeof(double);
   KernelCfg kc;
   if (igab_status cst = kernel_config((const void*)eval_2d_kernel<DW, P, Q, ORDER, false>, WARPS * 32, smem, &kc)) return cst;
-  const long long blocks = (npts + WARPS * 32 - 1) / (WARPS * 32);
+  long long blocks = (npts + WARPS * 32 - 1) / (WARPS * 32);
+  if (!getenv("IGAB_2D_NONPERSISTENT")) blocks = std::min(blocks, (long long)kc.sms * kc.blocksPerSm);
   if (blocks > 0x7fffffffLL) {
     set_error("eval_tensor: too many points for one launch");
     return IGAB_INVALID_ARGUMENT;
@@ -339,7 +343,8 @@ igab_status launch_list(const PatchDev& Pd, const PointSource& src, long long np
   const size_t smem = (size_t)WARPS * C::SLAB * sizeof(double);
   KernelCfg kc;
   if (igab_status cst = kernel_config((const void*)eval_2d_kernel<DW, P, 0, ORDER, true>, WARPS * 32, smem, &kc)) return cst;
-  const long long blocks = (npts + WARPS * 32 - 1) / (WARPS * 32);
+  long long blocks = (npts + WARPS * 32 - 1) / (WARPS * 32);
+  if (!getenv("IGAB_2D_NONPERSISTENT")) blocks = std::min(blocks, (long long)kc.sms * kc.blocksPerSm);
   if (blocks > 0x7fffffffLL) {
     set_error("eval_points: too many points for one launch");
     return IGAB_INVALID_ARGUMENT;

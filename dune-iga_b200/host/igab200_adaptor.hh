@@ -39,8 +39,10 @@
 #include <algorithm>
 #include <array>
 #include <cstdint>
+#include <map>
 #include <memory>
 #include <cmath>
+#include <utility>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -99,6 +101,25 @@ public:
   int64_t numDofs() const { return nDofs_; }
   const PatchData<dim, dimworld>& patchData() const { return data_; }
   const int32_t* dofsOf(int64_t e) const { return dof_.data() + (size_t)e * nb_; }
+
+  // NURBSPatch::getDirectIndex<0> / getRealIndex<0> (nurbspatch.hh:599-631): real index = position among the non-empty
+  // elements.  getRealIndex throws for an empty element, as the reference does ("No corresponding realIndex").
+  int64_t getDirectIndex(int64_t realIndex) const {
+    ensureIndexMaps();
+    if (realIndex < 0 || realIndex >= (int64_t)directOfReal_.size()) throw Error(IGAB_INVALID_ARGUMENT, "no such real index");
+    return directOfReal_[(size_t)realIndex];
+  }
+  int64_t getRealIndex(int64_t directIndex) const {
+    ensureIndexMaps();
+    if (directIndex < 0 || directIndex >= nElements_) throw Error(IGAB_INVALID_ARGUMENT, "no such element");
+    const int32_t r = realOfDirect_[(size_t)directIndex];
+    if (r < 0) throw std::runtime_error("No corresponding realIndex");
+    return r;
+  }
+  int64_t numRealElements() const {
+    ensureIndexMaps();
+    return (int64_t)directOfReal_.size();
+  }
 
   // The rule every untrimmed element uses (nurbsgridentity.hh:120-133): abscissae / weights per direction on [0,1].
   // derivOrder 1: N, dN, x, Jt, detJ, JinvT are cached; 2 adds d2N, H.
@@ -262,6 +283,15 @@ public:
   }
 
 private:
+  void ensureIndexMaps() const {
+    if (!realOfDirect_.empty() || nElements_ == 0) return;
+    realOfDirect_.resize((size_t)nElements_);
+    directOfReal_.resize((size_t)nElements_);
+    int64_t n = 0;
+    check(igab_patch_real_index_maps(h_, directOfReal_.data(), realOfDirect_.data(), &n, IGAB_HOST, nullptr));
+    directOfReal_.resize((size_t)n);
+  }
+  mutable std::vector<int32_t> realOfDirect_, directOfReal_;
   struct Slot {
     double* mem = nullptr;        // pinned host memory, all fields of one block back to back
     int64_t block = -1;           // which block it holds (or is being filled with)
@@ -795,6 +825,69 @@ inline void fillQuadratureRule(const std::vector<double>& triangles, std::vector
   }
 }
 
+// Gauss-Lobatto branch of fillQuadratureRuleImpl (fillquadraturerule.hh:21-44): points with exactly equal coordinates are
+// merged (weights added in order of appearance) and the rule is returned sorted by (x, y).  In place.
+inline void mergeDuplicatePoints(std::vector<double>& xi, std::vector<double>& w) {
+  struct Less {
+    bool operator()(const std::array<double, 2>& a, const std::array<double, 2>& b) const {
+      if (a[0] < b[0]) return true;
+      if (a[0] > b[0]) return false;
+      return a[1] < b[1];
+    }
+  };
+  std::map<std::array<double, 2>, double, Less> uniq;
+  for (size_t k = 0; k < w.size(); ++k) {
+    auto [it, fresh] = uniq.try_emplace({xi[2 * k], xi[2 * k + 1]}, w[k]);
+    if (!fresh) it->second += w[k];
+  }
+  xi.clear();
+  w.clear();
+  for (const auto& [pos, weight] : uniq) {
+    xi.push_back(pos[0]);
+    xi.push_back(pos[1]);
+    w.push_back(weight);
+  }
+}
+
+// ---- multi-GPU: one process per GPU, element slabs, NCCL behind the C-ABI ------------------------------------------------
+// The reference is sequential; a DUNE program that runs one rank per GPU creates the communicator once (the 128-byte id
+// travels by MPI_Bcast or any other means the host program has) and hands it to the reductions / the assembler.
+class Communicator {
+public:
+  using Id = std::array<char, 128>;
+  static Id uniqueId() {
+    Id id{};
+    check(igab_comm_unique_id(id.data()));
+    return id;
+  }
+  Communicator(int rank, int world, const Id& id) { check(igab_comm_create(rank, world, id.data(), &comm_)); }
+  Communicator(const Communicator&) = delete;
+  Communicator& operator=(const Communicator&) = delete;
+  ~Communicator() { igab_comm_destroy(comm_); }
+  void* get() const { return comm_; }
+  int rank() const {
+    int r = 0;
+    check(igab_comm_info(comm_, &r, nullptr));
+    return r;
+  }
+  int size() const {
+    int w = 1;
+    check(igab_comm_info(comm_, nullptr, &w));
+    return w;
+  }
+
+private:
+  void* comm_ = nullptr;
+};
+
+// [elem_begin, elem_end) of `rank`: whole layers of the slowest direction (igab_partition_slab)
+template <int dim>
+std::pair<int64_t, int64_t> partitionSlab(const std::array<int32_t, dim>& elementsPerDirection, int world, int rank) {
+  int64_t b = 0, e = 0;
+  check(igab_partition_slab(dim, elementsPerDirection.data(), world, rank, &b, &e));
+  return {b, e};
+}
+
 // ---- globalAssembler (dune/python/test/poisson.py:84-127), vectorised: the whole loop over elements, quadrature points
 //      and local DOF pairs is one device pass; what comes back is the CSR matrix and the load vector -----------------------
 struct CsrMatrix {
@@ -842,6 +935,40 @@ public:
                                nl ? trimmed->elem.data() : nullptr, nl ? trimmed->offset.data() : nullptr,
                                nl ? trimmed->xi.data() : nullptr, nl ? trimmed->w.data() : nullptr, A_.values.data(),
                                b_.data(), IGAB_HOST, nullptr));
+  }
+  // the same for the elements [elemBegin, elemEnd) only: one rank's slab of the shared pattern (partitionSlab); rows
+  // that elements of several ranks touch hold partial sums until exchangeInterfaceRows has run
+  void assemble(const std::array<std::vector<double>, dim>& xi, const std::array<std::vector<double>, dim>& w,
+                int64_t elemBegin, int64_t elemEnd, const double* D = nullptr, double f = 1.0) {
+    std::array<int, dim> nq1;
+    std::array<const double*, dim> xp, wp;
+    for (int i = 0; i < dim; ++i) {
+      nq1[i] = (int)xi[i].size();
+      xp[i] = xi[i].data();
+      wp[i] = w[i].data();
+    }
+    b_.assign((size_t)A_.rows, 0.0);
+    check(igab_global_assemble(p_->handle(), kind_, D, f, elemBegin, elemEnd, nq1.data(), xp.data(), wp.data(), 0, nullptr,
+                               nullptr, nullptr, nullptr, A_.values.data(), b_.data(), IGAB_HOST, nullptr));
+  }
+  void exchangeInterfaceRows(const Communicator& comm) {
+    check(igab_exchange_interface_rows(p_->handle(), ncomp_, nullptr, A_.values.data(), b_.data(), IGAB_HOST, comm.get(),
+                                       nullptr));
+  }
+  // load vector from a source evaluated by the caller at the quadrature points (poisson.py:79 with f(posGlobal)):
+  // f [n_elements * nq][ncomp], points in the order of the rule; replaces rhs()
+  void assembleLoadVector(const std::array<std::vector<double>, dim>& xi, const std::array<std::vector<double>, dim>& w,
+                          const std::vector<double>& f) {
+    std::array<int, dim> nq1;
+    std::array<const double*, dim> xp, wp;
+    for (int i = 0; i < dim; ++i) {
+      nq1[i] = (int)xi[i].size();
+      xp[i] = xi[i].data();
+      wp[i] = w[i].data();
+    }
+    b_.assign((size_t)A_.rows, 0.0);
+    check(igab_global_load_vector(p_->handle(), ncomp_, 0, p_->size0(), nq1.data(), xp.data(), wp.data(), f.data(), 0,
+                                  nullptr, nullptr, nullptr, nullptr, nullptr, b_.data(), IGAB_HOST, nullptr));
   }
   // rows of the marked DOFs become identity rows, b = g there (poisson.py:91-93,117-119)
   void applyDirichlet(const std::vector<uint8_t>& mask, const std::vector<double>* g = nullptr) {

@@ -286,6 +286,53 @@ int main() {
     CHECK(std::fabs(x0[2] - 0.75) < 1e-15 && J0[0][1] == Jt[0][1] && H0[0][0] == H[0][0], "zeroFirstAndSecondDerivativeOfPosition");
   }
 
+  // ---- real <-> direct element indices on a trimmed patch: the pattern of trimmedgridtests.cpp:335-373 (element 0 empty,
+  //      1..3 trimmed: real(i) = i - 1, direct(i - 1) = i, getRealIndex(0) throws), the Gauss-Lobatto merge of trimmed
+  //      rules (fillquadraturerule.hh:21-44), a load vector from a per-point source, a single-rank communicator
+  {
+    igab::PatchData<2, 2> td;
+    td.degree = {1, 1};
+    td.knotSpans = {std::vector<double>{0, 0, .5, 1, 1}, std::vector<double>{0, 0, .5, 1, 1}};
+    for (int j = 0; j < 3; ++j)
+      for (int i = 0; i < 3; ++i) {
+        td.controlPoints.push_back(0.5 * i);
+        td.controlPoints.push_back(0.5 * j);
+        td.controlPoints.push_back(1.0);
+      }
+    const std::vector<uint8_t> flags = {IGAB_TRIM_EMPTY, IGAB_TRIM_TRIMMED, IGAB_TRIM_TRIMMED, IGAB_TRIM_TRIMMED};
+    igab::Patch<2, 2> tp(td, &flags);
+    for (int i = 1; i < 4; ++i) CHECK(tp.getRealIndex(i) == i - 1 && tp.getDirectIndex(i - 1) == i, "real / direct index %d", i);
+    bool threw = false;
+    try { tp.getRealIndex(0); } catch (const std::runtime_error&) { threw = true; }
+    CHECK(threw && tp.numRealElements() == 3, "empty element has no real index");
+    std::vector<double> mx = {0.5, 0.5, 0.0, 0.0, 0.5, 0.5, 0.25, 1.0, 0.0, 0.0}, mw = {1, 2, 3, 4, 5};
+    igab::mergeDuplicatePoints(mx, mw);
+    CHECK(mw.size() == 3 && mx[0] == 0.0 && mw[0] == 7.0 && mx[2] == 0.25 && mw[1] == 4.0 && mw[2] == 4.0, "Lobatto merge");
+    // per-point source f = 1 + x on the plate patch: sum of the load vector = integral of f
+    igab::GlobalAssembler<dim, dw> gf(patch, IGAB_ASM_POISSON);
+    std::vector<double> fsrc((size_t)patch->size0() * 9);
+    double integral = 0;
+    for (int64_t e = 0; e < patch->size0(); ++e)
+      for (int64_t q = 0; q < 9; ++q) {
+        fsrc[(size_t)e * 9 + q] = 1.0 + patch->x(e, q)[0];
+        integral += fsrc[(size_t)e * 9 + q] * patch->detJ(e, q) * patch->weight(q);
+      }
+    gf.assembleLoadVector(xi, w, fsrc);
+    double bs = 0;
+    for (double v : gf.rhs()) bs += v;
+    CHECK(std::fabs(bs - integral) <= 1e-13 * std::fabs(integral), "load vector with a per-point source: %g vs %g", bs, integral);
+    // a one-rank communicator: slab = everything, the exchange finds no peer and leaves the system alone
+    igab::Communicator comm(0, 1, igab::Communicator::uniqueId());
+    CHECK(comm.rank() == 0 && comm.size() == 1, "communicator");
+    const auto slab = igab::partitionSlab<dim>({2, 1}, 1, 0);
+    CHECK(slab.first == 0 && slab.second == 2, "slab");
+    igab::GlobalAssembler<dim, dw> gs(patch, IGAB_ASM_POISSON);
+    gs.assemble(xi, w, slab.first, slab.second);
+    const std::vector<double> before = gs.matrix().values;
+    gs.exchangeInterfaceRows(comm);
+    CHECK(before == gs.matrix().values, "exchange without peers");
+  }
+
   // ---- a patch whose results do not fit the window: the element loop of gridtests.cpp:338-341 over 48^3 (p = 1) and
   //      32^3 (p = 2, checked against the oracle on a sample) elements with a small window of element blocks in pinned
   //      host memory.  Host memory stays at the window size, every block is evaluated exactly once when the elements are
