@@ -650,6 +650,12 @@ struct SCfg {
   // warp walks single tiles round-robin
   static constexpr bool GEN2 = !(TPW == 1 || NT2 % TPW == 0);
   static_assert(TPW * NWARP >= MT2 * NT2, "stage-2 tile distribution");
+  // Stage-2 column order.  Column position c of the B operand / the accumulator tile stands for the index pair
+  // n = cperm(c) = (j1, i1): within a group of eight, positions 2 lc + h hold the pairs lc + 4 h, so that the four lanes of
+  // a quad store CONSECUTIVE pairs -> consecutive rows of T2 (the natural order 2 lc + h put them two rows apart: 2.8x
+  // the ideal number of shared-memory wavefronts for the T2 stores, 1.4x now).
+  __host__ __device__ static constexpr int cperm(int c) { return 8 * (c / 8) + ((c % 8) / 2) + 4 * ((c % 8) % 2); }
+  __host__ __device__ static constexpr int cpos(int n) { return 8 * (n / 8) + 2 * ((n % 8) % 4) + ((n % 8) / 4); }
   // combo index (group order) -> (beta, gamma)
   __host__ __device__ static constexpr int set0(int k) { return k == 0 ? 0 : k + 1; }  // {0, 2, 3}
   __host__ __device__ static constexpr int beta_of(int g, int c) { return MASS ? 0 : (g == 0 ? set0(c / 3) : (g == 2 ? set0(c) : 1)); }
@@ -699,7 +705,7 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
     for (int s = 0; s < S::TPW; ++s)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int n = 8 * (nt2 + s) + 2 * lc + h;
+        const int n = S::cperm(8 * (nt2 + s) + 2 * lc + h);
         t2off[s][h] = (has2 && m < S::M2 && n < NP) ? ((n % NB1) + NB1 * (m / Q) + NP * (n / NB1)) * LDA3 + (m % Q) : -1;
       }
   }
@@ -734,7 +740,7 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
         const int n = idx % NP, r = idx / NP, q1 = r % Q, c = r / Q;
         const int j1 = n % NB1, i1 = n / NB1;
         const int bb = S::beta_of(g, c) == 2, bg = S::gamma_of(g, c) == 2;
-        sB2[(S::goff(g) + c * Q + q1) * LDB2 + n] =
+        sB2[(S::goff(g) + c * Q + q1) * LDB2 + S::cpos(n)] =
             sT[TAB + (q1 * NB1 + i1) * 2 + bb] * sT[TAB + (q1 * NB1 + j1) * 2 + bg];
       }
     }
@@ -854,7 +860,7 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
           int off[2];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const int n = 8 * nt + 2 * lc + h;
+            const int n = S::cperm(8 * nt + 2 * lc + h);
             off[h] = (m < S::M2 && n < NP) ? ((n % NB1) + NB1 * (m / Q) + NP * (n / NB1)) * LDA3 + (m % Q) : -1;
           }
 #pragma unroll
@@ -1031,7 +1037,7 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
     for (int s = 0; s < S::TPW; ++s)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int n = 8 * (nt2 + s) + 2 * lc + h;
+        const int n = S::cperm(8 * (nt2 + s) + 2 * lc + h);
         t2off[s][h] = (has2 && m < S::M2 && n < NP) ? ((n % NB1) + NB1 * (m / Q) + NP * (n / NB1)) * LDA3 + (m % Q) : -1;
       }
   }
@@ -1066,7 +1072,7 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
         const int n = idx % NP, r = idx / NP, q1 = r % Q, c = r / Q;
         const int j1 = n % NB1, i1 = n / NB1;
         const int bb = S::beta_of(g, c) == 2, bg = S::gamma_of(g, c) == 2;
-        sB2[(S::goff(g) + c * Q + q1) * LDB2 + n] =
+        sB2[(S::goff(g) + c * Q + q1) * LDB2 + S::cpos(n)] =
             sT[TAB + (q1 * NB1 + i1) * 2 + bb] * sT[TAB + (q1 * NB1 + j1) * 2 + bg];
       }
     }
@@ -1127,7 +1133,7 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
             int off[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const int n = 8 * nt + 2 * lc + h;
+              const int n = S::cperm(8 * nt + 2 * lc + h);
               off[h] = (m < S::M2 && n < NP) ? ((n % NB1) + NB1 * (m / Q) + NP * (n / NB1)) * LDA3 + (m % Q) : -1;
             }
 #pragma unroll
