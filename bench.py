@@ -393,7 +393,7 @@ def bench_configs(peak_hbm, dmma_peak):
     out.append({"config": "C3 elasticity: 3-D linear-elasticity element stiffness p=4 (n=375), 5^3 Gauss, isotropic D",
                 "metric": "element matrices/sec", "value": nel / ms * 1e3, "unit": "elements/s", "elements": nel,
                 "ms_per_launch": ms, "launches_queued_per_sample": inner, "gpu_launches": int(capi.launch_count() - l0),
-                "roofline": {"bound": "tensor", "kernel": "gram_sf_kernel<4,5,ELASTICITY>",
+                "roofline": {"bound": "tensor", "kernel": "gram_ws_kernel<4,5,2> (warp-specialised: DMMA warps + helper warps, complete rows stored)",
                              "achieved": ex * nel / ms / 1e9, "peak": dmma_peak, "unit": "TFLOP/s",
                              "frac": ex * nel / ms / 1e9 / dmma_peak,
                              "traffic": tr * nel if tr else None, "algorithmic_bytes": 8.0 * n * n * nel,
