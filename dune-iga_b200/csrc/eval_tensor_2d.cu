@@ -308,7 +308,9 @@ igab_status launch_2d(const PatchDev& Pd, SfWorkspace& ws, const PointSource& sr
   KernelCfg kc;
   if (igab_status cst = kernel_config((const void*)eval_2d_kernel<DW, P, Q, ORDER, false>, WARPS * 32, smem, &kc)) return cst;
   long long blocks = (npts + WARPS * 32 - 1) / (WARPS * 32);
-  if (!getenv("IGAB_2D_NONPERSISTENT")) blocks = std::min(blocks, (long long)kc.sms * kc.blocksPerSm);
+  // persistent grid where the tail of the last wave matters (measured: +7 % at 6 waves, +5 % at 17, -2 % at 177)
+  if (!getenv("IGAB_2D_NONPERSISTENT") && blocks <= 64LL * kc.sms * kc.blocksPerSm)
+    blocks = std::min(blocks, (long long)kc.sms * kc.blocksPerSm);
   if (blocks > 0x7fffffffLL) {
     set_error("eval_tensor: too many points for one launch");
     return IGAB_INVALID_ARGUMENT;
@@ -344,7 +346,9 @@ igab_status launch_list(const PatchDev& Pd, const PointSource& src, long long np
   KernelCfg kc;
   if (igab_status cst = kernel_config((const void*)eval_2d_kernel<DW, P, 0, ORDER, true>, WARPS * 32, smem, &kc)) return cst;
   long long blocks = (npts + WARPS * 32 - 1) / (WARPS * 32);
-  if (!getenv("IGAB_2D_NONPERSISTENT")) blocks = std::min(blocks, (long long)kc.sms * kc.blocksPerSm);
+  // persistent grid where the tail of the last wave matters (measured: +7 % at 6 waves, +5 % at 17, -2 % at 177)
+  if (!getenv("IGAB_2D_NONPERSISTENT") && blocks <= 64LL * kc.sms * kc.blocksPerSm)
+    blocks = std::min(blocks, (long long)kc.sms * kc.blocksPerSm);
   if (blocks > 0x7fffffffLL) {
     set_error("eval_points: too many points for one launch");
     return IGAB_INVALID_ARGUMENT;
