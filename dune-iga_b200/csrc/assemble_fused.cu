@@ -944,20 +944,40 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
     }  // (a, i2, b): the next block rewrites sM, last read two barriers ago
     // ---- load vector f_e[i] = sum_q w detJ R_i fconst  (poisson.py:79)
     if (fe) {
-      for (int i = tid; i < NB; i += NT) {
-        const int i0 = i % NB1, i1 = (i / NB1) % NB1, i2 = i / (NB1 * NB1);
-        const double w = sW[i];
-        double s = 0.0;
-        for (int pt = 0; pt < NQ; ++pt) {
-          const int q0 = pt % Q, q1 = (pt / Q) % Q, q2 = pt / (Q * Q);
-          const double R = sT[(q0 * NB1 + i0) * 2] * sT[TAB + (q1 * NB1 + i1) * 2] *
-                           (w * sT[2 * TAB + (q2 * NB1 + i2) * 2]) * sC[CS * pt];
-          s += sC[CS * pt + 13] * R * fconst;
+      // sum-factorised: f_i = w_i sum_q0 N0[q0][i0] sum_q1 N1[q1][i1] sum_q2 N2[q2][i2] (w detJ / W)(q) fconst, one direction
+      // per step (the plain loop over all points per function cost a quarter of the kernel's time); scratch in the T1
+      // region, which stage 2 of the last pass was the last to read
+      double* const fA = sT1;                // [q0 + Q q1][i2]
+      double* const fB = sT1 + Q * Q * NB1;  // [q0][i1 + NB1 i2]
+      for (int idx = tid; idx < Q * Q * NB1; idx += NT) {
+        const int q01 = idx % (Q * Q), i2 = idx / (Q * Q);
+        double a = 0.0;
+#pragma unroll
+        for (int q2 = 0; q2 < Q; ++q2) {
+          const double* o = sC + CS * (q01 + Q * Q * q2);
+          a = fma(sT[2 * TAB + (q2 * NB1 + i2) * 2], o[13] * o[0], a);
         }
+        fA[idx] = a;
+      }
+      __syncthreads();
+      for (int idx = tid; idx < Q * NB1 * NB1; idx += NT) {
+        const int q0 = idx % Q, i12 = idx / Q, i1 = i12 % NB1, i2 = i12 / NB1;
+        double b = 0.0;
+#pragma unroll
+        for (int q1 = 0; q1 < Q; ++q1) b = fma(sT[TAB + (q1 * NB1 + i1) * 2], fA[q0 + Q * q1 + Q * Q * i2], b);
+        fB[idx] = b;
+      }
+      __syncthreads();
+      for (int i = tid; i < NB; i += NT) {
+        const int i0 = i % NB1, i12 = i / NB1;
+        double f = 0.0;
+#pragma unroll
+        for (int q0 = 0; q0 < Q; ++q0) f = fma(sT[(q0 * NB1 + i0) * 2], fB[q0 + Q * i12], f);
+        f *= sW[i] * fconst;
         if constexpr (ELAS)
-          fe[el * NROWK + 3 * i] = fe[el * NROWK + 3 * i + 1] = fe[el * NROWK + 3 * i + 2] = s;
+          fe[el * NROWK + 3 * i] = fe[el * NROWK + 3 * i + 1] = fe[el * NROWK + 3 * i + 2] = f;
         else
-          fe[el * NB + i] = s;
+          fe[el * NB + i] = f;
       }
     }
   }
@@ -1308,22 +1328,40 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
         }
       }
       IGAB_WPT(12)
-      // ---- load vector f_e[i] = sum_q w detJ R_i fconst  (poisson.py:79)
+      // ---- load vector f_e[i] = sum_q w detJ R_i fconst  (poisson.py:79), sum-factorised as in gram_sf_kernel; the
+      //      DMMA warps are done with T1 (every T1_FULL they waited for has been consumed)
       if (fe) {
-        for (int i = htid; i < NB; i += NTH) {
-          const int i0 = i % NB1, i1 = (i / NB1) % NB1, i2 = i / (NB1 * NB1);
-          const double w = sW[i];
-          double s = 0.0;
-          for (int pt = 0; pt < NQ; ++pt) {
-            const int q0 = pt % Q, q1 = (pt / Q) % Q, q2 = pt / (Q * Q);
-            const double R = sT[(q0 * NB1 + i0) * 2] * sT[TAB + (q1 * NB1 + i1) * 2] *
-                             (w * sT[2 * TAB + (q2 * NB1 + i2) * 2]) * sC[CS * pt];
-            s += sC[CS * pt + 13] * R * fconst;
+        double* const fA = sT1;
+        double* const fB = sT1 + Q * Q * NB1;
+        for (int idx = htid; idx < Q * Q * NB1; idx += NTH) {
+          const int q01 = idx % (Q * Q), i2 = idx / (Q * Q);
+          double a = 0.0;
+#pragma unroll
+          for (int q2 = 0; q2 < Q; ++q2) {
+            const double* o = sC + CS * (q01 + Q * Q * q2);
+            a = fma(sT[2 * TAB + (q2 * NB1 + i2) * 2], o[13] * o[0], a);
           }
+          fA[idx] = a;
+        }
+        nb_sync(BAR_HLP, NTH);
+        for (int idx = htid; idx < Q * NB1 * NB1; idx += NTH) {
+          const int q0 = idx % Q, i12 = idx / Q, i1 = i12 % NB1, i2 = i12 / NB1;
+          double b = 0.0;
+#pragma unroll
+          for (int q1 = 0; q1 < Q; ++q1) b = fma(sT[TAB + (q1 * NB1 + i1) * 2], fA[q0 + Q * q1 + Q * Q * i2], b);
+          fB[idx] = b;
+        }
+        nb_sync(BAR_HLP, NTH);
+        for (int i = htid; i < NB; i += NTH) {
+          const int i0 = i % NB1, i12 = i / NB1;
+          double f = 0.0;
+#pragma unroll
+          for (int q0 = 0; q0 < Q; ++q0) f = fma(sT[(q0 * NB1 + i0) * 2], fB[q0 + Q * i12], f);
+          f *= sW[i] * fconst;
           if constexpr (ELAS)
-            fe[el * NROWK + 3 * i] = fe[el * NROWK + 3 * i + 1] = fe[el * NROWK + 3 * i + 2] = s;
+            fe[el * NROWK + 3 * i] = fe[el * NROWK + 3 * i + 1] = fe[el * NROWK + 3 * i + 2] = f;
           else
-            fe[el * NB + i] = s;
+            fe[el * NB + i] = f;
         }
       }
     }

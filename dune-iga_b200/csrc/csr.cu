@@ -245,29 +245,59 @@ __global__ void __launch_bounds__(128) csr_gather_rows_kernel(CsrGeom G, long lo
     fb[q] = q < G.dim ? min(gd[q], G.n[q] - 1 - G.p[q]) : 0;
   }
   __syncwarp();
-  for (int f2 = fa[2]; f2 <= fb[2]; ++f2) {
+  // Candidate elements in a fixed order (f0 fastest), software-pipelined: the first PF x 32 entries of the NEXT element's
+  // matrix row are in flight while the current one is added into the accumulator -- a warp otherwise has only one
+  // 1000-byte row outstanding and the gather runs at a quarter of the HBM bandwidth.  The position of entry jj inside the
+  // row's box does not depend on the element: computed once per lane.
+  constexpr int PF = 4;
+  int pos[PF];
+#pragma unroll
+  for (int t = 0; t < PF; ++t) {
+    const int jj = lane + 32 * t;
+    const int j = jj / G.ncomp, d = jj - j * G.ncomp;
+    const int j0 = j % o0, r = j / o0, j1 = r % o1, j2 = r / o1;
+    pos[t] = ((j2 * len[1] + j1) * len[0] + j0) * G.ncomp + d;
+  }
+  const int nc0 = fb[0] - fa[0] + 1, nc1 = fb[1] - fa[1] + 1, nc2 = fb[2] - fa[2] + 1;
+  const int total = nc0 * nc1 * nc2;
+  auto fetch = [&](int cidx, double (&v)[PF], const double*& src, int& kb) -> bool {
+    const int f0 = fa[0] + cidx % nc0, r = cidx / nc0, f1 = fa[1] + r % nc1, f2 = fa[2] + r / nc1;
+    const int e0 = G.elemOfFirst[0][f0];
+    const int e1 = G.dim > 1 ? G.elemOfFirst[1][f1] : 0;
     const int e2 = G.dim > 2 ? G.elemOfFirst[2][f2] : 0;
-    if (e2 < 0) continue;
-    for (int f1 = fa[1]; f1 <= fb[1]; ++f1) {
-      const int e1 = G.dim > 1 ? G.elemOfFirst[1][f1] : 0;
-      if (e1 < 0) continue;
-      for (int f0 = fa[0]; f0 <= fb[0]; ++f0) {
-        const int e0 = G.elemOfFirst[0][f0];
-        if (e0 < 0) continue;
-        const long long e = e0 + (long long)G.nel[0] * (e1 + (long long)nel1 * e2);
-        if (e < elem_begin || e >= elem_end) continue;
-        const int i = (gd[0] - f0) + o0 * ((gd[1] - f1) + o1 * (gd[2] - f2));
-        const double* __restrict__ src = Ke + (e - elem_begin) * (long long)n * n + (long long)(i * G.ncomp + c) * n;
-        // column h = f + j sits at ((h2 - lo2) len1 + (h1 - lo1)) len0 + (h0 - lo0) of the row's box
-        const int kb = ((f2 - lo[2]) * len[1] + (f1 - lo[1])) * len[0] + (f0 - lo[0]);
-        for (int jj = lane; jj < n; jj += 32) {
-          const int j = jj / G.ncomp, d = jj - j * G.ncomp;
-          const int j0 = j % o0, r = j / o0, j1 = r % o1, j2 = r / o1;
-          acc[(kb + (j2 * len[1] + j1) * len[0] + j0) * G.ncomp + d] += src[jj];
-        }
-        __syncwarp();  // the next element's columns map to other lanes: order the read-modify-writes of acc
+    if (e0 < 0 || e1 < 0 || e2 < 0) return false;
+    const long long e = e0 + (long long)G.nel[0] * (e1 + (long long)nel1 * e2);
+    if (e < elem_begin || e >= elem_end) return false;
+    const int i = (gd[0] - f0) + o0 * ((gd[1] - f1) + o1 * (gd[2] - f2));
+    src = Ke + (e - elem_begin) * (long long)n * n + (long long)(i * G.ncomp + c) * n;
+    // column h = f + j sits at ((h2 - lo2) len1 + (h1 - lo1)) len0 + (h0 - lo0) of the row's box
+    kb = (((f2 - lo[2]) * len[1] + (f1 - lo[1])) * len[0] + (f0 - lo[0])) * G.ncomp;
+#pragma unroll
+    for (int t = 0; t < PF; ++t) v[t] = (lane + 32 * t < n) ? __ldg(src + lane + 32 * t) : 0.0;
+    return true;
+  };
+  double cur[PF], nxt[PF];
+  const double *srcC = nullptr, *srcN = nullptr;
+  int kbC = 0, kbN = 0;
+  bool okC = total > 0 && fetch(0, cur, srcC, kbC), okN = false;
+  for (int cidx = 0; cidx < total; ++cidx) {
+    okN = (cidx + 1 < total) && fetch(cidx + 1, nxt, srcN, kbN);
+    if (okC) {
+#pragma unroll
+      for (int t = 0; t < PF; ++t)
+        if (lane + 32 * t < n) acc[kbC + pos[t]] += cur[t];
+      for (int jj = lane + 32 * PF; jj < n; jj += 32) {  // rows longer than PF x 32 entries (vector-valued, p >= 5)
+        const int j = jj / G.ncomp, d = jj - j * G.ncomp;
+        const int j0 = j % o0, r = j / o0, j1 = r % o1, j2 = r / o1;
+        acc[kbC + ((j2 * len[1] + j1) * len[0] + j0) * G.ncomp + d] += srcC[jj];
       }
     }
+    __syncwarp();  // the next element's columns map to other lanes: order the read-modify-writes of acc
+    okC = okN;
+    srcC = srcN;
+    kbC = kbN;
+#pragma unroll
+    for (int t = 0; t < PF; ++t) cur[t] = nxt[t];
   }
   __syncwarp();
   for (int k = lane; k < nn; k += 32) {
