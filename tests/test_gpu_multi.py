@@ -64,3 +64,29 @@ def test_interface_rows_exchange_over_nccl():
     r = _torchrun("nccl_interface_rows_check.py", 29612)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "interface rows check ok" in r.stdout
+
+
+@needs2
+def test_two_devices_in_one_process_large_shared_memory_gather():
+    """ADVICE (round 1): per-kernel attributes (dynamic shared memory above 48 KB) are per DEVICE.  Two handles on two
+    devices in one process, p=4 elasticity (the CSR gather needs 70 KB per block, the assembly kernel 213 KB): both must
+    launch, and give the same bits."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import torch
+    import igab200  # noqa: F401
+    from dune_iga_b200 import capi, patchdata as PD
+    pd = PD.thickCylinder(4, (1, 1, 1))
+    x, w = PD.gaussLegendre01(5)
+    D = np.eye(6) + 0.1
+    res = []
+    for dev in (1, 0):  # start with the device that is NOT the process default
+        torch.cuda.set_device(dev)
+        P = capi.Patch.fromPatchData(pd)
+        vals, b = P.globalAssemble(capi.ASM_ELASTICITY, [x] * 3, [w] * 3, D=D)
+        res.append((vals, b))
+        P.close()
+    torch.cuda.set_device(0)
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert np.isfinite(res[0][0]).all() and np.abs(res[0][0]).max() > 0
