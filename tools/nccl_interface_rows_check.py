@@ -73,6 +73,42 @@ def main():
             assert all(r[3] < 1e-14 and r[4] < 1e-14 and r[5] for r in res), res
         worst = max(worst, err, errb)
         P.close()
+    # ---- vector-valued (plane elasticity, ncomp = 2) on a TRIMMED 2-D patch: compacted numbering (prepareForTrim), rows of
+    #      DOFs only empty elements touch drop out of every range; 16 x 16 elements p = 2, a hole of empty elements across
+    #      the cuts, a few trimmed elements treated with the tensor rule (the exchange does not care where K_e comes from)
+    pd2 = PD.squarePlate(2, 4)
+    nel = 256
+    flags = np.zeros(nel, np.uint8)
+    ex, ey = np.meshgrid(np.arange(16), np.arange(16), indexing="xy")
+    hole = ((ex - 7.5) ** 2 + (ey - 7.5) ** 2 < 9.0).reshape(-1)
+    flags[hole] = 1
+    flags[[3, 40, 200]] = 2
+    P2 = capi.Patch.fromPatchData(pd2, trimflags=flags)
+    x3, w3 = PD.gaussLegendre01(3)
+    D3 = np.array([[1.1, 0.3, 0.0], [0.3, 1.1, 0.0], [0.0, 0.0, 0.4]])
+    eb, ee = partition.slab_range(pd2.elementsPerDirection, world, rank)
+    vals, rhs = P2.globalAssemble(capi.ASM_ELASTICITY, [x3] * 2, [w3] * 2, D=D3, device=True, elem_begin=eb, elem_end=ee)
+    P2.exchangeInterfaceRows(comm, values=vals, b=rhs, ncomp=2)
+    full, bfull = P2.globalAssemble(capi.ASM_ELASTICITY, [x3] * 2, [w3] * 2, D=D3, device=True)
+    rowptr2, _ = P2.csrPattern(2)
+    dof2, ndof2 = P2.dofmap()
+    mine = dof2[eb:ee][flags[eb:ee] != 1]
+    touched = np.unique(mine[mine >= 0])
+    mask = np.zeros(ndof2 * 2, bool)
+    mask[touched * 2] = True
+    mask[touched * 2 + 1] = True
+    sel = torch.from_numpy(np.repeat(mask, np.diff(rowptr2))).cuda()
+    err2 = float((vals[sel] - full[sel]).abs().max() / full.abs().max()) if int(sel.sum()) else 0.0
+    mt = torch.from_numpy(mask).cuda()
+    errb2 = float((rhs[mt] - bfull[mt]).abs().max() / bfull.abs().max()) if int(mt.sum()) else 0.0
+    res = [None] * world
+    dist.all_gather_object(res, (rank, eb, ee, err2, errb2, int(mask.sum()), int(ndof2)))
+    if rank == 0:
+        print("trimmed, ncomp 2:", res)
+        assert all(r[3] < 1e-14 and r[4] < 1e-14 for r in res), res
+        assert ndof2 < 18 * 18
+    worst = max(worst, err2, errb2)
+    P2.close()
     if rank == 0:
         print("interface rows check ok; worst %.2e over %d ranks" % (worst, world))
     comm.close()
