@@ -606,6 +606,12 @@ igab_status launch_elas(const PatchDev& Pd, SfWorkspace& ws, const double* D_hos
 // and the 8x8 accumulator tiles go straight to global memory: rows of a tile step j by NB1, columns by 1, so a warp's
 // stores form contiguous runs of the 25 complete K_e rows that belong to this i2.
 // KIND: 0 Poisson, 1 mass, 2 elasticity (nine (a, b) blocks, each a Poisson-like contraction with its own 4x4 M4)
+// Weighted univariate tables (tensor-product weights, PatchDev::wfac): wtab_d[e][q][i][a] = w_d(i) * tab_d[e][q][i][a].
+// With them the contraction runs on w_i Phi_i directly and the stored entries need no w_i w_j scaling; null otherwise.
+struct WTabs {
+  const double *t0, *t1, *t2;
+};
+
 template <int P, int Q, int KIND, int NW = 8>
 struct SCfg {
   static constexpr bool MASS = KIND == 1, ELAS = KIND == 2;
@@ -645,7 +651,7 @@ struct SCfg {
   static constexpr int SZ_M = F::ev(NU * NQ);
   static constexpr int SZ_T2 = M3P * LDA3;
   static constexpr int SZ_B2 = KTOT * LDB2;
-  static constexpr int SZ_TOTAL = F::SZ_T + F::SZ_W + SZ_CS + SZ_X + SZ_M + SZ_T2 + SZ_B2;
+  static constexpr int SZ_TOTAL = F::SZ_T + F::SZ_W + SZ_CS + SZ_X + SZ_M + SZ_T2 + SZ_B2 + F::SZ_T;  // + weighted tables
   // tiles of a warp share a tile row (one A fragment for TPW tiles) when that divides evenly; otherwise (GEN2) every
   // warp walks single tiles round-robin
   static constexpr bool GEN2 = !(TPW == 1 || NT2 % TPW == 0);
@@ -672,7 +678,7 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
     PatchDev Pd, long long elem_begin, long long nelem, const double* __restrict__ tab0,
     const double* __restrict__ tab1, const double* __restrict__ tab2, const double* __restrict__ w0,
     const double* __restrict__ w1, const double* __restrict__ w2, ElasCoef coef, double fconst,
-    double* __restrict__ Ke, double* __restrict__ fe) {
+    double* __restrict__ Ke, double* __restrict__ fe, WTabs wt) {
   using C = FCfg<P, Q>;
   using S = SCfg<P, Q, KIND>;
   constexpr bool MASS = S::MASS, ELAS = S::ELAS;
@@ -688,6 +694,9 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
   double* const sM = rX + S::SZ_X;
   double* const sT2 = sM + S::SZ_M;
   double* const sB2 = sT2 + S::SZ_T2;
+  double* const sTw = sB2 + S::SZ_B2;  // weighted tables (tensor-product weights)
+  const bool useW = wt.t0 != nullptr;
+  const double* const sTc = useW ? sTw : sT;  // the tables the contraction stages read
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lr = lane >> 2, lc = lane & 3;
   for (int idx = tid; idx < C::SZ_W; idx += NT) sW[idx] = 0.0;
@@ -730,6 +739,16 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
 
   for (long long el = blockIdx.x; el < nelem; el += gridDim.x) {
     const long long e = elem_begin + el;
+    if (useW) {
+      // nobody reads sTw any more: the previous element's last stage 1 lies two barriers back; element_prepare's barriers
+      // order these writes before the operand builds below
+      const int e0 = (int)(e % Pd.nel[0]), e1 = (int)((e / Pd.nel[0]) % Pd.nel[1]), e2 = (int)(e / ((long long)Pd.nel[0] * Pd.nel[1]));
+      for (int j = tid; j < TAB; j += NT) {
+        sTw[j] = __ldg(wt.t0 + (size_t)e0 * TAB + j);
+        sTw[TAB + j] = __ldg(wt.t1 + (size_t)e1 * TAB + j);
+        sTw[2 * TAB + j] = __ldg(wt.t2 + (size_t)e2 * TAB + j);
+      }
+    }
     element_prepare<P, Q, NT, CS>(Pd, e, tab0, tab1, tab2, w0, w1, w2, sT, sW, rX, rX + C::SZ_A, sC);
     // ---- T1 zeroed (its padding columns must stay zero; the scratch it aliases is free after element_prepare)
     for (int idx = tid; idx < S::SZ_T1; idx += NT) sT1[idx] = 0.0;
@@ -741,7 +760,7 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
         const int j1 = n % NB1, i1 = n / NB1;
         const int bb = S::beta_of(g, c) == 2, bg = S::gamma_of(g, c) == 2;
         sB2[(S::goff(g) + c * Q + q1) * LDB2 + S::cpos(n)] =
-            sT[TAB + (q1 * NB1 + i1) * 2 + bb] * sT[TAB + (q1 * NB1 + j1) * 2 + bg];
+            sTc[TAB + (q1 * NB1 + i1) * 2 + bb] * sTc[TAB + (q1 * NB1 + j1) * 2 + bg];
       }
     }
     // ---- B3[(g, q0)][pi0 = j0 + NB1 i0] = Phi0[q0][i0][b0(beta)] Phi0[q0][j0][b0(gamma)], group g = (b0(beta), b0(gamma)):
@@ -752,7 +771,7 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
       if (k < S::NG * Q && n < NP) {
         const int g = k / Q, q0 = k % Q, j0 = n % NB1, i0 = n / NB1;
         const int bb = (g == 1 || g == 3) ? 1 : 0, bg = (g >= 2) ? 1 : 0;
-        v = sT[(q0 * NB1 + i0) * 2 + bb] * sT[(q0 * NB1 + j0) * 2 + bg];
+        v = sTc[(q0 * NB1 + i0) * 2 + bb] * sTc[(q0 * NB1 + j0) * 2 + bg];
       }
       sT2[k * LDB2 + n] = v;
     }
@@ -830,7 +849,7 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
         double am[QH][Q];
 #pragma unroll
         for (int q2 = 0; q2 < Q; ++q2) {
-          const double a2 = sT[2 * TAB + (q2 * NB1 + i2) * 2 + bb];
+          const double a2 = sTc[2 * TAB + (q2 * NB1 + i2) * 2 + bb];
 #pragma unroll
           for (int u = 0; u < QH; ++u) am[u][q2] = a2 * mrow[min(qa + u, Q - 1) + Q * Q * q2];
         }
@@ -839,7 +858,7 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
         for (int j2 = 0; j2 < NB1; ++j2) {
           double f[Q];
 #pragma unroll
-          for (int q2 = 0; q2 < Q; ++q2) f[q2] = sT[2 * TAB + (q2 * NB1 + j2) * 2 + bg];
+          for (int q2 = 0; q2 < Q; ++q2) f[q2] = sTc[2 * TAB + (q2 * NB1 + j2) * 2 + bg];
 #pragma unroll
           for (int u = 0; u < QH; ++u) {
             double sum = 0.0;
@@ -917,25 +936,45 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
           const double* const wJ = sW + jb;
           if constexpr (ELAS) {
             double* const Kb = K + (long long)(ib * 3 + ca) * NROWK + jb * 3 + cb;
+            if (useW) {
 #pragma unroll
-            for (int nt = 0; nt < S::NT3; ++nt)
+              for (int nt = 0; nt < S::NT3; ++nt)
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int pk = c3[nt][h];
-                if (pk >= 0) {
-                  const int i0 = (pk >> 16) & 15, j0 = pk >> 20;
-                  Kb[i0 * 3 * NROWK + j0 * 3] = acc[nt][h] * (wI[i0] * wJ[j0]);
+                for (int h = 0; h < 2; ++h) {
+                  const int pk = c3[nt][h];
+                  if (pk >= 0) Kb[((pk >> 16) & 15) * 3 * NROWK + (pk >> 20) * 3] = acc[nt][h];
                 }
-              }
+            } else {
+#pragma unroll
+              for (int nt = 0; nt < S::NT3; ++nt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const int pk = c3[nt][h];
+                  if (pk >= 0) {
+                    const int i0 = (pk >> 16) & 15, j0 = pk >> 20;
+                    Kb[i0 * 3 * NROWK + j0 * 3] = acc[nt][h] * (wI[i0] * wJ[j0]);
+                  }
+                }
+            }
           } else {
             double* const Kb = K + ib * NB + jb;
+            if (useW) {  // the weights are inside the tables: the accumulators are the entries of K_e
 #pragma unroll
-            for (int nt = 0; nt < S::NT3; ++nt)
+              for (int nt = 0; nt < S::NT3; ++nt)
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int pk = c3[nt][h];
-                if (pk >= 0) Kb[pk & 0xffff] = acc[nt][h] * (wI[(pk >> 16) & 15] * wJ[pk >> 20]);
-              }
+                for (int h = 0; h < 2; ++h) {
+                  const int pk = c3[nt][h];
+                  if (pk >= 0) Kb[pk & 0xffff] = acc[nt][h];
+                }
+            } else {
+#pragma unroll
+              for (int nt = 0; nt < S::NT3; ++nt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const int pk = c3[nt][h];
+                  if (pk >= 0) Kb[pk & 0xffff] = acc[nt][h] * (wI[(pk >> 16) & 15] * wJ[pk >> 20]);
+                }
+            }
           }
         }
       }
@@ -1007,7 +1046,8 @@ struct WCfg {
   static constexpr int NCP = S::ELAS ? 3 : 1;
   static constexpr int SZ_B3 = S::K3 * S::LDB2;
   static constexpr int SZ_K = F::ev(S::NP * S::NB * NCP);  // the rows (i0, i1) of one i2 (x the three b-blocks)
-  static constexpr int SZ_TOTAL = F::SZ_T + F::SZ_W + S::SZ_CS + S::SZ_X + S::SZ_M + 2 * S::SZ_T2 + S::SZ_B2 + SZ_B3 + SZ_K;
+  static constexpr int SZ_TOTAL =
+      F::SZ_T + F::SZ_W + S::SZ_CS + S::SZ_X + S::SZ_M + 2 * S::SZ_T2 + S::SZ_B2 + SZ_B3 + SZ_K + F::SZ_T;
   static constexpr bool FITS = SZ_TOTAL * 8 <= 227 * 1024;
 };
 
@@ -1016,7 +1056,7 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
     PatchDev Pd, long long elem_begin, long long nelem, const double* __restrict__ tab0,
     const double* __restrict__ tab1, const double* __restrict__ tab2, const double* __restrict__ w0,
     const double* __restrict__ w1, const double* __restrict__ w2, ElasCoef coef, double fconst,
-    double* __restrict__ Ke, double* __restrict__ fe) {
+    double* __restrict__ Ke, double* __restrict__ fe, WTabs wt) {
   using C = FCfg<P, Q>;
   using WC = WCfg<P, Q, KIND>;
   using S = typename WC::S;
@@ -1038,6 +1078,9 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
   double* const sB2 = sT2 + 2 * S::SZ_T2;
   double* const sB3 = sB2 + S::SZ_B2;
   double* const sK = sB3 + WC::SZ_B3;
+  double* const sTw = sK + WC::SZ_K;  // weighted tables (tensor-product weights)
+  const bool useW = wt.t0 != nullptr;
+  const double* const sTc = useW ? sTw : sT;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool is_mma = warp < WC::NWM;
   const int htid = tid - NTM;  // helper thread index (negative for the DMMA warps)
@@ -1082,6 +1125,15 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
   IGAB_WPT_BEGIN
   for (long long el = blockIdx.x; el < nelem; el += gridDim.x) {
     const long long e = elem_begin + el;
+    __syncthreads();  // the helpers' last stage 1 of the previous element is done with sTw
+    if (useW) {
+      const int e0 = (int)(e % Pd.nel[0]), e1 = (int)((e / Pd.nel[0]) % Pd.nel[1]), e2 = (int)(e / ((long long)Pd.nel[0] * Pd.nel[1]));
+      for (int j = tid; j < TAB; j += NT) {
+        sTw[j] = __ldg(wt.t0 + (size_t)e0 * TAB + j);
+        sTw[TAB + j] = __ldg(wt.t1 + (size_t)e1 * TAB + j);
+        sTw[2 * TAB + j] = __ldg(wt.t2 + (size_t)e2 * TAB + j);
+      }
+    }
     element_prepare<P, Q, NT, CS>(Pd, e, tab0, tab1, tab2, w0, w1, w2, sT, sW, rX, rX + C::SZ_A, sC);
     IGAB_WPT(is_mma ? 8 : 9)
     // ---- between two elements, all 16 warps: T1 zeroed, the B operands of stages 2 / 3, the point matrices M4
@@ -1093,7 +1145,7 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
         const int j1 = n % NB1, i1 = n / NB1;
         const int bb = S::beta_of(g, c) == 2, bg = S::gamma_of(g, c) == 2;
         sB2[(S::goff(g) + c * Q + q1) * LDB2 + S::cpos(n)] =
-            sT[TAB + (q1 * NB1 + i1) * 2 + bb] * sT[TAB + (q1 * NB1 + j1) * 2 + bg];
+            sTc[TAB + (q1 * NB1 + i1) * 2 + bb] * sTc[TAB + (q1 * NB1 + j1) * 2 + bg];
       }
     }
     for (int idx = tid; idx < S::K3 * S::NPP; idx += NT) {
@@ -1102,7 +1154,7 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
       if (k < S::NG * Q && n < NP) {
         const int g = k / Q, q0 = k % Q, j0 = n % NB1, i0 = n / NB1;
         const int bb = (g == 1 || g == 3) ? 1 : 0, bg = (g >= 2) ? 1 : 0;
-        v = sT[(q0 * NB1 + i0) * 2 + bb] * sT[(q0 * NB1 + j0) * 2 + bg];
+        v = sTc[(q0 * NB1 + i0) * 2 + bb] * sTc[(q0 * NB1 + j0) * 2 + bg];
       }
       sB3[k * LDB2 + n] = v;
     }
@@ -1272,7 +1324,7 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
           double am[QH][Q];
 #pragma unroll
           for (int q2 = 0; q2 < Q; ++q2) {
-            const double a2 = sT[2 * TAB + (q2 * NB1 + i2) * 2 + bb];
+            const double a2 = sTc[2 * TAB + (q2 * NB1 + i2) * 2 + bb];
 #pragma unroll
             for (int u = 0; u < QH; ++u) am[u][q2] = a2 * mrow[min(qa + u, Q - 1) + Q * Q * q2];
           }
@@ -1281,7 +1333,7 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
           for (int j2 = 0; j2 < NB1; ++j2) {
             double f[Q];
 #pragma unroll
-            for (int q2 = 0; q2 < Q; ++q2) f[q2] = sT[2 * TAB + (q2 * NB1 + j2) * 2 + bg];
+            for (int q2 = 0; q2 < Q; ++q2) f[q2] = sTc[2 * TAB + (q2 * NB1 + j2) * 2 + bg];
 #pragma unroll
             for (int u = 0; u < QH; ++u) {
               double sum = 0.0;
@@ -1319,8 +1371,11 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
               const double wi = sW[i];
               const double* src = sK + row * NROWK;
               double* dst = ELAS ? K + (long long)(i * 3 + ca) * NROWK : K + (long long)i * NB;
-#pragma unroll 4
-              for (int c = lane; c < NROWK; c += 32) dst[c] = src[c] * (wi * sW[ELAS ? c / 3 : c]);
+              if (useW) {  // the weights are inside the tables: a plain coalesced copy
+                for (int c = lane; c < NROWK; c += 32) dst[c] = src[c];
+              } else {
+                for (int c = lane; c < NROWK; c += 32) dst[c] = src[c] * (wi * sW[ELAS ? c / 3 : c]);
+              }
             }
           }
           IGAB_WPT(7)
@@ -1368,6 +1423,11 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
   }
 }
 
+inline WTabs wtabs_of(const PatchDev& Pd, const SfWorkspace& ws) {
+  if (Pd.wfac[0] && ws.wvalid) return WTabs{ws.wtab[0], ws.wtab[1], ws.wtab[2]};
+  return WTabs{nullptr, nullptr, nullptr};
+}
+
 template <int P, int Q, int KIND>
 igab_status launch_ws(const PatchDev& Pd, SfWorkspace& ws, const ElasCoef& coef, double fconst, long long eb,
                       long long nel, const double* const* w_dev, double* Ke, double* fe, cudaStream_t stream) {
@@ -1377,7 +1437,7 @@ igab_status launch_ws(const PatchDev& Pd, SfWorkspace& ws, const ElasCoef& coef,
   if (igab_status cst = kernel_config((const void*)gram_ws_kernel<P, Q, KIND>, WC::NT, sm, &kc)) return cst;
   const unsigned grid = (unsigned)std::min<long long>(nel, (long long)kc.blocksPerSm * kc.sms);
   gram_ws_kernel<P, Q, KIND><<<grid, WC::NT, sm, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],
-                                                          w_dev[1], w_dev[2], coef, fconst, Ke, fe);
+                                                          w_dev[1], w_dev[2], coef, fconst, Ke, fe, wtabs_of(Pd, ws));
   count_launch();
   IGAB_CUDA_TRY(cudaGetLastError());
   return IGAB_OK;
@@ -1414,7 +1474,7 @@ igab_status launch_elas_sf(const PatchDev& Pd, SfWorkspace& ws, const double* D_
   if (igab_status cst = kernel_config((const void*)gram_sf_kernel<P, Q, 2>, 256, sm, &kc)) return cst;
   const unsigned grid = (unsigned)std::min<long long>(nel, (long long)kc.blocksPerSm * kc.sms);
   gram_sf_kernel<P, Q, 2><<<grid, 256, sm, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0], w_dev[1],
-                                                    w_dev[2], coef, fconst, Ke, fe);
+                                                    w_dev[2], coef, fconst, Ke, fe, wtabs_of(Pd, ws));
   count_launch();
   IGAB_CUDA_TRY(cudaGetLastError());
   return IGAB_OK;
@@ -1432,10 +1492,10 @@ igab_status launch_sf_only(const PatchDev& Pd, SfWorkspace& ws, bool mass, doubl
   const unsigned grid = (unsigned)std::min<long long>(nel, (long long)kc.blocksPerSm * kc.sms);
   if (mass)
     gram_sf_kernel<P, Q, 1><<<grid, 256, sm, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0], w_dev[1],
-                                                      w_dev[2], nocoef, fconst, Ke, fe);
+                                                      w_dev[2], nocoef, fconst, Ke, fe, wtabs_of(Pd, ws));
   else
     gram_sf_kernel<P, Q, 0><<<grid, 256, sm, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0], w_dev[1],
-                                                      w_dev[2], nocoef, fconst, Ke, fe);
+                                                      w_dev[2], nocoef, fconst, Ke, fe, wtabs_of(Pd, ws));
   count_launch();
   IGAB_CUDA_TRY(cudaGetLastError());
   return IGAB_OK;
@@ -1465,10 +1525,10 @@ igab_status launch_pq(const PatchDev& Pd, SfWorkspace& ws, bool mass, double fco
       const unsigned grid = (unsigned)std::min<long long>(nel, (long long)kc.blocksPerSm * kc.sms);
       if (mass)
         gram_sf_kernel<P, Q, 1><<<grid, 256, sm, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],
-                                                          w_dev[1], w_dev[2], nocoef, fconst, Ke, fe);
+                                                          w_dev[1], w_dev[2], nocoef, fconst, Ke, fe, wtabs_of(Pd, ws));
       else
         gram_sf_kernel<P, Q, 0><<<grid, 256, sm, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],
-                                                          w_dev[1], w_dev[2], nocoef, fconst, Ke, fe);
+                                                          w_dev[1], w_dev[2], nocoef, fconst, Ke, fe, wtabs_of(Pd, ws));
       count_launch();
       IGAB_CUDA_TRY(cudaGetLastError());
       return IGAB_OK;
@@ -1516,6 +1576,7 @@ igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* 
   }
   igab_status st = ensure_tables3d(P, ws, nq1[0], xi1d_dev, xi1d_host, stream);
   if (st) return st;
+  if ((st = ensure_wtables3d(P, ws, nq1[0], stream))) return st;
   if (kind == IGAB_ASM_ELASTICITY) {
     if (!D_host) {
       set_error("assemble: elasticity needs the 6x6 D matrix");

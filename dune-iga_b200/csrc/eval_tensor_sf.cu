@@ -54,6 +54,17 @@ __global__ void tables_kernel(PatchDev P, int d, int nq, const double* __restric
   }
 }
 
+// weighted copy: wtab[e][q][i][a] = tab[e][q][i][a] * wfac[span(e) - p + i]
+__global__ void wtables_kernel(PatchDev P, int d, int nq, const double* __restrict__ tab, double* __restrict__ wtab) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nb1 = P.degree[d] + 1;
+  if (t >= P.nel[d] * nq * nb1) return;
+  const int i = t % nb1, e = t / (nb1 * nq);
+  const double w = P.wfac[d][P.spanTab[d][e] - P.degree[d] + i];
+  wtab[2 * t] = tab[2 * t] * w;
+  wtab[2 * t + 1] = tab[2 * t + 1] * w;
+}
+
 template <int P, int Q>
 struct Cfg {
   static constexpr int NB1 = P + 1;
@@ -391,7 +402,28 @@ igab_status ensure_tables3d(const PatchDev& Pd, SfWorkspace& ws, int Q, const do
   }
   count_launch(3);
   ws.valid = true;
+  ws.wvalid = false;
   ws.stream = stream;
+  return IGAB_OK;
+}
+
+igab_status ensure_wtables3d(const PatchDev& Pd, SfWorkspace& ws, int Q, cudaStream_t stream) {
+  if (!Pd.wfac[0] || ws.wvalid) return IGAB_OK;
+  for (int d = 0; d < 3; ++d) {
+    const size_t n = (size_t)Pd.nel[d] * Q * (Pd.degree[d] + 1) * 2;
+    if (ws.wtabCap[d] < n) {
+      if (ws.wtab[d]) IGAB_CUDA_TRY(cudaFreeAsync(ws.wtab[d], stream));
+      ws.wtab[d] = nullptr;
+      ws.wtabCap[d] = 0;
+      IGAB_CUDA_TRY(cudaMallocAsync(&ws.wtab[d], n * sizeof(double), stream));
+      ws.wtabCap[d] = n;
+    }
+    const int threads = 128, total = (int)(n / 2);
+    wtables_kernel<<<(total + threads - 1) / threads, threads, 0, stream>>>(Pd, d, Q, ws.tab[d], ws.wtab[d]);
+  }
+  count_launch(3);
+  IGAB_CUDA_TRY(cudaGetLastError());
+  ws.wvalid = true;
   return IGAB_OK;
 }
 
@@ -455,6 +487,8 @@ void free_sf_workspace(SfWorkspace& ws) {
     if (ws.tab[d]) cudaFree(ws.tab[d]);
   for (int d = 0; d < kMaxDim; ++d)
     if (ws.tabO2[d]) cudaFree(ws.tabO2[d]);
+  for (int d = 0; d < kMaxDim; ++d)
+    if (ws.wtab[d]) cudaFree(ws.wtab[d]);
   if (ws.counter) cudaFree(ws.counter);
   ws = SfWorkspace();
 }

@@ -436,6 +436,37 @@ static igab_status run_eval_points_device(igab_patch* p, const PointSource& src,
   return launch_eval_generic(p->dev, src, npts, order, out, stream);
 }
 
+// Are the weights of a 3-D net a tensor product w(i,j,k) = a_i b_j c_k (to 1e-14 relative)?  Then the factors go to the
+// device (PatchDev::wfac) and the assembly kernels fold them into their univariate tables.  cp: HOST net [n][dw+1].
+igab_status detect_tensor_product_weights(igab_patch* p, const double* cp) {
+  PatchDev& D = p->dev;
+  for (int d = 0; d < kMaxDim; ++d) D.wfac[d] = nullptr;
+  if (D.dim != 3 || getenv("IGAB_NO_WTAB")) return IGAB_OK;
+  const int n0 = D.ncp[0], n1 = D.ncp[1], n2 = D.ncp[2], st = D.dw + 1;
+  auto w = [&](int i, int j, int k) { return cp[((size_t)i + (size_t)n0 * ((size_t)j + (size_t)n1 * k)) * st + D.dw]; };
+  const double w000 = w(0, 0, 0);
+  if (!(w000 > 0.0)) return IGAB_OK;
+  std::vector<double> a(n0), b(n1), c(n2);
+  for (int i = 0; i < n0; ++i) a[i] = w(i, 0, 0);
+  for (int j = 0; j < n1; ++j) b[j] = w(0, j, 0) / w000;
+  for (int k = 0; k < n2; ++k) c[k] = w(0, 0, k) / w000;
+  for (int k = 0; k < n2; ++k)
+    for (int j = 0; j < n1; ++j) {
+      const double bc = b[j] * c[k];
+      for (int i = 0; i < n0; ++i) {
+        const double v = w(i, j, k);
+        if (!(std::fabs(v - a[i] * bc) <= 1e-14 * std::fabs(v))) return IGAB_OK;  // not a tensor product: general path
+      }
+    }
+  const std::vector<double>* f[3] = {&a, &b, &c};
+  for (int d = 0; d < 3; ++d) {
+    if (!p->d_wfac[d]) IGAB_CUDA_TRY(cudaMalloc(&p->d_wfac[d], sizeof(double) * D.ncp[d]));
+    IGAB_CUDA_TRY(cudaMemcpy(p->d_wfac[d], f[d]->data(), sizeof(double) * D.ncp[d], cudaMemcpyHostToDevice));
+  }
+  for (int d = 0; d < 3; ++d) D.wfac[d] = p->d_wfac[d];
+  return IGAB_OK;
+}
+
 }  // namespace igab
 
 using namespace igab;
@@ -631,6 +662,20 @@ static igab_status patch_create_impl(int dim, int dimworld, const int* degree, c
       cudaSuccess)
     return fail(e, "copy control net");
   D.cp = p->d_cp;
+  {
+    igab_status wst = IGAB_OK;
+    if (cp_space == IGAB_HOST) {
+      wst = detect_tensor_product_weights(p, cp);
+    } else if (dim == 3 && !getenv("IGAB_NO_WTAB")) {  // device net: one copy back for the host-side check
+      std::vector<double> tmp((size_t)p->ncp_total * (dimworld + 1));
+      if ((e = cudaMemcpy(tmp.data(), p->d_cp, cpBytes, cudaMemcpyDeviceToHost)) != cudaSuccess) return fail(e, "read control net");
+      wst = detect_tensor_product_weights(p, tmp.data());
+    }
+    if (wst) {
+      igab_patch_destroy(p);
+      return wst;
+    }
+  }
   if (trimflags) {
     if ((e = cudaMalloc(&p->d_trim, D.nelem)) != cudaSuccess) return fail(e, "cudaMalloc trim flags");
     if ((e = cudaMemcpy(p->d_trim, trimflags, D.nelem, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e, "copy trim");
@@ -648,6 +693,8 @@ void igab_patch_destroy(igab_patch* p) {
     if (p->d_rden[d]) cudaFree(p->d_rden[d]);
   }
   if (p->d_cp) cudaFree(p->d_cp);
+  for (int d = 0; d < kMaxDim; ++d)
+    if (p->d_wfac[d]) cudaFree(p->d_wfac[d]);
   if (p->d_trim) cudaFree(p->d_trim);
   if (p->d_rule) cudaFree(p->d_rule);
   if (p->d_red) cudaFree(p->d_red);
@@ -696,7 +743,8 @@ igab_status igab_patch_update_control_points(igab_patch* p, const double* cp) {
   // kernels still in flight on the stream of the last call (possibly a non-blocking one) read the control net
   if (p->have_last_stream && cudaStreamSynchronize(p->last_stream) != cudaSuccess) cudaGetLastError();
   IGAB_CUDA_TRY(cudaMemcpy(p->d_cp, cp, sizeof(double) * p->ncp_total * (p->dev.dw + 1), cudaMemcpyHostToDevice));
-  return IGAB_OK;
+  p->sf.wvalid = false;  // the weighted tables carry the old weights
+  return detect_tensor_product_weights(p, cp);
 }
 
 igab_status igab_patch_spans(igab_patch* p, int32_t* span, igab_memspace space, void* stream_) {

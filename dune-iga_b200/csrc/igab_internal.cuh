@@ -25,6 +25,10 @@ struct PatchDev {
   const int* spanTab[kMaxDim];    // device: span index of element e_d, bit-exact with findSpanCorrected(p,uq[e],U,e)
   const double* rden[kMaxDim];    // device [nel_d][p(p+1)/2]: reciprocals of the knot differences A2.3 divides by (per span)
   const double* cp;               // device [prod ncp][dw+1]  (x.., w)
+  // 3-D patches whose weights are a tensor product w(i,j,k) = a_i b_j c_k (B-splines, conics, revolved / extruded /
+  // ruled solids and every refinement of them): the per-direction factors on the device, else nullptr.  The assembly
+  // kernels then carry the weights inside their univariate tables and skip the w_i w_j scaling of every stored entry.
+  const double* wfac[kMaxDim];
   int nb;                         // prod (degree+1)
   long long nelem;
 };
@@ -61,6 +65,10 @@ struct SfWorkspace {
   std::vector<double> xiO2[kMaxDim];
   bool validO2 = false;
   cudaStream_t streamO2 = nullptr;
+  // the same tables multiplied by the weight factor of their control point (tensor-product weights only)
+  double* wtab[kMaxDim] = {nullptr, nullptr, nullptr};
+  size_t wtabCap[kMaxDim] = {0, 0, 0};
+  bool wvalid = false;
 };
 
 // orders `stream` behind the handle's previous stream when the caller switches streams (handle scratch is shared)
@@ -97,6 +105,8 @@ igab_status launch_eval_tensor_sf(const PatchDev& P, SfWorkspace& ws, const Poin
 void free_sf_workspace(SfWorkspace& ws);
 igab_status ensure_tables3d(const PatchDev& Pd, SfWorkspace& ws, int Q, const double* const* xi1d_dev,
                             const double* const* xi1d_host, cudaStream_t stream);
+// weighted copies of the tables (after ensure_tables3d); no-op unless Pd.wfac is set
+igab_status ensure_wtables3d(const PatchDev& Pd, SfWorkspace& ws, int Q, cudaStream_t stream);
 // fully fused element matrices (3-D Poisson / mass / elasticity, p = 2, 3, 4)
 bool gram_fused_supported(const PatchDev& P, int kind, const int* nq1);
 igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host,
@@ -198,6 +208,7 @@ struct igab_patch {
   int* d_span[igab::kMaxDim] = {nullptr, nullptr, nullptr};
   double* d_rden[igab::kMaxDim] = {nullptr, nullptr, nullptr};
   double* d_cp = nullptr;
+  double* d_wfac[igab::kMaxDim] = {nullptr, nullptr, nullptr};
   uint8_t* d_trim = nullptr;
   long long ncp_total = 0;
   long long ndof_untrimmed = 0;

@@ -290,3 +290,52 @@ def test_device_resident_refinement_chain_matches_host_and_reference():
             k5.append(np.sort(np.concatenate([coarse.knotSpans[d], PD.generateRefinedKnots(coarse.knotSpans, d, 5)])))
         n5 = capi.refineKnots(coarse, k5)
         assert np.abs(n5 - np.asarray(R.cp).reshape(n5.shape)).max() <= 1e-13 * np.abs(n5).max()
+
+
+@pytest.mark.parametrize("p", [3, 4])
+@pytest.mark.parametrize("kind", [capi.ASM_POISSON, capi.ASM_MASS, capi.ASM_ELASTICITY])
+def test_tensor_product_weights_folded_into_the_tables(p, kind, monkeypatch):
+    """Patches whose weights are a tensor product (here: the quarter cylinder, weights (1, 1/sqrt 2, 1) x 1 x 1 and its
+    refinements) take the assembly path with the weights inside the univariate tables (no w_i w_j scaling per stored
+    entry); IGAB_NO_WTAB=1 at handle creation keeps the general path.  Same element matrices to rounding, both kernels
+    (barrier-separated / warp-specialised), and the oracle on a sample; a handle whose weights stop being a tensor
+    product after igab_patch_update_control_points falls back by itself."""
+    import torch
+    pd = PD.thickCylinder(p, (2, 2, 2))
+    spec = dict(degree=pd.degree, knots=pd.knotSpans, cp=pd.cp, dimworld=3)
+    x, w = PD.gaussLegendre01(p + 1)
+    D = np.eye(6) * 2.0 + 0.3 if kind == capi.ASM_ELASTICITY else None
+    monkeypatch.setenv("IGAB_ELAS_SF", "1")
+    res = {}
+    for wtab in ("on", "off"):
+        if wtab == "off":
+            monkeypatch.setenv("IGAB_NO_WTAB", "1")
+        else:
+            monkeypatch.delenv("IGAB_NO_WTAB", raising=False)
+        P = gpu_patch(spec)
+        for ws in ("0", "1"):
+            monkeypatch.setenv("IGAB_GRAM_WS", ws)
+            res[(wtab, ws)] = P.assemble(kind, [x] * 3, [w] * 3, D=D, fconst=1.3)
+    monkeypatch.delenv("IGAB_NO_WTAB", raising=False)
+    ref = res[("off", "0")]
+    assert np.array_equal(res[("off", "1")][0], ref[0]) and np.array_equal(res[("on", "1")][0], res[("on", "0")][0])
+    n = ref[0].shape[1]
+    assert relerr(res[("on", "0")][0].reshape(-1, n * n), ref[0].reshape(-1, n * n)) <= 1e-13
+    assert relerr(res[("on", "0")][1], ref[1]) <= 1e-13
+    O = port_for(spec)
+    for e in (0, 17, 63):
+        Kr, fr = O.assemble(kind, [x] * 3, [w] * 3, D=D, fconst=1.3, elem_begin=e, elem_end=e + 1)
+        assert relerr(res[("on", "0")][0][e].reshape(1, -1), Kr.reshape(1, -1)) <= TOL
+        assert relerr(res[("on", "0")][1][e].reshape(1, -1), fr.reshape(1, -1)) <= TOL
+    # weights perturbed through igab_patch_update_control_points: not a tensor product any more
+    P = gpu_patch(spec)
+    cp2 = PD.perturbed(pd, seed=4, amp=0.0).cp
+    assert np.abs(cp2[:, 3] - pd.cp[:, 3]).max() > 0.1
+    P.updateControlPoints(cp2)
+    K2, _ = P.assemble(kind, [x] * 3, [w] * 3, D=D, elem_end=2)
+    O2 = PT.PortPatch(pd.degree, pd.knotSpans, cp2, 3)
+    Kr2, _ = O2.assemble(kind, [x] * 3, [w] * 3, D=D, elem_end=2)
+    assert relerr(K2.reshape(2, -1), Kr2.reshape(2, -1)) <= TOL
+    P.updateControlPoints(pd.cp)  # ... and back
+    K3, _ = P.assemble(kind, [x] * 3, [w] * 3, D=D, elem_end=2)
+    assert np.array_equal(K3, res[("on", "1")][0][:2]) or relerr(K3.reshape(2, -1), ref[0][:2].reshape(2, -1)) <= 1e-13
