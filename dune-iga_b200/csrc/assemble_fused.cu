@@ -833,9 +833,10 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
     }
     {
       // ---- stage 1: thread <-> (combo, q1, half of the q0 range), all j2: the M4 line and the i2 factor in registers
-      constexpr int QH = (Q + 1) / 2;
-      for (int item = tid; item < S::NCOMBO * Q * 2; item += NT) {
-        const int half = item & 1, r = item >> 1, q1 = r % Q, cc = r / Q;
+      // the q0 range in pieces of two: NCOMBO Q ceil(Q / 2) items (240 of the block's 256 threads at p = 4, Poisson)
+      constexpr int QH = 2, NSPL = (Q + QH - 1) / QH;
+      for (int item = tid; item < S::NCOMBO * Q * NSPL; item += NT) {
+        const int half = item % NSPL, r = item / NSPL, q1 = r % Q, cc = r / Q;
         int g = 0, c = cc;
         if constexpr (!MASS) {
           if (cc >= 15) { g = 3; c = 0; }
