@@ -2286,9 +2286,17 @@ igab_status igab_reduce_norms_trimmed(igab_patch* p, int64_t elem_begin, int64_t
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_lw, w, sizeof(double) * npts_list, cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) st = cuda_fail(e, "reduce_norms: list staging");
   }
-  if (!st)
-    st = launch_norms(p->dev, elem_begin, elem_end - elem_begin, nq1, rule.xi, rule.w, u_dev, ncomp, p->d_norm, npartial,
-                      res_dev, stream, p->d_trim, p->d_dofc_map, npts_list, d_le, d_lx, d_lw);
+  if (!st) {
+    // tensor part: sum-factorised kernel where one is compiled (3-D, equal degrees), else thread per point
+    bool tensor_done = false;
+    const igab_status sst = launch_norms_sf(p->dev, p->sf, xi1d, elem_begin, elem_end - elem_begin, nq1, rule.xi, rule.w,
+                                            u_dev, ncomp, p->d_norm, npartial, res_dev, stream, p->d_trim, p->d_dofc_map);
+    if (sst == IGAB_OK) tensor_done = true;
+    else if (sst != IGAB_UNSUPPORTED) st = sst;
+    if (!st && !(tensor_done && npts_list == 0))
+      st = launch_norms(p->dev, elem_begin, elem_end - elem_begin, nq1, rule.xi, rule.w, u_dev, ncomp, p->d_norm, npartial,
+                        res_dev, stream, p->d_trim, p->d_dofc_map, npts_list, d_le, d_lx, d_lw, tensor_done);
+  }
   if (npts_list > 0) cudaStreamSynchronize(stream);  // the host list arrays may go away after the call
   if (d_le) cudaFreeAsync(d_le, stream);
   if (d_lx) cudaFreeAsync(d_lx, stream);

@@ -176,7 +176,13 @@ igab_status launch_norms(const PatchDev& P, long long elem_begin, long long nele
                          double* partial_dev, int npartial, double* result_dev, cudaStream_t stream,
                          const uint8_t* trim_dev = nullptr, const int32_t* map_dev = nullptr, long long npts_list = 0,
                          const int32_t* lelem_dev = nullptr, const double* lxi_dev = nullptr,
-                         const double* lw_dev = nullptr);
+                         const double* lw_dev = nullptr, bool tensor_done = false);
+// sum-factorised tensor part (3-D, equal degrees 2..4); IGAB_UNSUPPORTED when it does not apply
+igab_status launch_norms_sf(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host, long long elem_begin,
+                            long long nelem, const int* nq1, const double* const* xi1d_dev,
+                            const double* const* w1d_dev, const double* u_dev, int ncomp, double* partial_dev,
+                            int npartial, double* result_dev, cudaStream_t stream, const uint8_t* trim_dev,
+                            const int32_t* map_dev);
 // trimmed patches: builds (once) the compacted DOF numbering of prepareForTrim in the handle (d_dofc_map / d_dofc_inv)
 igab_status ensure_dof_compaction(igab_patch* p);
 igab_status geometry_local_device(const PatchDev& P, long long npts, const int* elem, const double* xg, double* xi,
