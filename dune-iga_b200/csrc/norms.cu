@@ -493,9 +493,6 @@ igab_status launch_norms_sf(const PatchDev& P, SfWorkspace& ws, const double* co
   return IGAB_UNSUPPORTED;
 }
 
-namespace {
-}  // namespace
-
 // Tensor rule over the (full) elements [elem_begin, elem_begin + nelem), then -- npts_list > 0 -- the trimmed elements' own
 // points (device arrays) added on.  trim_dev / map_dev: nullptr on untrimmed patches.
 igab_status launch_norms(const PatchDev& P, long long elem_begin, long long nelem, const int* nq1,
