@@ -763,7 +763,13 @@ def main():
     # ---- the collectives of the path on all ranks (also with one rank: a single-rank communicator)
     multi = None
     if not args.no_multi_gpu:
-        multi = bench_multi_gpu(args, rank, world, P, pd, xi, barrier, dist)
+        if world == 1:
+            try:  # one rank: a side measurement must not take the headline line down (N > 1: fail loudly, torchrun ends all ranks)
+                multi = bench_multi_gpu(args, rank, world, P, pd, xi, barrier, dist)
+            except Exception as ex:  # noqa: BLE001
+                multi = {"error": "%s: %s" % (type(ex).__name__, ex)}
+        else:
+            multi = bench_multi_gpu(args, rank, world, P, pd, xi, barrier, dist)
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference's own headers (oracle/_ref), all host threads
     cpu = None
@@ -814,8 +820,11 @@ def main():
     # ---- the remaining configs of BASELINE.json, one GPU each (N = 1 line only)
     configs = None
     if rank == 0 and world == 1 and not args.no_configs:
-        dm = assembly["roofline"]["peak"] if assembly else measured_fp64_peak()[0]
-        configs = bench_configs(peak, dm)
+        try:
+            dm = assembly["roofline"]["peak"] if assembly else measured_fp64_peak()[0]
+            configs = bench_configs(peak, dm)
+        except Exception as ex:  # noqa: BLE001
+            configs = [{"error": "%s: %s" % (type(ex).__name__, ex)}]
 
     if rank == 0:
         print(json.dumps({
