@@ -1425,7 +1425,7 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
 }
 
 inline WTabs wtabs_of(const PatchDev& Pd, const SfWorkspace& ws) {
-  if (Pd.wfac[0] && ws.wvalid) return WTabs{ws.wtab[0], ws.wtab[1], ws.wtab[2]};
+  if (Pd.wfac[0] && ws.wvalid && ws.wuse) return WTabs{ws.wtab[0], ws.wtab[1], ws.wtab[2]};
   return WTabs{nullptr, nullptr, nullptr};
 }
 
@@ -1577,7 +1577,14 @@ igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* 
   }
   igab_status st = ensure_tables3d(P, ws, nq1[0], xi1d_dev, xi1d_host, stream);
   if (st) return st;
-  if ((st = ensure_wtables3d(P, ws, nq1[0], stream))) return st;
+  {
+    // Inside a CUDA graph capture the general path is recorded: a graph replayed after igab_patch_update_control_points
+    // must not read weighted tables that were built from the previous weights.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (stream) cudaStreamIsCapturing(stream, &cap);
+    ws.wuse = cap == cudaStreamCaptureStatusNone;
+    if (ws.wuse && (st = ensure_wtables3d(P, ws, nq1[0], stream))) return st;
+  }
   if (kind == IGAB_ASM_ELASTICITY) {
     if (!D_host) {
       set_error("assemble: elasticity needs the 6x6 D matrix");

@@ -436,34 +436,54 @@ static igab_status run_eval_points_device(igab_patch* p, const PointSource& src,
   return launch_eval_generic(p->dev, src, npts, order, out, stream);
 }
 
-// Are the weights of a 3-D net a tensor product w(i,j,k) = a_i b_j c_k (to 1e-14 relative)?  Then the factors go to the
-// device (PatchDev::wfac) and the assembly kernels fold them into their univariate tables.  cp: HOST net [n][dw+1].
-igab_status detect_tensor_product_weights(igab_patch* p, const double* cp) {
+// Are the weights of a 3-D net a tensor product w(i,j,k) = a_i b_j c_k (to 1e-14 relative)?  Then the factors stay on the
+// device (PatchDev::wfac) and the assembly kernels fold them into their univariate tables.  Checked ON THE DEVICE and
+// lazily -- by the first assembly call after the net was set -- so that evaluation-only callers and
+// igab_patch_update_control_points pay nothing (a host pass over the 2.2 M weights of config C2 costs 10 ms).
+__global__ void wfac_extract_kernel(PatchDev P, double* a, double* b, double* c) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n0 = P.ncp[0], n1 = P.ncp[1], n2 = P.ncp[2];
+  const double w000 = P.cp[3];
+  if (t < n0) a[t] = P.cp[(size_t)t * 4 + 3];
+  if (t < n1) b[t] = P.cp[(size_t)t * n0 * 4 + 3] / w000;
+  if (t < n2) c[t] = P.cp[(size_t)t * n0 * n1 * 4 + 3] / w000;
+}
+__global__ void wfac_check_kernel(PatchDev P, const double* __restrict__ a, const double* __restrict__ b,
+                                  const double* __restrict__ c, long long n, int* __restrict__ bad) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const int i = (int)(g % P.ncp[0]), j = (int)((g / P.ncp[0]) % P.ncp[1]), k = (int)(g / ((long long)P.ncp[0] * P.ncp[1]));
+  const double w = P.cp[g * 4 + 3];
+  if (!(w > 0.0) || !(fabs(w - a[i] * (b[j] * c[k])) <= 1e-14 * fabs(w))) *bad = 1;
+}
+igab_status detect_tensor_product_weights(igab_patch* p, cudaStream_t stream) {
   PatchDev& D = p->dev;
+  p->wfac_known = true;
   for (int d = 0; d < kMaxDim; ++d) D.wfac[d] = nullptr;
-  if (D.dim != 3 || getenv("IGAB_NO_WTAB")) return IGAB_OK;
-  const int n0 = D.ncp[0], n1 = D.ncp[1], n2 = D.ncp[2], st = D.dw + 1;
-  auto w = [&](int i, int j, int k) { return cp[((size_t)i + (size_t)n0 * ((size_t)j + (size_t)n1 * k)) * st + D.dw]; };
-  const double w000 = w(0, 0, 0);
-  if (!(w000 > 0.0)) return IGAB_OK;
-  std::vector<double> a(n0), b(n1), c(n2);
-  for (int i = 0; i < n0; ++i) a[i] = w(i, 0, 0);
-  for (int j = 0; j < n1; ++j) b[j] = w(0, j, 0) / w000;
-  for (int k = 0; k < n2; ++k) c[k] = w(0, 0, k) / w000;
-  for (int k = 0; k < n2; ++k)
-    for (int j = 0; j < n1; ++j) {
-      const double bc = b[j] * c[k];
-      for (int i = 0; i < n0; ++i) {
-        const double v = w(i, j, k);
-        if (!(std::fabs(v - a[i] * bc) <= 1e-14 * std::fabs(v))) return IGAB_OK;  // not a tensor product: general path
-      }
-    }
-  const std::vector<double>* f[3] = {&a, &b, &c};
-  for (int d = 0; d < 3; ++d) {
-    if (!p->d_wfac[d]) IGAB_CUDA_TRY(cudaMalloc(&p->d_wfac[d], sizeof(double) * D.ncp[d]));
-    IGAB_CUDA_TRY(cudaMemcpy(p->d_wfac[d], f[d]->data(), sizeof(double) * D.ncp[d], cudaMemcpyHostToDevice));
+  if (D.dim != 3 || D.dw != 3 || getenv("IGAB_NO_WTAB")) return IGAB_OK;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (stream) cudaStreamIsCapturing(stream, &cap);
+  if (cap != cudaStreamCaptureStatusNone) {  // no synchronisation inside a capture: general path, decide after the capture
+    p->wfac_known = false;
+    return IGAB_OK;
   }
-  for (int d = 0; d < 3; ++d) D.wfac[d] = p->d_wfac[d];
+  for (int d = 0; d < 3; ++d)
+    if (!p->d_wfac[d]) IGAB_CUDA_TRY(cudaMalloc(&p->d_wfac[d], sizeof(double) * D.ncp[d]));
+  int* d_bad = nullptr;
+  IGAB_CUDA_TRY(cudaMallocAsync(&d_bad, sizeof(int), stream));
+  IGAB_CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(int), stream));
+  const int nmax = std::max(D.ncp[0], std::max(D.ncp[1], D.ncp[2]));
+  wfac_extract_kernel<<<(nmax + 127) / 128, 128, 0, stream>>>(D, p->d_wfac[0], p->d_wfac[1], p->d_wfac[2]);
+  wfac_check_kernel<<<(unsigned)((p->ncp_total + 255) / 256), 256, 0, stream>>>(D, p->d_wfac[0], p->d_wfac[1], p->d_wfac[2],
+                                                                              p->ncp_total, d_bad);
+  count_launch(2);
+  int bad = 1;
+  cudaError_t e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFreeAsync(d_bad, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "tensor-product weight check");
+  if (!bad)
+    for (int d = 0; d < 3; ++d) D.wfac[d] = p->d_wfac[d];
   return IGAB_OK;
 }
 
@@ -662,20 +682,7 @@ static igab_status patch_create_impl(int dim, int dimworld, const int* degree, c
       cudaSuccess)
     return fail(e, "copy control net");
   D.cp = p->d_cp;
-  {
-    igab_status wst = IGAB_OK;
-    if (cp_space == IGAB_HOST) {
-      wst = detect_tensor_product_weights(p, cp);
-    } else if (dim == 3 && !getenv("IGAB_NO_WTAB")) {  // device net: one copy back for the host-side check
-      std::vector<double> tmp((size_t)p->ncp_total * (dimworld + 1));
-      if ((e = cudaMemcpy(tmp.data(), p->d_cp, cpBytes, cudaMemcpyDeviceToHost)) != cudaSuccess) return fail(e, "read control net");
-      wst = detect_tensor_product_weights(p, tmp.data());
-    }
-    if (wst) {
-      igab_patch_destroy(p);
-      return wst;
-    }
-  }
+  for (int d = 0; d < kMaxDim; ++d) D.wfac[d] = nullptr;  // decided lazily by the first assembly call
   if (trimflags) {
     if ((e = cudaMalloc(&p->d_trim, D.nelem)) != cudaSuccess) return fail(e, "cudaMalloc trim flags");
     if ((e = cudaMemcpy(p->d_trim, trimflags, D.nelem, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e, "copy trim");
@@ -744,7 +751,9 @@ igab_status igab_patch_update_control_points(igab_patch* p, const double* cp) {
   if (p->have_last_stream && cudaStreamSynchronize(p->last_stream) != cudaSuccess) cudaGetLastError();
   IGAB_CUDA_TRY(cudaMemcpy(p->d_cp, cp, sizeof(double) * p->ncp_total * (p->dev.dw + 1), cudaMemcpyHostToDevice));
   p->sf.wvalid = false;  // the weighted tables carry the old weights
-  return detect_tensor_product_weights(p, cp);
+  p->wfac_known = false;
+  for (int d = 0; d < kMaxDim; ++d) p->dev.wfac[d] = nullptr;
+  return IGAB_OK;
 }
 
 igab_status igab_patch_spans(igab_patch* p, int32_t* span, igab_memspace space, void* stream_) {
@@ -1101,6 +1110,7 @@ igab_status igab_assemble(igab_patch* p, int kind, const double* D, double fcons
   if (st) return st;
   const long long nel = elem_end - elem_begin;
   if (nel == 0) return IGAB_OK;
+  if (!p->wfac_known && (st = detect_tensor_product_weights(p, stream))) return st;
   const int n = p->dev.nb * (kind == IGAB_ASM_ELASTICITY ? p->dev.dim : 1);
   const int ns = p->dev.dim == 2 ? 3 : 6;
   double* d_D = nullptr;

@@ -68,7 +68,7 @@ struct SfWorkspace {
   // the same tables multiplied by the weight factor of their control point (tensor-product weights only)
   double* wtab[kMaxDim] = {nullptr, nullptr, nullptr};
   size_t wtabCap[kMaxDim] = {0, 0, 0};
-  bool wvalid = false;
+  bool wvalid = false, wuse = false;  // wuse: set per launch (off inside a graph capture)
 };
 
 // orders `stream` behind the handle's previous stream when the caller switches streams (handle scratch is shared)
@@ -215,6 +215,7 @@ struct igab_patch {
   double* d_rden[igab::kMaxDim] = {nullptr, nullptr, nullptr};
   double* d_cp = nullptr;
   double* d_wfac[igab::kMaxDim] = {nullptr, nullptr, nullptr};
+  bool wfac_known = false;  // has the tensor-product check run for the current control net?
   uint8_t* d_trim = nullptr;
   long long ncp_total = 0;
   long long ndof_untrimmed = 0;

@@ -1083,7 +1083,7 @@ def test_fused_3d_element_matrices_over_integrated(p, kind):
     Kref, fref = Pp.assemble(kind, [x] * 3, [w] * 3, D=D, fconst=0.9, elem_end=ne)
     l0 = capi.launch_count()
     K, f = P.assemble(kind, [x] * 3, [w] * 3, D=D, fconst=0.9, elem_end=ne)
-    assert capi.launch_count() - l0 <= 7  # tables + weighted tables + one fused kernel, not the evaluate / stack / contract sequence
+    assert capi.launch_count() - l0 <= 9  # tables + weight check + weighted tables + one fused kernel, not the evaluate / stack / contract sequence
     assert relerr(K.reshape(ne, -1), Kref.reshape(ne, -1)) <= TOL, relerr(K.reshape(ne, -1), Kref.reshape(ne, -1))
     assert relerr(f, fref) <= TOL
 
@@ -1110,7 +1110,7 @@ def test_fused_3d_element_matrices_both_contractions(p, extra, kind, sf, monkeyp
     Kref, fref = Pp.assemble(kind, [x] * 3, [w] * 3, D=D, fconst=1.3, elem_begin=eb, elem_end=ee)
     l0 = capi.launch_count()
     K, f = P.assemble(kind, [x] * 3, [w] * 3, D=D, fconst=1.3, elem_begin=eb, elem_end=ee)
-    assert capi.launch_count() - l0 <= 7   # tables (+ weighted tables) + ONE fused kernel (p = 4 with 7 points = the reference's default rule)
+    assert capi.launch_count() - l0 <= 9   # tables (+ weight check, weighted tables) + ONE fused kernel (p = 4 with 7 points = the reference's default rule)
     assert relerr(K.reshape(ee - eb, -1), Kref.reshape(ee - eb, -1)) <= TOL, relerr(K.reshape(ee - eb, -1), Kref.reshape(ee - eb, -1))
     assert relerr(f, fref) <= TOL
 
@@ -1130,7 +1130,7 @@ def test_fused_3d_element_matrices_p5(kind, q):
     Kref, fref = Pp.assemble(kind, [x] * 3, [w] * 3, fconst=0.4, elem_begin=1, elem_end=4)
     l0 = capi.launch_count()
     K, f = P.assemble(kind, [x] * 3, [w] * 3, fconst=0.4, elem_begin=1, elem_end=4)
-    assert capi.launch_count() - l0 <= 7
+    assert capi.launch_count() - l0 <= 9
     assert relerr(K.reshape(3, -1), Kref.reshape(3, -1)) <= TOL, relerr(K.reshape(3, -1), Kref.reshape(3, -1))
     assert relerr(f, fref) <= TOL
 
