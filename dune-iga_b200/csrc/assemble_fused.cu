@@ -896,24 +896,28 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
       } else if (has2) {
         const double* arow = sT1 + (8 * mt2 + lr) * LDA2 + lc;
         const double* brow = sB2 + lc * LDB2 + 8 * nt2 + lr;
+        // all groups' accumulators first, the T2 stores afterwards: the stores (which may alias the operand loads as far as
+        // the compiler can tell) no longer separate the groups, so their NG x TPW independent DMMA chains interleave
+        double acc[S::NG][S::TPW][2];
 #pragma unroll
         for (int g = 0; g < S::NG; ++g) {
-          double acc[S::TPW][2];
 #pragma unroll
-          for (int s = 0; s < S::TPW; ++s) acc[s][0] = acc[s][1] = 0.0;
+          for (int s = 0; s < S::TPW; ++s) acc[g][s][0] = acc[g][s][1] = 0.0;
           const int kb = S::goff(g), nks = S::r4(S::ncombo(g) * Q) / 4;  // constants after unrolling over g
 #pragma unroll
           for (int ks = 0; ks < nks; ++ks) {
             const double a = arow[kb + 4 * ks];
 #pragma unroll
-            for (int s = 0; s < S::TPW; ++s) dmma8x8x4_f(acc[s][0], acc[s][1], a, brow[(kb + 4 * ks) * LDB2 + 8 * s]);
+            for (int s = 0; s < S::TPW; ++s) dmma8x8x4_f(acc[g][s][0], acc[g][s][1], a, brow[(kb + 4 * ks) * LDB2 + 8 * s]);
           }
+        }
+#pragma unroll
+        for (int g = 0; g < S::NG; ++g)
 #pragma unroll
           for (int s = 0; s < S::TPW; ++s)
 #pragma unroll
             for (int h = 0; h < 2; ++h)
-              if (t2off[s][h] >= 0) sT2[t2off[s][h] + g * Q] = acc[s][h];
-        }
+              if (t2off[s][h] >= 0) sT2[t2off[s][h] + g * Q] = acc[g][s][h];
       }
       __syncthreads();
       // ---- stage 3: K[(j1,j2,i1)][pi0] = sum_{(g,q0)} T2 B3, straight to global memory with the weights w_i w_j
@@ -1223,7 +1227,7 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
           const double* arow = sT1 + (8 * mt2 + lr) * LDA2 + lc;
           const double* brow = sB2 + lc * LDB2 + 8 * nt2 + lr;
 #pragma unroll
-          for (int g = 0; g < S::NG; ++g) {
+          for (int g = 0; g < S::NG; ++g) {  // (all groups before the stores, as in gram_sf_kernel, costs registers here: -6 %)
             double acc[S::TPW][2];
 #pragma unroll
             for (int s = 0; s < S::TPW; ++s) acc[s][0] = acc[s][1] = 0.0;
