@@ -855,6 +855,9 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
           for (int u = 0; u < QH; ++u) am[u][q2] = a2 * mrow[min(qa + u, Q - 1) + Q * Q * q2];
         }
         double* trow = sT1 + S::goff(g) + c * Q + q1;
+        // all sums first, the T1 stores afterwards: shared stores may alias the table loads as far as the compiler can
+        // tell, so a store inside the j2 loop pins the next iteration's loads behind it
+        double sums[NB1][QH];
 #pragma unroll
         for (int j2 = 0; j2 < NB1; ++j2) {
           double f[Q];
@@ -865,9 +868,14 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
             double sum = 0.0;
 #pragma unroll
             for (int q2 = 0; q2 < Q; ++q2) sum = fma(am[u][q2], f[q2], sum);
-            if (qa + u < Q) trow[(j2 * Q + qa + u) * LDA2] = sum;
+            sums[j2][u] = sum;
           }
         }
+#pragma unroll
+        for (int j2 = 0; j2 < NB1; ++j2)
+#pragma unroll
+          for (int u = 0; u < QH; ++u)
+            if (qa + u < Q) trow[(j2 * Q + qa + u) * LDA2] = sums[j2][u];
       }
       __syncthreads();
       // ---- stage 2: C_g[(j2,q0)][pi1] = sum_{k in g} T1[.][k] B2[k][.]  ->  T2[j1 + NB1 j2 + NP i1][g Q + q0]
