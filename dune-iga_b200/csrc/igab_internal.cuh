@@ -109,6 +109,11 @@ igab_status ensure_tables3d(const PatchDev& Pd, SfWorkspace& ws, int Q, const do
 igab_status ensure_wtables3d(const PatchDev& Pd, SfWorkspace& ws, int Q, cudaStream_t stream);
 // fully fused element matrices (3-D Poisson / mass / elasticity, p = 2, 3, 4)
 bool gram_fused_supported(const PatchDev& P, int kind, const int* nq1);
+// assemble_sym.cu: sum-factorised Poisson / mass element matrices, upper block triangle + mirror (the default at p >= 3)
+bool gram_sym_supported(int p, int q, int kind);
+bool gram_sym_default(int p, int q, int kind);
+igab_status launch_gram_sym(const PatchDev& Pd, SfWorkspace& ws, int kind, int q, double fconst, long long eb,
+                            long long nel, const double* const* w_dev, double* Ke, double* fe, cudaStream_t stream);
 igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* const* xi1d_host,
                               const double* const* xi1d_dev, const double* const* w1d_dev, int kind, double fconst,
                               long long eb, long long nel, const int* nq1, double* Ke, double* fe, cudaStream_t stream,
