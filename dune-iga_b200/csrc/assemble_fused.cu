@@ -524,13 +524,15 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
         t2off[s][h] = (has2 && m < S::M2 && n < NP) ? ((n % NB1) + NB1 * (m / Q) + NP * (n / NB1)) * LDA3 + (m % Q) : -1;
       }
   }
-  // stage 3: column n = 8 nt + 2 lc + h of a tile is (j0, i0) = (n % NB1, n / NB1): offset i0 NB + j0 | i0 << 16 | j0 << 20
+  // stage 3: column position 8 nt + 2 lc + h of a tile holds the pair n = cperm(position) = 8 nt + lc + 4 h, (j0, i0) =
+  // (n % NB1, n / NB1): offset i0 NB + j0 | i0 << 16 | j0 << 20.  The four lanes of a quad then store four CONSECUTIVE
+  // entries of a row of K_e (every other one in the natural order: twice the sectors per store instruction)
   int c3[S::NT3][2];
 #pragma unroll
   for (int nt = 0; nt < S::NT3; ++nt)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int n = 8 * nt + 2 * lc + h;
+      const int n = S::cperm(8 * nt + 2 * lc + h);
       c3[nt][h] = n < NP ? ((n / NB1) * NB + (n % NB1)) | ((n / NB1) << 16) | ((n % NB1) << 20) : -1;
     }
 
@@ -579,7 +581,7 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
         const int bb = (g == 1 || g == 3) ? 1 : 0, bg = (g >= 2) ? 1 : 0;
         v = sTc[(q0 * NB1 + i0) * 2 + bb] * sTc[(q0 * NB1 + j0) * 2 + bg];
       }
-      sT2[k * LDB2 + n] = v;
+      sT2[k * LDB2 + S::cpos(n)] = v;
     }
     __syncthreads();
     double b3[S::K3 / 4][S::NT3];

@@ -14,12 +14,32 @@
 // Slot s of a pass: s < na = p+1-a  ->  (i2, j2) = (a, a + s);  otherwise (b, b + s - na).
 #include <algorithm>
 #include <cstdlib>
+#include <utility>
 
 #include "gram_common.cuh"
 
 namespace igab {
 
 namespace {
+
+#ifdef IGAB_SYM_EXPERIMENT
+__constant__ int c_skip;   // timing experiments only (results are wrong): bit 0 stage 1, 1 B2 build, 2 mirror, 3 K_e stores, 4 stage 2, 5 stage 3 DMMA
+#define SKIP(b) (c_skip & (1 << (b)))
+#else
+#define SKIP(b) false
+#endif
+
+// compile-time loop: f(std::integral_constant<int, 0>{}), ..., f(std::integral_constant<int, N - 1>{}) -- the loop index is a
+// constant EXPRESSION inside f (an unrolled run-time loop leaves the constexpr table look-ups below to the optimiser,
+// which kept them as code: 12 k warp instructions per element)
+template <class F, int... I>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) {
+  (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  static_for_impl(static_cast<F&&>(f), std::make_integer_sequence<int, N>{});
+}
 
 template <int P, int Q, int KIND>
 struct YCfg {
@@ -43,6 +63,27 @@ struct YCfg {
     return n;
   }
   static constexpr int NPADC = npadc();
+  // stage 1 on the tensor cores: per combo (beta, gamma) a small product  [slot] x [q2] x [(q1, q0)]  whose A operand
+  // Phi2[q2][i2][b2(beta)] Phi2[q2][j2][b2(gamma)] exists in four variants v = b2(beta) + 2 b2(gamma), b2(.) = (. == 3)
+  static constexpr int g_of(int cc) { return MASS ? 0 : (cc >= 15 ? 3 : (cc >= 12 ? 2 : (cc >= 9 ? 1 : 0))); }
+  static constexpr int c_of(int cc) { return MASS ? 0 : (cc >= 15 ? 0 : (cc >= 12 ? cc - 12 : (cc >= 9 ? cc - 9 : cc))); }
+  static constexpr int var_of(int cc) {
+    return (S::beta_of(g_of(cc), c_of(cc)) == 3 ? 1 : 0) + (S::gamma_of(g_of(cc), c_of(cc)) == 3 ? 2 : 0);
+  }
+  static constexpr int var_count(int v) {
+    int n = 0;
+    for (int cc = 0; cc < S::NCOMBO; ++cc) n += var_of(cc) == v ? 1 : 0;
+    return n;
+  }
+  static constexpr int var_item(int v, int k) {  // k-th combo of variant v, -1 past the end
+    for (int cc = 0; cc < S::NCOMBO; ++cc)
+      if (var_of(cc) == v && k-- == 0) return cc;
+    return -1;
+  }
+  static constexpr int moff_of(int cc) { return cc < 0 ? 0 : S::usym(S::beta_of(g_of(cc), c_of(cc)), S::gamma_of(g_of(cc), c_of(cc))) * NQ; }
+  static constexpr int coff_of(int cc) { return cc < 0 ? 0 : S::goff(g_of(cc)) + c_of(cc) * Q; }
+  static constexpr int NTQ = S::r8(Q * Q) / 8;   // 8-column tiles over (q1, q0)
+  static constexpr bool S1_DMMA = NWARP % NTQ == 0 && NSLOT <= 8;
   static constexpr int SZ_X = F::ev(imax(F::SZ_A + F::SZ_S2, SZ_T1));
   static constexpr int SZ_M = S::SZ_M;
   static constexpr int SZ_T2 = F::ev(imax(M3P * LDA3, K3 * LDB2));
@@ -106,14 +147,17 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
       const int n = S::cperm(8 * (nt2 + s) + 2 * lc + h);
       t2off[s][h] = (has2 && m2 < Y::M2 && n < NP) ? (n + NP * (m2 / Q)) * LDA3 + (m2 % Q) : -1;
     }
-  // stage 3: column n = 8 nt + 2 lc + h of a tile is (j0, i0) = (n % NB1, n / NB1):
+  // stage 3: column position 8 nt + 2 lc + h of a tile holds the pair n = cperm(position) = 8 nt + lc + 4 h, (j0, i0) =
+  // (n % NB1, n / NB1): the four lanes of a quad store four CONSECUTIVE entries of a row of K_e, and with the rows of the
+  // tile (j1 = lr) a store instruction fills runs of 4 out of every 5 doubles instead of every other one (sectors written
+  // per instruction: ~11 instead of ~25)
   //   bits 0-15 i0 NB + j0 (offset in K_e), 16-19 i0, 20-23 j0, 24-31 j0 NP + i0 (offset in the mirror buffer); -1 = padding
   int c3[Y::NT3][2];
 #pragma unroll
   for (int nt = 0; nt < Y::NT3; ++nt)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int n = 8 * nt + 2 * lc + h;
+      const int n = S::cperm(8 * nt + 2 * lc + h);
       const int i0 = n / NB1, j0 = n % NB1;
       c3[nt][h] = n < NP ? (int)((unsigned)(i0 * NB + j0) | ((unsigned)i0 << 16) | ((unsigned)j0 << 20) |
                                  ((unsigned)(j0 * NP + i0) << 24))
@@ -128,7 +172,29 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
     r3[u] = mp < Y::M3 ? (NB1 * (n1 / NB1)) | ((NB1 * (n1 % NB1)) << 8) | (slot << 16) : -1;
   }
 
-  for (long long el = blockIdx.x; el < nelem; el += gridDim.x) {
+  // stage 1 (tensor-core version): warp <-> column tile nt1 of (q1, q0) and a share wg of the combos; lane (lr, lc) holds
+  // C[slot = lr][n = 8 nt1 + 2 lc + h], n = q1 Q + q0  ->  T1[(slot Q + q0)][combo columns + q1]
+  constexpr int WG1 = Y::S1_DMMA ? Y::NWARP / Y::NTQ : 1;
+  const int nt1 = warp % Y::NTQ, wg1 = warp / Y::NTQ;
+  int s1off[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int n = 8 * nt1 + 2 * lc + h;
+    s1off[h] = (n < Q * Q && lr < NSLOT) ? (lr * Q + n % Q) * LDA2 + n / Q : -1;
+  }
+
+  // mirror copy-out: entry NT k + tid of a (p+1)^2 x (p+1)^2 block is (row, c) -> offset row NB + c in K_e
+  constexpr int NCO = (NP * NP + NT - 1) / NT;
+  int cooff[NCO];
+#pragma unroll
+  for (int k = 0; k < NCO; ++k) cooff[k] = ((NT * k + tid) / NP) * NB + (NT * k + tid) % NP;
+
+  // a block takes a CONTIGUOUS run of elements: consecutive elements share e1 (and mostly e2), so the stage-2 operand B2,
+  // which depends on direction 1 only, is rebuilt once per row of elements instead of once per element
+  const long long chunk = (nelem + gridDim.x - 1) / gridDim.x;
+  const long long el_lo = blockIdx.x * chunk, el_hi = el_lo + chunk < nelem ? el_lo + chunk : nelem;
+  int b2_e1 = -1;
+  for (long long el = el_lo; el < el_hi; ++el) {
     const long long e = elem_begin + el;
     IGAB_PT_BEGIN
     if (useW) {
@@ -159,6 +225,8 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
       sT1[row * LDA2 + col] = 0.0;
     }
     // ---- B2[(g, c, q1)][pi1 = j1 + NB1 i1] = Phi1[q1][i1][b1(beta)] Phi1[q1][j1][b1(gamma)],  b1(beta) = (beta == 2)
+    const int e1cur = (int)((e / Pd.nel[0]) % Pd.nel[1]);
+    if (e1cur != b2_e1 && !SKIP(1))
 #pragma unroll
     for (int g = 0; g < S::NG; ++g) {
       for (int idx = tid; idx < S::ncombo(g) * Q * NP; idx += NT) {
@@ -169,6 +237,7 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
             sTc[TAB + (q1 * NB1 + i1) * 2 + bb] * sTc[TAB + (q1 * NB1 + j1) * 2 + bg];
       }
     }
+    b2_e1 = e1cur;
     // ---- B3[(g, q0)][pi0 = j0 + NB1 i0] = Phi0[q0][i0][b0(beta)] Phi0[q0][j0][b0(gamma)], group g = (b0(beta), b0(gamma)):
     //      0 (0,0), 1 (1,0), 2 (0,1), 3 (1,1).  Built once in the (still unused) T2 region, then held as fragments.
     for (int idx = tid; idx < S::K3 * S::NPP; idx += NT) {
@@ -179,7 +248,7 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
         const int bb = (g == 1 || g == 3) ? 1 : 0, bg = (g >= 2) ? 1 : 0;
         v = sTc[(q0 * NB1 + i0) * 2 + bb] * sTc[(q0 * NB1 + j0) * 2 + bg];
       }
-      sT2[k * LDB2 + n] = v;
+      sT2[k * LDB2 + S::cpos(n)] = v;
     }
     // ---- per point: M4 = C^T C (symmetric 4x4; mass: (sqrt(w detJ)/W)^2), and w detJ / W for the load vector
     for (int pt = tid; pt < NQ; pt += NT) {
@@ -217,10 +286,53 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
       const bool paired = i2b > pass;
       const int nslots = paired ? NSLOT : na;
       const int rows2 = nslots * Q, rows3 = nslots * NP;
-      {
+      if constexpr (Y::S1_DMMA) {
+        // ---- stage 1 on the tensor cores: T1[(slot, q0)][(combo, q1)] = sum_q2 A_v[slot][q2] M4_combo[q2][(q1, q0)]
+        constexpr int KS1 = (Q + 3) / 4;
+        const bool sv = lr < nslots, sa1 = lr < na;
+        const int i2 = sv ? (sa1 ? pass : i2b) : 0, j2 = sv ? i2 + (sa1 ? lr : lr - na) : 0;
+        if (!SKIP(0))
+        static_for<(MASS ? 1 : 4)>([&](auto vc) {
+          constexpr int v = decltype(vc)::value;
+          double a[KS1];
+#pragma unroll
+          for (int ks = 0; ks < KS1; ++ks) {
+            const int q2 = 4 * ks + lc;
+            a[ks] = (sv && q2 < Q) ? sTc[2 * TAB + (min(q2, Q - 1) * NB1 + i2) * 2 + (v & 1)] *
+                                         sTc[2 * TAB + (min(q2, Q - 1) * NB1 + j2) * 2 + (v >> 1)]
+                                   : 0.0;
+          }
+          static_for<(Y::var_count(v) + WG1 - 1) / WG1>([&](auto itc) {
+            constexpr int it = decltype(itc)::value;
+            int moff = 0, coff = 0;
+            bool ok = false;
+            static_for<WG1>([&](auto kc) {
+              constexpr int k = decltype(kc)::value;
+              constexpr int cc = Y::var_item(v, it * WG1 + k);
+              if constexpr (cc >= 0) {
+                constexpr int mo = Y::moff_of(cc), co = Y::coff_of(cc);
+                if (wg1 == k) {
+                  ok = true;
+                  moff = mo;
+                  coff = co;
+                }
+              }
+            });
+            if (ok) {
+              const double* brow = sM + moff + 8 * nt1 + lr;
+              double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+              for (int ks = 0; ks < KS1; ++ks) dmma8x8x4_f(c0, c1, a[ks], brow[Q * Q * min(4 * ks + lc, Q - 1)]);
+              if (sv && s1off[0] >= 0) sT1[s1off[0] + coff] = c0;
+              if (sv && s1off[1] >= 0) sT1[s1off[1] + coff] = c1;
+            }
+          });
+        });
+      } else {
         // ---- stage 1: thread <-> (combo, q1, piece of the q0 range); per side the M4 line times the i2 factor in
         // registers, then all slots of that side: T1[(slot, q0)][(combo, q1)] = sum_q2 Phi2[q2][i2] Phi2[q2][j2] M4
         constexpr int QH = 2, NSPL = (Q + QH - 1) / QH;
+        if (!SKIP(0))
         for (int item = tid; item < S::NCOMBO * Q * NSPL; item += NT) {
           const int half = item % NSPL, r = item / NSPL, q1 = r % Q, cc = r / Q;
           int g = 0, c = cc;
@@ -299,7 +411,7 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
             if (off[1] >= 0) sT2[off[1] + g * Q] = a1;
           }
         }
-      } else if (has2 && 8 * mt2 < rows2) {
+      } else if (has2 && 8 * mt2 < rows2 && !SKIP(4)) {
         const double* arow = sT1 + (8 * mt2 + lr) * LDA2 + lc;
         const double* brow = sB2 + lc * LDB2 + 8 * nt2 + lr;
         // all groups' accumulators first, the T2 stores afterwards: NG x TPW independent DMMA chains interleave
@@ -339,6 +451,7 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
 #pragma unroll
         for (int nt = 0; nt < Y::NT3; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
         const double* arow = sT2 + (8 * mt + lr) * LDA3 + lc;
+        if (!SKIP(5))
 #pragma unroll
         for (int ks = 0; ks < S::K3 / 4; ++ks) {
           const double a = arow[4 * ks];
@@ -363,6 +476,7 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
                 if (pk != -1) acc[nt][h] *= wI[(pk >> 16) & 15] * wJ[(pk >> 20) & 15];
               }
           }
+          if (!SKIP(3))
 #pragma unroll
           for (int nt = 0; nt < Y::NT3; ++nt)
 #pragma unroll
@@ -372,7 +486,7 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
             }
           // (the transposed entries straight from the registers -- scattered 8-byte stores, merged in L2 -- were measured:
           //  0.94x at p = 4 Poisson, 0.74x for the mass matrix; profiles/README.md)
-          if (j2 > i2) {
+          if (j2 > i2 && !SKIP(2)) {
             double* const Mb = sMB + (sa ? slot - 1 : slot - 2) * (NP * NP) + j1b * NP + i1b;
 #pragma unroll
             for (int nt = 0; nt < Y::NT3; ++nt)
@@ -390,12 +504,16 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
       // ---- mirror: block (j2, i2) = block (i2, j2)^T, complete runs of (p+1)^2 doubles per row of K_e.  No barrier after
       //      it: the next pass writes the buffer in its stage 3, two barriers away (T1 and T2 are not touched here)
       {
-        const int nm = paired ? NSLOT - 2 : na - 1;
-        for (int idx = tid; idx < nm * NP * NP; idx += NT) {
-          const int ms = idx / (NP * NP), rem = idx - ms * (NP * NP), jr = rem / NP, cidx = rem - jr * NP;
+        const int nm = SKIP(2) ? 0 : (paired ? NSLOT - 2 : na - 1);
+        // block by block (warp-uniform i2, j2); inside a block the thread's entries sit at offsets fixed for the whole kernel
+        for (int ms = 0; ms < nm; ++ms) {
           const bool sa = ms < na - 1;
           const int i2 = sa ? pass : i2b, j2 = i2 + 1 + (sa ? ms : ms - (na - 1));
-          K[(long long)(jr + NP * j2) * NB + NP * i2 + cidx] = sMB[idx];
+          double* const Kd = K + (NP * j2) * NB + NP * i2;
+          const double* const src = sMB + ms * (NP * NP);
+#pragma unroll
+          for (int k = 0; k < NCO; ++k)
+            if (NT * k + tid < NP * NP) Kd[cooff[k]] = src[NT * k + tid];
         }
       }
       IGAB_PT(5)
@@ -446,6 +564,13 @@ igab_status launch_sym_t(const PatchDev& Pd, SfWorkspace& ws, double fconst, lon
     KernelCfg kc;
     if (igab_status cst = kernel_config((const void*)gram_sym_kernel<P, Q, KIND>, Y::NT, sm, &kc)) return cst;
     const unsigned grid = (unsigned)std::min<long long>(nel, (long long)kc.blocksPerSm * kc.sms);
+#ifdef IGAB_SYM_EXPERIMENT
+    {
+      const char* sk = getenv("IGAB_SYM_SKIP");
+      const int v = sk ? atoi(sk) : 0;
+      cudaMemcpyToSymbolAsync(c_skip, &v, sizeof(int), 0, cudaMemcpyHostToDevice, stream);
+    }
+#endif
     gram_sym_kernel<P, Q, KIND><<<grid, Y::NT, sm, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],
                                                             w_dev[1], w_dev[2], fconst, Ke, fe, wtabs_of(Pd, ws));
     count_launch();
@@ -464,11 +589,11 @@ constexpr bool sym_fits(bool mass) {
 #define IGAB_SYM_LIST(X) X(3, 4) X(3, 5) X(4, 5) X(4, 6) X(4, 7) X(5, 6) X(5, 7)
 
 // Where the symmetric kernel is the default (measured on B200 against gram_sf_kernel, tools/sym_bench.py, element matrices/s):
-// Poisson p = 4: 1.10x (5 points), 1.17x (7 points); p = 3 with 5 points 1.10x; p = 5 1.25x; mass p = 5 1.09x.  Elsewhere
-// the contraction is too small a share of the element's time to pay for the mirror pass (Poisson p = 3 / 4 points 0.98x,
-// p = 4 / 6 points 1.00x; mass p = 3, 4: 0.83-0.94x) and gram_sf_kernel stays.  IGAB_GRAM_SYM=1 forces it wherever compiled.
+// Poisson p = 4: 1.32x (5 points), 1.23x (7 points); p = 3 with 5 points 1.17x; p = 5 1.31x.  Elsewhere the contraction is too
+// small a share of the element's time to pay for the mirror pass (Poisson p = 3 / 4 points 0.89x, p = 4 / 6 points 0.99x;
+// mass 0.74-0.92x) and gram_sf_kernel stays.  IGAB_GRAM_SYM=1 forces it wherever it is compiled.
 bool gram_sym_default(int p, int q, int kind) {
-  if (kind == IGAB_ASM_MASS) return p == 5 && q == 6;
+  if (kind != IGAB_ASM_POISSON) return false;
   return (p == 4 && (q == 5 || q == 7)) || (p == 3 && q == 5) || (p == 5 && q == 6);
 }
 
