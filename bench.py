@@ -96,7 +96,7 @@ def build_patch(n_gpus, scaling="weak"):
     return PD.thickCylinder(P_DEG, (LEVEL, LEVEL, LEVEL + extra))
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     """--impl reference: the reference's own CPU implementation of the path (oracle/_ref = the reference headers
     compiled where they lie; falls back to the pinned C restatement), all host threads, bounded sample per step."""
     if rank != 0:
@@ -129,7 +129,7 @@ def run_reference(args, rank, world):
     val = args.steps * nel * NQ / dt
     sample = "%d k-layer(s) of the C2 patch per step (%d elements, %d points), outputs %s" % (
         layers, nel, nel * NQ, "+".join(FIELDS))
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "quad-pt basis+Jacobian evals/sec", "value": val, "unit": "points/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -195,28 +195,46 @@ def bench_assembly(args, rank, world, local, barrier, dist):
             P.assemble(capi.ASM_POISSON, xi, ww, elem_begin=eb, elem_end=eb + per_call, Ke=ring[j & 1], fe=None,
                        stream=stream.cuda_stream)
 
-    one_pass()
-    barrier()
-    l0 = capi.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     npass = 3
-    e0.record(stream)
-    for _ in range(npass):
+
+    def timed_passes():
         one_pass()
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    launches = int(capi.launch_count() - l0)
+        barrier()
+        l0 = capi.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(npass):
+            one_pass()
+        e1.record(stream)
+        barrier()
+        t_ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([t_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_ms = float(t.item())
+        return t_ms, int(capi.launch_count() - l0)
+
+    # the default kernel: gram_sym_kernel<4,5,0> (upper block triangle + mirror, assemble_sym.cu)
+    ms, launches = timed_passes()
+    # beside it, the kernel that contracts every block (gram_sf_kernel<4,5,0>, round 1 / 2's default)
+    prev_sym = os.environ.get("IGAB_GRAM_SYM")
+    os.environ["IGAB_GRAM_SYM"] = "0"
+    ms_all, _ = timed_passes()
+    if prev_sym is None:
+        del os.environ["IGAB_GRAM_SYM"]
+    else:
+        os.environ["IGAB_GRAM_SYM"] = prev_sym
     nel = 64 ** 3 * world * npass
     flops_el = 125 * (2 * 3 * n * n + 2 * 9 * n)  # nq (2 s n^2 + 2 s^2 n)
-    exec_el = 3360 * 512 + 5 * 400 * 55  # DMMA instructions x 512 flop + stage-1 FMAs of gram_sf_kernel<4,5>
+    # executed per element: DMMA instructions x 512 flop + the scalar FP64 of stage 1
+    #   gram_sym_kernel<4,5,0>: stage 1 384 + stage 2 880 + stage 3 960 = 2,224 DMMA; 6,144 flop of operand products
+    #   gram_sf_kernel<4,5,0>:  stage 2 1,760 + stage 3 1,600 = 3,360 DMMA; stage 1 in FMAs, 0.11 MFLOP
+    exec_el = 2224 * 512 + 6144
+    exec_el_all = 3360 * 512 + 5 * 400 * 55
     dmma, dfma, src = measured_fp64_peak() if rank == 0 else (37.0, 34.0, "")
     achieved = flops_el * nel / world / (ms * 1e-3) / 1e12  # per GPU, dense-equivalent
     executed = achieved * exec_el / flops_el
+    executed_all = flops_el * nel / world / (ms_all * 1e-3) / 1e12 * exec_el_all / flops_el
     tr = _traffic().get("gram_sf_poisson_p4q5_bytes_per_element")
     del ring
     # end to end through the reference-facing call: host patch (handle creation = control-net H2D), igab_global_assemble
@@ -265,8 +283,14 @@ def bench_assembly(args, rank, world, local, barrier, dist):
             "config": {"workload": "C3: 3-D Poisson stiffness p=4 (n=125), 5^3 Gauss, 64x64x%d elements (64^3 per GPU)"
                                    % (64 * world)},
             "ms_per_pass": ms / npass, "gpu_launches": launches, "e2e": asm_e2e, "cpu_baseline": asm_cpu,
-            "roofline": {"bound": "tensor", "kernel": "gram_sf_kernel<4,5> (evaluation + sum-factorised Gram contraction, "
-                                                      "stages 2 and 3 on the FP64 tensor cores, one kernel)",
+            "all_blocks_kernel": {"kernel": "gram_sf_kernel<4,5,0> (IGAB_GRAM_SYM=0: every (i2, j2) block contracted; the "
+                                            "default before gram_sym_kernel)",
+                                  "value": nel / (ms_all * 1e-3), "unit": "elements/s",
+                                  "executed_flops_per_element": exec_el_all, "achieved": executed_all,
+                                  "frac": executed_all / dmma},
+            "roofline": {"bound": "tensor", "kernel": "gram_sym_kernel<4,5,0> (evaluation + sum-factorised Gram contraction of "
+                                                      "the upper block triangle, all three stages on the FP64 tensor cores, "
+                                                      "mirror from shared memory; one kernel)",
                          "achieved": executed, "peak": dmma, "unit": "TFLOP/s", "frac": executed / dmma,
                          "traffic": (tr * per_call if tr else None), "traffic_source": _traffic().get("source_gram_sf"),
                          "algorithmic_bytes_per_launch": 8.0 * n * n * per_call,
@@ -275,10 +299,15 @@ def bench_assembly(args, rank, world, local, barrier, dist):
                          "executed_flops_per_element": exec_el,
                          "dense_equivalent": achieved, "dense_equivalent_frac": achieved / dmma,
                          "hbm_write_gbs": 8.0 * n * n * nel / world / (ms * 1e-3) / 1e9,
-                         "note": "achieved = the flops the kernel EXECUTES per element (3,360 DMMA instructions x 512 + "
-                                 "0.11 MFLOP of scalar FMA = 1.83 MFLOP; DMMA and DFMA share one FP64 datapath) x elements "
+                         "equivalent_all_blocks": executed * exec_el_all / exec_el,
+                         "equivalent_all_blocks_frac": executed * exec_el_all / exec_el / dmma,
+                         "note": "achieved = the flops the kernel EXECUTES per element (2,224 DMMA instructions x 512 + "
+                                 "6 kFLOP of scalar FP64 = 1.14 MFLOP; DMMA and DFMA share one FP64 datapath) x elements "
                                  "/ time, against the DMMA rate measured live by tools/fp64_peak: `frac` is the share of "
-                                 "the FP64 tensor pipe the kernel sustains.  dense_equivalent = the SURVEY 8(d) count of "
+                                 "the FP64 tensor pipe the kernel sustains.  The kernel contracts only the blocks j2 >= i2 "
+                                 "of the symmetric matrix: it executes 0.62x the flops of gram_sf_kernel (all_blocks_kernel, "
+                                 "1.83 MFLOP per element, timed beside it), so its frac is lower at a higher throughput; "
+                                 "equivalent_all_blocks rates its throughput in that kernel's flops.  dense_equivalent = the SURVEY 8(d) count of "
                                  "the dense B^T D B contraction it replaces (12.0 MFLOP per element): a value above the "
                                  "peak is the algorithmic saving of sum factorisation, not a roofline fraction.  "
                                  "hbm_write_gbs is the K_e stream (125 kB per element); traffic = ncu dram bytes read + "
@@ -573,11 +602,21 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config lines (C1, C3 elasticity, C4, C5)")
     ap.add_argument("--no-multi-gpu", action="store_true", help="skip the timed NCCL reductions / interface-row exchange")
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: libraries write banners to file descriptor 1 (NCCL prints its
+    # version there when the first communicator is created), so everything before the final print goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(json_fd, (line + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
 
     import torch
@@ -827,7 +866,7 @@ def main():
             configs = [{"error": "%s: %s" % (type(ex).__name__, ex)}]
 
     if rank == 0:
-        print(json.dumps({
+        emit(json.dumps({
             "metric": "quad-pt basis+Jacobian evals/sec", "value": value, "unit": "points/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",

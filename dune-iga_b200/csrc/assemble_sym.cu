@@ -22,6 +22,28 @@ namespace igab {
 
 namespace {
 
+// Phase accounting (tools/sym_phase.py builds with -DIGAB_PHASE_TIMING): clock64 deltas accumulated in registers, one
+// atomicAdd per phase and warp at the END of the kernel (an atomic per phase and element distorts the picture)
+#ifdef IGAB_PHASE_TIMING
+#define SYM_PT_DECL unsigned long long pt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_last = 0;
+#define SYM_PT_BEGIN pt_last = clock64();
+#define SYM_PT(k)                                  \
+  {                                                \
+    const long long pt_now = clock64();            \
+    pt_acc[k] += (unsigned long long)(pt_now - pt_last); \
+    pt_last = pt_now;                              \
+  }
+#define SYM_PT_FLUSH                                                                 \
+  if ((threadIdx.x & 31) == 0) {                                                     \
+    for (int k = 0; k < 8; ++k) atomicAdd(&g_phase_ticks[k], pt_acc[k]);              \
+  }
+#else
+#define SYM_PT_DECL
+#define SYM_PT_BEGIN
+#define SYM_PT(k)
+#define SYM_PT_FLUSH
+#endif
+
 #ifdef IGAB_SYM_EXPERIMENT
 __constant__ int c_skip;   // timing experiments only (results are wrong): bit 0 stage 1, 1 B2 build, 2 mirror, 3 K_e stores, 4 stage 2, 5 stage 3 DMMA
 #define SKIP(b) (c_skip & (1 << (b)))
@@ -191,12 +213,13 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
 
   // a block takes a CONTIGUOUS run of elements: consecutive elements share e1 (and mostly e2), so the stage-2 operand B2,
   // which depends on direction 1 only, is rebuilt once per row of elements instead of once per element
+  SYM_PT_DECL
   const long long chunk = (nelem + gridDim.x - 1) / gridDim.x;
   const long long el_lo = blockIdx.x * chunk, el_hi = el_lo + chunk < nelem ? el_lo + chunk : nelem;
   int b2_e1 = -1;
   for (long long el = el_lo; el < el_hi; ++el) {
     const long long e = elem_begin + el;
-    IGAB_PT_BEGIN
+    SYM_PT_BEGIN
     if (useW) {
       // nobody reads sTw any more: the previous element's last stage 1 lies three barriers back; element_prepare's
       // barriers order these writes before the operand builds below
@@ -209,7 +232,7 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
     }
     // (the first barrier inside also ends the previous element's mirror copy-out, which reads the region sC aliases)
     element_prepare<P, Q, NT, CS>(Pd, e, tab0, tab1, tab2, w0, w1, w2, sT, sW, rX, rX + C::SZ_A, sC);
-    IGAB_PT(0)
+    SYM_PT(0)
     // ---- T1: the padding columns of every group must be zero (they meet zero rows of B2, but the scratch T1 aliases may
     //      hold anything); the other columns of the rows in use are written by stage 1, and rows are independent
     for (int idx = tid; idx < Y::M2P * Y::NPADC; idx += NT) {
@@ -280,7 +303,7 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
     __syncthreads();
 
     double* const K = Ke + el * (long long)NB * NB;
-    IGAB_PT(1)
+    SYM_PT(1)
     for (int pass = 0; pass < Y::NPASS; ++pass) {
       const int i2b = NB1 - 1 - pass, na = NB1 - pass;   // side a: i2 = pass, na slots; side b: i2 = i2b, pass + 1 slots
       const bool paired = i2b > pass;
@@ -291,40 +314,56 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
         constexpr int KS1 = (Q + 3) / 4;
         const bool sv = lr < nslots, sa1 = lr < na;
         const int i2 = sv ? (sa1 ? pass : i2b) : 0, j2 = sv ? i2 + (sa1 ? lr : lr - na) : 0;
+        // the table entries every variant is made of, one round of loads: tv[ks][0..3] = Phi2[q2][i2][0 / 1], Phi2[q2][j2][0 / 1]
+        double tv[KS1][4];
+#pragma unroll
+        for (int ks = 0; ks < KS1; ++ks) {
+          const int q2 = min(4 * ks + lc, Q - 1);
+          const bool on = sv && 4 * ks + lc < Q;
+          const double2 ti = lds2f(sTc + 2 * TAB + (q2 * NB1 + i2) * 2), tj = lds2f(sTc + 2 * TAB + (q2 * NB1 + j2) * 2);
+          tv[ks][0] = on ? ti.x : 0.0;
+          tv[ks][1] = on ? ti.y : 0.0;
+          tv[ks][2] = tj.x;
+          tv[ks][3] = tj.y;
+        }
         if (!SKIP(0))
         static_for<(MASS ? 1 : 4)>([&](auto vc) {
           constexpr int v = decltype(vc)::value;
+          constexpr int NIT = (Y::var_count(v) + WG1 - 1) / WG1;
           double a[KS1];
 #pragma unroll
-          for (int ks = 0; ks < KS1; ++ks) {
-            const int q2 = 4 * ks + lc;
-            a[ks] = (sv && q2 < Q) ? sTc[2 * TAB + (min(q2, Q - 1) * NB1 + i2) * 2 + (v & 1)] *
-                                         sTc[2 * TAB + (min(q2, Q - 1) * NB1 + j2) * 2 + (v >> 1)]
-                                   : 0.0;
-          }
-          static_for<(Y::var_count(v) + WG1 - 1) / WG1>([&](auto itc) {
+          for (int ks = 0; ks < KS1; ++ks) a[ks] = tv[ks][v & 1] * tv[ks][2 + (v >> 1)];
+          // all rounds' products first, the T1 stores afterwards: a shared store between two rounds would pin the next
+          // round's operand loads behind it (the compiler cannot tell T1 from the point matrices)
+          double cacc[NIT][2];
+          int coffs[NIT];
+          static_for<NIT>([&](auto itc) {
             constexpr int it = decltype(itc)::value;
-            int moff = 0, coff = 0;
-            bool ok = false;
+            int moff = -1, coff = 0;
             static_for<WG1>([&](auto kc) {
               constexpr int k = decltype(kc)::value;
               constexpr int cc = Y::var_item(v, it * WG1 + k);
               if constexpr (cc >= 0) {
                 constexpr int mo = Y::moff_of(cc), co = Y::coff_of(cc);
                 if (wg1 == k) {
-                  ok = true;
                   moff = mo;
                   coff = co;
                 }
               }
             });
-            if (ok) {
+            coffs[it] = moff >= 0 ? coff : -1;
+            cacc[it][0] = cacc[it][1] = 0.0;
+            if (moff >= 0) {
               const double* brow = sM + moff + 8 * nt1 + lr;
-              double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-              for (int ks = 0; ks < KS1; ++ks) dmma8x8x4_f(c0, c1, a[ks], brow[Q * Q * min(4 * ks + lc, Q - 1)]);
-              if (sv && s1off[0] >= 0) sT1[s1off[0] + coff] = c0;
-              if (sv && s1off[1] >= 0) sT1[s1off[1] + coff] = c1;
+              for (int ks = 0; ks < KS1; ++ks) dmma8x8x4_f(cacc[it][0], cacc[it][1], a[ks], brow[Q * Q * min(4 * ks + lc, Q - 1)]);
+            }
+          });
+          static_for<NIT>([&](auto itc) {
+            constexpr int it = decltype(itc)::value;
+            if (coffs[it] >= 0 && sv) {
+              if (s1off[0] >= 0) sT1[s1off[0] + coffs[it]] = cacc[it][0];
+              if (s1off[1] >= 0) sT1[s1off[1] + coffs[it]] = cacc[it][1];
             }
           });
         });
@@ -384,9 +423,9 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
           }
         }
       }
-      IGAB_PT(2)
+      SYM_PT(2)
       __syncthreads();
-      IGAB_PT(6)
+      SYM_PT(6)
       // ---- stage 2: C_g[(slot,q0)][pi1] = sum_{k in g} T1[.][k] B2[k][.]  ->  T2[pi1 + NP slot][g Q + q0]
       if constexpr (Y::GEN2) {
         for (int tile = warp; tile < Y::MT2 * Y::NT2; tile += Y::NWARP) {
@@ -438,9 +477,9 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
                 if (t2off[s][h] >= 0) sT2[t2off[s][h] + g * Q] = acc[g][s][h];
         }
       }
-      IGAB_PT(3)
+      SYM_PT(3)
       __syncthreads();
-      IGAB_PT(6)
+      SYM_PT(6)
       // ---- stage 3: K[(j1,i1,slot)][pi0] = sum_{(g,q0)} T2 B3: to global memory (with the weights w_i w_j on the general
       //      path), and the strictly upper blocks (j2 > i2) also into the mirror buffer, transposed
 #pragma unroll
@@ -498,9 +537,9 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
           }
         }
       }
-      IGAB_PT(4)
+      SYM_PT(4)
       __syncthreads();
-      IGAB_PT(6)
+      SYM_PT(6)
       // ---- mirror: block (j2, i2) = block (i2, j2)^T, complete runs of (p+1)^2 doubles per row of K_e.  No barrier after
       //      it: the next pass writes the buffer in its stage 3, two barriers away (T1 and T2 are not touched here)
       {
@@ -516,7 +555,7 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
             if (NT * k + tid < NP * NP) Kd[cooff[k]] = src[NT * k + tid];
         }
       }
-      IGAB_PT(5)
+      SYM_PT(5)
     }
     // ---- load vector f_e[i] = sum_q w detJ R_i fconst  (poisson.py:79)
     if (fe) {
@@ -549,8 +588,9 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
         fe[el * NB + i] = f;
       }
     }
-    IGAB_PT(7)
+    SYM_PT(7)
   }
+  SYM_PT_FLUSH
 }
 
 template <int P, int Q, int KIND>
