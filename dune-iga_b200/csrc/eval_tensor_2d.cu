@@ -95,16 +95,31 @@ __device__ __forceinline__ constexpr int al0(int a) { return a == 1 ? 1 : (a == 
 __device__ __forceinline__ constexpr int al1(int a) { return a == 2 ? 1 : (a == 4 ? 2 : (a == 5 ? 1 : 0)); }
 
 // stage one field row-by-row (thread = point) and flush the warp's contiguous run
-template <int W, int STRIDE>
+template <int W, int STRIDE, bool FAST>
 __device__ __forceinline__ void flush_field(double* __restrict__ slab, const double (&row)[W], double* __restrict__ g,
                                             int lane, int nvalid) {
 #pragma unroll
   for (int k = 0; k < W; ++k) slab[lane * STRIDE + k] = row[k];
   __syncwarp();
-  const int n = nvalid * W;
-  for (int j = lane; j < n; j += 32) {
-    const int r = j / W, k = j - r * W;
-    g[j] = slab[r * STRIDE + k];
+  // (odd widths have STRIDE = W: the slab is dense, entry j sits at slab[j]; even widths need j / W per entry and are unrolled
+  //  for FAST = p >= 3 only: in the 96-register p = 2 instantiations that address arithmetic spilled and cost 5-10 %)
+  if ((STRIDE == W || FAST) && nvalid == 32) {
+    // full chunk (all but the last one of a launch): W fully unrolled 256-byte stores, entry j = lane + 32 it of the run
+    // sits at slab[j + (j / W) (STRIDE - W)] -- no loop counter, no division per entry (the general loop below spent 12
+    // instructions per stored double: 39 % of the kernel's instructions at config C5, ncu source view)
+#pragma unroll
+    for (int it = 0; it < W; ++it) {
+      const int j = lane + 32 * it;
+      g[j] = slab[j + (j / W) * (STRIDE - W)];
+      // four loads in flight, not W: the fully hoisted version spilled in the 96-register instantiations (p = 2)
+      if (it % 4 == 3) asm volatile("" ::: "memory");
+    }
+  } else {
+    const int n = nvalid * W;
+    for (int j = lane; j < n; j += 32) {
+      const int r = j / W, k = j - r * W;
+      g[j] = slab[r * STRIDE + k];
+    }
   }
   __syncwarp();
 }
@@ -211,7 +226,7 @@ __global__ void __launch_bounds__(128, (ORDER >= 2 ? 3 : (P <= 2 ? 5 : (P >= 4 ?
     for (int i1 = 0; i1 < NB1; ++i1)
 #pragma unroll
       for (int i0 = 0; i0 < NB1; ++i0) row[i0 + NB1 * i1] = n0[0][i0] * n1[0][i1] * wv[i0 + NB1 * i1] * invW;
-    flush_field<NB, C::STRIDE>(slab, row, out.N + pt0 * NB, lane, nvalid);
+    flush_field<NB, C::STRIDE, (P >= 3)>(slab, row, out.N + pt0 * NB, lane, nvalid);
   }
   if constexpr (ORDER >= 1) {
     if (out.dN || (ORDER >= 2 && out.d2N)) {
@@ -234,9 +249,9 @@ __global__ void __launch_bounds__(128, (ORDER >= 2 ? 3 : (P <= 2 ? 5 : (P >= 4 ?
             rowH[NH * i + 2] = (n0[1][i0] * n1[1][i1] * w - Wa[1] * R1 - Wa[2] * R0 - Wa[5] * R) * invW;
           }
         }
-      if (out.dN) flush_field<NB * 2, C::STRIDE>(slab, rowD, out.dN + pt0 * NB * 2, lane, nvalid);
+      if (out.dN) flush_field<NB * 2, C::STRIDE, (P >= 3)>(slab, rowD, out.dN + pt0 * NB * 2, lane, nvalid);
       if constexpr (ORDER >= 2) {
-        if (out.d2N) flush_field<NB * NH, C::STRIDE>(slab, rowH, out.d2N + pt0 * NB * NH, lane, nvalid);
+        if (out.d2N) flush_field<NB * NH, C::STRIDE, (P >= 3)>(slab, rowH, out.d2N + pt0 * NB * NH, lane, nvalid);
       }
     }
   }
@@ -244,7 +259,7 @@ __global__ void __launch_bounds__(128, (ORDER >= 2 ? 3 : (P <= 2 ? 5 : (P >= 4 ?
     double row[DW];
 #pragma unroll
     for (int c = 0; c < DW; ++c) row[c] = x[c];
-    flush_field<DW, C::STRIDE>(slab, row, out.x + pt0 * DW, lane, nvalid);
+    flush_field<DW, C::STRIDE, (P >= 3)>(slab, row, out.x + pt0 * DW, lane, nvalid);
   }
   if constexpr (ORDER >= 1) {
     if (out.Jt) {
@@ -253,7 +268,7 @@ __global__ void __launch_bounds__(128, (ORDER >= 2 ? 3 : (P <= 2 ? 5 : (P >= 4 ?
       for (int d = 0; d < 2; ++d)
 #pragma unroll
         for (int c = 0; c < DW; ++c) row[d * DW + c] = J[d][c];
-      flush_field<2 * DW, C::STRIDE>(slab, row, out.Jt + pt0 * 2 * DW, lane, nvalid);
+      flush_field<2 * DW, C::STRIDE, (P >= 3)>(slab, row, out.Jt + pt0 * 2 * DW, lane, nvalid);
     }
     double det;
     if constexpr (DW == 2) {
@@ -280,7 +295,7 @@ __global__ void __launch_bounds__(128, (ORDER >= 2 ? 3 : (P <= 2 ? 5 : (P >= 4 ?
         row[c * 2 + 0] = (J[0][c] * g11 - J[1][c] * g01) * idet;
         row[c * 2 + 1] = (J[1][c] * g00 - J[0][c] * g01) * idet;
       }
-      flush_field<2 * DW, C::STRIDE>(slab, row, out.JinvT + pt0 * 2 * DW, lane, nvalid);
+      flush_field<2 * DW, C::STRIDE, (P >= 3)>(slab, row, out.JinvT + pt0 * 2 * DW, lane, nvalid);
     }
   }
   if constexpr (ORDER >= 2) {
@@ -290,7 +305,7 @@ __global__ void __launch_bounds__(128, (ORDER >= 2 ? 3 : (P <= 2 ? 5 : (P >= 4 ?
       for (int r = 0; r < NH; ++r)
 #pragma unroll
         for (int c = 0; c < DW; ++c) row[r * DW + c] = H[r][c];
-      flush_field<NH * DW, C::STRIDE>(slab, row, out.H + pt0 * NH * DW, lane, nvalid);
+      flush_field<NH * DW, C::STRIDE, (P >= 3)>(slab, row, out.H + pt0 * NH * DW, lane, nvalid);
     }
   }
   }  // chunk loop
