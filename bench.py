@@ -235,7 +235,7 @@ def bench_assembly(args, rank, world, local, barrier, dist):
     achieved = flops_el * nel / world / (ms * 1e-3) / 1e12  # per GPU, dense-equivalent
     executed = achieved * exec_el / flops_el
     executed_all = flops_el * nel / world / (ms_all * 1e-3) / 1e12 * exec_el_all / flops_el
-    tr = _traffic().get("gram_sf_poisson_p4q5_bytes_per_element")
+    tr = _traffic().get("gram_sym_poisson_p4q5_bytes_per_element")
     del ring
     # end to end through the reference-facing call: host patch (handle creation = control-net H2D), igab_global_assemble
     # (element matrices in device chunks, CSR gather), CSR values + load vector back to host memory
@@ -292,7 +292,7 @@ def bench_assembly(args, rank, world, local, barrier, dist):
                                                       "the upper block triangle, all three stages on the FP64 tensor cores, "
                                                       "mirror from shared memory; one kernel)",
                          "achieved": executed, "peak": dmma, "unit": "TFLOP/s", "frac": executed / dmma,
-                         "traffic": (tr * per_call if tr else None), "traffic_source": _traffic().get("source_gram_sf"),
+                         "traffic": (tr * per_call if tr else None), "traffic_source": _traffic().get("source_gram_sym"),
                          "algorithmic_bytes_per_launch": 8.0 * n * n * per_call,
                          "peak_source": src, "dfma_peak": dfma,
                          "algorithmic_flops_per_element": flops_el,
