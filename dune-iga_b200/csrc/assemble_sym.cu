@@ -14,7 +14,6 @@
 // Slot s of a pass: s < na = p+1-a  ->  (i2, j2) = (a, a + s);  otherwise (b, b + s - na).
 #include <algorithm>
 #include <cstdlib>
-#include <utility>
 
 #include "gram_common.cuh"
 
@@ -51,18 +50,6 @@ __constant__ int c_skip;   // timing experiments only (results are wrong): bit 0
 #define SKIP(b) false
 #endif
 
-// compile-time loop: f(std::integral_constant<int, 0>{}), ..., f(std::integral_constant<int, N - 1>{}) -- the loop index is a
-// constant EXPRESSION inside f (an unrolled run-time loop leaves the constexpr table look-ups below to the optimiser,
-// which kept them as code: 12 k warp instructions per element)
-template <class F, int... I>
-__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) {
-  (f(std::integral_constant<int, I>{}), ...);
-}
-template <int N, class F>
-__device__ __forceinline__ void static_for(F&& f) {
-  static_for_impl(static_cast<F&&>(f), std::make_integer_sequence<int, N>{});
-}
-
 template <int P, int Q, int KIND>
 struct YCfg {
   using S = SCfg<P, Q, KIND>;
@@ -85,27 +72,8 @@ struct YCfg {
     return n;
   }
   static constexpr int NPADC = npadc();
-  // stage 1 on the tensor cores: per combo (beta, gamma) a small product  [slot] x [q2] x [(q1, q0)]  whose A operand
-  // Phi2[q2][i2][b2(beta)] Phi2[q2][j2][b2(gamma)] exists in four variants v = b2(beta) + 2 b2(gamma), b2(.) = (. == 3)
-  static constexpr int g_of(int cc) { return MASS ? 0 : (cc >= 15 ? 3 : (cc >= 12 ? 2 : (cc >= 9 ? 1 : 0))); }
-  static constexpr int c_of(int cc) { return MASS ? 0 : (cc >= 15 ? 0 : (cc >= 12 ? cc - 12 : (cc >= 9 ? cc - 9 : cc))); }
-  static constexpr int var_of(int cc) {
-    return (S::beta_of(g_of(cc), c_of(cc)) == 3 ? 1 : 0) + (S::gamma_of(g_of(cc), c_of(cc)) == 3 ? 2 : 0);
-  }
-  static constexpr int var_count(int v) {
-    int n = 0;
-    for (int cc = 0; cc < S::NCOMBO; ++cc) n += var_of(cc) == v ? 1 : 0;
-    return n;
-  }
-  static constexpr int var_item(int v, int k) {  // k-th combo of variant v, -1 past the end
-    for (int cc = 0; cc < S::NCOMBO; ++cc)
-      if (var_of(cc) == v && k-- == 0) return cc;
-    return -1;
-  }
-  static constexpr int moff_of(int cc) { return cc < 0 ? 0 : S::usym(S::beta_of(g_of(cc), c_of(cc)), S::gamma_of(g_of(cc), c_of(cc))) * NQ; }
-  static constexpr int coff_of(int cc) { return cc < 0 ? 0 : S::goff(g_of(cc)) + c_of(cc) * Q; }
-  static constexpr int NTQ = S::r8(Q * Q) / 8;   // 8-column tiles over (q1, q0)
-  static constexpr bool S1_DMMA = NWARP % NTQ == 0 && NSLOT <= 8;
+  using S1 = S1Cfg<P, Q, KIND>;
+  static constexpr bool S1_DMMA = S1::OK && NSLOT <= 8;
   static constexpr int SZ_X = F::ev(imax(F::SZ_A + F::SZ_S2, SZ_T1));
   static constexpr int SZ_M = S::SZ_M;
   static constexpr int SZ_T2 = F::ev(imax(M3P * LDA3, K3 * LDB2));
@@ -194,16 +162,9 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
     r3[u] = mp < Y::M3 ? (NB1 * (n1 / NB1)) | ((NB1 * (n1 % NB1)) << 8) | (slot << 16) : -1;
   }
 
-  // stage 1 (tensor-core version): warp <-> column tile nt1 of (q1, q0) and a share wg of the combos; lane (lr, lc) holds
-  // C[slot = lr][n = 8 nt1 + 2 lc + h], n = q1 Q + q0  ->  T1[(slot Q + q0)][combo columns + q1]
-  constexpr int WG1 = Y::S1_DMMA ? Y::NWARP / Y::NTQ : 1;
-  const int nt1 = warp % Y::NTQ, wg1 = warp / Y::NTQ;
+  // stage 1 (tensor-core version, stage1_dmma in gram_common.cuh): where this lane's two accumulator columns go in T1
   int s1off[2];
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int n = 8 * nt1 + 2 * lc + h;
-    s1off[h] = (n < Q * Q && lr < NSLOT) ? (lr * Q + n % Q) * LDA2 + n / Q : -1;
-  }
+  S1Cfg<P, Q, KIND>::store_offsets(warp, lane, NSLOT, LDA2, s1off);
 
   // mirror copy-out: entry NT k + tid of a (p+1)^2 x (p+1)^2 block is (row, c) -> offset row NB + c in K_e
   constexpr int NCO = (NP * NP + NT - 1) / NT;
@@ -311,62 +272,9 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
       const int rows2 = nslots * Q, rows3 = nslots * NP;
       if constexpr (Y::S1_DMMA) {
         // ---- stage 1 on the tensor cores: T1[(slot, q0)][(combo, q1)] = sum_q2 A_v[slot][q2] M4_combo[q2][(q1, q0)]
-        constexpr int KS1 = (Q + 3) / 4;
         const bool sv = lr < nslots, sa1 = lr < na;
         const int i2 = sv ? (sa1 ? pass : i2b) : 0, j2 = sv ? i2 + (sa1 ? lr : lr - na) : 0;
-        // the table entries every variant is made of, one round of loads: tv[ks][0..3] = Phi2[q2][i2][0 / 1], Phi2[q2][j2][0 / 1]
-        double tv[KS1][4];
-#pragma unroll
-        for (int ks = 0; ks < KS1; ++ks) {
-          const int q2 = min(4 * ks + lc, Q - 1);
-          const bool on = sv && 4 * ks + lc < Q;
-          const double2 ti = lds2f(sTc + 2 * TAB + (q2 * NB1 + i2) * 2), tj = lds2f(sTc + 2 * TAB + (q2 * NB1 + j2) * 2);
-          tv[ks][0] = on ? ti.x : 0.0;
-          tv[ks][1] = on ? ti.y : 0.0;
-          tv[ks][2] = tj.x;
-          tv[ks][3] = tj.y;
-        }
-        if (!SKIP(0))
-        static_for<(MASS ? 1 : 4)>([&](auto vc) {
-          constexpr int v = decltype(vc)::value;
-          constexpr int NIT = (Y::var_count(v) + WG1 - 1) / WG1;
-          double a[KS1];
-#pragma unroll
-          for (int ks = 0; ks < KS1; ++ks) a[ks] = tv[ks][v & 1] * tv[ks][2 + (v >> 1)];
-          // all rounds' products first, the T1 stores afterwards: a shared store between two rounds would pin the next
-          // round's operand loads behind it (the compiler cannot tell T1 from the point matrices)
-          double cacc[NIT][2];
-          int coffs[NIT];
-          static_for<NIT>([&](auto itc) {
-            constexpr int it = decltype(itc)::value;
-            int moff = -1, coff = 0;
-            static_for<WG1>([&](auto kc) {
-              constexpr int k = decltype(kc)::value;
-              constexpr int cc = Y::var_item(v, it * WG1 + k);
-              if constexpr (cc >= 0) {
-                constexpr int mo = Y::moff_of(cc), co = Y::coff_of(cc);
-                if (wg1 == k) {
-                  moff = mo;
-                  coff = co;
-                }
-              }
-            });
-            coffs[it] = moff >= 0 ? coff : -1;
-            cacc[it][0] = cacc[it][1] = 0.0;
-            if (moff >= 0) {
-              const double* brow = sM + moff + 8 * nt1 + lr;
-#pragma unroll
-              for (int ks = 0; ks < KS1; ++ks) dmma8x8x4_f(cacc[it][0], cacc[it][1], a[ks], brow[Q * Q * min(4 * ks + lc, Q - 1)]);
-            }
-          });
-          static_for<NIT>([&](auto itc) {
-            constexpr int it = decltype(itc)::value;
-            if (coffs[it] >= 0 && sv) {
-              if (s1off[0] >= 0) sT1[s1off[0] + coffs[it]] = cacc[it][0];
-              if (s1off[1] >= 0) sT1[s1off[1] + coffs[it]] = cacc[it][1];
-            }
-          });
-        });
+        if (!SKIP(0)) stage1_dmma<P, Q, KIND>(warp, lane, i2, j2, sv, s1off, sTc, sM, sT1);
       } else {
         // ---- stage 1: thread <-> (combo, q1, piece of the q0 range); per side the M4 line times the i2 factor in
         // registers, then all slots of that side: T1[(slot, q0)][(combo, q1)] = sum_q2 Phi2[q2][i2] Phi2[q2][j2] M4

@@ -2,6 +2,8 @@
 // tensor-core instruction, the shared-memory configuration of the fused front end, element_prepare (tables + control
 // points + sum-factorised geometry + per-point constants) and the group layout of the sum-factorised contraction.
 #pragma once
+#include <utility>
+
 #include "igab_internal.cuh"
 #include "sf_geometry.cuh"
 
@@ -202,6 +204,124 @@ struct SCfg {
   }
 };
 
+
+// compile-time loop: f(std::integral_constant<int, 0>{}), ..., f(std::integral_constant<int, N - 1>{}) -- the loop index is a
+// constant EXPRESSION inside f (an unrolled run-time loop leaves the constexpr table look-ups below to the optimiser,
+// which kept them as code: 12 k warp instructions per element)
+template <class F, int... I>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) {
+  (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  static_for_impl(static_cast<F&&>(f), std::make_integer_sequence<int, N>{});
+}
+
+// Stage 1 of the sum-factorised contraction on the tensor cores (gram_sym_kernel, gram_sf_kernel, gram_ws_kernel):
+//   T1[(slot, q0)][(combo, q1)] = sum_q2 Phi2[q2][i2][b2(beta)] Phi2[q2][j2][b2(gamma)] M4_combo[q2][(q1, q0)],   b2(.) = (. == 3)
+// per combo (beta, gamma) a small product [slot] x [q2] x [(q1, q0)] whose A operand exists in four variants
+// v = b2(beta) + 2 b2(gamma); a slot is a pair (i2, j2) -- all j2 of one i2 in the kernels that contract every block.
+// Eight warps: warp <-> column tile nt of (q1, q0) and a share wg of the combos; lane (lr, lc) holds
+// C[slot = lr][n = 8 nt + 2 lc + h], n = q1 Q + q0.  Needs the number of column tiles to divide 8 (Q = 4, 5).
+template <int P, int Q, int KIND>
+struct S1Cfg {
+  using S = SCfg<P, Q, KIND>;
+  static constexpr bool MASS = KIND == 1;
+  static constexpr int NQ = S::NQ;
+  static constexpr int g_of(int cc) { return MASS ? 0 : (cc >= 15 ? 3 : (cc >= 12 ? 2 : (cc >= 9 ? 1 : 0))); }
+  static constexpr int c_of(int cc) { return MASS ? 0 : (cc >= 15 ? 0 : (cc >= 12 ? cc - 12 : (cc >= 9 ? cc - 9 : cc))); }
+  static constexpr int var_of(int cc) {
+    return (S::beta_of(g_of(cc), c_of(cc)) == 3 ? 1 : 0) + (S::gamma_of(g_of(cc), c_of(cc)) == 3 ? 2 : 0);
+  }
+  static constexpr int var_count(int v) {
+    int n = 0;
+    for (int cc = 0; cc < S::NCOMBO; ++cc) n += var_of(cc) == v ? 1 : 0;
+    return n;
+  }
+  static constexpr int var_item(int v, int k) {  // k-th combo of variant v, -1 past the end
+    for (int cc = 0; cc < S::NCOMBO; ++cc)
+      if (var_of(cc) == v && k-- == 0) return cc;
+    return -1;
+  }
+  static constexpr int moff_of(int cc) { return cc < 0 ? 0 : S::usym(S::beta_of(g_of(cc), c_of(cc)), S::gamma_of(g_of(cc), c_of(cc))) * NQ; }
+  static constexpr int coff_of(int cc) { return cc < 0 ? 0 : S::goff(g_of(cc)) + c_of(cc) * Q; }
+  static constexpr int NW = 8;                   // warps that share the stage
+  static constexpr int NTQ = S::r8(Q * Q) / 8;   // 8-column tiles over (q1, q0)
+  static constexpr bool OK = NW % NTQ == 0;
+  static constexpr int WG = OK ? NW / NTQ : 1;
+  // gw = index of the warp among the eight; rows lr >= nslot_max are never stored
+  __device__ static __forceinline__ void store_offsets(int gw, int lane, int nslot_max, int lda2, int (&s1off)[2]) {
+    const int lr = lane >> 2, lc = lane & 3, nt = gw % NTQ;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n = 8 * nt + 2 * lc + h;
+      s1off[h] = (n < Q * Q && lr < nslot_max) ? (lr * Q + n % Q) * lda2 + n / Q : -1;
+    }
+  }
+};
+
+// (i2, j2) = the pair of this lane's slot lr, sv = slot in use; sTc = the (weighted) tables, sM = point matrices [u][q2][q1][q0]
+template <int P, int Q, int KIND>
+__device__ __forceinline__ void stage1_dmma(int gw, int lane, int i2, int j2, bool sv, const int (&s1off)[2],
+                                            const double* sTc, const double* sM, double* sT1) {
+  using Y = S1Cfg<P, Q, KIND>;
+  constexpr bool MASS = Y::MASS;
+  constexpr int NB1 = P + 1, TAB = FCfg<P, Q>::TAB, WG1 = Y::WG, KS1 = (Q + 3) / 4;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int nt1 = gw % Y::NTQ, wg1 = gw / Y::NTQ;
+  // the table entries every variant is made of, one round of loads: tv[ks][0..3] = Phi2[q2][i2][0 / 1], Phi2[q2][j2][0 / 1]
+  double tv[KS1][4];
+#pragma unroll
+  for (int ks = 0; ks < KS1; ++ks) {
+    const int q2 = min(4 * ks + lc, Q - 1);
+    const bool on = sv && 4 * ks + lc < Q;
+    const double2 ti = lds2f(sTc + 2 * TAB + (q2 * NB1 + i2) * 2), tj = lds2f(sTc + 2 * TAB + (q2 * NB1 + j2) * 2);
+    tv[ks][0] = on ? ti.x : 0.0;
+    tv[ks][1] = on ? ti.y : 0.0;
+    tv[ks][2] = tj.x;
+    tv[ks][3] = tj.y;
+  }
+  static_for<(MASS ? 1 : 4)>([&](auto vc) {
+    constexpr int v = decltype(vc)::value;
+    constexpr int NIT = (Y::var_count(v) + WG1 - 1) / WG1;
+    double a[KS1];
+#pragma unroll
+    for (int ks = 0; ks < KS1; ++ks) a[ks] = tv[ks][v & 1] * tv[ks][2 + (v >> 1)];
+    // all rounds' products first, the T1 stores afterwards: a shared store between two rounds would pin the next
+    // round's operand loads behind it (the compiler cannot tell T1 from the point matrices)
+    double cacc[NIT][2];
+    int coffs[NIT];
+    static_for<NIT>([&](auto itc) {
+      constexpr int it = decltype(itc)::value;
+      int moff = -1, coff = 0;
+      static_for<WG1>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        constexpr int cc = Y::var_item(v, it * WG1 + k);
+        if constexpr (cc >= 0) {
+          constexpr int mo = Y::moff_of(cc), co = Y::coff_of(cc);
+          if (wg1 == k) {
+            moff = mo;
+            coff = co;
+          }
+        }
+      });
+      coffs[it] = moff >= 0 ? coff : -1;
+      cacc[it][0] = cacc[it][1] = 0.0;
+      if (moff >= 0) {
+        const double* brow = sM + moff + 8 * nt1 + lr;
+#pragma unroll
+        for (int ks = 0; ks < KS1; ++ks) dmma8x8x4_f(cacc[it][0], cacc[it][1], a[ks], brow[Q * Q * min(4 * ks + lc, Q - 1)]);
+      }
+    });
+    static_for<NIT>([&](auto itc) {
+      constexpr int it = decltype(itc)::value;
+      if (coffs[it] >= 0 && sv) {
+        if (s1off[0] >= 0) sT1[s1off[0] + coffs[it]] = cacc[it][0];
+        if (s1off[1] >= 0) sT1[s1off[1] + coffs[it]] = cacc[it][1];
+      }
+    });
+  });
+}
 
 inline WTabs wtabs_of(const PatchDev& Pd, const SfWorkspace& ws) {
   if (Pd.wfac[0] && ws.wvalid && ws.wuse) return WTabs{ws.wtab[0], ws.wtab[1], ws.wtab[2]};
