@@ -1633,7 +1633,27 @@ igab_status igab_global_assemble(igab_patch* p, int kind, const double* D, doubl
   int64_t nrows = 0, nnz = 0;
   igab_status st = csr_pattern(p, ncomp, &nrows, &nnz, nullptr, nullptr, IGAB_HOST, stream);
   if (st) return st;
-  long long chunk = std::max(1LL, (1024LL << 20) / (8 * n2));  // <= 1 GB of element matrices per chunk
+  // Element matrices per chunk.  Every chunk re-reads and re-writes the CSR rows it shares with its neighbours (p layers
+  // of DOFs on either side), so large chunks pay: measured on the C3 patch 42.7 ms with 1 GB chunks, 31.1 ms with 8 GB
+  // (tools/ga_chunk_big.py).  Up to 8 GB, at most a quarter of the free device memory (this handle's scratch counted as
+  // free), whole layers of elements; host outputs keep at least four chunks, so that the D2H copy of finished rows
+  // overlaps the assembly of later chunks.
+  const long long gb1 = std::max(1LL, (1024LL << 20) / (8 * n2));
+  long long chunk = 8 * gb1;
+  {
+    size_t freeB = 0, totalB = 0;
+    if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
+      const long long avail = (long long)freeB + (long long)p->ga_cap * 8;
+      chunk = std::min(chunk, std::max(gb1 / 4 + 1, avail / 4 / (8 * n2)));
+    } else {
+      cudaGetLastError();
+      chunk = gb1;
+    }
+    if (space == IGAB_HOST && !p->d_trim) chunk = std::min(chunk, std::max(gb1, (nrange + 3) / 4));
+    long long layer = 1;
+    for (int d = 0; d + 1 < p->dev.dim; ++d) layer *= p->dev.nel[d];
+    if (chunk > layer) chunk -= chunk % layer;
+  }
   if (const char* env = getenv("IGAB_GA_CHUNK_ELEMS")) chunk = std::max(1L, atol(env));  // test knob
   chunk = std::min(chunk, std::max(1LL, nrange));
   double *dK = nullptr, *dF = nullptr, *dV = values, *dB = b, *dKt = nullptr, *dFt = nullptr, *dXi = nullptr, *dW = nullptr;
