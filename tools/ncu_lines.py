@@ -14,11 +14,20 @@ def main():
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name",
                           "regex:" + kern], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
-    blocks, cur = [], None
+    # the source page is a sequence of (file, function) blocks; all files of ONE launch of a function are merged, a file
+    # path seen twice for the same function starts the next launch
+    blocks, cur, fpath = [], None, ""
     for r in rows:
+        if r and r[0] == "File Path":
+            fpath = r[1].split("/")[-1] if len(r) > 1 else ""
+            continue
         if r and r[0] == "Function Name":
-            cur = {"name": r[1], "rows": [], "hdr": None, "file": None}
-            blocks.append(cur)
+            if cur is not None and cur["name"] == r[1] and fpath not in cur["files"]:
+                cur["files"].add(fpath)
+                cur["file"] = fpath
+            else:
+                cur = {"name": r[1], "rows": [], "hdr": None, "file": fpath, "files": {fpath}}
+                blocks.append(cur)
             continue
         if cur is None:
             continue
@@ -26,7 +35,7 @@ def main():
             cur["hdr"] = r
             continue
         if cur["hdr"] and len(r) == len(cur["hdr"]):
-            cur["rows"].append(r)
+            cur["rows"].append([cur["file"] + ":" + r[0]] + r[1:])
     done = set()
     for b in blocks:
         if not b["rows"] or b["name"] in done:
@@ -53,7 +62,7 @@ def main():
         print("stalls: " + ", ".join("%s %.1f%%" % (k[6:], 100 * v / max(ts, 1)) for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:8]))
         for l, v in sorted(agg.items(), key=lambda kv: -(kv[1][3]))[:top]:
             big = max(v[5].items(), key=lambda kv: kv[1])
-            print("%5s samp %4.1f%% (%s) wf/el %6.0f exc %6.0f inst/el %6.0f | %s" % (
+            print("%26s samp %4.1f%% (%s) wf/el %6.0f exc %6.0f inst/el %6.0f | %s" % (
                 l, 100 * v[3] / max(ts, 1), big[0][6:], v[0] / nel, v[1] / nel, v[2] / nel, v[4].strip()[:90]))
 
 
