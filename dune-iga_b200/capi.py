@@ -26,7 +26,7 @@ EXPORTS = ("igab_last_error_string", "igab_version", "igab_launch_count", "igab_
            "igab_eval_points", "igab_partial", "igab_assemble", "igab_reduce_volume", "igab_csr_pattern",
            "igab_csr_assemble", "igab_eval_faces", "igab_refine_apply", "igab_surface_forms", "igab_geometry_local", "igab_reduce_norms", "igab_local_keys", "igab_rhs_assemble",
            "igab_csr_dirichlet", "igab_assemble_points", "igab_global_assemble", "igab_reduce_volume_trimmed", "igab_reduce_norms_trimmed",
-           "igab_partition_slab", "igab_interface_row_ranges", "igab_comm_unique_id", "igab_comm_create",
+           "igab_partition_slab", "igab_partition_weighted", "igab_interface_row_ranges", "igab_comm_unique_id", "igab_comm_create",
            "igab_comm_destroy", "igab_comm_info", "igab_exchange_interface_rows", "igab_patch_real_index_maps",
            "igab_load_vector", "igab_load_vector_points", "igab_global_load_vector", "igab_device_numa_node", "igab_eval_tensor_begin", "igab_patch_wait", "igab_refine_knots",
            "igab_patch_create_from_device")
@@ -743,6 +743,16 @@ def partitionSlab(nel_dir, world, rank):
     _check(lib().igab_partition_slab(len(n), n.ctypes.data, world, rank, C.byref(eb), C.byref(ee)))
     return eb.value, ee.value
 
+
+
+def partitionWeighted(counts, world, per_layer=1):
+    """world + 1 element bounds with (nearly) equal cumulative point counts (igab_partition_weighted): trimmed patches,
+    counts[e] = quadrature points of element e; per_layer > 1 rounds the bounds to whole layers."""
+    c = np.ascontiguousarray(counts, dtype=np.int64)
+    out = np.empty(world + 1, dtype=np.int64)
+    _check(lib().igab_partition_weighted(C.c_int64(c.size), c.ctypes.data_as(C.c_void_p), world, C.c_int64(max(1, int(per_layer or 1))),
+                                         out.ctypes.data_as(C.c_void_p)))
+    return [int(v) for v in out]
 
 def interfaceRowRanges(degree, knotSpans, world, ncomp=1, elem_bounds=None):
     """(row_begin, row_end) int64 [world]: the rows every rank's slab touches (igab_interface_row_ranges; host only)."""

@@ -190,6 +190,34 @@ igab_status igab_partition_slab(int dim, const int32_t* n_elem_dir, int world, i
   return IGAB_OK;
 }
 
+igab_status igab_partition_weighted(int64_t n_elem, const int64_t* counts, int world, int64_t per_layer,
+                                    int64_t* bounds) {
+  if (n_elem < 0 || (n_elem > 0 && !counts) || world < 1 || per_layer < 1 || !bounds) {
+    set_error("partition_weighted: invalid argument");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  long long total = 0;
+  for (int64_t e = 0; e < n_elem; ++e) {
+    if (counts[e] < 0) {
+      set_error("partition_weighted: negative point count");
+      return IGAB_INVALID_ARGUMENT;
+    }
+    total += counts[e];
+  }
+  bounds[0] = 0;
+  long long run = 0;
+  int64_t e = 0;
+  for (int r = 1; r < world; ++r) {
+    // first element index b with (points of elements < b) >= total * r / world, compared without division
+    while (e < n_elem && (__int128)run * world < (__int128)total * r) run += counts[e++];
+    int64_t b = e;
+    if (per_layer > 1) b = (b + per_layer / 2) / per_layer * per_layer;
+    bounds[r] = std::min<int64_t>(std::max<int64_t>(b, bounds[r - 1]), n_elem);
+  }
+  bounds[world] = n_elem;
+  return IGAB_OK;
+}
+
 igab_status igab_interface_row_ranges(int dim, const int* degree, const int* nknots, const double* const* knots,
                                       int ncomp, int world, const int64_t* elem_bounds, int64_t* row_begin,
                                       int64_t* row_end) {

@@ -888,6 +888,14 @@ std::pair<int64_t, int64_t> partitionSlab(const std::array<int32_t, dim>& elemen
   return {b, e};
 }
 
+// world + 1 element bounds of a trimmed patch balanced by the cumulative number of quadrature points (empty elements
+// none, trimmed ones their own rules); perLayer > 1 rounds to whole layers of the slowest direction (igab_partition_weighted)
+inline std::vector<int64_t> partitionWeighted(const std::vector<int64_t>& pointsPerElement, int world, int64_t perLayer = 1) {
+  std::vector<int64_t> bounds((size_t)world + 1);
+  check(igab_partition_weighted((int64_t)pointsPerElement.size(), pointsPerElement.data(), world, perLayer, bounds.data()));
+  return bounds;
+}
+
 // ---- globalAssembler (dune/python/test/poisson.py:84-127), vectorised: the whole loop over elements, quadrature points
 //      and local DOF pairs is one device pass; what comes back is the CSR matrix and the load vector -----------------------
 struct CsrMatrix {

@@ -29,17 +29,7 @@ def weighted_ranges(counts, world, per_layer=None):
     """Trimmed patches: contiguous element ranges with (nearly) equal cumulative point counts.
     counts[e] = quadrature points of element e (0 for empty elements).  Returns world+1 boundaries; with per_layer the
     boundaries are rounded to whole layers of the slowest direction (what the interface-row exchange needs)."""
-    counts = np.asarray(counts, dtype=np.int64)
-    cum = np.concatenate([[0], np.cumsum(counts)])
-    total = cum[-1]
-    bounds = [0]
-    for r in range(1, world):
-        b = int(np.searchsorted(cum, total * r / world, side="left"))
-        if per_layer:
-            b = int(round(b / per_layer)) * per_layer
-        bounds.append(b)
-    bounds.append(len(counts))
-    return [min(max(b, bounds[i - 1] if i else 0), len(counts)) for i, b in enumerate(bounds)]
+    return capi.partitionWeighted(counts, world, per_layer or 1)
 
 
 def interface_dofs(dofmap, ranges):

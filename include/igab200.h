@@ -364,6 +364,15 @@ igab_status igab_reduce_norms_trimmed(igab_patch* p, int64_t elem_begin, int64_t
 igab_status igab_partition_slab(int dim, const int32_t* n_elem_dir, int world, int rank, int64_t* elem_begin,
                                 int64_t* elem_end);
 
+/* Trimmed patches: elements carry unequal work (empty ones none, trimmed ones their own rules,
+ * dune/iga/utils/fillquadraturerule.hh:8-19), so the slabs are balanced by the cumulative number of quadrature points
+ * instead of the element count.  counts[n_elem] = points of every element in direct-index order; bounds[world + 1]:
+ * rank r owns [bounds[r], bounds[r+1]), boundary r placed where the running point count first reaches r/world of the
+ * total and rounded to a multiple of per_layer (the elements of one layer of the slowest direction: what
+ * igab_interface_row_ranges / igab_exchange_interface_rows take as elem_bounds; 1 = no rounding).  Host only.         */
+igab_status igab_partition_weighted(int64_t n_elem, const int64_t* counts, int world, int64_t per_layer,
+                                    int64_t* bounds);
+
 /* Rows of the global system (untrimmed numbering g*ncomp + c) that the elements of every rank touch: the DOF layers
  * span(l) - p .. span(l') of the slab's first / last element layer (g_d = s_d - p_d + l_d, dune/iga/nurbsbasis.hh:576).
  * elem_bounds: NULL (igab_partition_slab) or world + 1 ascending multiples of the layer size.  Rows shared by ranks r

@@ -132,3 +132,27 @@ def test_slab_partition_and_interface_row_planner_host_only():
     pd = PD.thickCylinder(3, (1, 1, 2))
     rb, re = capi.interfaceRowRanges(pd.degree, pd.knotSpans, 4)
     assert min(re[0], re[3]) > max(rb[0], rb[3])
+
+
+def test_partition_weighted_balances_cumulative_point_counts():
+    """igab_partition_weighted (trimmed patches are partitioned by cumulative point count): every boundary sits
+    where the running count first reaches r / world of the total, bounds are monotone, rounding to whole layers, empty
+    input, and the error path -- host integer code, no device needed."""
+    rng = np.random.default_rng(3)
+    counts = rng.integers(0, 241, 4096).astype(np.int64)
+    counts[rng.random(4096) < 0.3] = 0            # empty elements
+    cum = np.concatenate([[0], np.cumsum(counts)])
+    for world in (1, 2, 3, 8):
+        b = capi.partitionWeighted(counts, world)
+        assert b[0] == 0 and b[-1] == 4096 and all(x <= y for x, y in zip(b, b[1:]))
+        for r in range(1, world):
+            assert cum[b[r]] * world >= cum[-1] * r and (b[r] == 0 or cum[b[r] - 1] * world < cum[-1] * r)
+        work = [cum[b[r + 1]] - cum[b[r]] for r in range(world)]
+        assert max(work) - min(work) <= 2 * 240
+        bl = capi.partitionWeighted(counts, world, per_layer=64)
+        assert all(x % 64 == 0 for x in bl) and bl[0] == 0 and bl[-1] == 4096
+        assert all(abs(x - y) <= 32 for x, y in zip(bl, b))
+    assert capi.partitionWeighted(np.zeros(0, np.int64), 4) == [0, 0, 0, 0, 0]
+    assert capi.partitionWeighted(np.zeros(10, np.int64), 2) == [0, 0, 10]
+    with pytest.raises(Exception):
+        capi.partitionWeighted(np.array([1, -1], np.int64), 2)
