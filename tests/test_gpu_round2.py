@@ -391,3 +391,32 @@ def test_symmetric_assembly_kernel_matches_oracle_and_the_full_kernel(p, q, kind
         Kr, fr = O.assemble(kind, [x] * 3, [w] * 3, fconst=0.7, elem_begin=int(e), elem_end=int(e) + 1)
         assert relerr(K1[e].reshape(1, -1), Kr.reshape(1, -1)) <= TOL
         assert relerr(out["1"][1][e].reshape(1, -1), fr.reshape(1, -1)) <= TOL
+
+
+@pytest.mark.parametrize("name", ["plate_hole_p2", "cylinder_p3", "square_p3"])
+def test_output_pointers_that_are_only_8_byte_aligned(name):
+    """The async bulk stores (TMA) of the tensor-rule kernels need 16-byte aligned global rows; a caller's double* is only
+    guaranteed 8-byte alignment.  Every field is written once into freshly allocated tensors and once into views that
+    start one double into a buffer (address = 8 mod 16): same bits, nothing written outside the views."""
+    import torch
+    spec = PFT.small_patch(name, level=2)
+    P = gpu_patch(spec)
+    q = spec["degree"][0] + 1
+    xi = [PD.gaussLegendre01(q)[0]] * P.dim
+    want = ("N", "dN", "x", "Jt", "detJ", "JinvT")
+    npts = P.nelem * q ** P.dim
+    sh = P.shapes(npts)
+    ref = {f: torch.empty(sh[f], dtype=torch.float64, device="cuda") for f in want}
+    P.evalTensor(xi, order=1, want=want, out=ref)
+    bufs, views = {}, {}
+    for f in want:
+        n = int(np.prod(sh[f]))
+        bufs[f] = torch.full((n + 2,), -7.0, dtype=torch.float64, device="cuda")
+        assert bufs[f].data_ptr() % 16 == 0
+        views[f] = bufs[f][1:n + 1].view(sh[f])
+        assert views[f].data_ptr() % 16 == 8
+    P.evalTensor(xi, order=1, want=want, out=views)
+    torch.cuda.synchronize()
+    for f in want:
+        assert torch.equal(views[f], ref[f]), f
+        assert float(bufs[f][0]) == -7.0 and float(bufs[f][-1]) == -7.0, f
