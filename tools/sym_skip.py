@@ -1,10 +1,22 @@
-"""Timing experiments on gram_sym_kernel (library built with -DIGAB_SYM_EXPERIMENT into tools/_exp): element matrices/s with
+"""Timing experiments on gram_sym_kernel (library built with -DIGAB_SYM_EXPERIMENT into tools/_exp by --build): element matrices/s with
 single pieces of the kernel switched off (results are wrong on purpose) -- an upper bound of what optimising a piece can buy."""
+import glob
 import os
+import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-os.environ["IGAB200_SO"] = os.path.join(ROOT, "tools", "_exp", "libigab200.so")
+SO = os.path.join(ROOT, "tools", "_exp", "libigab200.so")
+if "--build" in sys.argv:  # here (no GPU): python tools/sym_skip.py --build ; then on the GPU box: python tools/sym_skip.py
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    src = sorted(glob.glob(os.path.join(ROOT, "dune-iga_b200", "csrc", "*.cu")))
+    env = dict(os.environ); env.pop("CC", None); env.pop("CXX", None)
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-O3", "-std=c++17", "-lineinfo", "-gencode",
+                           "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+                           "-DIGAB_SYM_EXPERIMENT", "-shared", "-o", SO, "-t", "8"] + src + ["-lcudart", "-ldl"], env=env)
+    print("built", SO)
+    sys.exit(0)
+os.environ["IGAB200_SO"] = SO
 os.environ["IGAB_GRAM_SYM"] = "1"
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
