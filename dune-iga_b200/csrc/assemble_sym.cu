@@ -64,6 +64,17 @@ struct YCfg {
   static constexpr bool GEN2 = !(TPW == 1 || NT2 % TPW == 0);
   static constexpr int M3 = NSLOT * NP, M3P = S::r8(M3), MT3 = M3P / 8, NT3 = NPP / 8;  // stage-3 rows (j1, i1, slot)
   static constexpr int NMT = (MT3 + NWARP - 1) / NWARP;
+  // stage 3 split by column halves: warp w takes the column tiles of half w % 2 and the row tiles w / 2 + 4 v -- 19 row tiles
+  // over 8 warps were 3 / 2 whole rows per warp (12 against 8 tiles); now 5 / 4 half rows (10 against 8), and a warp
+  // holds only its half of the B3 fragments
+  // (only where a half still has two tiles per A fragment and both halves are equal: p = 4.  Measured against whole rows:
+  //  p = 4 +3-8 %, p = 3 with one tile per half -5 %, p = 5 with halves of 3 + 2 tiles -3 %)
+  static constexpr bool SPLIT3 = NT3 >= 4 && NT3 % 2 == 0;
+  static constexpr int NH0 = SPLIT3 ? (NT3 + 1) / 2 : NT3, NH1 = NT3 - NH0;
+  static constexpr int NMT3 = SPLIT3 ? (MT3 + 3) / 4 : NMT;
+  // stage 2 in the middle pass of an odd p + 1 (half the slots): one tile per warp when they are at most eight
+  static constexpr int MIDROWS = ((NB1 + 1) / 2) * Q, MTMID = (MIDROWS + 7) / 8;
+  static constexpr bool ALT2 = (NB1 % 2 == 1) && !GEN2 && TPW > 1 && MTMID * NT2 <= NWARP;
   static constexpr int LDA2 = S::LDA2, LDB2 = S::LDB2, LDA3 = S::LDA3, CSS = S::CSS;
   static constexpr int SZ_T1 = M2P * LDA2;
   static constexpr int npadc() {  // padding columns of T1: the tail of every group's k range and the tail of the row
@@ -142,26 +153,38 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
   // tile (j1 = lr) a store instruction fills runs of 4 out of every 5 doubles instead of every other one (sectors written
   // per instruction: ~11 instead of ~25)
   //   bits 0-15 i0 NB + j0 (offset in K_e), 16-19 i0, 20-23 j0, 24-31 j0 NP + i0 (offset in the mirror buffer); -1 = padding
-  int c3[Y::NT3][2];
+  const int hw3 = Y::SPLIT3 ? (warp & 1) : 0, ntBase3 = hw3 ? Y::NH0 : 0, ntCnt3 = hw3 ? Y::NH1 : Y::NH0;
+  int c3[Y::NH0][2];
 #pragma unroll
-  for (int nt = 0; nt < Y::NT3; ++nt)
+  for (int t = 0; t < Y::NH0; ++t)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int n = S::cperm(8 * nt + 2 * lc + h);
+      const int n = S::cperm(8 * (ntBase3 + t) + 2 * lc + h);
       const int i0 = n / NB1, j0 = n % NB1;
-      c3[nt][h] = n < NP ? (int)((unsigned)(i0 * NB + j0) | ((unsigned)i0 << 16) | ((unsigned)j0 << 20) |
-                                 ((unsigned)(j0 * NP + i0) << 24))
-                         : -1;
+      c3[t][h] = (t < ntCnt3 && n < NP) ? (int)((unsigned)(i0 * NB + j0) | ((unsigned)i0 << 16) | ((unsigned)j0 << 20) |
+                                                ((unsigned)(j0 * NP + i0) << 24))
+                                        : -1;
     }
-  // stage 3: row lr of this warp's u-th tile (tile row warp + 8 u) is (j1, i1, slot): NB1 i1 | NB1 j1 << 8 | slot << 16, or -1
-  int r3[NMT];
+  // stage 3: row lr of this warp's v-th row tile is (j1, i1, slot): NB1 i1 | NB1 j1 << 8 | slot << 16, or -1
+  constexpr int NMT3 = Y::NMT3;
+  const int mtFirst3 = Y::SPLIT3 ? (warp >> 1) : warp, mtStep3 = Y::SPLIT3 ? 4 : Y::NWARP;
+  int r3[NMT3];
 #pragma unroll
-  for (int u = 0; u < NMT; ++u) {
-    const int mp = 8 * (warp + Y::NWARP * u) + lr;
+  for (int u = 0; u < NMT3; ++u) {
+    const int mp = 8 * (mtFirst3 + mtStep3 * u) + lr;
     const int slot = mp / NP, n1 = mp % NP;
     r3[u] = mp < Y::M3 ? (NB1 * (n1 / NB1)) | ((NB1 * (n1 % NB1)) << 8) | (slot << 16) : -1;
   }
-
+  // stage 2, middle pass: tile (warp / NT2, warp % NT2)
+  [[maybe_unused]] int t2alt[2] = {-1, -1};
+  if constexpr (Y::ALT2) {
+    const int mtA = warp / Y::NT2, ntA = warp % Y::NT2, m = 8 * mtA + lr;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n = S::cperm(8 * ntA + 2 * lc + h);
+      t2alt[h] = (mtA < Y::MTMID && m < Y::MIDROWS && n < NP) ? (n + NP * (m / Q)) * LDA3 + (m % Q) : -1;
+    }
+  }
   // stage 1 (tensor-core version, stage1_dmma in gram_common.cuh): where this lane's two accumulator columns go in T1
   int s1off[2];
   S1Cfg<P, Q, KIND>::store_offsets(warp, lane, NSLOT, LDA2, s1off);
@@ -256,11 +279,12 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
       }
     }
     __syncthreads();
-    double b3[S::K3 / 4][Y::NT3];
+    double b3[S::K3 / 4][Y::NH0];  // this warp's half of the column tiles (zero tile past the end of a shorter half)
 #pragma unroll
     for (int ks = 0; ks < S::K3 / 4; ++ks)
 #pragma unroll
-      for (int nt = 0; nt < Y::NT3; ++nt) b3[ks][nt] = sT2[(4 * ks + lc) * LDB2 + 8 * nt + lr];
+      for (int t = 0; t < Y::NH0; ++t)
+        b3[ks][t] = t < ntCnt3 ? sT2[(4 * ks + lc) * LDB2 + 8 * (ntBase3 + t) + lr] : 0.0;
     __syncthreads();
 
     double* const K = Ke + el * (long long)NB * NB;
@@ -358,6 +382,26 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
             if (off[1] >= 0) sT2[off[1] + g * Q] = a1;
           }
         }
+      } else if (Y::ALT2 && !paired) {
+        // middle pass: half the slots, one tile per warp
+        const int mtA = warp / Y::NT2, ntA = warp % Y::NT2;
+        if (mtA < Y::MTMID && !SKIP(4)) {
+          const double* arow = sT1 + (8 * mtA + lr) * LDA2 + lc;
+          const double* brow = sB2 + lc * LDB2 + 8 * ntA + lr;
+          double acc[S::NG][2];
+#pragma unroll
+          for (int g = 0; g < S::NG; ++g) {
+            acc[g][0] = acc[g][1] = 0.0;
+            const int kb = S::goff(g), nks = S::r4(S::ncombo(g) * Q) / 4;
+#pragma unroll
+            for (int ks = 0; ks < nks; ++ks) dmma8x8x4_f(acc[g][0], acc[g][1], arow[kb + 4 * ks], brow[(kb + 4 * ks) * LDB2]);
+          }
+#pragma unroll
+          for (int g = 0; g < S::NG; ++g)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              if (t2alt[h] >= 0) sT2[t2alt[h] + g * Q] = acc[g][h];
+        }
       } else if (has2 && 8 * mt2 < rows2 && !SKIP(4)) {
         const double* arow = sT1 + (8 * mt2 + lr) * LDA2 + lc;
         const double* brow = sB2 + lc * LDB2 + 8 * nt2 + lr;
@@ -391,19 +435,19 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
       // ---- stage 3: K[(j1,i1,slot)][pi0] = sum_{(g,q0)} T2 B3: to global memory (with the weights w_i w_j on the general
       //      path), and the strictly upper blocks (j2 > i2) also into the mirror buffer, transposed
 #pragma unroll
-      for (int u = 0; u < NMT; ++u) {
-        const int mt = warp + Y::NWARP * u;
+      for (int u = 0; u < NMT3; ++u) {
+        const int mt = mtFirst3 + mtStep3 * u;
         if (mt >= Y::MT3 || 8 * mt >= rows3) break;
-        double acc[Y::NT3][2];
+        double acc[Y::NH0][2];
 #pragma unroll
-        for (int nt = 0; nt < Y::NT3; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+        for (int t = 0; t < Y::NH0; ++t) acc[t][0] = acc[t][1] = 0.0;
         const double* arow = sT2 + (8 * mt + lr) * LDA3 + lc;
         if (!SKIP(5))
 #pragma unroll
         for (int ks = 0; ks < S::K3 / 4; ++ks) {
           const double a = arow[4 * ks];
 #pragma unroll
-          for (int nt = 0; nt < Y::NT3; ++nt) dmma8x8x4_f(acc[nt][0], acc[nt][1], a, b3[ks][nt]);
+          for (int t = 0; t < Y::NH0; ++t) dmma8x8x4_f(acc[t][0], acc[t][1], a, b3[ks][t]);
         }
         const int slot = r3[u] >> 16;
         if (r3[u] >= 0 && slot < nslots) {
@@ -416,7 +460,7 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
             const double* const wI = sW + ib;
             const double* const wJ = sW + jb;
 #pragma unroll
-            for (int nt = 0; nt < Y::NT3; ++nt)
+            for (int nt = 0; nt < Y::NH0; ++nt)
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const int pk = c3[nt][h];
@@ -425,7 +469,7 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
           }
           if (!SKIP(3))
 #pragma unroll
-          for (int nt = 0; nt < Y::NT3; ++nt)
+          for (int nt = 0; nt < Y::NH0; ++nt)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int pk = c3[nt][h];
@@ -436,7 +480,7 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
           if (j2 > i2 && !SKIP(2)) {
             double* const Mb = sMB + (sa ? slot - 1 : slot - 2) * (NP * NP) + j1b * NP + i1b;
 #pragma unroll
-            for (int nt = 0; nt < Y::NT3; ++nt)
+            for (int nt = 0; nt < Y::NH0; ++nt)
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const int pk = c3[nt][h];
