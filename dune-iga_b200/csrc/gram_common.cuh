@@ -249,6 +249,13 @@ struct S1Cfg {
   static constexpr int NTQ = S::r8(Q * Q) / 8;   // 8-column tiles over (q1, q0)
   static constexpr bool OK = NW % NTQ == 0;
   static constexpr int WG = OK ? NW / NTQ : 1;
+  // the combos of a variant are dealt to the WG warp groups round-robin, starting where the previous variant stopped:
+  // 9 + 3 + 3 + 1 combos over two groups are 8 + 8 (started at group 0 every time they were 10 + 6 rounds)
+  static constexpr int var_first_group(int v) {
+    int n = 0;
+    for (int u = 0; u < v; ++u) n += var_count(u);
+    return n % WG;
+  }
   // gw = index of the warp among the eight; rows lr >= nslot_max are never stored
   __device__ static __forceinline__ void store_offsets(int gw, int lane, int nslot_max, int lda2, int (&s1off)[2]) {
     const int lr = lane >> 2, lc = lane & 3, nt = gw % NTQ;
@@ -296,7 +303,8 @@ __device__ __forceinline__ void stage1_dmma(int gw, int lane, int i2, int j2, bo
       int moff = -1, coff = 0;
       static_for<WG1>([&](auto kc) {
         constexpr int k = decltype(kc)::value;
-        constexpr int cc = Y::var_item(v, it * WG1 + k);
+        // group k takes item (k - first group of the variant) mod WG of this round
+        constexpr int cc = Y::var_item(v, it * WG1 + (k - Y::var_first_group(v) + WG1) % WG1);
         if constexpr (cc >= 0) {
           constexpr int mo = Y::moff_of(cc), co = Y::coff_of(cc);
           if (wg1 == k) {
