@@ -215,7 +215,8 @@ __global__ void __launch_bounds__(256, (YCfg<P, Q, KIND>::BLOCKS)) gram_sym_kern
       }
     }
     // (the first barrier inside also ends the previous element's mirror copy-out, which reads the region sC aliases)
-    element_prepare<P, Q, NT, CS>(Pd, e, tab0, tab1, tab2, w0, w1, w2, sT, sW, rX, rX + C::SZ_A, sC);
+    if (!SKIP(6)) element_prepare<P, Q, NT, CS>(Pd, e, tab0, tab1, tab2, w0, w1, w2, sT, sW, rX, rX + C::SZ_A, sC);
+    else __syncthreads();
     SYM_PT(0)
     // ---- T1: the padding columns of every group must be zero (they meet zero rows of B2, but the scratch T1 aliases may
     //      hold anything); the other columns of the rows in use are written by stage 1, and rows are independent

@@ -25,7 +25,7 @@ import igab200  # noqa: E402,F401
 from dune_iga_b200 import capi, patchdata as PD  # noqa: E402
 
 NAMES = {0: "all on", 1: "no stage 1", 2: "no B2 build", 4: "no mirror", 8: "no K_e stores", 16: "no stage 2", 32: "no stage-3 DMMA",
-         12: "no mirror, no K_e stores", 1 + 16 + 32: "no stage 1/2/3 math", 63: "everything off (prepare + operands + barriers left)"}
+         12: "no mirror, no K_e stores", 64: "no element_prepare (tables, control points, geometry, constants)", 64 + 63: "all off incl. element_prepare", 1 + 16 + 32: "no stage 1/2/3 math", 63: "everything off (prepare + operands + barriers left)"}
 for p, q, kind, name in ((4, 5, capi.ASM_POISSON, "poisson"), (4, 5, capi.ASM_MASS, "mass")):
     pd = PD.thickCylinder(p, (5, 5, 5))
     P = capi.Patch.fromPatchData(pd)
