@@ -545,7 +545,17 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
     r3[u] = mp < S::M3 ? (NB1 * (mp / NP)) | ((NB1 * (mp % NB1) + NP * ((mp / NB1) % NB1)) << 8) : -1;
   }
 
-  for (long long el = blockIdx.x; el < nelem; el += gridDim.x) {
+  // a block takes a CONTIGUOUS run of elements (as gram_sym_kernel): consecutive elements share e1, so the stage-2 operand
+  // B2, which depends on direction 1 only, is rebuilt once per row of elements instead of once per element
+  // (not for the mass matrix, whose B2 is tiny and which is bound by its stores: contiguous runs measured 0.89-0.99x there,
+  //  1.02-1.17x for Poisson / elasticity)
+  constexpr bool RUNS = !MASS;
+  const long long chunk = (nelem + gridDim.x - 1) / gridDim.x;
+  const long long el_lo = RUNS ? blockIdx.x * chunk : blockIdx.x;
+  const long long el_hi = RUNS ? (el_lo + chunk < nelem ? el_lo + chunk : nelem) : nelem;
+  const long long el_step = RUNS ? 1 : gridDim.x;
+  int b2_e1 = -1;
+  for (long long el = el_lo; el < el_hi; el += el_step) {
     const long long e = elem_begin + el;
     if (useW) {
       // nobody reads sTw any more: the previous element's last stage 1 lies two barriers back; element_prepare's barriers
@@ -561,6 +571,8 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
     // ---- T1 zeroed (its padding columns must stay zero; the scratch it aliases is free after element_prepare)
     for (int idx = tid; idx < S::SZ_T1; idx += NT) sT1[idx] = 0.0;
     // ---- B2[(g, c, q1)][pi1 = j1 + NB1 i1] = Phi1[q1][i1][b1(beta)] Phi1[q1][j1][b1(gamma)],  b1(beta) = (beta == 2)
+    const int e1cur = (int)((e / Pd.nel[0]) % Pd.nel[1]);
+    if (e1cur != b2_e1)
 #pragma unroll
     for (int g = 0; g < S::NG; ++g) {
       for (int idx = tid; idx < S::ncombo(g) * Q * NP; idx += NT) {
@@ -571,6 +583,7 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
             sTc[TAB + (q1 * NB1 + i1) * 2 + bb] * sTc[TAB + (q1 * NB1 + j1) * 2 + bg];
       }
     }
+    b2_e1 = e1cur;
     // ---- B3[(g, q0)][pi0 = j0 + NB1 i0] = Phi0[q0][i0][b0(beta)] Phi0[q0][j0][b0(gamma)], group g = (b0(beta), b0(gamma)):
     //      0 (0,0), 1 (1,0), 2 (0,1), 3 (1,1).  Built once in the (still unused) T2 region, then held as fragments.
     for (int idx = tid; idx < S::K3 * S::NPP; idx += NT) {
@@ -1417,10 +1430,11 @@ igab_status launch_gram_fused(const PatchDev& P, SfWorkspace& ws, const double* 
       set_error("assemble: elasticity needs the 6x6 D matrix");
       return IGAB_INVALID_ARGUMENT;
     }
-    // elasticity: the sum-factorised kernel pays off at p = 4 (1.09x; its interleaved (j, b) stores cost a quarter of its
-    // time), the nine-Gram-block kernel stays ahead below; IGAB_ELAS_SF=0 / 1 forces one of them
+    // elasticity: the sum-factorised kernels from p = 3 on (tools/elas_sf_bench.py: p = 3 1.13x with 4 and 5 points, p = 4
+    // 1.40x; before the stage-3 column permutation and the contiguous element runs p = 3 was 0.9x), the nine-Gram-block
+    // kernel at p = 2 (2.6x / 1.8x ahead there); IGAB_ELAS_SF=0 / 1 forces one of them
     const char* esf = getenv("IGAB_ELAS_SF");
-    const bool use_sf = esf ? esf[0] != '0' : P.degree[0] >= 4;
+    const bool use_sf = esf ? esf[0] != '0' : P.degree[0] >= 3;
 #define IGAB_ELAS_CASE(PP, QQ)                                                                                   \
   if (P.degree[0] == PP && nq1[0] == QQ)                                                                         \
     return use_sf ? launch_elas_sf<PP, QQ>(P, ws, D_host, fconst, eb, nel, w1d_dev, Ke, fe, stream)              \
