@@ -881,7 +881,7 @@ struct WCfg {
   static constexpr int SZ_B3 = S::K3 * S::LDB2;
   static constexpr int SZ_K = F::ev(S::NP * S::NB * NCP);  // the rows (i0, i1) of one i2 (x the three b-blocks)
   static constexpr int SZ_TOTAL =
-      F::SZ_T + F::SZ_W + S::SZ_CS + S::SZ_X + S::SZ_M + 2 * S::SZ_T2 + S::SZ_B2 + SZ_B3 + SZ_K + F::SZ_T;
+      F::SZ_T + F::SZ_W + S::SZ_CS + S::SZ_X + S::SZ_M + S::SZ_T2 + S::SZ_T1 + S::SZ_B2 + SZ_B3 + SZ_K + F::SZ_T;
   static constexpr bool FITS = SZ_TOTAL * 8 <= 227 * 1024;
 };
 
@@ -900,7 +900,11 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
   constexpr int NT = WC::NT, NTH = WC::NTH, NTM = WC::NTM;
   constexpr int LDA2 = S::LDA2, LDB2 = S::LDB2, LDA3 = S::LDA3;
   constexpr int NPASS = NCP * NB1 * NCP;
-  enum { BAR_T1_FULL = 1, BAR_T1_FREE = 2, BAR_K_FULL = 3, BAR_K_FREE = 4, BAR_MMA = 5, BAR_HLP = 6 };
+  // T1 is double-buffered (FULL / FREE barriers per buffer: + 0 / + 1): stage 1 of pass k + 1 (helper warps) overlaps stage 2
+  // of pass k (DMMA warps).  With one buffer the two were serialised -- pass period = stage 1 + stage 2, 6.0 k cycles at C3
+  // elasticity (tools/ws_phase.py) -- although they run on different warps.  T2 needs one buffer only: stages 2 and 3 of a
+  // pass run on the same warps, one after the other.
+  enum { BAR_T1_FULL = 1, BAR_T1_FREE = 3, BAR_K_FULL = 5, BAR_K_FREE = 6, BAR_MMA = 7, BAR_HLP = 8, BAR_MMA2 = 9 };
   extern __shared__ __align__(16) double ssm[];
   double* const sT = ssm;
   double* const sW = sT + C::SZ_T;
@@ -908,8 +912,9 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
   double* const rX = sC + S::SZ_CS;  // element_prepare's scratch (rA | sS2), then T1
   double* const sT1 = rX;
   double* const sM = rX + S::SZ_X;
-  double* const sT2 = sM + S::SZ_M;  // two buffers
-  double* const sB2 = sT2 + 2 * S::SZ_T2;
+  double* const sT2 = sM + S::SZ_M;
+  double* const sT1b = sT2 + S::SZ_T2;  // second T1 buffer (odd passes)
+  double* const sB2 = sT1b + S::SZ_T1;
   double* const sB3 = sB2 + S::SZ_B2;
   double* const sK = sB3 + WC::SZ_B3;
   double* const sTw = sK + WC::SZ_K;  // weighted tables (tensor-product weights)
@@ -921,7 +926,7 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
   const int lr = lane >> 2, lc = lane & 3;
   for (int idx = tid; idx < C::SZ_W; idx += NT) sW[idx] = 0.0;
   for (int idx = tid; idx < S::SZ_B2; idx += NT) sB2[idx] = 0.0;      // padding rows stay zero
-  for (int idx = tid; idx < 2 * S::SZ_T2; idx += NT) sT2[idx] = 0.0;  // padding rows / columns of T2 stay zero
+  for (int idx = tid; idx < S::SZ_T2 + S::SZ_T1; idx += NT) sT2[idx] = 0.0;  // padding of T2 and of the second T1 buffer stays zero
 
   // ---- DMMA warps: fragment <-> index maps, the same for every element (see gram_sf_kernel)
   const int tile0 = warp * S::TPW;
@@ -1026,14 +1031,16 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
         for (int nt = 0; nt < S::NT3; ++nt) b3[ks][nt] = sB3[(4 * ks + lc) * LDB2 + 8 * nt + lr];
       for (int k = 0; k < NPASS; ++k) {
         const int cb = k % NCP;
-        double* const T2 = sT2 + (k & 1) * S::SZ_T2;
-        nb_sync(BAR_T1_FULL, NT);
+        double* const T2 = sT2;
+        const double* const T1 = (k & 1) ? sT1b : sT1;
+        if (k > 0) nb_sync(BAR_MMA2, NTM);  // every DMMA warp has left stage 3 of the previous pass: T2 may be rewritten
+        nb_sync(BAR_T1_FULL + (k & 1), NT);
         IGAB_WPT(0)
         // ---- stage 2: C_g[(j2,q0)][pi1] = sum_{k in g} T1[.][k] B2[k][.]  ->  T2[j1 + NB1 j2 + NP i1][g Q + q0]
         if constexpr (S::GEN2) {
           for (int tile = warp; tile < S::MT2 * S::NT2; tile += WC::NWM) {
             const int mt = tile / S::NT2, nt = tile % S::NT2;
-            const double* arow = sT1 + (8 * mt + lr) * LDA2 + lc;
+            const double* arow = T1 + (8 * mt + lr) * LDA2 + lc;
             const double* brow = sB2 + lc * LDB2 + 8 * nt + lr;
             const int m = 8 * mt + lr;
             int off[2];
@@ -1053,7 +1060,7 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
             }
           }
         } else if (has2) {
-          const double* arow = sT1 + (8 * mt2 + lr) * LDA2 + lc;
+          const double* arow = T1 + (8 * mt2 + lr) * LDA2 + lc;
           const double* brow = sB2 + lc * LDB2 + 8 * nt2 + lr;
 #pragma unroll
           for (int g = 0; g < S::NG; ++g) {  // (all groups before the stores, as in gram_sf_kernel, costs registers here: -6 %)
@@ -1075,7 +1082,7 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
           }
         }
         IGAB_WPT(1)
-        if (k + 1 < NPASS) nb_arrive(BAR_T1_FREE, NT);  // T1 consumed: the helpers may write pass k+1 into it
+        if (k + 2 < NPASS) nb_arrive(BAR_T1_FREE + (k & 1), NT);  // buffer consumed: the helpers may write pass k+2 into it
         nb_sync(BAR_MMA, NTM);                           // T2 of this pass complete
         if (cb == 0 && k > 0) nb_sync(BAR_K_FREE, NT);   // the epilogue of the previous rows has left the tile buffer
         IGAB_WPT(2)
@@ -1140,7 +1147,8 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
           nb_sync(BAR_HLP, NTH);
         }
       };
-      auto stage1 = [&](int i2) {
+      auto stage1 = [&](int i2, int buf) {
+        double* const T1w = buf ? sT1b : sT1;
         // thread <-> (combo, q1, pair of q0), all j2: the M4 line and the i2 factor in registers
         constexpr int QH = 2, NSPL = (Q + QH - 1) / QH;
         for (int item = htid; item < S::NCOMBO * Q * NSPL; item += NTH) {
@@ -1162,7 +1170,7 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
 #pragma unroll
             for (int u = 0; u < QH; ++u) am[u][q2] = a2 * mrow[min(qa + u, Q - 1) + Q * Q * q2];
           }
-          double* trow = sT1 + S::goff(g) + c * Q + q1;
+          double* trow = T1w + S::goff(g) + c * Q + q1;
 #pragma unroll
           for (int j2 = 0; j2 < NB1; ++j2) {
             double f[Q];
@@ -1178,19 +1186,19 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
           }
         }
         __threadfence_block();
-        nb_arrive(BAR_T1_FULL, NT);
+        nb_arrive(BAR_T1_FULL + buf, NT);
       };
       point_matrices(0, 0);
-      stage1(0);
+      stage1(0, 0);
       IGAB_WPT(5)
       for (int k = 0; k < NPASS; ++k) {
         const int cb = k % NCP, i2 = (k / NCP) % NB1, ca = k / (NCP * NB1);
         if (k + 1 < NPASS) {
           const int k1 = k + 1;
-          nb_sync(BAR_T1_FREE, NT);
+          if (k1 >= 2) nb_sync(BAR_T1_FREE + (k1 & 1), NT);  // stage 2 of pass k1 - 2 is done with this buffer
           IGAB_WPT(4)
           point_matrices(k1 / (NCP * NB1), k1 % NCP);
-          stage1((k1 / NCP) % NB1);
+          stage1((k1 / NCP) % NB1, k1 & 1);
           IGAB_WPT(5)
         }
         if (cb == NCP - 1) {
