@@ -1171,6 +1171,9 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
             for (int u = 0; u < QH; ++u) am[u][q2] = a2 * mrow[min(qa + u, Q - 1) + Q * Q * q2];
           }
           double* trow = T1w + S::goff(g) + c * Q + q1;
+          // all sums first, the T1 stores afterwards (as in gram_sf_kernel: a shared store inside the j2 loop pins the next
+          // iteration's table loads behind it; the helpers' stage 1 is the critical path of the pass pipeline)
+          double sums[NB1][QH];
 #pragma unroll
           for (int j2 = 0; j2 < NB1; ++j2) {
             double f[Q];
@@ -1181,9 +1184,14 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
               double sum = 0.0;
 #pragma unroll
               for (int q2 = 0; q2 < Q; ++q2) sum = fma(am[u][q2], f[q2], sum);
-              if (qa + u < Q) trow[(j2 * Q + qa + u) * LDA2] = sum;
+              sums[j2][u] = sum;
             }
           }
+#pragma unroll
+          for (int j2 = 0; j2 < NB1; ++j2)
+#pragma unroll
+            for (int u = 0; u < QH; ++u)
+              if (qa + u < Q) trow[(j2 * Q + qa + u) * LDA2] = sums[j2][u];
         }
         __threadfence_block();
         nb_arrive(BAR_T1_FULL + buf, NT);
