@@ -199,8 +199,68 @@ __global__ void __launch_bounds__(FCfg<P, Q>::NT, 2) gram_fused_kernel(
 // combined with Cf through shared memory and written as contiguous rows, the mirror block with the transposed
 // coefficients (no symmetry of D is assumed).
 struct ElasCoef {
-  double cf[81];  // [a][c][b][c']
+  double cf[81];   // [a][c][b][c']
+  unsigned nz[9];  // per (a, b): bit 3 c + c' set where cf[a][c][b][c'] != 0 (fill_nz; read by elas_point_matrix only)
+  void fill_nz() {
+    for (int ab = 0; ab < 9; ++ab) {
+      nz[ab] = 0;
+      for (int c = 0; c < 3; ++c)
+        for (int cp = 0; cp < 3; ++cp)
+          if (cf[(((ab / 3) * 3 + c) * 3 + ab % 3) * 3 + cp] != 0.0) nz[ab] |= 1u << (3 * c + cp);
+    }
+  }
 };
+
+// elasticity: M4 = C^T Cf[a][.][b][.] C of one point, entry (beta, gamma) stored at dst[(4 beta + gamma) * stride].
+// Terms with a zero coefficient are skipped (warp-uniform branches on coef.nz): an isotropic / orthotropic D leaves 3 of the
+// 9 coefficients of a diagonal pair (a, a) and 2 of an off-diagonal one, and a whole row of the intermediate Cf C is zero
+// off the diagonal -- 60 / 40 FMAs instead of 84.  The helpers' FP64 FMAs queue behind the DMMAs of the other warps on the
+// shared FP64 datapath, so every FMA less is a DMMA slot less on the critical path of the pass pipeline.  The skipped
+// terms are exact zeros: same bits as the full sums.
+template <int CS>
+__device__ __forceinline__ void elas_point_matrix(const double* sC, const ElasCoef& coef, int ca, int cb, int pt,
+                                                  double* dst, int stride) {
+  const double* o = sC + CS * pt;
+  const unsigned nz = coef.nz[ca * 3 + cb];
+  double Cm[3][4], Tm[3][4];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    Cm[c][0] = -o[1 + c];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) Cm[c][1 + d] = o[4 + 3 * c + d];
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) Tm[c][g] = 0.0;
+#pragma unroll
+    for (int cp = 0; cp < 3; ++cp)
+      if (nz & (1u << (3 * c + cp))) {
+        const double f = coef.cf[((ca * 3 + c) * 3 + cb) * 3 + cp];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) Tm[c][g] = fma(f, Cm[cp][g], Tm[c][g]);
+      }
+  }
+  const bool row0 = nz & 7u, row1 = nz & (7u << 3), row2 = nz & (7u << 6);
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {  // one row of M4 at a time: four live accumulators
+    double M[4] = {0.0, 0.0, 0.0, 0.0};
+    if (row0) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) M[g] = fma(Cm[0][b], Tm[0][g], M[g]);
+    }
+    if (row1) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) M[g] = fma(Cm[1][b], Tm[1][g], M[g]);
+    }
+    if (row2) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) M[g] = fma(Cm[2][b], Tm[2][g], M[g]);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) dst[(size_t)(b * 4 + g) * stride] = M[g];
+  }
+}
 
 template <int P, int Q>
 struct ECfg {
@@ -432,6 +492,7 @@ igab_status launch_elas(const PatchDev& Pd, SfWorkspace& ws, const double* D_hos
   for (double& v : coef.cf) v = 0.0;
   for (auto& s1 : S)
     for (auto& s2 : S) coef.cf[((s1[1] * 3 + s1[2]) * 3 + s2[1]) * 3 + s2[2]] += D_host[s1[0] * 6 + s2[0]];
+  coef.fill_nz();
   // orthotropic / isotropic D (the usual case): only 21 coefficients can be non-zero, the combination is specialised
   bool ortho = true;
   for (int a = 0; a < 3; ++a)
@@ -617,6 +678,8 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
       const double* o = sC + CS * pt;
       if constexpr (MASS) {
         sM[pt] = o[15] * o[15];
+      } else if constexpr (ELAS) {
+        elas_point_matrix<CS>(sC, coef, ca, cb, pt, sM + pt, NQ);
       } else {
         double Cm[3][4];
 #pragma unroll
@@ -625,29 +688,11 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
 #pragma unroll
           for (int d = 0; d < 3; ++d) Cm[c][1 + d] = o[4 + 3 * c + d];
         }
-        if constexpr (ELAS) {
-          double Tm[3][4];
 #pragma unroll
-          for (int c = 0; c < 3; ++c)
+        for (int b = 0; b < 4; ++b)
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              double t = 0.0;
-#pragma unroll
-              for (int cp = 0; cp < 3; ++cp) t = fma(coef.cf[((ca * 3 + c) * 3 + cb) * 3 + cp], Cm[cp][g], t);
-              Tm[c][g] = t;
-            }
-#pragma unroll
-          for (int b = 0; b < 4; ++b)
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              sM[(b * 4 + g) * NQ + pt] = Cm[0][b] * Tm[0][g] + Cm[1][b] * Tm[1][g] + Cm[2][b] * Tm[2][g];
-        } else {
-#pragma unroll
-          for (int b = 0; b < 4; ++b)
-#pragma unroll
-            for (int g = b; g < 4; ++g)
-              sM[S::usym(b, g) * NQ + pt] = Cm[0][b] * Cm[0][g] + Cm[1][b] * Cm[1][g] + Cm[2][b] * Cm[2][g];
-        }
+          for (int g = b; g < 4; ++g)
+            sM[S::usym(b, g) * NQ + pt] = Cm[0][b] * Cm[0][g] + Cm[1][b] * Cm[1][g] + Cm[2][b] * Cm[2][g];
       }
     }
     __syncthreads();
@@ -872,6 +917,15 @@ __global__ void __launch_bounds__(256, (SCfg<P, Q, KIND>::SZ_TOTAL * 8 > 113 * 1
 __device__ __forceinline__ void nb_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void nb_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+// ---- async bulk copy shared -> global (TMA engine; SASS: UBLKCP), bulk-group completion (as in eval_tensor_sf.cu)
+__device__ __forceinline__ void ws_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void ws_bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ws_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ws_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 template <int P, int Q, int KIND>
 struct WCfg {
   static constexpr int NWM = 8, NWH = 8, NT = 32 * (NWM + NWH), NTH = 32 * NWH, NTM = 32 * NWM;
@@ -879,7 +933,11 @@ struct WCfg {
   using F = FCfg<P, Q>;
   static constexpr int NCP = S::ELAS ? 3 : 1;
   static constexpr int SZ_B3 = S::K3 * S::LDB2;
-  static constexpr int SZ_K = F::ev(S::NP * S::NB * NCP);  // the rows (i0, i1) of one i2 (x the three b-blocks)
+  // tile buffer: the rows (i0, i1) of one i2 (x the three b-blocks).  Row slots of RSK doubles (even: 16-byte aligned slots);
+  // a row starts at slot + 0 or + 1 -- whichever gives it the 16-byte phase of its destination in global memory (rows of
+  // 125 / 375 doubles alternate there) -- so that it can leave through ONE async bulk store of the TMA engine
+  static constexpr int RSK = F::ev(S::NB * NCP + 1);
+  static constexpr int SZ_K = S::NP * RSK;
   static constexpr int SZ_TOTAL =
       F::SZ_T + F::SZ_W + S::SZ_CS + S::SZ_X + S::SZ_M + S::SZ_T2 + S::SZ_T1 + S::SZ_B2 + SZ_B3 + SZ_K + F::SZ_T;
   static constexpr bool FITS = SZ_TOTAL * 8 <= 227 * 1024;
@@ -890,7 +948,7 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
     PatchDev Pd, long long elem_begin, long long nelem, const double* __restrict__ tab0,
     const double* __restrict__ tab1, const double* __restrict__ tab2, const double* __restrict__ w0,
     const double* __restrict__ w1, const double* __restrict__ w2, ElasCoef coef, double fconst,
-    double* __restrict__ Ke, double* __restrict__ fe, WTabs wt) {
+    double* __restrict__ Ke, double* __restrict__ fe, WTabs wt, int bulk_rows) {
   using C = FCfg<P, Q>;
   using WC = WCfg<P, Q, KIND>;
   using S = typename WC::S;
@@ -900,6 +958,10 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
   constexpr int NT = WC::NT, NTH = WC::NTH, NTM = WC::NTM;
   constexpr int LDA2 = S::LDA2, LDB2 = S::LDB2, LDA3 = S::LDA3;
   constexpr int NPASS = NCP * NB1 * NCP;
+  constexpr int RSK = WC::RSK;
+  constexpr bool ODDK = (NROWK & 1) != 0;  // rows of K_e alternate between the two 16-byte phases
+  static_assert((C::SZ_T + C::SZ_W + S::SZ_CS + S::SZ_X + S::SZ_M + S::SZ_T2 + S::SZ_T1 + S::SZ_B2 + WC::SZ_B3) % 2 == 0 &&
+                    RSK % 2 == 0, "tile-buffer row slots must be 16-byte aligned");
   // T1 is double-buffered (FULL / FREE barriers per buffer: + 0 / + 1): stage 1 of pass k + 1 (helper warps) overlaps stage 2
   // of pass k (DMMA warps).  With one buffer the two were serialised -- pass period = stage 1 + stage 2, 6.0 k cycles at C3
   // elasticity (tools/ws_phase.py) -- although they run on different warps.  T2 needs one buffer only: stages 2 and 3 of a
@@ -919,6 +981,7 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
   double* const sK = sB3 + WC::SZ_B3;
   double* const sTw = sK + WC::SZ_K;  // weighted tables (tensor-product weights)
   const bool useW = wt.t0 != nullptr;
+  const bool useB = useW && bulk_rows;  // rows leave by async bulk stores
   const double* const sTc = useW ? sTw : sT;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool is_mma = warp < WC::NWM;
@@ -943,22 +1006,27 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
         t2off[s][h] = (has2 && m < S::M2 && n < NP) ? ((n % NB1) + NB1 * (m / Q) + NP * (n / NB1)) * LDA3 + (m % Q) : -1;
       }
   }
-  // stage 3: column n of a tile is (j0, i0) = (n % NB1, n / NB1): offset into the tile buffer i0 * (NB * NCP) + j0 * NCP
+  // stage 3: column n of a tile is (j0, i0) = (n % NB1, n / NB1): offset into the tile buffer i0 * RSK + j0 * NCP; the
+  // buffer row is i0 + NB1 i1, its start shifted by (row + group parity) & 1 when the rows of K_e alternate in phase:
+  // bit 2 nt + h of pc3 = parity of i0, bit u of pr3 = parity of NB1 i1
   int c3[S::NT3][2];
+  unsigned pc3 = 0, pr3 = 0;
 #pragma unroll
   for (int nt = 0; nt < S::NT3; ++nt)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int n = 8 * nt + 2 * lc + h;
-      c3[nt][h] = n < NP ? (n / NB1) * (NB * NCP) + (n % NB1) * NCP : -1;
+      c3[nt][h] = n < NP ? (n / NB1) * RSK + (n % NB1) * NCP : -1;
+      if (ODDK && n < NP) pc3 |= (unsigned)((n / NB1) & 1) << (2 * nt + h);
     }
-  // stage 3: row lr of this warp's u-th tile row is (j1, j2, i1): offset NB1 i1 * (NB * NCP) + (NB1 j1 + NP j2) * NCP
+  // stage 3: row lr of this warp's u-th tile row is (j1, j2, i1): offset NB1 i1 * RSK + (NB1 j1 + NP j2) * NCP
   constexpr int NMT = (S::MT3 + WC::NWM - 1) / WC::NWM;
   int r3[NMT];
 #pragma unroll
   for (int u = 0; u < NMT; ++u) {
     const int mp = 8 * (warp + WC::NWM * u) + lr;
-    r3[u] = (is_mma && mp < S::M3) ? (NB1 * (mp / NP)) * (NB * NCP) + (NB1 * (mp % NB1) + NP * ((mp / NB1) % NB1)) * NCP : -1;
+    r3[u] = (is_mma && mp < S::M3) ? (NB1 * (mp / NP)) * RSK + (NB1 * (mp % NB1) + NP * ((mp / NB1) % NB1)) * NCP : -1;
+    if (ODDK && is_mma && mp < S::M3) pr3 |= (unsigned)((NB1 * (mp / NP)) & 1) << u;
   }
 
   IGAB_WPT_BEGIN
@@ -1021,6 +1089,10 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
     __syncthreads();
     IGAB_WPT(is_mma ? 10 : 11)
     double* const K = Ke + el * (long long)NROWK * NROWK;
+    // 16-byte phase (0 / 1, in doubles) of row `row` of the group (i2, a) of this element in global memory:
+    // (kpar + ((row + NP i2) NCP + a) NROWK) & 1 = gpar(i2, a) ^ (row & 1) for odd NROWK, kpar otherwise
+    const unsigned kpar = (unsigned)(reinterpret_cast<unsigned long long>(K) >> 3) & 1u;
+    auto gpar = [&](int i2, int ca) -> unsigned { return ODDK ? (kpar ^ (unsigned)((NP * i2 * NCP + ca) & 1)) : kpar; };
 
     if (is_mma) {
       // ================================ DMMA warps: stage 2, stage 3 ================================================
@@ -1031,9 +1103,11 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
         for (int nt = 0; nt < S::NT3; ++nt) b3[ks][nt] = sB3[(4 * ks + lc) * LDB2 + 8 * nt + lr];
       for (int k = 0; k < NPASS; ++k) {
         const int cb = k % NCP;
+        const unsigned gp = gpar((k / NCP) % NB1, k / (NCP * NB1));
         double* const T2 = sT2;
         const double* const T1 = (k & 1) ? sT1b : sT1;
-        if (k > 0) nb_sync(BAR_MMA2, NTM);  // every DMMA warp has left stage 3 of the previous pass: T2 may be rewritten
+        // every DMMA warp has left stage 3 of the previous pass: T2 may be rewritten (the bulk path has just met there)
+        if (k > 0 && !(useB && cb == 0)) nb_sync(BAR_MMA2, NTM);
         nb_sync(BAR_T1_FULL + (k & 1), NT);
         IGAB_WPT(0)
         // ---- stage 2: C_g[(j2,q0)][pi1] = sum_{k in g} T1[.][k] B2[k][.]  ->  T2[j1 + NB1 j2 + NP i1][g Q + q0]
@@ -1083,8 +1157,12 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
         }
         IGAB_WPT(1)
         if (k + 2 < NPASS) nb_arrive(BAR_T1_FREE + (k & 1), NT);  // buffer consumed: the helpers may write pass k+2 into it
-        nb_sync(BAR_MMA, NTM);                           // T2 of this pass complete
-        if (cb == 0 && k > 0) nb_sync(BAR_K_FREE, NT);   // the epilogue of the previous rows has left the tile buffer
+        if (useB && cb == 0 && k > 0) {  // the engine has read this warp's rows of the previous group out of the tile buffer
+          if (lane == 0) ws_bulk_wait_read();
+          __syncwarp();
+        }
+        nb_sync(BAR_MMA, NTM);                                     // T2 of this pass complete (and the tile buffer free)
+        if (!useB && cb == 0 && k > 0) nb_sync(BAR_K_FREE, NT);    // the epilogue of the previous rows has left the tile buffer
         IGAB_WPT(2)
         // ---- stage 3: G[(j1,j2,i1)][pi0] = sum_{(g,q0)} T2 B3, unscaled, into the tile buffer
 #pragma unroll
@@ -1103,47 +1181,55 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
           }
           if (r3[u] >= 0) {
             double* const kb = sK + r3[u] + cb;
+            const unsigned t = gp ^ (pr3 >> u);
 #pragma unroll
             for (int nt = 0; nt < S::NT3; ++nt)
 #pragma unroll
               for (int h = 0; h < 2; ++h)
-                if (c3[nt][h] >= 0) kb[c3[nt][h]] = acc[nt][h];
+                if (c3[nt][h] >= 0) kb[c3[nt][h] + (int)(((pc3 >> (2 * nt + h)) ^ t) & 1u)] = acc[nt][h];
           }
         }
         IGAB_WPT(3)
         if (cb == NCP - 1) {
           __threadfence_block();
-          nb_arrive(BAR_K_FULL, NT);
+          if (useB) {
+            // ---- the NP rows (i0, i1) of this i2 (x component a) are complete.  Tensor-product weights are inside the
+            //      tables, so a row is a plain copy: it leaves through ONE async bulk store (lane 0 of the warp that takes
+            //      the row; the odd double before / after the 16-byte aligned run by lanes 1 / 2), issued by the DMMA
+            //      warps themselves -- three instructions per warp -- and read out of the tile buffer by the TMA engine
+            //      while they run stage 2 of the next pass.  The helpers have no epilogue at all: their copy loop
+            //      (1.1 MB of shared loads / global stores per element) and the FULL / FREE hand-offs put them behind
+            //      with stage 1, the critical path of the pass pipeline (tools/ws_phase.py).
+            ws_fence_proxy_async();  // generic-proxy writes of the tile buffer -> visible to the async proxy
+            nb_sync(BAR_MMA2, NTM);
+            const int i2 = (k / NCP) % NB1, ca = k / (NCP * NB1);
+            for (int row = warp; row < NP; row += WC::NWM) {
+              const int i = row + NP * i2;
+              const int sh = (int)(ODDK ? (gp ^ (unsigned)(row & 1)) : gp);
+              const double* src = sK + row * RSK + sh;
+              double* dst = ELAS ? K + (long long)(i * 3 + ca) * NROWK : K + (long long)i * NB;
+              const int nbulk = (NROWK - sh) & ~1;  // src + sh and dst + sh are 16-byte aligned
+              if (lane == 0) ws_bulk_store(dst + sh, src + sh, nbulk * 8);
+              else if (lane == 1 && sh) dst[0] = src[0];
+              else if (lane == 2 && sh + nbulk < NROWK) dst[NROWK - 1] = src[NROWK - 1];
+            }
+            if (lane == 0) ws_bulk_commit();
+            __syncwarp();
+          } else {
+            nb_arrive(BAR_K_FULL, NT);
+          }
         }
+      }
+      if (useB) {  // the next element's first pass writes the tile buffer without a hand-off
+        if (lane == 0) ws_bulk_wait_read();
+        __syncwarp();
+        if (fe) nb_arrive(BAR_K_FULL, NT);  // stage 2 of the last pass has read T1: the helpers' load vector may use it
       }
     } else {
       // ================================ helper warps: stage 1, epilogue ============================================
       auto point_matrices = [&](int ca, int cb) {  // elasticity: M4 = C^T Cf[a][.][b][.] C per point
         if constexpr (ELAS) {
-          for (int pt = htid; pt < NQ; pt += NTH) {
-            const double* o = sC + CS * pt;
-            double Cm[3][4], Tm[3][4];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              Cm[c][0] = -o[1 + c];
-#pragma unroll
-              for (int d = 0; d < 3; ++d) Cm[c][1 + d] = o[4 + 3 * c + d];
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                double t = 0.0;
-#pragma unroll
-                for (int cp = 0; cp < 3; ++cp) t = fma(coef.cf[((ca * 3 + c) * 3 + cb) * 3 + cp], Cm[cp][g], t);
-                Tm[c][g] = t;
-              }
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-#pragma unroll
-              for (int g = 0; g < 4; ++g)
-                sM[(b * 4 + g) * NQ + pt] = Cm[0][b] * Tm[0][g] + Cm[1][b] * Tm[1][g] + Cm[2][b] * Tm[2][g];
-          }
+          for (int pt = htid; pt < NQ; pt += NTH) elas_point_matrix<CS>(sC, coef, ca, cb, pt, sM + pt, NQ);
           nb_sync(BAR_HLP, NTH);
         }
       };
@@ -1209,21 +1295,24 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
           stage1((k1 / NCP) % NB1, k1 & 1);
           IGAB_WPT(5)
         }
-        if (cb == NCP - 1) {
+        if (cb == NCP - 1 && !useB) {
           nb_sync(BAR_K_FULL, NT);
           IGAB_WPT(6)
-          // ---- epilogue: the NP rows (i0, i1) of this i2 (x component a), scaled by w_i w_j, as complete rows: a warp
-          //      takes whole rows, its lanes consecutive columns (coalesced 256-byte stores)
+          // ---- epilogue without the bulk path (general weights: scaled by w_i w_j; or IGAB_WS_BULK=0): the NP rows (i0, i1)
+          //      of this i2 (x component a) as complete rows; a warp takes whole rows, its lanes consecutive columns
+          //      (coalesced 256-byte stores)
           {
             const int hw = warp - WC::NWM;
+            const unsigned gp = gpar(i2, ca);
             for (int row = hw; row < NP; row += WC::NWH) {
               const int i = row + NP * i2;
-              const double wi = sW[i];
-              const double* src = sK + row * NROWK;
+              const int sh = (int)(ODDK ? (gp ^ (unsigned)(row & 1)) : gp);
+              const double* src = sK + row * RSK + sh;
               double* dst = ELAS ? K + (long long)(i * 3 + ca) * NROWK : K + (long long)i * NB;
-              if (useW) {  // the weights are inside the tables: a plain coalesced copy
+              if (useW) {
                 for (int c = lane; c < NROWK; c += 32) dst[c] = src[c];
               } else {
+                const double wi = sW[i];
                 for (int c = lane; c < NROWK; c += 32) dst[c] = src[c] * (wi * sW[ELAS ? c / 3 : c]);
               }
             }
@@ -1236,6 +1325,7 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
       // ---- load vector f_e[i] = sum_q w detJ R_i fconst  (poisson.py:79), sum-factorised as in gram_sf_kernel; the
       //      DMMA warps are done with T1 (every T1_FULL they waited for has been consumed)
       if (fe) {
+        if (useB) nb_sync(BAR_K_FULL, NT);  // (without the bulk path the last epilogue has waited for the DMMA warps)
         double* const fA = sT1;
         double* const fB = sT1 + Q * Q * NB1;
         for (int idx = htid; idx < Q * Q * NB1; idx += NTH) {
@@ -1281,8 +1371,10 @@ igab_status launch_ws(const PatchDev& Pd, SfWorkspace& ws, const ElasCoef& coef,
   KernelCfg kc;
   if (igab_status cst = kernel_config((const void*)gram_ws_kernel<P, Q, KIND>, WC::NT, sm, &kc)) return cst;
   const unsigned grid = (unsigned)std::min<long long>(nel, (long long)kc.blocksPerSm * kc.sms);
-  gram_ws_kernel<P, Q, KIND><<<grid, WC::NT, sm, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0],
-                                                          w_dev[1], w_dev[2], coef, fconst, Ke, fe, wtabs_of(Pd, ws));
+  const char* const benv = getenv("IGAB_WS_BULK");  // 0: the helpers copy the rows themselves (measurement switch)
+  const int bulk_rows = !(benv && benv[0] == '0');
+  gram_ws_kernel<P, Q, KIND><<<grid, WC::NT, sm, stream>>>(Pd, eb, nel, ws.tab[0], ws.tab[1], ws.tab[2], w_dev[0], w_dev[1],
+                                                          w_dev[2], coef, fconst, Ke, fe, wtabs_of(Pd, ws), bulk_rows);
   count_launch();
   IGAB_CUDA_TRY(cudaGetLastError());
   return IGAB_OK;
@@ -1320,6 +1412,7 @@ igab_status launch_elas_sf(const PatchDev& Pd, SfWorkspace& ws, const double* D_
   for (double& v : coef.cf) v = 0.0;
   for (auto& s1 : S)
     for (auto& s2 : S) coef.cf[((s1[1] * 3 + s1[2]) * 3 + s2[1]) * 3 + s2[2]] += D_host[s1[0] * 6 + s2[0]];
+  coef.fill_nz();
   if constexpr (ws_compiled<P, Q, 2>()) {
     if (ws_wanted<P, Q, 2>()) return launch_ws<P, Q, 2>(Pd, ws, coef, fconst, eb, nel, w_dev, Ke, fe, stream);
   }
