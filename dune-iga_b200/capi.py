@@ -29,7 +29,7 @@ EXPORTS = ("igab_last_error_string", "igab_version", "igab_launch_count", "igab_
            "igab_partition_slab", "igab_partition_weighted", "igab_interface_row_ranges", "igab_comm_unique_id", "igab_comm_create",
            "igab_comm_destroy", "igab_comm_info", "igab_exchange_interface_rows", "igab_patch_real_index_maps",
            "igab_load_vector", "igab_load_vector_points", "igab_global_load_vector", "igab_device_numa_node", "igab_eval_tensor_begin", "igab_patch_wait", "igab_refine_knots",
-           "igab_patch_create_from_device")
+           "igab_patch_create_from_device", "igab_refine_operators")
 
 
 class EvalOut(C.Structure):
@@ -59,6 +59,9 @@ def lib():
                                                     C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]
         L.igab_refine_knots.argtypes = [C.c_int, C.c_int, ip, ip, C.POINTER(dp), ip, C.POINTER(dp), C.c_void_p, C.c_int,
                                         C.c_void_p, C.c_int, C.c_void_p]
+        L.igab_refine_operators.argtypes = [C.c_int, C.c_int, ip, C.c_int, ip, ip, ip, C.POINTER(C.c_void_p),
+                                            C.POINTER(C.c_void_p), C.POINTER(dp), C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                            C.c_void_p]
         L.igab_patch_destroy.argtypes = [C.c_void_p]
         L.igab_patch_destroy.restype = None
         L.igab_patch_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
@@ -203,6 +206,55 @@ def refineApply(pd, direction, T, newKnots, newDegree=None):
     if newDegree is not None:
         deg[direction] = newDegree
     return NurbsPatchData(knots, cp_out, deg, pd.dimworld)
+
+
+def refineOperators(pd, ops, cp_dev=None, device_out=False, stream=None):
+    """A chain of 1-D refinement operators applied in HBM (igab_refine_operators): ops = [(direction, T), ...] with T the
+    dense [n_new, n_old] operator of that step (patchdata.knotInsertionOperator / degreeElevationOperator), acting on the
+    net the previous steps produced.  cp_dev: the coarse net as a CUDA tensor (else pd.cp is copied in).  Returns the new
+    net [prod n_new][dimworld+1] as numpy array, or as CUDA tensor with device_out=True."""
+    dim = pd.patchDim
+    ncp = _i32(pd.ncp)
+    cur = list(pd.ncp)
+    band = []
+    for d, T in ops:
+        T = np.asarray(T, float)
+        assert T.shape[1] == cur[d], "operator does not fit the net it is applied to"
+        band.append(banded(T))
+        cur[d] = T.shape[0]
+    nops = len(ops)
+    dirs, nnew = _i32([d for d, _ in ops]), _i32([b[2].shape[0] for b in band])
+    mlen = _i32([b[2].shape[1] for b in band])
+    firsts = (C.c_void_p * max(nops, 1))(*[b[0].ctypes.data for b in band])
+    lens = (C.c_void_p * max(nops, 1))(*[b[1].ctypes.data for b in band])
+    coefs = (dp * max(nops, 1))(*[b[2].ctypes.data_as(dp) for b in band])
+    src = cp_dev if cp_dev is not None else _f64(pd.cp)
+    sa, ss = _ptr(src)
+    nout = int(np.prod(cur))
+    if device_out:
+        import torch
+        out = torch.empty((nout, pd.dimworld + 1), dtype=torch.float64, device="cuda")
+    else:
+        out = np.empty((nout, pd.dimworld + 1))
+    oa, os_ = _ptr(out)
+    _check(lib().igab_refine_operators(dim, pd.dimworld, ncp.ctypes.data_as(ip), nops, dirs.ctypes.data_as(ip),
+                                       nnew.ctypes.data_as(ip), mlen.ctypes.data_as(ip), firsts, lens, coefs, sa, ss, oa,
+                                       os_, stream))
+    return out
+
+
+def degreeElevateAll(pd, factors, cp_dev=None, device_out=False, stream=None):
+    """degreeElevate of every direction with factors[d] > 0 (NURBSGrid::globalDegreeElevate, nurbsgrid.hh:166-178 ->
+    degreeElevate, nurbsalgorithms.hh:264-439) without the net leaving HBM: the 1-D elevation operators are built on the
+    host (they depend on one knot vector each), the chain runs on the device.  Returns (degree, knotSpans, net)."""
+    from .patchdata import degreeElevationOperator
+    ops, knots, deg = [], [k.copy() for k in pd.knotSpans], list(pd.degree)
+    for d, t in enumerate(factors):
+        if t > 0:
+            knots[d], E = degreeElevationOperator(pd.knotSpans[d], pd.degree[d], t)
+            deg[d] += t
+            ops.append((d, E))
+    return deg, knots, refineOperators(pd, ops, cp_dev=cp_dev, device_out=device_out, stream=stream)
 
 
 def refineKnots(pd, newKnotVectors, cp_dev=None, device_out=False, stream=None):

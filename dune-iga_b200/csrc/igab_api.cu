@@ -1236,6 +1236,88 @@ igab_status igab_refine_apply(int dim, int dimworld, const int* ncp_old, int dir
   return st;
 }
 
+// A chain of banded 1-D operators (knot insertion, degree elevation, any linear refinement) applied direction by direction
+// with every intermediate net in HBM; only the operators (n_new x maxlen doubles each) cross PCIe.
+igab_status igab_refine_operators(int dim, int dimworld, const int* ncp_old, int nops, const int* direction,
+                                  const int* n_new, const int* maxlen, const int32_t* const* first,
+                                  const int32_t* const* len, const double* const* coef, const double* cp_in,
+                                  igab_memspace in_space, double* cp_out, igab_memspace out_space, void* stream_) {
+  if (dim < 1 || dim > kMaxDim || dimworld < 1 || dimworld > 3 || !ncp_old || nops < 0 || !cp_in || !cp_out ||
+      (nops > 0 && (!direction || !n_new || !maxlen || !first || !len || !coef))) {
+    set_error("refine_operators: invalid argument");
+    return IGAB_INVALID_ARGUMENT;
+  }
+  int ncp[kMaxDim] = {1, 1, 1};
+  long long nin = 1;
+  for (int d = 0; d < dim; ++d) {
+    if (ncp_old[d] < 1) {
+      set_error("refine_operators: empty net");
+      return IGAB_INVALID_ARGUMENT;
+    }
+    ncp[d] = ncp_old[d];
+    nin *= ncp[d];
+  }
+  long long nmax = nin, nout = nin;
+  size_t ibytes = 0, cbytes = 0;
+  for (int o = 0; o < nops; ++o) {
+    const int d = direction[o];
+    if (d < 0 || d >= dim || n_new[o] < 1 || maxlen[o] < 1 || !first[o] || !len[o] || !coef[o]) {
+      set_error("refine_operators: invalid operator");
+      return IGAB_INVALID_ARGUMENT;
+    }
+    for (int i = 0; i < n_new[o]; ++i)
+      if (len[o][i] < 0 || len[o][i] > maxlen[o] || first[o][i] < 0 || first[o][i] + len[o][i] > ncp[d]) {
+        set_error("refine_operators: operator row outside the net it is applied to");
+        return IGAB_INVALID_ARGUMENT;
+      }
+    nout = nout / ncp[d] * n_new[o];
+    ncp[d] = n_new[o];
+    nmax = std::max(nmax, nout);
+    ibytes = std::max(ibytes, sizeof(int) * (size_t)n_new[o]);
+    cbytes = std::max(cbytes, sizeof(double) * (size_t)n_new[o] * maxlen[o]);
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const size_t row = sizeof(double) * (dimworld + 1);
+  const cudaMemcpyKind kin = in_space == IGAB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  const cudaMemcpyKind kout = out_space == IGAB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  double *buf[2] = {nullptr, nullptr}, *dCoef = nullptr;
+  int *dFirst = nullptr, *dLen = nullptr;
+  cudaError_t e = cudaMallocAsync(&buf[0], row * nmax, stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&buf[1], row * nmax, stream);
+  if (e == cudaSuccess && nops > 0) e = cudaMallocAsync(&dFirst, ibytes, stream);
+  if (e == cudaSuccess && nops > 0) e = cudaMallocAsync(&dLen, ibytes, stream);
+  if (e == cudaSuccess && nops > 0) e = cudaMallocAsync(&dCoef, cbytes, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(buf[0], cp_in, row * nin, kin, stream);
+  igab_status st = e == cudaSuccess ? IGAB_OK : cuda_fail(e, "refine_operators: buffers");
+  for (int d = 0; d < dim; ++d) ncp[d] = ncp_old[d];
+  int cur = 0;
+  for (int o = 0; o < nops && !st; ++o) {
+    // the operator arrays are pageable host memory and the staging buffers are reused: one operator in flight at a time
+    e = cudaMemcpyAsync(dFirst, first[o], sizeof(int) * n_new[o], cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dLen, len[o], sizeof(int) * n_new[o], cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(dCoef, coef[o], sizeof(double) * n_new[o] * maxlen[o], cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) st = cuda_fail(e, "refine_operators: operator H2D");
+    if (!st)
+      st = refine_apply(dim, dimworld, ncp, direction[o], n_new[o], maxlen[o], dFirst, dLen, dCoef, buf[cur], buf[cur ^ 1],
+                        stream);
+    if (!st && (e = cudaStreamSynchronize(stream)) != cudaSuccess) st = cuda_fail(e, "refine_operators: apply");
+    ncp[direction[o]] = n_new[o];
+    cur ^= 1;
+  }
+  if (!st) {
+    e = cudaMemcpyAsync(cp_out, buf[cur], row * nout, kout, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) st = cuda_fail(e, "refine_operators: output");
+  }
+  if (buf[0]) cudaFreeAsync(buf[0], stream);
+  if (buf[1]) cudaFreeAsync(buf[1], stream);
+  if (dFirst) cudaFreeAsync(dFirst, stream);
+  if (dLen) cudaFreeAsync(dLen, stream);
+  if (dCoef) cudaFreeAsync(dCoef, stream);
+  return st;
+}
+
 igab_status igab_refine_knots(int dim, int dimworld, const int* degree, const int* nknots_old,
                               const double* const* knots_old, const int* nknots_new, const double* const* knots_new,
                               const double* cp_in, igab_memspace in_space, double* cp_out, igab_memspace out_space,

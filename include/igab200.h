@@ -208,6 +208,17 @@ igab_status igab_refine_apply(int dim, int dimworld, const int* ncp_old, int dir
                               const int32_t* first, const int32_t* len, const double* coef, const double* cp_in,
                               double* cp_out);
 
+/* A CHAIN of such operators -- degree elevation (degreeElevate, dune/iga/nurbsalgorithms.hh:264-439) and / or knot
+ * insertion of several directions, as NURBSGrid::globalDegreeElevate / globalRefine apply them one direction after the other
+ * (dune/iga/nurbsgrid.hh:130-178) -- with every intermediate net in HBM: operator o (row-banded as above, HOST arrays) acts
+ * along direction[o] on the net the previous operators produced.  cp_in [prod ncp_old][dimworld+1] in `in_space`, cp_out
+ * [prod n_final][dimworld+1] in `out_space`; with IGAB_DEVICE on both sides and igab_patch_create_from_device only the
+ * operators (n_new x maxlen doubles each) cross PCIe.  nops = 0 copies the net.  Synchronises `stream` before returning. */
+igab_status igab_refine_operators(int dim, int dimworld, const int* ncp_old, int nops, const int* direction,
+                                  const int* n_new, const int* maxlen, const int32_t* const* first,
+                                  const int32_t* const* len, const double* const* coef, const double* cp_in,
+                                  igab_memspace in_space, double* cp_out, igab_memspace out_space, void* stream);
+
 /* Knot refinement of ALL directions without leaving HBM (the chain NURBSGrid::globalRefine -> knotRefinement per direction,
  * dune/iga/nurbsgrid.hh:130-165 -> dune/iga/nurbsalgorithms.hh:441-528): for every direction whose knot vector grows, the
  * knot-insertion operator is built on the device (Oslo recursion, one thread per new control-point row) and applied to

@@ -1,6 +1,8 @@
 """GPU parity tests (-m gpu) of the entry points added in round 2: real <-> direct element index maps, the multi-block
 ordered scan behind them and behind the trim compaction of the DOF map, load vectors with a per-point source, and the
 handle's stream discipline.  Everything goes through the C-ABI and is compared with the oracle."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -232,6 +234,60 @@ def test_warp_specialised_assembly_kernel_matches_oracle_and_the_barrier_separat
         Kr, fr = O.assemble(kind, [x] * 3, [w] * 3, D=D, fconst=0.7, elem_begin=int(e), elem_end=int(e) + 1)
         assert relerr(out["1"][0][e].reshape(1, -1), Kr.reshape(1, -1)) <= TOL
         assert relerr(out["1"][1][e].reshape(1, -1), fr.reshape(1, -1)) <= TOL
+
+
+def test_device_resident_degree_elevation_chain_matches_host_and_reference():
+    """igab_refine_operators: degree elevation of several directions (and a mixed elevation + knot-insertion chain) applied
+    in HBM, against the host operators (patchdata.degreeElevate), the reference's own degreeElevate
+    (nurbsalgorithms.hh:264-439 through oracle/_ref) and -- the curve must not change -- the geometry map itself."""
+    import torch
+    import refbind as RF
+    cases = [(PFT.small_patch("torus_p2", level=0)["patch"], (1, 2)), (PD.perturbed(PD.thickCylinder(2, (1, 0, 1)), seed=5), (1, 0, 2)),
+             (PFT.small_patch("mixed_deg_3d", level=0)["patch"], (2, 1, 1)), (PFT.small_patch("curve_p3", level=0)["patch"], (1,))]
+    for pd, fac in cases:
+        host = pd
+        for d, t in enumerate(fac):
+            host = host.degreeElevate(d, t)
+        deg, knots, got = capi.degreeElevateAll(pd, fac)
+        assert list(deg) == list(host.degree) and all(np.array_equal(a, b) for a, b in zip(knots, host.knotSpans))
+        scale = np.abs(host.cp).max()
+        assert got.shape == host.cp.shape and np.abs(got - host.cp).max() <= 1e-12 * scale
+        if RF.available():
+            R = RF.RefPatch.create(pd.degree, pd.knotSpans, pd.cp, pd.dimworld)
+            for d, t in enumerate(fac):
+                if t:
+                    R = R.degree_elevate(d, t)
+            assert np.abs(got - np.asarray(R.cp).reshape(got.shape)).max() <= 1e-11 * scale
+        # device in / device out, handle from the device net; the map x(xi) is the one of the original patch
+        gdev = capi.degreeElevateAll(pd, fac, cp_dev=torch.from_numpy(np.ascontiguousarray(pd.cp)).cuda(), device_out=True)[2]
+        assert np.array_equal(gdev.cpu().numpy(), got)
+        Pe = capi.Patch.fromDeviceNet(deg, knots, gdev, pd.dimworld)
+        P0 = capi.Patch.fromPatchData(pd)
+        xi = [PD.gaussLegendre01(3)[0]] * pd.patchDim
+        a, b = Pe.evalTensor(xi, order=1, want=("x", "Jt")), P0.evalTensor(xi, order=1, want=("x", "Jt"))
+        assert np.abs(a["x"] - b["x"]).max() <= 1e-12 * np.abs(b["x"]).max()
+        assert np.abs(a["Jt"] - b["Jt"]).max() <= 1e-10 * np.abs(b["Jt"]).max()
+    # a mixed chain: elevate direction 0, then insert knots in direction 1 of the elevated net
+    pd = cases[0][0]
+    U0, E0 = PD.degreeElevationOperator(pd.knotSpans[0], pd.degree[0], 1)
+    nk = PD.generateRefinedKnots(pd.knotSpans, 1, 2)
+    U1, T1 = PD.knotInsertionOperator(pd.knotSpans[1], pd.degree[1], nk)
+    got = capi.refineOperators(pd, [(0, E0), (1, T1)])
+    host = pd.degreeElevate(0, 1).knotRefinement(nk, 1)
+    assert np.abs(got - host.cp).max() <= 1e-12 * np.abs(host.cp).max()
+    # no operator: a copy; an operator that does not fit: refused
+    assert np.array_equal(capi.refineOperators(pd, []), pd.cp)
+    first, ln, coef = capi.banded(E0)
+    first = first.copy(); first[-1] += 1
+    ncp = np.asarray(pd.ncp, np.int32)
+    out = np.empty((E0.shape[0] * pd.ncp[1], pd.dimworld + 1))
+    one = lambda a: np.asarray([a], np.int32)
+    st = capi.lib().igab_refine_operators(pd.patchDim, pd.dimworld, ncp.ctypes.data_as(capi.ip), 1, one(0).ctypes.data_as(capi.ip),
+                                          one(E0.shape[0]).ctypes.data_as(capi.ip), one(coef.shape[1]).ctypes.data_as(capi.ip),
+                                          (C.c_void_p * 1)(first.ctypes.data), (C.c_void_p * 1)(ln.ctypes.data),
+                                          (capi.dp * 1)(coef.ctypes.data_as(capi.dp)), np.ascontiguousarray(pd.cp).ctypes.data,
+                                          capi.HOST, out.ctypes.data, capi.HOST, None)
+    assert st == capi.INVALID_ARGUMENT
 
 
 def test_device_resident_refinement_chain_matches_host_and_reference():
