@@ -449,6 +449,50 @@ def test_symmetric_assembly_kernel_matches_oracle_and_the_full_kernel(p, q, kind
         assert relerr(out["1"][1][e].reshape(1, -1), fr.reshape(1, -1)) <= TOL
 
 
+@pytest.mark.parametrize("p", [3, 4])
+@pytest.mark.parametrize("kind", [capi.ASM_POISSON, capi.ASM_MASS, capi.ASM_ELASTICITY])
+def test_warp_specialised_kernel_bulk_store_epilogue(p, kind, monkeypatch):
+    """gram_ws_kernel with tensor-product weights: the rows of K_e leave the tile buffer through async bulk stores issued by
+    the DMMA warps (row start shifted to the 16-byte phase of its destination; rows of 125 / 375 doubles alternate in
+    phase, rows of 64 / 192 do not) against the helpers' copy loop (IGAB_WS_BULK=0): same bits for K_e and the load vector,
+    also when K_e starts at an address that is 8 mod 16 (nothing written outside the view), and the oracle on a sample --
+    with an isotropic D (zero coefficients skipped in the point matrices) and a full D (nothing skipped)."""
+    import torch
+    pd = PD.thickCylinder(p, (2, 1, 2))
+    spec = dict(degree=pd.degree, knots=pd.knotSpans, cp=pd.cp, dimworld=3)
+    x, w = PD.gaussLegendre01(p + 1)
+    monkeypatch.setenv("IGAB_ELAS_SF", "1")
+    monkeypatch.setenv("IGAB_GRAM_WS", "1")
+    monkeypatch.setenv("IGAB_GRAM_SYM", "0")
+    P, O = gpu_patch(spec), port_for(spec)
+    n = P.nb * (3 if kind == capi.ASM_ELASTICITY else 1)
+    rng = np.random.default_rng(7)
+    A = rng.uniform(-1, 1, (6, 6))
+    lam, mu = 0.6, 0.4
+    Diso = np.zeros((6, 6)); Diso[:3, :3] = lam; Diso[np.arange(3), np.arange(3)] = lam + 2 * mu; Diso[np.arange(3, 6), np.arange(3, 6)] = mu
+    for D in ([Diso, A @ A.T + np.eye(6)] if kind == capi.ASM_ELASTICITY else [None]):
+        out = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("IGAB_WS_BULK", mode)
+            for off in (0, 1):
+                buf = torch.full((P.nelem * n * n + 2,), -7.0, dtype=torch.float64, device="cuda")
+                Ke = buf[off:off + P.nelem * n * n].view(P.nelem, n, n)
+                assert Ke.data_ptr() % 16 == 8 * off
+                fe = torch.full((P.nelem, n), float("nan"), dtype=torch.float64, device="cuda")
+                P.assemble(kind, [x] * 3, [w] * 3, D=D, fconst=0.9, Ke=Ke, fe=fe)
+                torch.cuda.synchronize()
+                assert float(buf[-1]) == -7.0 and float(buf[-2 + off]) == -7.0 and (off == 0 or float(buf[0]) == -7.0)
+                out[(mode, off)] = (Ke.cpu().numpy(), fe.cpu().numpy())
+        ref = out[("0", 0)]
+        assert np.isfinite(ref[0]).all() and np.isfinite(ref[1]).all()
+        for key, (K, f) in out.items():
+            assert np.array_equal(K, ref[0]) and np.array_equal(f, ref[1]), key
+        for e in (0, 1, P.nelem - 1):
+            Kr, fr = O.assemble(kind, [x] * 3, [w] * 3, D=D, fconst=0.9, elem_begin=e, elem_end=e + 1)
+            assert relerr(ref[0][e].reshape(1, -1), Kr.reshape(1, -1)) <= TOL
+            assert relerr(ref[1][e].reshape(1, -1), fr.reshape(1, -1)) <= TOL
+
+
 @pytest.mark.parametrize("name", ["plate_hole_p2", "cylinder_p3", "square_p3"])
 def test_output_pointers_that_are_only_8_byte_aligned(name):
     """The async bulk stores (TMA) of the tensor-rule kernels need 16-byte aligned global rows; a caller's double* is only
