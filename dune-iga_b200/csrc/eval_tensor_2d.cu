@@ -55,6 +55,7 @@ igab_status ensure_tables2d(const PatchDev& Pd, SfWorkspace& ws, int Q, int orde
     same = ws.nq1[d] == Q && (int)ws.xi[d].size() == Q;
     for (int q = 0; q < Q && same; ++q) same = ws.xi[d][q] == xi1d_host[d][q];
   }
+  ws.built2d = !same;  // a tables kernel precedes the caller's launch in the stream
   if (same) return IGAB_OK;
   for (int d = 0; d < 2; ++d) {
     const size_t n = (size_t)Pd.nel[d] * Q * (Pd.degree[d] + 1) * (order + 1);
@@ -180,6 +181,19 @@ __global__ void __launch_bounds__(128, (ORDER >= 2 ? 3 : (P <= 2 ? 5 : (P >= 4 ?
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* slab = smem2 + (size_t)warp * (C::SLAB * C::SLABS);
   int fld = 0;  // fields flushed so far (slab ring of the bulk path)
+  // Programmatic dependent launch: the next launch of this kernel in the stream may become resident while this one drains.
+  // Tensor rules read only handle-owned buffers (tables, control net, spans) that no kernel preceding this launch wrote --
+  // launch_2d drops the attribute when it has just rebuilt the tables, and control-net updates are copies, which keep the
+  // plain stream order -- so the kernel does everything up to its first store (loads, the homogeneous sums of its first
+  // chunk) before it waits for its predecessor to complete (griddepcontrol.wait: outputs may alias the predecessor's).
+  // Point lists read caller arrays that the preceding kernel may have produced: they wait before their first load, and
+  // only the launch itself overlaps.  At config C1 (31 us per launch) launch gap and ramp are a tenth of the time.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  bool pdl_waited = false;
+  if constexpr (LIST) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_waited = true;
+  }
   // persistent warps: the grid is a fixed number of resident blocks per SM (no partial last wave: at config C1 the
   // one-block-per-128-points grid ran 6.2 waves), every warp walks chunks of 32 points with the grid's stride
   const long long wstride = (long long)gridDim.x * (blockDim.x >> 5) * 32;
@@ -264,6 +278,10 @@ __global__ void __launch_bounds__(128, (ORDER >= 2 ? 3 : (P <= 2 ? 5 : (P >= 4 ?
   }
 
   // ---- pass 2 + stores, field by field
+  if (!pdl_waited) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_waited = true;
+  }
   if (out.N) {
     double row[NB];
 #pragma unroll
@@ -359,6 +377,25 @@ __global__ void __launch_bounds__(128, (ORDER >= 2 ? 3 : (P <= 2 ? 5 : (P >= 4 ?
   }
 }
 
+// launch with the programmatic-stream-serialization attribute (see the kernel); allow = false or IGAB_NO_PDL=1: plain launch
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(bool allow, void (*kernel)(KArgs...), unsigned blocks, unsigned threads, size_t smem,
+                       cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  const char* env = getenv("IGAB_NO_PDL");
+  const bool pdl = allow && !(env && env[0] == '1');
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <int DW, int P, int Q, int ORDER>
 igab_status launch_2d(const PatchDev& Pd, SfWorkspace& ws, const PointSource& src, const double* const* xi1d_host,
                       long long nelem, const EvalOutDev& out, cudaStream_t stream) {
@@ -378,8 +415,9 @@ igab_status launch_2d(const PatchDev& Pd, SfWorkspace& ws, const PointSource& sr
     set_error("eval_tensor: too many points for one launch");
     return IGAB_INVALID_ARGUMENT;
   }
-  eval_2d_kernel<DW, P, Q, ORDER, false><<<(unsigned)blocks, WARPS * 32, smem, stream>>>(
-      Pd, src.elem_begin, npts, ws.tab[0], ws.tab[1], nullptr, nullptr, out);
+  IGAB_CUDA_TRY(launch_pdl(!ws.built2d, eval_2d_kernel<DW, P, Q, ORDER, false>, (unsigned)blocks, WARPS * 32, smem, stream, Pd,
+                           (long long)src.elem_begin, npts, (const double*)ws.tab[0], (const double*)ws.tab[1],
+                           (const int*)nullptr, (const double*)nullptr, out));
   count_launch();
   IGAB_CUDA_TRY(cudaGetLastError());
   return IGAB_OK;
@@ -416,8 +454,8 @@ igab_status launch_list(const PatchDev& Pd, const PointSource& src, long long np
     set_error("eval_points: too many points for one launch");
     return IGAB_INVALID_ARGUMENT;
   }
-  eval_2d_kernel<DW, P, 0, ORDER, true><<<(unsigned)blocks, WARPS * 32, smem, stream>>>(Pd, 0, npts, nullptr, nullptr,
-                                                                                       src.elem, src.xi, out);
+  IGAB_CUDA_TRY(launch_pdl(true, eval_2d_kernel<DW, P, 0, ORDER, true>, (unsigned)blocks, WARPS * 32, smem, stream, Pd, 0LL, npts,
+                           (const double*)nullptr, (const double*)nullptr, (const int*)src.elem, (const double*)src.xi, out));
   count_launch();
   IGAB_CUDA_TRY(cudaGetLastError());
   return IGAB_OK;

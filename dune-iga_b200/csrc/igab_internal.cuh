@@ -69,6 +69,7 @@ struct SfWorkspace {
   double* wtab[kMaxDim] = {nullptr, nullptr, nullptr};
   size_t wtabCap[kMaxDim] = {0, 0, 0};
   bool wvalid = false, wuse = false;  // wuse: set per launch (off inside a graph capture)
+  bool built2d = false;  // ensure_tables2d launched its table kernels in the current call
 };
 
 // orders `stream` behind the handle's previous stream when the caller switches streams (handle scratch is shared)
