@@ -201,27 +201,75 @@ __global__ void __launch_bounds__(FCfg<P, Q>::NT, 2) gram_fused_kernel(
 struct ElasCoef {
   double cf[81];   // [a][c][b][c']
   unsigned nz[9];  // per (a, b): bit 3 c + c' set where cf[a][c][b][c'] != 0 (fill_nz; read by elas_point_matrix only)
+  int ortho;       // every non-zero coefficient has (a==c, b==c') or (a==b, c==c') or (a==c', b==c): orthotropic / isotropic D
   void fill_nz() {
+    ortho = 1;
     for (int ab = 0; ab < 9; ++ab) {
+      const int a = ab / 3, b = ab % 3;
       nz[ab] = 0;
       for (int c = 0; c < 3; ++c)
         for (int cp = 0; cp < 3; ++cp)
-          if (cf[(((ab / 3) * 3 + c) * 3 + ab % 3) * 3 + cp] != 0.0) nz[ab] |= 1u << (3 * c + cp);
+          if (cf[((a * 3 + c) * 3 + b) * 3 + cp] != 0.0) {
+            nz[ab] |= 1u << (3 * c + cp);
+            if (!((a == c && b == cp) || (a == b && c == cp) || (a == cp && b == c))) ortho = 0;
+          }
     }
   }
 };
 
 // elasticity: M4 = C^T Cf[a][.][b][.] C of one point, entry (beta, gamma) stored at dst[(4 beta + gamma) * stride].
-// Terms with a zero coefficient are skipped (warp-uniform branches on coef.nz): an isotropic / orthotropic D leaves 3 of the
-// 9 coefficients of a diagonal pair (a, a) and 2 of an off-diagonal one, and a whole row of the intermediate Cf C is zero
-// off the diagonal -- 60 / 40 FMAs instead of 84.  The helpers' FP64 FMAs queue behind the DMMAs of the other warps on the
-// shared FP64 datapath, so every FMA less is a DMMA slot less on the critical path of the pass pipeline.  The skipped
-// terms are exact zeros: same bits as the full sums.
+// The helpers' FP64 FMAs queue behind the DMMAs of the other warps on the shared FP64 datapath, and this step is on the
+// critical path of the pass pipeline (tools/ws_phase.py), so an orthotropic / isotropic D (the usual case; ElasCoef::ortho)
+// takes its structure literally instead of the 84 FMAs of the general triple product:
+//   a != b:  M4 = n C[a] (x) C[b] + t C[b] (x) C[a],  n = Cf[a][a][b][b], t = Cf[a][b][b][a]   (rows a, b of C only)
+//   a == b:  M4 = sum_c k_c C[c] (x) C[c],            k_c = Cf[a][c][a][c]
+// (tests on the coefficient mask inside the general loops were tried first: ptxas predicates them, all 84 still issue).
+// The terms left out are exact zeros of the general sums, which are taken in the same order: same bits.
 template <int CS>
 __device__ __forceinline__ void elas_point_matrix(const double* sC, const ElasCoef& coef, int ca, int cb, int pt,
                                                   double* dst, int stride) {
   const double* o = sC + CS * pt;
-  const unsigned nz = coef.nz[ca * 3 + cb];
+  if (coef.ortho) {
+    if (ca != cb) {
+      const int lo = min(ca, cb), hi = max(ca, cb);  // rows in ascending order, as the general loop meets them
+      double Cl[4], Ch[4], Tl[4], Th[4];
+      Cl[0] = -o[1 + lo];
+      Ch[0] = -o[1 + hi];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        Cl[1 + d] = o[4 + 3 * lo + d];
+        Ch[1 + d] = o[4 + 3 * hi + d];
+      }
+      // Tm[c][.] = Cf[a][c][b][c'] C[c'][.]: row c = a pairs with c' = b, row c = b with c' = a
+      const double fl = coef.cf[((ca * 3 + lo) * 3 + cb) * 3 + hi], fh = coef.cf[((ca * 3 + hi) * 3 + cb) * 3 + lo];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        Tl[g] = fl * Ch[g];
+        Th[g] = fh * Cl[g];
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) dst[(size_t)(b * 4 + g) * stride] = fma(Ch[b], Th[g], Cl[b] * Tl[g]);
+    } else {
+      double Cm[3][4], Tm[3][4];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        Cm[c][0] = -o[1 + c];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) Cm[c][1 + d] = o[4 + 3 * c + d];
+        const double k = coef.cf[((ca * 3 + c) * 3 + ca) * 3 + c];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) Tm[c][g] = k * Cm[c][g];
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          dst[(size_t)(b * 4 + g) * stride] = fma(Cm[2][b], Tm[2][g], fma(Cm[1][b], Tm[1][g], Cm[0][b] * Tm[0][g]));
+    }
+    return;
+  }
   double Cm[3][4], Tm[3][4];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -230,36 +278,19 @@ __device__ __forceinline__ void elas_point_matrix(const double* sC, const ElasCo
     for (int d = 0; d < 3; ++d) Cm[c][1 + d] = o[4 + 3 * c + d];
   }
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
+  for (int c = 0; c < 3; ++c)
 #pragma unroll
-    for (int g = 0; g < 4; ++g) Tm[c][g] = 0.0;
+    for (int g = 0; g < 4; ++g) {
+      double t = 0.0;
 #pragma unroll
-    for (int cp = 0; cp < 3; ++cp)
-      if (nz & (1u << (3 * c + cp))) {
-        const double f = coef.cf[((ca * 3 + c) * 3 + cb) * 3 + cp];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) Tm[c][g] = fma(f, Cm[cp][g], Tm[c][g]);
-      }
-  }
-  const bool row0 = nz & 7u, row1 = nz & (7u << 3), row2 = nz & (7u << 6);
-#pragma unroll
-  for (int b = 0; b < 4; ++b) {  // one row of M4 at a time: four live accumulators
-    double M[4] = {0.0, 0.0, 0.0, 0.0};
-    if (row0) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) M[g] = fma(Cm[0][b], Tm[0][g], M[g]);
-    }
-    if (row1) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) M[g] = fma(Cm[1][b], Tm[1][g], M[g]);
-    }
-    if (row2) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) M[g] = fma(Cm[2][b], Tm[2][g], M[g]);
+      for (int cp = 0; cp < 3; ++cp) t = fma(coef.cf[((ca * 3 + c) * 3 + cb) * 3 + cp], Cm[cp][g], t);
+      Tm[c][g] = t;
     }
 #pragma unroll
-    for (int g = 0; g < 4; ++g) dst[(size_t)(b * 4 + g) * stride] = M[g];
-  }
+  for (int b = 0; b < 4; ++b)
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      dst[(size_t)(b * 4 + g) * stride] = fma(Cm[2][b], Tm[2][g], fma(Cm[1][b], Tm[1][g], Cm[0][b] * Tm[0][g]));
 }
 
 template <int P, int Q>
