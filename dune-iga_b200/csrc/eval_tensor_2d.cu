@@ -390,7 +390,7 @@ cudaError_t launch_pdl(bool allow, void (*kernel)(KArgs...), unsigned blocks, un
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   const char* env = getenv("IGAB_NO_PDL");
-  const bool pdl = allow && !(env && env[0] == '1');
+  const bool pdl = allow && pdl_allowed() && !(env && env[0] == '1');
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);

@@ -42,6 +42,10 @@ static std::atomic<long long> g_launches{0};
 
 void set_error(const std::string& msg) { g_last_error = msg; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static thread_local int t_no_pdl = 0;
+NoPdlScope::NoPdlScope() { ++t_no_pdl; }
+NoPdlScope::~NoPdlScope() { --t_no_pdl; }
+bool pdl_allowed() { return t_no_pdl == 0; }
 igab_status cuda_fail(cudaError_t e, const char* what) {
   g_last_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
   return e == cudaErrorMemoryAllocation ? IGAB_OUT_OF_MEMORY : IGAB_CUDA_ERROR;
@@ -886,6 +890,7 @@ static igab_status eval_tensor_impl(igab_patch* p, int64_t elem_begin, int64_t e
 
   // HOST outputs: element chunks through two sets of device buffers; the D2H copy of chunk k overlaps the kernel of
   // chunk k+1 (copy stream + events).  Full PCIe rate needs pinned destination memory (igab_host_alloc).
+  NoPdlScope plain_launches;
   long long nq = 1;
   for (int d = 0; d < p->dev.dim; ++d) nq *= nq1[d];
   long long per_pt[8], bytes_pt = 0;

@@ -77,6 +77,14 @@ igab_status enter_stream(igab_patch* p, cudaStream_t stream);
 void set_error(const std::string& msg);
 igab_status cuda_fail(cudaError_t e, const char* what);
 void count_launch(int n = 1);
+// Programmatic dependent launch (eval_tensor_2d.cu) is for device-resident callers.  The HOST-space entry points recycle
+// staging buffers behind events of a copy stream; their kernels are launched plainly (PCIe bounds them anyway), so that
+// nothing rests on how a programmatic edge combines with an event wait in front of the kernel.
+struct NoPdlScope {
+  NoPdlScope();
+  ~NoPdlScope();
+};
+bool pdl_allowed();
 
 // Per (kernel, device) launch configuration: raises the dynamic shared-memory limit once and caches the SM count and the
 // resident blocks per SM.  Thread-safe (handles may be driven from different host threads) and correct when a process
