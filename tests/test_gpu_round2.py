@@ -449,6 +449,67 @@ def test_symmetric_assembly_kernel_matches_oracle_and_the_full_kernel(p, q, kind
         assert relerr(out["1"][1][e].reshape(1, -1), fr.reshape(1, -1)) <= TOL
 
 
+def test_programmatic_dependent_launches_keep_the_stream_order():
+    """The 2-D evaluation kernels are launched with the programmatic-stream-serialization attribute (the next launch is
+    resident while the current one drains and waits only before its first store).  What must still hold on one stream:
+    launches queued back to back into the SAME outputs leave the last launch's values; a control-net update between two
+    launches is seen by the second one; a rule switch (tables rebuilt: plain launch) right behind a launch is correct;
+    point lists produced on the stream just before the call are read after they are complete.  Compared with the same
+    calls made one by one with a synchronisation after each (IGAB_NO_PDL=1 for the reference values)."""
+    import os
+    import torch
+    spec = PFT.small_patch("plate_hole_p2", level=4)
+    pd = spec["patch"]
+    cpA = np.ascontiguousarray(pd.cp)
+    cpB = PD.perturbed(pd, seed=11, amp=0.02).cp
+    fields = ("N", "dN", "x", "Jt", "detJ")
+    x3, x4 = PD.gaussLegendre01(3)[0], PD.gaussLegendre01(4)[0]
+
+    ref = {}
+    os.environ["IGAB_NO_PDL"] = "1"
+    try:
+        for key, cp, xi in (("A3", cpA, x3), ("B3", cpB, x3), ("B4", cpB, x4)):
+            ref[key] = capi.Patch(pd.degree, pd.knotSpans, cp, pd.dimworld).evalTensor([xi, xi], order=1, want=fields)
+    finally:
+        del os.environ["IGAB_NO_PDL"]
+    P = capi.Patch(pd.degree, pd.knotSpans, cpA, pd.dimworld)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        sh3, sh4 = P.shapes(P.nelem * 9), P.shapes(P.nelem * 16)
+        o3 = {f: torch.full(sh3[f], float("nan"), dtype=torch.float64, device="cuda") for f in fields}
+        o4 = {f: torch.full(sh4[f], float("nan"), dtype=torch.float64, device="cuda") for f in fields}
+        P.evalTensor([x3, x3], order=1, want=fields, out=o3, stream=s.cuda_stream)   # builds the tables (plain launch)
+        for _ in range(8):                                                            # resident rule: dependent launches
+            P.evalTensor([x3, x3], order=1, want=fields, out=o3, stream=s.cuda_stream)
+        P.updateControlPoints(cpB)                                                    # copy between two launches
+        for _ in range(4):
+            P.evalTensor([x3, x3], order=1, want=fields, out=o3, stream=s.cuda_stream)
+        P.evalTensor([x4, x4], order=1, want=fields, out=o4, stream=s.cuda_stream)   # rule switch right behind a launch
+        s.synchronize()
+        for f in fields:
+            assert np.array_equal(o3[f].cpu().numpy(), ref["B3"][f]), f
+            assert np.array_equal(o4[f].cpu().numpy(), ref["B4"][f]), f
+        # point lists written on the stream immediately before the call
+        rng = np.random.default_rng(3)
+        npts = 40000
+        elem = torch.from_numpy(np.sort(rng.integers(0, P.nelem, npts)).astype(np.int32)).cuda()
+        xi_h = rng.random((npts, 2))
+        shl = P.shapes(npts)
+        ol = {f: torch.empty(shl[f], dtype=torch.float64, device="cuda") for f in fields}
+        xi_d = torch.zeros((npts, 2), dtype=torch.float64, device="cuda")
+        src = torch.from_numpy(xi_h).cuda()
+        s.synchronize()
+        P.evalTensor([x3, x3], order=1, want=fields, out=o3, stream=s.cuda_stream)   # a launch that triggers early ...
+        xi_d.copy_(src)                                                               # ... a producer kernel / copy ...
+        xi_d.mul_(1.0)                                                                # (a kernel writing the list)
+        P.evalPoints(elem, xi_d, order=1, want=fields, out=ol, stream=s.cuda_stream)  # ... and the consumer
+        s.synchronize()
+    got = {f: ol[f].cpu().numpy() for f in fields}
+    want = capi.Patch(pd.degree, pd.knotSpans, cpB, pd.dimworld).evalPoints(elem.cpu().numpy(), xi_h, order=1, want=fields)
+    for f in fields:
+        assert np.array_equal(got[f], want[f]), f
+
+
 @pytest.mark.parametrize("p", [3, 4])
 @pytest.mark.parametrize("kind", [capi.ASM_POISSON, capi.ASM_MASS, capi.ASM_ELASTICITY])
 def test_warp_specialised_kernel_bulk_store_epilogue(p, kind, monkeypatch):
