@@ -972,6 +972,8 @@ struct WCfg {
   static constexpr int SZ_TOTAL =
       F::SZ_T + F::SZ_W + S::SZ_CS + S::SZ_X + S::SZ_M + S::SZ_T2 + S::SZ_T1 + S::SZ_B2 + SZ_B3 + SZ_K + F::SZ_T;
   static constexpr bool FITS = SZ_TOTAL * 8 <= 227 * 1024;
+  // registers per thread after the role split (8 + 8 warps x 32 lanes: REG_MMA + REG_HLP = 256 fills the register file)
+  static constexpr int REG_MMA = 168, REG_HLP = 88;
 };
 
 template <int P, int Q, int KIND>
@@ -1061,7 +1063,9 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
   }
 
   IGAB_WPT_BEGIN
-  for (long long el = blockIdx.x; el < nelem; el += gridDim.x) {
+  // The roles never rejoin (each walks the elements in its own loop, the common preparation is a lambda instantiated in
+  // both), so that setmaxnreg can move registers from the helper warps to the DMMA warps for the whole kernel.
+  auto element_common = [&](long long el) {
     const long long e = elem_begin + el;
     __syncthreads();  // the helpers' last stage 1 of the previous element is done with sTw
     if (useW) {
@@ -1119,13 +1123,18 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
     }
     __syncthreads();
     IGAB_WPT(is_mma ? 10 : 11)
+  };
+  if (is_mma) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WC::REG_MMA));
+    for (long long el = blockIdx.x; el < nelem; el += gridDim.x) {
+    element_common(el);
     double* const K = Ke + el * (long long)NROWK * NROWK;
     // 16-byte phase (0 / 1, in doubles) of row `row` of the group (i2, a) of this element in global memory:
     // (kpar + ((row + NP i2) NCP + a) NROWK) & 1 = gpar(i2, a) ^ (row & 1) for odd NROWK, kpar otherwise
     const unsigned kpar = (unsigned)(reinterpret_cast<unsigned long long>(K) >> 3) & 1u;
     auto gpar = [&](int i2, int ca) -> unsigned { return ODDK ? (kpar ^ (unsigned)((NP * i2 * NCP + ca) & 1)) : kpar; };
 
-    if (is_mma) {
+    {
       // ================================ DMMA warps: stage 2, stage 3 ================================================
       double b3[S::K3 / 4][S::NT3];
 #pragma unroll
@@ -1167,24 +1176,28 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
         } else if (has2) {
           const double* arow = T1 + (8 * mt2 + lr) * LDA2 + lc;
           const double* brow = sB2 + lc * LDB2 + 8 * nt2 + lr;
+          // all groups' accumulators first, the T2 stores afterwards: NG x TPW independent DMMA chains interleave (the
+          // DMMA warps run with REG_MMA registers after the role split; with 128 this cost 6 %)
+          double acc[S::NG][S::TPW][2];
 #pragma unroll
-          for (int g = 0; g < S::NG; ++g) {  // (all groups before the stores, as in gram_sf_kernel, costs registers here: -6 %)
-            double acc[S::TPW][2];
+          for (int g = 0; g < S::NG; ++g) {
 #pragma unroll
-            for (int s = 0; s < S::TPW; ++s) acc[s][0] = acc[s][1] = 0.0;
+            for (int s = 0; s < S::TPW; ++s) acc[g][s][0] = acc[g][s][1] = 0.0;
             const int kb = S::goff(g), nks = S::r4(S::ncombo(g) * Q) / 4;
 #pragma unroll
             for (int ks = 0; ks < nks; ++ks) {
               const double a = arow[kb + 4 * ks];
 #pragma unroll
-              for (int s = 0; s < S::TPW; ++s) dmma8x8x4_f(acc[s][0], acc[s][1], a, brow[(kb + 4 * ks) * LDB2 + 8 * s]);
+              for (int s = 0; s < S::TPW; ++s) dmma8x8x4_f(acc[g][s][0], acc[g][s][1], a, brow[(kb + 4 * ks) * LDB2 + 8 * s]);
             }
+          }
+#pragma unroll
+          for (int g = 0; g < S::NG; ++g)
 #pragma unroll
             for (int s = 0; s < S::TPW; ++s)
 #pragma unroll
               for (int h = 0; h < 2; ++h)
-                if (t2off[s][h] >= 0) T2[t2off[s][h] + g * Q] = acc[s][h];
-          }
+                if (t2off[s][h] >= 0) T2[t2off[s][h] + g * Q] = acc[g][s][h];
         }
         IGAB_WPT(1)
         if (k + 2 < NPASS) nb_arrive(BAR_T1_FREE + (k & 1), NT);  // buffer consumed: the helpers may write pass k+2 into it
@@ -1256,7 +1269,19 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
         __syncwarp();
         if (fe) nb_arrive(BAR_K_FULL, NT);  // stage 2 of the last pass has read T1: the helpers' load vector may use it
       }
-    } else {
+    }
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WC::REG_HLP));
+    for (long long el = blockIdx.x; el < nelem; el += gridDim.x) {
+    element_common(el);
+    double* const K = Ke + el * (long long)NROWK * NROWK;
+    // 16-byte phase (0 / 1, in doubles) of row `row` of the group (i2, a) of this element in global memory:
+    // (kpar + ((row + NP i2) NCP + a) NROWK) & 1 = gpar(i2, a) ^ (row & 1) for odd NROWK, kpar otherwise
+    const unsigned kpar = (unsigned)(reinterpret_cast<unsigned long long>(K) >> 3) & 1u;
+    auto gpar = [&](int i2, int ca) -> unsigned { return ODDK ? (kpar ^ (unsigned)((NP * i2 * NCP + ca) & 1)) : kpar; };
+
+    {
       // ================================ helper warps: stage 1, epilogue ============================================
       auto point_matrices = [&](int ca, int cb) {  // elasticity: M4 = C^T Cf[a][.][b][.] C per point
         if constexpr (ELAS) {
@@ -1390,6 +1415,7 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
             fe[el * NB + i] = f;
         }
       }
+    }
     }
   }
 }
