@@ -156,3 +156,17 @@ def test_partition_weighted_balances_cumulative_point_counts():
     assert capi.partitionWeighted(np.zeros(10, np.int64), 2) == [0, 0, 10]
     with pytest.raises(Exception):
         capi.partitionWeighted(np.array([1, -1], np.int64), 2)
+
+
+def test_register_budget_of_the_role_split_kernel():
+    """gram_ws_kernel moves registers from its helper warps to its DMMA warps (setmaxnreg); ptxas reports only the launch-time
+    count, so the SASS is checked: nothing a helper warp can reach names a register outside the helpers' budget, nothing at
+    all one outside the DMMA warps' (tools/ws_regs_check.py)."""
+    import shutil
+    import subprocess
+    import sys
+    obj = os.path.join(ROOT, "dune-iga_b200", "csrc", "_build", "assemble_fused.o")
+    if not (shutil.which("cuobjdump") and os.path.exists(obj)):
+        pytest.skip("needs cuobjdump and the built object file")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ws_regs_check.py"), obj], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.count("ok") >= 6, r.stdout + r.stderr
