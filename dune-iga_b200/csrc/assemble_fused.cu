@@ -1152,8 +1152,8 @@ __global__ void __launch_bounds__(512, 1) gram_ws_kernel(
         const unsigned gp = gpar((k / NCP) % NB1, k / (NCP * NB1));
         double* const T2 = sT2;
         const double* const T1 = (k & 1) ? sT1b : sT1;
-        // every DMMA warp has left stage 3 of the previous pass: T2 may be rewritten (the bulk path has just met there)
-        if (k > 0 && !(useB && cb == 0)) nb_sync(BAR_MMA2, NTM);
+        // T2 may be rewritten once every DMMA warp has left stage 3 of the previous pass: the FULL barrier below completes
+        // only when all of them (and the helpers' arrivals) are in, so it orders that as well -- no barrier of its own
         nb_sync(BAR_T1_FULL + (k & 1), NT);
         IGAB_WPT(0)
         // ---- stage 2: C_g[(j2,q0)][pi1] = sum_{k in g} T1[.][k] B2[k][.]  ->  T2[j1 + NB1 j2 + NP i1][g Q + q0]
